@@ -1,0 +1,466 @@
+// audio8_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+// Roles inside one 256-thread CTA (one CTA per SM, persistent over output tiles):
+//   warp 0 (one elected lane)  TMA producer: cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
+//   warp 1 (one elected lane)  MMA issuer:   tcgen05.mma (M=128, N=BN, K=16) -> TMEM accumulators
+//   warp 2                     TMEM allocator / deallocator
+//   warps 4..7                 epilogue: tcgen05.ld -> registers -> bias/GELU/residual -> HBM
+// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
+// (MMA <-> epilogue), so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "a8_common.cuh"
+#include "../../include/audio8_b200.h"
+
+namespace a8 {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+enum { MAJOR_K = A8_MAJOR_K, MAJOR_MN = A8_MAJOR_MN };
+enum { OUT_BF16 = A8_OUT_BF16, OUT_F32 = A8_OUT_F32, OUT_F32_ATOMIC = A8_OUT_F32_ATOMIC };
+enum { ACT_NONE = A8_ACT_NONE, ACT_GELU = A8_ACT_GELU };
+enum { AUX_NONE = A8_AUX_NONE, AUX_ADD = A8_AUX_ADD, AUX_MUL_GELU_GRAD = A8_AUX_MUL_GELU_GRAD };
+
+struct OpCoef {
+  int base[4], ck[4], cb[4], cr[4], cl[4], ch[4];
+};
+
+struct KParams {
+  int M, N, m_tiles, n_tiles, lo_count, hi_count;
+  int k_blocks, k_inner, split_k;
+  OpCoef a, b;
+  void* c;
+  int c_dtype;
+  void* z_out;
+  const void* aux;
+  int aux_mode;
+  const float* bias;
+  int bias_stride_lo;
+  int act;
+  float alpha;
+  long long ldc, c_stride_lo, c_stride_hi;
+  int total_tiles;
+};
+
+__device__ __forceinline__ void op_coords(const OpCoef& o, int kin, int kbatch, int r, int lo, int hi,
+                                          int (&c)[4]) {
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    c[d] = o.base[d] + o.ck[d] * kin + o.cb[d] * kbatch + o.cr[d] * r + o.cl[d] * lo + o.ch[d] * hi;
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+};
+
+// UMMA shared-memory matrix descriptor, 128B swizzle (layout type 2), descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+struct TileCoord {
+  int nt, mt, lo, hi, kb_begin, kb_end;
+};
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  t.mt = r % p.m_tiles;
+  r /= p.m_tiles;
+  t.lo = r % p.lo_count;
+  r /= p.lo_count;
+  t.hi = r % p.hi_count;
+  const int split = r / p.hi_count;
+  t.kb_begin = (int)(((long long)split * p.k_blocks) / p.split_k);
+  t.kb_end = (int)(((long long)(split + 1) * p.k_blocks) / p.split_k);
+  return t;
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_group(const KParams& p, const uint32_t* r, long long off,
+                                               int n, int lo) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (p.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + (long long)lo * p.bias_stride_lo + n);
+    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (p.z_out != nullptr) {
+    uint4 z;
+    z.x = pack_bf16(v[0], v[1]); z.y = pack_bf16(v[2], v[3]);
+    z.z = pack_bf16(v[4], v[5]); z.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.z_out) + off) = z;
+  }
+  if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.aux_mode != AUX_NONE) {
+    const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
+    float x[8];
+    float2 t;
+    t = unpack_bf16(a.x); x[0] = t.x; x[1] = t.y;
+    t = unpack_bf16(a.y); x[2] = t.x; x[3] = t.y;
+    t = unpack_bf16(a.z); x[4] = t.x; x[5] = t.y;
+    t = unpack_bf16(a.w); x[6] = t.x; x[7] = t.y;
+    if (p.aux_mode == AUX_ADD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += x[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(x[i]);
+    }
+  }
+  if (p.c_dtype == OUT_BF16) {
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.c) + off) = o;
+  } else if (p.c_dtype == OUT_F32) {
+    float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + off);
+    cp[0] = make_float4(v[0], v[1], v[2], v[3]);
+    cp[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    float* cp = reinterpret_cast<float*>(p.c) + off;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(cp + i, v[i]);
+  }
+}
+
+template <int MA, int MB, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const KParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * C::A_BYTES;
+  const uint32_t bars = sB + STAGES * C::B_BYTES;
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (STAGES + i); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(full_bar(i), 1);
+        mbar_init(empty_bar(i), 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(tfull_bar(i), 1);
+        mbar_init(tempty_bar(i), 128);
+      }
+      mbar_fence_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int m0 = t.mt * BLOCK_M, n0 = t.nt * BN;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          const int kin = kb % p.k_inner;
+          const int kbatch = kb / p.k_inner;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::A_BYTES + C::B_BYTES);
+          const uint32_t a_dst = sA + stage * C::A_BYTES;
+          const uint32_t b_dst = sB + stage * C::B_BYTES;
+          int cc[4];
+          if (MA == MAJOR_K) {
+            op_coords(p.a, kin, kbatch, m0, t.lo, t.hi, cc);
+            tma_load_4d(&map_a, full_bar(stage), a_dst, cc[0], cc[1], cc[2], cc[3]);
+          } else {
+#pragma unroll
+            for (int at = 0; at < BLOCK_M / 64; ++at) {
+              op_coords(p.a, kin, kbatch, m0 / 64 + at, t.lo, t.hi, cc);
+              tma_load_4d(&map_a, full_bar(stage), a_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+            }
+          }
+          if (MB == MAJOR_K) {
+            op_coords(p.b, kin, kbatch, n0, t.lo, t.hi, cc);
+            tma_load_4d(&map_b, full_bar(stage), b_dst, cc[0], cc[1], cc[2], cc[3]);
+          } else {
+#pragma unroll
+            for (int at = 0; at < BN / 64; ++at) {
+              op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
+              tma_load_4d(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MA << 15) |
+                                 ((uint32_t)MB << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BLOCK_M >> 4) << 24);
+      // K-major: 8-row groups are 1024 B apart (SBO), one swizzle span along K (LBO unused).
+      // MN-major: 64-element MN atoms are BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B (SBO).
+      constexpr uint32_t A_LBO = (MA == MAJOR_K) ? 0u : BLOCK_K * 128u;
+      constexpr uint32_t B_LBO = (MB == MAJOR_K) ? 0u : BLOCK_K * 128u;
+      constexpr uint32_t A_KADV = (MA == MAJOR_K) ? UMMA_K * 2u : UMMA_K * 128u;
+      constexpr uint32_t B_KADV = (MB == MAJOR_K) ? UMMA_K * 2u : UMMA_K * 128u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+        const TileCoord t = decode_tile(p, tile);
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = sA + stage * C::A_BYTES;
+          const uint32_t b_addr = sB + stage * C::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * A_KADV, A_LBO, 1024u);
+            const uint64_t db = make_smem_desc(b_addr + k * B_KADV, B_LBO, 1024u);
+            umma_bf16(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == t.kb_end - 1) umma_commit(tfull_bar(as));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+      const TileCoord t = decode_tile(p, tile);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = t.mt * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const long long row_off =
+          (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row * p.ldc;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        const int nb = t.nt * BN + c * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = nb + g * 8;
+            if (n < p.N) epilogue_group<BN>(p, r + g * 8, row_off + n, n, t.lo);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, const a8_operand_t& v, int box0, int box1, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  A8_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  for (int i = 0; i < 4; ++i) {
+    A8_REQUIRE(v.dims[i] >= 1, "gemm %s: dim %d is %lld", what, i, (long long)v.dims[i]);
+    dims[i] = (cuuint64_t)v.dims[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    A8_REQUIRE(v.strides[i] > 0 && v.strides[i] % 8 == 0,
+               "gemm %s: stride %d = %lld elements is not a positive multiple of 8", what, i + 1,
+               (long long)v.strides[i]);
+    strides[i] = (cuuint64_t)v.strides[i] * 2ull;
+  }
+  A8_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15u) == 0, "gemm %s: pointer not 16B aligned", what);
+  cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  A8_REQUIRE(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled(%s) failed with %d: dims=(%lld,%lld,%lld,%lld) "
+             "strides=(%lld,%lld,%lld) box=(%d,%d)",
+             what, (int)r, (long long)v.dims[0], (long long)v.dims[1], (long long)v.dims[2],
+             (long long)v.dims[3], (long long)v.strides[0], (long long)v.strides[1],
+             (long long)v.strides[2], box0, box1);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int MA, int MB, int BN>
+int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<MA, MB, BN>;
+  if (!configured) {
+    A8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, kp);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int MA, int MB>
+int launch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
+              cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_inst<MA, MB, 64>(ma, mb, kp, stream);
+    case 128: return launch_inst<MA, MB, 128>(ma, mb, kp, stream);
+    case 256: return launch_inst<MA, MB, 256>(ma, mb, kp, stream);
+  }
+  set_error("gemm: unsupported block_n %d", bn);
+  return -1;
+}
+
+void copy_coef(OpCoef& o, const a8_operand_t& v) {
+  for (int d = 0; d < 4; ++d) {
+    o.base[d] = v.base[d]; o.ck[d] = v.ck[d]; o.cb[d] = v.cb[d];
+    o.cr[d] = v.cr[d]; o.cl[d] = v.cl[d]; o.ch[d] = v.ch[d];
+  }
+}
+
+}  // namespace
+}  // namespace a8
+
+using namespace a8;
+
+extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
+  A8_REQUIRE(gp != nullptr, "gemm: null descriptor");
+  const a8_gemm_t& g = *gp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(g.M > 0 && g.N > 0 && g.k_blocks > 0, "gemm: empty problem M=%d N=%d kb=%d", g.M, g.N,
+             g.k_blocks);
+  A8_REQUIRE(g.ldc % 8 == 0 && g.c_stride_lo % 8 == 0 && g.c_stride_hi % 8 == 0,
+             "gemm: output strides must be multiples of 8 elements");
+  A8_REQUIRE(g.c != nullptr && (reinterpret_cast<uintptr_t>(g.c) & 15u) == 0, "gemm: C null or not 16B aligned");
+  A8_REQUIRE(g.bias == nullptr || g.N % 8 == 0, "gemm: bias needs N %% 8 == 0");
+  A8_REQUIRE(g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0, "gemm: bias not 16B aligned");
+  A8_REQUIRE(!(g.a.major == MAJOR_MN && g.b.major == MAJOR_K), "gemm: (MN,K) majors not instantiated");
+  A8_REQUIRE(g.c_dtype >= OUT_BF16 && g.c_dtype <= OUT_F32_ATOMIC, "gemm: bad c_dtype %d", g.c_dtype);
+  int bn = g.block_n;
+  if (bn == 0) bn = (g.N <= 64) ? 64 : ((g.N <= 128) ? 128 : 256);
+  const int split = g.split_k > 1 ? g.split_k : 1;
+  A8_REQUIRE(split <= g.k_blocks, "gemm: split_k %d > k_blocks %d", split, g.k_blocks);
+  A8_REQUIRE(split == 1 || g.c_dtype == OUT_F32_ATOMIC, "gemm: split_k needs atomic fp32 output");
+  A8_REQUIRE(g.k_inner > 0, "gemm: k_inner must be positive");
+
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = g.M; kp.N = g.N;
+  kp.m_tiles = cdiv(g.M, BLOCK_M);
+  kp.n_tiles = cdiv(g.N, bn);
+  kp.lo_count = g.lo_count > 0 ? g.lo_count : 1;
+  kp.hi_count = g.hi_count > 0 ? g.hi_count : 1;
+  kp.k_blocks = g.k_blocks; kp.k_inner = g.k_inner; kp.split_k = split;
+  copy_coef(kp.a, g.a);
+  copy_coef(kp.b, g.b);
+  kp.c = g.c; kp.c_dtype = g.c_dtype; kp.z_out = g.z_out; kp.aux = g.aux; kp.aux_mode = g.aux_mode;
+  kp.bias = g.bias; kp.bias_stride_lo = g.bias_stride_lo; kp.act = g.act; kp.alpha = g.alpha;
+  kp.ldc = g.ldc; kp.c_stride_lo = g.c_stride_lo; kp.c_stride_hi = g.c_stride_hi;
+  const long long tiles = (long long)kp.m_tiles * kp.n_tiles * kp.lo_count * kp.hi_count * split;
+  A8_REQUIRE(tiles < (1ll << 30), "gemm: too many tiles");
+  kp.total_tiles = (int)tiles;
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (g.a.major == MAJOR_K) rc = make_tmap(&ma, g.a, BLOCK_K, BLOCK_M, "A");
+  else rc = make_tmap(&ma, g.a, 64, BLOCK_K, "A");
+  if (rc) return rc;
+  if (g.b.major == MAJOR_K) rc = make_tmap(&mb, g.b, BLOCK_K, bn, "B");
+  else rc = make_tmap(&mb, g.b, 64, BLOCK_K, "B");
+  if (rc) return rc;
+
+  if (g.a.major == MAJOR_K && g.b.major == MAJOR_K) return launch_bn<MAJOR_K, MAJOR_K>(bn, ma, mb, kp, stream);
+  if (g.a.major == MAJOR_K && g.b.major == MAJOR_MN) return launch_bn<MAJOR_K, MAJOR_MN>(bn, ma, mb, kp, stream);
+  return launch_bn<MAJOR_MN, MAJOR_MN>(bn, ma, mb, kp, stream);
+}

@@ -1,0 +1,222 @@
+"""GEMM problem descriptors for every dense contraction on the wav2vec2 training path.
+
+Each builder returns an `ops.GemmSpec` for the tcgen05 GEMM core (include/audio8_b200.h: a8_gemm_t).  All
+activations are bf16, channels-last; nothing is transposed, padded or im2col'ed in memory — conv windows,
+tap shifts, 'same' padding, head and group offsets are expressed through the operands' affine TMA
+coordinates and TMA's zero fill.
+
+Reference call sites replaced (under /root/reference/audio8):
+  linear_*    nn.Linear / eight_mile Dense            wav2vec2.py:932,950,951,762,613-622
+  conv_*      feature-encoder conv layers 1..6        wav2vec2.py:426-428
+  posconv_*   grouped positional conv (k=128, g=16)   wav2vec2.py:600-609,634
+  attn_*      scaled-dot-product attention matmuls    eight_mile SeqScaledDotProductAttention via wav2vec2.py:644
+"""
+from .ops import (ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, MAJOR_K, MAJOR_MN, OUT_BF16, OUT_F32,
+                  OUT_F32_ATOMIC, GemmSpec, Op)
+
+NUM_SMS = 148
+
+
+def cdiv(a, b):
+    return (a + b - 1) // b
+
+
+def _pick_bn(N):
+    return 64 if N <= 64 else (128 if N <= 128 else 256)
+
+
+def _split_k(M, N, k_blocks, batch=1):
+    """split the contraction so that at least ~one wave of CTAs exists (fp32 atomics into a zeroed C)"""
+    tiles = cdiv(M, 128) * cdiv(N, _pick_bn(N)) * batch
+    return max(1, min(k_blocks, NUM_SMS // max(tiles, 1)))
+
+
+# ------------------------------------------------------------------------------------------------ linear
+def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
+    """out[M,N] = act(x[M,K] w[N,K]^T + bias) (+ aux)."""
+    M, K = x.shape
+    N = w.shape[0]
+    a = Op(x, (K, M), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
+    b = Op(w, (K, N), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
+    return GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
+                    aux_mode=aux_mode, bias=bias)
+
+
+def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE):
+    """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | + aux)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
+    b = Op(w, (K, N), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
+    return GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, OUT_BF16, aux=aux, aux_mode=aux_mode)
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N,K] (fp32, zeroed by the caller) += dy[M,N]^T x[M,K]; both operands read MN-major, split-K."""
+    M, N = dy.shape
+    K = x.shape[1]
+    a = Op(dy, (N, M), (N,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
+    b = Op(x, (K, M), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
+    kb = cdiv(M, 64)
+    return GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC, split_k=_split_k(N, K, kb))
+
+
+# ------------------------------------------------------------------------------------------------ conv 1..6
+def conv_fwd(x, wk, y, k, s, z_out=None, act=ACT_GELU):
+    """y[b,t,:] = act( sum_{j,c} x[b, s*t+j, c] wk[:, j*C+c] ).  x [B,Lin,C], wk [Cout, k*C], y [B,Lout,Cout].
+    The A operand is a tensor map with OVERLAPPING rows (row pitch s*C, row length k*C): zero-copy im2col."""
+    B, Lin, Cin = x.shape
+    _, Lout, Cout = y.shape
+    a = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, 0, 1, 0))
+    b = Op(wk, (k * Cin, Cout), (k * Cin,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
+    return GemmSpec(a, b, Lout, Cout, k * Cin // 64, y, Cout, OUT_BF16, lo_count=B, c_stride_lo=Lout * Cout,
+                    act=act, z_out=z_out)
+
+
+def conv_dgrad_taps(k, s, p):
+    """taps j with j % s == p, ascending; tap number i has time shift i (t = u - i for output l = s*u + p)"""
+    return [j for j in range(k) if j % s == p]
+
+
+def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
+    """dx[b, s*u+p, :] = sum_{i, co} dz[b, u-i, co] wt_p[:, i*Cout+co]  (* gelu'(aux[b, s*u+p, :])).
+    dz [B,Lout,Cout], wt_p [Cin, ntaps*Cout], dx [B,Lin,Cin]; one launch per phase p of the stride."""
+    B, Lout, Cout = dz.shape
+    _, Lin, Cin = dx.shape
+    ntaps = len(conv_dgrad_taps(k, s, p))
+    U = cdiv(Lin - p, s)
+    a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_K, ck=(64, 0, 0, 0), cb=(0, -1, 0, 0), cr=(0, 1, 0, 0),
+           cl=(0, 0, 1, 0))
+    b = Op(wt_p, (ntaps * Cout, Cin), (ntaps * Cout,), MAJOR_K, ck=(64, 0, 0, 0), cb=(Cout, 0, 0, 0), cr=(0, 1, 0, 0))
+    return GemmSpec(a, b, U, Cin, ntaps * Cout // 64, dx, s * Cin, OUT_BF16, lo_count=B, k_inner=Cout // 64,
+                    c_offset=p * Cin, c_stride_lo=Lin * Cin, aux=aux,
+                    aux_mode=AUX_MUL_GELU_GRAD if aux is not None else AUX_NONE)
+
+
+def conv_wgrad(dz, x, dwk, k, s):
+    """dwk[co, j*C+c] (fp32, zeroed) += sum_{b,t} dz[b,t,co] x[b, s*t+j, c]; contraction over (b,t), split-K."""
+    B, Lout, Cout = dz.shape
+    _, Lin, Cin = x.shape
+    a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
+    b = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
+    ki = cdiv(Lout, 64)
+    return GemmSpec(a, b, Cout, k * Cin, B * ki, dwk, k * Cin, OUT_F32_ATOMIC, k_inner=ki,
+                    split_k=_split_k(Cout, k * Cin, B * ki))
+
+
+# ------------------------------------------------------------------------------------------------ pos conv
+def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
+    """out = x + gelu(conv_same(x) + bias) for the grouped positional conv.  x/out [B,T,D]; wp [D, k*64] packed
+    (row = output channel, column j*64+ci, ci >= D/groups zero).  One k-block per tap: the A tile is 64
+    channels starting at the group's first channel, shifted in time by the tap ('same' padding = TMA zero fill)."""
+    B, T, D = x.shape
+    cg = D // groups
+    a = Op(x, (D, T, B), (D, T * D), MAJOR_K, base=(0, -pad_left, 0, 0), cb=(0, 1, 0, 0), cr=(0, 1, 0, 0),
+           cl=(cg, 0, 0, 0), ch=(0, 0, 1, 0))
+    b = Op(wp, (k * 64, D), (k * 64,), MAJOR_K, cb=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, cg, 0, 0))
+    return GemmSpec(a, b, T, cg, k, out, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
+                    c_stride_lo=cg, c_stride_hi=T * D, act=ACT_GELU, z_out=z_out, aux=x, aux_mode=AUX_ADD,
+                    bias=bias, bias_stride_lo=cg)
+
+
+def posconv_dgrad(dz, wpt, dx, groups, k, pad_left, aux=None):
+    """dx[b,t,g*cg+ci] = sum_{j,co} dz[b, t+pad_left-j, g*cg+co] wpt[g*cg+ci, j*64+co]  (+ aux)."""
+    B, T, D = dz.shape
+    cg = D // groups
+    a = Op(dz, (D, T, B), (D, T * D), MAJOR_K, base=(0, pad_left, 0, 0), cb=(0, -1, 0, 0), cr=(0, 1, 0, 0),
+           cl=(cg, 0, 0, 0), ch=(0, 0, 1, 0))
+    b = Op(wpt, (k * 64, D), (k * 64,), MAJOR_K, cb=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, cg, 0, 0))
+    return GemmSpec(a, b, T, cg, k, dx, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
+                    c_stride_lo=cg, c_stride_hi=T * D, aux=aux, aux_mode=AUX_ADD if aux is not None else AUX_NONE)
+
+
+def posconv_wgrad(dz, x, dwp, groups, k, pad_left):
+    """dwp[g][j*64+ci][co] (fp32 [groups, k*64, 64]) = sum_{b,t} x[b, t+j-pad_left, g*cg+ci] dz[b,t,g*cg+co]."""
+    B, T, D = dz.shape
+    cg = D // groups
+    a = Op(x, (D, T, B), (D, T * D), MAJOR_MN, base=(0, -pad_left, 0, 0), ck=(0, 64, 0, 0), cb=(0, 0, 1, 0),
+           cr=(0, 1, 0, 0), cl=(cg, 0, 0, 0))
+    b = Op(dz, (D, T, B), (D, T * D), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cl=(cg, 0, 0, 0))
+    ki = cdiv(T, 64)
+    return GemmSpec(a, b, k * 64, 64, B * ki, dwp, 64, OUT_F32, lo_count=groups, k_inner=ki, block_n=64,
+                    c_stride_lo=k * 64 * 64)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _qkv_op(qkv, which, major, H):
+    """a [T, 64] head slice of the fused projection buffer qkv [B,T,3D]; which = 0 (Q), 1 (K), 2 (V)"""
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    if major == MAJOR_K:  # rows = time, contraction over the 64 head channels
+        return Op(qkv, (D3, T, B), (D3, T * D3), MAJOR_K, base=(which * D, 0, 0, 0), ck=(64, 0, 0, 0),
+                  cr=(0, 1, 0, 0), cl=(64, 0, 0, 0), ch=(0, 0, 1, 0))
+    return Op(qkv, (D3, T, B), (D3, T * D3), MAJOR_MN, base=(which * D, 0, 0, 0), ck=(0, 64, 0, 0),
+              cr=(64, 0, 0, 0), cl=(64, 0, 0, 0), ch=(0, 0, 1, 0))
+
+
+def _ctx_op(ctx, major):
+    """a [T, 64] head slice of a [B,T,D] buffer (attention context or its gradient)"""
+    B, T, D = ctx.shape
+    if major == MAJOR_K:
+        return Op(ctx, (D, T, B), (D, T * D), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(64, 0, 0, 0),
+                  ch=(0, 0, 1, 0))
+    return Op(ctx, (D, T, B), (D, T * D), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0), cl=(64, 0, 0, 0),
+              ch=(0, 0, 1, 0))
+
+
+def _score_op(p, major):
+    """p [B,H,T,Tp] (Tp = T rounded up to 8): K-major = rows are queries, contraction over keys;
+    MN-major = rows are keys (the contiguous dim), contraction over queries (i.e. p^T)."""
+    B, H, T, Tp = p.shape
+    if major == MAJOR_K:
+        return Op(p, (T, T, H, B), (Tp, T * Tp, H * T * Tp), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0),
+                  cl=(0, 0, 1, 0), ch=(0, 0, 0, 1))
+    return Op(p, (T, T, H, B), (Tp, T * Tp, H * T * Tp), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0),
+              cl=(0, 0, 1, 0), ch=(0, 0, 0, 1))
+
+
+def attn_scores(qkv, s_out, H, scale):
+    """S[b,h] = scale * Q K^T  -> fp32 [B,H,T,Tp]"""
+    B, T, D3 = qkv.shape
+    Tp = s_out.shape[-1]
+    dk = D3 // 3 // H
+    return GemmSpec(_qkv_op(qkv, 0, MAJOR_K, H), _qkv_op(qkv, 1, MAJOR_K, H), T, T, dk // 64, s_out, Tp, OUT_F32,
+                    lo_count=H, hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp, alpha=scale)
+
+
+def attn_context(p, qkv, ctx, H):
+    """ctx[b,:,h*64:(h+1)*64] = P[b,h] V[b,h]   (V read MN-major)"""
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    return GemmSpec(_score_op(p, MAJOR_K), _qkv_op(qkv, 2, MAJOR_MN, H), T, 64, cdiv(T, 64), ctx, D, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D)
+
+
+def attn_dprobs(dctx, qkv, dp_out, H):
+    """dP[b,h] = dctx[b,:,h] V[b,h]^T -> fp32 [B,H,T,Tp]"""
+    B, T, D3 = qkv.shape
+    Tp = dp_out.shape[-1]
+    return GemmSpec(_ctx_op(dctx, MAJOR_K), _qkv_op(qkv, 2, MAJOR_K, H), T, T, 1, dp_out, Tp, OUT_F32, lo_count=H,
+                    hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp)
+
+
+def attn_dq(ds, qkv, dqkv, H, scale):
+    """dQ = scale * dS K -> dqkv[..., 0:D]"""
+    B, T, D3 = qkv.shape
+    return GemmSpec(_score_op(ds, MAJOR_K), _qkv_op(qkv, 1, MAJOR_MN, H), T, 64, cdiv(T, 64), dqkv, D3, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D3, alpha=scale)
+
+
+def attn_dk(ds, qkv, dqkv, H, scale):
+    """dK = scale * dS^T Q -> dqkv[..., D:2D]"""
+    B, T, D3 = qkv.shape
+    return GemmSpec(_score_op(ds, MAJOR_MN), _qkv_op(qkv, 0, MAJOR_MN, H), T, 64, cdiv(T, 64), dqkv, D3, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_offset=D3 // 3, c_stride_lo=64, c_stride_hi=T * D3,
+                    alpha=scale)
+
+
+def attn_dv(p, dctx, dqkv, H):
+    """dV = P^T dctx -> dqkv[..., 2D:3D]"""
+    B, T, D = dctx.shape
+    return GemmSpec(_score_op(p, MAJOR_MN), _ctx_op(dctx, MAJOR_MN), T, 64, cdiv(T, 64), dqkv, 3 * D, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_offset=2 * D, c_stride_lo=64, c_stride_hi=T * 3 * D)

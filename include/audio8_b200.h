@@ -1,0 +1,122 @@
+/* audio8_b200 — C ABI of the B200-native wav2vec2 training hot path (libaudio8_b200.so).
+ *
+ * The reference (mead-ml/audio8) exposes no FFI: its hot path sits behind Python classes in
+ * audio8/wav2vec2.py and audio8/ctc.py whose arithmetic is dispatched by PyTorch to ATen / cuDNN / cuBLAS
+ * kernels.  This header is the boundary a drop-in replacement binds instead: each entry point names the
+ * reference call site (file:line under /root/reference/audio8) whose library kernels it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - no allocation, no synchronisation and no host<->device copies inside: the caller allocates outputs and
+ *     workspaces and keeps them alive until the stream work completes;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns immediately;
+ *   - return value 0 on success, negative on error; a8_last_error() then returns a thread-local message;
+ *   - bf16 tensors are channels-last ([rows, channels], unit stride on channels); fp32 where stated.
+ */
+#ifndef AUDIO8_B200_H
+#define AUDIO8_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A8_ABI_VERSION 1
+
+int a8_version(void);
+const char* a8_last_error(void);
+/* number of kernels launched by this library in this process since load (bench.py reports the delta) */
+int64_t a8_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM / TMA GEMM core.
+ * Replaces: every nn.Linear / Dense (`wav2vec2.py:932,950,951,762`, eight_mile Dense inside
+ * TransformerEncoderStack `wav2vec2.py:613-622`), conv layers 1-6 of the feature encoder as implicit GEMM
+ * (`wav2vec2.py:426-428`), the grouped positional conv (`wav2vec2.py:600-609,634`), the attention
+ * score/context products (eight_mile SeqScaledDotProductAttention via `wav2vec2.py:644`), and all of their
+ * data-gradient / weight-gradient products in backward.
+ *
+ *   C[hi][lo][m][n] = epilogue( alpha * sum_k A(hi,lo)[m][k] * B(hi,lo)[n][k] )
+ *
+ * Operands are bf16 tensors described as 4-D strided views (dims[0] has unit stride); a tile of an operand is
+ * fetched by TMA at coordinates that are affine in the loop indices, so convolution windows, time shifts,
+ * head/group offsets and batch indices need no materialised im2col:
+ *   coord[d] = base[d] + ck[d]*kin + cb[d]*kbatch + cr[d]*r + cl[d]*lo + ch[d]*hi
+ * with k-block index kb in [0,k_blocks), kin = kb % k_inner, kbatch = kb / k_inner, and
+ *   major == A8_MAJOR_K : one box {64 k-elements, 128 (A) or block_n (B) rows} per k-block, r = first row (m0 / n0)
+ *   major == A8_MAJOR_MN: boxes {64 mn-elements, 64 k-rows}, one per 64 rows of the tile, r = (row0/64 + i)
+ * Out-of-range coordinates read as zero (TMA fill), which implements 'same' padding and ragged edges.
+ * ---------------------------------------------------------------------------------------------- */
+enum { A8_MAJOR_K = 0, A8_MAJOR_MN = 1 };
+enum { A8_OUT_BF16 = 0, A8_OUT_F32 = 1, A8_OUT_F32_ATOMIC = 2 };
+enum { A8_ACT_NONE = 0, A8_ACT_GELU = 1 };
+enum { A8_AUX_NONE = 0, A8_AUX_ADD = 1, A8_AUX_MUL_GELU_GRAD = 2 };
+
+typedef struct {
+  const void* ptr;    /* bf16 */
+  int64_t dims[4];    /* extents in elements; dims[0] is contiguous */
+  int64_t strides[3]; /* element strides of dims 1..3 (positive multiples of 8) */
+  int32_t major;      /* A8_MAJOR_* */
+  int32_t base[4], ck[4], cb[4], cr[4], cl[4], ch[4];
+} a8_operand_t;
+
+typedef struct {
+  a8_operand_t a, b;
+  int32_t M, N;               /* valid rows / columns of each (hi, lo) output block */
+  int32_t lo_count, hi_count; /* >= 1 */
+  int32_t k_blocks, k_inner;  /* 64-wide k-blocks per output tile; k-blocks per k-batch */
+  int32_t split_k;            /* > 1 requires A8_OUT_F32_ATOMIC into a zeroed C */
+  int32_t block_n;            /* 0 = choose, else 64 / 128 / 256 */
+  void* c;                    /* output; element offset = hi*c_stride_hi + lo*c_stride_lo + m*ldc + n */
+  int32_t c_dtype;            /* A8_OUT_* */
+  int32_t act;                /* A8_ACT_* applied after bias */
+  int64_t ldc, c_stride_lo, c_stride_hi; /* multiples of 8 elements; rows are padded to 8 columns */
+  void* z_out;                /* optional bf16 copy of (alpha*acc + bias) before the activation, addressed like C */
+  const void* aux;            /* optional bf16 tensor addressed like C */
+  int32_t aux_mode;           /* A8_AUX_ADD: out = act(..) + aux;  A8_AUX_MUL_GELU_GRAD: out = (..) * gelu'(aux) */
+  int32_t bias_stride_lo;
+  const float* bias;          /* optional fp32, index lo*bias_stride_lo + n */
+  float alpha;
+  int32_t reserved;
+} a8_gemm_t;
+
+int a8_gemm(const a8_gemm_t* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC loss.  Replaces `torch.nn.functional.ctc_loss` as called at `ctc.py:197-205`
+ * (ATen ctc_loss_log_alpha / log_beta / collect kernels; cuDNN disabled by the reference).
+ * log_probs: fp32 [T,B,V] with arbitrary element strides (the reference passes a transposed view,
+ * `train.py:39`).  targets: int32 concatenated labels (ctc.py:193-194 stripping is done by the caller),
+ * tgt_offsets[b] = start of utterance b.  alpha/beta: fp32 scratch [B, T, 2*max_S+1].
+ * a8_ctc_forward fills alpha, beta (log2 domain, row pitch 32*ceil4((2*max_S+1)/32)), nll[b] (+inf if
+ * infeasible) and, if loss != NULL, the reduced loss: sum_b nll_b, or mean_b(nll_b / max(S_b,1)) when
+ * reduction_mean; infinite rows count as 0 when zero_infinity.
+ * a8_ctc_backward writes grad[T,B,V] (contiguous) = (exp(lp) - occupancy) * scale_b for t < len, else 0
+ * (PyTorch's convention), scale_b = grad_out[b*grad_out_stride] (/ (max(S_b,1)*B) when
+ * reduction_mean); infeasible rows get 0.
+ * ---------------------------------------------------------------------------------------------- */
+size_t a8_ctc_scratch_floats(int32_t T, int32_t B, int32_t max_S);
+/* ctc.py:193-194 on the device, sync-free: flat[] = row-major compaction of targets[B,S] (int64, strided)
+ * without PAD/EOS; tgt_offsets = exclusive cumsum(target_lengths); lengths converted to int32.
+ * flat has room for B*S entries, row_start is B ints of scratch. */
+int a8_ctc_prep(const int64_t* targets, int64_t stride_b, int64_t stride_s, int32_t B, int32_t S, int32_t pad,
+                int32_t eos, const int64_t* target_lengths, const int64_t* input_lengths, int32_t* flat,
+                int32_t* row_start, int32_t* tgt_offsets, int32_t* tgt_lengths, int32_t* in_lengths, void* stream);
+int a8_ctc_forward(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T,
+                   int32_t B, int32_t V, const int32_t* targets, const int32_t* tgt_offsets,
+                   const int32_t* tgt_lengths, const int32_t* in_lengths, int32_t max_S, int32_t blank,
+                   int32_t reduction_mean, int32_t zero_infinity, float* alpha, float* beta, float* nll,
+                   float* loss, void* stream);
+int a8_ctc_backward(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T,
+                    int32_t B, int32_t V, const int32_t* targets, const int32_t* tgt_offsets,
+                    const int32_t* tgt_lengths, const int32_t* in_lengths, int32_t max_S, int32_t blank,
+                    const float* alpha, const float* beta, const float* nll, const float* grad_out,
+                    int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity, float* grad,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIO8_B200_H */

@@ -1,0 +1,86 @@
+"""CTC loss: oracle pinned on CPU against the fixtures generated from the unmodified reference; the CUDA kernels
+checked on the GPU against the oracle (installed torch F.ctc_loss on CPU — the function the reference calls)
+and against the same fixtures.  Tolerances (fp32 kernels): loss rtol 2e-5; gradients (occupancy probabilities
+in [0,1]) atol 5e-5 + 2e-5*sqrt(T): alpha/beta are fp32 log-space values of magnitude ~|nll| (hundreds), so
+each of the T recursion steps rounds at ~1.5e-5 and the error random-walks — the same holds for ATen's own
+fp32 CPU/CUDA kernels against each other."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_ctc
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ctc_cases.npz"))
+CASES = ["small", "rep", "infeasible", "mid"]
+
+
+def _case(name):
+    return (torch.from_numpy(GOLD[f"{name}_lp"]), torch.from_numpy(GOLD[f"{name}_targets"]),
+            torch.from_numpy(GOLD[f"{name}_il"]), torch.from_numpy(GOLD[f"{name}_tl"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("red", ["sum", "mean"])
+def test_oracle_matches_reference_fixture(name, red):
+    lp, tg, il, tl = _case(name)
+    lp = lp.clone().requires_grad_(True)
+    loss = ref_ctc.ctc_loss_reference(lp, il, tg, tl, 0, 1, 2, red)
+    loss.backward()
+    assert abs(loss.item() - GOLD[f"{name}_{red}_loss"][0]) <= 1e-5 * max(1, abs(loss.item()))
+    np.testing.assert_allclose(lp.grad.numpy(), GOLD[f"{name}_{red}_grad"], atol=1e-6)
+
+
+def test_numpy_restatement_matches_torch():
+    lp, tg, il, tl = _case("rep")
+    labels = [tg[b, : tl[b]].numpy() for b in range(tg.shape[0])]
+    nll, grad = ref_ctc.ctc_numpy(lp.double().numpy(), il.numpy(), labels, 0)
+    assert abs(nll.sum() - GOLD["rep_sum_loss"][0]) < 1e-4
+    np.testing.assert_allclose(grad, GOLD["rep_sum_grad"], atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("red", ["sum", "mean"])
+def test_cuda_ctc_matches_fixture(name, red):
+    from audio8_b200.ctc import ctc_loss
+    lp, tg, il, tl = _case(name)
+    lpd = lp.cuda().requires_grad_(True)
+    loss = ctc_loss(lpd, il.cuda(), tg.cuda(), tl, blank=0, pad=1, eos=2, reduction=red)
+    loss.backward()
+    want = GOLD[f"{name}_{red}_loss"][0]
+    assert abs(loss.item() - want) <= 2e-5 * max(1.0, abs(want)), (loss.item(), want)
+    np.testing.assert_allclose(lpd.grad.cpu().numpy(), GOLD[f"{name}_{red}_grad"], rtol=0,
+                               atol=5e-5 + 2e-5 * math.sqrt(lp.shape[0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,B,S,V", [(50, 8, 10, 32), (250, 32, 50, 32), (750, 64, 150, 32), (300, 5, 40, 100),
+                                     (1500, 16, 300, 32), (64, 3, 0, 8)])
+def test_cuda_ctc_matches_oracle_sweep(T, B, S, V):
+    """config-5 sweep shapes; log-probs arrive as the transposed [B,T,V] view the trainer passes (train.py:39)"""
+    from audio8_b200.ctc import ctc_loss
+    g = torch.Generator().manual_seed(T + B)
+    lp_btv = torch.randn(B, T, V, generator=g).log_softmax(-1)
+    tl = torch.randint(max(S // 2, 0), S + 1, (B,), generator=g)
+    il = torch.randint(max(T // 2, 2 * S + 1), T + 1, (B,), generator=g)
+    tg = torch.full((B, S + 1), 1, dtype=torch.long)
+    for b in range(B):
+        tg[b, : tl[b]] = torch.randint(3, V, (int(tl[b]),), generator=g)
+        tg[b, tl[b]] = 2
+    ref_in = lp_btv.transpose(0, 1).clone().requires_grad_(True)
+    ref = ref_ctc.ctc_loss_reference(ref_in, il, tg, tl, 0, 1, 2, "sum")
+    ref.backward()
+    d = lp_btv.cuda().requires_grad_(True)
+    loss = ctc_loss(d.transpose(0, 1), il.cuda(), tg.cuda(), tl, reduction="sum")
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-5 * abs(ref.item()), (loss.item(), ref.item())
+    np.testing.assert_allclose(d.grad.transpose(0, 1).cpu().numpy(), ref_in.grad.numpy(), rtol=0,
+                               atol=5e-5 + 2e-5 * math.sqrt(T))
+    # size-independent properties: zero gradient beyond each utterance's length; rows sum to ~0 (softmax - occupancy)
+    gr = d.grad.cpu()
+    for b in range(B):
+        assert gr[b, il[b]:].abs().max().item() == 0 if il[b] < T else True
+    assert gr.sum(-1).abs().max().item() < 1e-3
