@@ -48,6 +48,32 @@ SIGNATURES = {
     "a8_ctc_backward": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
 }
 
+_U = C.c_uint64
+SIGNATURES.update({
+    "a8_layernorm_fwd": (_I, [_P, _P, _F, _U, _P, _P, _P, _F, _P, _P, _F, _U, _P, _P, _I, _I, _P]),
+    "a8_layernorm_bwd": (_I, [_P, _P, _F, _U, _P, _P, _P, _P, _P, _P, _F, _U, _P, _P, _P, _I, _I, _P]),
+    "a8_softmax_fwd": (_I, [_P, _P, _P, _P, _F, _U, _I, _I, _I, _I, _P]),
+    "a8_softmax_bwd": (_I, [_P, _P, _P, _F, _U, _I, _I, _I, _I, _P]),
+    "a8_colsum": (_I, [_P, _L, _I, _I, _P, _P]),
+    "a8_dropout": (_I, [_P, _P, _I, _L, _F, _U, _P]),
+    "a8_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "a8_log_softmax_fwd": (_I, [_P, _P, _I, _I, _P]),
+    "a8_log_softmax_bwd": (_I, [_P, _L, _L, _L, _I, _P, _P, _I, _I, _P]),
+    "a8_conv0_stats": (_I, [_P, _I, _L, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "a8_conv0_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "a8_conv0_bwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "a8_rows_copy": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "a8_rows_set": (_I, [_P, _P, _I, _I, _P, _P]),
+    "a8_rows_set_bwd": (_I, [_P, _P, _I, _I, _P, _P]),
+    "a8_mask_apply": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "a8_cast": (_I, [_P, _I, _P, _I, _L, _P]),
+    "a8_split3": (_I, [_P, _P, _I, _I, _I, _P]),
+    "a8_vq_fwd": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "a8_vq_bwd": (_I, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_contrastive_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+})
+
 _lib = None
 
 

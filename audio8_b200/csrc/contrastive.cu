@@ -1,0 +1,181 @@
+// audio8_b200 — contrastive loss of wav2vec2 pre-training, fused (reference: wav2vec2.py:377-392).
+//
+// The reference gathers K negatives per masked step into a [K,B,Tm,C] tensor (213 MB at the base config),
+// concatenates, runs cosine_similarity as several kernels and then cross_entropy.  Here one warp owns one
+// masked step: it keeps x_i in registers, walks its K+1 candidate rows of y (L2 resident, 1 KB coalesced
+// reads addressed by the host-generated indices), reduces dot products with shuffles and finishes the
+// log-softmax / cross-entropy in registers.  Nothing but the [R,K+1] probabilities is written.
+#include "a8_common.cuh"
+#include "../../include/audio8_b200.h"
+
+namespace a8 {
+namespace {
+
+constexpr int CPL = 16;           // channels per lane: C <= 512
+constexpr float COS_EPS = 1e-8f;  // torch.cosine_similarity eps
+
+__global__ void __launch_bounds__(256) row_norm_kernel(const float* x, const float* y, int R, int C, float* xn,
+                                                       float* yn) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < 2 * R; i += warps) {
+    const float* p = (i < R ? x + (long long)i * C : y + (long long)(i - R) * C);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += p[c] * p[c];
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float n = fmaxf(sqrtf(s), COS_EPS);
+      if (i < R) xn[i] = n;
+      else yn[i - R] = n;
+    }
+  }
+}
+
+struct ConArgs {
+  const float* x;   // [R,C]
+  const float* y;   // [R,C]
+  const int* idx;   // [R,K] rows of y (negatives)
+  const float* xn;  // [R] clamped norms
+  const float* yn;
+  int R, C, K;
+  float* cosv;      // [R,K+1]
+  float* prob;      // [R,K+1] softmax over candidates
+  float* row_loss;  // [R]
+  // backward
+  const float* dce;  // scalar: d loss / d CE
+  float* dx;         // [R,C]
+  float* dy;         // [R,C] zeroed, atomics
+};
+
+__global__ void __launch_bounds__(256) contrastive_fwd_kernel(const ConArgs a) {
+  extern __shared__ float s_cos[];  // [8 warps][K+1]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  float* cs = s_cos + w * (a.K + 1);
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.R; i += warps) {
+    float xv[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      xv[q] = c < a.C ? a.x[(long long)i * a.C + c] : 0.f;
+    }
+    const float inx = 1.f / a.xn[i];
+    for (int j = 0; j <= a.K; ++j) {
+      const int cand = (j == 0) ? i : a.idx[(long long)i * a.K + j - 1];
+      const float* yr = a.y + (long long)cand * a.C;
+      float dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        if (c < a.C) dot = fmaf(xv[q], yr[c], dot);
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) cs[j] = dot * inx / a.yn[cand];
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j <= a.K; j += 32) mx = fmaxf(mx, cs[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j <= a.K; j += 32) sum += expf(cs[j] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    for (int j = lane; j <= a.K; j += 32) {
+      a.cosv[(long long)i * (a.K + 1) + j] = cs[j];
+      a.prob[(long long)i * (a.K + 1) + j] = expf(cs[j] - lse);
+    }
+    if (lane == 0) a.row_loss[i] = lse - cs[0];
+    __syncwarp();
+  }
+}
+
+// ce = mean_i row_loss;  loss = xe_w * ce + div_w * (n_vars - ppl) / n_vars   (single CTA, deterministic)
+__global__ void __launch_bounds__(1024) contrastive_finalize_kernel(const float* row_loss, int R, const float* ppl,
+                                                                    float n_vars, float xe_w, float div_w,
+                                                                    float* ce, float* loss) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) acc += row_loss[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float c = acc / (float)R;
+    *ce = c;
+    *loss = xe_w * c + (ppl ? div_w * (n_vars - *ppl) / n_vars : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) contrastive_bwd_kernel(const ConArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const float scale = (*a.dce) / (float)a.R;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.R; i += warps) {
+    float xh[CPL], dxv[CPL];
+    const float inx = 1.f / a.xn[i];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      xh[q] = c < a.C ? a.x[(long long)i * a.C + c] * inx : 0.f;
+      dxv[q] = 0.f;
+    }
+    for (int j = 0; j <= a.K; ++j) {
+      const int cand = (j == 0) ? i : a.idx[(long long)i * a.K + j - 1];
+      const float cosj = a.cosv[(long long)i * (a.K + 1) + j];
+      const float dcos = (a.prob[(long long)i * (a.K + 1) + j] - (j == 0 ? 1.f : 0.f)) * scale;
+      const float iny = 1.f / a.yn[cand];
+      const float* yr = a.y + (long long)cand * a.C;
+      float* dyr = a.dy + (long long)cand * a.C;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        if (c < a.C) {
+          const float yh = yr[c] * iny;
+          dxv[q] = fmaf(dcos, yh - cosj * xh[q], dxv[q]);
+          atomicAdd(dyr + c, dcos * (xh[q] - cosj * yh) * iny);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const int c = lane + 32 * q;
+      if (c < a.C) a.dx[(long long)i * a.C + c] = dxv[q] * inx;
+    }
+  }
+}
+
+int con_grid(int R) {
+  int g = cdiv(R, 8);
+  return g < 1 ? 1 : (g > 148 * 4 ? 148 * 4 : g);
+}
+
+}  // namespace
+}  // namespace a8
+
+using namespace a8;
+
+extern "C" int a8_contrastive_fwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
+                                  const float* ppl, float n_vars, float xe_w, float div_w, float* xn, float* yn,
+                                  float* cosv, float* prob, float* row_loss, float* ce, float* loss, void* stream_v) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && C > 0 && C <= 32 * CPL && K >= 0 && K <= 4095, "contrastive: unsupported shape R=%d C=%d K=%d",
+             R, C, K);
+  row_norm_kernel<<<con_grid(2 * R), 256, 0, st>>>(x, y, R, C, xn, yn);
+  int rc = check_launch("row_norm_kernel");
+  if (rc) return rc;
+  ConArgs a{x, y, idx, xn, yn, R, C, K, cosv, prob, row_loss, nullptr, nullptr, nullptr};
+  contrastive_fwd_kernel<<<con_grid(R), 256, 8 * (K + 1) * sizeof(float), st>>>(a);
+  rc = check_launch("contrastive_fwd_kernel");
+  if (rc) return rc;
+  contrastive_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, R, ppl, n_vars, xe_w, div_w, ce, loss);
+  return check_launch("contrastive_finalize_kernel");
+}
+
+extern "C" int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
+                                  const float* xn, const float* yn, const float* cosv, const float* prob,
+                                  const float* dce, float* dx, float* dy, void* stream_v) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && C > 0 && C <= 32 * CPL && K >= 0, "contrastive_bwd: unsupported shape");
+  A8_CUDA(cudaMemsetAsync(dy, 0, sizeof(float) * (size_t)R * C, st));
+  ConArgs a{x, y, idx, xn, yn, R, C, K, const_cast<float*>(cosv), const_cast<float*>(prob), nullptr, dce, dx, dy};
+  contrastive_bwd_kernel<<<con_grid(R), 256, 0, st>>>(a);
+  return check_launch("contrastive_bwd_kernel");
+}

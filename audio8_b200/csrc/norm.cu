@@ -1,0 +1,616 @@
+// audio8_b200 — HBM-bound row kernels: LayerNorm (+residual, +dropout) fwd/bwd, attention softmax fwd/bwd,
+// column sums (bias gradients), element-wise dropout, log-softmax fwd/bwd.
+//
+// Replaces the ATen kernels the reference dispatches for nn.LayerNorm (wav2vec2.py:623,639,904,930 and the
+// ln1/ln2 of every eight_mile TransformerEncoder layer), the residual adds and nn.Dropout around them,
+// softmax / masked_fill / dropout inside eight_mile's SeqScaledDotProductAttention, and F.log_softmax
+// (wav2vec2.py:770).  One warp owns one row; 128-bit accesses; statistics in fp32; no shared-memory staging
+// of rows (each element is read exactly once).
+#include "a8_common.cuh"
+#include "../../include/audio8_b200.h"
+
+namespace a8 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// counter-based dropout mask: Philox-4x32 (7 rounds) -> 8 x 16-bit uniforms per call, one call per group of
+// 8 consecutive elements.  Forward and backward regenerate the same mask from (seed, element group).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox8(unsigned long long seed, unsigned long long group) {
+  uint32_t c0 = (uint32_t)group, c1 = (uint32_t)(group >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+struct DropMask8 {
+  float m[8];
+};
+// keep-scale per element: 0 or 1/(1-p)
+__device__ __forceinline__ DropMask8 drop_mask8(float p, unsigned long long seed, unsigned long long group) {
+  DropMask8 d;
+  if (p <= 0.f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d.m[i] = 1.f;
+    return d;
+  }
+  const uint4 r = philox8(seed, group);
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const float s = 1.f / (1.f - p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    d.m[2 * i] = ((w[i] & 0xFFFFu) >= thr) ? s : 0.f;
+    d.m[2 * i + 1] = ((w[i] >> 16) >= thr) ? s : 0.f;
+  }
+  return d;
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 t;
+  t = unpack_bf16(u.x); v[0] = t.x; v[1] = t.y;
+  t = unpack_bf16(u.y); v[2] = t.x; v[3] = t.y;
+  t = unpack_bf16(u.z); v[4] = t.x; v[5] = t.y;
+  t = unpack_bf16(u.w); v[6] = t.x; v[7] = t.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+  u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8f(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward:  s = x + drop_h(h);  y = drop_y(LN(s) * gamma + beta)
+// ------------------------------------------------------------------------------------------------
+struct LnFwdArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* h;  // nullable
+  float p_h;
+  unsigned long long seed_h;
+  __nv_bfloat16* s_out;  // nullable (required when h != null and backward is wanted)
+  const float* gamma;
+  const float* beta;
+  float eps;
+  __nv_bfloat16* y;
+  float* y_f32;  // nullable
+  float p_y;
+  unsigned long long seed_y;
+  float* mean;
+  float* rstd;
+  int R, C;
+};
+
+template <int NCH>  // chunks of 8 elements per lane: C <= NCH*256
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int C = a.C;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.R; row += warps) {
+    float v[NCH][8];
+    float sum = 0.f;
+    const long long ro = (long long)row * C;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < C) {
+        load8(a.x + ro + c, v[i]);
+        if (a.h != nullptr) {
+          float hv[8];
+          load8(a.h + ro + c, hv);
+          const DropMask8 d = drop_mask8(a.p_h, a.seed_h, (unsigned long long)(ro + c) >> 3);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += hv[j] * d.m[j];
+          // statistics are taken on the bf16-rounded sum, the value backward re-reads
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16(v[i][j]));
+          if (a.s_out != nullptr) store8(a.s_out + ro + c, v[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[i][j];
+      }
+    }
+    const float mu = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mu;
+          sq += d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(sq) / (float)C + a.eps);
+    if (lane == 0) {
+      a.mean[row] = mu;
+      a.rstd[row] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < C) {
+        float g[8], b[8], o[8];
+        load8f(a.gamma + c, g);
+        load8f(a.beta + c, b);
+        const DropMask8 d = drop_mask8(a.p_y, a.seed_y, (unsigned long long)(ro + c) >> 3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = ((v[i][j] - mu) * rs * g[j] + b[j]) * d.m[j];
+        store8(a.y + ro + c, o);
+        if (a.y_f32 != nullptr) store8f(a.y_f32 + ro + c, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  g = drop_y(dy (+ dy_f32));  ds = rstd * (g*gamma - mean(g*gamma) - xhat*mean(g*gamma*xhat))
+// (+ dres: extra gradient arriving directly at s); dh = drop_h(ds); dgamma += g*xhat; dbeta += g; dbias_h += dh
+// ------------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  const __nv_bfloat16* dy;
+  const float* dy_f32;  // nullable, added to dy
+  float p_y;
+  unsigned long long seed_y;
+  const __nv_bfloat16* s;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  __nv_bfloat16* ds;
+  __nv_bfloat16* dh;  // nullable
+  float p_h;
+  unsigned long long seed_h;
+  float* dgamma;   // [C] accumulated (atomics)
+  float* dbeta;    // [C]
+  float* dbias_h;  // nullable [C]
+  int R, C;
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  __shared__ float red[8][NCH * 256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int C = a.C;
+  float acc_g[NCH][8], acc_b[NCH][8], acc_h[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = acc_h[i][j] = 0.f;
+
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.R; row += warps) {
+    const long long ro = (long long)row * C;
+    const float mu = a.mean[row], rs = a.rstd[row];
+    float g[NCH][8], xh[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < C) {
+        float dy[8], sv[8], gm[8];
+        load8(a.dy + ro + c, dy);
+        if (a.dy_f32 != nullptr) {
+          float e[8];
+          load8f(a.dy_f32 + ro + c, e);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dy[j] += e[j];
+        }
+        load8(a.s + ro + c, sv);
+        load8f(a.gamma + c, gm);
+        const DropMask8 d = drop_mask8(a.p_y, a.seed_y, (unsigned long long)(ro + c) >> 3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = dy[j] * d.m[j];
+          xh[i][j] = (sv[j] - mu) * rs;
+          acc_g[i][j] += gg * xh[i][j];
+          acc_b[i][j] += gg;
+          g[i][j] = gg * gm[j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+        store8(a.ds + ro + c, o);
+        if (a.dh != nullptr) {
+          const DropMask8 d = drop_mask8(a.p_h, a.seed_h, (unsigned long long)(ro + c) >> 3);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] *= d.m[j];
+            acc_h[i][j] += o[j];
+          }
+          store8(a.dh + ro + c, o);
+        } else if (a.dbias_h != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc_h[i][j] += o[j];
+        }
+      }
+    }
+  }
+  // block reduction of the column partials, then one atomic per column per CTA
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dbias_h);
+    if (dst == nullptr) continue;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        red[w][c + j] = pass == 0 ? acc_g[i][j] : (pass == 1 ? acc_b[i][j] : acc_h[i][j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][c];
+      atomicAdd(dst + c, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention softmax: P = softmax(S + key_mask) (bf16), optionally P_drop = dropout(P)
+// S fp32 [rows, Tp] (rows = B*H*T), valid columns T; key_keep uint8 [B, T] (0 = padded key -> -1e9)
+// ------------------------------------------------------------------------------------------------
+struct SmFwdArgs {
+  const float* s;
+  const unsigned char* key_keep;  // nullable
+  __nv_bfloat16* p;
+  __nv_bfloat16* p_drop;  // nullable
+  float pdrop;
+  unsigned long long seed;
+  int rows, T, Tp, rows_per_batch;
+};
+
+template <int NV>  // 8-element chunks per lane: Tp <= NV*256
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const SmFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps) {
+    const long long ro = (long long)row * a.Tp;
+    const unsigned char* keep = a.key_keep ? a.key_keep + (long long)(row / a.rows_per_batch) * a.T : nullptr;
+    float v[NV][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < a.Tp) {
+        load8f(a.s + ro + c, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c + j >= a.T) v[i][j] = -INFINITY;
+          else if (keep != nullptr && keep[c + j] == 0) v[i][j] = -1e9f;
+          mx = fmaxf(mx, v[i][j]);
+        }
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < a.Tp) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[i][j] = __expf(v[i][j] - mx);
+          sum += v[i][j];
+        }
+      }
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < a.Tp) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] *= inv;
+        store8(a.p + ro + c, v[i]);
+        if (a.p_drop != nullptr) {
+          const DropMask8 d = drop_mask8(a.pdrop, a.seed, (unsigned long long)(ro + c) >> 3);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] *= d.m[j];
+          store8(a.p_drop + ro + c, v[i]);
+        }
+      }
+    }
+  }
+}
+
+// dS = P * (g - sum(P*g)),  g = dropout-mask * dP   (bf16 out; pad columns written as 0)
+struct SmBwdArgs {
+  const __nv_bfloat16* p;
+  const float* dp;
+  __nv_bfloat16* ds;
+  float pdrop;
+  unsigned long long seed;
+  int rows, T, Tp;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const SmBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps) {
+    const long long ro = (long long)row * a.Tp;
+    float pv[NV][8], g[NV][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < a.Tp) {
+        load8(a.p + ro + c, pv[i]);
+        load8f(a.dp + ro + c, g[i]);
+        const DropMask8 d = drop_mask8(a.pdrop, a.seed, (unsigned long long)(ro + c) >> 3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c + j >= a.T) {
+            pv[i][j] = 0.f;
+            g[i][j] = 0.f;
+          }
+          g[i][j] *= d.m[j];
+          dot += pv[i][j] * g[i][j];
+        }
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < a.Tp) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = pv[i][j] * (g[i][j] - dot);
+        store8(a.ds + ro + c, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sum: out[c] += sum_r x[r][c]   (bf16 [R, ld] -> fp32 atomics; out zeroed by the caller)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* x, long long ld, int R, int C,
+                                                     int rows_per_block, float* out) {
+  // thread = one 8-column chunk (blockIdx.y selects the 2048-column slab), loops over this CTA's rows
+  const int c = (blockIdx.y * 256 + threadIdx.x) * 8;
+  if (c >= C) return;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0; r < r1; ++r) {
+    float v[8];
+    load8(x + (long long)r * ld + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (c + j < C) atomicAdd(out + c + j, acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise dropout on bf16 (n % 8 == 0): out = x * mask/(1-p); the same call is its own backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* x, __nv_bfloat16* out, long long n8,
+                                                      float p, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(x + i * 8, v);
+    const DropMask8 d = drop_mask8(p, seed, (unsigned long long)i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= d.m[j];
+    store8(out + i * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_f32_kernel(const float* x, float* out, long long n8, float p,
+                                                          unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    load8f(x + i * 8, v);
+    const DropMask8 d = drop_mask8(p, seed, (unsigned long long)i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= d.m[j];
+    store8f(out + i * 8, v);
+  }
+}
+
+// dz = dy * gelu'(z)   (bf16, n % 8 == 0)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* z,
+                                                       __nv_bfloat16* dz, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], zz[8];
+    load8(dy + i * 8, g);
+    load8(z + i * 8, zz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= gelu_erf_grad(zz[j]);
+    store8(dz + i * 8, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// log-softmax over a small class dimension: x fp32 [R,V] -> y fp32 [R,V];  backward dx = dy - exp(y)*sum(dy)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* x, float* y, int R, int V) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < R; row += warps) {
+    const float* xr = x + (long long)row * V;
+    float mx = -INFINITY;
+    for (int c = lane; c < V; c += 32) mx = fmaxf(mx, xr[c]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < V; c += 32) sum += expf(xr[c] - mx);
+    const float lse = mx + logf(warp_sum(sum));
+    for (int c = lane; c < V; c += 32) y[(long long)row * V + c] = xr[c] - lse;
+  }
+}
+__global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* dy, long long s_r, long long s_v,
+                                                              const float* y, __nv_bfloat16* dx, int R, int V,
+                                                              int rows_inner, long long s_outer) {
+  // dy is addressed as dy[(row / rows_inner) * s_outer + (row % rows_inner) * s_r + c * s_v] so that the
+  // [T,B,V] gradient CTC returns can be consumed without a transpose copy
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < R; row += warps) {
+    const float* dr = dy + (long long)(row / rows_inner) * s_outer + (long long)(row % rows_inner) * s_r;
+    float sum = 0.f;
+    for (int c = lane; c < V; c += 32) sum += dr[(long long)c * s_v];
+    sum = warp_sum(sum);
+    for (int c = lane; c < V; c += 32)
+      dx[(long long)row * V + c] =
+          __float2bfloat16(dr[(long long)c * s_v] - expf(y[(long long)row * V + c]) * sum);
+  }
+}
+
+int row_grid(int rows) {
+  const int blocks = cdiv(rows, 8);
+  return blocks < 148 * 8 ? (blocks > 0 ? blocks : 1) : 148 * 8;
+}
+
+}  // namespace
+}  // namespace a8
+
+using namespace a8;
+
+extern "C" int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_t seed_h, void* s_out,
+                                const float* gamma, const float* beta, float eps, void* y, float* y_f32, float p_y,
+                                uint64_t seed_y, float* mean, float* rstd, int32_t R, int32_t C, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm: unsupported shape R=%d C=%d", R, C);
+  LnFwdArgs a{(const __nv_bfloat16*)x, (const __nv_bfloat16*)h, p_h, seed_h, (__nv_bfloat16*)s_out, gamma, beta,
+              eps, (__nv_bfloat16*)y, y_f32, p_y, seed_y, mean, rstd, R, C};
+  const int nch = cdiv(C, 256);
+  const int grid = row_grid(R);
+  switch (nch) {
+    case 1: ln_fwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: ln_fwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
+    case 3: ln_fwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
+    default: ln_fwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
+  }
+  return check_launch("ln_fwd_kernel");
+}
+
+extern "C" int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, uint64_t seed_y, const void* s,
+                                const float* mean, const float* rstd, const float* gamma, void* ds, void* dh,
+                                float p_h, uint64_t seed_h, float* dgamma, float* dbeta, float* dbias_h, int32_t R,
+                                int32_t C, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: unsupported shape R=%d C=%d", R, C);
+  LnBwdArgs a{(const __nv_bfloat16*)dy, dy_f32, p_y, seed_y, (const __nv_bfloat16*)s, mean, rstd, gamma,
+              (__nv_bfloat16*)ds, (__nv_bfloat16*)dh, p_h, seed_h, dgamma, dbeta, dbias_h, R, C};
+  const int nch = cdiv(C, 256);
+  int grid = cdiv(R, 8 * 4);  // >= 4 rows per warp so the column partials amortise their atomics
+  grid = grid < 1 ? 1 : (grid > 148 * 2 ? 148 * 2 : grid);
+  switch (nch) {
+    case 1: ln_bwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: ln_bwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
+    case 3: ln_bwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
+    default: ln_bwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
+  }
+  return check_launch("ln_bwd_kernel");
+}
+
+extern "C" int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, void* p_drop, float pdrop,
+                              uint64_t seed, int32_t B, int32_t H, int32_t T, int32_t Tp, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax: bad T=%d Tp=%d", T, Tp);
+  SmFwdArgs a{s, key_keep, (__nv_bfloat16*)p, (__nv_bfloat16*)p_drop, pdrop, seed, B * H * T, T, Tp, H * T};
+  const int nv = cdiv(Tp, 256);
+  const int grid = row_grid(a.rows);
+  if (nv <= 1) softmax_fwd_kernel<1><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 2) softmax_fwd_kernel<2><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 3) softmax_fwd_kernel<3><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 4) softmax_fwd_kernel<4><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 8) softmax_fwd_kernel<8><<<grid, 256, 0, stream>>>(a);
+  else softmax_fwd_kernel<16><<<grid, 256, 0, stream>>>(a);
+  return check_launch("softmax_fwd_kernel");
+}
+
+extern "C" int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pdrop, uint64_t seed, int32_t B,
+                              int32_t H, int32_t T, int32_t Tp, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax_bwd: bad T=%d Tp=%d", T, Tp);
+  SmBwdArgs a{(const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, pdrop, seed, B * H * T, T, Tp};
+  const int nv = cdiv(Tp, 256);
+  const int grid = row_grid(a.rows);
+  if (nv <= 1) softmax_bwd_kernel<1><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 2) softmax_bwd_kernel<2><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 3) softmax_bwd_kernel<3><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 4) softmax_bwd_kernel<4><<<grid, 256, 0, stream>>>(a);
+  else if (nv <= 8) softmax_bwd_kernel<8><<<grid, 256, 0, stream>>>(a);
+  else softmax_bwd_kernel<16><<<grid, 256, 0, stream>>>(a);
+  return check_launch("softmax_bwd_kernel");
+}
+
+extern "C" int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0, "colsum: bad shape R=%d C=%d ld=%lld", R, C, (long long)ld);
+  const int slabs = cdiv(C, 2048);
+  int rpb = cdiv(R, cdiv(148 * 4, slabs));
+  rpb = rpb < 16 ? 16 : rpb;
+  dim3 grid(cdiv(R, rpb), slabs);
+  colsum_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, R, C, rpb, out);
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int a8_dropout(const void* x, void* out, int32_t dtype, int64_t n, float p, uint64_t seed,
+                          void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(n > 0 && n % 8 == 0, "dropout: n=%lld must be a positive multiple of 8", (long long)n);
+  const long long n8 = n / 8;
+  const int grid = (int)(n8 / 256 + 1 > 148 * 8 ? 148 * 8 : n8 / 256 + 1);
+  if (dtype == 0) dropout_f32_kernel<<<grid, 256, 0, stream>>>((const float*)x, (float*)out, n8, p, seed);
+  else dropout_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n8, p, seed);
+  return check_launch("dropout_kernel");
+}
+
+extern "C" int a8_gelu_bwd(const void* dy, const void* z, void* dz, int64_t n, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(n > 0 && n % 8 == 0, "gelu_bwd: n=%lld must be a positive multiple of 8", (long long)n);
+  const long long n8 = n / 8;
+  const int grid = (int)(n8 / 256 + 1 > 148 * 8 ? 148 * 8 : n8 / 256 + 1);
+  gelu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n8);
+  return check_launch("gelu_bwd_kernel");
+}
+
+extern "C" int a8_log_softmax_fwd(const float* x, float* y, int32_t R, int32_t V, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && V > 0, "log_softmax: bad shape");
+  log_softmax_fwd_kernel<<<row_grid(R), 256, 0, stream>>>(x, y, R, V);
+  return check_launch("log_softmax_fwd_kernel");
+}
+
+extern "C" int a8_log_softmax_bwd(const float* dy, int64_t stride_outer, int64_t stride_row, int64_t stride_v,
+                                  int32_t rows_inner, const float* y, void* dx, int32_t R, int32_t V,
+                                  void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(R > 0 && V > 0 && rows_inner > 0, "log_softmax_bwd: bad shape");
+  log_softmax_bwd_kernel<<<row_grid(R), 256, 0, stream>>>(dy, stride_row, stride_v, y, (__nv_bfloat16*)dx, R, V,
+                                                          rows_inner, stride_outer);
+  return check_launch("log_softmax_bwd_kernel");
+}

@@ -39,13 +39,13 @@ class _CTCFunction(torch.autograd.Function):
         tg = targets.to(device=dev, dtype=torch.int64, non_blocking=True)
         flat, off, tl32, il32 = be.ctc_prep(tg, pad, eos, tl, il)
         loss, nll, alpha, beta = be.ctc_forward(lp, flat, off, tl32, il32, max_S, blank, mean, zero_infinity)
-        ctx.save_for_backward(lp, flat, off, tl32, il32, alpha, beta, nll)
+        ctx.saved = (lp, flat, off, tl32, il32, alpha, beta, nll)
         ctx.cfg = (max_S, blank, mean, zero_infinity, log_prob.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        lp, flat, off, tl32, il32, alpha, beta, nll = ctx.saved_tensors
+        lp, flat, off, tl32, il32, alpha, beta, nll = ctx.saved
         max_S, blank, mean, zero_infinity, dtype = ctx.cfg
         grad = ops.backend().ctc_backward(lp, flat, off, tl32, il32, max_S, blank, alpha, beta, nll, grad_out, mean,
                                           zero_infinity)

@@ -1,0 +1,512 @@
+"""autograd Functions of the wav2vec2 training path.
+
+Each Function's forward and backward is a hand-ordered sequence of launches into libaudio8_b200.so (through
+`ops.backend()`); PyTorch only owns the tensors, the streams and the outer autograd graph between these
+few coarse nodes.  Activations are bf16 channels-last, parameters stay fp32 (their bf16 copies are made per
+call), parameter gradients are returned in fp32.
+
+Reference call sites are cited per Function (paths under /root/reference/audio8).
+"""
+import math
+
+import torch
+
+from . import gemm_specs as G
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, OUT_BF16, OUT_F32
+
+BF16, F32 = torch.bfloat16, torch.float32
+_seed_state = [0x9E3779B97F4A7C15]
+
+
+def next_seed():
+    """dropout seeds: drawn from torch's CPU generator so torch.manual_seed() makes runs reproducible"""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def _be():
+    return ops.backend()
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _zeros(shape, dtype, like):
+    return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+def _bf16(t):
+    """bf16 contiguous copy of a tensor through the cast kernel (parameters are fp32 masters)"""
+    t = t.detach()
+    if t.dtype == BF16:
+        return t.contiguous()
+    return _be().cast(t.contiguous().float(), BF16)
+
+
+# =================================================================================================
+# Linear  (nn.Linear / eight_mile Dense: wav2vec2.py:932,950,951,762)
+# =================================================================================================
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_f32):
+        be = _be()
+        shp = x.shape
+        x2 = x.detach().reshape(-1, shp[-1])
+        xb = _bf16(x2)
+        wb = _bf16(weight)
+        N = weight.shape[0]
+        out = _empty((x2.shape[0], N), F32 if out_f32 else BF16, x)
+        be.gemm(G.linear_fwd(xb, wb, out, bias.detach() if bias is not None else None,
+                             c_dtype=OUT_F32 if out_f32 else OUT_BF16))
+        ctx.saved = (xb, wb, x.dtype, shp, bias is not None)
+        return out.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        be = _be()
+        xb, wb, xdtype, shp, has_bias = ctx.saved
+        N, K = wb.shape
+        dyb = _bf16(dy.reshape(-1, N))
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty(xb.shape, xdtype, xb)
+            be.gemm(G.linear_dgrad(dyb, wb, dx, c_dtype=OUT_F32 if xdtype == F32 else OUT_BF16))
+            dx = dx.view(shp)
+        if ctx.needs_input_grad[1]:
+            dw = _zeros((N, K), F32, xb)
+            be.gemm(G.linear_wgrad(dyb, xb, dw))
+        if has_bias and ctx.needs_input_grad[2]:
+            db = be.colsum(dyb)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, out_f32=False):
+    return LinearFn.apply(x, weight, bias, out_f32)
+
+
+# =================================================================================================
+# LayerNorm  (nn.LayerNorm: wav2vec2.py:904,930 / :679,701)
+# =================================================================================================
+class LayerNormFn(torch.autograd.Function):
+    """y = LN(x) in bf16 and, optionally, a second fp32 copy of the same values (for the quantizer branch)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, want_f32):
+        be = _be()
+        xb = _bf16(x)
+        y, yf, s, mean, rstd = be.layernorm_fwd(xb, gamma.detach(), beta.detach(), eps, want_f32=want_f32)
+        ctx.saved = (s, mean, rstd, gamma.detach(), x.dtype)
+        if want_f32:
+            return y, yf
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, dyf=None):
+        be = _be()
+        s, mean, rstd, gamma, xdtype = ctx.saved
+        if dy is None:
+            dy = _zeros(s.shape, BF16, s)
+        ds, _, dg, db, _ = be.layernorm_bwd(_bf16(dy), s, mean, rstd, gamma,
+                                            dy_f32=dyf.contiguous() if dyf is not None else None)
+        return ds.to(xdtype), dg, db, None, None
+
+
+def layer_norm(x, gamma, beta, eps, want_f32=False):
+    return LayerNormFn.apply(x, gamma, beta, eps, want_f32)
+
+
+# =================================================================================================
+# Dropout (nn.Dropout on activations: wav2vec2.py:934-935, 713)
+# =================================================================================================
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.cfg = (p, seed)
+        return _be().dropout(x.detach().contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed = ctx.cfg
+        return _be().dropout(dy.contiguous(), p, seed), None, None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return DropoutFn.apply(x, float(p), next_seed())
+
+
+# =================================================================================================
+# time-mask plumbing (wav2vec2.py:939, 946, 381, 717, 721)
+# =================================================================================================
+class RowsSetFn(torch.autograd.Function):
+    """features[time_mask] = mask_emb   (rows of a [B,T,C] bf16 tensor given flat row indices)"""
+
+    @staticmethod
+    def forward(ctx, x, idx, vec):
+        out = x.detach().clone()
+        _be().rows_set(out.view(-1, out.shape[-1]), idx, vec.detach().float().contiguous())
+        ctx.idx = idx
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = dy.clone().contiguous()
+        dvec = _be().rows_set_bwd(dx.view(-1, dx.shape[-1]), ctx.idx)
+        return dx, None, dvec
+
+
+class RowsGatherFn(torch.autograd.Function):
+    """x[time_mask] as rows: [n, C] gathered from a [B*T, C] view (fp32 or bf16 in, fp32 out)"""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        x2 = x.detach().reshape(-1, x.shape[-1]).contiguous()
+        ctx.cfg = (idx, x.shape, x.dtype)
+        return _be().rows_gather(x2, idx, F32)
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx, shp, dtype = ctx.cfg
+        n_rows = 1
+        for d in shp[:-1]:
+            n_rows *= d
+        dx = _be().rows_scatter(dy.contiguous().float(), idx, n_rows, dtype)
+        return dx.view(shp), None
+
+
+class MaskApplyFn(torch.autograd.Function):
+    """zero padded frames (`x[~pad_mask] = 0`, wav2vec2.py:632) and masked channels (:721); self-adjoint"""
+
+    @staticmethod
+    def forward(ctx, x, row_keep, chan_zero):
+        out = x.detach().clone()
+        _be().mask_apply(out, row_keep, chan_zero)
+        ctx.cfg = (row_keep, chan_zero)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = dy.clone().contiguous()
+        _be().mask_apply(dx, *ctx.cfg)
+        return dx, None, None
+
+
+# =================================================================================================
+# conv feature encoder (wav2vec2.py:399-456)
+# =================================================================================================
+def _conv_pack(w):
+    """[Cout, Cin, k] fp32 -> bf16 [Cout, k*Cin] (contraction index = tap*Cin + channel)"""
+    return _bf16(w.detach().permute(0, 2, 1).reshape(w.shape[0], -1))
+
+
+def _conv_pack_t(w, s, p):
+    """[Cout, Cin, k] -> bf16 [Cin, ntaps*Cout] for the phase-p data-gradient GEMM"""
+    taps = G.conv_dgrad_taps(w.shape[2], s, p)
+    return _bf16(torch.cat([w.detach()[:, :, j].t() for j in taps], 1))
+
+
+class ConvFeatureFn(torch.autograd.Function):
+    """x fp32 [B,L] -> bf16 [B,T,C] channels-last.  Layer 0 = fused conv+GroupNorm+GELU kernels (csrc/conv0.cu),
+    layers 1.. = implicit-GEMM tcgen05 convs with GELU epilogues (zero-copy im2col through overlapping TMA rows)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, gn_w, gn_b, *weights):
+        be = _be()
+        x = x.detach().contiguous().float()
+        (c0, k0, s0) = spec[0]
+        w0 = weights[0].detach().reshape(c0, k0).contiguous()
+        gw, gb = gn_w.detach(), gn_b.detach()
+        mean, rstd = be.conv0_stats(x, w0, k0, s0, 1e-5)
+        a = be.conv0_fwd(x, w0, gw, gb, mean, rstd, k0, s0)
+        acts, zs = [a], [None]
+        for i in range(1, len(spec)):
+            (c, k, s) = spec[i]
+            B, Lin, Cin = a.shape
+            Lout = (Lin - k) // s + 1
+            y = _empty((B, Lout, c), BF16, a)
+            z = _empty((B, Lout, c), BF16, a) if any(ctx.needs_input_grad) else None
+            be.gemm(G.conv_fwd(a, _conv_pack(weights[i]), y, k, s, z_out=z))
+            acts.append(y)
+            zs.append(z)
+            a = y
+        ctx.saved = (x, w0, gw, gb, mean, rstd, acts, zs, [w.detach() for w in weights], spec)
+        return a
+
+    @staticmethod
+    def backward(ctx, dy):
+        be = _be()
+        x, w0, gw, gb, mean, rstd, acts, zs, weights, spec = ctx.saved
+        n = len(spec)
+        grads = [None] * n
+        if n > 1:
+            dz = be.gelu_bwd(_bf16(dy), zs[n - 1])
+            for i in range(n - 1, 0, -1):
+                (c, k, s) = spec[i]
+                a_prev = acts[i - 1]
+                dwk = _zeros((c, k * a_prev.shape[2]), F32, a_prev)
+                be.gemm(G.conv_wgrad(dz, a_prev, dwk, k, s))
+                grads[i] = dwk.view(c, k, a_prev.shape[2]).permute(0, 2, 1)
+                dprev = _empty(a_prev.shape, BF16, a_prev)
+                for p in range(s):
+                    be.gemm(G.conv_dgrad(dz, _conv_pack_t(weights[i], s, p), dprev, k, s, p,
+                                         aux=zs[i - 1] if i > 1 else None))
+                dz = dprev  # for i == 1 this is dL/d(a0), the gradient w.r.t. layer 0's GELU output
+            da0 = dz
+        else:
+            da0 = _bf16(dy)
+        (c0, k0, s0) = spec[0]
+        dw0, dg, db = be.conv0_bwd(x, w0, gw, gb, mean, rstd, k0, s0, da0)
+        grads[0] = dw0.view(c0, 1, k0)
+        return (None, None, dg, db, *grads)
+
+
+# =================================================================================================
+# transformer encoder with positional conv (wav2vec2.py:579-646 + eight_mile TransformerEncoderStack)
+# =================================================================================================
+def _posconv_pack(w, groups, transpose):
+    """w [D, cg, k] fp32 -> bf16 [D, k*64]: row = output (input if transpose) channel, column = tap*64 + channel
+    of the same group, zero padded from cg to 64"""
+    D, cg, k = w.shape
+    wg = w.detach().view(groups, cg, cg, k)
+    if transpose:
+        wg = wg.permute(0, 2, 1, 3)
+    out = torch.zeros(groups, cg, k, 64, dtype=F32, device=w.device)
+    out[..., :cg] = wg.permute(0, 1, 3, 2)
+    return _bf16(out.reshape(D, k * 64))
+
+
+class EncoderFn(torch.autograd.Function):
+    """AudioTransformerEncoder.extract_features:  x (+pad zeroing) -> x + gelu(pos_conv(x)) -> LN -> dropout ->
+    num_layers x post-LN transformer layer.  Per layer the parameters arrive as
+    (w_qkv [3D,D], b_qkv, w_o, b_o, ln2_g, ln2_b, w_1 [F,D], b_1, w_2 [D,F], b_2, ln1_g, ln1_b)."""
+
+    N_FRONT = 5  # pos_w, pos_b, ln_g, ln_b + row_keep placeholder handled separately
+    PER_LAYER = 12
+
+    @staticmethod
+    def forward(ctx, x, cfg, row_keep, pos_w, pos_b, ln_g, ln_b, *lw):
+        be = _be()
+        H, groups, pdrop, training, active = cfg["num_heads"], cfg["groups"], cfg["pdrop"], cfg["training"], cfg["active"]
+        p = pdrop if training else 0.0
+        x = _bf16(x)
+        B, T, D = x.shape
+        M = B * T
+        if D % (8 * groups) != 0 or (D // H) % 64 != 0:
+            raise ValueError(f"d_model={D}, heads={H}: this build needs d_model % {8 * groups} == 0 and d_k % 64 == 0")
+        k = pos_w.shape[-1]
+        pad_l = k // 2 - 1 if k % 2 == 0 else k // 2
+        if row_keep is not None:
+            x = x.clone()
+            be.mask_apply(x, row_keep, None)
+        need_grad = any(ctx.needs_input_grad)
+        s0 = _empty(x.shape, BF16, x)
+        z0 = _empty(x.shape, BF16, x)
+        be.gemm(G.posconv_fwd(x, _posconv_pack(pos_w, groups, False), s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
+        seed0 = next_seed() if p > 0 else 0
+        h, _, _, mean0, rstd0 = be.layernorm_fwd(s0, ln_g.detach(), ln_b.detach(), 1e-5, p_y=p, seed_y=seed0)
+        Tp = (T + 7) // 8 * 8
+        scale = 1.0 / math.sqrt(D // H)
+        layers = []
+        for li in range(len(lw) // EncoderFn.PER_LAYER):
+            if not active[li]:
+                layers.append(None)
+                continue
+            (wqkv, bqkv, wo, bo, g2, b2, w1, b1, w2, bb2, g1, b1ln) = (t.detach() for t in
+                                                                      lw[li * 12:(li + 1) * 12])
+            F_ = w1.shape[0]
+            wqkv_b, wo_b, w1_b, w2_b = _bf16(wqkv), _bf16(wo), _bf16(w1), _bf16(w2)
+            xin = h
+            x2d = xin.view(M, D)
+            qkv = _empty((B, T, 3 * D), BF16, x)
+            be.gemm(G.linear_fwd(x2d, wqkv_b, qkv.view(M, 3 * D), bqkv))
+            S = _empty((B, H, T, Tp), F32, x)
+            be.gemm(G.attn_scores(qkv, S, H, scale))
+            seed_a = next_seed() if p > 0 else 0
+            P, Pd = be.softmax_fwd(S, T, row_keep, p, seed_a)
+            del S
+            ctxv = _empty((B, T, D), BF16, x)
+            be.gemm(G.attn_context(Pd if Pd is not None else P, qkv, ctxv, H))
+            a = _empty((M, D), BF16, x)
+            be.gemm(G.linear_fwd(ctxv.view(M, D), wo_b, a, bo))
+            seed1 = next_seed() if p > 0 else 0
+            x1, _, s1, mean2, rstd2 = be.layernorm_fwd(x2d, g2, b2, 1e-6, h=a, p_h=p, seed_h=seed1)
+            z1 = _empty((M, F_), BF16, x)
+            hid = _empty((M, F_), BF16, x)
+            be.gemm(G.linear_fwd(x1, w1_b, hid, b1, act=ACT_GELU, z_out=z1))
+            f = _empty((M, D), BF16, x)
+            be.gemm(G.linear_fwd(hid, w2_b, f, bb2))
+            seed2 = next_seed() if p > 0 else 0
+            x2, _, s2, mean1, rstd1 = be.layernorm_fwd(x1, g1, b1ln, 1e-6, h=f, p_h=p, seed_h=seed2)
+            h = x2.view(B, T, D)
+            if need_grad:
+                layers.append(dict(xin=x2d, qkv=qkv, P=P, Pd=Pd, ctx=ctxv, s1=s1, mean2=mean2, rstd2=rstd2, x1=x1,
+                                   z1=z1, hid=hid, s2=s2, mean1=mean1, rstd1=rstd1, seeds=(seed_a, seed1, seed2),
+                                   w=(wqkv_b, wo_b, w1_b, w2_b), ln=(g2, g1)))
+        if need_grad:
+            ctx.saved = dict(x=x, s0=s0, z0=z0, mean0=mean0, rstd0=rstd0, seed0=seed0, ln_g=ln_g.detach(),
+                             pos_w=pos_w.detach(), layers=layers, row_keep=row_keep, p=p, H=H, groups=groups,
+                             k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw))
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        be = _be()
+        sv = ctx.saved
+        p, H, Tp, scale = sv["p"], sv["H"], sv["Tp"], sv["scale"]
+        x = sv["x"]
+        B, T, D = x.shape
+        M = B * T
+        dcur = _bf16(dh).view(M, D)
+        lgrads = [None] * sv["nlw"]
+        for li in range(len(sv["layers"]) - 1, -1, -1):
+            L = sv["layers"][li]
+            if L is None:
+                continue
+            wqkv_b, wo_b, w1_b, w2_b = L["w"]
+            g2, g1 = L["ln"]
+            seed_a, seed1, seed2 = L["seeds"]
+            F_ = w1_b.shape[0]
+            # ---- ln1( x1 + drop(ffn) )
+            ds2, df, dg1, db1ln, dbias2 = be.layernorm_bwd(dcur, L["s2"], L["mean1"], L["rstd1"], g1, want_dh=p > 0,
+                                                           p_h=p, seed_h=seed2, want_dbias=True)
+            if df is None:
+                df = ds2
+            dw2 = _zeros((D, F_), F32, x)
+            be.gemm(G.linear_wgrad(df, L["hid"], dw2))
+            dz1 = _empty((M, F_), BF16, x)
+            be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL_GELU_GRAD))
+            db1 = be.colsum(dz1)
+            dw1 = _zeros((F_, D), F32, x)
+            be.gemm(G.linear_wgrad(dz1, L["x1"], dw1))
+            dx1 = _empty((M, D), BF16, x)
+            be.gemm(G.linear_dgrad(dz1, w1_b, dx1, aux=ds2, aux_mode=AUX_ADD))
+            # ---- ln2( x + drop(attn) )
+            ds1, da, dg2, db2ln, dbo = be.layernorm_bwd(dx1, L["s1"], L["mean2"], L["rstd2"], g2, want_dh=p > 0,
+                                                        p_h=p, seed_h=seed1, want_dbias=True)
+            if da is None:
+                da = ds1
+            dwo = _zeros((D, D), F32, x)
+            be.gemm(G.linear_wgrad(da, L["ctx"].view(M, D), dwo))
+            dctx = _empty((B, T, D), BF16, x)
+            be.gemm(G.linear_dgrad(da, wo_b, dctx.view(M, D)))
+            dP = _empty((B, H, T, Tp), F32, x)
+            be.gemm(G.attn_dprobs(dctx, L["qkv"], dP, H))
+            dS = be.softmax_bwd(L["P"], dP, T, p, seed_a)
+            del dP
+            dqkv = _empty((B, T, 3 * D), BF16, x)
+            be.gemm(G.attn_dq(dS, L["qkv"], dqkv, H, scale))
+            be.gemm(G.attn_dk(dS, L["qkv"], dqkv, H, scale))
+            be.gemm(G.attn_dv(L["Pd"] if L["Pd"] is not None else L["P"], dctx, dqkv, H))
+            dqkv2 = dqkv.view(M, 3 * D)
+            dbqkv = be.colsum(dqkv2)
+            dwqkv = _zeros((3 * D, D), F32, x)
+            be.gemm(G.linear_wgrad(dqkv2, L["xin"], dwqkv))
+            dxin = _empty((M, D), BF16, x)
+            be.gemm(G.linear_dgrad(dqkv2, wqkv_b, dxin, aux=ds1, aux_mode=AUX_ADD))
+            dcur = dxin
+            lgrads[li * 12:(li + 1) * 12] = [dwqkv, dbqkv, dwo, dbo, dg2, db2ln, dw1, db1, dw2, dbias2, dg1, db1ln]
+            sv["layers"][li] = None  # free this layer's activations
+        # ---- front: LN(+dropout) <- x + gelu(pos_conv(x))
+        ds0, _, dlg, dlb, _ = be.layernorm_bwd(dcur.view(B, T, D), sv["s0"], sv["mean0"], sv["rstd0"], sv["ln_g"],
+                                               p_y=p, seed_y=sv["seed0"])
+        dz0 = be.gelu_bwd(ds0, sv["z0"])
+        dpos_b = be.colsum(dz0)
+        groups, k, pad_l = sv["groups"], sv["k"], sv["pad_l"]
+        cg = D // groups
+        dwp = _empty((groups, k * 64, 64), F32, x)
+        be.gemm(G.posconv_wgrad(dz0, x, dwp, groups, k, pad_l))
+        dpos_w = dwp.view(groups, k, 64, 64)[:, :, :cg, :cg].permute(0, 3, 2, 1).reshape(D, cg, k)
+        dx = _empty((B, T, D), BF16, x)
+        be.gemm(G.posconv_dgrad(dz0, _posconv_pack(sv["pos_w"], groups, True), dx, groups, k, pad_l, aux=ds0))
+        if sv["row_keep"] is not None:
+            be.mask_apply(dx, sv["row_keep"], None)
+        return (dx, None, None, dpos_w, dpos_b, dlg, dlb, *lgrads)
+
+
+# =================================================================================================
+# Gumbel vector quantizer (wav2vec2.py:547-576)
+# =================================================================================================
+class QuantizerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, w, b, vars_, G_, tau, noise):
+        be = _be()
+        Bq, Tm, Cin = y.shape
+        R = Bq * Tm
+        y2 = y.detach().reshape(R, Cin).contiguous().float()
+        w32 = w.detach().contiguous().float()
+        # logits with fp32-accurate products on the tensor cores: bf16x3 split along K (csrc/misc.cu)
+        z = _empty((R, w.shape[0]), F32, y)
+        be.gemm(G.linear_fwd(be.split3(y2, False), be.split3(w32, True), z, b.detach(), c_dtype=OUT_F32))
+        v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
+        q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_)
+        ctx.saved = (y2, w32, v2, z, noise, kidx, avg, ppl, G_, float(tau), y.shape, vars_.shape)
+        ctx.mark_non_differentiable(kidx)
+        return q.view(Bq, Tm, -1), ppl, kidx
+
+    @staticmethod
+    def backward(ctx, dq, dppl, _dk):
+        be = _be()
+        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape = ctx.saved
+        R = y2.shape[0]
+        vd = v2.shape[1]
+        if dq is None:
+            dq = _zeros((R, G_ * vd), F32, y2)
+        dq2 = dq.reshape(R, G_ * vd).contiguous().float()
+        if dppl is None:
+            dppl = _zeros((), F32, y2)
+        a_dot = None
+        if noise is not None:
+            a_dot = _empty((R, v2.shape[0]), F32, y2)
+            be.gemm(G.vq_codebook_dots(_bf16(dq2), _bf16(v2), a_dot, G_))
+        dz, dvars = be.vq_bwd(z, noise, tau, G_, vd, a_dot, dq2, kidx, avg, ppl, dppl.contiguous().float())
+        db = be.colsum(dz)
+        dw = _zeros(w32.shape, F32, y2)
+        be.gemm(G.linear_wgrad(dz, _bf16(y2), dw))
+        dy = _empty(y2.shape, F32, y2)
+        be.gemm(G.linear_dgrad(dz, _bf16(w32), dy, c_dtype=OUT_F32))
+        return dy.view(yshape), dw, db, dvars.view(vshape), None, None, None
+
+
+# =================================================================================================
+# contrastive loss (wav2vec2.py:377-392)
+# =================================================================================================
+class ContrastiveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, idx, ppl, n_vars, xe_w, div_w):
+        be = _be()
+        x2 = x.detach().reshape(-1, x.shape[-1]).contiguous().float()
+        y2 = y.detach().reshape(-1, y.shape[-1]).contiguous().float()
+        loss, ce, saved = be.contrastive_fwd(x2, y2, idx, ppl.detach().float() if ppl is not None else None,
+                                             float(n_vars), float(xe_w), float(div_w))
+        ctx.saved = (x2, y2, idx, saved, x.shape, y.shape, float(n_vars), float(xe_w), float(div_w), ppl is not None)
+        return loss, ce
+
+    @staticmethod
+    def backward(ctx, dloss, dce_extra):
+        be = _be()
+        x2, y2, idx, saved, xs, ys, n_vars, xe_w, div_w, has_ppl = ctx.saved
+        dce = dloss * xe_w
+        if dce_extra is not None:
+            dce = dce + dce_extra
+        dx, dy = be.contrastive_bwd(x2, y2, idx, saved, dce.contiguous().float())
+        dppl = (-div_w / n_vars) * dloss if has_ppl else None
+        return dx.view(xs), dy.view(ys), None, dppl, None, None, None
+
+
+# =================================================================================================
+# log-softmax head (wav2vec2.py:770)
+# =================================================================================================
+class LogSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = _be().log_softmax_fwd(x.detach().contiguous().float())
+        ctx.saved = y
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y = ctx.saved
+        dx = _be().log_softmax_bwd(dy.float(), y)  # strided dy (e.g. CTC's [T,B,V] transposed back) is consumed as is
+        return dx.float()

@@ -42,13 +42,13 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
                     aux_mode=aux_mode, bias=bias)
 
 
-def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE):
+def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | + aux)."""
     M, N = dy.shape
     K = w.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
-    return GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, OUT_BF16, aux=aux, aux_mode=aux_mode)
+    return GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode)
 
 
 def linear_wgrad(dy, x, dw):
@@ -220,3 +220,14 @@ def attn_dv(p, dctx, dqkv, H):
     B, T, D = dctx.shape
     return GemmSpec(_score_op(p, MAJOR_MN), _ctx_op(dctx, MAJOR_MN), T, 64, cdiv(T, 64), dqkv, 3 * D, OUT_BF16,
                     lo_count=H, hi_count=B, block_n=64, c_offset=2 * D, c_stride_lo=64, c_stride_hi=T * 3 * D)
+
+
+# ------------------------------------------------------------------------------------------------ quantizer
+def vq_codebook_dots(dq, vars2d, a_out, G):
+    """a[r, g*V+v] = sum_d dq[r, g*vd+d] vars[g*V+v, d]   (dq bf16 [R,G*vd], vars bf16 [G*V,vd], a fp32 [R,G*V])"""
+    R = dq.shape[0]
+    GV, vd = vars2d.shape
+    V = GV // G
+    a = Op(dq, (G * vd, R), (G * vd,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(vd, 0, 0, 0))
+    b = Op(vars2d, (vd, GV), (vd,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, V, 0, 0))
+    return GemmSpec(a, b, R, V, cdiv(vd, 64), a_out, GV, OUT_F32, lo_count=G, c_stride_lo=V)

@@ -137,6 +137,225 @@ class CudaBackend:
                                             _stream()), "a8_ctc_backward")
         return grad
 
+    # ------------------------------------------------------------------ row kernels
+    def layernorm_fwd(self, x, gamma, beta, eps, h=None, p_h=0.0, seed_h=0, want_f32=False, p_y=0.0, seed_y=0):
+        """returns y (bf16), y_f32 or None, s (bf16: x + drop(h), or x itself when h is None), mean, rstd"""
+        C = x.shape[-1]
+        R = x.numel() // C
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.is_cuda
+        y = torch.empty_like(x)
+        yf = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want_f32 else None
+        s = torch.empty_like(x) if h is not None else x
+        mean = torch.empty(R, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.a8_layernorm_fwd(_ptr(x), _ptr(h), p_h, seed_h, _ptr(s) if h is not None else None,
+                                             _ptr(gamma), _ptr(beta), eps, _ptr(y), _ptr(yf), p_y, seed_y, _ptr(mean),
+                                             _ptr(rstd), R, C, _stream()), "a8_layernorm_fwd")
+        return y, yf, s, mean, rstd
+
+    def layernorm_bwd(self, dy, s, mean, rstd, gamma, dy_f32=None, p_y=0.0, seed_y=0, want_dh=False, p_h=0.0,
+                      seed_h=0, want_dbias=False):
+        """returns ds, dh (or None), dgamma, dbeta, dbias (or None)"""
+        C = s.shape[-1]
+        R = s.numel() // C
+        assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and s.is_contiguous()
+        ds = torch.empty_like(s)
+        dh = torch.empty_like(s) if want_dh else None
+        acc = torch.zeros(3, C, dtype=torch.float32, device=s.device)
+        _lib.check(self.lib.a8_layernorm_bwd(_ptr(dy), _ptr(dy_f32), p_y, seed_y, _ptr(s), _ptr(mean), _ptr(rstd),
+                                             _ptr(gamma), _ptr(ds), _ptr(dh), p_h, seed_h, _ptr(acc[0]), _ptr(acc[1]),
+                                             _ptr(acc[2]) if want_dbias else None, R, C, _stream()),
+                   "a8_layernorm_bwd")
+        return ds, dh, acc[0], acc[1], (acc[2] if want_dbias else None)
+
+    def softmax_fwd(self, s, T, key_keep=None, pdrop=0.0, seed=0):
+        B, H, _, Tp = s.shape
+        p = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+        pd = torch.empty_like(p) if pdrop > 0 else None
+        _lib.check(self.lib.a8_softmax_fwd(_ptr(s), _ptr(key_keep), _ptr(p), _ptr(pd), pdrop, seed, B, H, T, Tp,
+                                           _stream()), "a8_softmax_fwd")
+        return p, pd
+
+    def softmax_bwd(self, p, dp, T, pdrop=0.0, seed=0):
+        B, H, _, Tp = p.shape
+        ds = torch.empty_like(p)
+        _lib.check(self.lib.a8_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), pdrop, seed, B, H, T, Tp, _stream()),
+                   "a8_softmax_bwd")
+        return ds
+
+    def colsum(self, x):
+        C = x.shape[-1]
+        R = x.numel() // C
+        assert x.dtype == torch.bfloat16 and x.is_contiguous()
+        out = torch.zeros(C, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.a8_colsum(_ptr(x), C, R, C, _ptr(out), _stream()), "a8_colsum")
+        return out
+
+    def dropout(self, x, p, seed):
+        assert x.is_contiguous()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.a8_dropout(_ptr(x), _ptr(out), self._dt(x.dtype), x.numel(), p, seed, _stream()),
+                   "a8_dropout")
+        return out
+
+    def gelu_bwd(self, dy, z):
+        assert dy.dtype == torch.bfloat16 and z.dtype == torch.bfloat16 and dy.is_contiguous() and z.is_contiguous()
+        dz = torch.empty_like(z)
+        _lib.check(self.lib.a8_gelu_bwd(_ptr(dy), _ptr(z), _ptr(dz), z.numel(), _stream()), "a8_gelu_bwd")
+        return dz
+
+    def log_softmax_fwd(self, x):
+        V = x.shape[-1]
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        y = torch.empty_like(x)
+        _lib.check(self.lib.a8_log_softmax_fwd(_ptr(x), _ptr(y), x.numel() // V, V, _stream()), "a8_log_softmax_fwd")
+        return y
+
+    def log_softmax_bwd(self, dy, y):
+        """dy: fp32 gradient w.r.t. y [B,T,V], any strides (e.g. the transposed [T,B,V] tensor CTC returns)"""
+        B, T, V = y.shape
+        assert dy.shape == y.shape and dy.dtype == torch.float32 and y.is_contiguous()
+        dx = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
+        _lib.check(self.lib.a8_log_softmax_bwd(_ptr(dy), dy.stride(0), dy.stride(1), dy.stride(2), T, _ptr(y), _ptr(dx),
+                                               B * T, V, _stream()), "a8_log_softmax_bwd")
+        return dx
+
+    # ------------------------------------------------------------------ conv layer 0
+    def conv0_stats(self, x, w, k, stride, eps):
+        B, L = x.shape
+        C = w.shape[0]
+        assert x.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
+        mom = torch.empty(65 * B, dtype=torch.float64, device=x.device)
+        mean = torch.empty(B, C, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(B, C, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.a8_conv0_stats(_ptr(x), B, L, _ptr(w), C, k, stride, eps, _ptr(mom), _ptr(mean), _ptr(rstd),
+                                           _stream()), "a8_conv0_stats")
+        return mean, rstd
+
+    def conv0_fwd(self, x, w, gamma, beta, mean, rstd, k, stride):
+        B, L = x.shape
+        C = w.shape[0]
+        L0 = (L - k) // stride + 1
+        y = torch.empty(B, L0, C, dtype=torch.bfloat16, device=x.device)
+        _lib.check(self.lib.a8_conv0_fwd(_ptr(x), B, L, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), C, k,
+                                         stride, _ptr(y), _stream()), "a8_conv0_fwd")
+        return y
+
+    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, k, stride, da):
+        B, L = x.shape
+        C = w.shape[0]
+        assert da.dtype == torch.bfloat16 and da.is_contiguous()
+        sums = torch.empty(B * C * 2, dtype=torch.float32, device=x.device)
+        acc = torch.zeros(C * k + 2 * C, dtype=torch.float32, device=x.device)
+        dw, dg, db = acc[:C * k].view(C, k), acc[C * k:C * k + C], acc[C * k + C:]
+        _lib.check(self.lib.a8_conv0_bwd(_ptr(x), B, L, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), C, k,
+                                         stride, _ptr(da), _ptr(sums), _ptr(dw), _ptr(dg), _ptr(db), _stream()),
+                   "a8_conv0_bwd")
+        return dw, dg, db
+
+    # ------------------------------------------------------------------ masks / indices / casts
+    @staticmethod
+    def _dt(t):
+        return {torch.float32: 0, torch.bfloat16: 1}[t]
+
+    def rows_gather(self, src, idx, out_dtype):
+        C = src.shape[-1]
+        assert src.is_contiguous() and idx.dtype == torch.int32
+        out = torch.empty(idx.numel(), C, dtype=out_dtype, device=src.device)
+        _lib.check(self.lib.a8_rows_copy(_ptr(src), self._dt(src.dtype), _ptr(out), self._dt(out_dtype), _ptr(idx),
+                                         idx.numel(), C, 0, _stream()), "a8_rows_copy")
+        return out
+
+    def rows_scatter(self, src, idx, n_rows, out_dtype):
+        """zero-filled [n_rows, C] with out[idx[i]] = src[i]"""
+        C = src.shape[-1]
+        assert src.is_contiguous() and idx.dtype == torch.int32
+        out = torch.zeros(n_rows, C, dtype=out_dtype, device=src.device)
+        _lib.check(self.lib.a8_rows_copy(_ptr(src), self._dt(src.dtype), _ptr(out), self._dt(out_dtype), _ptr(idx),
+                                         idx.numel(), C, 1, _stream()), "a8_rows_copy")
+        return out
+
+    def rows_set(self, x, idx, vec):
+        """in place: x[idx[i], :] = vec"""
+        C = x.shape[-1]
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and vec.dtype == torch.float32
+        _lib.check(self.lib.a8_rows_set(_ptr(x), _ptr(idx), idx.numel(), C, _ptr(vec), _stream()), "a8_rows_set")
+
+    def rows_set_bwd(self, dx, idx):
+        """in place: zero dx[idx[i], :]; returns the column sum of the rows it zeroed"""
+        C = dx.shape[-1]
+        dvec = torch.zeros(C, dtype=torch.float32, device=dx.device)
+        _lib.check(self.lib.a8_rows_set_bwd(_ptr(dx), _ptr(idx), idx.numel(), C, _ptr(dvec), _stream()),
+                   "a8_rows_set_bwd")
+        return dvec
+
+    def mask_apply(self, x, row_keep=None, chan_zero=None):
+        """in place on x bf16 [B,T,C]: zero rows with row_keep == 0 and channels with chan_zero != 0"""
+        B, T, C = x.shape
+        _lib.check(self.lib.a8_mask_apply(_ptr(x), _ptr(row_keep), _ptr(chan_zero), B, T, C, _stream()), "a8_mask_apply")
+
+    def cast(self, x, dtype):
+        assert x.is_contiguous()
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        _lib.check(self.lib.a8_cast(_ptr(x), self._dt(x.dtype), _ptr(out), self._dt(dtype), x.numel(), _stream()),
+                   "a8_cast")
+        return out
+
+    def split3(self, x, b_side):
+        R, C = x.shape
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        out = torch.empty(R, 3 * C, dtype=torch.bfloat16, device=x.device)
+        _lib.check(self.lib.a8_split3(_ptr(x), _ptr(out), R, C, int(b_side), _stream()), "a8_split3")
+        return out
+
+    # ------------------------------------------------------------------ quantizer / contrastive
+    def vq_fwd(self, z, noise, tau, vars2d, G):
+        R = z.shape[0]
+        V = z.shape[1] // G
+        vd = vars2d.shape[1]
+        dev = z.device
+        q = torch.empty(R, G * vd, dtype=torch.float32, device=dev)
+        qb = torch.empty(R, G * vd, dtype=torch.bfloat16, device=dev)
+        kidx = torch.empty(R * G, dtype=torch.int32, device=dev)
+        avg = torch.empty(V, dtype=torch.float32, device=dev)
+        ppl = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.a8_vq_fwd(_ptr(z), _ptr(noise), tau, _ptr(vars2d), R, G, V, vd, _ptr(q), _ptr(qb), _ptr(kidx),
+                                      _ptr(avg), _ptr(ppl), _stream()), "a8_vq_fwd")
+        return q, qb, kidx, avg, ppl
+
+    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl):
+        R = z.shape[0]
+        V = z.shape[1] // G
+        dz = torch.empty(R, G * V, dtype=torch.bfloat16, device=z.device)
+        dvars = torch.zeros(G * V, vd, dtype=torch.float32, device=z.device)
+        _lib.check(self.lib.a8_vq_bwd(_ptr(z), _ptr(noise), tau, R, G, V, vd, _ptr(a_dot), _ptr(dq), _ptr(kidx), _ptr(avg),
+                                      _ptr(ppl), _ptr(dppl), _ptr(dz), _ptr(dvars), _stream()), "a8_vq_bwd")
+        return dz, dvars
+
+    def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w):
+        R, Cc = x.shape
+        K = idx.numel() // R
+        dev = x.device
+        assert x.dtype == torch.float32 and y.dtype == torch.float32 and idx.dtype == torch.int32
+        xn = torch.empty(2 * R, dtype=torch.float32, device=dev)
+        cp = torch.empty(2, R, K + 1, dtype=torch.float32, device=dev)
+        rl = torch.empty(R + 2, dtype=torch.float32, device=dev)
+        _lib.check(self.lib.a8_contrastive_fwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(ppl), n_vars, xe_w, div_w,
+                                               _ptr(xn), _ptr(xn, R), _ptr(cp[0]), _ptr(cp[1]), _ptr(rl), _ptr(rl, R),
+                                               _ptr(rl, R + 1), _stream()), "a8_contrastive_fwd")
+        return rl[R + 1], rl[R], (xn, cp)
+
+    def contrastive_bwd(self, x, y, idx, saved, dce):
+        R, Cc = x.shape
+        K = idx.numel() // R
+        xn, cp = saved
+        dx = torch.empty_like(x)
+        dy = torch.empty_like(y)
+        _lib.check(self.lib.a8_contrastive_bwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(xn), _ptr(xn, R), _ptr(cp[0]),
+                                               _ptr(cp[1]), _ptr(dce), _ptr(dx), _ptr(dy), _stream()),
+                   "a8_contrastive_bwd")
+        return dx, dy
+
 
 _BACKEND = None
 

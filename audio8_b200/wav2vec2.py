@@ -1,0 +1,456 @@
+"""Drop-in for the hot-path classes of `audio8/wav2vec2.py` (reference: /root/reference/audio8/wav2vec2.py).
+
+Same factories, constructor arguments, attribute names, return tuples and `state_dict` keys as the reference
+(`create_model` :219, `create_acoustic_model` :262, `create_loss` :395, `ConvFeatureExtractionModel` :399,
+`GumbelVectorQuantizer` :459, `AudioTransformerEncoder` :579, `Wav2Vec2Encoder` :649, `Wav2Vec2AcousticModel` :726,
+`Wav2Vec2Model` :871, `Sampler` :955, `Wav2Vec2Loss` :371), so `pretrain.py` / `train.py` run unmodified when
+`audio8.wav2vec2` resolves here.  The arithmetic runs in hand-written sm_100a kernels
+(audio8_b200/csrc) through `functional.py`; host-side integer work (span masks, negative indices) repeats the
+reference's numpy calls in the reference's order so that the draws are bit-identical.
+"""
+import contextlib
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .functional import BF16, F32
+
+CONV_FEATURES = {
+    16: [(512, 10, 5), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 2, 2), (512, 2, 2)],
+    8: [(512, 10, 5), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 2, 2), (512, 2, 2)],
+}
+START_TEMP = 2
+END_TEMP = 0.5
+TEMP_DECAY_FACTOR = 0.999995
+XE_WGT = 0.1
+DIVERSITY_WGT = 10
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side integer work (numpy global RNG, same call order as the reference)
+# --------------------------------------------------------------------------------------------------
+def create_mask(shape, p_start=0.65, mask_length=10):
+    """Span mask with every row subsampled to the batch-minimum count (reference wav2vec2.py:189-216).
+    Draw order on numpy's global RNG: rand() once, choice() per row, choice() per over-long row."""
+    bsz, T = shape
+    mask = np.full((bsz, T), False)
+    num_mask = int(p_start * T / float(mask_length) + np.random.rand())
+    if num_mask == 0:
+        return mask
+    rows = []
+    for _ in range(bsz):
+        span = mask_length
+        if T - span <= num_mask:
+            span = T - num_mask - 1
+        starts = np.random.choice(T - span, num_mask, replace=False)
+        idx = (starts[:, None] + np.arange(mask_length)[None, :]).reshape(-1)
+        rows.append(np.unique(idx[idx < T]))
+    keep = min(len(r) for r in rows)
+    for i, r in enumerate(rows):
+        if len(r) > keep:
+            r = np.random.choice(r, keep, replace=False)
+        mask[i, r] = True
+    return mask
+
+
+def _mask_rows(mask_np, device):
+    """flat row indices (b*T + t, row-major: the order boolean indexing produces) as int32 on the device"""
+    idx = np.flatnonzero(mask_np.reshape(-1)).astype(np.int32)
+    return torch.from_numpy(idx).to(device, non_blocking=True)
+
+
+class Sampler:
+    """Negative sampling among the masked steps of the same utterance (reference wav2vec2.py:955-976)."""
+
+    def __init__(self, n_negatives=100):
+        self.n_negatives = n_negatives
+
+    def indices(self, B, T):
+        """[B, K*T] int64 numpy, already offset by b*T; identical draws to the reference's np.random.randint"""
+        own_t = np.repeat(np.arange(T), self.n_negatives)[None, :]
+        idx = np.random.randint(0, T - 1, (B, self.n_negatives * T))
+        idx = np.where(idx >= own_t, idx + 1, idx)
+        return idx + (np.arange(B) * T)[:, None]
+
+    def negatives(self, y):
+        """reference-compatible API: returns (negs [K,B,T,C], neg_idxs [B,K*T]); the fused loss never calls this"""
+        B, T, C = y.shape
+        idx = torch.from_numpy(self.indices(B, T))
+        negs = y.reshape(-1, C)[idx.view(-1).to(y.device)]
+        return negs.view(B, T, self.n_negatives, C).permute(2, 0, 1, 3), idx
+
+
+# --------------------------------------------------------------------------------------------------
+# small modules with reference-identical parameter names
+# --------------------------------------------------------------------------------------------------
+class _Linear(nn.Module):
+    """nn.Linear parameters (weight [out,in], bias) evaluated by the tcgen05 GEMM"""
+
+    def __init__(self, in_sz, out_sz):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_sz, in_sz))
+        self.bias = nn.Parameter(torch.zeros(out_sz))
+        nn.init.xavier_uniform_(self.weight)
+
+    def forward(self, x, out_f32=False):
+        return Fn.linear(x, self.weight, self.bias, out_f32)
+
+
+class Dense(nn.Module):
+    """eight_mile Dense: `.layer` is the Linear (keys `*.layer.weight`, reference wav2vec2.py:132-137)"""
+
+    def __init__(self, insz, outsz):
+        super().__init__()
+        self.layer = _Linear(insz, outsz)
+        self.output_dim = outsz
+
+    def forward(self, x, out_f32=False):
+        return self.layer(x, out_f32)
+
+
+class _Conv1dParams(nn.Module):
+    def __init__(self, cin, cout, k, bias=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, k))
+        nn.init.kaiming_uniform_(self.weight)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _Affine(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n))
+        self.bias = nn.Parameter(torch.zeros(n))
+
+
+class ConvFeatureExtractionModel(nn.Module):
+    """Reference wav2vec2.py:399-456.  Keys: conv_layers.{i}.0.weight, conv_layers.0.2.{weight,bias} (GroupNorm)."""
+
+    def __init__(self, conv_layers, dropout=0.0, conv_bias=False):
+        super().__init__()
+        if conv_bias or dropout != 0.0:
+            raise NotImplementedError("the reference only ever uses conv_bias=False, dropout=0.0 (wav2vec2.py:403-404)")
+        self.spec = [tuple(c) for c in conv_layers]
+        self.conv_layers = nn.ModuleList()
+        cin = 1
+        for i, (dim, k, stride) in enumerate(self.spec):
+            mods = [_Conv1dParams(cin, dim, k), nn.Identity()]
+            if i == 0:
+                mods.append(_Affine(dim))  # GroupNorm(dim, dim) affine parameters at index 2
+            mods.append(nn.Identity())
+            self.conv_layers.append(nn.ModuleList(mods))
+            cin = dim
+
+    def forward_channels_last(self, x):
+        """[B,L] fp32 -> bf16 [B,T,C]"""
+        gn = self.conv_layers[0][2]
+        weights = [layer[0].weight for layer in self.conv_layers]
+        return Fn.ConvFeatureFn.apply(x, self.spec, gn.weight, gn.bias, *weights)
+
+    def forward(self, x):
+        """reference layout: [B,C,T] fp32"""
+        return self.forward_channels_last(x).float().transpose(1, 2)
+
+
+class GumbelVectorQuantizer(nn.Module):
+    """Reference wav2vec2.py:459-576 (keys: vars [1,G*V,vd], weight_proj.{weight,bias})."""
+
+    def __init__(self, dim, num_vars, min_temperature, max_temperature, temperature_decay, num_groups, vq_dim):
+        super().__init__()
+        self.num_groups = num_groups
+        self.input_dim = dim
+        self.num_vars = num_vars
+        assert vq_dim % num_groups == 0, f"dim {vq_dim} must be divisible by groups {num_groups} for concatenation"
+        var_dim = vq_dim // num_groups
+        self.vars = nn.Parameter(torch.FloatTensor(1, num_groups * num_vars, var_dim))
+        nn.init.uniform_(self.vars)
+        self.weight_proj = _Linear(self.input_dim, num_groups * num_vars)
+        nn.init.normal_(self.weight_proj.weight, mean=0, std=1)
+        nn.init.zeros_(self.weight_proj.bias)
+        self.max_temperature = max_temperature
+        self.min_temperature = min_temperature
+        self.temperature_decay = temperature_decay
+        self.curr_temperature = self.max_temperature
+        self.codebook_indices = None
+        self.noise_override = None  # parity tests: Gumbel noise [B*T*G, V] drawn like F.gumbel_softmax does
+        self.last_indices = None
+
+    def set_num_updates(self, num_updates):
+        self.curr_temperature = max(self.max_temperature * self.temperature_decay ** num_updates, self.min_temperature)
+
+    def forward(self, x):
+        B, T, _ = x.shape
+        noise = None
+        if self.training:
+            noise = self.noise_override
+            if noise is None:  # what F.gumbel_softmax draws (wav2vec2.py:557)
+                n = B * T * self.num_groups
+                noise = -torch.empty(n, self.num_vars, dtype=F32, device=x.device).exponential_().log()
+            noise = noise.to(device=x.device, dtype=F32).contiguous()
+        q, ppl, kidx = Fn.QuantizerFn.apply(x, self.weight_proj.weight, self.weight_proj.bias, self.vars,
+                                            self.num_groups, self.curr_temperature, noise)
+        self.last_indices = kidx
+        return q, ppl
+
+
+class _PosConv(nn.Module):
+    """Conv1DSame(...).conv = Sequential(pad, conv, act) with weight_norm(dim=2) on conv[1]
+    (keys pos_conv.conv.1.{bias,weight_g,weight_v}, reference wav2vec2.py:140-142, 600-609)"""
+
+    def __init__(self, d_model, k, groups, std):
+        super().__init__()
+        conv = nn.Module()
+        conv.bias = nn.Parameter(torch.zeros(d_model))
+        v = torch.empty(d_model, d_model // groups, k).normal_(0, std)
+        conv.weight_g = nn.Parameter(v.norm(2, dim=(0, 1), keepdim=True))
+        conv.weight_v = nn.Parameter(v)
+        self.conv = nn.ModuleList([nn.Identity(), conv, nn.Identity()])
+
+    def weight(self):
+        c = self.conv[1]
+        return c.weight_g * c.weight_v / c.weight_v.norm(2, dim=(0, 1), keepdim=True)
+
+
+class _MHAParams(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.w_Q, self.w_K, self.w_V, self.w_O = Dense(d, d), Dense(d, d), Dense(d, d), Dense(d, d)
+
+
+class _LayerParams(nn.Module):
+    """parameter container with eight_mile TransformerEncoder's names: self_attn.w_{Q,K,V,O}.layer, ffn.{0,3}.layer,
+    ln1, ln2 (reference wav2vec2.py:110-126)"""
+
+    def __init__(self, d, d_ff):
+        super().__init__()
+        self.self_attn = _MHAParams(d)
+        self.ffn = nn.ModuleList([Dense(d, d_ff), nn.Identity(), nn.Identity(), Dense(d_ff, d)])
+        self.ln1 = _Affine(d)
+        self.ln2 = _Affine(d)
+
+    def flat(self):
+        a = self.self_attn
+        wqkv = torch.cat([a.w_Q.layer.weight, a.w_K.layer.weight, a.w_V.layer.weight], 0)
+        bqkv = torch.cat([a.w_Q.layer.bias, a.w_K.layer.bias, a.w_V.layer.bias], 0)
+        return [wqkv, bqkv, a.w_O.layer.weight, a.w_O.layer.bias, self.ln2.weight, self.ln2.bias,
+                self.ffn[0].layer.weight, self.ffn[0].layer.bias, self.ffn[3].layer.weight, self.ffn[3].layer.bias,
+                self.ln1.weight, self.ln1.bias]
+
+
+class _Stack(nn.Module):
+    def __init__(self, d, d_ff, layers):
+        super().__init__()
+        self.encoders = nn.ModuleList([_LayerParams(d, d_ff) for _ in range(layers)])
+
+
+class AudioTransformerEncoder(nn.Module):
+    """Reference wav2vec2.py:579-646: positional conv (k=128, groups=16, weight-normed) + GELU, residual, LayerNorm,
+    dropout, then a post-LN transformer stack (eight_mile TransformerEncoderStack, layer_norms_after=True)."""
+
+    def __init__(self, num_heads, d_model, pdrop, layers=1, activation="gelu", d_ff=None, conv_pos_kernel=128,
+                 conv_groups=16, layer_drop=0.0, **kwargs):
+        super().__init__()
+        if activation != "gelu":
+            raise NotImplementedError("the reference always uses gelu here (wav2vec2.py:618)")
+        self.d_model = d_model
+        self.num_heads = num_heads
+        self.pdrop = pdrop
+        self.conv_pos_kernel = conv_pos_kernel
+        self.conv_groups = conv_groups
+        self.layer_drop = layer_drop
+        std = math.sqrt((4 * (1.0 - pdrop)) / (conv_pos_kernel * d_model))
+        self.pos_conv = _PosConv(d_model, conv_pos_kernel, conv_groups, std)
+        self.transformer = _Stack(d_model, d_ff if d_ff else 4 * d_model, layers)
+        self.ln = _Affine(d_model)
+
+    def forward(self, x, pad_mask=None):
+        return self.extract_features(x, pad_mask)
+
+    def extract_features(self, x, pad_mask=None):
+        """x [B,T,D] (bf16 or fp32), pad_mask bool [B,T] (True = valid) or None -> bf16 [B,T,D]"""
+        n = len(self.transformer.encoders)
+        active = []
+        for _ in range(n):  # eight_mile draws one numpy random per layer, even with layer_drop == 0
+            pdrop = np.random.random()
+            active.append((not self.training) or pdrop >= self.layer_drop)
+        row_keep = None
+        if pad_mask is not None:
+            row_keep = pad_mask.to(device=x.device, dtype=torch.uint8).contiguous()
+        cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
+                   active=active)
+        flat = []
+        for layer in self.transformer.encoders:
+            flat += layer.flat()
+        return Fn.EncoderFn.apply(x, cfg, row_keep, self.pos_conv.weight(), self.pos_conv.conv[1].bias, self.ln.weight,
+                                  self.ln.bias, *flat)
+
+
+class Wav2Vec2Encoder(nn.Module):
+    """Reference wav2vec2.py:649-723 (fine-tuning encoder: pad handling, time + channel masking when training)."""
+
+    def __init__(self, conv_features=CONV_FEATURES[16], d_model=768, num_heads=12, num_layers=12, dropout=0.1, d_ff=None,
+                 dropout_input=0.1, dropout_features=0.0, timestep_masking=0.5, channel_masking=0.1,
+                 timestep_mask_len=10, channel_mask_len=64, layer_drop=0.0, freeze_fx=True):
+        super().__init__()
+        fx_dsz = conv_features[-1][0]
+        self.layer_norm = _Affine(fx_dsz)
+        self.dropout_input_p = dropout_input
+        self.dropout_features_p = dropout_features
+        self.feature_extractor = ConvFeatureExtractionModel(conv_features)
+        self.proj_to_input = Dense(fx_dsz, d_model)
+        self.encoder = AudioTransformerEncoder(num_heads, d_model, dropout, num_layers, d_ff=d_ff, layer_drop=layer_drop)
+        self.mask_emb = nn.Parameter(torch.FloatTensor(d_model).uniform_())
+        self.timestep_masking = timestep_masking
+        self.channel_masking = channel_masking
+        self.timestep_mask_len = timestep_mask_len
+        self.channel_mask_len = channel_mask_len
+        self.output_dim = d_model
+        self.freeze_fx = freeze_fx
+
+    def forward(self, x, pad_mask=None):
+        with torch.no_grad() if self.freeze_fx else contextlib.ExitStack():
+            fx = self.feature_extractor.forward_channels_last(x)
+        features = Fn.layer_norm(fx, self.layer_norm.weight, self.layer_norm.bias, 1e-5)
+        B, T, _ = features.shape
+        if pad_mask is not None:  # reference :703-708
+            extra = pad_mask.size(1) % T
+            if extra > 0:
+                pad_mask = pad_mask[:, :-extra]
+            pad_mask = pad_mask.view(pad_mask.size(0), T, -1).all(-1)
+        features = self.proj_to_input(features)
+        C = features.shape[-1]
+        features = Fn.dropout(features, self.dropout_input_p, self.training)
+        if self.training and self.timestep_masking > 0.0:
+            time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
+            features = Fn.RowsSetFn.apply(features, _mask_rows(time_mask, x.device), self.mask_emb)
+        if self.training and self.channel_masking > 0.0:
+            channel_mask = create_mask((B, C), p_start=self.channel_masking, mask_length=self.channel_mask_len)
+            cz = torch.from_numpy(channel_mask.astype(np.uint8)).to(x.device, non_blocking=True)
+            features = Fn.MaskApplyFn.apply(features, None, cz)
+        out = self.encoder(features, pad_mask)
+        return out, pad_mask
+
+
+class Wav2Vec2AcousticModel(nn.Module):
+    """Reference wav2vec2.py:726-770: encoder + linear head + log_softmax; `freeze` gates the encoder's gradients."""
+
+    def __init__(self, num_labels, conv_features=CONV_FEATURES[16], d_model=768, num_heads=12, num_layers=12,
+                 dropout=0.1, d_ff=None, dropout_input=0.0, dropout_features=0.0, timestep_masking=0.5,
+                 channel_masking=0.1, timestep_mask_len=10, channel_mask_len=64, layer_drop=0.0, freeze_fx=True):
+        super().__init__()
+        self.encoder = Wav2Vec2Encoder(conv_features, d_model, num_heads, num_layers, dropout, d_ff, dropout_input,
+                                       dropout_features, timestep_masking, channel_masking, timestep_mask_len,
+                                       channel_mask_len, layer_drop, freeze_fx=freeze_fx)
+        self.proj = _Linear(d_model, num_labels)
+        self.freeze = True
+
+    def forward(self, x, pad_mask=None):
+        with torch.no_grad() if self.freeze else contextlib.ExitStack():
+            encoded, pad_mask = self.encoder(x, pad_mask)
+        logits = self.proj(encoded, out_f32=True)
+        return Fn.LogSoftmaxFn.apply(logits), pad_mask
+
+
+class Wav2Vec2Model(nn.Module):
+    """Reference wav2vec2.py:871-952: contrastive pre-training model.  Returns (x [B,T,final], y [B,Tm,final],
+    vq perplexity (scalar), time_mask bool [B,T]) like the reference; the mask's row indices ride along on the
+    returned tensor (`time_mask.a8_rows`) so the loss needs no nonzero / host sync."""
+
+    def __init__(self, conv_features=CONV_FEATURES[16], num_vq_vars=320, start_temp=START_TEMP, end_temp=END_TEMP,
+                 temp_decay_factor=TEMP_DECAY_FACTOR, num_vq_groups=2, d_model=768, num_heads=12, num_layers=12,
+                 dropout=0.1, d_ff=None, final_dim=256, dropout_input=0.1, dropout_features=0.1, timestep_masking=0.65,
+                 channel_masking=0.0, timestep_mask_len=10, channel_mask_len=64, layer_drop=0.0):
+        super().__init__()
+        fx_dsz = conv_features[-1][0]
+        self.layer_norm = _Affine(fx_dsz)
+        self.dropout_input_p = dropout_input
+        self.dropout_features_p = dropout_features
+        self.feature_extractor = ConvFeatureExtractionModel(conv_features)
+        self.proj_to_input = Dense(fx_dsz, d_model)
+        # the reference passes (start, end, decay) into (min, max, decay) slots: tau == end_temp
+        self.quantizer = GumbelVectorQuantizer(fx_dsz, num_vq_vars, start_temp, end_temp, temp_decay_factor,
+                                               num_vq_groups, final_dim)
+        self.encoder = AudioTransformerEncoder(num_heads, d_model, dropout, num_layers, d_ff=d_ff, layer_drop=layer_drop)
+        self.project_q = Dense(final_dim, final_dim)
+        self.final_proj = Dense(d_model, final_dim)
+        self.timestep_masking = timestep_masking
+        self.channel_masking = channel_masking
+        self.timestep_mask_len = timestep_mask_len
+        self.channel_mask_len = channel_mask_len
+        self.mask_emb = nn.Parameter(torch.FloatTensor(d_model).uniform_())
+
+    def set_num_updates(self, s):
+        self.quantizer.set_num_updates(s)
+
+    def forward(self, x):
+        fx = self.feature_extractor.forward_channels_last(x)
+        features, unmasked = Fn.layer_norm(fx, self.layer_norm.weight, self.layer_norm.bias, 1e-5, want_f32=True)
+        B, T, C = unmasked.shape
+        features = self.proj_to_input(features)
+        features = Fn.dropout(features, self.dropout_input_p, self.training)
+        # masking runs in eval mode too (reference :937 has no training guard)
+        time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
+        rows = _mask_rows(time_mask, x.device)
+        features = Fn.RowsSetFn.apply(features, rows, self.mask_emb)
+        if self.channel_masking > 0.0:
+            raise NotImplementedError("channel masking in pre-training is broken in the reference (wav2vec2.py:943)")
+        y = Fn.RowsGatherFn.apply(unmasked, rows).view(B, -1, C)
+        y = Fn.dropout(y, self.dropout_features_p, self.training)
+        enc = self.encoder(features)
+        q, vq_probs = self.quantizer(y)
+        y = self.project_q(q, out_f32=True)
+        xo = self.final_proj(enc, out_f32=True)
+        mask_t = torch.from_numpy(time_mask).to(x.device, non_blocking=True)
+        mask_t.a8_rows = rows
+        return xo, y, vq_probs, mask_t
+
+
+class Wav2Vec2Loss(nn.Module):
+    """Reference wav2vec2.py:371-392: 0.1 * CE(cos-sim logits over [positive | K negatives]) + 10 * (n_vars - ppl) / n_vars."""
+
+    def __init__(self, n_vars, n_negatives=100):
+        super().__init__()
+        self.n_vars = n_vars
+        self.sample = Sampler(n_negatives)
+        self.last_neg_idx = None
+
+    def __call__(self, model, features):
+        outputs, latents, gs_probs, time_mask = model(features)
+        B, Tm, C = latents.shape
+        rows = getattr(time_mask, "a8_rows", None)
+        if rows is None:
+            rows = torch.nonzero(time_mask.reshape(-1)).reshape(-1).int()
+        xm = Fn.RowsGatherFn.apply(outputs, rows)  # outputs[time_mask] -> [B*Tm, C]
+        neg = self.sample.indices(B, Tm)  # numpy, bit-exact with the reference's Sampler
+        self.last_neg_idx = neg
+        idx = torch.from_numpy(neg.astype(np.int32)).to(outputs.device, non_blocking=True)
+        loss, _ = Fn.ContrastiveFn.apply(xm, latents.reshape(B * Tm, C), idx, gs_probs, self.n_vars, XE_WGT,
+                                         DIVERSITY_WGT)
+        return loss
+
+
+def create_loss(n_vars, n_negatives):
+    return Wav2Vec2Loss(n_vars, n_negatives)
+
+
+def create_model(sample_rate=16, num_vq_vars=320, num_vq_groups=2, d_model=768, num_heads=12, num_layers=12,
+                 dropout=0.1, d_ff=None, final_dim=256, dropout_input=0.1, dropout_features=0.1, timestep_masking=0.65,
+                 channel_masking=0.0, timestep_mask_len=10, channel_mask_len=64, layer_drop=0.0, **kwargs):
+    """Same signature as the reference factory (wav2vec2.py:219-259); extra kwargs are swallowed like there."""
+    return Wav2Vec2Model(CONV_FEATURES[sample_rate], num_vq_vars, START_TEMP, END_TEMP, TEMP_DECAY_FACTOR,
+                         num_vq_groups, d_model, num_heads, num_layers, dropout, d_ff, final_dim, dropout_input,
+                         dropout_features, timestep_masking, channel_masking, timestep_mask_len, channel_mask_len,
+                         layer_drop)
+
+
+def create_acoustic_model(num_labels, sample_rate=16, d_model=768, num_heads=12, num_layers=12, dropout=0.1, d_ff=None,
+                          dropout_input=0.0, timestep_masking=0.5, channel_masking=0.1, timestep_mask_len=10,
+                          channel_mask_len=64, layer_drop=0.0, freeze_fx=True, **kwargs):
+    """Same signature as the reference factory (wav2vec2.py:262-296)."""
+    return Wav2Vec2AcousticModel(num_labels, CONV_FEATURES[sample_rate], d_model, num_heads, num_layers, dropout, d_ff,
+                                 dropout_input, 0.0, timestep_masking, channel_masking, timestep_mask_len,
+                                 channel_mask_len, layer_drop, freeze_fx)

@@ -116,6 +116,103 @@ int a8_ctc_backward(const float* log_probs, int64_t stride_t, int64_t stride_b, 
                     int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity, float* grad,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (+ residual add, + dropout), bf16 rows of C <= 1024 channels (C % 8 == 0), fp32 statistics.
+ * Replaces nn.LayerNorm + residual `+` + nn.Dropout around it: `wav2vec2.py:904,930` (post-extractor LN),
+ * `:623,638-640` (encoder LN after the positional conv) and ln1/ln2 of every transformer layer.
+ *   fwd:  s = x + drop_h(h);  y = drop_y(LN(s)*gamma + beta);  h, s_out, y_f32 optional (NULL)
+ *   bwd:  g = drop_y(dy (+ dy_f32));  ds = dLN(g);  dh = drop_h(ds) (optional);
+ *         dgamma/dbeta/dbias_h (= column sum of dh, or of ds when dh is NULL) are ACCUMULATED (zero them first)
+ * Dropout masks are regenerated from (seed, element index): Philox-4x32, nothing is stored.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_t seed_h, void* s_out, const float* gamma,
+                     const float* beta, float eps, void* y, float* y_f32, float p_y, uint64_t seed_y, float* mean,
+                     float* rstd, int32_t R, int32_t C, void* stream);
+int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, uint64_t seed_y, const void* s,
+                     const float* mean, const float* rstd, const float* gamma, void* ds, void* dh, float p_h,
+                     uint64_t seed_h, float* dgamma, float* dbeta, float* dbias_h, int32_t R, int32_t C,
+                     void* stream);
+
+/* Attention softmax over keys.  Replaces softmax / masked_fill(-1e9) / dropout in eight_mile's
+ * SeqScaledDotProductAttention (called via `wav2vec2.py:644`).  s fp32 [B,H,T,Tp] (Tp = T rounded up to 8),
+ * key_keep uint8 [B,T] or NULL (0 = padded key), p / p_drop / ds bf16 [B,H,T,Tp] (pad columns written 0).
+ *   fwd: p = softmax(s);  p_drop = dropout(p) if p_drop != NULL
+ *   bwd: ds = p * (g - sum(p*g)),  g = dropout-mask * dp */
+int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, void* p_drop, float pdrop, uint64_t seed,
+                   int32_t B, int32_t H, int32_t T, int32_t Tp, void* stream);
+int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pdrop, uint64_t seed, int32_t B, int32_t H,
+                   int32_t T, int32_t Tp, void* stream);
+
+/* out[c] += sum_r x[r][c]  (bias gradients; x bf16 [R, ld], out fp32 zeroed by the caller) */
+int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void* stream);
+/* element-wise dropout (nn.Dropout at `wav2vec2.py:934-935,713`), dtype 0 = fp32, 1 = bf16; its own backward */
+int a8_dropout(const void* x, void* out, int32_t dtype, int64_t n, float p, uint64_t seed, void* stream);
+/* dz = dy * gelu'(z) (bf16): backward of the GELU that a GEMM epilogue applied (`wav2vec2.py:422,428,607`) */
+int a8_gelu_bwd(const void* dy, const void* z, void* dz, int64_t n, void* stream);
+/* F.log_softmax(-1) of `wav2vec2.py:770`: x fp32 [R,V] -> y fp32; bwd consumes a strided fp32 gradient
+ * (element (row, c) at dy[(row / rows_inner)*stride_outer + (row % rows_inner)*stride_row + c*stride_v], so the
+ * [T,B,V] CTC gradient needs no transpose) and writes dx bf16 [R,V] */
+int a8_log_softmax_fwd(const float* x, float* y, int32_t R, int32_t V, void* stream);
+int a8_log_softmax_bwd(const float* dy, int64_t stride_outer, int64_t stride_row, int64_t stride_v,
+                       int32_t rows_inner, const float* y, void* dx, int32_t R, int32_t V, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Feature-encoder layer 0: Conv1d(1->C,k,stride, no bias) + GroupNorm(C,C) + GELU, fused (`wav2vec2.py:419-422`).
+ * x fp32 [B,L]; w fp32 [C,k]; y / da bf16 [B,L0,C] channels-last, L0 = (L-k)/stride + 1.
+ *   stats: per-(b,c) mean / rstd over time from the window moments of x (moments: 65*B doubles of scratch)
+ *   fwd:   y = gelu(((conv(x) - mean) * rstd) * gamma + beta)
+ *   bwd:   given da = dL/dy: dw, dgamma, dbeta ACCUMULATED (zero first); sums: 2*B*C floats of scratch
+ * ---------------------------------------------------------------------------------------------- */
+int a8_conv0_stats(const float* x, int32_t B, int64_t L, const float* w, int32_t C, int32_t k, int32_t stride,
+                   float eps, double* moments, float* mean, float* rstd, void* stream);
+int a8_conv0_fwd(const float* x, int32_t B, int64_t L, const float* w, const float* gamma, const float* beta,
+                 const float* mean, const float* rstd, int32_t C, int32_t k, int32_t stride, void* y, void* stream);
+int a8_conv0_bwd(const float* x, int32_t B, int64_t L, const float* w, const float* gamma, const float* beta,
+                 const float* mean, const float* rstd, int32_t C, int32_t k, int32_t stride, const void* da,
+                 float* sums, float* dw, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Time-mask plumbing (`wav2vec2.py:939,946,381,632,717,721`): index driven, no nonzero / host sync.
+ * dtype codes: 0 = fp32, 1 = bf16.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_rows_copy(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, const int32_t* idx, int32_t n,
+                 int32_t C, int32_t scatter, void* stream); /* gather dst[i]=src[idx[i]] / scatter dst[idx[i]]=src[i] */
+int a8_rows_set(void* x, const int32_t* idx, int32_t n, int32_t C, const float* vec, void* stream);
+int a8_rows_set_bwd(void* dx, const int32_t* idx, int32_t n, int32_t C, float* dvec, void* stream);
+int a8_mask_apply(void* x, const uint8_t* row_keep, const uint8_t* chan_zero, int32_t B, int32_t T, int32_t C,
+                  void* stream);
+int a8_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+/* bf16x3 split of an fp32 matrix [R,C] -> bf16 [R,3C] so one bf16 GEMM reproduces an fp32-accurate product */
+int a8_split3(const float* src, void* dst, int32_t R, int32_t C, int32_t b_side, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gumbel vector quantizer rows (`wav2vec2.py:547-576`; closed forms in SURVEY D.2).
+ * z fp32 [R,G*V] logits; noise fp32 [R*G,V] = -log(Exp(1)) drawn by the caller exactly as F.gumbel_softmax does,
+ * or NULL in eval mode; vars fp32 [G*V,vd].  fwd: kidx[R*G] = argmax, q[R,G*vd] = selected codewords (+ bf16
+ * copy), avg_sums[V] = sum of softmax(z) rows pooled over groups, ppl = exp(-sum q log(q+1e-7)).
+ * bwd: a_dot fp32 [R,G*V] = dq . vars^T per group (from a8_gemm); writes dz bf16 [R,G*V]; dvars ACCUMULATED.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_vq_fwd(const float* z, const float* noise, float tau, const float* vars, int32_t R, int32_t G, int32_t V,
+              int32_t vd, float* q, void* q_bf16, int32_t* kidx, float* avg_sums, float* ppl, void* stream);
+int a8_vq_bwd(const float* z, const float* noise, float tau, int32_t R, int32_t G, int32_t V, int32_t vd,
+              const float* a_dot, const float* dq, const int32_t* kidx, const float* avg_sums, const float* ppl,
+              const float* dppl, void* dz, float* dvars, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Contrastive loss (`wav2vec2.py:377-392`, Sampler :955-976; closed forms in SURVEY D.3).
+ * x, y fp32 [R,C] (context outputs at the masked steps, projected quantized targets), idx int32 [R,K] rows of y
+ * (the reference's numpy-drawn negatives, already offset by b*Tm).  cos-sim logits over [positive | K negatives],
+ * ce = mean_i CE(logits_i, 0), loss = xe_w*ce + div_w*(n_vars - *ppl)/n_vars (ppl may be NULL).
+ * Scratch kept for backward: xn, yn [R]; cosv, prob [R,K+1]; row_loss [R].
+ * bwd: dce = d loss / d ce (device scalar) -> dx [R,C], dy [R,C].
+ * ---------------------------------------------------------------------------------------------- */
+int a8_contrastive_fwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
+                       const float* ppl, float n_vars, float xe_w, float div_w, float* xn, float* yn, float* cosv,
+                       float* prob, float* row_loss, float* ce, float* loss, void* stream);
+int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
+                       const float* xn, const float* yn, const float* cosv, const float* prob, const float* dce,
+                       float* dx, float* dy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

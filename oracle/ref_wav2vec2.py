@@ -143,9 +143,11 @@ def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", p
     return x
 
 
-def gumbel_quantizer(sd, y, num_groups, tau=0.5, gumbel_noise=None, prefix="quantizer."):
+def gumbel_quantizer(sd, y, num_groups, tau=0.5, gumbel_noise=None, prefix="quantizer.", force_idx=None):
     """wav2vec2.py:547-576.  y [B,Tm,512] -> (q [B,Tm,G*var_dim], prob_ppl, argmax indices [B*Tm*G]).
-    training: gumbel_noise [B*Tm*G, V] (= -log(Exp(1)), as F.gumbel_softmax draws it); eval: None."""
+    training: gumbel_noise [B*Tm*G, V] (= -log(Exp(1)), as F.gumbel_softmax draws it); eval: None.
+    force_idx (test aid, not in the reference): use these code indices instead of the arg-max, so that a
+    bf16 near-tie flip upstream does not pollute every downstream comparison; flips are counted separately."""
     B, Tm, _ = y.shape
     z = _lin(sd, prefix + "weight_proj", y).reshape(B * Tm * num_groups, -1).float()
     V = z.shape[-1]
@@ -153,11 +155,11 @@ def gumbel_quantizer(sd, y, num_groups, tau=0.5, gumbel_noise=None, prefix="quan
     if gumbel_noise is not None:
         u = (z + gumbel_noise) / tau
         soft = torch.softmax(u, -1)
-        k = soft.argmax(-1)
+        k = soft.argmax(-1) if force_idx is None else torch.as_tensor(force_idx).long()
         hard = torch.zeros_like(z).scatter_(-1, k[:, None], 1.0)
         onehot = hard - soft.detach() + soft  # straight-through (torch F.gumbel_softmax hard=True)
     else:
-        k = z.argmax(-1)
+        k = z.argmax(-1) if force_idx is None else torch.as_tensor(force_idx).long()
         onehot = torch.zeros_like(z).scatter_(-1, k[:, None], 1.0)
     ppl = torch.exp(-torch.sum(avg_probs * torch.log(avg_probs + 1e-7)))  # wav2vec2.py:565
     vars_ = sd[prefix + "vars"]  # [1, G*V, var_dim]
@@ -182,7 +184,7 @@ def contrastive_loss(x_masked, y, neg_idx, ppl, n_vars):
 # whole-model forwards (dropout off)
 # ------------------------------------------------------------------------------------------------
 def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2, tau=0.5, gumbel_noise=None,
-                     conv_features=CONV_FEATURES[16]):
+                     conv_features=CONV_FEATURES[16], force_idx=None):
     """Wav2Vec2Model.forward (wav2vec2.py:927-952) with the time mask supplied.  Returns a dict of stages."""
     fx = conv_feature_extractor(sd, x, conv_features=conv_features).transpose(1, 2)
     feats = _ln(sd, "layer_norm", fx, LN_EPS_TORCH)
@@ -193,7 +195,7 @@ def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2
     h = torch.where(tm[..., None], sd["mask_emb"].expand_as(h), h)
     y_in = unmasked[tm].view(B, -1, unmasked.shape[-1])
     enc = audio_transformer_encoder(sd, h, num_heads, num_layers)
-    q, ppl, k = gumbel_quantizer(sd, y_in, num_groups, tau, gumbel_noise)
+    q, ppl, k = gumbel_quantizer(sd, y_in, num_groups, tau, gumbel_noise, force_idx=force_idx)
     y = _lin(sd, "project_q.layer", q)
     xo = _lin(sd, "final_proj.layer", enc)
     return dict(fx=fx, features=feats, y_in=y_in, enc=enc, q=q, ppl=ppl, vq_idx=k, y=y, x=xo)

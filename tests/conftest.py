@@ -19,6 +19,6 @@ def emu_backend():
     from audio8_b200 import ops
     import emu
     prev = ops._BACKEND
-    ops.set_backend(emu.EmuBackend())
+    ops.set_backend(emu.EmuOps())
     yield ops._BACKEND
     ops.set_backend(prev)

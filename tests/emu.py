@@ -99,3 +99,228 @@ class EmuBackend:
 
     def gemm(self, g):
         emu_gemm(g)
+
+
+def _drop_mask(shape, p, seed):
+    """consistent between forward and backward within the emulation (not bit-identical to the CUDA Philox stream)"""
+    if p <= 0:
+        return torch.ones(shape)
+    g = torch.Generator().manual_seed(int(seed) & 0x7FFFFFFF)
+    return (torch.rand(shape, generator=g) >= p).float() / (1.0 - p)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+class EmuOps(EmuBackend):
+    """row / index / loss kernels of the ABI, emulated with fp32 PyTorch math and bf16 storage"""
+
+    # ---- layernorm
+    def layernorm_fwd(self, x, gamma, beta, eps, h=None, p_h=0.0, seed_h=0, want_f32=False, p_y=0.0, seed_y=0):
+        s = x
+        if h is not None:
+            s = _bf(x.float() + h.float() * _drop_mask(h.shape, p_h, seed_h))
+        sf = s.float()
+        mean = sf.mean(-1)
+        var = sf.var(-1, unbiased=False)
+        rstd = (var + eps).rsqrt()
+        y = ((sf - mean[..., None]) * rstd[..., None] * gamma + beta) * _drop_mask(s.shape, p_y, seed_y)
+        return _bf(y), (y.clone() if want_f32 else None), s, mean.reshape(-1), rstd.reshape(-1)
+
+    def layernorm_bwd(self, dy, s, mean, rstd, gamma, dy_f32=None, p_y=0.0, seed_y=0, want_dh=False, p_h=0.0,
+                      seed_h=0, want_dbias=False):
+        C = s.shape[-1]
+        g = dy.float() + (dy_f32 if dy_f32 is not None else 0.0)
+        g = (g * _drop_mask(s.shape, p_y, seed_y)).reshape(-1, C)
+        xh = (s.float().reshape(-1, C) - mean[:, None]) * rstd[:, None]
+        dgamma, dbeta = (g * xh).sum(0), g.sum(0)
+        gg = g * gamma
+        ds = rstd[:, None] * (gg - gg.mean(-1, keepdim=True) - xh * (gg * xh).mean(-1, keepdim=True))
+        ds = ds.reshape(s.shape)
+        dh = None
+        if want_dh:
+            dh = ds * _drop_mask(s.shape, p_h, seed_h)
+        dbias = None
+        if want_dbias:
+            dbias = (dh if dh is not None else ds).reshape(-1, C).sum(0)
+        return _bf(ds), (_bf(dh) if dh is not None else None), dgamma, dbeta, dbias
+
+    # ---- softmax
+    def softmax_fwd(self, s, T, key_keep=None, pdrop=0.0, seed=0):
+        B, H, _, Tp = s.shape
+        x = s[..., :T].clone()
+        if key_keep is not None:
+            x = x.masked_fill(key_keep[:, None, None, :] == 0, -1e9)
+        p = torch.zeros(s.shape)
+        p[..., :T] = torch.softmax(x, -1)
+        pd = _bf(p * _drop_mask(p.shape, pdrop, seed)) if pdrop > 0 else None
+        return _bf(p), pd
+
+    def softmax_bwd(self, p, dp, T, pdrop=0.0, seed=0):
+        pf = p.float()
+        g = dp.clone()
+        g[..., T:] = 0
+        g = g * _drop_mask(p.shape, pdrop, seed)
+        ds = pf * (g - (pf * g).sum(-1, keepdim=True))
+        return _bf(ds)
+
+    def colsum(self, x):
+        return x.float().reshape(-1, x.shape[-1]).sum(0)
+
+    def dropout(self, x, p, seed):
+        return (x.float() * _drop_mask(x.shape, p, seed)).to(x.dtype)
+
+    def gelu_bwd(self, dy, z):
+        return _bf(dy.float() * gelu_grad(z.float()))
+
+    def log_softmax_fwd(self, x):
+        return torch.log_softmax(x, -1)
+
+    def log_softmax_bwd(self, dy, y):
+        return _bf(dy - y.exp() * dy.sum(-1, keepdim=True))
+
+    # ---- conv0
+    def conv0_stats(self, x, w, k, stride, eps):
+        z = torch.nn.functional.conv1d(x.double()[:, None, :], w.double()[:, None, :], stride=stride)  # [B,C,L0]
+        mean = z.mean(-1)
+        var = z.var(-1, unbiased=False)
+        return mean.float(), (var + eps).rsqrt().float()
+
+    def _conv0_z(self, x, w, stride):
+        return torch.nn.functional.conv1d(x[:, None, :], w[:, None, :], stride=stride).transpose(1, 2)  # [B,L0,C]
+
+    def conv0_fwd(self, x, w, gamma, beta, mean, rstd, k, stride):
+        z = self._conv0_z(x, w, stride)
+        y = (z - mean[:, None, :]) * rstd[:, None, :] * gamma + beta
+        return _bf(gelu(y)).contiguous()
+
+    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, k, stride, da):
+        z = self._conv0_z(x, w, stride)
+        xh = (z - mean[:, None, :]) * rstd[:, None, :]
+        dy = da.float() * gelu_grad(xh * gamma + beta)
+        dgamma, dbeta = (dy * xh).sum((0, 1)), dy.sum((0, 1))
+        dz = (rstd[:, None, :] * gamma) * (dy - dy.mean(1, keepdim=True) - xh * (dy * xh).mean(1, keepdim=True))
+        B, L0, C = dz.shape
+        win = x.unfold(1, k, stride)  # [B, L0, k]
+        dw = torch.einsum("blc,blk->ck", dz, win)
+        return dw, dgamma, dbeta
+
+    # ---- masks / indices / casts
+    def rows_gather(self, src, idx, out_dtype):
+        return src[idx.long()].to(out_dtype)
+
+    def rows_scatter(self, src, idx, n_rows, out_dtype):
+        out = torch.zeros(n_rows, src.shape[-1], dtype=out_dtype)
+        out[idx.long()] = src.to(out_dtype)
+        return out
+
+    def rows_set(self, x, idx, vec):
+        x[idx.long()] = vec.to(x.dtype)
+
+    def rows_set_bwd(self, dx, idx):
+        dvec = dx[idx.long()].float().sum(0)
+        dx[idx.long()] = 0
+        return dvec
+
+    def mask_apply(self, x, row_keep=None, chan_zero=None):
+        B, T, C = x.shape
+        if row_keep is not None:
+            x.view(B * T, C)[row_keep.reshape(-1) == 0] = 0
+        if chan_zero is not None:
+            x.masked_fill_(chan_zero[:, None, :] != 0, 0)
+
+    def cast(self, x, dtype):
+        return x.to(dtype)
+
+    def split3(self, x, b_side):
+        hi = _bf(x)
+        lo = _bf(x - hi.float())
+        return torch.cat([hi, lo, hi] if b_side else [hi, hi, lo], 1).contiguous()
+
+    # ---- quantizer / contrastive
+    def vq_fwd(self, z, noise, tau, vars2d, G):
+        R = z.shape[0]
+        V = z.shape[1] // G
+        zz = z.reshape(R * G, V)
+        u = (zz + noise) / tau if noise is not None else zz
+        kidx = u.argmax(-1)
+        avg = torch.softmax(zz, -1).sum(0)
+        qbar = avg / (R * G)
+        ppl = torch.exp(-(qbar * torch.log(qbar + 1e-7)).sum())
+        g = torch.arange(R * G) % G
+        q = vars2d[g * V + kidx].reshape(R, -1)
+        return q, _bf(q), kidx.int(), avg, ppl
+
+    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl):
+        R = z.shape[0]
+        V = z.shape[1] // G
+        N = R * G
+        zz = z.reshape(N, V)
+        qbar = avg / N
+        dqb = -(dppl * ppl / N) * (torch.log(qbar + 1e-7) + qbar / (qbar + 1e-7))
+        s = torch.softmax(zz, -1)
+        dz = s * (dqb - (s * dqb).sum(-1, keepdim=True))
+        if noise is not None:
+            p = torch.softmax((zz + noise) / tau, -1)
+            a = a_dot.reshape(N, V)
+            dz = dz + p * (a - (p * a).sum(-1, keepdim=True)) / tau
+        dvars = torch.zeros(G * V, vd)
+        g = torch.arange(N) % G
+        dvars.index_add_(0, g * V + kidx.long(), dq.reshape(N, vd))
+        return _bf(dz.reshape(R, G * V)), dvars
+
+    def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w):
+        R, C = x.shape
+        K = idx.numel() // R
+        xn = x.norm(dim=-1).clamp_min(1e-8)
+        yn = y.norm(dim=-1).clamp_min(1e-8)
+        cand = torch.cat([torch.arange(R)[:, None], idx.reshape(R, K).long()], 1)
+        cos = torch.einsum("rc,rkc->rk", x, y[cand]) / (xn[:, None] * yn[cand])
+        lse = torch.logsumexp(cos, -1)
+        prob = torch.exp(cos - lse[:, None])
+        ce = (lse - cos[:, 0]).mean()
+        loss = xe_w * ce + (div_w * (n_vars - ppl) / n_vars if ppl is not None else 0.0)
+        return loss, ce, (xn, yn, cos, prob, cand)
+
+    def contrastive_bwd(self, x, y, idx, saved, dce):
+        xn, yn, cos, prob, cand = saved
+        R, C = x.shape
+        dcos = prob.clone()
+        dcos[:, 0] -= 1.0
+        dcos = dcos * (dce / R)
+        xh = x / xn[:, None]
+        yh = y[cand] / yn[cand][..., None]
+        dx = (dcos[..., None] * (yh - cos[..., None] * xh[:, None, :])).sum(1) / xn[:, None]
+        dyc = dcos[..., None] * (xh[:, None, :] - cos[..., None] * yh) / yn[cand][..., None]
+        dy = torch.zeros_like(y)
+        dy.index_add_(0, cand.reshape(-1), dyc.reshape(-1, C))
+        return dx, dy
+
+    # ---- ctc (emulated with the installed torch op)
+    def ctc_prep(self, targets, pad, eos, target_lengths, input_lengths):
+        keep = (targets != pad) & (targets != eos)
+        flat = targets[keep].int()
+        off = (torch.cumsum(target_lengths, 0) - target_lengths).int()
+        return flat, off, target_lengths.int(), input_lengths.int()
+
+    def ctc_forward(self, lp, flat, off, tl, il, max_S, blank, mean, zero_inf):
+        with torch.enable_grad():
+            lpg = lp.detach().clone().requires_grad_(True)
+            nll = torch.nn.functional.ctc_loss(lpg, flat.long(), il.long(), tl.long(), blank=blank, reduction="none",
+                                               zero_infinity=False)
+        v = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll) if zero_inf else nll
+        loss = (v / tl.clamp_min(1)).mean() if mean else v.sum()
+        return loss.detach(), nll.detach(), (lpg, nll), None
+
+    def ctc_backward(self, lp, flat, off, tl, il, max_S, blank, alpha, beta, nll, grad_out, mean, zero_inf):
+        lpg, nll_g = alpha
+        B = lp.shape[1]
+        scale = grad_out.reshape(-1).expand(B).clone()
+        if mean:
+            scale = scale / (tl.clamp_min(1) * B)
+        scale = torch.where(torch.isinf(nll_g.detach()), torch.zeros_like(scale), scale)
+        with torch.enable_grad():
+            fin = torch.where(torch.isinf(nll_g), torch.zeros_like(nll_g), nll_g)
+            (g,) = torch.autograd.grad((fin * scale).sum(), lpg)
+        return torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0)

@@ -1,0 +1,212 @@
+"""Per-kernel parity on the GPU: every row / index / loss kernel of the C ABI against the pure-PyTorch fp32
+emulation of the same ABI (tests/emu.py), on seeded inputs.  bf16 outputs: max|err| <= 2e-2 * max|ref| (one
+bf16 rounding of an fp32 value is 2^-9 relative; sums of a few of them stay well inside); fp32 outputs 1e-4."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import emu
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _bf(shape, seed, scale=1.0):
+    return (torch.randn(shape, generator=_g(seed)) * scale).to(torch.bfloat16)
+
+
+def _close(got, want, tol, what):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"{what}: max abs err {err:.4g} vs scale {scale:.4g}"
+
+
+@pytest.fixture(scope="module")
+def be():
+    from audio8_b200 import ops
+    return ops.backend()
+
+
+E = emu.EmuOps()
+
+
+@pytest.mark.parametrize("R,C", [(37, 128), (300, 512), (1000, 768), (64, 1024)])
+def test_layernorm(be, R, C):
+    x, h = _bf((R, C), 1), _bf((R, C), 2)
+    gamma = 1 + 0.1 * torch.randn(C, generator=_g(3))
+    beta = 0.1 * torch.randn(C, generator=_g(4))
+    dy = _bf((R, C), 5)
+    dyf = torch.randn(R, C, generator=_g(6))
+    for use_h in (False, True):
+        ref = E.layernorm_fwd(x, gamma, beta, 1e-5, h=h if use_h else None, want_f32=True)
+        got = be.layernorm_fwd(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5, h=h.cuda() if use_h else None, want_f32=True)
+        for i, name in enumerate(["y", "y_f32", "s", "mean", "rstd"]):
+            _close(got[i], ref[i], 2e-2 if i < 3 else 1e-3, f"ln fwd {name} (h={use_h})")
+        s, mean, rstd = ref[2], ref[3], ref[4]
+        rb = E.layernorm_bwd(dy, s, mean, rstd, gamma, dy_f32=dyf, want_dh=use_h, want_dbias=True)
+        gb = be.layernorm_bwd(dy.cuda(), s.cuda(), mean.cuda(), rstd.cuda(), gamma.cuda(), dy_f32=dyf.cuda(),
+                              want_dh=use_h, want_dbias=True)
+        for i, name in enumerate(["ds", "dh", "dgamma", "dbeta", "dbias"]):
+            if rb[i] is None:
+                assert gb[i] is None
+                continue
+            _close(gb[i], rb[i], 2e-2, f"ln bwd {name} (h={use_h})")
+
+
+def test_layernorm_dropout_consistency(be):
+    """forward and backward regenerate the same Philox mask; keep-rate matches p"""
+    R, C, p = 256, 768, 0.1
+    x, h = torch.zeros(R, C, dtype=torch.bfloat16).cuda(), _bf((R, C), 2).cuda()
+    gamma, beta = torch.ones(C).cuda(), torch.zeros(C).cuda()
+    y, _, s, mean, rstd = be.layernorm_fwd(x, gamma, beta, 1e-5, h=h, p_h=p, seed_h=1234)
+    mask_fwd = s.float() != 0  # x == 0, so s = drop(h)
+    keep = mask_fwd.float().mean().item()
+    assert abs(keep - (1 - p)) < 0.01, keep
+    ds, dh, *_ = be.layernorm_bwd(_bf((R, C), 3).cuda(), s, mean, rstd, gamma, want_dh=True, p_h=p, seed_h=1234)
+    live = ds.float() != 0
+    assert ((dh.float() != 0) == mask_fwd)[live].float().mean().item() > 0.9999
+    nz = dh.float() != 0
+    _close(dh.float()[nz], (ds.float() / (1 - p))[nz], 1e-2, "dh scale")
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 2, 49), (1, 3, 300), (2, 1, 749)])
+def test_softmax(be, B, H, T):
+    Tp = (T + 7) // 8 * 8
+    s = torch.randn(B, H, T, Tp, generator=_g(1)) * 3
+    keep = (torch.rand(B, T, generator=_g(2)) > 0.2).to(torch.uint8)
+    keep[:, 0] = 1
+    dp = torch.randn(B, H, T, Tp, generator=_g(3))
+    for kk in (None, keep):
+        p_ref, _ = E.softmax_fwd(s, T, kk)
+        p_got, pd = be.softmax_fwd(s.cuda(), T, kk.cuda() if kk is not None else None)
+        assert pd is None
+        _close(p_got, p_ref, 1e-2, "softmax fwd")
+        assert p_got[..., T:].abs().max().item() == 0 if Tp > T else True
+        _close(be.softmax_bwd(p_ref.cuda(), dp.cuda(), T), E.softmax_bwd(p_ref, dp, T), 2e-2, "softmax bwd")
+    # dropout: P_drop is P where kept (scaled), 0 where dropped, and backward uses the same mask
+    p_got, pd = be.softmax_fwd(s.cuda(), T, None, 0.25, 77)
+    kept = pd[..., :T].float() != 0
+    assert abs(kept.float().mean().item() - 0.75) < 0.02
+
+
+def test_colsum_gelu_dropout_cast(be):
+    x = _bf((1000, 3072), 1)
+    _close(be.colsum(x.cuda()), E.colsum(x), 2e-3, "colsum")
+    dy, z = _bf((300, 512), 2), _bf((300, 512), 3, 2.0)
+    _close(be.gelu_bwd(dy.cuda(), z.cuda()), E.gelu_bwd(dy, z), 2e-2, "gelu_bwd")
+    for t in (x, torch.randn(64, 512, generator=_g(4))):
+        d = be.dropout(t.cuda(), 0.1, 99)
+        kept = (d.float() != 0).float().mean().item()
+        assert abs(kept - 0.9) < 0.01
+        d2 = be.dropout(t.cuda(), 0.1, 99)
+        assert torch.equal(d, d2)
+        nz = d.float() != 0
+        _close(d.float()[nz], (t.cuda().float() / 0.9)[nz], 1e-2, "dropout scale")
+    f = torch.randn(513, 40, generator=_g(5))
+    assert torch.equal(be.cast(f.cuda(), torch.bfloat16).cpu(), f.to(torch.bfloat16))
+    for side in (False, True):
+        assert torch.equal(be.split3(f.cuda(), side).cpu(), E.split3(f, side))
+
+
+def test_log_softmax(be):
+    x = torch.randn(3, 50, 32, generator=_g(1)) * 3
+    y = be.log_softmax_fwd(x.cuda())
+    _close(y, torch.log_softmax(x, -1), 1e-5, "log_softmax fwd")
+    dy_tbv = torch.randn(50, 3, 32, generator=_g(2))  # CTC hands back [T,B,V]
+    got = be.log_softmax_bwd(dy_tbv.cuda().transpose(0, 1), y)
+    _close(got, E.log_softmax_bwd(dy_tbv.transpose(0, 1), torch.log_softmax(x, -1)), 2e-2, "log_softmax bwd")
+
+
+@pytest.mark.parametrize("B,L", [(2, 4000), (3, 16000)])
+def test_conv0(be, B, L):
+    C, k, s = 512, 10, 5
+    x = torch.randn(B, L, generator=_g(1)) * 0.1
+    w = (torch.rand(C, k, generator=_g(2)) * 2 - 1) * math.sqrt(3.0 / k)
+    gamma = 1 + 0.1 * torch.randn(C, generator=_g(3))
+    beta = 0.1 * torch.randn(C, generator=_g(4))
+    mean_r, rstd_r = E.conv0_stats(x, w, k, s, 1e-5)
+    mean, rstd = be.conv0_stats(x.cuda(), w.cuda(), k, s, 1e-5)
+    _close(mean, mean_r, 1e-4, "conv0 mean")
+    _close(rstd, rstd_r, 1e-4, "conv0 rstd")
+    y_r = E.conv0_fwd(x, w, gamma, beta, mean_r, rstd_r, k, s)
+    y = be.conv0_fwd(x.cuda(), w.cuda(), gamma.cuda(), beta.cuda(), mean, rstd, k, s)
+    _close(y, y_r, 1e-2, "conv0 fwd")
+    da = _bf(tuple(y_r.shape), 5)
+    ref = E.conv0_bwd(x, w, gamma, beta, mean_r, rstd_r, k, s, da)
+    got = be.conv0_bwd(x.cuda(), w.cuda(), gamma.cuda(), beta.cuda(), mean, rstd, k, s, da.cuda())
+    for g, r, name in zip(got, ref, ["dw", "dgamma", "dbeta"]):
+        _close(g, r, 5e-3, "conv0 bwd " + name)
+
+
+def test_rows_and_masks(be):
+    src = torch.randn(200, 96, generator=_g(1))
+    idx = torch.randperm(200, generator=_g(2))[:57].sort().values.int()
+    for dt in (torch.float32, torch.bfloat16):
+        assert torch.equal(be.rows_gather(src.cuda(), idx.cuda(), dt).cpu(), E.rows_gather(src, idx, dt))
+        rows = torch.randn(57, 96, generator=_g(3))
+        assert torch.equal(be.rows_scatter(rows.cuda(), idx.cuda(), 200, dt).cpu(), E.rows_scatter(rows, idx, 200, dt))
+    xb = _bf((200, 96), 4)
+    vec = torch.randn(96, generator=_g(5))
+    a, b = xb.clone().cuda(), xb.clone()
+    be.rows_set(a, idx.cuda(), vec.cuda())
+    E.rows_set(b, idx, vec)
+    assert torch.equal(a.cpu(), b)
+    a, b = xb.clone().cuda(), xb.clone()
+    _close(be.rows_set_bwd(a, idx.cuda()), E.rows_set_bwd(b, idx), 1e-3, "rows_set_bwd dvec")
+    assert torch.equal(a.cpu(), b)
+    x3 = _bf((4, 50, 96), 6)
+    rk = (torch.rand(4, 50, generator=_g(7)) > 0.3).to(torch.uint8)
+    cz = (torch.rand(4, 96, generator=_g(8)) > 0.8).to(torch.uint8)
+    for r_, c_ in ((rk, None), (None, cz), (rk, cz)):
+        a, b = x3.clone().cuda(), x3.clone()
+        be.mask_apply(a, r_.cuda() if r_ is not None else None, c_.cuda() if c_ is not None else None)
+        E.mask_apply(b, r_, c_)
+        assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_vq(be, train):
+    R, G, V, vd = 130, 2, 320, 128
+    z = torch.randn(R, G * V, generator=_g(1)) * 4
+    noise = -torch.empty(R * G, V).exponential_(generator=_g(2)).log() if train else None
+    vars2d = torch.rand(G * V, vd, generator=_g(3))
+    ref = E.vq_fwd(z, noise, 0.5, vars2d, G)
+    got = be.vq_fwd(z.cuda(), noise.cuda() if train else None, 0.5, vars2d.cuda(), G)
+    assert torch.equal(got[2].cpu(), ref[2]), "VQ arg-max indices must be bit-exact"
+    assert torch.equal(got[0].cpu(), ref[0]), "selected codewords must be an exact gather"
+    _close(got[3], ref[3], 1e-4, "avg_sums")
+    _close(got[4], ref[4], 1e-4, "ppl")
+    dq = torch.randn(R, G * vd, generator=_g(4))
+    a_dot = torch.einsum("rgd,gvd->rgv", dq.view(R, G, vd), vars2d.view(G, V, vd)).reshape(R, G * V)
+    dppl = torch.tensor(-10.0 / 640)
+    rb = E.vq_bwd(z, noise, 0.5, G, vd, a_dot, dq, ref[2], ref[3], ref[4], dppl)
+    gb = be.vq_bwd(z.cuda(), noise.cuda() if train else None, 0.5, G, vd, a_dot.cuda(), dq.cuda(), got[2], got[3],
+                   got[4], dppl.cuda())
+    _close(gb[0], rb[0], 2e-2, "vq dz")
+    _close(gb[1], rb[1], 1e-4, "vq dvars")
+
+
+def test_contrastive(be):
+    B, Tm, C, K = 3, 40, 256, 100
+    R = B * Tm
+    x, y = torch.randn(R, C, generator=_g(1)), torch.randn(R, C, generator=_g(2))
+    rng = np.random.RandomState(5)
+    own = np.repeat(np.arange(Tm), K)[None, :]
+    idx = rng.randint(0, Tm - 1, (B, K * Tm))
+    idx = np.where(idx >= own, idx + 1, idx) + (np.arange(B) * Tm)[:, None]
+    idx = torch.from_numpy(idx.astype(np.int32))
+    ppl = torch.tensor(123.4)
+    l_r, ce_r, sv_r = E.contrastive_fwd(x, y, idx, ppl, 640.0, 0.1, 10.0)
+    l_g, ce_g, sv_g = be.contrastive_fwd(x.cuda(), y.cuda(), idx.cuda(), ppl.cuda(), 640.0, 0.1, 10.0)
+    assert abs(l_g.item() - l_r.item()) < 1e-5 * abs(l_r.item()) and abs(ce_g.item() - ce_r.item()) < 1e-5 * ce_r.item()
+    dce = torch.tensor(0.1)
+    dx_r, dy_r = E.contrastive_bwd(x, y, idx, sv_r, dce)
+    dx_g, dy_g = be.contrastive_bwd(x.cuda(), y.cuda(), idx.cuda(), sv_g, dce.cuda())
+    _close(dx_g, dx_r, 1e-4, "contrastive dx")
+    _close(dy_g, dy_r, 1e-4, "contrastive dy")
