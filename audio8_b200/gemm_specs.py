@@ -21,6 +21,11 @@ def cdiv(a, b):
     return (a + b - 1) // b
 
 
+def _with_flops(spec, flops):
+    spec.flops = int(flops)
+    return spec
+
+
 def _pick_bn(N):
     return 64 if N <= 64 else (128 if N <= 128 else 256)
 
@@ -38,8 +43,8 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
     N = w.shape[0]
     a = Op(x, (K, M), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
-    return GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
-                    aux_mode=aux_mode, bias=bias)
+    return _with_flops(GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
+                                aux_mode=aux_mode, bias=bias), 2 * M * N * K)
 
 
 def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
@@ -48,7 +53,7 @@ def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     K = w.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
-    return GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode)
+    return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode), 2 * M * N * K)
 
 
 def linear_wgrad(dy, x, dw):
@@ -58,7 +63,7 @@ def linear_wgrad(dy, x, dw):
     a = Op(dy, (N, M), (N,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     b = Op(x, (K, M), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     kb = cdiv(M, 64)
-    return GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC, split_k=_split_k(N, K, kb))
+    return _with_flops(GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC, split_k=_split_k(N, K, kb)), 2 * M * N * K)
 
 
 # ------------------------------------------------------------------------------------------------ conv 1..6
@@ -69,8 +74,8 @@ def conv_fwd(x, wk, y, k, s, z_out=None, act=ACT_GELU):
     _, Lout, Cout = y.shape
     a = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, 0, 1, 0))
     b = Op(wk, (k * Cin, Cout), (k * Cin,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
-    return GemmSpec(a, b, Lout, Cout, k * Cin // 64, y, Cout, OUT_BF16, lo_count=B, c_stride_lo=Lout * Cout,
-                    act=act, z_out=z_out)
+    return _with_flops(GemmSpec(a, b, Lout, Cout, k * Cin // 64, y, Cout, OUT_BF16, lo_count=B,
+                                c_stride_lo=Lout * Cout, act=act, z_out=z_out), 2 * B * Lout * Cout * k * Cin)
 
 
 def conv_dgrad_taps(k, s, p):
@@ -88,9 +93,10 @@ def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
     a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_K, ck=(64, 0, 0, 0), cb=(0, -1, 0, 0), cr=(0, 1, 0, 0),
            cl=(0, 0, 1, 0))
     b = Op(wt_p, (ntaps * Cout, Cin), (ntaps * Cout,), MAJOR_K, ck=(64, 0, 0, 0), cb=(Cout, 0, 0, 0), cr=(0, 1, 0, 0))
-    return GemmSpec(a, b, U, Cin, ntaps * Cout // 64, dx, s * Cin, OUT_BF16, lo_count=B, k_inner=Cout // 64,
-                    c_offset=p * Cin, c_stride_lo=Lin * Cin, aux=aux,
-                    aux_mode=AUX_MUL_GELU_GRAD if aux is not None else AUX_NONE)
+    return _with_flops(GemmSpec(a, b, U, Cin, ntaps * Cout // 64, dx, s * Cin, OUT_BF16, lo_count=B,
+                                k_inner=Cout // 64, c_offset=p * Cin, c_stride_lo=Lin * Cin, aux=aux,
+                                aux_mode=AUX_MUL_GELU_GRAD if aux is not None else AUX_NONE),
+                       2 * B * U * Cin * ntaps * Cout)
 
 
 def conv_wgrad(dz, x, dwk, k, s):
@@ -100,8 +106,8 @@ def conv_wgrad(dz, x, dwk, k, s):
     a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
     b = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
     ki = cdiv(Lout, 64)
-    return GemmSpec(a, b, Cout, k * Cin, B * ki, dwk, k * Cin, OUT_F32_ATOMIC, k_inner=ki,
-                    split_k=_split_k(Cout, k * Cin, B * ki))
+    return _with_flops(GemmSpec(a, b, Cout, k * Cin, B * ki, dwk, k * Cin, OUT_F32_ATOMIC, k_inner=ki,
+                                split_k=_split_k(Cout, k * Cin, B * ki)), 2 * B * Lout * Cout * k * Cin)
 
 
 # ------------------------------------------------------------------------------------------------ pos conv
@@ -114,9 +120,9 @@ def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
     a = Op(x, (D, T, B), (D, T * D), MAJOR_K, base=(0, -pad_left, 0, 0), cb=(0, 1, 0, 0), cr=(0, 1, 0, 0),
            cl=(cg, 0, 0, 0), ch=(0, 0, 1, 0))
     b = Op(wp, (k * 64, D), (k * 64,), MAJOR_K, cb=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, cg, 0, 0))
-    return GemmSpec(a, b, T, cg, k, out, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
+    return _with_flops(GemmSpec(a, b, T, cg, k, out, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
                     c_stride_lo=cg, c_stride_hi=T * D, act=ACT_GELU, z_out=z_out, aux=x, aux_mode=AUX_ADD,
-                    bias=bias, bias_stride_lo=cg)
+                    bias=bias, bias_stride_lo=cg), 2 * B * T * D * cg * k)
 
 
 def posconv_dgrad(dz, wpt, dx, groups, k, pad_left, aux=None):
@@ -126,8 +132,8 @@ def posconv_dgrad(dz, wpt, dx, groups, k, pad_left, aux=None):
     a = Op(dz, (D, T, B), (D, T * D), MAJOR_K, base=(0, pad_left, 0, 0), cb=(0, -1, 0, 0), cr=(0, 1, 0, 0),
            cl=(cg, 0, 0, 0), ch=(0, 0, 1, 0))
     b = Op(wpt, (k * 64, D), (k * 64,), MAJOR_K, cb=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, cg, 0, 0))
-    return GemmSpec(a, b, T, cg, k, dx, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
-                    c_stride_lo=cg, c_stride_hi=T * D, aux=aux, aux_mode=AUX_ADD if aux is not None else AUX_NONE)
+    return _with_flops(GemmSpec(a, b, T, cg, k, dx, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
+                    c_stride_lo=cg, c_stride_hi=T * D, aux=aux, aux_mode=AUX_ADD if aux is not None else AUX_NONE), 2 * B * T * D * cg * k)
 
 
 def posconv_wgrad(dz, x, dwp, groups, k, pad_left):
@@ -138,8 +144,8 @@ def posconv_wgrad(dz, x, dwp, groups, k, pad_left):
            cr=(0, 1, 0, 0), cl=(cg, 0, 0, 0))
     b = Op(dz, (D, T, B), (D, T * D), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cl=(cg, 0, 0, 0))
     ki = cdiv(T, 64)
-    return GemmSpec(a, b, k * 64, 64, B * ki, dwp, 64, OUT_F32, lo_count=groups, k_inner=ki, block_n=64,
-                    c_stride_lo=k * 64 * 64)
+    return _with_flops(GemmSpec(a, b, k * 64, 64, B * ki, dwp, 64, OUT_F32, lo_count=groups, k_inner=ki, block_n=64,
+                    c_stride_lo=k * 64 * 64), 2 * B * T * D * cg * k)
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -180,46 +186,46 @@ def attn_scores(qkv, s_out, H, scale):
     B, T, D3 = qkv.shape
     Tp = s_out.shape[-1]
     dk = D3 // 3 // H
-    return GemmSpec(_qkv_op(qkv, 0, MAJOR_K, H), _qkv_op(qkv, 1, MAJOR_K, H), T, T, dk // 64, s_out, Tp, OUT_F32,
-                    lo_count=H, hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp, alpha=scale)
+    return _with_flops(GemmSpec(_qkv_op(qkv, 0, MAJOR_K, H), _qkv_op(qkv, 1, MAJOR_K, H), T, T, dk // 64, s_out, Tp, OUT_F32,
+                    lo_count=H, hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp, alpha=scale), 2 * B * H * T * T * dk)
 
 
 def attn_context(p, qkv, ctx, H):
     """ctx[b,:,h*64:(h+1)*64] = P[b,h] V[b,h]   (V read MN-major)"""
     B, T, D3 = qkv.shape
     D = D3 // 3
-    return GemmSpec(_score_op(p, MAJOR_K), _qkv_op(qkv, 2, MAJOR_MN, H), T, 64, cdiv(T, 64), ctx, D, OUT_BF16,
-                    lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D)
+    return _with_flops(GemmSpec(_score_op(p, MAJOR_K), _qkv_op(qkv, 2, MAJOR_MN, H), T, 64, cdiv(T, 64), ctx, D, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D), 2 * B * H * T * T * 64)
 
 
 def attn_dprobs(dctx, qkv, dp_out, H):
     """dP[b,h] = dctx[b,:,h] V[b,h]^T -> fp32 [B,H,T,Tp]"""
     B, T, D3 = qkv.shape
     Tp = dp_out.shape[-1]
-    return GemmSpec(_ctx_op(dctx, MAJOR_K), _qkv_op(qkv, 2, MAJOR_K, H), T, T, 1, dp_out, Tp, OUT_F32, lo_count=H,
-                    hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp)
+    return _with_flops(GemmSpec(_ctx_op(dctx, MAJOR_K), _qkv_op(qkv, 2, MAJOR_K, H), T, T, 1, dp_out, Tp, OUT_F32, lo_count=H,
+                    hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp), 2 * B * H * T * T * 64)
 
 
 def attn_dq(ds, qkv, dqkv, H, scale):
     """dQ = scale * dS K -> dqkv[..., 0:D]"""
     B, T, D3 = qkv.shape
-    return GemmSpec(_score_op(ds, MAJOR_K), _qkv_op(qkv, 1, MAJOR_MN, H), T, 64, cdiv(T, 64), dqkv, D3, OUT_BF16,
-                    lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D3, alpha=scale)
+    return _with_flops(GemmSpec(_score_op(ds, MAJOR_K), _qkv_op(qkv, 1, MAJOR_MN, H), T, 64, cdiv(T, 64), dqkv, D3, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D3, alpha=scale), 2 * B * H * T * T * 64)
 
 
 def attn_dk(ds, qkv, dqkv, H, scale):
     """dK = scale * dS^T Q -> dqkv[..., D:2D]"""
     B, T, D3 = qkv.shape
-    return GemmSpec(_score_op(ds, MAJOR_MN), _qkv_op(qkv, 0, MAJOR_MN, H), T, 64, cdiv(T, 64), dqkv, D3, OUT_BF16,
+    return _with_flops(GemmSpec(_score_op(ds, MAJOR_MN), _qkv_op(qkv, 0, MAJOR_MN, H), T, 64, cdiv(T, 64), dqkv, D3, OUT_BF16,
                     lo_count=H, hi_count=B, block_n=64, c_offset=D3 // 3, c_stride_lo=64, c_stride_hi=T * D3,
-                    alpha=scale)
+                    alpha=scale), 2 * B * H * T * T * 64)
 
 
 def attn_dv(p, dctx, dqkv, H):
     """dV = P^T dctx -> dqkv[..., 2D:3D]"""
     B, T, D = dctx.shape
-    return GemmSpec(_score_op(p, MAJOR_MN), _ctx_op(dctx, MAJOR_MN), T, 64, cdiv(T, 64), dqkv, 3 * D, OUT_BF16,
-                    lo_count=H, hi_count=B, block_n=64, c_offset=2 * D, c_stride_lo=64, c_stride_hi=T * 3 * D)
+    return _with_flops(GemmSpec(_score_op(p, MAJOR_MN), _ctx_op(dctx, MAJOR_MN), T, 64, cdiv(T, 64), dqkv, 3 * D, OUT_BF16,
+                    lo_count=H, hi_count=B, block_n=64, c_offset=2 * D, c_stride_lo=64, c_stride_hi=T * 3 * D), 2 * B * H * T * T * 64)
 
 
 # ------------------------------------------------------------------------------------------------ quantizer
@@ -230,4 +236,4 @@ def vq_codebook_dots(dq, vars2d, a_out, G):
     V = GV // G
     a = Op(dq, (G * vd, R), (G * vd,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(vd, 0, 0, 0))
     b = Op(vars2d, (vd, GV), (vd,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, V, 0, 0))
-    return GemmSpec(a, b, R, V, cdiv(vd, 64), a_out, GV, OUT_F32, lo_count=G, c_stride_lo=V)
+    return _with_flops(GemmSpec(a, b, R, V, cdiv(vd, 64), a_out, GV, OUT_F32, lo_count=G, c_stride_lo=V), 2 * R * GV * vd)

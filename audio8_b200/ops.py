@@ -45,6 +45,7 @@ class GemmSpec:
         self.c_stride_lo, self.c_stride_hi = c_stride_lo, c_stride_hi
         self.act, self.z_out, self.aux, self.aux_mode = act, z_out, aux, aux_mode
         self.bias, self.bias_stride_lo, self.alpha = bias, bias_stride_lo, alpha
+        self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
 
 
 def _stream():
@@ -64,6 +65,7 @@ class CudaBackend:
 
     def __init__(self):
         self.lib = _lib.load()
+        self.profiler = None  # bench.py installs a CUDA-event recorder around GEMM launches
 
     # ------------------------------------------------------------------ gemm
     @staticmethod
@@ -96,7 +98,11 @@ class CudaBackend:
             assert g.bias.dtype == torch.float32 and g.bias.is_cuda
             s.bias = g.bias.data_ptr()
         s.alpha = float(g.alpha)
+        if self.profiler is not None:
+            self.profiler.begin("gemm", g.flops)
         _lib.check(self.lib.a8_gemm(C.byref(s), _stream()), "a8_gemm")
+        if self.profiler is not None:
+            self.profiler.end()
 
 
     # ------------------------------------------------------------------ ctc

@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the wav2vec2-base contrastive pre-training step (BASELINE.json: configs[1], "C2" in SURVEY §8):
+fwd+bwd of `loss_function(model, inputs)` on synthetic 16 kHz audio, B=6 x 15 s crops per GPU, dropout 0.1
+(the reference's defaults), reported as audio-seconds/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+* our arm: audio8_b200 modules (hand-written sm_100a kernels through the C ABI); N>1 under torchrun with DDP/NCCL.
+* `--impl reference`: the reference algorithm on the host CPU cores (oracle port of audio8/wav2vec2.py — the
+  reference itself cannot be installed: its `mead-baseline` dependency is absent and there is no network), on a
+  bounded sample of the same workload.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 16000
+CROP_S = 15
+L = SAMPLE_RATE * CROP_S  # 240000 samples -> 749 frames
+B_PER_GPU = 6  # what AudioFileDataset emits for 15 s crops at tokens_per_batch=1.4M (data.py:417-426)
+N_VARS, N_NEG = 640, 100
+GFLOP_PER_AUDIO_S = 46.0  # algorithmic fwd+bwd, SURVEY §8(d)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+class GemmProfiler:
+    """CUDA events around every a8_gemm launch (on the launching stream)"""
+
+    def __init__(self):
+        self.pairs = []
+        self.cur = None
+
+    def begin(self, kind, flops):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.cur = (e0, e1, flops)
+
+    def end(self):
+        e0, e1, flops = self.cur
+        e1.record()
+        self.pairs.append((e0, e1, flops))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.pairs)
+        return ms, sum(f for _, _, f in self.pairs), len(self.pairs)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(threads):
+    """the reference algorithm (oracle port of audio8/wav2vec2.py:377-392, 927-952) fwd+bwd on the host CPU"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_params as P
+    import ref_wav2vec2 as R
+    torch.set_num_threads(threads)
+    sd = {k: v.requires_grad_(True) for k, v in P.pretrain_state_dict(seed=0).items()}
+    g = torch.Generator().manual_seed(0)
+
+    def step(batch):
+        x = torch.randn(batch, L, generator=g) * 0.1
+        T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+        tmask = R.create_mask((batch, T), 0.65, 10)
+        Tm = int(tmask[0].sum())
+        for _ in range(12):
+            np.random.random()
+        idx = R.sample_negative_indices(batch, Tm, N_NEG)
+        noise = -torch.empty(batch * Tm * 2, 320).exponential_().log()
+        st = R.pretrain_loss(sd, x, tmask, idx, n_vars=N_VARS, gumbel_noise=noise)
+        st["loss"].backward()
+        for v in sd.values():
+            v.grad = None
+        return st["loss"].item()
+
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    step = cpu_reference_step_fn(threads)
+    batch = 1  # bounded sample: one 15 s crop per step
+    for _ in range(args.warmup):
+        step(batch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(batch)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = batch * CROP_S / dt
+    out = {
+        "impl": "reference", "metric": "wav2vec2-base pretrain audio-sec/sec fwd+bwd", "value": v, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "wav2vec2-base contrastive pretrain fwd+bwd, G=2 V=320 K=100, 15 s crops, dropout 0 (oracle)",
+                   "batch_per_step": batch},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of B={batch} x {CROP_S} s on the host CPU (oracle port, fp32)"},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from audio8_b200 import _lib, ops
+    from audio8_b200 import wav2vec2 as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)
+    np.random.seed(1234 + rank)
+
+    model = W.create_model().to(dev)  # wav2vec2-base defaults: 12L d=768, dropout 0.1, G=2 V=320
+    model.train()
+    loss_fn = W.create_loss(N_VARS, N_NEG)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local)
+    B = B_PER_GPU
+    lib = _lib.load()
+    x_dev = torch.randn(B, L, device=dev) * 0.1
+    x_host = (torch.randn(B, L) * 0.1).pin_memory()
+
+    def step(x):
+        loss = loss_fn(net, x)
+        loss.backward()
+        for p in model.parameters():
+            p.grad = None
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    # ---- device-resident timing: exactly K steps between barriers, CUDA events, max over ranks
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = lib.a8_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    launches = lib.a8_launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * CROP_S / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host input -> device every step, loss read back every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step(x_host.to(dev, non_blocking=True))
+        loss_val = loss.item()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = world * B * CROP_S / (dt.item() / args.steps)
+
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of 2 further steps
+        prof = GemmProfiler()
+        ops.backend().profiler = prof
+        for _ in range(2):
+            step(x_dev)
+        gemm_ms, gemm_flops, n_gemm = prof.summary()
+        ops.backend().profiler = None
+        tf_peak, hbm_peak, which = peaks()
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cstep = cpu_reference_step_fn(threads)
+            cstep(1)
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                cstep(1)
+            cdt = (time.perf_counter() - t0) / reps
+            cpu = {"value": CROP_S / cdt, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                   "sample": f"{reps} steps of B=1 x {CROP_S} s (oracle port of the reference algorithm, fp32, dropout 0)"}
+        out = {
+            "metric": "wav2vec2-base pretrain audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "wav2vec2-base (12L d=768) contrastive pretrain fwd+bwd, G=2 V=320 K=100, dropout 0.1",
+                       "batch_per_gpu": B, "crop_s": CROP_S, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": 4,
+                    "last_loss": loss_val},
+            "gpu_launches": int(launches),
+            "gpu_launches_per_step": launches / args.steps,
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": which,
+                         "launches_per_step": n_gemm / 2, "gemm_ms_per_step": gemm_ms / 2,
+                         "gemm_share_of_step": (gemm_ms / 2) / ms_per_step,
+                         "algorithmic_gflop_per_step": gemm_flops / 2 / 1e9,
+                         "measured_on": "2 extra steps after the timed region, CUDA events around each launch",
+                         "model_frac_of_tensor_roofline": value / world * GFLOP_PER_AUDIO_S / 1e3 / tf_peak},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

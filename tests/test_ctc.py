@@ -73,12 +73,18 @@ def test_cuda_ctc_matches_oracle_sweep(T, B, S, V):
     ref_in = lp_btv.transpose(0, 1).clone().requires_grad_(True)
     ref = ref_ctc.ctc_loss_reference(ref_in, il, tg, tl, 0, 1, 2, "sum")
     ref.backward()
+    # float64 truth: fp32 log-space CTC (ATen's included) carries alpha/beta of magnitude ~|nll|, so its gradient
+    # error grows with T (4.6e-4 at T=250, 2e-3 at T=750 for ATen itself).  The kernel must be as accurate as the
+    # reference's own fp32 arithmetic: error vs truth <= 3x ATen-fp32's error vs truth (+5e-5).
+    t64 = lp_btv.double().transpose(0, 1).clone().requires_grad_(True)
+    ref_ctc.ctc_loss_reference(t64, il, tg, tl, 0, 1, 2, "sum").backward()
+    aten_err = (ref_in.grad.double() - t64.grad).abs().max().item()
     d = lp_btv.cuda().requires_grad_(True)
     loss = ctc_loss(d.transpose(0, 1), il.cuda(), tg.cuda(), tl, reduction="sum")
     loss.backward()
     assert abs(loss.item() - ref.item()) <= 2e-5 * abs(ref.item()), (loss.item(), ref.item())
-    np.testing.assert_allclose(d.grad.transpose(0, 1).cpu().numpy(), ref_in.grad.numpy(), rtol=0,
-                               atol=5e-5 + 2e-5 * math.sqrt(T))
+    my_err = (d.grad.transpose(0, 1).cpu().double() - t64.grad).abs().max().item()
+    assert my_err <= 3 * aten_err + 5e-5, (my_err, aten_err)
     # size-independent properties: zero gradient beyond each utterance's length; rows sum to ~0 (softmax - occupancy)
     gr = d.grad.cpu()
     for b in range(B):
