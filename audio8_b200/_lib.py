@@ -71,6 +71,11 @@ SIGNATURES.update({
     "a8_vq_fwd": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "a8_vq_bwd": (_I, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "a8_contrastive_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_cast_multi": (_I, [_P, _I, _P]),
+    "a8_conv_pack": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "a8_conv_unpack": (_I, [_P, _I, _I, _I, _P, _P]),
+    "a8_posconv_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "a8_posconv_wn_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
 })
 

@@ -396,20 +396,38 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const SmBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* x, long long ld, int R, int C,
                                                      int rows_per_block, float* out) {
-  // thread = one 8-column chunk (blockIdx.y selects the 2048-column slab), loops over this CTA's rows
-  const int c = (blockIdx.y * 256 + threadIdx.x) * 8;
-  if (c >= C) return;
+  // 64 column-octets x 4 row phases per CTA (512 columns, blockIdx.y selects the slab); each thread streams its
+  // rows with 4 independent 16-byte loads in flight, phases are reduced in smem, one atomic per column per CTA
+  __shared__ float red[4][64 * 8];
+  const int oct = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int c = (blockIdx.y * 64 + oct) * 8;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int r = r0; r < r1; ++r) {
-    float v[8];
-    load8(x + (long long)r * ld + c, v);
+  if (c < C) {
+    int r = r0 + ph;
+    for (; r + 12 < r1; r += 16) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8(x + (long long)r * ld + c, v0);
+      load8(x + (long long)(r + 4) * ld + c, v1);
+      load8(x + (long long)(r + 8) * ld + c, v2);
+      load8(x + (long long)(r + 12) * ld + c, v3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; r < r1; r += 4) {
+      float v[8];
+      load8(x + (long long)r * ld + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (c + j < C) atomicAdd(out + c + j, acc[j]);
+  for (int j = 0; j < 8; ++j) red[ph][oct * 8 + j] = acc[j];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 512; e += 256) {
+    const int cc = blockIdx.y * 512 + e;
+    if (cc < C) atomicAdd(out + cc, red[0][e] + red[1][e] + red[2][e] + red[3][e]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,9 +588,10 @@ extern "C" int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pd
 extern "C" int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0, "colsum: bad shape R=%d C=%d ld=%lld", R, C, (long long)ld);
-  const int slabs = cdiv(C, 2048);
-  int rpb = cdiv(R, cdiv(148 * 4, slabs));
-  rpb = rpb < 16 ? 16 : rpb;
+  const int slabs = cdiv(C, 512);
+  int chunks = cdiv(148 * 4, slabs);  // ~4 CTAs per SM over the whole grid
+  int rpb = cdiv(R, chunks);
+  rpb = rpb < 32 ? 32 : rpb;
   dim3 grid(cdiv(R, rpb), slabs);
   colsum_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, R, C, rpb, out);
   return check_launch("colsum_kernel");

@@ -196,17 +196,6 @@ class MaskApplyFn(torch.autograd.Function):
 # =================================================================================================
 # conv feature encoder (wav2vec2.py:399-456)
 # =================================================================================================
-def _conv_pack(w):
-    """[Cout, Cin, k] fp32 -> bf16 [Cout, k*Cin] (contraction index = tap*Cin + channel)"""
-    return _bf16(w.detach().permute(0, 2, 1).reshape(w.shape[0], -1))
-
-
-def _conv_pack_t(w, s, p):
-    """[Cout, Cin, k] -> bf16 [Cin, ntaps*Cout] for the phase-p data-gradient GEMM"""
-    taps = G.conv_dgrad_taps(w.shape[2], s, p)
-    return _bf16(torch.cat([w.detach()[:, :, j].t() for j in taps], 1))
-
-
 class ConvFeatureFn(torch.autograd.Function):
     """x fp32 [B,L] -> bf16 [B,T,C] channels-last.  Layer 0 = fused conv+GroupNorm+GELU kernels (csrc/conv0.cu),
     layers 1.. = implicit-GEMM tcgen05 convs with GELU epilogues (zero-copy im2col through overlapping TMA rows)."""
@@ -218,26 +207,30 @@ class ConvFeatureFn(torch.autograd.Function):
         (c0, k0, s0) = spec[0]
         w0 = weights[0].detach().reshape(c0, k0).contiguous()
         gw, gb = gn_w.detach(), gn_b.detach()
+        need_grad = any(ctx.needs_input_grad)
         mean, rstd = be.conv0_stats(x, w0, k0, s0, 1e-5)
         a = be.conv0_fwd(x, w0, gw, gb, mean, rstd, k0, s0)
-        acts, zs = [a], [None]
+        acts, zs, wts = [a], [None], [None]
         for i in range(1, len(spec)):
             (c, k, s) = spec[i]
             B, Lin, Cin = a.shape
             Lout = (Lin - k) // s + 1
+            wk, wt = be.conv_pack(weights[i].detach().contiguous(), s, need_grad)
             y = _empty((B, Lout, c), BF16, a)
-            z = _empty((B, Lout, c), BF16, a) if any(ctx.needs_input_grad) else None
-            be.gemm(G.conv_fwd(a, _conv_pack(weights[i]), y, k, s, z_out=z))
+            z = _empty((B, Lout, c), BF16, a) if need_grad else None
+            be.gemm(G.conv_fwd(a, wk, y, k, s, z_out=z))
             acts.append(y)
             zs.append(z)
+            wts.append(wt)
             a = y
-        ctx.saved = (x, w0, gw, gb, mean, rstd, acts, zs, [w.detach() for w in weights], spec)
+        if need_grad:
+            ctx.saved = (x, w0, gw, gb, mean, rstd, acts, zs, wts, spec)
         return a
 
     @staticmethod
     def backward(ctx, dy):
         be = _be()
-        x, w0, gw, gb, mean, rstd, acts, zs, weights, spec = ctx.saved
+        x, w0, gw, gb, mean, rstd, acts, zs, wts, spec = ctx.saved
         n = len(spec)
         grads = [None] * n
         if n > 1:
@@ -245,14 +238,15 @@ class ConvFeatureFn(torch.autograd.Function):
             for i in range(n - 1, 0, -1):
                 (c, k, s) = spec[i]
                 a_prev = acts[i - 1]
-                dwk = _zeros((c, k * a_prev.shape[2]), F32, a_prev)
+                Cin = a_prev.shape[2]
+                dwk = _zeros((c, k * Cin), F32, a_prev)
                 be.gemm(G.conv_wgrad(dz, a_prev, dwk, k, s))
-                grads[i] = dwk.view(c, k, a_prev.shape[2]).permute(0, 2, 1)
+                grads[i] = be.conv_unpack(dwk, Cin, k)
                 dprev = _empty(a_prev.shape, BF16, a_prev)
                 for p in range(s):
-                    be.gemm(G.conv_dgrad(dz, _conv_pack_t(weights[i], s, p), dprev, k, s, p,
-                                         aux=zs[i - 1] if i > 1 else None))
+                    be.gemm(G.conv_dgrad(dz, wts[i][p], dprev, k, s, p, aux=zs[i - 1] if i > 1 else None))
                 dz = dprev  # for i == 1 this is dL/d(a0), the gradient w.r.t. layer 0's GELU output
+                acts[i] = zs[i] = None
             da0 = dz
         else:
             da0 = _bf16(dy)
@@ -265,58 +259,82 @@ class ConvFeatureFn(torch.autograd.Function):
 # =================================================================================================
 # transformer encoder with positional conv (wav2vec2.py:579-646 + eight_mile TransformerEncoderStack)
 # =================================================================================================
-def _posconv_pack(w, groups, transpose):
-    """w [D, cg, k] fp32 -> bf16 [D, k*64]: row = output (input if transpose) channel, column = tap*64 + channel
-    of the same group, zero padded from cg to 64"""
-    D, cg, k = w.shape
-    wg = w.detach().view(groups, cg, cg, k)
-    if transpose:
-        wg = wg.permute(0, 2, 1, 3)
-    out = torch.zeros(groups, cg, k, 64, dtype=F32, device=w.device)
-    out[..., :cg] = wg.permute(0, 1, 3, 2)
-    return _bf16(out.reshape(D, k * 64))
+def _prepare_layer_weights(be, arena, lw, per_layer):
+    """one launch: every transformer GEMM weight fp32 -> bf16 into a persistent arena (w_Q|w_K|w_V land in one fused
+    [3D,D] operand, their biases in one fp32 [3D] vector).  Values are rewritten on every call; only the buffers and
+    the device-side pointer table persist."""
+    nl = len(lw) // per_layer
+    D = lw[0].shape[1]
+    F_ = lw[10].shape[0]
+    dev = lw[0].device
+    sig = (nl, D, F_, dev)
+    if arena.get("shape") != sig:
+        per = 4 * D * D + 2 * F_ * D
+        wbuf = torch.empty(nl * per, dtype=BF16, device=dev)
+        bbuf = torch.empty(nl * 3 * D, dtype=F32, device=dev)
+        views, dsts = [], []
+        for li in range(nl):
+            o = li * per
+            wqkv = wbuf[o:o + 3 * D * D].view(3 * D, D)
+            wo = wbuf[o + 3 * D * D:o + 4 * D * D].view(D, D)
+            w1 = wbuf[o + 4 * D * D:o + 4 * D * D + F_ * D].view(F_, D)
+            w2 = wbuf[o + 4 * D * D + F_ * D:o + per].view(D, F_)
+            bqkv = bbuf[li * 3 * D:(li + 1) * 3 * D]
+            views.append((wqkv, wo, w1, w2, bqkv))
+            dsts.append([wqkv[0:D], wqkv[D:2 * D], wqkv[2 * D:], wo, w1, w2, bqkv[0:D], bqkv[D:2 * D], bqkv[2 * D:]])
+        arena.update(shape=sig, wbuf=wbuf, bbuf=bbuf, views=views, dsts=dsts, cache={})
+    pairs = []
+    for li in range(nl):
+        (wq, bq, wk, bk, wv, bv, wo, _bo, _g2, _b2, w1, _b1, w2, _bb2, _g1, _b1l) = lw[li * per_layer:(li + 1) * per_layer]
+        srcs = [wq, wk, wv, wo, w1, w2, bq, bk, bv]
+        pairs += [(sv.detach(), d) for sv, d in zip(srcs, arena["dsts"][li])]
+    be.cast_multi(pairs, arena["cache"])
+    return arena["views"]
 
 
 class EncoderFn(torch.autograd.Function):
     """AudioTransformerEncoder.extract_features:  x (+pad zeroing) -> x + gelu(pos_conv(x)) -> LN -> dropout ->
     num_layers x post-LN transformer layer.  Per layer the parameters arrive as
-    (w_qkv [3D,D], b_qkv, w_o, b_o, ln2_g, ln2_b, w_1 [F,D], b_1, w_2 [D,F], b_2, ln1_g, ln1_b)."""
+    (w_Q, b_Q, w_K, b_K, w_V, b_V, w_O, b_O, ln2_g, ln2_b, w_1 [F,D], b_1, w_2 [D,F], b_2, ln1_g, ln1_b)."""
 
-    N_FRONT = 5  # pos_w, pos_b, ln_g, ln_b + row_keep placeholder handled separately
-    PER_LAYER = 12
+    PER_LAYER = 16
 
     @staticmethod
-    def forward(ctx, x, cfg, row_keep, pos_w, pos_b, ln_g, ln_b, *lw):
+    def forward(ctx, x, cfg, row_keep, pos_g, pos_v, pos_b, ln_g, ln_b, *lw):
         be = _be()
         H, groups, pdrop, training, active = cfg["num_heads"], cfg["groups"], cfg["pdrop"], cfg["training"], cfg["active"]
+        PL = EncoderFn.PER_LAYER
         p = pdrop if training else 0.0
         x = _bf16(x)
         B, T, D = x.shape
         M = B * T
         if D % (8 * groups) != 0 or (D // H) % 64 != 0:
             raise ValueError(f"d_model={D}, heads={H}: this build needs d_model % {8 * groups} == 0 and d_k % 64 == 0")
-        k = pos_w.shape[-1]
+        k = pos_v.shape[-1]
         pad_l = k // 2 - 1 if k % 2 == 0 else k // 2
         if row_keep is not None:
             x = x.clone()
             be.mask_apply(x, row_keep, None)
         need_grad = any(ctx.needs_input_grad)
+        pg, pv = pos_g.detach().contiguous(), pos_v.detach().contiguous()
+        wp, wpt, norm2 = be.posconv_pack(pg, pv, need_grad)
         s0 = _empty(x.shape, BF16, x)
         z0 = _empty(x.shape, BF16, x)
-        be.gemm(G.posconv_fwd(x, _posconv_pack(pos_w, groups, False), s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
+        be.gemm(G.posconv_fwd(x, wp, s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
         seed0 = next_seed() if p > 0 else 0
         h, _, _, mean0, rstd0 = be.layernorm_fwd(s0, ln_g.detach(), ln_b.detach(), 1e-5, p_y=p, seed_y=seed0)
         Tp = (T + 7) // 8 * 8
         scale = 1.0 / math.sqrt(D // H)
+        wviews = _prepare_layer_weights(be, cfg["arena"], lw, PL) if len(lw) else []
         layers = []
-        for li in range(len(lw) // EncoderFn.PER_LAYER):
+        for li in range(len(lw) // PL):
             if not active[li]:
                 layers.append(None)
                 continue
-            (wqkv, bqkv, wo, bo, g2, b2, w1, b1, w2, bb2, g1, b1ln) = (t.detach() for t in
-                                                                      lw[li * 12:(li + 1) * 12])
-            F_ = w1.shape[0]
-            wqkv_b, wo_b, w1_b, w2_b = _bf16(wqkv), _bf16(wo), _bf16(w1), _bf16(w2)
+            (_wq, _bq, _wk, _bk, _wv, _bv, _wo, bo, g2, b2, _w1, b1, _w2, bb2, g1, b1ln) = (
+                t.detach() for t in lw[li * PL:(li + 1) * PL])
+            wqkv_b, wo_b, w1_b, w2_b, bqkv = wviews[li]
+            F_ = w1_b.shape[0]
             xin = h
             x2d = xin.view(M, D)
             qkv = _empty((B, T, 3 * D), BF16, x)
@@ -346,14 +364,15 @@ class EncoderFn(torch.autograd.Function):
                                    w=(wqkv_b, wo_b, w1_b, w2_b), ln=(g2, g1)))
         if need_grad:
             ctx.saved = dict(x=x, s0=s0, z0=z0, mean0=mean0, rstd0=rstd0, seed0=seed0, ln_g=ln_g.detach(),
-                             pos_w=pos_w.detach(), layers=layers, row_keep=row_keep, p=p, H=H, groups=groups,
-                             k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw))
+                             pg=pg, pv=pv, norm2=norm2, wpt=wpt, layers=layers, row_keep=row_keep, p=p, H=H,
+                             groups=groups, k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw))
         return h
 
     @staticmethod
     def backward(ctx, dh):
         be = _be()
         sv = ctx.saved
+        PL = EncoderFn.PER_LAYER
         p, H, Tp, scale = sv["p"], sv["H"], sv["Tp"], sv["scale"]
         x = sv["x"]
         B, T, D = x.shape
@@ -368,26 +387,32 @@ class EncoderFn(torch.autograd.Function):
             g2, g1 = L["ln"]
             seed_a, seed1, seed2 = L["seeds"]
             F_ = w1_b.shape[0]
+            # every fp32 accumulator of this layer's backward comes from ONE zero-filled buffer (one fill launch)
+            sizes = [3 * D * D, D * D, F_ * D, D * F_, 3 * D, 3 * D, F_, 3 * D]
+            zbuf = _zeros((sum(sizes),), F32, x)
+            parts, o = [], 0
+            for n_ in sizes:
+                parts.append(zbuf[o:o + n_])
+                o += n_
+            dwqkv, dwo, dw1, dw2 = parts[0].view(3 * D, D), parts[1].view(D, D), parts[2].view(F_, D), parts[3].view(D, F_)
+            acc1, acc2, db1, dbqkv = parts[4].view(3, D), parts[5].view(3, D), parts[6], parts[7]
             # ---- ln1( x1 + drop(ffn) )
             ds2, df, dg1, db1ln, dbias2 = be.layernorm_bwd(dcur, L["s2"], L["mean1"], L["rstd1"], g1, want_dh=p > 0,
-                                                           p_h=p, seed_h=seed2, want_dbias=True)
+                                                           p_h=p, seed_h=seed2, want_dbias=True, acc=acc1)
             if df is None:
                 df = ds2
-            dw2 = _zeros((D, F_), F32, x)
             be.gemm(G.linear_wgrad(df, L["hid"], dw2))
             dz1 = _empty((M, F_), BF16, x)
             be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL_GELU_GRAD))
-            db1 = be.colsum(dz1)
-            dw1 = _zeros((F_, D), F32, x)
+            db1 = be.colsum(dz1, out=db1)
             be.gemm(G.linear_wgrad(dz1, L["x1"], dw1))
             dx1 = _empty((M, D), BF16, x)
             be.gemm(G.linear_dgrad(dz1, w1_b, dx1, aux=ds2, aux_mode=AUX_ADD))
             # ---- ln2( x + drop(attn) )
             ds1, da, dg2, db2ln, dbo = be.layernorm_bwd(dx1, L["s1"], L["mean2"], L["rstd2"], g2, want_dh=p > 0,
-                                                        p_h=p, seed_h=seed1, want_dbias=True)
+                                                        p_h=p, seed_h=seed1, want_dbias=True, acc=acc2)
             if da is None:
                 da = ds1
-            dwo = _zeros((D, D), F32, x)
             be.gemm(G.linear_wgrad(da, L["ctx"].view(M, D), dwo))
             dctx = _empty((B, T, D), BF16, x)
             be.gemm(G.linear_dgrad(da, wo_b, dctx.view(M, D)))
@@ -400,13 +425,13 @@ class EncoderFn(torch.autograd.Function):
             be.gemm(G.attn_dk(dS, L["qkv"], dqkv, H, scale))
             be.gemm(G.attn_dv(L["Pd"] if L["Pd"] is not None else L["P"], dctx, dqkv, H))
             dqkv2 = dqkv.view(M, 3 * D)
-            dbqkv = be.colsum(dqkv2)
-            dwqkv = _zeros((3 * D, D), F32, x)
+            dbqkv = be.colsum(dqkv2, out=dbqkv)
             be.gemm(G.linear_wgrad(dqkv2, L["xin"], dwqkv))
             dxin = _empty((M, D), BF16, x)
             be.gemm(G.linear_dgrad(dqkv2, wqkv_b, dxin, aux=ds1, aux_mode=AUX_ADD))
             dcur = dxin
-            lgrads[li * 12:(li + 1) * 12] = [dwqkv, dbqkv, dwo, dbo, dg2, db2ln, dw1, db1, dw2, dbias2, dg1, db1ln]
+            lgrads[li * PL:(li + 1) * PL] = [dwqkv[0:D], dbqkv[0:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:],
+                                             dbqkv[2 * D:], dwo, dbo, dg2, db2ln, dw1, db1, dw2, dbias2, dg1, db1ln]
             sv["layers"][li] = None  # free this layer's activations
         # ---- front: LN(+dropout) <- x + gelu(pos_conv(x))
         ds0, _, dlg, dlb, _ = be.layernorm_bwd(dcur.view(B, T, D), sv["s0"], sv["mean0"], sv["rstd0"], sv["ln_g"],
@@ -414,15 +439,14 @@ class EncoderFn(torch.autograd.Function):
         dz0 = be.gelu_bwd(ds0, sv["z0"])
         dpos_b = be.colsum(dz0)
         groups, k, pad_l = sv["groups"], sv["k"], sv["pad_l"]
-        cg = D // groups
         dwp = _empty((groups, k * 64, 64), F32, x)
         be.gemm(G.posconv_wgrad(dz0, x, dwp, groups, k, pad_l))
-        dpos_w = dwp.view(groups, k, 64, 64)[:, :, :cg, :cg].permute(0, 3, 2, 1).reshape(D, cg, k)
+        dpos_v, dpos_g = be.posconv_wn_bwd(dwp, sv["pg"], sv["pv"], sv["norm2"])
         dx = _empty((B, T, D), BF16, x)
-        be.gemm(G.posconv_dgrad(dz0, _posconv_pack(sv["pos_w"], groups, True), dx, groups, k, pad_l, aux=ds0))
+        be.gemm(G.posconv_dgrad(dz0, sv["wpt"], dx, groups, k, pad_l, aux=ds0))
         if sv["row_keep"] is not None:
             be.mask_apply(dx, sv["row_keep"], None)
-        return (dx, None, None, dpos_w, dpos_b, dlg, dlb, *lgrads)
+        return (dx, None, None, dpos_g, dpos_v, dpos_b, dlg, dlb, *lgrads)
 
 
 # =================================================================================================

@@ -14,7 +14,48 @@ Reference call sites replaced (under /root/reference/audio8):
 from .ops import (ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, MAJOR_K, MAJOR_MN, OUT_BF16, OUT_F32,
                   OUT_F32_ATOMIC, GemmSpec, Op)
 
+import functools
+
+import torch
+
 NUM_SMS = 148
+
+
+class BoundSpec:
+    """A builder call frozen by argument signature: the C struct is built once per (builder, shapes, strides,
+    scalars) and only the pointer fields are refreshed on later calls (host-side launch cost ~5 us, not ~30)."""
+
+    __slots__ = ("cache", "key", "builder", "args", "kwargs")
+
+    def __init__(self, cache, key, builder, args, kwargs):
+        self.cache, self.key, self.builder, self.args, self.kwargs = cache, key, builder, args, kwargs
+
+    def spec(self):
+        return self.builder(*self.args, **self.kwargs)
+
+    def tensors(self):
+        return [a for a in self.args if isinstance(a, torch.Tensor)] + \
+               [v for v in self.kwargs.values() if isinstance(v, torch.Tensor)]
+
+
+def _sig(v):
+    if isinstance(v, torch.Tensor):
+        return (v.shape, v.stride(), v.dtype)
+    return v
+
+
+def cached_spec(builder):
+    cache = {}
+
+    @functools.wraps(builder)
+    def wrapper(*args, **kwargs):
+        key = tuple(_sig(a) for a in args)
+        if kwargs:
+            key += tuple((k, _sig(v)) for k, v in sorted(kwargs.items()))
+        return BoundSpec(cache, key, builder, args, kwargs)
+
+    wrapper.raw = builder
+    return wrapper
 
 
 def cdiv(a, b):
@@ -37,6 +78,7 @@ def _split_k(M, N, k_blocks, batch=1):
 
 
 # ------------------------------------------------------------------------------------------------ linear
+@cached_spec
 def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     """out[M,N] = act(x[M,K] w[N,K]^T + bias) (+ aux)."""
     M, K = x.shape
@@ -47,6 +89,7 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
                                 aux_mode=aux_mode, bias=bias), 2 * M * N * K)
 
 
+@cached_spec
 def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | + aux)."""
     M, N = dy.shape
@@ -56,6 +99,7 @@ def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode), 2 * M * N * K)
 
 
+@cached_spec
 def linear_wgrad(dy, x, dw):
     """dw[N,K] (fp32, zeroed by the caller) += dy[M,N]^T x[M,K]; both operands read MN-major, split-K."""
     M, N = dy.shape
@@ -67,6 +111,7 @@ def linear_wgrad(dy, x, dw):
 
 
 # ------------------------------------------------------------------------------------------------ conv 1..6
+@cached_spec
 def conv_fwd(x, wk, y, k, s, z_out=None, act=ACT_GELU):
     """y[b,t,:] = act( sum_{j,c} x[b, s*t+j, c] wk[:, j*C+c] ).  x [B,Lin,C], wk [Cout, k*C], y [B,Lout,Cout].
     The A operand is a tensor map with OVERLAPPING rows (row pitch s*C, row length k*C): zero-copy im2col."""
@@ -83,6 +128,7 @@ def conv_dgrad_taps(k, s, p):
     return [j for j in range(k) if j % s == p]
 
 
+@cached_spec
 def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
     """dx[b, s*u+p, :] = sum_{i, co} dz[b, u-i, co] wt_p[:, i*Cout+co]  (* gelu'(aux[b, s*u+p, :])).
     dz [B,Lout,Cout], wt_p [Cin, ntaps*Cout], dx [B,Lin,Cin]; one launch per phase p of the stride."""
@@ -99,6 +145,7 @@ def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
                        2 * B * U * Cin * ntaps * Cout)
 
 
+@cached_spec
 def conv_wgrad(dz, x, dwk, k, s):
     """dwk[co, j*C+c] (fp32, zeroed) += sum_{b,t} dz[b,t,co] x[b, s*t+j, c]; contraction over (b,t), split-K."""
     B, Lout, Cout = dz.shape
@@ -111,6 +158,7 @@ def conv_wgrad(dz, x, dwk, k, s):
 
 
 # ------------------------------------------------------------------------------------------------ pos conv
+@cached_spec
 def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
     """out = x + gelu(conv_same(x) + bias) for the grouped positional conv.  x/out [B,T,D]; wp [D, k*64] packed
     (row = output channel, column j*64+ci, ci >= D/groups zero).  One k-block per tap: the A tile is 64
@@ -125,6 +173,7 @@ def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
                     bias=bias, bias_stride_lo=cg), 2 * B * T * D * cg * k)
 
 
+@cached_spec
 def posconv_dgrad(dz, wpt, dx, groups, k, pad_left, aux=None):
     """dx[b,t,g*cg+ci] = sum_{j,co} dz[b, t+pad_left-j, g*cg+co] wpt[g*cg+ci, j*64+co]  (+ aux)."""
     B, T, D = dz.shape
@@ -136,6 +185,7 @@ def posconv_dgrad(dz, wpt, dx, groups, k, pad_left, aux=None):
                     c_stride_lo=cg, c_stride_hi=T * D, aux=aux, aux_mode=AUX_ADD if aux is not None else AUX_NONE), 2 * B * T * D * cg * k)
 
 
+@cached_spec
 def posconv_wgrad(dz, x, dwp, groups, k, pad_left):
     """dwp[g][j*64+ci][co] (fp32 [groups, k*64, 64]) = sum_{b,t} x[b, t+j-pad_left, g*cg+ci] dz[b,t,g*cg+co]."""
     B, T, D = dz.shape
@@ -181,6 +231,7 @@ def _score_op(p, major):
               cl=(0, 0, 1, 0), ch=(0, 0, 0, 1))
 
 
+@cached_spec
 def attn_scores(qkv, s_out, H, scale):
     """S[b,h] = scale * Q K^T  -> fp32 [B,H,T,Tp]"""
     B, T, D3 = qkv.shape
@@ -190,6 +241,7 @@ def attn_scores(qkv, s_out, H, scale):
                     lo_count=H, hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp, alpha=scale), 2 * B * H * T * T * dk)
 
 
+@cached_spec
 def attn_context(p, qkv, ctx, H):
     """ctx[b,:,h*64:(h+1)*64] = P[b,h] V[b,h]   (V read MN-major)"""
     B, T, D3 = qkv.shape
@@ -198,6 +250,7 @@ def attn_context(p, qkv, ctx, H):
                     lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D), 2 * B * H * T * T * 64)
 
 
+@cached_spec
 def attn_dprobs(dctx, qkv, dp_out, H):
     """dP[b,h] = dctx[b,:,h] V[b,h]^T -> fp32 [B,H,T,Tp]"""
     B, T, D3 = qkv.shape
@@ -206,6 +259,7 @@ def attn_dprobs(dctx, qkv, dp_out, H):
                     hi_count=B, c_stride_lo=T * Tp, c_stride_hi=H * T * Tp), 2 * B * H * T * T * 64)
 
 
+@cached_spec
 def attn_dq(ds, qkv, dqkv, H, scale):
     """dQ = scale * dS K -> dqkv[..., 0:D]"""
     B, T, D3 = qkv.shape
@@ -213,6 +267,7 @@ def attn_dq(ds, qkv, dqkv, H, scale):
                     lo_count=H, hi_count=B, block_n=64, c_stride_lo=64, c_stride_hi=T * D3, alpha=scale), 2 * B * H * T * T * 64)
 
 
+@cached_spec
 def attn_dk(ds, qkv, dqkv, H, scale):
     """dK = scale * dS^T Q -> dqkv[..., D:2D]"""
     B, T, D3 = qkv.shape
@@ -221,6 +276,7 @@ def attn_dk(ds, qkv, dqkv, H, scale):
                     alpha=scale), 2 * B * H * T * T * 64)
 
 
+@cached_spec
 def attn_dv(p, dctx, dqkv, H):
     """dV = P^T dctx -> dqkv[..., 2D:3D]"""
     B, T, D = dctx.shape
@@ -229,6 +285,7 @@ def attn_dv(p, dctx, dqkv, H):
 
 
 # ------------------------------------------------------------------------------------------------ quantizer
+@cached_spec
 def vq_codebook_dots(dq, vars2d, a_out, G):
     """a[r, g*V+v] = sum_d dq[r, g*vd+d] vars[g*V+v, d]   (dq bf16 [R,G*vd], vars bf16 [G*V,vd], a fp32 [R,G*V])"""
     R = dq.shape[0]

@@ -49,13 +49,21 @@ class GemmSpec:
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw cudaStream_t of torch's current stream on the current device (cheaper than current_stream().cuda_stream)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def _ptr(t, offset_elems=0):
+    """device address as a plain int (ctypes converts it for c_void_p parameters); None stays NULL"""
     if t is None:
         return None
-    return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+    return t.data_ptr() + offset_elems * t.element_size()
+
+
+class _FrozenGemm:
+    """prebuilt a8_gemm_t + the recipe to refresh its pointer fields from a call's tensor arguments"""
+
+    __slots__ = ("struct", "ref", "slots", "flops")
 
 
 class CudaBackend:
@@ -82,6 +90,64 @@ class CudaBackend:
         return s
 
     def gemm(self, g):
+        if not isinstance(g, GemmSpec):
+            return self._gemm_bound(g)
+        self._gemm_spec(g)
+
+    def _gemm_bound(self, b):
+        fz = b.cache.get(b.key)
+        tens = b.tensors()
+        if fz is None:
+            spec = b.spec()
+            st = self._fill(spec)
+            fz = _FrozenGemm()
+            fz.struct, fz.flops = st, spec.flops
+            fz.ref = C.byref(st)
+            # pointer field -> (index of the argument tensor that owns it, byte offset from that tensor's data_ptr)
+            fields = [("a", spec.a.t, st.a.ptr), ("b", spec.b.t, st.b.ptr), ("c", spec.c, st.c), ("z", spec.z_out, st.z_out),
+                      ("x", spec.aux, st.aux), ("s", spec.bias, st.bias)]
+            fz.slots = []
+            for name, t, val in fields:
+                if t is None:
+                    continue
+                owner = [i for i, u in enumerate(tens) if u is t]
+                if not owner:  # the builder derived a new tensor: cannot be frozen
+                    fz = None
+                    break
+                fz.slots.append((name, owner[0], val - t.data_ptr()))
+            if fz is None:
+                return self._gemm_spec(spec)
+            b.cache[b.key] = fz
+        st = fz.struct
+        for name, i, delta in fz.slots:
+            p = tens[i].data_ptr() + delta
+            if name == "a":
+                st.a.ptr = p
+            elif name == "b":
+                st.b.ptr = p
+            elif name == "c":
+                st.c = p
+            elif name == "z":
+                st.z_out = p
+            elif name == "x":
+                st.aux = p
+            else:
+                st.bias = p
+        if self.profiler is not None:
+            self.profiler.begin("gemm", fz.flops)
+        _lib.check(self.lib.a8_gemm(fz.ref, _stream()), "a8_gemm")
+        if self.profiler is not None:
+            self.profiler.end()
+
+    def _gemm_spec(self, g):
+        s = self._fill(g)
+        if self.profiler is not None:
+            self.profiler.begin("gemm", g.flops)
+        _lib.check(self.lib.a8_gemm(C.byref(s), _stream()), "a8_gemm")
+        if self.profiler is not None:
+            self.profiler.end()
+
+    def _fill(self, g):
         s = _lib.Gemm()
         s.a, s.b = self._operand(g.a), self._operand(g.b)
         s.M, s.N, s.lo_count, s.hi_count = g.M, g.N, g.lo_count, g.hi_count
@@ -98,11 +164,7 @@ class CudaBackend:
             assert g.bias.dtype == torch.float32 and g.bias.is_cuda
             s.bias = g.bias.data_ptr()
         s.alpha = float(g.alpha)
-        if self.profiler is not None:
-            self.profiler.begin("gemm", g.flops)
-        _lib.check(self.lib.a8_gemm(C.byref(s), _stream()), "a8_gemm")
-        if self.profiler is not None:
-            self.profiler.end()
+        return s
 
 
     # ------------------------------------------------------------------ ctc
@@ -160,14 +222,15 @@ class CudaBackend:
         return y, yf, s, mean, rstd
 
     def layernorm_bwd(self, dy, s, mean, rstd, gamma, dy_f32=None, p_y=0.0, seed_y=0, want_dh=False, p_h=0.0,
-                      seed_h=0, want_dbias=False):
-        """returns ds, dh (or None), dgamma, dbeta, dbias (or None)"""
+                      seed_h=0, want_dbias=False, acc=None):
+        """returns ds, dh (or None), dgamma, dbeta, dbias (or None); acc: optional ZEROED fp32 [3,C] accumulator"""
         C = s.shape[-1]
         R = s.numel() // C
         assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and s.is_contiguous()
         ds = torch.empty_like(s)
         dh = torch.empty_like(s) if want_dh else None
-        acc = torch.zeros(3, C, dtype=torch.float32, device=s.device)
+        if acc is None:
+            acc = torch.zeros(3, C, dtype=torch.float32, device=s.device)
         _lib.check(self.lib.a8_layernorm_bwd(_ptr(dy), _ptr(dy_f32), p_y, seed_y, _ptr(s), _ptr(mean), _ptr(rstd),
                                              _ptr(gamma), _ptr(ds), _ptr(dh), p_h, seed_h, _ptr(acc[0]), _ptr(acc[1]),
                                              _ptr(acc[2]) if want_dbias else None, R, C, _stream()),
@@ -189,11 +252,13 @@ class CudaBackend:
                    "a8_softmax_bwd")
         return ds
 
-    def colsum(self, x):
+    def colsum(self, x, out=None):
+        """out: optional ZEROED fp32 [C] accumulator"""
         C = x.shape[-1]
         R = x.numel() // C
         assert x.dtype == torch.bfloat16 and x.is_contiguous()
-        out = torch.zeros(C, dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.zeros(C, dtype=torch.float32, device=x.device)
         _lib.check(self.lib.a8_colsum(_ptr(x), C, R, C, _ptr(out), _stream()), "a8_colsum")
         return out
 
@@ -313,6 +378,57 @@ class CudaBackend:
         out = torch.empty(R, 3 * C, dtype=torch.bfloat16, device=x.device)
         _lib.check(self.lib.a8_split3(_ptr(x), _ptr(out), R, C, int(b_side), _stream()), "a8_split3")
         return out
+
+    # ------------------------------------------------------------------ parameter re-layout
+    def cast_multi(self, pairs, cache):
+        """pairs: [(src fp32, dst bf16|fp32)] with equal numel; the device table is cached in `cache` while the
+        pointers stay the same (parameters are updated in place by optimizers)"""
+        sig = tuple((s.data_ptr(), d.data_ptr()) for s, d in pairs)
+        if cache.get("sig") != sig:
+            rows = [[s.data_ptr(), d.data_ptr(), s.numel(), 1 if d.dtype == torch.float32 else 0] for s, d in pairs]
+            for (s, d) in pairs:
+                assert s.dtype == torch.float32 and s.is_contiguous() and d.is_contiguous() and s.numel() == d.numel()
+            cache["table"] = torch.tensor(rows, dtype=torch.int64).to(pairs[0][0].device)
+            cache["sig"] = sig
+        _lib.check(self.lib.a8_cast_multi(_ptr(cache["table"]), len(pairs), _stream()), "a8_cast_multi")
+
+    def conv_pack(self, w, s, want_t):
+        """[Cout,Cin,k] fp32 -> (wk bf16 [Cout,k*Cin], [wt_0, wt_1] bf16 [Cin, ntaps_p*Cout] or None)"""
+        Cout, Cin, k = w.shape
+        assert w.dtype == torch.float32 and w.is_contiguous() and s == 2
+        wk = torch.empty(Cout, k * Cin, dtype=torch.bfloat16, device=w.device)
+        wts = None
+        if want_t:
+            wts = [torch.empty(Cin, ((k - p + s - 1) // s) * Cout, dtype=torch.bfloat16, device=w.device) for p in range(s)]
+        _lib.check(self.lib.a8_conv_pack(_ptr(w), Cout, Cin, k, s, _ptr(wk), _ptr(wts[0]) if wts else None,
+                                         _ptr(wts[1]) if wts else None, _stream()), "a8_conv_pack")
+        return wk, wts
+
+    def conv_unpack(self, dwk, Cin, k):
+        Cout = dwk.shape[0]
+        dw = torch.empty(Cout, Cin, k, dtype=torch.float32, device=dwk.device)
+        _lib.check(self.lib.a8_conv_unpack(_ptr(dwk), Cout, Cin, k, _ptr(dw), _stream()), "a8_conv_unpack")
+        return dw
+
+    def posconv_pack(self, g, v, want_t):
+        """weight-normed pos-conv weight -> (wp, wpt or None, norm2)"""
+        D, cg, k = v.shape
+        assert g.numel() == k and v.is_contiguous() and g.is_contiguous()
+        norm2 = torch.empty(k, dtype=torch.float32, device=v.device)
+        wp = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device)
+        wpt = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device) if want_t else None
+        _lib.check(self.lib.a8_posconv_pack(_ptr(g), _ptr(v), D, cg, k, _ptr(norm2), _ptr(wp), _ptr(wpt), _stream()),
+                   "a8_posconv_pack")
+        return wp, wpt, norm2
+
+    def posconv_wn_bwd(self, dwp, g, v, norm2):
+        D, cg, k = v.shape
+        t = torch.empty(k, dtype=torch.float32, device=v.device)
+        dv = torch.empty_like(v)
+        dg = torch.empty_like(g)
+        _lib.check(self.lib.a8_posconv_wn_bwd(_ptr(dwp), _ptr(g), _ptr(v), _ptr(norm2), D, cg, k, _ptr(t), _ptr(dv),
+                                              _ptr(dg), _stream()), "a8_posconv_wn_bwd")
+        return dv, dg
 
     # ------------------------------------------------------------------ quantizer / contrastive
     def vq_fwd(self, z, noise, tau, vars2d, G):

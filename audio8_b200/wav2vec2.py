@@ -211,6 +211,7 @@ class _PosConv(nn.Module):
         self.conv = nn.ModuleList([nn.Identity(), conv, nn.Identity()])
 
     def weight(self):
+        """the effective (weight-normed) kernel, for inspection; the training path fuses this into a pack kernel"""
         c = self.conv[1]
         return c.weight_g * c.weight_v / c.weight_v.norm(2, dim=(0, 1), keepdim=True)
 
@@ -234,9 +235,8 @@ class _LayerParams(nn.Module):
 
     def flat(self):
         a = self.self_attn
-        wqkv = torch.cat([a.w_Q.layer.weight, a.w_K.layer.weight, a.w_V.layer.weight], 0)
-        bqkv = torch.cat([a.w_Q.layer.bias, a.w_K.layer.bias, a.w_V.layer.bias], 0)
-        return [wqkv, bqkv, a.w_O.layer.weight, a.w_O.layer.bias, self.ln2.weight, self.ln2.bias,
+        return [a.w_Q.layer.weight, a.w_Q.layer.bias, a.w_K.layer.weight, a.w_K.layer.bias, a.w_V.layer.weight,
+                a.w_V.layer.bias, a.w_O.layer.weight, a.w_O.layer.bias, self.ln2.weight, self.ln2.bias,
                 self.ffn[0].layer.weight, self.ffn[0].layer.bias, self.ffn[3].layer.weight, self.ffn[3].layer.bias,
                 self.ln1.weight, self.ln1.bias]
 
@@ -266,6 +266,8 @@ class AudioTransformerEncoder(nn.Module):
         self.pos_conv = _PosConv(d_model, conv_pos_kernel, conv_groups, std)
         self.transformer = _Stack(d_model, d_ff if d_ff else 4 * d_model, layers)
         self.ln = _Affine(d_model)
+        self._arena = {}  # persistent bf16 operand buffers + device pointer table (values rewritten every call)
+        self._flat = None
 
     def forward(self, x, pad_mask=None):
         return self.extract_features(x, pad_mask)
@@ -281,12 +283,13 @@ class AudioTransformerEncoder(nn.Module):
         if pad_mask is not None:
             row_keep = pad_mask.to(device=x.device, dtype=torch.uint8).contiguous()
         cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
-                   active=active)
+                   active=active, arena=self._arena)
         flat = []
         for layer in self.transformer.encoders:
             flat += layer.flat()
-        return Fn.EncoderFn.apply(x, cfg, row_keep, self.pos_conv.weight(), self.pos_conv.conv[1].bias, self.ln.weight,
-                                  self.ln.bias, *flat)
+        pc = self.pos_conv.conv[1]
+        return Fn.EncoderFn.apply(x, cfg, row_keep, pc.weight_g, pc.weight_v, pc.bias, self.ln.weight, self.ln.bias,
+                                  *flat)
 
 
 class Wav2Vec2Encoder(nn.Module):

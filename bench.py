@@ -242,6 +242,13 @@ def run_ours(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = world * B * CROP_S / (dt.item() / args.steps)
 
+    # ---- host-side enqueue time of one step (queue empty at start, no sync inside): the launch-overhead floor
+    barrier()
+    t0 = time.perf_counter()
+    step(x_dev)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
     out = None
     if rank == 0:
         # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of 2 further steps
@@ -277,6 +284,7 @@ def run_ours(args):
                     "last_loss": loss_val},
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
+            "host_enqueue_ms_per_step": host_ms,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": which,

@@ -213,6 +213,25 @@ int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32
                        const float* xn, const float* yn, const float* cosv, const float* prob, const float* dce,
                        float* dx, float* dy, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Parameter re-layout, once per step: fp32 masters in PyTorch layouts -> bf16 GEMM operands (csrc/wprep.cu).
+ * a8_cast_multi: table of n entries {const float* src; void* dst; int64 numel; int64 dst_is_f32} in DEVICE memory;
+ *   one launch casts / copies them all (e.g. w_Q|w_K|w_V into one fused [3D,D] bf16 operand without a concat).
+ * a8_conv_pack: Conv1d weight [Cout,Cin,k] (`wav2vec2.py:426`) -> wk [Cout,k*Cin] and, per stride phase p < 2,
+ *   wt_p [Cin, ntaps_p*Cout] for the data-gradient GEMMs (wt0/wt1 may be NULL).  a8_conv_unpack: the inverse for dwk.
+ * a8_posconv_pack: weight_norm(dim=2) (`wav2vec2.py:609`): w = g[j]*v/||v[:,:,j]|| -> packed bf16 [D,k*64] (rows =
+ *   output channels) and its per-group transpose (rows = input channels); norm2[k] is kept for backward.
+ * a8_posconv_wn_bwd: from the GEMM's dwp fp32 [groups,k*64,64] to dv [D,cg,k], dg [k]; t_scratch: k floats.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_cast_multi(const void* table, int32_t n_entries, void* stream);
+int a8_conv_pack(const float* w, int32_t Cout, int32_t Cin, int32_t k, int32_t s, void* wk, void* wt0, void* wt1,
+                 void* stream);
+int a8_conv_unpack(const float* dwk, int32_t Cout, int32_t Cin, int32_t k, float* dw, void* stream);
+int a8_posconv_pack(const float* g, const float* v, int32_t D, int32_t cg, int32_t k, float* norm2, void* wp,
+                    void* wpt, void* stream);
+int a8_posconv_wn_bwd(const float* dwp, const float* g, const float* v, const float* norm2, int32_t D, int32_t cg,
+                      int32_t k, float* t_scratch, float* dv, float* dg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,7 +98,7 @@ class EmuBackend:
     name = "emu"
 
     def gemm(self, g):
-        emu_gemm(g)
+        emu_gemm(g.spec() if hasattr(g, "spec") else g)
 
 
 def _drop_mask(shape, p, seed):
@@ -129,7 +129,7 @@ class EmuOps(EmuBackend):
         return _bf(y), (y.clone() if want_f32 else None), s, mean.reshape(-1), rstd.reshape(-1)
 
     def layernorm_bwd(self, dy, s, mean, rstd, gamma, dy_f32=None, p_y=0.0, seed_y=0, want_dh=False, p_h=0.0,
-                      seed_h=0, want_dbias=False):
+                      seed_h=0, want_dbias=False, acc=None):
         C = s.shape[-1]
         g = dy.float() + (dy_f32 if dy_f32 is not None else 0.0)
         g = (g * _drop_mask(s.shape, p_y, seed_y)).reshape(-1, C)
@@ -165,8 +165,51 @@ class EmuOps(EmuBackend):
         ds = pf * (g - (pf * g).sum(-1, keepdim=True))
         return _bf(ds)
 
-    def colsum(self, x):
+    def colsum(self, x, out=None):
         return x.float().reshape(-1, x.shape[-1]).sum(0)
+
+    # ---- parameter re-layout
+    def cast_multi(self, pairs, cache):
+        for s, d in pairs:
+            d.copy_(s.reshape(d.shape))
+
+    def conv_pack(self, w, s, want_t):
+        Cout, Cin, k = w.shape
+        wk = _bf(w.permute(0, 2, 1).reshape(Cout, -1)).contiguous()
+        wts = None
+        if want_t:
+            wts = [_bf(torch.cat([w[:, :, j].t() for j in range(k) if j % s == p], 1)).contiguous() for p in range(s)]
+        return wk, wts
+
+    def conv_unpack(self, dwk, Cin, k):
+        return dwk.view(dwk.shape[0], k, Cin).permute(0, 2, 1).contiguous()
+
+    @staticmethod
+    def _pc_pack(w, groups, transpose):
+        D, cg, k = w.shape
+        wg = w.view(groups, cg, cg, k)
+        if transpose:
+            wg = wg.permute(0, 2, 1, 3)
+        out = torch.zeros(groups, cg, k, 64)
+        out[..., :cg] = wg.permute(0, 1, 3, 2)
+        return _bf(out.reshape(D, k * 64)).contiguous()
+
+    def posconv_pack(self, g, v, want_t):
+        D, cg, k = v.shape
+        norm2 = (v * v).sum((0, 1))
+        w = g.reshape(1, 1, k) * v / norm2.sqrt()
+        groups = D // cg
+        return self._pc_pack(w, groups, False), (self._pc_pack(w, groups, True) if want_t else None), norm2
+
+    def posconv_wn_bwd(self, dwp, g, v, norm2):
+        D, cg, k = v.shape
+        groups = D // cg
+        dW = dwp.view(groups, k, 64, 64)[:, :, :cg, :cg].permute(0, 3, 2, 1).reshape(D, cg, k)
+        nrm = norm2.sqrt()
+        t = (dW * v).sum((0, 1))
+        dg = (t / nrm).reshape(g.shape)
+        dv = g.reshape(1, 1, k) / nrm * (dW - v * t / norm2)
+        return dv, dg
 
     def dropout(self, x, p, seed):
         return (x.float() * _drop_mask(x.shape, p, seed)).to(x.dtype)

@@ -210,3 +210,43 @@ def test_contrastive(be):
     dx_g, dy_g = be.contrastive_bwd(x.cuda(), y.cuda(), idx.cuda(), sv_g, dce.cuda())
     _close(dx_g, dx_r, 1e-4, "contrastive dx")
     _close(dy_g, dy_r, 1e-4, "contrastive dy")
+
+
+def test_weight_prep(be):
+    """parameter re-layout kernels (csrc/wprep.cu) against the emulation"""
+    w = torch.randn(192, 128, 3, generator=_g(1)) * 0.1
+    for want_t in (False, True):
+        wk, wts = be.conv_pack(w.cuda(), 2, want_t)
+        wk_r, wts_r = E.conv_pack(w, 2, want_t)
+        assert torch.equal(wk.cpu(), wk_r)
+        if want_t:
+            for a, b in zip(wts, wts_r):
+                assert torch.equal(a.cpu(), b)
+    w2 = torch.randn(64, 128, 2, generator=_g(2))
+    wk, wts = be.conv_pack(w2.cuda(), 2, True)
+    wk_r, wts_r = E.conv_pack(w2, 2, True)
+    assert torch.equal(wk.cpu(), wk_r) and all(torch.equal(a.cpu(), b) for a, b in zip(wts, wts_r))
+    dwk = torch.randn(192, 3 * 128, generator=_g(3))
+    assert torch.equal(be.conv_unpack(dwk.cuda(), 128, 3).cpu(), E.conv_unpack(dwk, 128, 3))
+    D, cg, k = 768, 48, 128
+    v = torch.randn(D, cg, k, generator=_g(4)) * 0.02
+    g = 0.5 + torch.rand(1, 1, k, generator=_g(5))
+    wp, wpt, n2 = be.posconv_pack(g.cuda(), v.cuda(), True)
+    wp_r, wpt_r, n2_r = E.posconv_pack(g, v, True)
+    _close(n2, n2_r, 1e-5, "posconv norm2")
+    _close(wp, wp_r, 1e-2, "posconv wp")
+    _close(wpt, wpt_r, 1e-2, "posconv wpt")
+    dwp = torch.randn(D // cg, k * 64, 64, generator=_g(6))
+    dv, dg = be.posconv_wn_bwd(dwp.cuda(), g.cuda(), v.cuda(), n2)
+    dv_r, dg_r = E.posconv_wn_bwd(dwp, g, v, n2_r)
+    _close(dv, dv_r, 1e-4, "posconv dv")
+    _close(dg, dg_r, 1e-4, "posconv dg")
+    srcs = [torch.randn(n, generator=_g(10 + i)) for i, n in enumerate((768 * 768, 17, 3072 * 768, 768))]
+    dsts = [torch.zeros(768 * 768, dtype=torch.bfloat16), torch.zeros(17, dtype=torch.bfloat16),
+            torch.zeros(3072 * 768, dtype=torch.bfloat16), torch.zeros(768)]
+    pairs = [(s_.cuda(), d_.cuda()) for s_, d_ in zip(srcs, dsts)]
+    cache = {}
+    be.cast_multi(pairs, cache)
+    be.cast_multi(pairs, cache)
+    for (s_, d_) in pairs:
+        assert torch.equal(d_.cpu(), s_.cpu().to(d_.dtype))
