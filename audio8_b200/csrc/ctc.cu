@@ -197,7 +197,11 @@ struct CtcGradArgs {
 };
 
 constexpr int GRAD_WARPS = 8;
-// grid (ceil(T / (GRAD_WARPS*TPW)), B): each warp handles TPW consecutive time steps of utterance b
+// grid (ceil(T / (GRAD_WARPS*TPW)), B): each warp handles TPW consecutive time steps of utterance b.
+// The state posteriors are normalised per time step by their own sum (in exact arithmetic that sum equals the
+// utterance likelihood for every t): this cancels the common-mode rounding drift that fp32 log-space alpha/beta
+// of magnitude ~|nll| accumulate over T steps, so each gradient row sums to zero to fp32 precision.
+template <int NS>
 __global__ void __launch_bounds__(GRAD_WARPS * 32) ctc_grad_kernel(const CtcGradArgs g, int tpw) {
   extern __shared__ float smem[];  // [GRAD_WARPS][2][V] : lp row, bins ; then int ext[epad]
   const CtcArgs& a = g.c;
@@ -214,17 +218,15 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) ctc_grad_kernel(const CtcGrad
   float* row = smem + (size_t)w * 2 * V;
   float* bins = row + V;
   const float nll = a.nll[b];
-  const bool dead = isinf(nll);
+  const bool dead = isinf(nll) || E > 32 * NS;
   float scale = g.grad_out[(long long)b * g.go_stride];
   if (g.mean) scale /= (float)(max(S, 1) * a.B);
-  if (dead && g.zero_inf) scale = 0.f;
-  const float nll2 = nll * LOG2E;
   const int t0 = (blockIdx.x * GRAD_WARPS + w) * tpw;
   for (int t = t0; t < min(t0 + tpw, a.T); ++t) {
     float* gout = g.grad + ((long long)t * a.B + b) * V;
     if (t >= Tb || dead) {
-      // PyTorch: zero for t >= input_length; for an infeasible row the formula degenerates to NaN/inf,
-      // zero_infinity zeroes it (without zero_infinity we return 0 as well: the loss itself is +inf)
+      // PyTorch: zero for t >= input_length; an infeasible row (loss +inf) is zeroed by zero_infinity — without
+      // zero_infinity the reference's gradient is NaN garbage, we return 0 there as well
       for (int c = lane; c < V; c += 32) gout[c] = 0.f;
       continue;
     }
@@ -236,13 +238,34 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32) ctc_grad_kernel(const CtcGrad
     __syncwarp();
     const float* al = a.alpha + ((long long)b * a.T + t) * a.epad;
     const float* be = a.beta + ((long long)b * a.T + t) * a.epad;
+    float wv[NS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int s = lane + 32 * i;
+      wv[i] = -INFINITY;
+      if (s < E) {
+        const float v = al[s] + be[s];
+        if (v > -INFINITY) wv[i] = v - row[ext[s]] * LOG2E;  // alpha and beta both include the emission at t
+      }
+      mx = fmaxf(mx, wv[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      wv[i] = (wv[i] > -INFINITY) ? ex2(wv[i] - mx) : 0.f;
+      sum += wv[i];
+    }
+    sum = warp_sum(sum);
+    const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
     float blank_sum = 0.f;
-    for (int s = lane; s < E; s += 32) {
-      const float v = al[s] + be[s];
-      if (v > -INFINITY) {
-        const int c = ext[s];
-        const float occ = ex2(v - row[c] * LOG2E + nll2);
-        if (s & 1) atomicAdd(&bins[c], occ);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      const int s = lane + 32 * i;
+      if (s < E && wv[i] > 0.f) {
+        const float occ = wv[i] * inv;
+        if (s & 1) atomicAdd(&bins[ext[s]], occ);
         else blank_sum += occ;
       }
     }
@@ -368,13 +391,23 @@ extern "C" int a8_ctc_backward(const float* log_probs, int64_t stride_t, int64_t
                 grad_out, grad_out_stride, reduction_mean, zero_infinity, grad};
   const size_t smem = (size_t)GRAD_WARPS * 2 * V * sizeof(float) + (size_t)(32 * ns) * sizeof(int);
   A8_REQUIRE(smem <= 200 * 1024, "ctc: vocabulary %d too large", V);
-  if (smem > 48 * 1024)
-    A8_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // enough CTAs to fill 148 SMs a few times over, at least 1 step per warp
   int tpw = 1;
   while ((long long)cdiv(T, GRAD_WARPS * tpw) * B > 148 * 16 && tpw < 16) tpw *= 2;
   dim3 grid(cdiv(T, GRAD_WARPS * tpw), B);
-  ctc_grad_kernel<<<grid, GRAD_WARPS * 32, smem, stream>>>(g, tpw);
+#define A8_CTCG_CASE(NS)                                                                               \
+  case NS: {                                                                                           \
+    if (smem > 48 * 1024)                                                                              \
+      A8_CUDA(cudaFuncSetAttribute(ctc_grad_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                   (int)smem));                                                        \
+    ctc_grad_kernel<NS><<<grid, GRAD_WARPS * 32, smem, stream>>>(g, tpw);                              \
+  } break;
+  switch (ns) {
+    A8_CTCG_CASE(4) A8_CTCG_CASE(8) A8_CTCG_CASE(12) A8_CTCG_CASE(16) A8_CTCG_CASE(20) A8_CTCG_CASE(24)
+    A8_CTCG_CASE(28) A8_CTCG_CASE(32)
+    default: set_error("ctc: bad NS %d", ns); return -1;
+  }
+#undef A8_CTCG_CASE
   return check_launch("ctc_grad_kernel");
 }
 
