@@ -18,23 +18,6 @@ constexpr int KMAX = 10;
 constexpr int NMOM = KMAX + KMAX * (KMAX + 1) / 2;  // 65
 constexpr int TILE_T = 64;
 
-// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 1 rcp + 1 ex2 + 7 FMA — the activation is stored
-// in bf16 (8 mantissa bits), so this is exact for the purpose and ~3x cheaper than erff()
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.f - p * t * __expf(-ax * ax);
-  return copysignf(e, x);
-}
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  return 0.5f * (1.f + erf_fast(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
-
 // ---------------------------------------------------------------------------------------------- moments
 // mom[b][0..k) = sum_t x[s t + j];  mom[b][k + idx(j,j')] = sum_t x[s t + j] x[s t + j'] (j <= j')
 __global__ void __launch_bounds__(256) conv0_moments_kernel(const float* x, long long L, int L0, int k, int s,

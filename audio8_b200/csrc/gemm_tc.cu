@@ -17,7 +17,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;  // warps 4..11: two per TMEM lane quarter, each owns half of the tile's columns
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
 enum { MAJOR_K = A8_MAJOR_K, MAJOR_MN = A8_MAJOR_MN };
 enum { OUT_BF16 = A8_OUT_BF16, OUT_F32 = A8_OUT_F32, OUT_F32_ATOMIC = A8_OUT_F32_ATOMIC };
 enum { ACT_NONE = A8_ACT_NONE, ACT_GELU = A8_ACT_GELU };
@@ -57,7 +58,7 @@ struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * 32 * 80 + 1024;
 };
 
 // UMMA shared-memory matrix descriptor, 128B swizzle (layout type 2), descriptor version 1.
@@ -86,57 +87,115 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
   return t;
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_group(const KParams& p, const uint32_t* r, long long off,
-                                               int n, int lo) {
-  float v[8];
+constexpr int STG_PITCH = 80;                 // bytes per staged row: 64 payload + 16 pad (conflict-free 16B writes)
+constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
+
+// Coalesced copy between a warp's staging buffer (32 rows x 64 B) and global rows `row_off0 + r*ldc` (element
+// offsets of element size ES): lane l moves 16 B of row (l/4 + 8i), piece (l%4) — every instruction touches 8 rows
+// x 64 contiguous bytes instead of 32 rows x 16 bytes.
+template <int ES, bool STORE>
+__device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long row_off0, long long ldc, int col0,
+                                           int rows_valid, int cols_valid, int lane) {
+  constexpr int EPP = 16 / ES;  // elements per 16-byte piece
+  const int piece = lane & 3;
+  const int col = col0 + piece * EPP;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-  if (p.bias != nullptr) {
-    const float4* bp = reinterpret_cast<const float4*>(p.bias + (long long)lo * p.bias_stride_lo + n);
-    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    if (r < rows_valid && col < cols_valid) {
+      uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (row_off0 + (long long)r * ldc + col) * ES;
+      uint4* sp = reinterpret_cast<uint4*>(stg + r * STG_PITCH + piece * 16);
+      if (STORE) *reinterpret_cast<uint4*>(g) = *sp;
+      else *sp = *reinterpret_cast<const uint4*>(g);
+    }
+  }
+}
+
+// 32 columns x 32 rows (one row per lane) of accumulators in registers -> epilogue math -> global memory.
+// Non-atomic outputs (and the bf16 aux input) go through the warp's smem staging buffer so that global accesses
+// are row-contiguous; the split-K fp32 path adds atomically straight from registers.
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t* r, long long row_off0, int row0,
+                                               int nb, const float* sb, uint8_t* stg, int lane) {
+  const int rows_valid = min(32, p.M - row0);        // may be <= 0
+  const int n8 = (p.N + 7) & ~7;
+  const int cols_valid = n8;                          // absolute column bound for the 16-byte pieces
+  const bool has_aux = p.aux_mode != AUX_NONE;
+  uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
+  uint4 a[4];
+  if (has_aux) {
+    stage_copy<2, false>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) a[g] = my[g];
+    __syncwarp();
+  }
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (sb != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += sb[i];
   }
   if (p.z_out != nullptr) {
-    uint4 z;
-    z.x = pack_bf16(v[0], v[1]); z.y = pack_bf16(v[2], v[3]);
-    z.z = pack_bf16(v[4], v[5]); z.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.z_out) + off) = z;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 z;
+      z.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); z.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+      z.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); z.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+      my[g] = z;
+    }
+    __syncwarp();
+    stage_copy<2, true>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    __syncwarp();
   }
   if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
   }
-  if (p.aux_mode != AUX_NONE) {
-    const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
-    float x[8];
-    float2 t;
-    t = unpack_bf16(a.x); x[0] = t.x; x[1] = t.y;
-    t = unpack_bf16(a.y); x[2] = t.x; x[3] = t.y;
-    t = unpack_bf16(a.z); x[4] = t.x; x[5] = t.y;
-    t = unpack_bf16(a.w); x[6] = t.x; x[7] = t.y;
-    if (p.aux_mode == AUX_ADD) {
+  if (has_aux) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += x[i];
-    } else {
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t w[4] = {a[g].x, a[g].y, a[g].z, a[g].w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(x[i]);
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16(w[j]);
+        if (p.aux_mode == AUX_ADD) {
+          v[8 * g + 2 * j] += t.x;
+          v[8 * g + 2 * j + 1] += t.y;
+        } else {
+          v[8 * g + 2 * j] *= gelu_erf_grad(t.x);
+          v[8 * g + 2 * j + 1] *= gelu_erf_grad(t.y);
+        }
+      }
     }
   }
   if (p.c_dtype == OUT_BF16) {
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-    o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.c) + off) = o;
-  } else if (p.c_dtype == OUT_F32) {
-    float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + off);
-    cp[0] = make_float4(v[0], v[1], v[2], v[3]);
-    cp[1] = make_float4(v[4], v[5], v[6], v[7]);
-  } else {
-    float* cp = reinterpret_cast<float*>(p.c) + off;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(cp + i, v[i]);
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+      o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+      my[g] = o;
+    }
+    __syncwarp();
+    stage_copy<2, true>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    __syncwarp();
+  } else if (p.c_dtype == OUT_F32) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        my[g] = make_uint4(__float_as_uint(v[16 * h + 4 * g]), __float_as_uint(v[16 * h + 4 * g + 1]),
+                           __float_as_uint(v[16 * h + 4 * g + 2]), __float_as_uint(v[16 * h + 4 * g + 3]));
+      __syncwarp();
+      stage_copy<4, true>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+      __syncwarp();
+    }
+  } else if (lane < rows_valid) {
+    float* cp = reinterpret_cast<float*>(p.c) + row_off0 + (long long)lane * p.ldc + nb;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (nb + i < n8) atomicAdd(cp + i, v[i]);
   }
 }
 
@@ -157,6 +216,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
   auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw_u32));  // [2 accumulator stages][BN]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + 2 * BN);                // [EPI_WARPS][32 rows][80 B]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
@@ -176,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(tfull_bar(i), 1);
-        mbar_init(tempty_bar(i), 128);
+        mbar_init(tempty_bar(i), 32 * EPI_WARPS);
       }
       mbar_fence_init();
     }
@@ -275,32 +336,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the tile's columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int COLS = BN / 2;         // columns per warp
+    constexpr int NCH = COLS / 32;       // 32-column chunks per warp (4 / 2 / 1)
+    const int tid_e = threadIdx.x - 128;
     int iter = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
       const TileCoord t = decode_tile(p, tile);
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1u;
+      float* sb = nullptr;
+      if (p.bias != nullptr) {
+        // stage this tile's bias slice in shared memory while the main loop of the tile is still running
+        sb = s_bias + as * BN;
+        const float* bsrc = p.bias + (long long)t.lo * p.bias_stride_lo + t.nt * BN;
+        for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) sb[i] = (t.nt * BN + i < p.N) ? __ldg(bsrc + i) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = t.mt * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const long long row_off =
-          (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row * p.ldc;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c * 32, r);
-        tmem_ld_wait();
-        const int nb = t.nt * BN + c * 32;
-        if (row_ok) {
+      const int row0 = t.mt * BLOCK_M + q * 32;
+      const long long row_off0 =
+          (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row0 * p.ldc;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * COLS;
+      const int nb0 = t.nt * BN + half * COLS;
+      const float* sbw = sb ? sb + half * COLS : nullptr;
+      uint8_t* stg = s_stage + (warp - 4) * STG_BYTES;
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(t_addr, ra);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = nb + g * 8;
-            if (n < p.N) epilogue_group<BN>(p, r + g * 8, row_off + n, n, t.lo);
-          }
-        }
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld_wait();
+        // prefetch the next chunk's accumulators into the other register buffer while this one is processed
+        if (c + 1 < NCH) tmem_ld_32x32(t_addr + (c + 1) * 32, (c & 1) ? ra : rb);
+        if (nb0 + c * 32 < p.N)
+          epilogue_chunk(p, (c & 1) ? rb : ra, row_off0, row0, nb0 + c * 32, sbw ? sbw + c * 32 : nullptr, stg, lane);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
