@@ -41,6 +41,8 @@ SIGNATURES = {
     "a8_version": (_I, []),
     "a8_last_error": (C.c_char_p, []),
     "a8_launch_count": (_L, []),
+    "a8_launch_count_add": (_I, [_L]),
+    "a8_set_seed_source": (_I, [_P]),
     "a8_gemm": (_I, [C.POINTER(Gemm), _P]),
     "a8_ctc_scratch_floats": (_Z, [_I, _I, _I]),
     "a8_ctc_prep": (_I, [_P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -29,3 +29,7 @@ int check_launch(const char* what) {
 extern "C" int a8_version(void) { return A8_ABI_VERSION; }
 extern "C" const char* a8_last_error(void) { return a8::g_err; }
 extern "C" int64_t a8_launch_count(void) { return (int64_t)a8::g_launches.load(); }
+extern "C" int a8_launch_count_add(int64_t n) {
+  a8::g_launches.fetch_add(n, std::memory_order_relaxed);
+  return 0;
+}

@@ -50,21 +50,53 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 1 rcp + 1 ex2 + 7 FMA.  Used where the result is stored
 // in bf16 (8 mantissa bits): exact for the purpose and ~3x cheaper than erff().
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = 1.f - p * t * __expf(-ax * ax);
+  const float e = 1.f - p * t * ex2_approx(-1.4426950408889634f * ax * ax);
   return copysignf(e, x);
 }
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
+// exact-erf GELU with |error| < 1e-6 and ONE special-function op (A&S 7.1.28: 1-erf(u) = (1+a1 u+..+a6 u^6)^-16)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  float p = fmaf(0.0000430638f, u, 0.0002765672f);
+  p = fmaf(p, u, 0.0001520143f);
+  p = fmaf(p, u, 0.0092705272f);
+  p = fmaf(p, u, 0.0422820123f);
+  p = fmaf(p, u, 0.0705230784f);
+  p = fmaf(p, u, 1.f);
+  p *= p; p *= p; p *= p; p *= p;              // overflows to +inf for |x| > ~25: rcp(inf) = 0, the right limit
+  const float h = 0.5f * rcp_approx(p);        // (1 - erf(u)) / 2
+  return x * (x >= 0.f ? 1.f - h : h);
+}
+// d/dx gelu(x) = Phi(x) + x phi(x), |error| < 1e-6: 1 rcp + 1 ex2, the exponential shared by erf (7.1.26) and phi
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  return 0.5f * (1.f + erf_fast(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  const float u = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = ex2_approx(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  const float half_erf = 0.5f - 0.5f * p * t * e;
+  const float cdf = 0.5f + copysignf(half_erf, x);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -54,10 +54,10 @@ __device__ __forceinline__ void op_coords(const OpCoef& o, int kin, int kbatch, 
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // powers of two >= 32; 2 accumulator stages
   static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * 32 * 80 + 1024;
 };
 
@@ -93,7 +93,8 @@ constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
 // Coalesced copy between a warp's staging buffer (32 rows x 64 B) and global rows `row_off0 + r*ldc` (element
 // offsets of element size ES): lane l moves 16 B of row (l/4 + 8i), piece (l%4) — every instruction touches 8 rows
 // x 64 contiguous bytes instead of 32 rows x 16 bytes.
-template <int ES, bool STORE>
+enum { STG_LOAD = 0, STG_STORE = 1, STG_RED = 2 };
+template <int ES, int MODE>
 __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long row_off0, long long ldc, int col0,
                                            int rows_valid, int cols_valid, int lane) {
   constexpr int EPP = 16 / ES;  // elements per 16-byte piece
@@ -105,8 +106,15 @@ __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long 
     if (r < rows_valid && col < cols_valid) {
       uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (row_off0 + (long long)r * ldc + col) * ES;
       uint4* sp = reinterpret_cast<uint4*>(stg + r * STG_PITCH + piece * 16);
-      if (STORE) *reinterpret_cast<uint4*>(g) = *sp;
-      else *sp = *reinterpret_cast<const uint4*>(g);
+      if (MODE == STG_STORE) {
+        *reinterpret_cast<uint4*>(g) = *sp;
+      } else if (MODE == STG_LOAD) {
+        *sp = *reinterpret_cast<const uint4*>(g);
+      } else {  // split-K: one 16-byte vector reduction per lane, 64 contiguous bytes per row
+        const float4 v = *reinterpret_cast<const float4*>(sp);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+      }
     }
   }
 }
@@ -123,7 +131,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
   uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
   uint4 a[4];
   if (has_aux) {
-    stage_copy<2, false>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_LOAD>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
 #pragma unroll
     for (int g = 0; g < 4; ++g) a[g] = my[g];
@@ -145,12 +153,12 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
       my[g] = z;
     }
     __syncwarp();
-    stage_copy<2, true>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_STORE>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
   }
   if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
   if (has_aux) {
 #pragma unroll
@@ -163,8 +171,8 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
           v[8 * g + 2 * j] += t.x;
           v[8 * g + 2 * j + 1] += t.y;
         } else {
-          v[8 * g + 2 * j] *= gelu_erf_grad(t.x);
-          v[8 * g + 2 * j + 1] *= gelu_erf_grad(t.y);
+          v[8 * g + 2 * j] *= gelu_grad_fast(t.x);
+          v[8 * g + 2 * j + 1] *= gelu_grad_fast(t.y);
         }
       }
     }
@@ -178,9 +186,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
       my[g] = o;
     }
     __syncwarp();
-    stage_copy<2, true>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_STORE>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
-  } else if (p.c_dtype == OUT_F32) {
+  } else {  // fp32: plain stores, or vector reductions for split-K partial sums
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -188,14 +196,12 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
         my[g] = make_uint4(__float_as_uint(v[16 * h + 4 * g]), __float_as_uint(v[16 * h + 4 * g + 1]),
                            __float_as_uint(v[16 * h + 4 * g + 2]), __float_as_uint(v[16 * h + 4 * g + 3]));
       __syncwarp();
-      stage_copy<4, true>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+      if (p.c_dtype == OUT_F32)
+        stage_copy<4, STG_STORE>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+      else
+        stage_copy<4, STG_RED>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
       __syncwarp();
     }
-  } else if (lane < rows_valid) {
-    float* cp = reinterpret_cast<float*>(p.c) + row_off0 + (long long)lane * p.ldc + nb;
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (nb + i < n8) atomicAdd(cp + i, v[i]);
   }
 }
 
@@ -468,6 +474,7 @@ int launch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const KParam
   switch (bn) {
     case 64: return launch_inst<MA, MB, 64>(ma, mb, kp, stream);
     case 128: return launch_inst<MA, MB, 128>(ma, mb, kp, stream);
+    case 192: return launch_inst<MA, MB, 192>(ma, mb, kp, stream);
     case 256: return launch_inst<MA, MB, 256>(ma, mb, kp, stream);
   }
   set_error("gemm: unsupported block_n %d", bn);

@@ -32,6 +32,13 @@ struct DropMask8 {
   float m[8];
 };
 // keep-scale per element: 0 or 1/(1-p)
+// Seeds: every launch passes a per-call-site constant; kernels add the 64-bit word at `g_seed_src` (device memory,
+// nullable) so that a captured CUDA graph draws fresh masks on every replay (a8_set_seed_source).
+static thread_local const unsigned long long* g_seed_src = nullptr;
+__device__ __forceinline__ unsigned long long seed_base(const unsigned long long* src) {
+  return src != nullptr ? __ldg(src) : 0ull;
+}
+
 __device__ __forceinline__ DropMask8 drop_mask8(float p, unsigned long long seed, unsigned long long group) {
   DropMask8 d;
   if (p <= 0.f) {
@@ -93,10 +100,12 @@ struct LnFwdArgs {
   float* mean;
   float* rstd;
   int R, C;
+  const unsigned long long* seed_src;
 };
 
 template <int NCH>  // chunks of 8 elements per lane: C <= NCH*256
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
+  const unsigned long long sbase = seed_base(a.seed_src);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int C = a.C;
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
         if (a.h != nullptr) {
           float hv[8];
           load8(a.h + ro + c, hv);
-          const DropMask8 d = drop_mask8(a.p_h, a.seed_h, (unsigned long long)(ro + c) >> 3);
+          const DropMask8 d = drop_mask8(a.p_h, a.seed_h + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[i][j] += hv[j] * d.m[j];
           // statistics are taken on the bf16-rounded sum, the value backward re-reads
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
         float g[8], b[8], o[8];
         load8f(a.gamma + c, g);
         load8f(a.beta + c, b);
-        const DropMask8 d = drop_mask8(a.p_y, a.seed_y, (unsigned long long)(ro + c) >> 3);
+        const DropMask8 d = drop_mask8(a.p_y, a.seed_y + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = ((v[i][j] - mu) * rs * g[j] + b[j]) * d.m[j];
         store8(a.y + ro + c, o);
@@ -180,10 +189,12 @@ struct LnBwdArgs {
   float* dbeta;    // [C]
   float* dbias_h;  // nullable [C]
   int R, C;
+  const unsigned long long* seed_src;
 };
 
 template <int NCH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  const unsigned long long sbase = seed_base(a.seed_src);
   __shared__ float red[8][NCH * 256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
         }
         load8(a.s + ro + c, sv);
         load8f(a.gamma + c, gm);
-        const DropMask8 d = drop_mask8(a.p_y, a.seed_y, (unsigned long long)(ro + c) >> 3);
+        const DropMask8 d = drop_mask8(a.p_y, a.seed_y + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float gg = dy[j] * d.m[j];
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
         for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
         store8(a.ds + ro + c, o);
         if (a.dh != nullptr) {
-          const DropMask8 d = drop_mask8(a.p_h, a.seed_h, (unsigned long long)(ro + c) >> 3);
+          const DropMask8 d = drop_mask8(a.p_h, a.seed_h + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             o[j] *= d.m[j];
@@ -285,10 +296,12 @@ struct SmFwdArgs {
   float pdrop;
   unsigned long long seed;
   int rows, T, Tp, rows_per_batch;
+  const unsigned long long* seed_src;
 };
 
 template <int NV>  // 8-element chunks per lane: Tp <= NV*256
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const SmFwdArgs a) {
+  const unsigned long long sbase = seed_base(a.seed_src);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps) {
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const SmFwdArgs a) {
         for (int j = 0; j < 8; ++j) v[i][j] *= inv;
         store8(a.p + ro + c, v[i]);
         if (a.p_drop != nullptr) {
-          const DropMask8 d = drop_mask8(a.pdrop, a.seed, (unsigned long long)(ro + c) >> 3);
+          const DropMask8 d = drop_mask8(a.pdrop, a.seed + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[i][j] *= d.m[j];
           store8(a.p_drop + ro + c, v[i]);
@@ -349,10 +362,12 @@ struct SmBwdArgs {
   float pdrop;
   unsigned long long seed;
   int rows, T, Tp;
+  const unsigned long long* seed_src;
 };
 
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const SmBwdArgs a) {
+  const unsigned long long sbase = seed_base(a.seed_src);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps) {
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const SmBwdArgs a) {
       if (c < a.Tp) {
         load8(a.p + ro + c, pv[i]);
         load8f(a.dp + ro + c, g[i]);
-        const DropMask8 d = drop_mask8(a.pdrop, a.seed, (unsigned long long)(ro + c) >> 3);
+        const DropMask8 d = drop_mask8(a.pdrop, a.seed + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (c + j >= a.T) {
@@ -434,7 +449,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* x, lon
 // element-wise dropout on bf16 (n % 8 == 0): out = x * mask/(1-p); the same call is its own backward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* x, __nv_bfloat16* out, long long n8,
-                                                      float p, unsigned long long seed) {
+                                                      float p, unsigned long long seed,
+                                                      const unsigned long long* seed_src) {
+  seed += seed_base(seed_src);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float v[8];
     load8(x + i * 8, v);
@@ -446,7 +463,9 @@ __global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* x, __
 }
 
 __global__ void __launch_bounds__(256) dropout_f32_kernel(const float* x, float* out, long long n8, float p,
-                                                          unsigned long long seed) {
+                                                          unsigned long long seed,
+                                                          const unsigned long long* seed_src) {
+  seed += seed_base(seed_src);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float v[8];
     load8f(x + i * 8, v);
@@ -515,13 +534,18 @@ int row_grid(int rows) {
 
 using namespace a8;
 
+extern "C" int a8_set_seed_source(const void* dev_u64) {
+  g_seed_src = static_cast<const unsigned long long*>(dev_u64);
+  return 0;
+}
+
 extern "C" int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_t seed_h, void* s_out,
                                 const float* gamma, const float* beta, float eps, void* y, float* y_f32, float p_y,
                                 uint64_t seed_y, float* mean, float* rstd, int32_t R, int32_t C, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm: unsupported shape R=%d C=%d", R, C);
   LnFwdArgs a{(const __nv_bfloat16*)x, (const __nv_bfloat16*)h, p_h, seed_h, (__nv_bfloat16*)s_out, gamma, beta,
-              eps, (__nv_bfloat16*)y, y_f32, p_y, seed_y, mean, rstd, R, C};
+              eps, (__nv_bfloat16*)y, y_f32, p_y, seed_y, mean, rstd, R, C, g_seed_src};
   const int nch = cdiv(C, 256);
   const int grid = row_grid(R);
   switch (nch) {
@@ -540,7 +564,7 @@ extern "C" int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: unsupported shape R=%d C=%d", R, C);
   LnBwdArgs a{(const __nv_bfloat16*)dy, dy_f32, p_y, seed_y, (const __nv_bfloat16*)s, mean, rstd, gamma,
-              (__nv_bfloat16*)ds, (__nv_bfloat16*)dh, p_h, seed_h, dgamma, dbeta, dbias_h, R, C};
+              (__nv_bfloat16*)ds, (__nv_bfloat16*)dh, p_h, seed_h, dgamma, dbeta, dbias_h, R, C, g_seed_src};
   const int nch = cdiv(C, 256);
   int grid = cdiv(R, 8 * 4);  // >= 4 rows per warp so the column partials amortise their atomics
   grid = grid < 1 ? 1 : (grid > 148 * 2 ? 148 * 2 : grid);
@@ -557,7 +581,7 @@ extern "C" int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, 
                               uint64_t seed, int32_t B, int32_t H, int32_t T, int32_t Tp, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax: bad T=%d Tp=%d", T, Tp);
-  SmFwdArgs a{s, key_keep, (__nv_bfloat16*)p, (__nv_bfloat16*)p_drop, pdrop, seed, B * H * T, T, Tp, H * T};
+  SmFwdArgs a{s, key_keep, (__nv_bfloat16*)p, (__nv_bfloat16*)p_drop, pdrop, seed, B * H * T, T, Tp, H * T, g_seed_src};
   const int nv = cdiv(Tp, 256);
   const int grid = row_grid(a.rows);
   if (nv <= 1) softmax_fwd_kernel<1><<<grid, 256, 0, stream>>>(a);
@@ -573,7 +597,7 @@ extern "C" int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pd
                               int32_t H, int32_t T, int32_t Tp, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax_bwd: bad T=%d Tp=%d", T, Tp);
-  SmBwdArgs a{(const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, pdrop, seed, B * H * T, T, Tp};
+  SmBwdArgs a{(const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, pdrop, seed, B * H * T, T, Tp, g_seed_src};
   const int nv = cdiv(Tp, 256);
   const int grid = row_grid(a.rows);
   if (nv <= 1) softmax_bwd_kernel<1><<<grid, 256, 0, stream>>>(a);
@@ -603,8 +627,8 @@ extern "C" int a8_dropout(const void* x, void* out, int32_t dtype, int64_t n, fl
   A8_REQUIRE(n > 0 && n % 8 == 0, "dropout: n=%lld must be a positive multiple of 8", (long long)n);
   const long long n8 = n / 8;
   const int grid = (int)(n8 / 256 + 1 > 148 * 8 ? 148 * 8 : n8 / 256 + 1);
-  if (dtype == 0) dropout_f32_kernel<<<grid, 256, 0, stream>>>((const float*)x, (float*)out, n8, p, seed);
-  else dropout_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n8, p, seed);
+  if (dtype == 0) dropout_f32_kernel<<<grid, 256, 0, stream>>>((const float*)x, (float*)out, n8, p, seed, g_seed_src);
+  else dropout_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n8, p, seed, g_seed_src);
   return check_launch("dropout_kernel");
 }
 

@@ -16,12 +16,20 @@ from . import ops
 from .ops import ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, OUT_BF16, OUT_F32
 
 BF16, F32 = torch.bfloat16, torch.float32
-_seed_state = [0x9E3779B97F4A7C15]
+_site = [0]
 
 
 def next_seed():
-    """dropout seeds: drawn from torch's CPU generator so torch.manual_seed() makes runs reproducible"""
-    return int(torch.randint(0, 2 ** 62, (1,)).item())
+    """per-call-site dropout seed (a host constant, baked into CUDA-graph captures); the per-step randomness comes
+    from `step_seed()`, a device word that kernels add to it at run time"""
+    _site[0] = (_site[0] + 0x9E3779B97F4A7C15) & 0x3FFFFFFFFFFFFFFF
+    return _site[0]
+
+
+def step_seed(like):
+    """one int64 on the device from torch's CUDA generator: reproducible under torch.manual_seed() and refreshed on
+    every replay when the surrounding code is captured in a CUDA graph (the generator is graph-safe)"""
+    return torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=like.device)
 
 
 def _be():
@@ -122,13 +130,20 @@ def layer_norm(x, gamma, beta, eps, want_f32=False):
 class DropoutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, p, seed):
-        ctx.cfg = (p, seed)
-        return _be().dropout(x.detach().contiguous(), p, seed)
+        src = step_seed(x)
+        ctx.cfg = (p, seed, src)
+        _be().set_seed_source(src)
+        out = _be().dropout(x.detach().contiguous(), p, seed)
+        _be().set_seed_source(None)
+        return out
 
     @staticmethod
     def backward(ctx, dy):
-        p, seed = ctx.cfg
-        return _be().dropout(dy.contiguous(), p, seed), None, None
+        p, seed, src = ctx.cfg
+        _be().set_seed_source(src)
+        dx = _be().dropout(dy.contiguous(), p, seed)
+        _be().set_seed_source(None)
+        return dx, None, None
 
 
 def dropout(x, p, training):
@@ -316,6 +331,8 @@ class EncoderFn(torch.autograd.Function):
             x = x.clone()
             be.mask_apply(x, row_keep, None)
         need_grad = any(ctx.needs_input_grad)
+        seed_src = step_seed(x) if p > 0 else None
+        be.set_seed_source(seed_src)
         pg, pv = pos_g.detach().contiguous(), pos_v.detach().contiguous()
         wp, wpt, norm2 = be.posconv_pack(pg, pv, need_grad)
         s0 = _empty(x.shape, BF16, x)
@@ -365,7 +382,8 @@ class EncoderFn(torch.autograd.Function):
         if need_grad:
             ctx.saved = dict(x=x, s0=s0, z0=z0, mean0=mean0, rstd0=rstd0, seed0=seed0, ln_g=ln_g.detach(),
                              pg=pg, pv=pv, norm2=norm2, wpt=wpt, layers=layers, row_keep=row_keep, p=p, H=H,
-                             groups=groups, k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw))
+                             groups=groups, k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw), seed_src=seed_src)
+        be.set_seed_source(None)
         return h
 
     @staticmethod
@@ -378,6 +396,7 @@ class EncoderFn(torch.autograd.Function):
         B, T, D = x.shape
         M = B * T
         dcur = _bf16(dh).view(M, D)
+        be.set_seed_source(sv["seed_src"])
         lgrads = [None] * sv["nlw"]
         for li in range(len(sv["layers"]) - 1, -1, -1):
             L = sv["layers"][li]
@@ -446,6 +465,7 @@ class EncoderFn(torch.autograd.Function):
         be.gemm(G.posconv_dgrad(dz0, sv["wpt"], dx, groups, k, pad_l, aux=ds0))
         if sv["row_keep"] is not None:
             be.mask_apply(dx, sv["row_keep"], None)
+        be.set_seed_source(None)
         return (dx, None, None, dpos_g, dpos_v, dpos_b, dlg, dlb, *lgrads)
 
 

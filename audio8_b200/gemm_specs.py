@@ -71,6 +71,34 @@ def _pick_bn(N):
     return 64 if N <= 64 else (128 if N <= 128 else 256)
 
 
+# cycles of one 128 x BN x 64 k-block on the tensor pipe (BN <= 128 tiles are bound by shared-memory operand reads)
+_MMA_CLK = {64: 192, 128: 282, 192: 384, 256: 512}
+_EPI_CLK_PER_COL = {"bf16": 10, "f32": 14, "atomic": 20, "gelu": 22}
+
+
+@functools.lru_cache(maxsize=None)
+def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(128, 192, 256)):
+    """(block_n, split_k) minimising a small cost model of the persistent kernel: CTAs take ceil(tiles / SMs) tiles
+    each; a tile costs max(main loop, epilogue) because the two overlap through the TMEM accumulator ring."""
+    best = None
+    for bn in candidates:
+        if bn > 64 and N <= bn // 2 and bn != candidates[0]:
+            continue
+        tiles = cdiv(M, 128) * cdiv(N, bn) * batch
+        splits = [1]
+        if allow_split:
+            splits += [s for s in (2, 3, 4, 6, 8, 12, 16) if s <= k_blocks // 4]
+        for sp in splits:
+            kind = "atomic" if sp > 1 else epi
+            epi_clk = _EPI_CLK_PER_COL[kind] * bn
+            main = cdiv(k_blocks, sp) * _MMA_CLK[bn]
+            per_cta = cdiv(tiles * sp, NUM_SMS)
+            cost = per_cta * max(main, epi_clk) + epi_clk + 2000 + (1500 if sp > 1 else 0)
+            if best is None or cost < best[0]:
+                best = (cost, bn, sp)
+    return best[1], best[2]
+
+
 def _split_k(M, N, k_blocks, batch=1):
     """split the contraction so that at least ~one wave of CTAs exists (fp32 atomics into a zeroed C)"""
     tiles = cdiv(M, 128) * cdiv(N, _pick_bn(N)) * batch
@@ -85,8 +113,10 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
     N = w.shape[0]
     a = Op(x, (K, M), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
+    epi = "gelu" if act == ACT_GELU else ("f32" if c_dtype == OUT_F32 else "bf16")
+    bn, _ = _tiling(M, N, cdiv(K, 64), epi=epi) if N > 128 else (0, 1)
     return _with_flops(GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
-                                aux_mode=aux_mode, bias=bias), 2 * M * N * K)
+                                aux_mode=aux_mode, bias=bias, block_n=bn), 2 * M * N * K)
 
 
 @cached_spec
@@ -96,18 +126,25 @@ def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     K = w.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
-    return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode), 2 * M * N * K)
+    epi = "gelu" if aux_mode == AUX_MUL_GELU_GRAD else ("f32" if c_dtype == OUT_F32 else "bf16")
+    bn, _ = _tiling(M, K, cdiv(N, 64), epi=epi) if K > 128 else (0, 1)
+    return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode, block_n=bn),
+                       2 * M * N * K)
 
 
 @cached_spec
 def linear_wgrad(dy, x, dw):
-    """dw[N,K] (fp32, zeroed by the caller) += dy[M,N]^T x[M,K]; both operands read MN-major, split-K."""
+    """dw[N,K] (fp32, ZEROED by the caller) += dy[M,N]^T x[M,K]; both operands read MN-major.  The tile shape is chosen
+    so that one wave of CTAs covers dw without splitting the contraction when possible (plain stores); otherwise
+    split-K partial sums are added with vector reductions."""
     M, N = dy.shape
     K = x.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     b = Op(x, (K, M), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     kb = cdiv(M, 64)
-    return _with_flops(GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC, split_k=_split_k(N, K, kb)), 2 * M * N * K)
+    bn, sp = _tiling(N, K, kb, epi="f32", allow_split=True) if K > 128 else (0, _split_k(N, K, kb))
+    return _with_flops(GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC if sp > 1 else OUT_F32, split_k=sp, block_n=bn),
+                       2 * M * N * K)
 
 
 # ------------------------------------------------------------------------------------------------ conv 1..6
@@ -153,8 +190,9 @@ def conv_wgrad(dz, x, dwk, k, s):
     a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
     b = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
     ki = cdiv(Lout, 64)
-    return _with_flops(GemmSpec(a, b, Cout, k * Cin, B * ki, dwk, k * Cin, OUT_F32_ATOMIC, k_inner=ki,
-                                split_k=_split_k(Cout, k * Cin, B * ki)), 2 * B * Lout * Cout * k * Cin)
+    bn, sp = _tiling(Cout, k * Cin, B * ki, epi="f32", allow_split=True)
+    return _with_flops(GemmSpec(a, b, Cout, k * Cin, B * ki, dwk, k * Cin, OUT_F32_ATOMIC if sp > 1 else OUT_F32,
+                                k_inner=ki, split_k=sp, block_n=bn), 2 * B * Lout * Cout * k * Cin)
 
 
 # ------------------------------------------------------------------------------------------------ pos conv

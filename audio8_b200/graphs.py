@@ -1,0 +1,79 @@
+"""Shape-keyed CUDA-graph execution of the static-shape segments of the training step.
+
+The step launches ~400 small kernels; enqueueing them from Python costs more host time than the GPU needs to run
+them.  The two segments whose shapes depend only on (batch, samples) — the conv feature encoder with its LayerNorm /
+projection, and the transformer encoder — are therefore captured once per shape signature (forward and backward
+separately, `torch.cuda.make_graphed_callables`) and replayed afterwards; everything data-dependent (span masks,
+masked-row gathers, quantizer, contrastive loss) stays eager.  Dropout stays random across replays because kernels
+read their per-step seed from device memory (ops.set_seed_source) that torch's graph-safe CUDA generator refreshes.
+
+Policy: a signature is captured when it is seen for the `A8_GRAPH_AFTER`-th time (default 2), at most
+`A8_GRAPH_SHAPES` signatures per segment are kept (default 2; further shapes run eagerly), `A8_CUDA_GRAPHS=0`
+disables the mechanism.  Captured activations live in the graph's private pool (~4 GB at B=6 x 15 s).
+"""
+import os
+
+import torch
+
+from . import _lib
+
+ENABLED = os.environ.get("A8_CUDA_GRAPHS", "1") != "0"
+MAX_SHAPES = int(os.environ.get("A8_GRAPH_SHAPES", "2"))
+CAPTURE_AFTER = int(os.environ.get("A8_GRAPH_AFTER", "2"))
+WARMUP_ITERS = 2
+
+
+def set_enabled(flag):
+    """runtime switch (bench.py turns graphs off while it brackets single launches with CUDA events)"""
+    global ENABLED
+    ENABLED = bool(flag)
+
+
+class GraphedSegment:
+    def __init__(self, name):
+        self.name = name
+        self.entries = {}  # key -> (graphed callable, kernels per replay)
+        self.seen = {}
+        self.failed = set()
+
+    def _key(self, inputs, params, extra):
+        return (tuple((tuple(t.shape), t.dtype, t.requires_grad) for t in inputs),
+                tuple((p.data_ptr(), p.requires_grad) for p in params), torch.is_grad_enabled(), extra)
+
+    def run(self, fn, inputs, params, extra=()):
+        """fn(*inputs, *params) -> tensor or tuple of tensors.  `inputs` are the tensors whose VALUES change per call
+        (fixed shapes); `params` the nn.Parameters the segment reads (their storage must not move)."""
+        if not ENABLED or not inputs[0].is_cuda or torch.cuda.is_current_stream_capturing():
+            return fn(*inputs, *params)
+        key = self._key(inputs, params, extra)
+        ent = self.entries.get(key)
+        if ent is None:
+            n = self.seen.get(key, 0) + 1
+            self.seen[key] = n
+            if n < CAPTURE_AFTER or len(self.entries) >= MAX_SHAPES or key in self.failed:
+                return fn(*inputs, *params)
+            ent = self._capture(fn, inputs, params, key)
+            if ent is None:
+                return fn(*inputs, *params)
+        graphed, n_kernels = ent
+        _lib.load().a8_launch_count_add(n_kernels)
+        return graphed(*inputs, *params)
+
+    def _capture(self, fn, inputs, params, key):
+        lib = _lib.load()
+        static_in = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in inputs)
+        n0 = lib.a8_launch_count()
+        try:
+            graphed = torch.cuda.make_graphed_callables(fn, static_in + tuple(params), num_warmup_iters=WARMUP_ITERS,
+                                                        allow_unused_input=True)
+        except Exception as e:  # an un-capturable configuration runs eagerly; a broken capture must be loud once
+            if os.environ.get("A8_GRAPH_STRICT"):
+                raise
+            self.failed.add(key)
+            import warnings
+            warnings.warn(f"audio8_b200: CUDA-graph capture of segment '{self.name}' failed, running eagerly: {e!r}")
+            return None
+        per_replay = (lib.a8_launch_count() - n0) // (WARMUP_ITERS + 1)
+        ent = (graphed, int(per_replay))
+        self.entries[key] = ent
+        return ent

@@ -205,6 +205,13 @@ class CudaBackend:
                                             _stream()), "a8_ctc_backward")
         return grad
 
+    # ------------------------------------------------------------------ dropout seeds
+    def set_seed_source(self, t):
+        """t: int64 CUDA tensor with one element (or None): added to the seed argument of every later dropout-capable
+        launch, read on the device at run time (CUDA-graph replays see the refreshed value)"""
+        assert t is None or (t.is_cuda and t.dtype == torch.int64 and t.numel() >= 1)
+        self.lib.a8_set_seed_source(_ptr(t))
+
     # ------------------------------------------------------------------ row kernels
     def layernorm_fwd(self, x, gamma, beta, eps, h=None, p_h=0.0, seed_h=0, want_f32=False, p_y=0.0, seed_y=0):
         """returns y (bf16), y_f32 or None, s (bf16: x + drop(h), or x itself when h is None), mean, rstd"""

@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from .functional import BF16, F32
+from .graphs import GraphedSegment
 
 CONV_FEATURES = {
     16: [(512, 10, 5), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 2, 2), (512, 2, 2)],
@@ -267,7 +268,7 @@ class AudioTransformerEncoder(nn.Module):
         self.transformer = _Stack(d_model, d_ff if d_ff else 4 * d_model, layers)
         self.ln = _Affine(d_model)
         self._arena = {}  # persistent bf16 operand buffers + device pointer table (values rewritten every call)
-        self._flat = None
+        self._graph = GraphedSegment("transformer encoder")
 
     def forward(self, x, pad_mask=None):
         return self.extract_features(x, pad_mask)
@@ -288,8 +289,15 @@ class AudioTransformerEncoder(nn.Module):
         for layer in self.transformer.encoders:
             flat += layer.flat()
         pc = self.pos_conv.conv[1]
-        return Fn.EncoderFn.apply(x, cfg, row_keep, pc.weight_g, pc.weight_v, pc.bias, self.ln.weight, self.ln.bias,
-                                  *flat)
+        params = (pc.weight_g, pc.weight_v, pc.bias, self.ln.weight, self.ln.bias, *flat)
+        if not all(active):  # LayerDrop changes the launch sequence per step: eager
+            return Fn.EncoderFn.apply(x, cfg, row_keep, *params)
+        # static shapes: replay a captured CUDA graph once this (shape, mode) has been seen before (graphs.py)
+        if row_keep is None:
+            return self._graph.run(lambda x_, *ps: Fn.EncoderFn.apply(x_, cfg, None, *ps), (x,), params,
+                                   extra=(self.training, self.pdrop))
+        return self._graph.run(lambda x_, rk, *ps: Fn.EncoderFn.apply(x_, cfg, rk, *ps), (x, row_keep), params,
+                               extra=(self.training, self.pdrop))
 
 
 class Wav2Vec2Encoder(nn.Module):
@@ -385,16 +393,26 @@ class Wav2Vec2Model(nn.Module):
         self.timestep_mask_len = timestep_mask_len
         self.channel_mask_len = channel_mask_len
         self.mask_emb = nn.Parameter(torch.FloatTensor(d_model).uniform_())
+        self._front_graph = GraphedSegment("conv feature encoder + LayerNorm + input projection")
+
+    def _front(self, x, *_params):
+        """audio -> (projected, dropped-out features bf16 [B,T,D], un-projected LayerNorm output fp32 [B,T,512]);
+        reference :929-935.  `_params` only names the parameters for the graph capture's input surface."""
+        fx = self.feature_extractor.forward_channels_last(x)
+        features, unmasked = Fn.layer_norm(fx, self.layer_norm.weight, self.layer_norm.bias, 1e-5, want_f32=True)
+        features = self.proj_to_input(features)
+        features = Fn.dropout(features, self.dropout_input_p, self.training)
+        return features, unmasked
 
     def set_num_updates(self, s):
         self.quantizer.set_num_updates(s)
 
     def forward(self, x):
-        fx = self.feature_extractor.forward_channels_last(x)
-        features, unmasked = Fn.layer_norm(fx, self.layer_norm.weight, self.layer_norm.bias, 1e-5, want_f32=True)
+        front_params = (*self.feature_extractor.parameters(), self.layer_norm.weight, self.layer_norm.bias,
+                        *self.proj_to_input.parameters())
+        features, unmasked = self._front_graph.run(self._front, (x,), front_params,
+                                                   extra=(self.training, self.dropout_input_p))
         B, T, C = unmasked.shape
-        features = self.proj_to_input(features)
-        features = Fn.dropout(features, self.dropout_input_p, self.training)
         # masking runs in eval mode too (reference :937 has no training guard)
         time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
         rows = _mask_rows(time_mask, x.device)

@@ -29,6 +29,8 @@ int a8_version(void);
 const char* a8_last_error(void);
 /* number of kernels launched by this library in this process since load (bench.py reports the delta) */
 int64_t a8_launch_count(void);
+/* account for kernels launched by replaying a captured CUDA graph (the host-side counter cannot see them) */
+int a8_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * tcgen05 / TMEM / TMA GEMM core.
@@ -123,8 +125,12 @@ int a8_ctc_backward(const float* log_probs, int64_t stride_t, int64_t stride_b, 
  *   fwd:  s = x + drop_h(h);  y = drop_y(LN(s)*gamma + beta);  h, s_out, y_f32 optional (NULL)
  *   bwd:  g = drop_y(dy (+ dy_f32));  ds = dLN(g);  dh = drop_h(ds) (optional);
  *         dgamma/dbeta/dbias_h (= column sum of dh, or of ds when dh is NULL) are ACCUMULATED (zero them first)
- * Dropout masks are regenerated from (seed, element index): Philox-4x32, nothing is stored.
+ * Dropout masks are regenerated from (seed, element index): Philox-4x32, nothing is stored.  The effective seed of
+ * every dropout-capable launch is `seed argument + *seed_source`: a8_set_seed_source() names a 64-bit word in DEVICE
+ * memory (or NULL = 0) that subsequent launches of the calling host thread read at run time, so a captured CUDA graph
+ * draws fresh masks on each replay when the caller refreshes that word (torch's CUDA generator does, graph-safely).
  * ---------------------------------------------------------------------------------------------- */
+int a8_set_seed_source(const void* dev_u64);
 int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_t seed_h, void* s_out, const float* gamma,
                      const float* beta, float eps, void* y, float* y_f32, float p_y, uint64_t seed_y, float* mean,
                      float* rstd, int32_t R, int32_t C, void* stream);

@@ -13,6 +13,9 @@ from audio8_b200 import ops  # noqa: E402
 from audio8_b200.ops import ACT_GELU, AUX_ADD, AUX_MUL_GELU_GRAD, OUT_F32  # noqa: E402
 
 dev = "cuda"
+if os.environ.get("BN"):  # experiment: force the N tile (and optionally split-K) chosen by gemm_specs._tiling
+    _orig = G._tiling
+    G._tiling = lambda *a, **k: (int(os.environ["BN"]), int(os.environ.get("SPLIT", _orig(*a, **k)[1]) if k.get("allow_split") else 1))
 bf = torch.bfloat16
 be = ops.backend()
 
@@ -32,6 +35,8 @@ cases["ffn2_dgrad*gelu' 4494x3072x768"] = lambda: G.linear_dgrad(r(M, D), r(D, F
 cases["ffn1_dgrad+add 4494x768x3072"] = lambda: G.linear_dgrad(r(M, F_), r(F_, D), torch.empty(M, D, device=dev, dtype=bf), aux=r(M, D), aux_mode=AUX_ADD)
 cases["ffn_wgrad 3072x768x4494"] = lambda: G.linear_wgrad(r(M, F_), r(M, D), torch.zeros(F_, D, device=dev))
 cases["qkv_wgrad 2304x768x4494"] = lambda: G.linear_wgrad(r(M, 3 * D), r(M, D), torch.zeros(3 * D, D, device=dev))
+cases["wo_wgrad 768x768x4494"] = lambda: G.linear_wgrad(r(M, D), r(M, D), torch.zeros(D, D, device=dev))
+cases["qkv_dgrad+add 4494x768x2304"] = lambda: G.linear_dgrad(r(M, 3 * D), r(3 * D, D), torch.empty(M, D, device=dev, dtype=bf), aux=r(M, D), aux_mode=AUX_ADD)
 cases["attn_scores"] = lambda: G.attn_scores(r(B, T, 3 * D), torch.empty(B, H, T, Tp, device=dev), H, 0.125)
 cases["attn_context"] = lambda: G.attn_context(r(B, H, T, Tp), r(B, T, 3 * D), torch.empty(B, T, D, device=dev, dtype=bf), H)
 cases["attn_dk"] = lambda: G.attn_dk(r(B, H, T, Tp), r(B, T, 3 * D), torch.empty(B, T, 3 * D, device=dev, dtype=bf), H, 0.125)

@@ -101,7 +101,12 @@ class EmuBackend:
         emu_gemm(g.spec() if hasattr(g, "spec") else g)
 
 
+_SEED_SRC = [None]
+
+
 def _drop_mask(shape, p, seed):
+    if _SEED_SRC[0] is not None:
+        seed = int(seed) + int(_SEED_SRC[0].reshape(-1)[0].item())
     """consistent between forward and backward within the emulation (not bit-identical to the CUDA Philox stream)"""
     if p <= 0:
         return torch.ones(shape)
@@ -117,6 +122,9 @@ class EmuOps(EmuBackend):
     """row / index / loss kernels of the ABI, emulated with fp32 PyTorch math and bf16 storage"""
 
     # ---- layernorm
+    def set_seed_source(self, t):
+        _SEED_SRC[0] = t
+
     def layernorm_fwd(self, x, gamma, beta, eps, h=None, p_h=0.0, seed_h=0, want_f32=False, p_y=0.0, seed_y=0):
         s = x
         if h is not None:

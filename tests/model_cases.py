@@ -157,3 +157,50 @@ def run_acoustic_case(device, mode="train"):
     check_param_grads([(k, p.grad) for k, p in model.named_parameters()],
                       {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sdg.items()})
     return loss.item(), loss2.item()
+
+
+def run_graph_case():
+    """CUDA-graph replays of the static segments (audio8_b200/graphs.py) against the eager launch sequence of the
+    same kernels: same loss / gradients (up to fp32 atomic ordering), and dropout that still varies per replay."""
+    from audio8_b200 import graphs
+    from audio8_b200 import wav2vec2 as W
+    cfg = dict(TINY_PRE)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg).cuda().train()
+    loss_fn = W.create_loss(cfg["num_vq_vars"] * cfg["num_vq_groups"], 10)
+    x = torch.randn(2, 16000, device="cuda") * 0.1
+
+    def step():
+        np.random.seed(5)
+        torch.manual_seed(5)
+        model.zero_grad(set_to_none=True)
+        loss = loss_fn(model, x)
+        loss.backward()
+        return loss.item(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    was = graphs.ENABLED
+    try:
+        graphs.set_enabled(False)
+        l0, g0 = step()
+        graphs.set_enabled(True)
+        for _ in range(3):
+            l1, g1 = step()
+        assert model._front_graph.entries and model.encoder._graph.entries, "segments were not captured"
+        assert abs(l0 - l1) <= 1e-4 * abs(l0), (l0, l1)
+        assert set(g0) == set(g1)
+        for k in g0:
+            grad_close(g1[k], g0[k], "graph vs eager grad " + k, cos_min=0.9999, rel_max=1e-2)
+        # dropout: fresh masks on every replay, reproducible under torch.manual_seed
+        enc = W.AudioTransformerEncoder(2, 128, 0.1, layers=1, d_ff=256).cuda().train()
+        h = (torch.randn(2, 49, 128, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+        outs = []
+        for i in range(5):
+            torch.manual_seed(100 + (i if i < 4 else 3))
+            outs.append(enc(h).detach().float().clone())
+        assert enc._graph.entries
+        assert (outs[2] - outs[3]).abs().max().item() > 1e-3, "dropout mask did not change between graph replays"
+        assert torch.equal(outs[3], outs[4]), "same torch seed must give the same dropout mask"
+    finally:
+        graphs.set_enabled(was)
+    return l0, l1

@@ -24,3 +24,8 @@ def test_pretrain_cuda(mode):
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_acoustic_cuda(mode):
     model_cases.run_acoustic_case("cuda", mode)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager():
+    model_cases.run_graph_case()
