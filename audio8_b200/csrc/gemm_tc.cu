@@ -413,7 +413,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled is a DRIVER entry point: it fails with CUDA_ERROR_INVALID_CONTEXT on a host thread that
+// has not touched the runtime yet (e.g. autograd's worker thread on its first backward).  Bind the primary context.
+void ensure_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(dev);
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 int make_tmap(CUtensorMap* out, const a8_operand_t& v, int box0, int box1, const char* what) {
+  ensure_context();
   EncodeTiledFn fn = get_encode_fn();
   A8_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[4];

@@ -41,8 +41,9 @@ class GraphedSegment:
                 tuple((p.data_ptr(), p.requires_grad) for p in params), torch.is_grad_enabled(), extra)
 
     def run(self, fn, inputs, params, extra=()):
-        """fn(*inputs, *params) -> tensor or tuple of tensors.  `inputs` are the tensors whose VALUES change per call
-        (fixed shapes); `params` the nn.Parameters the segment reads (their storage must not move)."""
+        """fn(*inputs, *params) -> tensor or tuple of tensors, FUNCTIONAL in both (it must not reach parameters through
+        module attributes).  `inputs` are the tensors whose VALUES change per call (fixed shapes); `params` the
+        nn.Parameters the segment reads (their storage must not move)."""
         if not ENABLED or not inputs[0].is_cuda or torch.cuda.is_current_stream_capturing():
             return fn(*inputs, *params)
         key = self._key(inputs, params, extra)
@@ -62,9 +63,13 @@ class GraphedSegment:
     def _capture(self, fn, inputs, params, key):
         lib = _lib.load()
         static_in = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in inputs)
+        # The capture runs on ALIASES of the parameters (same storage, fresh autograd leaves).  The real parameters'
+        # AccumulateGrad nodes belong to whatever stream first used them — normally the legacy default stream — and
+        # the autograd engine would try to make that stream wait on the capturing one, which CUDA forbids.
+        alias = tuple(p.detach().requires_grad_(p.requires_grad) for p in params)
         n0 = lib.a8_launch_count()
         try:
-            graphed = torch.cuda.make_graphed_callables(fn, static_in + tuple(params), num_warmup_iters=WARMUP_ITERS,
+            graphed = torch.cuda.make_graphed_callables(fn, static_in + alias, num_warmup_iters=WARMUP_ITERS,
                                                         allow_unused_input=True)
         except Exception as e:  # an un-capturable configuration runs eagerly; a broken capture must be loud once
             if os.environ.get("A8_GRAPH_STRICT"):

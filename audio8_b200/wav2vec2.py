@@ -57,10 +57,62 @@ def create_mask(shape, p_start=0.65, mask_length=10):
     return mask
 
 
+class _PinnedRing:
+    """Persistent pinned staging memory for the small per-step index uploads (mask rows, negative indices), used as a
+    ring: a slice is reused only after the copy that last read it has completed (CUDA event per slice).  Neither a
+    pageable source (the copy would make the host wait for all queued GPU work) nor per-call pinned allocations
+    (cudaHostAlloc costs milliseconds) are acceptable inside the step."""
+
+    def __init__(self, nbytes=8 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        self.off = 0
+        self.inflight = []  # (start, end, event)
+
+    def upload(self, src, device):
+        n = src.numel() * src.element_size()
+        if n > self.buf.numel():
+            self.__init__(2 * n)
+        start = (self.off + 255) & ~255
+        if start + n > self.buf.numel():
+            start = 0
+        end = start + n
+        keep = []
+        for (a, b, ev) in self.inflight:
+            if a < end and start < b:
+                ev.synchronize()
+            elif not ev.query():
+                keep.append((a, b, ev))
+        self.inflight = keep
+        stage = self.buf[start:end].view(src.dtype).view(src.shape)
+        stage.copy_(src)
+        out = stage.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.inflight.append((start, end, ev))
+        self.off = end
+        return out
+
+
+_RING = {}
+
+
+def _to_device(arr, device):
+    """numpy -> device, asynchronously (through the pinned ring)"""
+    src = torch.from_numpy(np.ascontiguousarray(arr))
+    device = torch.device(device)
+    if device.type != "cuda" or src.numel() == 0:
+        return src.to(device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ring = _RING.get(key)
+    if ring is None:
+        ring = _RING[key] = _PinnedRing()
+    return ring.upload(src, device)
+
+
 def _mask_rows(mask_np, device):
     """flat row indices (b*T + t, row-major: the order boolean indexing produces) as int32 on the device"""
     idx = np.flatnonzero(mask_np.reshape(-1)).astype(np.int32)
-    return torch.from_numpy(idx).to(device, non_blocking=True)
+    return _to_device(idx, device)
 
 
 class Sampler:
@@ -340,7 +392,7 @@ class Wav2Vec2Encoder(nn.Module):
             features = Fn.RowsSetFn.apply(features, _mask_rows(time_mask, x.device), self.mask_emb)
         if self.training and self.channel_masking > 0.0:
             channel_mask = create_mask((B, C), p_start=self.channel_masking, mask_length=self.channel_mask_len)
-            cz = torch.from_numpy(channel_mask.astype(np.uint8)).to(x.device, non_blocking=True)
+            cz = _to_device(channel_mask.astype(np.uint8), x.device)
             features = Fn.MaskApplyFn.apply(features, None, cz)
         out = self.encoder(features, pad_mask)
         return out, pad_mask
@@ -395,12 +447,21 @@ class Wav2Vec2Model(nn.Module):
         self.mask_emb = nn.Parameter(torch.FloatTensor(d_model).uniform_())
         self._front_graph = GraphedSegment("conv feature encoder + LayerNorm + input projection")
 
-    def _front(self, x, *_params):
+    def _front_params(self):
+        fe = self.feature_extractor
+        gn = fe.conv_layers[0][2]
+        return (gn.weight, gn.bias, *[layer[0].weight for layer in fe.conv_layers], self.layer_norm.weight,
+                self.layer_norm.bias, self.proj_to_input.layer.weight, self.proj_to_input.layer.bias)
+
+    def _front(self, x, gn_w, gn_b, *rest):
         """audio -> (projected, dropped-out features bf16 [B,T,D], un-projected LayerNorm output fp32 [B,T,512]);
-        reference :929-935.  `_params` only names the parameters for the graph capture's input surface."""
-        fx = self.feature_extractor.forward_channels_last(x)
-        features, unmasked = Fn.layer_norm(fx, self.layer_norm.weight, self.layer_norm.bias, 1e-5, want_f32=True)
-        features = self.proj_to_input(features)
+        reference :929-935.  Functional in the parameters (order of `_front_params`) so that a CUDA-graph capture can
+        run it on aliases of them (graphs.py)."""
+        n = len(self.feature_extractor.spec)
+        conv_w, (ln_w, ln_b, pw, pb) = rest[:n], rest[n:]
+        fx = Fn.ConvFeatureFn.apply(x, self.feature_extractor.spec, gn_w, gn_b, *conv_w)
+        features, unmasked = Fn.layer_norm(fx, ln_w, ln_b, 1e-5, want_f32=True)
+        features = Fn.linear(features, pw, pb)
         features = Fn.dropout(features, self.dropout_input_p, self.training)
         return features, unmasked
 
@@ -408,9 +469,7 @@ class Wav2Vec2Model(nn.Module):
         self.quantizer.set_num_updates(s)
 
     def forward(self, x):
-        front_params = (*self.feature_extractor.parameters(), self.layer_norm.weight, self.layer_norm.bias,
-                        *self.proj_to_input.parameters())
-        features, unmasked = self._front_graph.run(self._front, (x,), front_params,
+        features, unmasked = self._front_graph.run(self._front, (x,), self._front_params(),
                                                    extra=(self.training, self.dropout_input_p))
         B, T, C = unmasked.shape
         # masking runs in eval mode too (reference :937 has no training guard)
@@ -425,7 +484,7 @@ class Wav2Vec2Model(nn.Module):
         q, vq_probs = self.quantizer(y)
         y = self.project_q(q, out_f32=True)
         xo = self.final_proj(enc, out_f32=True)
-        mask_t = torch.from_numpy(time_mask).to(x.device, non_blocking=True)
+        mask_t = _to_device(time_mask, x.device)
         mask_t.a8_rows = rows
         return xo, y, vq_probs, mask_t
 
@@ -448,7 +507,7 @@ class Wav2Vec2Loss(nn.Module):
         xm = Fn.RowsGatherFn.apply(outputs, rows)  # outputs[time_mask] -> [B*Tm, C]
         neg = self.sample.indices(B, Tm)  # numpy, bit-exact with the reference's Sampler
         self.last_neg_idx = neg
-        idx = torch.from_numpy(neg.astype(np.int32)).to(outputs.device, non_blocking=True)
+        idx = _to_device(neg.astype(np.int32), outputs.device)
         loss, _ = Fn.ContrastiveFn.apply(xm, latents.reshape(B * Tm, C), idx, gs_probs, self.n_vars, XE_WGT,
                                          DIVERSITY_WGT)
         return loss
