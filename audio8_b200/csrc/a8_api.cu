@@ -24,8 +24,14 @@ int check_launch(const char* what) {
   }
   return 0;
 }
+static thread_local const unsigned long long* g_seed_src = nullptr;
+const unsigned long long* seed_source() { return g_seed_src; }
 }  // namespace a8
 
+extern "C" int a8_set_seed_source(const void* dev_u64) {
+  a8::g_seed_src = static_cast<const unsigned long long*>(dev_u64);
+  return 0;
+}
 extern "C" int a8_version(void) { return A8_ABI_VERSION; }
 extern "C" const char* a8_last_error(void) { return a8::g_err; }
 extern "C" int64_t a8_launch_count(void) { return (int64_t)a8::g_launches.load(); }

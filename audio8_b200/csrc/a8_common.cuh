@@ -98,6 +98,10 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float cdf = 0.5f + copysignf(half_erf, x);
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
+// per-step dropout seed word in device memory (a8_set_seed_source), nullable
+__device__ __forceinline__ unsigned long long seed_base_ld(const unsigned long long* src) {
+  return src != nullptr ? __ldg(src) : 0ull;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

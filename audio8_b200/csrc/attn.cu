@@ -1,0 +1,785 @@
+// audio8_b200 — fused scaled-dot-product attention for sm_100a (d_k = 64): forward, dQ and dK/dV kernels.
+//
+// Replaces eight_mile's SeqScaledDotProductAttention as called through `wav2vec2.py:644` (QK^T * d_k^-1/2,
+// masked_fill(pad, -1e9), softmax, dropout, PV) and its autograd.  The [B,H,T,T] score / probability tensors are
+// never written to HBM (the reference materialises 161 MB per layer at base / 15 s): scores live in TMEM, the
+// probabilities go back to TMEM as the bf16 A-operand of the next tcgen05.mma.
+//
+// All three kernels share one shape: a CTA owns 128 rows (queries, or keys in the dK/dV kernel) and walks over
+// 128-wide blocks of the other sequence axis;
+//   warp 0  TMA producer (Q/K/V/dO tiles of the fused [B,T,3D] projection buffer, 128B swizzle, 2-stage ring)
+//   warp 1  tcgen05.mma issuer: "score" MMAs (both operands from smem) into TMEM, then "accumulate" MMAs whose
+//           A operand is the packed bf16 tile the math warps stored into TMEM (B = smem tile read MN-major)
+//   warp 2  TMEM allocator
+//   warps 4..  one thread per TMEM lane (= row): tcgen05.ld scores, exp2 / dropout / dS math, tcgen05.st
+// Softmax statistics: forward keeps a running max that is only raised when a block exceeds it by 2^8 (then the
+// O accumulator is rescaled through registers), so the common case is a single pass per block; log2-sum-exp is
+// saved per row and the backward kernels recompute probabilities from it.
+// Dropout: keep decisions are a pure function of (seed, b, h, q, k) (2 multiplies per 2x2 patch of the score
+// matrix, usable from both orientations), regenerated in backward; nothing is stored.
+#include "a8_common.cuh"
+#include "a8_tmap.cuh"
+#include "../../include/audio8_b200.h"
+
+namespace a8 {
+
+const unsigned long long* seed_source();  // a8_api.cu
+
+namespace {
+
+constexpr uint32_t TILE = 128 * 64 * 2;  // one [128 x 64] bf16 tile, 128B rows
+constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);  // f32 acc, bf16 A/B, M=128
+constexpr uint32_t IDESC_S = IDESC_BASE | ((uint32_t)(128 >> 3) << 17);                 // N=128, A and B K-major
+constexpr uint32_t IDESC_ACC = IDESC_BASE | ((uint32_t)(64 >> 3) << 17) | (1u << 16);   // N=64, B MN-major
+
+struct AttnArgs {
+  int B, H, T, nblk;
+  const unsigned char* key_keep;  // [B,T] or null
+  float scale, scale_log2, keep_scale;
+  uint32_t thr;                   // keep iff 16-bit field >= thr
+  unsigned long long seed;
+  const unsigned long long* seed_src;
+  __nv_bfloat16* ctx;             // fwd out [B,T,D]
+  const __nv_bfloat16* ctx_in;    // bwd in
+  const __nv_bfloat16* dctx;      // bwd in
+  float* lse;                     // [B,H,T]  log2-sum-exp2 of the scaled scores
+  float* delta;                   // [B,H,T]  rowsum(dO * O)
+  __nv_bfloat16* dqkv;            // bwd out [B,T,3D]
+};
+
+// ---------------------------------------------------------------------------------------------- dropout hash
+__device__ __forceinline__ uint32_t hmix(uint32_t x) {
+  x *= 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(unsigned long long seed, int bh) {
+  return hmix((uint32_t)seed ^ hmix((uint32_t)(seed >> 32) + 0x9E3779B1u * (uint32_t)(bh + 1)));
+}
+// word for the 2x2 patch (q>>1, k>>1), q even; fields: k even -> low 16 bits, k odd -> high 16 bits
+__device__ __forceinline__ uint32_t drop_word0(uint32_t key, int qp, int kp) {
+  return hmix((((uint32_t)qp << 16) | (uint32_t)kp) ^ key);
+}
+__device__ __forceinline__ uint32_t drop_word1(uint32_t w0) {  // same patch, q odd
+  const uint32_t w = w0 * 0xC2B2AE3Du;
+  return w ^ (w >> 15);
+}
+
+__device__ __forceinline__ uint32_t valid_word(const unsigned char* keep, int T, int k0) {
+  uint32_t w = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int k = k0 + i;
+    if (k < T && (keep == nullptr || keep[k] != 0)) w |= (1u << i);
+  }
+  return w;
+}
+
+// shared prologue: barrier ids are kernel specific; TMEM allocation by warp 2
+__device__ __forceinline__ uint32_t bar_at(uint32_t bars, int i) { return bars + 8u * i; }
+
+// ================================================================================================ forward
+// TMEM columns: S [0,128)  P (packed bf16) [128,192)  O [192,256)
+template <bool DROP>
+__global__ void __launch_bounds__(256, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = base + TILE, sV = base + 3 * TILE;
+  const uint32_t bars = base + 5 * TILE;
+  enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, P_READY = 6, PV_DONE = 7 };
+  const uint32_t tmem_slot = bars + 64;
+  uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = a.nblk;
+  const int qb = blockIdx.x % nblk;
+  const int bh = blockIdx.x / nblk;
+  const int h = bh % a.H, b = bh / a.H;
+  const int D = a.H * 64;
+
+  if (warp == 0) {
+    if (elect_one()) tma_prefetch_desc(&map_qkv);
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(bar_at(bars, Q_FULL), 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_at(bars, KV_FULL + i), 1);
+        mbar_init(bar_at(bars, KV_EMPTY + i), 1);
+      }
+      mbar_init(bar_at(bars, S_FULL), 1);
+      mbar_init(bar_at(bars, P_READY), 128);
+      mbar_init(bar_at(bars, PV_DONE), 1);
+      mbar_fence_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+  } else if (warp >= 4) {
+    const unsigned char* keep = a.key_keep ? a.key_keep + (long long)b * a.T : nullptr;
+    for (int w = threadIdx.x - 128; w < nblk * 4; w += 128) sValid[w] = valid_word(keep, a.T, w * 32);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_at(bars, Q_FULL), TILE);
+      tma_load_3d(&map_qkv, bar_at(bars, Q_FULL), sQ, h * 64, qb * 128, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_at(bars, KV_EMPTY + st), ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(bar_at(bars, KV_FULL + st), 2 * TILE);
+        tma_load_3d(&map_qkv, bar_at(bars, KV_FULL + st), sK + st * TILE, D + h * 64, j * 128, b);
+        tma_load_3d(&map_qkv, bar_at(bars, KV_FULL + st), sV + st * TILE, 2 * D + h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
+      auto issue_pv = [&](int j) {
+        const uint32_t v = sV + (j & 1) * TILE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tO, tP + k * 8, umma_smem_desc(v + k * 2048, 8192, 1024), IDESC_ACC, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_at(bars, KV_EMPTY + (j & 1)));
+        umma_commit(bar_at(bars, PV_DONE));
+      };
+      mbar_wait(bar_at(bars, Q_FULL), 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_at(bars, KV_FULL + st), (j >> 1) & 1);
+        if (j > 0) mbar_wait(bar_at(bars, P_READY), (j - 1) & 1);
+        tc_fence_after();
+        const uint32_t kk = sK + st * TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(bar_at(bars, S_FULL));
+        if (j > 0) issue_pv(j - 1);
+      }
+      mbar_wait(bar_at(bars, P_READY), (nblk - 1) & 1);
+      tc_fence_after();
+      issue_pv(nblk - 1);
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int row = qb * 128 + quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr, tP = tS + 128, tO = tS + 192;
+    const float c = a.scale_log2;
+    uint32_t dkey = 0;
+    if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(bar_at(bars, S_FULL), j & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      if (j == 0) {  // exact row max of the first block
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          tmem_ld_32x32(tS + ch * 32, r);
+          tmem_ld_wait();
+          const uint32_t word = sValid[ch];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float s = __uint_as_float(r[i]);
+            mx = fmaxf(mx, ((word >> i) & 1u) ? s : -INFINITY);
+          }
+        }
+        m = (mx == -INFINITY) ? 0.f : mx * c;
+      } else {
+        mbar_wait(bar_at(bars, PV_DONE), (j - 1) & 1);  // P buffer free, O up to date
+        tc_fence_after();
+      }
+      bool redo;
+      do {
+        float bmax = -INFINITY, lsum = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          tmem_ld_32x32(tS + ch * 32, r);
+          tmem_ld_wait();
+          const uint32_t word = sValid[j * 4 + ch];
+          const int k0 = j * 128 + ch * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float t0 = fmaf(__uint_as_float(r[i]), c, -m), t1 = fmaf(__uint_as_float(r[i + 1]), c, -m);
+            if (word != 0xFFFFFFFFu) {
+              if (!((word >> i) & 1u)) t0 = -INFINITY;
+              if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
+            }
+            bmax = fmaxf(bmax, fmaxf(t0, t1));
+            float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+            lsum += p0 + p1;
+            if (DROP) {
+              uint32_t w = drop_word0(dkey, row >> 1, (k0 + i) >> 1);
+              if (row & 1) w = drop_word1(w);
+              p0 = ((w & 0xFFFFu) >= a.thr) ? p0 : 0.f;
+              p1 = ((w >> 16) >= a.thr) ? p1 : 0.f;
+            }
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x16(tP + ch * 16, pk);
+        }
+        redo = false;
+        if (j > 0 && __any_sync(0xffffffffu, bmax > 8.f)) {
+          // this block exceeds the running max by more than 2^8: raise the max, rescale O and l, redo the block
+          const float m_new = fmaxf(m, m + bmax);
+          const float f = ex2_approx(m - m_new);
+          l *= f;
+          m = m_new;
+          tmem_st_wait();
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            tmem_ld_32x32(tO + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st_32x32(tO + ch * 32, r);
+          }
+          tmem_st_wait();
+          redo = true;
+        } else {
+          l += lsum;
+        }
+      } while (redo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_at(bars, P_READY));
+    }
+    mbar_wait(bar_at(bars, PV_DONE), (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv = l > 0.f ? a.keep_scale / l : 0.f;
+    uint32_t r[32];
+    __nv_bfloat16* dst = a.ctx + ((long long)b * a.T + row) * D + h * 64;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      tmem_ld_32x32(tO + ch * 32, r);
+      tmem_ld_wait();
+      if (row < a.T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+          o.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+          o.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+          o.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) = o;
+        }
+      }
+    }
+    if (row < a.T) a.lse[(long long)bh * a.T + row] = l > 0.f ? m + log2f(l) : INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ================================================================================================ backward: dQ
+// thread = query row; 8 math warps (two per lane quarter, each owns 64 of a block's 128 key columns)
+// TMEM columns: S [0,128)  dP [128,256)  dS packed [256,320)  dQ [320,384)
+template <bool DROP>
+__global__ void __launch_bounds__(384, 1)
+attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+               const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sdO = base + TILE, sK = base + 2 * TILE, sV = base + 4 * TILE;
+  const uint32_t bars = base + 6 * TILE;
+  enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, DS_READY = 6, DQ_DONE = 7 };
+  const uint32_t tmem_slot = bars + 64;
+  uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = a.nblk;
+  const int qb = blockIdx.x % nblk;
+  const int bh = blockIdx.x / nblk;
+  const int h = bh % a.H, b = bh / a.H;
+  const int D = a.H * 64;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(bar_at(bars, QDO_FULL), 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_at(bars, KV_FULL + i), 1);
+        mbar_init(bar_at(bars, KV_EMPTY + i), 1);
+      }
+      mbar_init(bar_at(bars, S_FULL), 1);
+      mbar_init(bar_at(bars, DS_READY), 256);
+      mbar_init(bar_at(bars, DQ_DONE), 1);
+      mbar_fence_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+  } else if (warp >= 4) {
+    const unsigned char* keep = a.key_keep ? a.key_keep + (long long)b * a.T : nullptr;
+    for (int w = threadIdx.x - 128; w < nblk * 4; w += 256) sValid[w] = valid_word(keep, a.T, w * 32);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_at(bars, QDO_FULL), 2 * TILE);
+      tma_load_3d(&map_qkv, bar_at(bars, QDO_FULL), sQ, h * 64, qb * 128, b);
+      tma_load_3d(&map_do, bar_at(bars, QDO_FULL), sdO, h * 64, qb * 128, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_at(bars, KV_EMPTY + st), ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(bar_at(bars, KV_FULL + st), 2 * TILE);
+        tma_load_3d(&map_qkv, bar_at(bars, KV_FULL + st), sK + st * TILE, D + h * 64, j * 128, b);
+        tma_load_3d(&map_qkv, bar_at(bars, KV_FULL + st), sV + st * TILE, 2 * D + h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdS = tmem_base + 256, tdQ = tmem_base + 320;
+      auto issue_dq = [&](int j) {
+        const uint32_t kk = sK + (j & 1) * TILE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tdQ, tdS + k * 8, umma_smem_desc(kk + k * 2048, 8192, 1024), IDESC_ACC, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_at(bars, KV_EMPTY + (j & 1)));
+        umma_commit(bar_at(bars, DQ_DONE));
+      };
+      mbar_wait(bar_at(bars, QDO_FULL), 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(bar_at(bars, KV_FULL + st), (j >> 1) & 1);
+        if (j > 0) mbar_wait(bar_at(bars, DS_READY), (j - 1) & 1);
+        tc_fence_after();
+        const uint32_t kk = sK + st * TILE, vv = sV + st * TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tdP, umma_smem_desc(sdO + k * 32, 0, 1024), umma_smem_desc(vv + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(bar_at(bars, S_FULL));
+        if (j > 0) issue_dq(j - 1);
+      }
+      mbar_wait(bar_at(bars, DS_READY), (nblk - 1) & 1);
+      tc_fence_after();
+      issue_dq(nblk - 1);
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int row = qb * 128 + quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr, tdP = tS + 128, tdS = tS + 256, tdQ = tS + 320;
+    const float c = a.scale_log2;
+    uint32_t dkey = 0;
+    if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
+    // delta = rowsum(dO * O); lse of this row
+    float delta = 0.f, nlse = -INFINITY;
+    if (row < a.T) {
+      const long long ro = ((long long)b * a.T + row) * D + h * 64;
+      const uint4* po = reinterpret_cast<const uint4*>(a.ctx_in + ro);
+      const uint4* pd = reinterpret_cast<const uint4*>(a.dctx + ro);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 o = __ldg(po + g), d = __ldg(pd + g);
+        const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = unpack_bf16(ow[t]), y = unpack_bf16(dw[t]);
+          delta = fmaf(x.x, y.x, delta);
+          delta = fmaf(x.y, y.y, delta);
+        }
+      }
+      nlse = -a.lse[(long long)bh * a.T + row];
+      if (half == 0) a.delta[(long long)bh * a.T + row] = delta;
+    }
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(bar_at(bars, S_FULL), j & 1);
+      tc_fence_after();
+      if (j > 0) {
+        mbar_wait(bar_at(bars, DQ_DONE), (j - 1) & 1);  // dS buffer consumed
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = half * 64 + cc * 32;
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(tS + col0, rs);
+        tmem_ld_32x32(tdP + col0, rp);
+        tmem_ld_wait();
+        const uint32_t word = sValid[j * 4 + (col0 >> 5)];
+        const int k0 = j * 128 + col0;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float t0 = fmaf(__uint_as_float(rs[i]), c, nlse), t1 = fmaf(__uint_as_float(rs[i + 1]), c, nlse);
+          if (word != 0xFFFFFFFFu) {
+            if (!((word >> i) & 1u)) t0 = -INFINITY;
+            if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
+          }
+          const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+          float d0 = __uint_as_float(rp[i]), d1 = __uint_as_float(rp[i + 1]);
+          if (DROP) {
+            uint32_t w = drop_word0(dkey, row >> 1, (k0 + i) >> 1);
+            if (row & 1) w = drop_word1(w);
+            d0 = ((w & 0xFFFFu) >= a.thr) ? d0 * a.keep_scale : 0.f;
+            d1 = ((w >> 16) >= a.thr) ? d1 * a.keep_scale : 0.f;
+          }
+          pk[i >> 1] = pack_bf16(p0 * (d0 - delta) * a.scale, p1 * (d1 - delta) * a.scale);
+        }
+        tmem_st_32x16(tdS + (col0 >> 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_at(bars, DS_READY));
+    }
+    mbar_wait(bar_at(bars, DQ_DONE), (nblk - 1) & 1);
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld_32x32(tdQ + half * 32, r);
+    tmem_ld_wait();
+    if (row < a.T) {
+      __nv_bfloat16* dst = a.dqkv + ((long long)b * a.T + row) * (3 * D) + h * 64 + half * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+        o.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+        o.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+        o.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================ backward: dK, dV
+// thread = key row, walks over query blocks.  TMEM columns:
+//   S^T [0,128)  dP^T [128,256)  P^T packed [256,320)  dS^T packed [320,384)  dV [384,448)  dK [448,512)
+template <bool DROP>
+__global__ void __launch_bounds__(384, 1)
+attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = base + TILE, sQ = base + 2 * TILE, sdO = base + 4 * TILE;
+  const uint32_t bars = base + 6 * TILE;
+  enum { KV_FULL = 0, Q_FULL = 1, Q_EMPTY = 3, S_FULL = 5, PS_READY = 6, ACC_DONE = 7 };
+  const uint32_t tmem_slot = bars + 64;
+  float* sStat = reinterpret_cast<float*>(smem_raw + (bars + 128 - raw));  // [2 stages][nlse 128 | delta 128]
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = a.nblk;
+  const int kb = blockIdx.x % nblk;
+  const int bh = blockIdx.x / nblk;
+  const int h = bh % a.H, b = bh / a.H;
+  const int D = a.H * 64;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(bar_at(bars, KV_FULL), 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_at(bars, Q_FULL + i), 1);
+        mbar_init(bar_at(bars, Q_EMPTY + i), 1);
+      }
+      mbar_init(bar_at(bars, S_FULL), 1);
+      mbar_init(bar_at(bars, PS_READY), 256);
+      mbar_init(bar_at(bars, ACC_DONE), 1);
+      mbar_fence_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // whole warp: lanes stage the per-query statistics of each block, lane 0 drives TMA and the barriers
+    if (lane == 0) {
+      mbar_expect_tx(bar_at(bars, KV_FULL), 2 * TILE);
+      tma_load_3d(&map_qkv, bar_at(bars, KV_FULL), sK, D + h * 64, kb * 128, b);
+      tma_load_3d(&map_qkv, bar_at(bars, KV_FULL), sV, 2 * D + h * 64, kb * 128, b);
+    }
+    for (int i = 0; i < nblk; ++i) {
+      const int st = i & 1;
+      mbar_wait(bar_at(bars, Q_EMPTY + st), ((i >> 1) & 1) ^ 1u);
+      float* dst = sStat + st * 256;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int q = i * 128 + t * 32 + lane;
+        const bool ok = q < a.T;
+        dst[t * 32 + lane] = ok ? -a.lse[(long long)bh * a.T + q] : -INFINITY;  // -inf: p == 0 for q >= T
+        dst[128 + t * 32 + lane] = ok ? a.delta[(long long)bh * a.T + q] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(bar_at(bars, Q_FULL + st), 2 * TILE);
+        tma_load_3d(&map_qkv, bar_at(bars, Q_FULL + st), sQ + st * TILE, h * 64, i * 128, b);
+        tma_load_3d(&map_do, bar_at(bars, Q_FULL + st), sdO + st * TILE, h * 64, i * 128, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tPT = tmem_base + 256, tdST = tmem_base + 320,
+                     tdV = tmem_base + 384, tdK = tmem_base + 448;
+      auto issue_acc = [&](int i) {
+        const uint32_t qq = sQ + (i & 1) * TILE, dd = sdO + (i & 1) * TILE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tdV, tPT + k * 8, umma_smem_desc(dd + k * 2048, 8192, 1024), IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16_ts(tdK, tdST + k * 8, umma_smem_desc(qq + k * 2048, 8192, 1024), IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_at(bars, Q_EMPTY + (i & 1)));
+        umma_commit(bar_at(bars, ACC_DONE));
+      };
+      mbar_wait(bar_at(bars, KV_FULL), 0);
+      for (int i = 0; i < nblk; ++i) {
+        const int st = i & 1;
+        mbar_wait(bar_at(bars, Q_FULL + st), (i >> 1) & 1);
+        if (i > 0) mbar_wait(bar_at(bars, PS_READY), (i - 1) & 1);
+        tc_fence_after();
+        const uint32_t qq = sQ + st * TILE, dd = sdO + st * TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tST, umma_smem_desc(sK + k * 32, 0, 1024), umma_smem_desc(qq + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tdPT, umma_smem_desc(sV + k * 32, 0, 1024), umma_smem_desc(dd + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+        umma_commit(bar_at(bars, S_FULL));
+        if (i > 0) issue_acc(i - 1);
+      }
+      mbar_wait(bar_at(bars, PS_READY), (nblk - 1) & 1);
+      tc_fence_after();
+      issue_acc(nblk - 1);
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int key = kb * 128 + quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tST = tmem_base + lane_addr, tdPT = tST + 128, tPT = tST + 256, tdST = tST + 320, tdV = tST + 384,
+                   tdK = tST + 448;
+    const bool valid_row = key < a.T && (a.key_keep == nullptr || a.key_keep[(long long)b * a.T + key] != 0);
+    const float c = valid_row ? a.scale_log2 : 0.f;
+    const float rowoff = valid_row ? 0.f : -INFINITY;
+    uint32_t dkey = 0;
+    if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
+    for (int i = 0; i < nblk; ++i) {
+      mbar_wait(bar_at(bars, S_FULL), i & 1);  // implies Q_FULL of this stage (statistics staged) has completed
+      tc_fence_after();
+      if (i > 0) {
+        mbar_wait(bar_at(bars, ACC_DONE), (i - 1) & 1);  // P^T / dS^T buffers consumed
+        tc_fence_after();
+      }
+      const float* stat = sStat + (i & 1) * 256;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = half * 64 + cc * 32;
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32(tST + col0, rs);
+        tmem_ld_32x32(tdPT + col0, rp);
+        tmem_ld_wait();
+        const int q0 = i * 128 + col0;
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float2 nl = *reinterpret_cast<const float2*>(stat + col0 + e);
+          const float2 dl = *reinterpret_cast<const float2*>(stat + 128 + col0 + e);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), c, nl.x + rowoff));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), c, nl.y + rowoff));
+          float d0 = __uint_as_float(rp[e]), d1 = __uint_as_float(rp[e + 1]);
+          float k0 = p0, k1 = p1;
+          if (DROP) {
+            const uint32_t w0 = drop_word0(dkey, (q0 + e) >> 1, key >> 1);  // q0 + e is even
+            const uint32_t w1 = drop_word1(w0);
+            const uint32_t f0 = (key & 1) ? (w0 >> 16) : (w0 & 0xFFFFu);
+            const uint32_t f1 = (key & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
+            const bool keep0 = f0 >= a.thr, keep1 = f1 >= a.thr;
+            k0 = keep0 ? p0 : 0.f;
+            k1 = keep1 ? p1 : 0.f;
+            d0 = keep0 ? d0 * a.keep_scale : 0.f;
+            d1 = keep1 ? d1 * a.keep_scale : 0.f;
+          }
+          pp[e >> 1] = pack_bf16(k0, k1);
+          pd[e >> 1] = pack_bf16(p0 * (d0 - dl.x) * a.scale, p1 * (d1 - dl.y) * a.scale);
+        }
+        tmem_st_32x16(tPT + (col0 >> 1), pp);
+        tmem_st_32x16(tdST + (col0 >> 1), pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_at(bars, PS_READY));
+    }
+    mbar_wait(bar_at(bars, ACC_DONE), (nblk - 1) & 1);
+    tc_fence_after();
+    // half 0 writes dV (scaled by 1/(1-p)), half 1 writes dK
+    const uint32_t src = half == 0 ? tdV : tdK;
+    const float sc = half == 0 ? a.keep_scale : 1.f;
+    __nv_bfloat16* dst = a.dqkv + ((long long)b * a.T + key) * (3 * D) + (half == 0 ? 2 * D : D) + h * 64;
+    uint32_t r[32];
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      tmem_ld_32x32(src + ch * 32, r);
+      tmem_ld_wait();
+      if (key < a.T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[8 * g + 0]) * sc, __uint_as_float(r[8 * g + 1]) * sc);
+          o.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * sc, __uint_as_float(r[8 * g + 3]) * sc);
+          o.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * sc, __uint_as_float(r[8 * g + 5]) * sc);
+          o.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * sc, __uint_as_float(r[8 * g + 7]) * sc);
+          *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// keep decisions as bytes [B,H,T,T] (tests: the mask the fused kernels regenerate)
+__global__ void attn_dropmask_kernel(unsigned char* out, int B, int H, int T, uint32_t thr, unsigned long long seed,
+                                     const unsigned long long* seed_src) {
+  const long long n = (long long)B * H * T * T;
+  const unsigned long long s = seed + seed_base_ld(seed_src);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % T);
+    const int q = (int)((i / T) % T);
+    const int bh = (int)(i / ((long long)T * T));
+    uint32_t w = drop_word0(drop_key(s, bh), q >> 1, k >> 1);
+    if (q & 1) w = drop_word1(w);
+    const uint32_t f = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+    out[i] = f >= thr ? 1 : 0;
+  }
+}
+
+int fill_args(AttnArgs& a, const uint8_t* key_keep, int B, int H, int T, float scale, float pdrop, uint64_t seed) {
+  A8_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 4096, "attention: unsupported shape B=%d H=%d T=%d (T <= 4096)", B, H, T);
+  A8_REQUIRE(pdrop >= 0.f && pdrop < 1.f, "attention: dropout probability %f", pdrop);
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.T = T; a.nblk = cdiv(T, 128);
+  a.key_keep = key_keep;
+  a.scale = scale;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.thr = (uint32_t)(pdrop * 65536.f);
+  a.keep_scale = pdrop > 0.f ? 65536.f / (65536.f - (float)a.thr) : 1.f;  // exact inverse of the realised keep rate
+  a.seed = seed;
+  a.seed_src = seed_source();
+  return 0;
+}
+
+constexpr int SMEM_FWD = 5 * TILE + 1024 + 128 + 512;
+constexpr int SMEM_BWD = 6 * TILE + 1024 + 128 + 2048;
+
+template <typename K>
+int set_smem(K kern, int bytes) {
+  A8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+}  // namespace
+}  // namespace a8
+
+using namespace a8;
+
+extern "C" int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, float* lse, int32_t B, int32_t H,
+                           int32_t T, float scale, float pdrop, uint64_t seed, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AttnArgs a;
+  if (int rc = fill_args(a, key_keep, B, H, T, scale, pdrop, seed)) return rc;
+  a.ctx = static_cast<__nv_bfloat16*>(ctx);
+  a.lse = lse;
+  const long long D3 = 3ll * H * 64;
+  CUtensorMap mq;
+  if (int rc = make_tmap_3d(&mq, qkv, D3, T, B, D3, (long long)T * D3, 64, 128, "attention qkv")) return rc;
+  static bool cfg = false;
+  if (!cfg) {
+    if (int rc = set_smem(attn_fwd_kernel<false>, SMEM_FWD)) return rc;
+    if (int rc = set_smem(attn_fwd_kernel<true>, SMEM_FWD)) return rc;
+    cfg = true;
+  }
+  const int grid = a.nblk * B * H;
+  if (pdrop > 0.f) attn_fwd_kernel<true><<<grid, 256, SMEM_FWD, stream>>>(mq, a);
+  else attn_fwd_kernel<false><<<grid, 256, SMEM_FWD, stream>>>(mq, a);
+  return check_launch("attn_fwd_kernel");
+}
+
+extern "C" int a8_attn_bwd(const void* qkv, const uint8_t* key_keep, const void* ctx, const void* dctx,
+                           const float* lse, float* delta, void* dqkv, int32_t B, int32_t H, int32_t T, float scale,
+                           float pdrop, uint64_t seed, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AttnArgs a;
+  if (int rc = fill_args(a, key_keep, B, H, T, scale, pdrop, seed)) return rc;
+  a.ctx_in = static_cast<const __nv_bfloat16*>(ctx);
+  a.dctx = static_cast<const __nv_bfloat16*>(dctx);
+  a.lse = const_cast<float*>(lse);
+  a.delta = delta;
+  a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  const long long D = 1ll * H * 64, D3 = 3 * D;
+  CUtensorMap mq, md;
+  if (int rc = make_tmap_3d(&mq, qkv, D3, T, B, D3, (long long)T * D3, 64, 128, "attention qkv")) return rc;
+  if (int rc = make_tmap_3d(&md, dctx, D, T, B, D, (long long)T * D, 64, 128, "attention dctx")) return rc;
+  static bool cfg = false;
+  if (!cfg) {
+    if (int rc = set_smem(attn_dq_kernel<false>, SMEM_BWD)) return rc;
+    if (int rc = set_smem(attn_dq_kernel<true>, SMEM_BWD)) return rc;
+    if (int rc = set_smem(attn_dkv_kernel<false>, SMEM_BWD)) return rc;
+    if (int rc = set_smem(attn_dkv_kernel<true>, SMEM_BWD)) return rc;
+    cfg = true;
+  }
+  const int grid = a.nblk * B * H;
+  if (pdrop > 0.f) attn_dq_kernel<true><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
+  else attn_dq_kernel<false><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
+  if (int rc = check_launch("attn_dq_kernel")) return rc;
+  if (pdrop > 0.f) attn_dkv_kernel<true><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
+  else attn_dkv_kernel<false><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
+  return check_launch("attn_dkv_kernel");
+}
+
+extern "C" int a8_attn_dropmask(uint8_t* keep_out, int32_t B, int32_t H, int32_t T, float pdrop, uint64_t seed,
+                                void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(B > 0 && H > 0 && T > 0, "dropmask: bad shape");
+  attn_dropmask_kernel<<<148 * 4, 256, 0, stream>>>(keep_out, B, H, T, (uint32_t)(pdrop * 65536.f), seed,
+                                                     seed_source());
+  return check_launch("attn_dropmask_kernel");
+}

@@ -82,8 +82,9 @@ __global__ void conv0_stats_kernel(const double* mom, const float* w, int C, int
 }
 
 // ---------------------------------------------------------------------------------------------- main kernels
-// thread mapping shared by forward and both backward passes: 256 threads = 64 channel-octets x 4 row phases;
-// a CTA walks its [t_begin, t_end) range in tiles of TILE_T rows with the waveform window staged in smem
+// Thread mapping shared by forward and backward: one thread = 2 adjacent channels (one bf16x2 word), a CTA of C/2
+// threads walks its [t_begin, t_end) rows in tiles of TILE_T with the waveform window staged in smem (every thread
+// of the CTA reads the same window element: a broadcast).  ~70 registers per thread keep 3 CTAs per SM resident.
 struct Conv0Args {
   const float* x;
   long long L;
@@ -95,26 +96,19 @@ struct Conv0Args {
   const float* rstd;
   __nv_bfloat16* y;          // fwd out [B,L0,C]
   const __nv_bfloat16* da;   // bwd in  [B,L0,C]
-  float* sums;               // [B,C,2]: sum dy, sum dy*xhat
-  float* dw;                 // [C,k]
-  float* dgamma;
-  float* dbeta;
+  float* acc;                // bwd: [B,C,12] = sum_t dy*x_j (j<10), sum_t dy, sum_t dy*xhat
 };
 
-enum { MODE_FWD = 0, MODE_BWD_SUMS = 1, MODE_BWD_W = 2 };
-
-template <int MODE>
+template <bool BWD>
 __global__ void __launch_bounds__(256) conv0_kernel(const Conv0Args a) {
   __shared__ float xs[TILE_T * 8 + KMAX + 8];
-  __shared__ float red[(MODE == MODE_BWD_W) ? 4 * 64 * 8 * 3 : (MODE == MODE_BWD_SUMS ? 4 * 64 * 16 : 1)];
   const int b = blockIdx.y;
-  const int oct = threadIdx.x & 63, ph = threadIdx.x >> 6;
-  const int c0 = oct * 8;
+  const int c0 = threadIdx.x * 2;
   const bool active = c0 < a.C;
   const int k = a.k, s = a.s;
-  float w[8][KMAX], sc[8], sh[8], mu[8], rs[8], gm[8], bt[8];
+  float w[2][KMAX], sc[2], sh[2], mu[2], rs[2], gm[2], bt[2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int c = min(c0 + i, a.C - 1);
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) w[i][j] = (j < k) ? a.w[c * k + j] : 0.f;
@@ -125,22 +119,11 @@ __global__ void __launch_bounds__(256) conv0_kernel(const Conv0Args a) {
     sc[i] = rs[i] * gm[i];
     sh[i] = bt[i] - mu[i] * sc[i];
   }
-  float s1m[8], s2m[8];  // BWD_W: mean(dy), mean(dy*xhat) per channel
-  if (MODE == MODE_BWD_W) {
+  float acc1[2] = {0.f, 0.f}, acc2[2] = {0.f, 0.f}, accx[2][KMAX];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = min(c0 + i, a.C - 1);
-      s1m[i] = a.sums[(b * a.C + c) * 2] / (float)a.L0;
-      s2m[i] = a.sums[(b * a.C + c) * 2 + 1] / (float)a.L0;
-    }
-  }
-  float acc1[8], acc2[8], accw[8][KMAX];
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    acc1[i] = acc2[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) accw[i][j] = 0.f;
-  }
+    for (int j = 0; j < KMAX; ++j) accx[i][j] = 0.f;
 
   const float* xb = a.x + (long long)b * a.L;
   const int t_begin = blockIdx.x * a.rows_per_cta;
@@ -149,100 +132,94 @@ __global__ void __launch_bounds__(256) conv0_kernel(const Conv0Args a) {
     const int nrows = min(TILE_T, t_end - tt);
     const int nx = (nrows - 1) * s + k;
     __syncthreads();
-    for (int i = threadIdx.x; i < nx; i += 256) xs[i] = xb[(long long)tt * s + i];
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = xb[(long long)tt * s + i];
     __syncthreads();
     if (!active) continue;
-    for (int r = ph; r < nrows; r += 4) {
+    const long long off0 = ((long long)b * a.L0 + tt) * a.C + c0;
+#pragma unroll 2
+    for (int r = 0; r < nrows; ++r) {
       float xv[KMAX];
 #pragma unroll
       for (int j = 0; j < KMAX; ++j) xv[j] = (j < k) ? xs[r * s + j] : 0.f;
-      float z[8];
+      float z[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float acc = 0.f;
+      for (int i = 0; i < 2; ++i) {
+        float t = 0.f;
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) acc = fmaf(w[i][j], xv[j], acc);
-        z[i] = acc;
+        for (int j = 0; j < KMAX; ++j) t = fmaf(w[i][j], xv[j], t);
+        z[i] = t;
       }
-      const long long off = ((long long)b * a.L0 + tt + r) * a.C + c0;
-      if (MODE == MODE_FWD) {
-        uint4 o;
-        float g[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = gelu_fast(fmaf(z[i], sc[i], sh[i]));
-        o.x = pack_bf16(g[0], g[1]); o.y = pack_bf16(g[2], g[3]);
-        o.z = pack_bf16(g[4], g[5]); o.w = pack_bf16(g[6], g[7]);
-        *reinterpret_cast<uint4*>(a.y + off) = o;
+      const long long off = off0 + (long long)r * a.C;
+      if (!BWD) {
+        *reinterpret_cast<uint32_t*>(a.y + off) =
+            pack_bf16(gelu_fast(fmaf(z[0], sc[0], sh[0])), gelu_fast(fmaf(z[1], sc[1], sh[1])));
       } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(a.da + off);
-        float d[8];
-        float2 t2;
-        t2 = unpack_bf16(u.x); d[0] = t2.x; d[1] = t2.y;
-        t2 = unpack_bf16(u.y); d[2] = t2.x; d[3] = t2.y;
-        t2 = unpack_bf16(u.z); d[4] = t2.x; d[5] = t2.y;
-        t2 = unpack_bf16(u.w); d[6] = t2.x; d[7] = t2.y;
+        const float2 d = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(a.da + off)));
+        const float dd[2] = {d.x, d.y};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 2; ++i) {
           const float xh = (z[i] - mu[i]) * rs[i];
-          const float dy = d[i] * gelu_grad_fast(fmaf(xh, gm[i], bt[i]));
-          if (MODE == MODE_BWD_SUMS) {
-            acc1[i] += dy;
-            acc2[i] += dy * xh;
-          } else {
-            const float dz = sc[i] * (dy - s1m[i] - xh * s2m[i]);
+          const float dy = dd[i] * gelu_grad_fast(fmaf(xh, gm[i], bt[i]));
+          acc1[i] += dy;
+          acc2[i] = fmaf(dy, xh, acc2[i]);
 #pragma unroll
-            for (int j = 0; j < KMAX; ++j) accw[i][j] = fmaf(dz, xv[j], accw[i][j]);
-          }
+          for (int j = 0; j < KMAX; ++j) accx[i][j] = fmaf(dy, xv[j], accx[i][j]);
         }
       }
     }
   }
-  if (MODE == MODE_BWD_SUMS) {
-    // reduce the 4 row phases in smem, then one atomic per (channel, stat) per CTA
+  if (BWD && active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red[(ph * 64 + oct) * 16 + i] = acc1[i];
-      red[(ph * 64 + oct) * 16 + 8 + i] = acc2[i];
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-      const int o = e >> 4, q = e & 15;
-      const int c = o * 8 + (q & 7);
-      if (c < a.C) {
-        const float v = red[e] + red[64 * 16 + e] + red[2 * 64 * 16 + e] + red[3 * 64 * 16 + e];
-        atomicAdd(a.sums + ((long long)b * a.C + c) * 2 + (q >> 3), v);
-      }
-    }
-  } else if (MODE == MODE_BWD_W) {
-    // taps in 4 passes of 3 (smem budget): reduce phases, atomics into dw[C,k]
+    for (int i = 0; i < 2; ++i) {
+      if (c0 + i < a.C) {
+        float* dst = a.acc + ((long long)b * a.C + c0 + i) * 12;
 #pragma unroll
-    for (int j0 = 0; j0 < 12; j0 += 3) {
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj)
-          red[((ph * 64 + oct) * 8 + i) * 3 + jj] = (j0 + jj < KMAX) ? accw[i][(j0 + jj < KMAX) ? j0 + jj : 0] : 0.f;
-      __syncthreads();
-      for (int e = threadIdx.x; e < 64 * 8 * 3; e += 256) {
-        const int c = e / 3, jj = e % 3;
-        if (c < a.C && j0 + jj < k) {
-          const float v = red[e] + red[64 * 24 + e] + red[2 * 64 * 24 + e] + red[3 * 64 * 24 + e];
-          atomicAdd(a.dw + c * k + j0 + jj, v);
-        }
-      }
-    }
-    if (blockIdx.x == 0) {  // dgamma / dbeta from the pass-1 sums (one CTA per batch item adds its share)
-      for (int c = threadIdx.x; c < a.C; c += 256) {
-        atomicAdd(a.dbeta + c, a.sums[((long long)b * a.C + c) * 2]);
-        atomicAdd(a.dgamma + c, a.sums[((long long)b * a.C + c) * 2 + 1]);
+        for (int j = 0; j < KMAX; ++j) atomicAdd(dst + j, accx[i][j]);
+        atomicAdd(dst + 10, acc1[i]);
+        atomicAdd(dst + 11, acc2[i]);
       }
     }
   }
 }
 
+// dW, dgamma, dbeta from the single backward pass and the forward's window moments.  With dz = sc (dy - mean(dy) -
+// xhat mean(dy xhat)) and xhat linear in the window,  sum_t dz x_j  needs only  sum_t dy x_j  and the moments:
+//   sum_t xhat x_j = rstd ( w . R[:,j] - mean m_j )
+__global__ void conv0_bwd_finalize_kernel(const float* acc, const double* mom, const float* w, const float* gamma,
+                                          const float* mean, const float* rstd, int B, int C, int k, int L0,
+                                          float* dw, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double dwc[KMAX];
+  for (int j = 0; j < KMAX; ++j) dwc[j] = 0.0;
+  double dg = 0.0, db = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* ac = acc + ((long long)b * C + c) * 12;
+    const double* m = mom + (long long)b * NMOM;
+    const double rs = rstd[b * C + c], mu = mean[b * C + c], sc = rs * gamma[c];
+    const double s1 = ac[10], s2 = ac[11];
+    const double s1m = s1 / L0, s2m = s2 / L0;
+    db += s1;
+    dg += s2;
+    for (int j = 0; j < k; ++j) {
+      double wr = 0.0;  // sum_j' w[c][j'] R[j'][j]
+      for (int jj = 0; jj < k; ++jj) {
+        const int lo = jj < j ? jj : j, hi = jj < j ? j : jj;
+        // packed upper triangle over KMAX taps: row lo starts at KMAX + lo*KMAX - lo*(lo-1)/2
+        const int idx = KMAX + lo * KMAX - (lo * (lo - 1)) / 2 + (hi - lo);
+        wr += (double)w[c * k + jj] * m[idx];
+      }
+      const double sxh = rs * (wr - mu * m[j]);
+      dwc[j] += sc * ((double)ac[j] - s1m * m[j] - s2m * sxh);
+    }
+  }
+  for (int j = 0; j < k; ++j) dw[c * k + j] = (float)dwc[j];
+  dgamma[c] = (float)dg;
+  dbeta[c] = (float)db;
+}
+
 int rows_per_cta(int L0, int B) {
-  int per_batch = (148 * 2) / (B > 0 ? B : 1);
+  int per_batch = (148 * 3) / (B > 0 ? B : 1);
   if (per_batch < 1) per_batch = 1;
   int rows = cdiv(L0, per_batch);
   rows = cdiv(rows, TILE_T) * TILE_T;
@@ -271,7 +248,7 @@ extern "C" int a8_conv0_stats(const float* x, int32_t B, int64_t L, const float*
 }
 
 static int conv0_check(int32_t C, int32_t k, int32_t s) {
-  A8_REQUIRE(C % 8 == 0 && C <= 512, "conv0: C=%d must be a multiple of 8, <= 512", C);
+  A8_REQUIRE(C % 64 == 0 && C <= 512, "conv0: C=%d must be a multiple of 64, <= 512", C);
   A8_REQUIRE(k >= 1 && k <= KMAX && s >= 1 && s <= 8, "conv0: kernel %d / stride %d unsupported", k, s);
   return 0;
 }
@@ -282,27 +259,27 @@ extern "C" int a8_conv0_fwd(const float* x, int32_t B, int64_t L, const float* w
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (conv0_check(C, k, s)) return -1;
   const int L0 = (int)((L - k) / s + 1);
-  Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B), w, gamma, beta, mean, rstd, (__nv_bfloat16*)y,
-              nullptr, nullptr, nullptr, nullptr, nullptr};
+  Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B), w, gamma, beta, mean, rstd, (__nv_bfloat16*)y, nullptr, nullptr};
   dim3 grid(cdiv(L0, a.rows_per_cta), B);
-  conv0_kernel<MODE_FWD><<<grid, 256, 0, stream>>>(a);
+  conv0_kernel<false><<<grid, C / 2, 0, stream>>>(a);
   return check_launch("conv0_kernel<fwd>");
 }
 
 extern "C" int a8_conv0_bwd(const float* x, int32_t B, int64_t L, const float* w, const float* gamma,
-                            const float* beta, const float* mean, const float* rstd, int32_t C, int32_t k,
-                            int32_t s, const void* da, float* sums, float* dw, float* dgamma, float* dbeta,
-                            void* stream_v) {
+                            const float* beta, const float* mean, const float* rstd, const double* moments,
+                            int32_t C, int32_t k, int32_t s, const void* da, float* acc, float* dw, float* dgamma,
+                            float* dbeta, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (conv0_check(C, k, s)) return -1;
   const int L0 = (int)((L - k) / s + 1);
   Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B), w, gamma, beta, mean, rstd, nullptr,
-              (const __nv_bfloat16*)da, sums, dw, dgamma, dbeta};
+              (const __nv_bfloat16*)da, acc};
   dim3 grid(cdiv(L0, a.rows_per_cta), B);
-  A8_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * B * C, stream));
-  conv0_kernel<MODE_BWD_SUMS><<<grid, 256, 0, stream>>>(a);
-  int rc = check_launch("conv0_kernel<bwd_sums>");
+  A8_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 12 * B * C, stream));
+  conv0_kernel<true><<<grid, C / 2, 0, stream>>>(a);
+  int rc = check_launch("conv0_kernel<bwd>");
   if (rc) return rc;
-  conv0_kernel<MODE_BWD_W><<<grid, 256, 0, stream>>>(a);
-  return check_launch("conv0_kernel<bwd_w>");
+  conv0_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(acc, moments, w, gamma, mean, rstd, B, C, k, L0, dw,
+                                                                dgamma, dbeta);
+  return check_launch("conv0_bwd_finalize_kernel");
 }

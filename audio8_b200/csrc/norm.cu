@@ -10,6 +10,7 @@
 #include "../../include/audio8_b200.h"
 
 namespace a8 {
+const unsigned long long* seed_source();  // a8_api.cu
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -32,12 +33,9 @@ struct DropMask8 {
   float m[8];
 };
 // keep-scale per element: 0 or 1/(1-p)
-// Seeds: every launch passes a per-call-site constant; kernels add the 64-bit word at `g_seed_src` (device memory,
+// Seeds: every launch passes a per-call-site constant; kernels add the 64-bit word at `seed_source()` (device memory,
 // nullable) so that a captured CUDA graph draws fresh masks on every replay (a8_set_seed_source).
-static thread_local const unsigned long long* g_seed_src = nullptr;
-__device__ __forceinline__ unsigned long long seed_base(const unsigned long long* src) {
-  return src != nullptr ? __ldg(src) : 0ull;
-}
+__device__ __forceinline__ unsigned long long seed_base(const unsigned long long* src) { return seed_base_ld(src); }
 
 __device__ __forceinline__ DropMask8 drop_mask8(float p, unsigned long long seed, unsigned long long group) {
   DropMask8 d;
@@ -534,18 +532,13 @@ int row_grid(int rows) {
 
 using namespace a8;
 
-extern "C" int a8_set_seed_source(const void* dev_u64) {
-  g_seed_src = static_cast<const unsigned long long*>(dev_u64);
-  return 0;
-}
-
 extern "C" int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_t seed_h, void* s_out,
                                 const float* gamma, const float* beta, float eps, void* y, float* y_f32, float p_y,
                                 uint64_t seed_y, float* mean, float* rstd, int32_t R, int32_t C, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm: unsupported shape R=%d C=%d", R, C);
   LnFwdArgs a{(const __nv_bfloat16*)x, (const __nv_bfloat16*)h, p_h, seed_h, (__nv_bfloat16*)s_out, gamma, beta,
-              eps, (__nv_bfloat16*)y, y_f32, p_y, seed_y, mean, rstd, R, C, g_seed_src};
+              eps, (__nv_bfloat16*)y, y_f32, p_y, seed_y, mean, rstd, R, C, seed_source()};
   const int nch = cdiv(C, 256);
   const int grid = row_grid(R);
   switch (nch) {
@@ -564,7 +557,7 @@ extern "C" int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: unsupported shape R=%d C=%d", R, C);
   LnBwdArgs a{(const __nv_bfloat16*)dy, dy_f32, p_y, seed_y, (const __nv_bfloat16*)s, mean, rstd, gamma,
-              (__nv_bfloat16*)ds, (__nv_bfloat16*)dh, p_h, seed_h, dgamma, dbeta, dbias_h, R, C, g_seed_src};
+              (__nv_bfloat16*)ds, (__nv_bfloat16*)dh, p_h, seed_h, dgamma, dbeta, dbias_h, R, C, seed_source()};
   const int nch = cdiv(C, 256);
   int grid = cdiv(R, 8 * 4);  // >= 4 rows per warp so the column partials amortise their atomics
   grid = grid < 1 ? 1 : (grid > 148 * 2 ? 148 * 2 : grid);
@@ -581,7 +574,7 @@ extern "C" int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, 
                               uint64_t seed, int32_t B, int32_t H, int32_t T, int32_t Tp, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax: bad T=%d Tp=%d", T, Tp);
-  SmFwdArgs a{s, key_keep, (__nv_bfloat16*)p, (__nv_bfloat16*)p_drop, pdrop, seed, B * H * T, T, Tp, H * T, g_seed_src};
+  SmFwdArgs a{s, key_keep, (__nv_bfloat16*)p, (__nv_bfloat16*)p_drop, pdrop, seed, B * H * T, T, Tp, H * T, seed_source()};
   const int nv = cdiv(Tp, 256);
   const int grid = row_grid(a.rows);
   if (nv <= 1) softmax_fwd_kernel<1><<<grid, 256, 0, stream>>>(a);
@@ -597,7 +590,7 @@ extern "C" int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pd
                               int32_t H, int32_t T, int32_t Tp, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax_bwd: bad T=%d Tp=%d", T, Tp);
-  SmBwdArgs a{(const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, pdrop, seed, B * H * T, T, Tp, g_seed_src};
+  SmBwdArgs a{(const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, pdrop, seed, B * H * T, T, Tp, seed_source()};
   const int nv = cdiv(Tp, 256);
   const int grid = row_grid(a.rows);
   if (nv <= 1) softmax_bwd_kernel<1><<<grid, 256, 0, stream>>>(a);
@@ -627,8 +620,8 @@ extern "C" int a8_dropout(const void* x, void* out, int32_t dtype, int64_t n, fl
   A8_REQUIRE(n > 0 && n % 8 == 0, "dropout: n=%lld must be a positive multiple of 8", (long long)n);
   const long long n8 = n / 8;
   const int grid = (int)(n8 / 256 + 1 > 148 * 8 ? 148 * 8 : n8 / 256 + 1);
-  if (dtype == 0) dropout_f32_kernel<<<grid, 256, 0, stream>>>((const float*)x, (float*)out, n8, p, seed, g_seed_src);
-  else dropout_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n8, p, seed, g_seed_src);
+  if (dtype == 0) dropout_f32_kernel<<<grid, 256, 0, stream>>>((const float*)x, (float*)out, n8, p, seed, seed_source());
+  else dropout_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n8, p, seed, seed_source());
   return check_launch("dropout_kernel");
 }
 

@@ -323,8 +323,9 @@ class EncoderFn(torch.autograd.Function):
         x = _bf16(x)
         B, T, D = x.shape
         M = B * T
-        if D % (8 * groups) != 0 or (D // H) % 64 != 0:
-            raise ValueError(f"d_model={D}, heads={H}: this build needs d_model % {8 * groups} == 0 and d_k % 64 == 0")
+        if D % (8 * groups) != 0 or D != H * 64:
+            raise ValueError(f"d_model={D}, heads={H}: this build needs d_model % {8 * groups} == 0 and d_k == 64 "
+                             "(wav2vec2 base and large both use 64)")
         k = pos_v.shape[-1]
         pad_l = k // 2 - 1 if k % 2 == 0 else k // 2
         if row_keep is not None:
@@ -356,13 +357,8 @@ class EncoderFn(torch.autograd.Function):
             x2d = xin.view(M, D)
             qkv = _empty((B, T, 3 * D), BF16, x)
             be.gemm(G.linear_fwd(x2d, wqkv_b, qkv.view(M, 3 * D), bqkv))
-            S = _empty((B, H, T, Tp), F32, x)
-            be.gemm(G.attn_scores(qkv, S, H, scale))
             seed_a = next_seed() if p > 0 else 0
-            P, Pd = be.softmax_fwd(S, T, row_keep, p, seed_a)
-            del S
-            ctxv = _empty((B, T, D), BF16, x)
-            be.gemm(G.attn_context(Pd if Pd is not None else P, qkv, ctxv, H))
+            ctxv, lse = be.attn_fwd(qkv, H, scale, row_keep, p, seed_a)
             a = _empty((M, D), BF16, x)
             be.gemm(G.linear_fwd(ctxv.view(M, D), wo_b, a, bo))
             seed1 = next_seed() if p > 0 else 0
@@ -376,7 +372,7 @@ class EncoderFn(torch.autograd.Function):
             x2, _, s2, mean1, rstd1 = be.layernorm_fwd(x1, g1, b1ln, 1e-6, h=f, p_h=p, seed_h=seed2)
             h = x2.view(B, T, D)
             if need_grad:
-                layers.append(dict(xin=x2d, qkv=qkv, P=P, Pd=Pd, ctx=ctxv, s1=s1, mean2=mean2, rstd2=rstd2, x1=x1,
+                layers.append(dict(xin=x2d, qkv=qkv, lse=lse, ctx=ctxv, s1=s1, mean2=mean2, rstd2=rstd2, x1=x1,
                                    z1=z1, hid=hid, s2=s2, mean1=mean1, rstd1=rstd1, seeds=(seed_a, seed1, seed2),
                                    w=(wqkv_b, wo_b, w1_b, w2_b), ln=(g2, g1)))
         if need_grad:
@@ -435,14 +431,7 @@ class EncoderFn(torch.autograd.Function):
             be.gemm(G.linear_wgrad(da, L["ctx"].view(M, D), dwo))
             dctx = _empty((B, T, D), BF16, x)
             be.gemm(G.linear_dgrad(da, wo_b, dctx.view(M, D)))
-            dP = _empty((B, H, T, Tp), F32, x)
-            be.gemm(G.attn_dprobs(dctx, L["qkv"], dP, H))
-            dS = be.softmax_bwd(L["P"], dP, T, p, seed_a)
-            del dP
-            dqkv = _empty((B, T, 3 * D), BF16, x)
-            be.gemm(G.attn_dq(dS, L["qkv"], dqkv, H, scale))
-            be.gemm(G.attn_dk(dS, L["qkv"], dqkv, H, scale))
-            be.gemm(G.attn_dv(L["Pd"] if L["Pd"] is not None else L["P"], dctx, dqkv, H))
+            dqkv = be.attn_bwd(L["qkv"], L["ctx"], dctx, L["lse"], H, scale, sv["row_keep"], p, seed_a)
             dqkv2 = dqkv.view(M, 3 * D)
             dbqkv = be.colsum(dqkv2, out=dbqkv)
             be.gemm(G.linear_wgrad(dqkv2, L["xin"], dwqkv))

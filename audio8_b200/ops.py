@@ -259,6 +259,33 @@ class CudaBackend:
                    "a8_softmax_bwd")
         return ds
 
+    # ------------------------------------------------------------------ fused attention
+    def attn_fwd(self, qkv, H, scale, key_keep=None, pdrop=0.0, seed=0):
+        """qkv bf16 [B,T,3D] -> (ctx bf16 [B,T,D], lse fp32 [B,H,T]); scores / probabilities stay on chip"""
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        assert qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and D == H * 64
+        ctx = torch.empty(B, T, D, dtype=torch.bfloat16, device=qkv.device)
+        lse = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
+        _lib.check(self.lib.a8_attn_fwd(_ptr(qkv), _ptr(key_keep), _ptr(ctx), _ptr(lse), B, H, T, scale, pdrop, seed,
+                                        _stream()), "a8_attn_fwd")
+        return ctx, lse
+
+    def attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0):
+        """-> dqkv bf16 [B,T,3D] (dQ | dK | dV)"""
+        B, T, D3 = qkv.shape
+        assert dctx.dtype == torch.bfloat16 and dctx.is_contiguous() and ctx.is_contiguous() and dctx.shape == ctx.shape
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
+        _lib.check(self.lib.a8_attn_bwd(_ptr(qkv), _ptr(key_keep), _ptr(ctx), _ptr(dctx), _ptr(lse), _ptr(delta),
+                                        _ptr(dqkv), B, H, T, scale, pdrop, seed, _stream()), "a8_attn_bwd")
+        return dqkv
+
+    def attn_dropmask(self, B, H, T, pdrop, seed, device):
+        out = torch.empty(B, H, T, T, dtype=torch.uint8, device=device)
+        _lib.check(self.lib.a8_attn_dropmask(_ptr(out), B, H, T, pdrop, seed, _stream()), "a8_attn_dropmask")
+        return out
+
     def colsum(self, x, out=None):
         """out: optional ZEROED fp32 [C] accumulator"""
         C = x.shape[-1]

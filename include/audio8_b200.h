@@ -149,6 +149,22 @@ int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, void* p_dro
 int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pdrop, uint64_t seed, int32_t B, int32_t H,
                    int32_t T, int32_t Tp, void* stream);
 
+/* Fused scaled-dot-product attention, d_k = 64 (tcgen05 / TMEM; scores and probabilities never reach HBM).
+ * Replaces eight_mile's SeqScaledDotProductAttention as called through `wav2vec2.py:644` and its autograd:
+ *   P = dropout(softmax(scale * Q K^T + key mask));  ctx = P V
+ * qkv bf16 [B,T,3*H*64] = the fused projection output (Q | K | V, head h at columns h*64 of each third);
+ * key_keep uint8 [B,T] or NULL (0 = padded key: the reference's masked_fill(-1e9)); ctx bf16 [B,T,H*64];
+ * lse fp32 [B,H,T] = log2-sum-exp2 of the scaled scores (saved for backward); delta fp32 [B,H,T] scratch;
+ * dqkv bf16 [B,T,3*H*64] receives dQ | dK | dV.  Dropout keep decisions are a function of (seed + *seed_source,
+ * b, h, q, k) with keep probability 1 - floor(pdrop*65536)/65536; a8_attn_dropmask writes them as bytes
+ * [B,H,T,T] (tests only). */
+int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, float* lse, int32_t B, int32_t H, int32_t T,
+                float scale, float pdrop, uint64_t seed, void* stream);
+int a8_attn_bwd(const void* qkv, const uint8_t* key_keep, const void* ctx, const void* dctx, const float* lse,
+                float* delta, void* dqkv, int32_t B, int32_t H, int32_t T, float scale, float pdrop, uint64_t seed,
+                void* stream);
+int a8_attn_dropmask(uint8_t* keep_out, int32_t B, int32_t H, int32_t T, float pdrop, uint64_t seed, void* stream);
+
 /* out[c] += sum_r x[r][c]  (bias gradients; x bf16 [R, ld], out fp32 zeroed by the caller) */
 int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void* stream);
 /* element-wise dropout (nn.Dropout at `wav2vec2.py:934-935,713`), dtype 0 = fp32, 1 = bf16; its own backward */

@@ -68,3 +68,28 @@ for name, mk in cases.items():
     ts.sort()
     med = ts[len(ts) // 2]
     print(f"{name:36s} {med * 1e3:8.1f} us   {full.flops / med / 1e9:7.1f} TFLOP/s   (min {ts[0] * 1e3:.1f} us)", flush=True)
+
+# ---- fused attention (csrc/attn.cu) at the step's shape
+if not sel or "attn" in sel:
+    qkv = r(B, T, 3 * D)
+    dctx = r(B, T, D)
+    for pdrop in (0.0, 0.1):
+        ctx, lse = be.attn_fwd(qkv, H, 0.125, None, pdrop, 7)
+        for name, fn, fl in (("fwd", lambda: be.attn_fwd(qkv, H, 0.125, None, pdrop, 7), 4),
+                             ("bwd", lambda: be.attn_bwd(qkv, ctx, dctx, lse, H, 0.125, None, pdrop, 7), 10)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            med = ts[len(ts) // 2]
+            flops = fl * B * H * T * T * 64
+            print(f"fused_attn_{name} p={pdrop:<4}                 {med * 1e3:8.1f} us   {flops / med / 1e9:7.1f} TFLOP/s   (min {ts[0] * 1e3:.1f} us)", flush=True)

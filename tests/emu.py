@@ -173,6 +173,42 @@ class EmuOps(EmuBackend):
         ds = pf * (g - (pf * g).sum(-1, keepdim=True))
         return _bf(ds)
 
+    # ---- fused attention (plain fp32 math; `keep` lets tests inject the mask the CUDA kernels regenerate)
+    @staticmethod
+    def _attn_probs(qkv, H, scale, key_keep):
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        q, k, v = (t.float().reshape(B, T, H, 64).transpose(1, 2) for t in qkv.split(D, dim=-1))
+        s = (q @ k.transpose(-1, -2)) * scale
+        if key_keep is not None:
+            s = s.masked_fill(key_keep[:, None, None, :] == 0, -1e9)
+        return q, k, v, torch.softmax(s, -1)
+
+    def attn_fwd(self, qkv, H, scale, key_keep=None, pdrop=0.0, seed=0, keep=None):
+        B, T, D3 = qkv.shape
+        q, k, v, p = self._attn_probs(qkv, H, scale, key_keep)
+        m = self._attn_mask(p.shape, pdrop, seed, keep)
+        ctx = ((p * m) @ v).transpose(1, 2).reshape(B, T, D3 // 3)
+        return _bf(ctx), torch.zeros(B, H, T)
+
+    def attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0, keep=None):
+        B, T, D3 = qkv.shape
+        q, k, v, p = self._attn_probs(qkv, H, scale, key_keep)
+        m = self._attn_mask(p.shape, pdrop, seed, keep)
+        do = dctx.float().reshape(B, T, H, 64).transpose(1, 2)
+        dv = (p * m).transpose(-1, -2) @ do
+        g = (do @ v.transpose(-1, -2)) * m
+        ds = p * (g - (p * g).sum(-1, keepdim=True)) * scale
+        dq, dk = ds @ k, ds.transpose(-1, -2) @ q
+        return _bf(torch.cat([t.transpose(1, 2).reshape(B, T, D3 // 3) for t in (dq, dk, dv)], -1))
+
+    @staticmethod
+    def _attn_mask(shape, pdrop, seed, keep):
+        if keep is not None:
+            thr = int(pdrop * 65536.0)
+            return keep.float() * (65536.0 / (65536.0 - thr))
+        return _drop_mask(shape, pdrop, seed)
+
     def colsum(self, x, out=None):
         return x.float().reshape(-1, x.shape[-1]).sum(0)
 

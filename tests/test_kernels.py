@@ -250,3 +250,37 @@ def test_weight_prep(be):
     be.cast_multi(pairs, cache)
     for (s_, d_) in pairs:
         assert torch.equal(d_.cpu(), s_.cpu().to(d_.dtype))
+
+
+@pytest.mark.parametrize("B,H,T,mask,pdrop", [(2, 2, 100, False, 0.0), (1, 3, 128, False, 0.0), (2, 2, 333, True, 0.0),
+                                              (1, 2, 749, False, 0.0), (2, 2, 300, True, 0.1), (1, 2, 749, False, 0.1)])
+def test_fused_attention(be, B, H, T, mask, pdrop):
+    """fused tcgen05 attention (csrc/attn.cu) vs fp32 softmax attention on the same bf16 inputs; with dropout the
+    reference uses the keep mask exported by a8_attn_dropmask (the function of (seed, b, h, q, k) the kernels use)"""
+    D = H * 64
+    qkv = _bf((B, T, 3 * D), 21, 1.0)
+    qkv[..., :D] *= 1.5  # scores with a spread of a few units
+    dctx = _bf((B, T, D), 22)
+    keep_keys = None
+    if mask:
+        lens = [T - 37 * (b + 1) for b in range(B)]
+        keep_keys = (torch.arange(T)[None, :] < torch.tensor(lens)[:, None]).to(torch.uint8)
+    scale, seed = 0.125, 1234567
+    kk = keep_keys.cuda() if mask else None
+    ctx, lse = be.attn_fwd(qkv.cuda(), H, scale, kk, pdrop, seed)
+    keep = be.attn_dropmask(B, H, T, pdrop, seed, "cuda").cpu() if pdrop > 0 else None
+    if keep is not None:
+        rate = 1.0 - keep.float().mean().item()
+        assert abs(rate - pdrop) < 0.01, f"dropout rate {rate}"
+    ref_ctx, _ = E.attn_fwd(qkv, H, scale, keep_keys, pdrop, seed, keep=keep)
+    _close(ctx, ref_ctx, 2e-2, "attention ctx")
+    # log2-sum-exp2 of the scaled scores
+    q, k, v, p = E._attn_probs(qkv, H, scale, keep_keys)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if mask:
+        s = s.masked_fill(keep_keys[:, None, None, :] == 0, float("-inf"))
+    _close(lse, torch.logsumexp(s, -1) / math.log(2.0), 1e-3, "attention lse")
+    dqkv = be.attn_bwd(qkv.cuda(), ctx, dctx.cuda(), lse, H, scale, kk, pdrop, seed)
+    ref_d = E.attn_bwd(qkv, ref_ctx, dctx, None, H, scale, keep_keys, pdrop, seed, keep=keep)
+    for i, name in enumerate(["dQ", "dK", "dV"]):
+        _close(dqkv[..., i * D:(i + 1) * D], ref_d[..., i * D:(i + 1) * D], 3e-2, "attention " + name)
