@@ -66,7 +66,7 @@ SIGNATURES.update({
     "a8_log_softmax_bwd": (_I, [_P, _L, _L, _L, _I, _P, _P, _I, _I, _P]),
     "a8_conv0_stats": (_I, [_P, _I, _L, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "a8_conv0_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
-    "a8_conv0_bwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "a8_conv0_bwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "a8_rows_copy": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "a8_rows_set": (_I, [_P, _P, _I, _I, _P, _P]),
     "a8_rows_set_bwd": (_I, [_P, _P, _I, _I, _P, _P]),

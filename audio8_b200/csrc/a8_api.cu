@@ -1,5 +1,6 @@
 // audio8_b200 — C-ABI plumbing: version, thread-local error string, launch accounting.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include "a8_common.cuh"
 #include "../../include/audio8_b200.h"
@@ -23,6 +24,14 @@ int check_launch(const char* what) {
     return -3;
   }
   return 0;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("A8_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 static thread_local const unsigned long long* g_seed_src = nullptr;
 const unsigned long long* seed_source() { return g_seed_src; }

@@ -37,6 +37,39 @@ int check_launch(const char* what);  // cudaGetLastError() -> 0 / negative code
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining,
+// so launch latency, the prologue (barrier init, TMEM allocation) and the predecessor's tail overlap.  Every kernel
+// launched through launch_pdl() calls pdl_wait() before it touches global memory.  A8_PDL=0 turns the attribute off.
+bool pdl_enabled();  // a8_api.cu
+#if defined(__CUDACC__)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------
 // math
@@ -98,6 +131,8 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float cdf = 0.5f + copysignf(half_erf, x);
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // per-step dropout seed word in device memory (a8_set_seed_source), nullable
 __device__ __forceinline__ unsigned long long seed_base_ld(const unsigned long long* src) {
   return src != nullptr ? __ldg(src) : 0ull;

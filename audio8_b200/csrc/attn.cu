@@ -36,7 +36,7 @@ struct AttnArgs {
   int B, H, T, nblk;
   const unsigned char* key_keep;  // [B,T] or null
   float scale, scale_log2, keep_scale;
-  uint32_t thr;                   // keep iff 16-bit field >= thr
+  uint32_t thr;                   // keep iff r(q,k) >= thr  (thr = p * 2^32)
   unsigned long long seed;
   const unsigned long long* seed_src;
   __nv_bfloat16* ctx;             // fwd out [B,T,D]
@@ -48,6 +48,11 @@ struct AttnArgs {
 };
 
 // ---------------------------------------------------------------------------------------------- dropout hash
+// keep(q,k) <=> r(q,k) >= thr32, with  x = xorshift(((q/2 << 16) + k/2 + key) * M1)  shared by a 2x2 patch of the score
+// matrix and r = x * M[(q&1)*2 + (k&1)].  Multiplies run on the FMA pipe; per element only the compare and the select
+// (plus the patch's shift/xor) hit the half-rate ALU pipe, which is what bounds these kernels.  Usable from both orientations (query-row threads
+// in forward / dQ, key-row threads in dK/dV).
+constexpr uint32_t HM1 = 0x9E3779B1u;
 __device__ __forceinline__ uint32_t hmix(uint32_t x) {
   x *= 0x9E3779B1u;
   x ^= x >> 15;
@@ -58,14 +63,16 @@ __device__ __forceinline__ uint32_t hmix(uint32_t x) {
 __device__ __forceinline__ uint32_t drop_key(unsigned long long seed, int bh) {
   return hmix((uint32_t)seed ^ hmix((uint32_t)(seed >> 32) + 0x9E3779B1u * (uint32_t)(bh + 1)));
 }
-// word for the 2x2 patch (q>>1, k>>1), q even; fields: k even -> low 16 bits, k odd -> high 16 bits
-__device__ __forceinline__ uint32_t drop_word0(uint32_t key, int qp, int kp) {
-  return hmix((((uint32_t)qp << 16) | (uint32_t)kp) ^ key);
+__device__ __forceinline__ uint32_t drop_mul(int qodd, int kodd) {
+  return qodd ? (kodd ? 0x165667B1u : 0x27D4EB2Fu) : (kodd ? 0xC2B2AE3Du : 0x85EBCA77u);
 }
-__device__ __forceinline__ uint32_t drop_word1(uint32_t w0) {  // same patch, q odd
-  const uint32_t w = w0 * 0xC2B2AE3Du;
-  return w ^ (w >> 15);
+// linear part (additive in qp and kp, so loops advance it with one multiply-add) ...
+__device__ __forceinline__ uint32_t drop_w(uint32_t key, int qp, int kp) {
+  return (((uint32_t)qp << 16) + (uint32_t)kp + key) * HM1;
 }
+// ... one xorshift to break the lattice, then an element-specific multiply; the compare reads the high bits
+__device__ __forceinline__ uint32_t drop_x(uint32_t w) { return w ^ (w >> 15); }
+__device__ __forceinline__ uint32_t drop_r(uint32_t x, uint32_t mul) { return x * mul; }
 
 __device__ __forceinline__ uint32_t valid_word(const unsigned char* keep, int T, int k0) {
   uint32_t w = 0;
@@ -94,6 +101,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
   const int qb = blockIdx.x % nblk;
@@ -174,38 +183,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
     const float c = a.scale_log2;
     uint32_t dkey = 0;
     if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
+    const uint32_t mul_e = drop_mul(row & 1, 0), mul_o = drop_mul(row & 1, 1);
+    const uint32_t wrow = drop_w(dkey, row >> 1, 0);
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(bar_at(bars, S_FULL), j & 1);
       tc_fence_after();
-      uint32_t r[32];
-      if (j == 0) {  // exact row max of the first block
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          tmem_ld_32x32(tS + ch * 32, r);
-          tmem_ld_wait();
-          const uint32_t word = sValid[ch];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float s = __uint_as_float(r[i]);
-            mx = fmaxf(mx, ((word >> i) & 1u) ? s : -INFINITY);
-          }
-        }
-        m = (mx == -INFINITY) ? 0.f : mx * c;
-      } else {
+      if (j > 0) {
         mbar_wait(bar_at(bars, PV_DONE), (j - 1) & 1);  // P buffer free, O up to date
         tc_fence_after();
       }
-      bool redo;
-      do {
-        float bmax = -INFINITY, lsum = 0.f;
+      uint32_t r[32];
+      // The running max is only raised when a block would overflow the row sum (any exp2 above 2^64): the common case
+      // is ONE pass per block with no per-element max.  Block 0 and the rare overflow take the exact-max pass first.
+      bool need_max = (j == 0);
+      while (true) {
+        if (need_max) {
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            tmem_ld_32x32(tS + ch * 32, r);
+            tmem_ld_wait();
+            const uint32_t word = sValid[j * 4 + ch];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((word >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+          float m_new = fmaxf(m, mx * c);
+          if (m_new == -INFINITY) m_new = 0.f;
+          if (j > 0) {  // rescale the row sum and the O accumulator (PV of the previous block has completed)
+            const float f = ex2_approx(m - m_new);
+            l *= f;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+              tmem_ld_32x32(tO + ch * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+              tmem_st_32x32(tO + ch * 32, r);
+            }
+            tmem_st_wait();
+          }
+          m = m_new;
+        }
+        float lsum = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           tmem_ld_32x32(tS + ch * 32, r);
           tmem_ld_wait();
           const uint32_t word = sValid[j * 4 + ch];
-          const int k0 = j * 128 + ch * 32;
+          const uint32_t wch = wrow + (uint32_t)((j * 128 + ch * 32) >> 1) * HM1;
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -214,41 +240,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
               if (!((word >> i) & 1u)) t0 = -INFINITY;
               if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
             }
-            bmax = fmaxf(bmax, fmaxf(t0, t1));
             float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
             lsum += p0 + p1;
             if (DROP) {
-              uint32_t w = drop_word0(dkey, row >> 1, (k0 + i) >> 1);
-              if (row & 1) w = drop_word1(w);
-              p0 = ((w & 0xFFFFu) >= a.thr) ? p0 : 0.f;
-              p1 = ((w >> 16) >= a.thr) ? p1 : 0.f;
+              const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
+              p0 = (drop_r(w, mul_e) >= a.thr) ? p0 : 0.f;
+              p1 = (drop_r(w, mul_o) >= a.thr) ? p1 : 0.f;
             }
             pk[i >> 1] = pack_bf16(p0, p1);
           }
           tmem_st_32x16(tP + ch * 16, pk);
         }
-        redo = false;
-        if (j > 0 && __any_sync(0xffffffffu, bmax > 8.f)) {
-          // this block exceeds the running max by more than 2^8: raise the max, rescale O and l, redo the block
-          const float m_new = fmaxf(m, m + bmax);
-          const float f = ex2_approx(m - m_new);
-          l *= f;
-          m = m_new;
+        if (!need_max && __any_sync(0xffffffffu, !(lsum < 1.8e19f))) {
+          need_max = true;
           tmem_st_wait();
-#pragma unroll 1
-          for (int ch = 0; ch < 2; ++ch) {
-            tmem_ld_32x32(tO + ch * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tmem_st_32x32(tO + ch * 32, r);
-          }
-          tmem_st_wait();
-          redo = true;
-        } else {
-          l += lsum;
+          continue;
         }
-      } while (redo);
+        l += lsum;
+        break;
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_at(bars, P_READY));
@@ -302,6 +312,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
   const int qb = blockIdx.x % nblk;
@@ -389,6 +401,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     const float c = a.scale_log2;
     uint32_t dkey = 0;
     if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
+    const uint32_t mul_e = drop_mul(row & 1, 0), mul_o = drop_mul(row & 1, 1);
+    const uint32_t wrow = drop_w(dkey, row >> 1, 0);
     // delta = rowsum(dO * O); lse of this row
     float delta = 0.f, nlse = -INFINITY;
     if (row < a.T) {
@@ -424,7 +438,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         tmem_ld_32x32(tdP + col0, rp);
         tmem_ld_wait();
         const uint32_t word = sValid[j * 4 + (col0 >> 5)];
-        const int k0 = j * 128 + col0;
+        const uint32_t wch = wrow + (uint32_t)((j * 128 + col0) >> 1) * HM1;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -436,10 +450,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
           const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
           float d0 = __uint_as_float(rp[i]), d1 = __uint_as_float(rp[i + 1]);
           if (DROP) {
-            uint32_t w = drop_word0(dkey, row >> 1, (k0 + i) >> 1);
-            if (row & 1) w = drop_word1(w);
-            d0 = ((w & 0xFFFFu) >= a.thr) ? d0 * a.keep_scale : 0.f;
-            d1 = ((w >> 16) >= a.thr) ? d1 * a.keep_scale : 0.f;
+            const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
+            d0 = (drop_r(w, mul_e) >= a.thr) ? d0 * a.keep_scale : 0.f;
+            d1 = (drop_r(w, mul_o) >= a.thr) ? d1 * a.keep_scale : 0.f;
           }
           pk[i >> 1] = pack_bf16(p0 * (d0 - delta) * a.scale, p1 * (d1 - delta) * a.scale);
         }
@@ -493,6 +506,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   float* sStat = reinterpret_cast<float*>(smem_raw + (bars + 128 - raw));  // [2 stages][nlse 128 | delta 128]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
   const int kb = blockIdx.x % nblk;
@@ -597,8 +612,11 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const float rowoff = valid_row ? 0.f : -INFINITY;
     uint32_t dkey = 0;
     if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
+    const uint32_t mul_qe = drop_mul(0, key & 1), mul_qo = drop_mul(1, key & 1);
+    const uint32_t wkey = drop_w(dkey, 0, key >> 1);
     for (int i = 0; i < nblk; ++i) {
-      mbar_wait(bar_at(bars, S_FULL), i & 1);  // implies Q_FULL of this stage (statistics staged) has completed
+      mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);  // the block's statistics are staged (acquire)
+      mbar_wait(bar_at(bars, S_FULL), i & 1);
       tc_fence_after();
       if (i > 0) {
         mbar_wait(bar_at(bars, ACC_DONE), (i - 1) & 1);  // P^T / dS^T buffers consumed
@@ -612,7 +630,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         tmem_ld_32x32(tST + col0, rs);
         tmem_ld_32x32(tdPT + col0, rp);
         tmem_ld_wait();
-        const int q0 = i * 128 + col0;
+        const uint32_t wq0 = wkey + (uint32_t)((i * 128 + col0) >> 1) * (HM1 << 16);
         uint32_t pp[16], pd[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
@@ -623,11 +641,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           float d0 = __uint_as_float(rp[e]), d1 = __uint_as_float(rp[e + 1]);
           float k0 = p0, k1 = p1;
           if (DROP) {
-            const uint32_t w0 = drop_word0(dkey, (q0 + e) >> 1, key >> 1);  // q0 + e is even
-            const uint32_t w1 = drop_word1(w0);
-            const uint32_t f0 = (key & 1) ? (w0 >> 16) : (w0 & 0xFFFFu);
-            const uint32_t f1 = (key & 1) ? (w1 >> 16) : (w1 & 0xFFFFu);
-            const bool keep0 = f0 >= a.thr, keep1 = f1 >= a.thr;
+            const uint32_t w = drop_x(wq0 + (uint32_t)(e >> 1) * (HM1 << 16));  // patch ((q0 + e) / 2, key / 2)
+            const bool keep0 = drop_r(w, mul_qe) >= a.thr, keep1 = drop_r(w, mul_qo) >= a.thr;
             k0 = keep0 ? p0 : 0.f;
             k1 = keep1 ? p1 : 0.f;
             d0 = keep0 ? d0 * a.keep_scale : 0.f;
@@ -685,10 +700,8 @@ __global__ void attn_dropmask_kernel(unsigned char* out, int B, int H, int T, ui
     const int k = (int)(i % T);
     const int q = (int)((i / T) % T);
     const int bh = (int)(i / ((long long)T * T));
-    uint32_t w = drop_word0(drop_key(s, bh), q >> 1, k >> 1);
-    if (q & 1) w = drop_word1(w);
-    const uint32_t f = (k & 1) ? (w >> 16) : (w & 0xFFFFu);
-    out[i] = f >= thr ? 1 : 0;
+    const uint32_t w = drop_x(drop_w(drop_key(s, bh), q >> 1, k >> 1));
+    out[i] = drop_r(w, drop_mul(q & 1, k & 1)) >= thr ? 1 : 0;
   }
 }
 
@@ -700,8 +713,8 @@ int fill_args(AttnArgs& a, const uint8_t* key_keep, int B, int H, int T, float s
   a.key_keep = key_keep;
   a.scale = scale;
   a.scale_log2 = scale * 1.4426950408889634f;
-  a.thr = (uint32_t)(pdrop * 65536.f);
-  a.keep_scale = pdrop > 0.f ? 65536.f / (65536.f - (float)a.thr) : 1.f;  // exact inverse of the realised keep rate
+  a.thr = (uint32_t)((double)pdrop * 4294967296.0);
+  a.keep_scale = pdrop > 0.f ? (float)(4294967296.0 / (4294967296.0 - (double)a.thr)) : 1.f;  // 1 / realised keep rate
   a.seed = seed;
   a.seed_src = seed_source();
   return 0;
@@ -738,8 +751,8 @@ extern "C" int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, 
     cfg = true;
   }
   const int grid = a.nblk * B * H;
-  if (pdrop > 0.f) attn_fwd_kernel<true><<<grid, 256, SMEM_FWD, stream>>>(mq, a);
-  else attn_fwd_kernel<false><<<grid, 256, SMEM_FWD, stream>>>(mq, a);
+  if (pdrop > 0.f) A8_CUDA(launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(256), SMEM_FWD, stream, 1, mq, a));
+  else A8_CUDA(launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(256), SMEM_FWD, stream, 1, mq, a));
   return check_launch("attn_fwd_kernel");
 }
 
@@ -767,11 +780,11 @@ extern "C" int a8_attn_bwd(const void* qkv, const uint8_t* key_keep, const void*
     cfg = true;
   }
   const int grid = a.nblk * B * H;
-  if (pdrop > 0.f) attn_dq_kernel<true><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
-  else attn_dq_kernel<false><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
+  if (pdrop > 0.f) A8_CUDA(launch_pdl(attn_dq_kernel<true>, dim3(grid), dim3(384), SMEM_BWD, stream, 1, mq, md, a));
+  else A8_CUDA(launch_pdl(attn_dq_kernel<false>, dim3(grid), dim3(384), SMEM_BWD, stream, 1, mq, md, a));
   if (int rc = check_launch("attn_dq_kernel")) return rc;
-  if (pdrop > 0.f) attn_dkv_kernel<true><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
-  else attn_dkv_kernel<false><<<grid, 384, SMEM_BWD, stream>>>(mq, md, a);
+  if (pdrop > 0.f) A8_CUDA(launch_pdl(attn_dkv_kernel<true>, dim3(grid), dim3(384), SMEM_BWD, stream, 1, mq, md, a));
+  else A8_CUDA(launch_pdl(attn_dkv_kernel<false>, dim3(grid), dim3(384), SMEM_BWD, stream, 1, mq, md, a));
   return check_launch("attn_dkv_kernel");
 }
 
@@ -779,7 +792,7 @@ extern "C" int a8_attn_dropmask(uint8_t* keep_out, int32_t B, int32_t H, int32_t
                                 void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(B > 0 && H > 0 && T > 0, "dropmask: bad shape");
-  attn_dropmask_kernel<<<148 * 4, 256, 0, stream>>>(keep_out, B, H, T, (uint32_t)(pdrop * 65536.f), seed,
+  attn_dropmask_kernel<<<148 * 4, 256, 0, stream>>>(keep_out, B, H, T, (uint32_t)((double)pdrop * 4294967296.0), seed,
                                                      seed_source());
   return check_launch("attn_dropmask_kernel");
 }

@@ -29,7 +29,7 @@ struct OpCoef {
 };
 
 struct KParams {
-  int M, N, m_tiles, n_tiles, lo_count, hi_count;
+  int M, N, m_tiles, n_tiles, lo_count, hi_count;  // m_tiles counts tile PAIRS when the kernel runs as 2-CTA clusters
   int k_blocks, k_inner, split_k;
   OpCoef a, b;
   void* c;
@@ -72,11 +72,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 struct TileCoord {
   int nt, mt, lo, hi, kb_begin, kb_end;
 };
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+template <int CL>
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int rank) {
   TileCoord t;
   t.nt = tile % p.n_tiles;
   int r = tile / p.n_tiles;
-  t.mt = r % p.m_tiles;
+  t.mt = (r % p.m_tiles) * CL + rank;
   r /= p.m_tiles;
   t.lo = r % p.lo_count;
   r /= p.lo_count;
@@ -205,7 +206,37 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
   }
 }
 
-template <int MA, int MB, int BN>
+// ---- 2-CTA cluster mode: the two CTAs of a cluster own vertically adjacent 128-row tiles of the same n-tile, so they
+// need the SAME B tile: each loads half of it and multicasts that half into both CTAs' shared memory.  L2 -> SM
+// traffic per CTA and k-block drops from (128 + BN) x 128 B to (128 + BN/2) x 128 B, which is what bounds these GEMMs
+// (the measured L2 feed is ~43 B/clk/SM).  A stage may be refilled only when BOTH CTAs have consumed it: the MMA
+// issuer's tcgen05.commit arrives on the stage's empty barrier of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1,
+                                               int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
+template <int MA, int MB, int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const KParams p) {
@@ -239,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (elect_one()) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(full_bar(i), 1);
-        mbar_init(empty_bar(i), 1);
+        mbar_init(empty_bar(i), CL);  // one tcgen05.commit arrival per CTA of the cluster
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(tfull_bar(i), 1);
@@ -252,16 +283,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();  // the next kernel's prologue may start; it waits for this grid before touching memory
+  pdl_wait();               // everything above overlapped the previous kernel's tail
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile<CL>(p, tile, rank);
         const int m0 = t.mt * BLOCK_M, n0 = t.nt * BN;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           const int kin = kb % p.k_inner;
@@ -281,14 +317,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_4d(&map_a, full_bar(stage), a_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
             }
           }
-          if (MB == MAJOR_K) {
-            op_coords(p.b, kin, kbatch, n0, t.lo, t.hi, cc);
-            tma_load_4d(&map_b, full_bar(stage), b_dst, cc[0], cc[1], cc[2], cc[3]);
-          } else {
+          if (CL == 1) {
+            if (MB == MAJOR_K) {
+              op_coords(p.b, kin, kbatch, n0, t.lo, t.hi, cc);
+              tma_load_4d(&map_b, full_bar(stage), b_dst, cc[0], cc[1], cc[2], cc[3]);
+            } else {
 #pragma unroll
-            for (int at = 0; at < BN / 64; ++at) {
-              op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
-              tma_load_4d(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+              for (int at = 0; at < BN / 64; ++at) {
+                op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
+                tma_load_4d(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+              }
+            }
+          } else {  // this CTA's half of the B tile, multicast into both CTAs (same smem offset, same barrier offset)
+            if (MB == MAJOR_K) {
+              op_coords(p.b, kin, kbatch, n0 + rank * (BN / 2), t.lo, t.hi, cc);
+              tma_load_4d_mc(&map_b, full_bar(stage), b_dst + rank * (C::B_BYTES / 2), cc[0], cc[1], cc[2], cc[3], 3);
+            } else {
+#pragma unroll
+              for (int a2 = 0; a2 < BN / 128; ++a2) {
+                const int at = rank * (BN / 128) + a2;
+                op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
+                tma_load_4d_mc(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3], 3);
+              }
             }
           }
           if (++stage == STAGES) {
@@ -313,8 +363,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
+        const TileCoord t = decode_tile<CL>(p, tile, rank);
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -331,7 +381,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t db = make_smem_desc(b_addr + k * B_KADV, B_LBO, 1024u);
             umma_bf16(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mc(empty_bar(stage), 3);
           if (kb == t.kb_end - 1) umma_commit(tfull_bar(as));
           if (++stage == STAGES) {
             stage = 0;
@@ -349,8 +400,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int NCH = COLS / 32;       // 32-column chunks per warp (4 / 2 / 1)
     const int tid_e = threadIdx.x - 128;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
+      const TileCoord t = decode_tile<CL>(p, tile, rank);
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1u;
       float* sb = nullptr;
@@ -387,6 +438,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // neither CTA exits while the peer may still write its smem or signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -468,28 +520,37 @@ int num_sms() {
   return n;
 }
 
-template <int MA, int MB, int BN>
+template <int MA, int MB, int BN, int CL>
 int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<MA, MB, BN>;
+  auto kern = gemm_tc_kernel<MA, MB, BN, CL>;
   if (!configured) {
     A8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)Cfg<BN>::SMEM_BYTES));
     configured = true;
   }
-  int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, kp);
+  const int slots = num_sms() / CL;
+  const int grid = CL * (kp.total_tiles < slots ? kp.total_tiles : slots);
+  A8_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM_BYTES, stream, CL, ma, mb, kp));
   return check_launch("gemm_tc_kernel");
 }
 
 template <int MA, int MB>
-int launch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
+int launch_bn(int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
               cudaStream_t stream) {
+  if (cl == 2) {
+    switch (bn) {
+      case 128: return launch_inst<MA, MB, 128, 2>(ma, mb, kp, stream);
+      case 256: return launch_inst<MA, MB, 256, 2>(ma, mb, kp, stream);
+    }
+    set_error("gemm: cluster mode needs block_n 128 or 256 (got %d)", bn);
+    return -1;
+  }
   switch (bn) {
-    case 64: return launch_inst<MA, MB, 64>(ma, mb, kp, stream);
-    case 128: return launch_inst<MA, MB, 128>(ma, mb, kp, stream);
-    case 192: return launch_inst<MA, MB, 192>(ma, mb, kp, stream);
-    case 256: return launch_inst<MA, MB, 256>(ma, mb, kp, stream);
+    case 64: return launch_inst<MA, MB, 64, 1>(ma, mb, kp, stream);
+    case 128: return launch_inst<MA, MB, 128, 1>(ma, mb, kp, stream);
+    case 192: return launch_inst<MA, MB, 192, 1>(ma, mb, kp, stream);
+    case 256: return launch_inst<MA, MB, 256, 1>(ma, mb, kp, stream);
   }
   set_error("gemm: unsupported block_n %d", bn);
   return -1;
@@ -530,7 +591,8 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   KParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.M = g.M; kp.N = g.N;
-  kp.m_tiles = cdiv(g.M, BLOCK_M);
+  const int cl = (g.reserved == 2) ? 2 : 1;  // a8_gemm_t.reserved doubles as the cluster-size request (0/1 = off)
+  kp.m_tiles = cdiv(cdiv(g.M, BLOCK_M), cl);
   kp.n_tiles = cdiv(g.N, bn);
   kp.lo_count = g.lo_count > 0 ? g.lo_count : 1;
   kp.hi_count = g.hi_count > 0 ? g.hi_count : 1;
@@ -549,11 +611,11 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   if (g.a.major == MAJOR_K) rc = make_tmap(&ma, g.a, BLOCK_K, BLOCK_M, "A");
   else rc = make_tmap(&ma, g.a, 64, BLOCK_K, "A");
   if (rc) return rc;
-  if (g.b.major == MAJOR_K) rc = make_tmap(&mb, g.b, BLOCK_K, bn, "B");
+  if (g.b.major == MAJOR_K) rc = make_tmap(&mb, g.b, BLOCK_K, bn / cl, "B");
   else rc = make_tmap(&mb, g.b, 64, BLOCK_K, "B");
   if (rc) return rc;
 
-  if (g.a.major == MAJOR_K && g.b.major == MAJOR_K) return launch_bn<MAJOR_K, MAJOR_K>(bn, ma, mb, kp, stream);
-  if (g.a.major == MAJOR_K && g.b.major == MAJOR_MN) return launch_bn<MAJOR_K, MAJOR_MN>(bn, ma, mb, kp, stream);
-  return launch_bn<MAJOR_MN, MAJOR_MN>(bn, ma, mb, kp, stream);
+  if (g.a.major == MAJOR_K && g.b.major == MAJOR_K) return launch_bn<MAJOR_K, MAJOR_K>(bn, cl, ma, mb, kp, stream);
+  if (g.a.major == MAJOR_K && g.b.major == MAJOR_MN) return launch_bn<MAJOR_K, MAJOR_MN>(bn, cl, ma, mb, kp, stream);
+  return launch_bn<MAJOR_MN, MAJOR_MN>(bn, cl, ma, mb, kp, stream);
 }

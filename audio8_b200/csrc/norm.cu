@@ -103,6 +103,8 @@ struct LnFwdArgs {
 
 template <int NCH>  // chunks of 8 elements per lane: C <= NCH*256
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned long long sbase = seed_base(a.seed_src);
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -192,6 +194,8 @@ struct LnBwdArgs {
 
 template <int NCH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned long long sbase = seed_base(a.seed_src);
   __shared__ float red[8][NCH * 256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -409,6 +413,8 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const SmBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* x, long long ld, int R, int C,
                                                      int rows_per_block, float* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   // 64 column-octets x 4 row phases per CTA (512 columns, blockIdx.y selects the slab); each thread streams its
   // rows with 4 independent 16-byte loads in flight, phases are reduced in smem, one atomic per column per CTA
   __shared__ float red[4][64 * 8];
@@ -477,6 +483,8 @@ __global__ void __launch_bounds__(256) dropout_f32_kernel(const float* x, float*
 // dz = dy * gelu'(z)   (bf16, n % 8 == 0)
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* z,
                                                        __nv_bfloat16* dz, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float g[8], zz[8];
     load8(dy + i * 8, g);
@@ -542,10 +550,10 @@ extern "C" int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_
   const int nch = cdiv(C, 256);
   const int grid = row_grid(R);
   switch (nch) {
-    case 1: ln_fwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
-    case 2: ln_fwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
-    case 3: ln_fwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
-    default: ln_fwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
+    case 1: A8_CUDA(launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    case 2: A8_CUDA(launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    case 3: A8_CUDA(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    default: A8_CUDA(launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
   }
   return check_launch("ln_fwd_kernel");
 }
@@ -562,10 +570,10 @@ extern "C" int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, 
   int grid = cdiv(R, 8 * 4);  // >= 4 rows per warp so the column partials amortise their atomics
   grid = grid < 1 ? 1 : (grid > 148 * 2 ? 148 * 2 : grid);
   switch (nch) {
-    case 1: ln_bwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
-    case 2: ln_bwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
-    case 3: ln_bwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
-    default: ln_bwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
+    case 1: A8_CUDA(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    case 2: A8_CUDA(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    case 3: A8_CUDA(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    default: A8_CUDA(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
   }
   return check_launch("ln_bwd_kernel");
 }
@@ -610,7 +618,7 @@ extern "C" int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float*
   int rpb = cdiv(R, chunks);
   rpb = rpb < 32 ? 32 : rpb;
   dim3 grid(cdiv(R, rpb), slabs);
-  colsum_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, R, C, rpb, out);
+  A8_CUDA(launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, 1, (const __nv_bfloat16*)x, (long long)ld, (int)R, (int)C, rpb, out));
   return check_launch("colsum_kernel");
 }
 
@@ -630,7 +638,8 @@ extern "C" int a8_gelu_bwd(const void* dy, const void* z, void* dz, int64_t n, v
   A8_REQUIRE(n > 0 && n % 8 == 0, "gelu_bwd: n=%lld must be a positive multiple of 8", (long long)n);
   const long long n8 = n / 8;
   const int grid = (int)(n8 / 256 + 1 > 148 * 8 ? 148 * 8 : n8 / 256 + 1);
-  gelu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)z, (__nv_bfloat16*)dz, n8);
+  A8_CUDA(launch_pdl(gelu_bwd_kernel, dim3(grid), dim3(256), 0, stream, 1, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)z,
+                     (__nv_bfloat16*)dz, n8));
   return check_launch("gelu_bwd_kernel");
 }
 

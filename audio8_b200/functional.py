@@ -36,11 +36,16 @@ def _be():
     return ops.backend()
 
 
-def _empty(shape, dtype, like):
+def _empty(shape, dtype, like, dynamic=False):
+    """dynamic=True: the size follows the per-step masked-row count -> bucketed allocation (ops.bucketed_empty)"""
+    if dynamic:
+        return ops.bucketed_empty(tuple(shape), dtype, like.device)
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
-def _zeros(shape, dtype, like):
+def _zeros(shape, dtype, like, dynamic=False):
+    if dynamic:
+        return ops.bucketed_empty(tuple(shape), dtype, like.device, zero=True)
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
@@ -64,7 +69,7 @@ class LinearFn(torch.autograd.Function):
         xb = _bf16(x2)
         wb = _bf16(weight)
         N = weight.shape[0]
-        out = _empty((x2.shape[0], N), F32 if out_f32 else BF16, x)
+        out = _empty((x2.shape[0], N), F32 if out_f32 else BF16, x, dynamic=True)
         be.gemm(G.linear_fwd(xb, wb, out, bias.detach() if bias is not None else None,
                              c_dtype=OUT_F32 if out_f32 else OUT_BF16))
         ctx.saved = (xb, wb, x.dtype, shp, bias is not None)
@@ -78,7 +83,7 @@ class LinearFn(torch.autograd.Function):
         dyb = _bf16(dy.reshape(-1, N))
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = _empty(xb.shape, xdtype, xb)
+            dx = _empty(xb.shape, xdtype, xb, dynamic=True)
             be.gemm(G.linear_dgrad(dyb, wb, dx, c_dtype=OUT_F32 if xdtype == F32 else OUT_BF16))
             dx = dx.view(shp)
         if ctx.needs_input_grad[1]:
@@ -223,7 +228,7 @@ class ConvFeatureFn(torch.autograd.Function):
         w0 = weights[0].detach().reshape(c0, k0).contiguous()
         gw, gb = gn_w.detach(), gn_b.detach()
         need_grad = any(ctx.needs_input_grad)
-        mean, rstd = be.conv0_stats(x, w0, k0, s0, 1e-5)
+        mean, rstd, mom = be.conv0_stats(x, w0, k0, s0, 1e-5)
         a = be.conv0_fwd(x, w0, gw, gb, mean, rstd, k0, s0)
         acts, zs, wts = [a], [None], [None]
         for i in range(1, len(spec)):
@@ -239,13 +244,13 @@ class ConvFeatureFn(torch.autograd.Function):
             wts.append(wt)
             a = y
         if need_grad:
-            ctx.saved = (x, w0, gw, gb, mean, rstd, acts, zs, wts, spec)
+            ctx.saved = (x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec)
         return a
 
     @staticmethod
     def backward(ctx, dy):
         be = _be()
-        x, w0, gw, gb, mean, rstd, acts, zs, wts, spec = ctx.saved
+        x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec = ctx.saved
         n = len(spec)
         grads = [None] * n
         if n > 1:
@@ -266,7 +271,7 @@ class ConvFeatureFn(torch.autograd.Function):
         else:
             da0 = _bf16(dy)
         (c0, k0, s0) = spec[0]
-        dw0, dg, db = be.conv0_bwd(x, w0, gw, gb, mean, rstd, k0, s0, da0)
+        dw0, dg, db = be.conv0_bwd(x, w0, gw, gb, mean, rstd, mom, k0, s0, da0)
         grads[0] = dw0.view(c0, 1, k0)
         return (None, None, dg, db, *grads)
 
@@ -470,7 +475,7 @@ class QuantizerFn(torch.autograd.Function):
         y2 = y.detach().reshape(R, Cin).contiguous().float()
         w32 = w.detach().contiguous().float()
         # logits with fp32-accurate products on the tensor cores: bf16x3 split along K (csrc/misc.cu)
-        z = _empty((R, w.shape[0]), F32, y)
+        z = _empty((R, w.shape[0]), F32, y, dynamic=True)
         be.gemm(G.linear_fwd(be.split3(y2, False), be.split3(w32, True), z, b.detach(), c_dtype=OUT_F32))
         v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
         q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_)
@@ -491,13 +496,13 @@ class QuantizerFn(torch.autograd.Function):
             dppl = _zeros((), F32, y2)
         a_dot = None
         if noise is not None:
-            a_dot = _empty((R, v2.shape[0]), F32, y2)
+            a_dot = _empty((R, v2.shape[0]), F32, y2, dynamic=True)
             be.gemm(G.vq_codebook_dots(_bf16(dq2), _bf16(v2), a_dot, G_))
         dz, dvars = be.vq_bwd(z, noise, tau, G_, vd, a_dot, dq2, kidx, avg, ppl, dppl.contiguous().float())
         db = be.colsum(dz)
         dw = _zeros(w32.shape, F32, y2)
         be.gemm(G.linear_wgrad(dz, _bf16(y2), dw))
-        dy = _empty(y2.shape, F32, y2)
+        dy = _empty(y2.shape, F32, y2, dynamic=True)
         be.gemm(G.linear_dgrad(dz, _bf16(w32), dy, c_dtype=OUT_F32))
         return dy.view(yshape), dw, db, dvars.view(vshape), None, None, None
 

@@ -74,29 +74,42 @@ def _pick_bn(N):
 # cycles of one 128 x BN x 64 k-block on the tensor pipe (BN <= 128 tiles are bound by shared-memory operand reads)
 _MMA_CLK = {64: 192, 128: 282, 192: 384, 256: 512}
 _EPI_CLK_PER_COL = {"bf16": 10, "f32": 14, "atomic": 20, "gelu": 22}
+_L2_BYTES_PER_CLK = 43.0  # measured L2 -> SM feed per SM with all SMs loading (what bounds these GEMMs)
+FORCE = {}  # experiments (scripts/gemm_bench.py): {"bn": .., "split": .., "cluster": ..}
 
 
 @functools.lru_cache(maxsize=None)
-def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(128, 192, 256)):
-    """(block_n, split_k) minimising a small cost model of the persistent kernel: CTAs take ceil(tiles / SMs) tiles
-    each; a tile costs max(main loop, epilogue) because the two overlap through the TMEM accumulator ring."""
+def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(128, 192, 256), allow_cluster=True):
+    """(block_n, split_k, cluster) minimising a small cost model of the persistent kernel: CTAs take
+    ceil(tiles / SMs) tiles each; a k-block costs max(tensor time, L2 feed time of its operand bytes); a tile costs
+    max(main loop, epilogue) because the two overlap through the TMEM accumulator ring.  cluster = 2: CTA pairs on
+    vertically adjacent tiles multicast one B tile (half the B bytes per CTA)."""
     best = None
+    m_tiles = cdiv(M, 128)
     for bn in candidates:
         if bn > 64 and N <= bn // 2 and bn != candidates[0]:
             continue
-        tiles = cdiv(M, 128) * cdiv(N, bn) * batch
-        splits = [1]
-        if allow_split:
-            splits += [s for s in (2, 3, 4, 6, 8, 12, 16) if s <= k_blocks // 4]
-        for sp in splits:
-            kind = "atomic" if sp > 1 else epi
-            epi_clk = _EPI_CLK_PER_COL[kind] * bn
-            main = cdiv(k_blocks, sp) * _MMA_CLK[bn]
-            per_cta = cdiv(tiles * sp, NUM_SMS)
-            cost = per_cta * max(main, epi_clk) + epi_clk + 2000 + (1500 if sp > 1 else 0)
-            if best is None or cost < best[0]:
-                best = (cost, bn, sp)
-    return best[1], best[2]
+        for cl in ((1, 2) if (allow_cluster and bn in (128, 256) and m_tiles >= 2) else (1,)):
+            tiles = cdiv(m_tiles, cl) * cdiv(N, bn) * batch  # tile pairs when cl == 2
+            slots = NUM_SMS // cl
+            kb_clk = max(_MMA_CLK[bn], (128 + bn // cl) * 128 / _L2_BYTES_PER_CLK)
+            splits = [1]
+            if allow_split:
+                splits += [s for s in (2, 3, 4, 6, 8, 12, 16) if s <= k_blocks // 4]
+            for sp in splits:
+                kind = "atomic" if sp > 1 else epi
+                epi_clk = _EPI_CLK_PER_COL[kind] * bn
+                main = cdiv(k_blocks, sp) * kb_clk
+                per_cta = cdiv(tiles * sp, slots)
+                cost = per_cta * max(main, epi_clk) + epi_clk + 2000 + (1500 if sp > 1 else 0) + (300 if cl > 1 else 0)
+                if best is None or cost < best[0]:
+                    best = (cost, bn, sp, cl)
+    bn, sp, cl = best[1], best[2], best[3]
+    if FORCE:
+        bn = FORCE.get("bn", bn)
+        cl = FORCE.get("cluster", cl) if bn in (128, 256) and m_tiles >= 2 else 1
+        sp = FORCE.get("split", sp) if allow_split else 1
+    return bn, sp, cl
 
 
 def _split_k(M, N, k_blocks, batch=1):
@@ -114,9 +127,9 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
     a = Op(x, (K, M), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     epi = "gelu" if act == ACT_GELU else ("f32" if c_dtype == OUT_F32 else "bf16")
-    bn, _ = _tiling(M, N, cdiv(K, 64), epi=epi) if N > 128 else (0, 1)
+    bn, _, cl = _tiling(M, N, cdiv(K, 64), epi=epi) if N > 128 else (0, 1, 1)
     return _with_flops(GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
-                                aux_mode=aux_mode, bias=bias, block_n=bn), 2 * M * N * K)
+                                aux_mode=aux_mode, bias=bias, block_n=bn, cluster=cl), 2 * M * N * K)
 
 
 @cached_spec
@@ -127,9 +140,9 @@ def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     epi = "gelu" if aux_mode == AUX_MUL_GELU_GRAD else ("f32" if c_dtype == OUT_F32 else "bf16")
-    bn, _ = _tiling(M, K, cdiv(N, 64), epi=epi) if K > 128 else (0, 1)
-    return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode, block_n=bn),
-                       2 * M * N * K)
+    bn, _, cl = _tiling(M, K, cdiv(N, 64), epi=epi) if K > 128 else (0, 1, 1)
+    return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode, block_n=bn,
+                                cluster=cl), 2 * M * N * K)
 
 
 @cached_spec
@@ -142,9 +155,9 @@ def linear_wgrad(dy, x, dw):
     a = Op(dy, (N, M), (N,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     b = Op(x, (K, M), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     kb = cdiv(M, 64)
-    bn, sp = _tiling(N, K, kb, epi="f32", allow_split=True) if K > 128 else (0, _split_k(N, K, kb))
-    return _with_flops(GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC if sp > 1 else OUT_F32, split_k=sp, block_n=bn),
-                       2 * M * N * K)
+    bn, sp, cl = _tiling(N, K, kb, epi="f32", allow_split=True) if K > 128 else (0, _split_k(N, K, kb), 1)
+    return _with_flops(GemmSpec(a, b, N, K, kb, dw, K, OUT_F32_ATOMIC if sp > 1 else OUT_F32, split_k=sp, block_n=bn,
+                                cluster=cl), 2 * M * N * K)
 
 
 # ------------------------------------------------------------------------------------------------ conv 1..6
@@ -156,7 +169,8 @@ def conv_fwd(x, wk, y, k, s, z_out=None, act=ACT_GELU):
     _, Lout, Cout = y.shape
     a = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, 0, 1, 0))
     b = Op(wk, (k * Cin, Cout), (k * Cin,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
-    return _with_flops(GemmSpec(a, b, Lout, Cout, k * Cin // 64, y, Cout, OUT_BF16, lo_count=B,
+    bn, _, cl = _tiling(Lout, Cout, k * Cin // 64, batch=B, epi="gelu" if act == ACT_GELU else "bf16", candidates=(256,))
+    return _with_flops(GemmSpec(a, b, Lout, Cout, k * Cin // 64, y, Cout, OUT_BF16, lo_count=B, block_n=bn, cluster=cl,
                                 c_stride_lo=Lout * Cout, act=act, z_out=z_out), 2 * B * Lout * Cout * k * Cin)
 
 
@@ -176,7 +190,8 @@ def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
     a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_K, ck=(64, 0, 0, 0), cb=(0, -1, 0, 0), cr=(0, 1, 0, 0),
            cl=(0, 0, 1, 0))
     b = Op(wt_p, (ntaps * Cout, Cin), (ntaps * Cout,), MAJOR_K, ck=(64, 0, 0, 0), cb=(Cout, 0, 0, 0), cr=(0, 1, 0, 0))
-    return _with_flops(GemmSpec(a, b, U, Cin, ntaps * Cout // 64, dx, s * Cin, OUT_BF16, lo_count=B,
+    bn, _, cl = _tiling(U, Cin, ntaps * Cout // 64, batch=B, epi="gelu" if aux is not None else "bf16", candidates=(256,))
+    return _with_flops(GemmSpec(a, b, U, Cin, ntaps * Cout // 64, dx, s * Cin, OUT_BF16, lo_count=B, block_n=bn, cluster=cl,
                                 k_inner=Cout // 64, c_offset=p * Cin, c_stride_lo=Lin * Cin, aux=aux,
                                 aux_mode=AUX_MUL_GELU_GRAD if aux is not None else AUX_NONE),
                        2 * B * U * Cin * ntaps * Cout)
@@ -190,9 +205,9 @@ def conv_wgrad(dz, x, dwk, k, s):
     a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
     b = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cr=(64, 0, 0, 0))
     ki = cdiv(Lout, 64)
-    bn, sp = _tiling(Cout, k * Cin, B * ki, epi="f32", allow_split=True)
+    bn, sp, cl = _tiling(Cout, k * Cin, B * ki, epi="f32", allow_split=True)
     return _with_flops(GemmSpec(a, b, Cout, k * Cin, B * ki, dwk, k * Cin, OUT_F32_ATOMIC if sp > 1 else OUT_F32,
-                                k_inner=ki, split_k=sp, block_n=bn), 2 * B * Lout * Cout * k * Cin)
+                                k_inner=ki, split_k=sp, block_n=bn, cluster=cl), 2 * B * Lout * Cout * k * Cin)
 
 
 # ------------------------------------------------------------------------------------------------ pos conv

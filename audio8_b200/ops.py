@@ -37,7 +37,7 @@ class GemmSpec:
 
     def __init__(self, a, b, M, N, k_blocks, c, ldc, c_dtype=OUT_BF16, lo_count=1, hi_count=1, k_inner=None,
                  split_k=1, block_n=0, c_offset=0, c_stride_lo=0, c_stride_hi=0, act=ACT_NONE, z_out=None,
-                 aux=None, aux_mode=AUX_NONE, bias=None, bias_stride_lo=0, alpha=1.0):
+                 aux=None, aux_mode=AUX_NONE, bias=None, bias_stride_lo=0, alpha=1.0, cluster=1):
         self.a, self.b, self.M, self.N, self.k_blocks = a, b, M, N, k_blocks
         self.k_inner = k_inner if k_inner is not None else k_blocks
         self.c, self.ldc, self.c_dtype, self.c_offset = c, ldc, c_dtype, c_offset
@@ -45,7 +45,26 @@ class GemmSpec:
         self.c_stride_lo, self.c_stride_hi = c_stride_lo, c_stride_hi
         self.act, self.z_out, self.aux, self.aux_mode = act, z_out, aux, aux_mode
         self.bias, self.bias_stride_lo, self.alpha = bias, bias_stride_lo, alpha
+        self.cluster = cluster  # 2: CTA pairs share (multicast) the B tile; needs block_n 128 or 256
         self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
+
+
+def bucketed_empty(shape, dtype, device, zero=False):
+    """torch.empty for tensors whose size follows the per-step masked-row count: the element count is rounded up to
+    4 size classes per power of two (<= 25 % slack) and a view of the exact shape is returned, so torch's caching
+    allocator re-uses the same few blocks step after step instead of calling cudaMalloc (which synchronises the
+    device) whenever a slightly larger size shows up."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if n * torch.empty((), dtype=dtype).element_size() < 65536:
+        return torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype, device=device)
+    g = 1 << max(n.bit_length() - 3, 0)
+    cap = (n + g - 1) // g * g
+    buf = torch.zeros(cap, dtype=dtype, device=device) if zero else torch.empty(cap, dtype=dtype, device=device)
+    return buf[:n].view(shape)
 
 
 def _stream():
@@ -164,6 +183,7 @@ class CudaBackend:
             assert g.bias.dtype == torch.float32 and g.bias.is_cuda
             s.bias = g.bias.data_ptr()
         s.alpha = float(g.alpha)
+        s.reserved = 2 if g.cluster == 2 else 0
         return s
 
 
@@ -298,7 +318,7 @@ class CudaBackend:
 
     def dropout(self, x, p, seed):
         assert x.is_contiguous()
-        out = torch.empty_like(x)
+        out = bucketed_empty(x.shape, x.dtype, x.device)
         _lib.check(self.lib.a8_dropout(_ptr(x), _ptr(out), self._dt(x.dtype), x.numel(), p, seed, _stream()),
                    "a8_dropout")
         return out
@@ -335,7 +355,7 @@ class CudaBackend:
         rstd = torch.empty(B, C, dtype=torch.float32, device=x.device)
         _lib.check(self.lib.a8_conv0_stats(_ptr(x), B, L, _ptr(w), C, k, stride, eps, _ptr(mom), _ptr(mean), _ptr(rstd),
                                            _stream()), "a8_conv0_stats")
-        return mean, rstd
+        return mean, rstd, mom
 
     def conv0_fwd(self, x, w, gamma, beta, mean, rstd, k, stride):
         B, L = x.shape
@@ -346,16 +366,16 @@ class CudaBackend:
                                          stride, _ptr(y), _stream()), "a8_conv0_fwd")
         return y
 
-    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, k, stride, da):
+    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, mom, k, stride, da):
         B, L = x.shape
         C = w.shape[0]
-        assert da.dtype == torch.bfloat16 and da.is_contiguous()
-        sums = torch.empty(B * C * 2, dtype=torch.float32, device=x.device)
-        acc = torch.zeros(C * k + 2 * C, dtype=torch.float32, device=x.device)
-        dw, dg, db = acc[:C * k].view(C, k), acc[C * k:C * k + C], acc[C * k + C:]
-        _lib.check(self.lib.a8_conv0_bwd(_ptr(x), B, L, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), C, k,
-                                         stride, _ptr(da), _ptr(sums), _ptr(dw), _ptr(dg), _ptr(db), _stream()),
-                   "a8_conv0_bwd")
+        assert da.dtype == torch.bfloat16 and da.is_contiguous() and mom.dtype == torch.float64
+        acc = torch.empty(B * C * 12, dtype=torch.float32, device=x.device)
+        out = torch.empty(C * k + 2 * C, dtype=torch.float32, device=x.device)
+        dw, dg, db = out[:C * k].view(C, k), out[C * k:C * k + C], out[C * k + C:]
+        _lib.check(self.lib.a8_conv0_bwd(_ptr(x), B, L, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd),
+                                         _ptr(mom), C, k, stride, _ptr(da), _ptr(acc), _ptr(dw), _ptr(dg), _ptr(db),
+                                         _stream()), "a8_conv0_bwd")
         return dw, dg, db
 
     # ------------------------------------------------------------------ masks / indices / casts
@@ -366,7 +386,7 @@ class CudaBackend:
     def rows_gather(self, src, idx, out_dtype):
         C = src.shape[-1]
         assert src.is_contiguous() and idx.dtype == torch.int32
-        out = torch.empty(idx.numel(), C, dtype=out_dtype, device=src.device)
+        out = bucketed_empty((idx.numel(), C), out_dtype, src.device)
         _lib.check(self.lib.a8_rows_copy(_ptr(src), self._dt(src.dtype), _ptr(out), self._dt(out_dtype), _ptr(idx),
                                          idx.numel(), C, 0, _stream()), "a8_rows_copy")
         return out
@@ -401,7 +421,7 @@ class CudaBackend:
 
     def cast(self, x, dtype):
         assert x.is_contiguous()
-        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        out = bucketed_empty(x.shape, dtype, x.device)
         _lib.check(self.lib.a8_cast(_ptr(x), self._dt(x.dtype), _ptr(out), self._dt(dtype), x.numel(), _stream()),
                    "a8_cast")
         return out
@@ -409,7 +429,7 @@ class CudaBackend:
     def split3(self, x, b_side):
         R, C = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous()
-        out = torch.empty(R, 3 * C, dtype=torch.bfloat16, device=x.device)
+        out = bucketed_empty((R, 3 * C), torch.bfloat16, x.device)
         _lib.check(self.lib.a8_split3(_ptr(x), _ptr(out), R, C, int(b_side), _stream()), "a8_split3")
         return out
 
@@ -470,8 +490,8 @@ class CudaBackend:
         V = z.shape[1] // G
         vd = vars2d.shape[1]
         dev = z.device
-        q = torch.empty(R, G * vd, dtype=torch.float32, device=dev)
-        qb = torch.empty(R, G * vd, dtype=torch.bfloat16, device=dev)
+        q = bucketed_empty((R, G * vd), torch.float32, dev)
+        qb = bucketed_empty((R, G * vd), torch.bfloat16, dev)
         kidx = torch.empty(R * G, dtype=torch.int32, device=dev)
         avg = torch.empty(V, dtype=torch.float32, device=dev)
         ppl = torch.empty((), dtype=torch.float32, device=dev)
@@ -482,7 +502,7 @@ class CudaBackend:
     def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl):
         R = z.shape[0]
         V = z.shape[1] // G
-        dz = torch.empty(R, G * V, dtype=torch.bfloat16, device=z.device)
+        dz = bucketed_empty((R, G * V), torch.bfloat16, z.device)
         dvars = torch.zeros(G * V, vd, dtype=torch.float32, device=z.device)
         _lib.check(self.lib.a8_vq_bwd(_ptr(z), _ptr(noise), tau, R, G, V, vd, _ptr(a_dot), _ptr(dq), _ptr(kidx), _ptr(avg),
                                       _ptr(ppl), _ptr(dppl), _ptr(dz), _ptr(dvars), _stream()), "a8_vq_bwd")
@@ -494,7 +514,7 @@ class CudaBackend:
         dev = x.device
         assert x.dtype == torch.float32 and y.dtype == torch.float32 and idx.dtype == torch.int32
         xn = torch.empty(2 * R, dtype=torch.float32, device=dev)
-        cp = torch.empty(2, R, K + 1, dtype=torch.float32, device=dev)
+        cp = bucketed_empty((2, R, K + 1), torch.float32, dev)
         rl = torch.empty(R + 2, dtype=torch.float32, device=dev)
         _lib.check(self.lib.a8_contrastive_fwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(ppl), n_vars, xe_w, div_w,
                                                _ptr(xn), _ptr(xn, R), _ptr(cp[0]), _ptr(cp[1]), _ptr(rl), _ptr(rl, R),
@@ -505,8 +525,8 @@ class CudaBackend:
         R, Cc = x.shape
         K = idx.numel() // R
         xn, cp = saved
-        dx = torch.empty_like(x)
-        dy = torch.empty_like(y)
+        dx = bucketed_empty(x.shape, x.dtype, x.device)
+        dy = bucketed_empty(y.shape, y.dtype, y.device)
         _lib.check(self.lib.a8_contrastive_bwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(xn), _ptr(xn, R), _ptr(cp[0]),
                                                _ptr(cp[1]), _ptr(dce), _ptr(dx), _ptr(dy), _stream()),
                    "a8_contrastive_bwd")

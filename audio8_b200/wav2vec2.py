@@ -242,7 +242,7 @@ class GumbelVectorQuantizer(nn.Module):
             noise = self.noise_override
             if noise is None:  # what F.gumbel_softmax draws (wav2vec2.py:557)
                 n = B * T * self.num_groups
-                noise = -torch.empty(n, self.num_vars, dtype=F32, device=x.device).exponential_().log()
+                noise = Fn.ops.bucketed_empty((n, self.num_vars), F32, x.device).exponential_().log_().neg_()
             noise = noise.to(device=x.device, dtype=F32).contiguous()
         q, ppl, kidx = Fn.QuantizerFn.apply(x, self.weight_proj.weight, self.weight_proj.bias, self.vars,
                                             self.num_groups, self.curr_temperature, noise)

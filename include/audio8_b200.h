@@ -156,7 +156,7 @@ int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pdrop, uint64
  * key_keep uint8 [B,T] or NULL (0 = padded key: the reference's masked_fill(-1e9)); ctx bf16 [B,T,H*64];
  * lse fp32 [B,H,T] = log2-sum-exp2 of the scaled scores (saved for backward); delta fp32 [B,H,T] scratch;
  * dqkv bf16 [B,T,3*H*64] receives dQ | dK | dV.  Dropout keep decisions are a function of (seed + *seed_source,
- * b, h, q, k) with keep probability 1 - floor(pdrop*65536)/65536; a8_attn_dropmask writes them as bytes
+ * b, h, q, k) with keep probability 1 - floor(pdrop*2^32)/2^32; a8_attn_dropmask writes them as bytes
  * [B,H,T,T] (tests only). */
 int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, float* lse, int32_t B, int32_t H, int32_t T,
                 float scale, float pdrop, uint64_t seed, void* stream);
@@ -181,17 +181,19 @@ int a8_log_softmax_bwd(const float* dy, int64_t stride_outer, int64_t stride_row
 /* ------------------------------------------------------------------------------------------------
  * Feature-encoder layer 0: Conv1d(1->C,k,stride, no bias) + GroupNorm(C,C) + GELU, fused (`wav2vec2.py:419-422`).
  * x fp32 [B,L]; w fp32 [C,k]; y / da bf16 [B,L0,C] channels-last, L0 = (L-k)/stride + 1.
- *   stats: per-(b,c) mean / rstd over time from the window moments of x (moments: 65*B doubles of scratch)
+ *   stats: per-(b,c) mean / rstd over time from the window moments of x (moments: 65*B doubles, kept for bwd)
  *   fwd:   y = gelu(((conv(x) - mean) * rstd) * gamma + beta)
- *   bwd:   given da = dL/dy: dw, dgamma, dbeta ACCUMULATED (zero first); sums: 2*B*C floats of scratch
+ *   bwd:   given da = dL/dy: dw [C,k], dgamma, dbeta are WRITTEN.  One pass over da accumulates sum_t dy x_j,
+ *          sum_t dy, sum_t dy xhat per (b,c) (acc: 12*B*C floats of scratch); the GroupNorm backward's mean
+ *          corrections of dw follow from those and the forward's window moments.
  * ---------------------------------------------------------------------------------------------- */
 int a8_conv0_stats(const float* x, int32_t B, int64_t L, const float* w, int32_t C, int32_t k, int32_t stride,
                    float eps, double* moments, float* mean, float* rstd, void* stream);
 int a8_conv0_fwd(const float* x, int32_t B, int64_t L, const float* w, const float* gamma, const float* beta,
                  const float* mean, const float* rstd, int32_t C, int32_t k, int32_t stride, void* y, void* stream);
 int a8_conv0_bwd(const float* x, int32_t B, int64_t L, const float* w, const float* gamma, const float* beta,
-                 const float* mean, const float* rstd, int32_t C, int32_t k, int32_t stride, const void* da,
-                 float* sums, float* dw, float* dgamma, float* dbeta, void* stream);
+                 const float* mean, const float* rstd, const double* moments, int32_t C, int32_t k, int32_t stride,
+                 const void* da, float* acc, float* dw, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Time-mask plumbing (`wav2vec2.py:939,946,381,632,717,721`): index driven, no nonzero / host sync.

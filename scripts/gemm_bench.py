@@ -13,9 +13,9 @@ from audio8_b200 import ops  # noqa: E402
 from audio8_b200.ops import ACT_GELU, AUX_ADD, AUX_MUL_GELU_GRAD, OUT_F32  # noqa: E402
 
 dev = "cuda"
-if os.environ.get("BN"):  # experiment: force the N tile (and optionally split-K) chosen by gemm_specs._tiling
-    _orig = G._tiling
-    G._tiling = lambda *a, **k: (int(os.environ["BN"]), int(os.environ.get("SPLIT", _orig(*a, **k)[1]) if k.get("allow_split") else 1))
+for _k, _e in (("bn", "BN"), ("split", "SPLIT"), ("cluster", "CL")):  # experiments: force gemm_specs._tiling's choice
+    if os.environ.get(_e):
+        G.FORCE[_k] = int(os.environ[_e])
 bf = torch.bfloat16
 be = ops.backend()
 

@@ -205,8 +205,8 @@ class EmuOps(EmuBackend):
     @staticmethod
     def _attn_mask(shape, pdrop, seed, keep):
         if keep is not None:
-            thr = int(pdrop * 65536.0)
-            return keep.float() * (65536.0 / (65536.0 - thr))
+            thr = int(pdrop * 4294967296.0)
+            return keep.float() * (4294967296.0 / (4294967296.0 - thr))
         return _drop_mask(shape, pdrop, seed)
 
     def colsum(self, x, out=None):
@@ -272,7 +272,7 @@ class EmuOps(EmuBackend):
         z = torch.nn.functional.conv1d(x.double()[:, None, :], w.double()[:, None, :], stride=stride)  # [B,C,L0]
         mean = z.mean(-1)
         var = z.var(-1, unbiased=False)
-        return mean.float(), (var + eps).rsqrt().float()
+        return mean.float(), (var + eps).rsqrt().float(), None  # (the CUDA backend also returns its window moments)
 
     def _conv0_z(self, x, w, stride):
         return torch.nn.functional.conv1d(x[:, None, :], w[:, None, :], stride=stride).transpose(1, 2)  # [B,L0,C]
@@ -282,7 +282,7 @@ class EmuOps(EmuBackend):
         y = (z - mean[:, None, :]) * rstd[:, None, :] * gamma + beta
         return _bf(gelu(y)).contiguous()
 
-    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, k, stride, da):
+    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, mom, k, stride, da):
         z = self._conv0_z(x, w, stride)
         xh = (z - mean[:, None, :]) * rstd[:, None, :]
         dy = da.float() * gelu_grad(xh * gamma + beta)

@@ -130,16 +130,16 @@ def test_conv0(be, B, L):
     w = (torch.rand(C, k, generator=_g(2)) * 2 - 1) * math.sqrt(3.0 / k)
     gamma = 1 + 0.1 * torch.randn(C, generator=_g(3))
     beta = 0.1 * torch.randn(C, generator=_g(4))
-    mean_r, rstd_r = E.conv0_stats(x, w, k, s, 1e-5)
-    mean, rstd = be.conv0_stats(x.cuda(), w.cuda(), k, s, 1e-5)
+    mean_r, rstd_r, _ = E.conv0_stats(x, w, k, s, 1e-5)
+    mean, rstd, mom = be.conv0_stats(x.cuda(), w.cuda(), k, s, 1e-5)
     _close(mean, mean_r, 1e-4, "conv0 mean")
     _close(rstd, rstd_r, 1e-4, "conv0 rstd")
     y_r = E.conv0_fwd(x, w, gamma, beta, mean_r, rstd_r, k, s)
     y = be.conv0_fwd(x.cuda(), w.cuda(), gamma.cuda(), beta.cuda(), mean, rstd, k, s)
     _close(y, y_r, 1e-2, "conv0 fwd")
     da = _bf(tuple(y_r.shape), 5)
-    ref = E.conv0_bwd(x, w, gamma, beta, mean_r, rstd_r, k, s, da)
-    got = be.conv0_bwd(x.cuda(), w.cuda(), gamma.cuda(), beta.cuda(), mean, rstd, k, s, da.cuda())
+    ref = E.conv0_bwd(x, w, gamma, beta, mean_r, rstd_r, None, k, s, da)
+    got = be.conv0_bwd(x.cuda(), w.cuda(), gamma.cuda(), beta.cuda(), mean, rstd, mom, k, s, da.cuda())
     for g, r, name in zip(got, ref, ["dw", "dgamma", "dbeta"]):
         _close(g, r, 5e-3, "conv0 bwd " + name)
 
