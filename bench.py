@@ -268,6 +268,20 @@ def run_ours(args):
         time.sleep(0.1)
     for _ in range(2):
         step(x_dev)
+    if args.ncu_step:
+        # `ncu --profile-from-start off ... bench.py --ncu-step`: exactly ONE warmed-up step inside the profiler range
+        # (numbers printed by a run under ncu are never bench values: nothing is printed)
+        eager = os.environ.get("A8_NCU_EAGER")
+        if eager:
+            from audio8_b200 import graphs
+            graphs.set_enabled(False)
+            step(x_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(x_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---- device-resident timing: exactly K steps between barriers, CUDA events, max over ranks
     barrier()
     clocks.mark_begin()
@@ -375,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (cudaProfilerStart/Stop) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

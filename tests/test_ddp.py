@@ -1,0 +1,148 @@
+"""Data-parallel path: one process per rank, batch sharded by utterance, gradients averaged by
+DistributedDataParallel — here world_size 2 over `gloo` on CPU with the ABI emulation standing in for the kernels
+(the host-side orchestration, the autograd Functions and their interaction with DDP's reducer hooks are what is
+being tested; NCCL replaces gloo on the GPU box, `bench.py --gpus N`).
+
+Reference behaviour (pretrain.py:158,178-179): `DistributedDataParallel(model)`, per-rank `loss_function(model, x)`,
+`.backward()` — DDP's plain average of per-rank gradients; masks / negatives / perplexity are per-rank quantities.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+TINY = dict(d_model=128, num_heads=2, num_layers=1, d_ff=256, final_dim=64, num_vq_vars=24, num_vq_groups=2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _local_grads(model, loss_fn, x, seed):
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    model.zero_grad(set_to_none=True)
+    loss = loss_fn(model, x)
+    loss.backward()
+    return loss.item(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def _worker(rank, world, port, out_dir, no_sync):
+    for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        from audio8_b200 import ops
+        from audio8_b200 import wav2vec2 as W
+        ops.set_backend(emu.EmuOps())
+        torch.manual_seed(0)  # identical initial weights on every rank (DDP would broadcast rank 0's anyway)
+        model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **TINY).train()
+        loss_fn = W.create_loss(TINY["num_vq_vars"] * TINY["num_vq_groups"], 10)
+        xs = [torch.randn(2, 8000, generator=torch.Generator().manual_seed(100 + r)) * 0.1 for r in range(world)]
+        # expected: average over ranks of the per-rank gradients, computed locally without DDP
+        want, losses = None, []
+        for r in range(world):
+            l, g = _local_grads(model, loss_fn, xs[r], 7 + r)
+            losses.append(l)
+            want = g if want is None else {k: want[k] + g[k] for k in g}
+        want = {k: v / world for k, v in want.items()}
+        ddp = torch.nn.parallel.DistributedDataParallel(model)
+        if no_sync:
+            # gradient accumulation (train.py:301): micro-step under no_sync() must not all-reduce
+            with ddp.no_sync():
+                l0, g_local = _local_grads(ddp, loss_fn, xs[rank], 7 + rank)
+            g_local = {k.replace("module.", "", 1): v for k, v in g_local.items()}
+            solo = _local_grads(model, loss_fn, xs[rank], 7 + rank)[1]
+            for k in solo:
+                assert torch.allclose(g_local[k], solo[k], rtol=1e-5, atol=1e-7), f"no_sync changed grad {k}"
+        l, got = _local_grads(ddp, loss_fn, xs[rank], 7 + rank)
+        assert abs(l - losses[rank]) <= 1e-5 * abs(l), (l, losses[rank])
+        got = {k.replace("module.", "", 1): v for k, v in got.items()}
+        assert set(got) == set(want)
+        for k in want:
+            err = (got[k] - want[k]).abs().max().item()
+            scale = want[k].abs().max().item() + 1e-8
+            assert err <= 1e-4 * scale + 1e-7, f"rank {rank} grad {k}: {err:.3g} vs scale {scale:.3g}"
+        # every rank holds the same averaged gradient
+        flat = torch.cat([got[k].reshape(-1) for k in sorted(got)])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        for g in gathered:
+            assert torch.equal(g, flat)
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_gloo_world2_matches_mean_of_rank_gradients(tmp_path, no_sync=True):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), no_sync), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _ctc_worker(rank, world, port, out_dir):
+    """fine-tuning normalisation (train.py:318-323): DDP mean x num_gpus / global target count"""
+    for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        from audio8_b200 import ops
+        from audio8_b200 import wav2vec2 as W
+        from audio8_b200.ctc import CTCLoss
+        ops.set_backend(emu.EmuOps())
+        torch.manual_seed(0)
+        model = W.create_acoustic_model(32, d_model=128, num_heads=2, num_layers=1, d_ff=256, dropout=0.0,
+                                        timestep_masking=0.0, channel_masking=0.0).train()
+        model.freeze = False
+        crit = CTCLoss()
+        B = 2 + rank  # unequal per-rank batches
+        g = torch.Generator().manual_seed(50 + rank)
+        x = torch.randn(B, 8000, generator=g) * 0.1
+        pad_mask = torch.ones(B, 8000, dtype=torch.bool)
+        targets = torch.randint(4, 32, (B, 5), generator=g)
+        tl = torch.full((B,), 5, dtype=torch.int64)
+        # train.py:266-268 wraps with find_unused_parameters=True (frozen feature encoder, unused mask_emb)
+        ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=True)
+        lp, fmask = ddp(x, pad_mask)
+        loss = crit(lp.transpose(1, 0), fmask.sum(-1), targets, tl)
+        loss.backward()
+        n = torch.tensor([float(tl.sum())])
+        dist.all_reduce(n)
+        scale = world / n.item()
+        grads = torch.cat([p.grad.reshape(-1) * scale for p in model.parameters() if p.grad is not None])
+        assert torch.isfinite(grads).all() and grads.abs().max() > 0
+        gathered = [torch.empty_like(grads) for _ in range(world)]
+        dist.all_gather(gathered, grads)
+        assert torch.equal(gathered[0], gathered[1])
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_gloo_world2_ctc_unequal_batches(tmp_path):
+    world = 2
+    mp.spawn(_ctc_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
