@@ -1,0 +1,511 @@
+// audio8_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+// Roles inside one 256-thread CTA (one CTA per SM, persistent over output tiles):
+//   warp 0 (one elected lane)  TMA producer: cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
+//   warp 1 (one elected lane)  MMA issuer:   tcgen05.mma (M=128, N=BN, K=16) -> TMEM accumulators
+//   warp 2                     TMEM allocator / deallocator
+//   warps 4..7                 epilogue: tcgen05.ld -> registers -> bias/GELU/residual -> HBM
+// Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
+// (MMA <-> epilogue), so the epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "a8_common.cuh"
+#include "../../include/audio8_b200.h"
+
+namespace a8 {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int EPI_WARPS = 8;  // warps 4..11: two per TMEM lane quarter, each owns half of the tile's columns
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+enum { MAJOR_K = A8_MAJOR_K, MAJOR_MN = A8_MAJOR_MN };
+enum { OUT_BF16 = A8_OUT_BF16, OUT_F32 = A8_OUT_F32, OUT_F32_ATOMIC = A8_OUT_F32_ATOMIC };
+enum { ACT_NONE = A8_ACT_NONE, ACT_GELU = A8_ACT_GELU };
+enum { AUX_NONE = A8_AUX_NONE, AUX_ADD = A8_AUX_ADD, AUX_MUL_GELU_GRAD = A8_AUX_MUL_GELU_GRAD };
+
+struct OpCoef {
+  int base[4], ck[4], cb[4], cr[4], cl[4], ch[4];
+};
+
+// Epilogue kind, a template parameter of the kernel: EK_GENERIC reads every switch from KParams at run time (one
+// large body: ~9000 SASS instructions, which thrashes the instruction cache of the 8 epilogue warps); any other
+// value fixes (c_dtype | gelu << 2 | z_out << 3 | aux_mode << 4) at compile time so that the hot shapes run a
+// straight-line epilogue a few hundred instructions long.
+constexpr int EK_GENERIC = -1;
+constexpr int ek_make(int c_dtype, int gelu, int z, int aux) { return c_dtype | (gelu << 2) | (z << 3) | (aux << 4); }
+
+struct KParams {
+  int M, N, m_tiles, n_tiles, lo_count, hi_count;  // m_tiles counts tile PAIRS when the kernel runs as 2-CTA clusters
+  int k_blocks, k_inner, split_k;
+  OpCoef a, b;
+  void* c;
+  int c_dtype;
+  void* z_out;
+  const void* aux;
+  int aux_mode;
+  const float* bias;
+  int bias_stride_lo;
+  int act;
+  float alpha;
+  long long ldc, c_stride_lo, c_stride_hi;
+  int total_tiles;
+};
+
+__device__ __forceinline__ void op_coords(const OpCoef& o, int kin, int kbatch, int r, int lo, int hi,
+                                          int (&c)[4]) {
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    c[d] = o.base[d] + o.ck[d] * kin + o.cb[d] * kbatch + o.cr[d] * r + o.cl[d] * lo + o.ch[d] * hi;
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // powers of two >= 32; 2 accumulator stages
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * 32 * 80 + 1024;
+};
+
+// UMMA shared-memory matrix descriptor, 128B swizzle (layout type 2), descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+struct TileCoord {
+  int nt, mt, lo, hi, kb_begin, kb_end;
+};
+template <int CL>
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int rank) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  t.mt = (r % p.m_tiles) * CL + rank;
+  r /= p.m_tiles;
+  t.lo = r % p.lo_count;
+  r /= p.lo_count;
+  t.hi = r % p.hi_count;
+  const int split = r / p.hi_count;
+  t.kb_begin = (int)(((long long)split * p.k_blocks) / p.split_k);
+  t.kb_end = (int)(((long long)(split + 1) * p.k_blocks) / p.split_k);
+  return t;
+}
+
+constexpr int STG_PITCH = 80;                 // bytes per staged row: 64 payload + 16 pad (conflict-free 16B writes)
+constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
+
+// Coalesced copy between a warp's staging buffer (32 rows x 64 B) and global rows `row_off0 + r*ldc` (element
+// offsets of element size ES): lane l moves 16 B of row (l/4 + 8i), piece (l%4) — every instruction touches 8 rows
+// x 64 contiguous bytes instead of 32 rows x 16 bytes.
+enum { STG_LOAD = 0, STG_STORE = 1, STG_RED = 2 };
+template <int ES, int MODE>
+__device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long row_off0, long long ldc, int col0,
+                                           int rows_valid, int cols_valid, int lane) {
+  constexpr int EPP = 16 / ES;  // elements per 16-byte piece
+  const int piece = lane & 3;
+  const int col = col0 + piece * EPP;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    if (r < rows_valid && col < cols_valid) {
+      uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (row_off0 + (long long)r * ldc + col) * ES;
+      uint4* sp = reinterpret_cast<uint4*>(stg + r * STG_PITCH + piece * 16);
+      if (MODE == STG_STORE) {
+        *reinterpret_cast<uint4*>(g) = *sp;
+      } else if (MODE == STG_LOAD) {
+        *sp = *reinterpret_cast<const uint4*>(g);
+      } else {  // split-K: one 16-byte vector reduction per lane, 64 contiguous bytes per row
+        const float4 v = *reinterpret_cast<const float4*>(sp);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+      }
+    }
+  }
+}
+
+// 32 columns x 32 rows (one row per lane) of accumulators in registers -> epilogue math -> global memory.
+// Non-atomic outputs (and the bf16 aux input) go through the warp's smem staging buffer so that global accesses
+// are row-contiguous; the split-K fp32 path adds atomically straight from registers.
+template <int EK>
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t* r, long long row_off0, int row0,
+                                               int nb, const float* sb, uint8_t* stg, int lane) {
+  constexpr bool GEN = (EK < 0);
+  const int c_dtype = GEN ? p.c_dtype : (EK & 3);
+  const bool do_gelu = GEN ? (p.act == ACT_GELU) : (((EK >> 2) & 1) != 0);
+  const bool do_z = GEN ? (p.z_out != nullptr) : (((EK >> 3) & 1) != 0);
+  const int aux_mode = GEN ? p.aux_mode : ((EK >> 4) & 3);
+  const int rows_valid = min(32, p.M - row0);        // may be <= 0
+  const int n8 = (p.N + 7) & ~7;
+  const int cols_valid = n8;                          // absolute column bound for the 16-byte pieces
+  const bool has_aux = aux_mode != AUX_NONE;
+  uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
+  uint4 a[4];
+  if (has_aux) {
+    stage_copy<2, STG_LOAD>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) a[g] = my[g];
+    __syncwarp();
+  }
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (sb != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += sb[i];
+  }
+  if (do_z) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 z;
+      z.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); z.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+      z.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); z.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+      my[g] = z;
+    }
+    __syncwarp();
+    stage_copy<2, STG_STORE>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    __syncwarp();
+  }
+  if (do_gelu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+  }
+  if (has_aux) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t w[4] = {a[g].x, a[g].y, a[g].z, a[g].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16(w[j]);
+        if (aux_mode == AUX_ADD) {
+          v[8 * g + 2 * j] += t.x;
+          v[8 * g + 2 * j + 1] += t.y;
+        } else {
+          v[8 * g + 2 * j] *= gelu_grad_fast(t.x);
+          v[8 * g + 2 * j + 1] *= gelu_grad_fast(t.y);
+        }
+      }
+    }
+  }
+  if (c_dtype == OUT_BF16) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+      o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+      my[g] = o;
+    }
+    __syncwarp();
+    stage_copy<2, STG_STORE>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    __syncwarp();
+  } else {  // fp32: plain stores, or vector reductions for split-K partial sums
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        my[g] = make_uint4(__float_as_uint(v[16 * h + 4 * g]), __float_as_uint(v[16 * h + 4 * g + 1]),
+                           __float_as_uint(v[16 * h + 4 * g + 2]), __float_as_uint(v[16 * h + 4 * g + 3]));
+      __syncwarp();
+      if (c_dtype == OUT_F32)
+        stage_copy<4, STG_STORE>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+      else
+        stage_copy<4, STG_RED>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+      __syncwarp();
+    }
+  }
+}
+
+// ---- 2-CTA cluster mode: the two CTAs of a cluster own vertically adjacent 128-row tiles of the same n-tile, so they
+// need the SAME B tile: each loads half of it and multicasts that half into both CTAs' shared memory.  L2 -> SM
+// traffic per CTA and k-block drops from (128 + BN) x 128 B to (128 + BN/2) x 128 B, which is what bounds these GEMMs
+// (the measured L2 feed is ~43 B/clk/SM).  A stage may be refilled only when BOTH CTAs have consumed it: the MMA
+// issuer's tcgen05.commit arrives on the stage's empty barrier of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1,
+                                               int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
+template <int MA, int MB, int BN, int CL, int EK>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const KParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * C::A_BYTES;
+  const uint32_t bars = sB + STAGES * C::B_BYTES;
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (STAGES + i); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw_u32));  // [2 accumulator stages][BN]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + 2 * BN);                // [EPI_WARPS][32 rows][80 B]
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(full_bar(i), 1);
+        mbar_init(empty_bar(i), CL);  // one tcgen05.commit arrival per CTA of the cluster
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(tfull_bar(i), 1);
+        mbar_init(tempty_bar(i), 32 * EPI_WARPS);
+      }
+      mbar_fence_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything can signal them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();  // the next kernel's prologue may start; it waits for this grid before touching memory
+  pdl_wait();               // everything above overlapped the previous kernel's tail
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile<CL>(p, tile, rank);
+        const int m0 = t.mt * BLOCK_M, n0 = t.nt * BN;
+        int kin = t.kb_begin % p.k_inner, kbatch = t.kb_begin / p.k_inner;  // advanced incrementally: no division
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {                     // on the per-k-block issue path
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::A_BYTES + C::B_BYTES);
+          const uint32_t a_dst = sA + stage * C::A_BYTES;
+          const uint32_t b_dst = sB + stage * C::B_BYTES;
+          int cc[4];
+          if (MA == MAJOR_K) {
+            op_coords(p.a, kin, kbatch, m0, t.lo, t.hi, cc);
+            tma_load_4d(&map_a, full_bar(stage), a_dst, cc[0], cc[1], cc[2], cc[3]);
+          } else {
+#pragma unroll
+            for (int at = 0; at < BLOCK_M / 64; ++at) {
+              op_coords(p.a, kin, kbatch, m0 / 64 + at, t.lo, t.hi, cc);
+              tma_load_4d(&map_a, full_bar(stage), a_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+            }
+          }
+          if (CL == 1) {
+            if (MB == MAJOR_K) {
+              op_coords(p.b, kin, kbatch, n0, t.lo, t.hi, cc);
+              tma_load_4d(&map_b, full_bar(stage), b_dst, cc[0], cc[1], cc[2], cc[3]);
+            } else {
+#pragma unroll
+              for (int at = 0; at < BN / 64; ++at) {
+                op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
+                tma_load_4d(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+              }
+            }
+          } else {  // this CTA's half of the B tile, multicast into both CTAs (same smem offset, same barrier offset)
+            if (MB == MAJOR_K) {
+              op_coords(p.b, kin, kbatch, n0 + rank * (BN / 2), t.lo, t.hi, cc);
+              tma_load_4d_mc(&map_b, full_bar(stage), b_dst + rank * (C::B_BYTES / 2), cc[0], cc[1], cc[2], cc[3], 3);
+            } else {
+#pragma unroll
+              for (int a2 = 0; a2 < BN / 128; ++a2) {
+                const int at = rank * (BN / 128) + a2;
+                op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
+                tma_load_4d_mc(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3], 3);
+              }
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          if (++kin == p.k_inner) {
+            kin = 0;
+            ++kbatch;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MA << 15) |
+                                 ((uint32_t)MB << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BLOCK_M >> 4) << 24);
+      // K-major: 8-row groups are 1024 B apart (SBO), one swizzle span along K (LBO unused).
+      // MN-major: 64-element MN atoms are BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B (SBO).
+      constexpr uint32_t A_LBO = (MA == MAJOR_K) ? 0u : BLOCK_K * 128u;
+      constexpr uint32_t B_LBO = (MB == MAJOR_K) ? 0u : BLOCK_K * 128u;
+      constexpr uint32_t A_KADV = (MA == MAJOR_K) ? UMMA_K * 2u : UMMA_K * 128u;
+      constexpr uint32_t B_KADV = (MB == MAJOR_K) ? UMMA_K * 2u : UMMA_K * 128u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
+        const TileCoord t = decode_tile<CL>(p, tile, rank);
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = sA + stage * C::A_BYTES;
+          const uint32_t b_addr = sB + stage * C::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * A_KADV, A_LBO, 1024u);
+            const uint64_t db = make_smem_desc(b_addr + k * B_KADV, B_LBO, 1024u);
+            umma_bf16(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+          }
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mc(empty_bar(stage), 3);
+          if (kb == t.kb_end - 1) umma_commit(tfull_bar(as));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    // warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the tile's columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int COLS = BN / 2;         // columns per warp
+    constexpr int NCH = COLS / 32;       // 32-column chunks per warp (4 / 2 / 1)
+    const int tid_e = threadIdx.x - 128;
+    int iter = 0;
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
+      const TileCoord t = decode_tile<CL>(p, tile, rank);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      float* sb = nullptr;
+      if (p.bias != nullptr) {
+        // stage this tile's bias slice in shared memory while the main loop of the tile is still running
+        sb = s_bias + as * BN;
+        const float* bsrc = p.bias + (long long)t.lo * p.bias_stride_lo + t.nt * BN;
+        for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) sb[i] = (t.nt * BN + i < p.N) ? __ldg(bsrc + i) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row0 = t.mt * BLOCK_M + q * 32;
+      const long long row_off0 =
+          (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row0 * p.ldc;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * COLS;
+      const int nb0 = t.nt * BN + half * COLS;
+      const float* sbw = sb ? sb + half * COLS : nullptr;
+      uint8_t* stg = s_stage + (warp - 4) * STG_BYTES;
+      // one 32-column chunk at a time, NOT unrolled: the chunk body is several hundred instructions and the 8
+      // epilogue warps must stay inside the instruction cache (the other 7 warps hide this warp's tcgen05.ld latency)
+      uint32_t ra[32];
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        if (nb0 + c * 32 >= p.N) break;
+        tmem_ld_32x32(t_addr + c * 32, ra);
+        tmem_ld_wait();
+        epilogue_chunk<EK>(p, ra, row_off0, row0, nb0 + c * 32, sbw ? sbw + c * 32 : nullptr, stg, lane);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // neither CTA exits while the peer may still write its smem or signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch (instantiated per (MA, MB) in gemm_tc_inst_*.cu so that the translation units build in parallel)
+// ---------------------------------------------------------------------------------------------
+int num_sms();  // gemm_tc.cu
+
+template <int MA, int MB, int BN, int CL, int EK>
+int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<MA, MB, BN, CL, EK>;
+  if (!configured) {
+    A8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  const int slots = num_sms() / CL;
+  const int grid = CL * (kp.total_tiles < slots ? kp.total_tiles : slots);
+  A8_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM_BYTES, stream, CL, ma, mb, kp));
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int MA, int MB, int EK>
+int launch_bn(int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
+              cudaStream_t stream) {
+  if (cl == 2) {
+    switch (bn) {
+      case 128: return launch_inst<MA, MB, 128, 2, EK>(ma, mb, kp, stream);
+      case 256: return launch_inst<MA, MB, 256, 2, EK>(ma, mb, kp, stream);
+    }
+    set_error("gemm: cluster mode needs block_n 128 or 256 (got %d)", bn);
+    return -1;
+  }
+  switch (bn) {
+    case 64: return launch_inst<MA, MB, 64, 1, EK>(ma, mb, kp, stream);
+    case 128: return launch_inst<MA, MB, 128, 1, EK>(ma, mb, kp, stream);
+    case 192: return launch_inst<MA, MB, 192, 1, EK>(ma, mb, kp, stream);
+    case 256: return launch_inst<MA, MB, 256, 1, EK>(ma, mb, kp, stream);
+  }
+  set_error("gemm: unsupported block_n %d", bn);
+  return -1;
+}
+
+// one entry per (MA, MB): picks the specialised epilogue when (c_dtype, act, z_out, aux_mode) is on its list
+int launch_kk(int ek, int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t s);
+int launch_kmn(int ek, int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t s);
+int launch_mnmn(int ek, int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t s);
+
+}  // namespace gemm
+}  // namespace a8
