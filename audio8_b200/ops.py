@@ -49,22 +49,39 @@ class GemmSpec:
         self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
 
 
+_DYN = [0, 0]  # (rows of the current step's masked-row tensors, their upper bound); set_dynamic_rows()
+
+
+def set_dynamic_rows(rows, rows_max):
+    """The model announces, per step, the masked-row count R = B*Tm and its upper bound for this input shape.
+    Tensors whose size is a multiple of R are then allocated with their worst-case size (`bucketed_empty`), so the
+    caching allocator sees the same request sizes on every step: no cudaMalloc (tens of ms, device-synchronising)
+    shows up in steady state when a step draws a few more masked frames than any step before it."""
+    _DYN[0], _DYN[1] = int(rows), int(max(rows, rows_max))
+
+
 def bucketed_empty(shape, dtype, device, zero=False):
-    """torch.empty for tensors whose size follows the per-step masked-row count: the element count is rounded up to
-    4 size classes per power of two (<= 25 % slack) and a view of the exact shape is returned, so torch's caching
-    allocator re-uses the same few blocks step after step instead of calling cudaMalloc (which synchronises the
-    device) whenever a slightly larger size shows up."""
+    """torch.empty for tensors whose size follows the per-step masked-row count.  With set_dynamic_rows() in effect
+    and an element count divisible by the row count, the worst-case size is allocated and a view of the exact shape
+    returned; otherwise the element count is rounded up to 4 size classes per power of two (<= 25 % slack)."""
     if isinstance(shape, int):
         shape = (shape,)
     n = 1
     for d in shape:
         n *= int(d)
-    if n * torch.empty((), dtype=dtype).element_size() < 65536:
-        return torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype, device=device)
-    g = 1 << max(n.bit_length() - 3, 0)
-    cap = (n + g - 1) // g * g
-    buf = torch.zeros(cap, dtype=dtype, device=device) if zero else torch.empty(cap, dtype=dtype, device=device)
-    return buf[:n].view(shape)
+    R, Rmax = _DYN
+    if R > 0 and n > 0 and n % R == 0:
+        cap = n // R * Rmax
+    else:
+        if n * torch.empty((), dtype=dtype).element_size() < 65536:
+            return torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype, device=device)
+        g = 1 << max(n.bit_length() - 3, 0)
+        cap = (n + g - 1) // g * g
+    buf = torch.empty(cap, dtype=dtype, device=device)
+    out = buf[:n]
+    if zero:
+        out.zero_()
+    return out.view(shape)
 
 
 def _stream():

@@ -42,18 +42,20 @@ def create_mask(shape, p_start=0.65, mask_length=10):
     if num_mask == 0:
         return mask
     rows = []
-    for _ in range(bsz):
+    offs = np.arange(mask_length)[None, :]
+    for i in range(bsz):
         span = mask_length
         if T - span <= num_mask:
             span = T - num_mask - 1
         starts = np.random.choice(T - span, num_mask, replace=False)
-        idx = (starts[:, None] + np.arange(mask_length)[None, :]).reshape(-1)
-        rows.append(np.unique(idx[idx < T]))
+        idx = (starts[:, None] + offs).reshape(-1)
+        mask[i, idx[idx < T]] = True
+        rows.append(np.flatnonzero(mask[i]))  # == np.unique(idx[idx < T]) of the reference: sorted, no duplicates
     keep = min(len(r) for r in rows)
     for i, r in enumerate(rows):
         if len(r) > keep:
-            r = np.random.choice(r, keep, replace=False)
-        mask[i, r] = True
+            mask[i] = False
+            mask[i, np.random.choice(r, keep, replace=False)] = True
     return mask
 
 
@@ -115,6 +117,13 @@ def _mask_rows(mask_np, device):
     return _to_device(idx, device)
 
 
+def conv_out_length(L, conv_features):
+    """frames produced by the conv feature encoder for L samples (no padding: floor((L - k) / s) + 1 per layer)"""
+    for (_, k, s) in conv_features:
+        L = (L - k) // s + 1
+    return L
+
+
 class Sampler:
     """Negative sampling among the masked steps of the same utterance (reference wav2vec2.py:955-976)."""
 
@@ -123,10 +132,17 @@ class Sampler:
 
     def indices(self, B, T):
         """[B, K*T] int64 numpy, already offset by b*T; identical draws to the reference's np.random.randint"""
-        own_t = np.repeat(np.arange(T), self.n_negatives)[None, :]
-        idx = np.random.randint(0, T - 1, (B, self.n_negatives * T))
-        idx = np.where(idx >= own_t, idx + 1, idx)
-        return idx + (np.arange(B) * T)[:, None]
+        return self.indices32(B, T).astype(np.int64)
+
+    def indices32(self, B, T):
+        """same values as int32 (what the kernels read).  Only the randint call is the reference's; the never-the-
+        positive shift and the per-utterance offset are done in place on the narrow copy (the int64 `where` of the
+        reference costs as much host time as the draw itself)."""
+        own_t = np.repeat(np.arange(T, dtype=np.int32), self.n_negatives)[None, :]
+        idx = np.random.randint(0, T - 1, (B, self.n_negatives * T)).astype(np.int32)
+        idx += idx >= own_t
+        idx += (np.arange(B, dtype=np.int32) * T)[:, None]
+        return idx
 
     def negatives(self, y):
         """reference-compatible API: returns (negs [K,B,T,C], neg_idxs [B,K*T]); the fused loss never calls this"""
@@ -135,6 +151,49 @@ class Sampler:
         negs = y.reshape(-1, C)[idx.view(-1).to(y.device)]
         return negs.view(B, T, self.n_negatives, C).permute(2, 0, 1, 3), idx
 
+
+class _HostDraws:
+    """All numpy-RNG draws of one pre-training step, made on a helper thread in the reference's order — span mask
+    (wav2vec2.py:189-216), one draw per transformer layer (eight_mile's LayerDrop test), negative indices
+    (wav2vec2.py:967) — while the main thread keeps enqueuing GPU work.  numpy's legacy generator releases the GIL
+    inside randint / permutation, so the ~3 ms of host time a step spends drawing no longer stalls the stream.
+    The draws are the same calls on the same global generator in the same order: results stay bit-identical to the
+    reference's as long as nothing else draws from np.random during the step (nothing in this package does)."""
+
+    def __init__(self, B, T, p_start, mask_length, n_layers, sampler=None):
+        import threading
+        self.args = (B, T, p_start, mask_length, n_layers, sampler)
+        self.mask = self.layer_draws = self.neg = self.error = None
+        self.ev_mask, self.ev_neg = threading.Event(), threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        B, T, p_start, mask_length, n_layers, sampler = self.args
+        try:
+            self.mask = create_mask((B, T), p_start=p_start, mask_length=mask_length)
+            self.layer_draws = [np.random.random() for _ in range(n_layers)]
+        except BaseException as e:  # re-raised on the consumer's thread
+            self.error = e
+        self.ev_mask.set()
+        try:
+            if self.error is None and sampler is not None:
+                self.neg = sampler.indices32(B, int(self.mask[0].sum()))
+        except BaseException as e:
+            self.error = e
+        self.ev_neg.set()
+
+    def time_mask(self):
+        self.ev_mask.wait()
+        if self.error is not None:
+            raise self.error
+        return self.mask, self.layer_draws
+
+    def negatives(self):
+        self.ev_neg.wait()
+        if self.error is not None:
+            raise self.error
+        return self.neg
 
 # --------------------------------------------------------------------------------------------------
 # small modules with reference-identical parameter names
@@ -325,12 +384,12 @@ class AudioTransformerEncoder(nn.Module):
     def forward(self, x, pad_mask=None):
         return self.extract_features(x, pad_mask)
 
-    def extract_features(self, x, pad_mask=None):
+    def extract_features(self, x, pad_mask=None, _layer_draws=None):
         """x [B,T,D] (bf16 or fp32), pad_mask bool [B,T] (True = valid) or None -> bf16 [B,T,D]"""
         n = len(self.transformer.encoders)
         active = []
-        for _ in range(n):  # eight_mile draws one numpy random per layer, even with layer_drop == 0
-            pdrop = np.random.random()
+        for i in range(n):  # eight_mile draws one numpy random per layer, even with layer_drop == 0
+            pdrop = np.random.random() if _layer_draws is None else _layer_draws[i]
             active.append((not self.training) or pdrop >= self.layer_drop)
         row_keep = None
         if pad_mask is not None:
@@ -468,19 +527,39 @@ class Wav2Vec2Model(nn.Module):
     def set_num_updates(self, s):
         self.quantizer.set_num_updates(s)
 
+    def request_host_draws(self, sampler):
+        """the loss announces that the next forward() belongs to a training step that will also need negative indices:
+        forward() then makes all of the step's numpy draws on a helper thread (see _HostDraws), started right after
+        the first GPU work of the step has been enqueued, and leaves the handle in `self._host_draws`"""
+        self._host_draw_request = sampler
+
     def forward(self, x):
+        sampler = self.__dict__.pop("_host_draw_request", None)
+        self._host_draws = draws = None
         features, unmasked = self._front_graph.run(self._front, (x,), self._front_params(),
                                                    extra=(self.training, self.dropout_input_p))
+        if sampler is not None:
+            self._host_draws = draws = _HostDraws(x.shape[0], unmasked.shape[1], self.timestep_masking,
+                                                  self.timestep_mask_len, len(self.encoder.transformer.encoders), sampler)
         B, T, C = unmasked.shape
         # masking runs in eval mode too (reference :937 has no training guard)
-        time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
+        layer_draws = None
+        if draws is not None:
+            time_mask, layer_draws = draws.time_mask()
+            assert time_mask.shape == (B, T)
+        else:
+            time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
         rows = _mask_rows(time_mask, x.device)
+        # masked-row tensors are allocated at their worst-case size for this (B, T): see ops.set_dynamic_rows
+        n_spans = int(self.timestep_masking * T / float(self.timestep_mask_len)) + 1
+        Fn.ops.set_dynamic_rows(rows.numel(), B * min(T, n_spans * self.timestep_mask_len))
         features = Fn.RowsSetFn.apply(features, rows, self.mask_emb)
         if self.channel_masking > 0.0:
             raise NotImplementedError("channel masking in pre-training is broken in the reference (wav2vec2.py:943)")
+        # the encoder (the longest stretch of GPU work) is enqueued first; the quantizer branch follows it on the stream
+        enc = self.encoder.extract_features(features, None, layer_draws)
         y = Fn.RowsGatherFn.apply(unmasked, rows).view(B, -1, C)
         y = Fn.dropout(y, self.dropout_features_p, self.training)
-        enc = self.encoder(features)
         q, vq_probs = self.quantizer(y)
         y = self.project_q(q, out_f32=True)
         xo = self.final_proj(enc, out_f32=True)
@@ -499,15 +578,26 @@ class Wav2Vec2Loss(nn.Module):
         self.last_neg_idx = None
 
     def __call__(self, model, features):
-        outputs, latents, gs_probs, time_mask = model(features)
+        inner = getattr(model, "module", model)  # DistributedDataParallel wraps the model (pretrain.py:158)
+        draws = None
+        if isinstance(inner, Wav2Vec2Model):
+            inner.request_host_draws(self.sample)
+        try:
+            outputs, latents, gs_probs, time_mask = model(features)
+        finally:
+            if isinstance(inner, Wav2Vec2Model):
+                inner.__dict__.pop("_host_draw_request", None)  # never leave a stale request behind a failed forward
+                draws = inner.__dict__.pop("_host_draws", None)
         B, Tm, C = latents.shape
         rows = getattr(time_mask, "a8_rows", None)
         if rows is None:
             rows = torch.nonzero(time_mask.reshape(-1)).reshape(-1).int()
         xm = Fn.RowsGatherFn.apply(outputs, rows)  # outputs[time_mask] -> [B*Tm, C]
-        neg = self.sample.indices(B, Tm)  # numpy, bit-exact with the reference's Sampler
+        # numpy draws, bit-exact with the reference's Sampler (already made on the helper thread when `draws`)
+        neg = draws.negatives() if draws is not None else self.sample.indices32(B, Tm)
+        assert neg.shape == (B, self.sample.n_negatives * Tm)
         self.last_neg_idx = neg
-        idx = _to_device(neg.astype(np.int32), outputs.device)
+        idx = _to_device(neg, outputs.device)
         loss, _ = Fn.ContrastiveFn.apply(xm, latents.reshape(B * Tm, C), idx, gs_probs, self.n_vars, XE_WGT,
                                          DIVERSITY_WGT)
         return loss
