@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaudio8_b200.so")
+_TAG = os.environ.get("A8_LIB_TAG", "")  # kernel experiments: load libaudio8_b200_<tag>.so (see build.py)
+LIB_PATH = os.path.join(HERE, "libaudio8_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 MAJOR_K, MAJOR_MN = 0, 1
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
@@ -79,6 +80,8 @@ SIGNATURES.update({
     "a8_cast_multi": (_I, [_P, _I, _P]),
     "a8_conv_pack": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "a8_conv_unpack": (_I, [_P, _I, _I, _I, _P, _P]),
+    "a8_gemm_set_trace": (None, [_P]),
+    "a8_posconv_norm_scratch_floats": (_L, [_I, _I, _I]),
     "a8_posconv_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_posconv_wn_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -13,10 +13,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libaudio8_b200.so")
+# experiments: A8_BUILD_TAG=x A8_NVCC_EXTRA="-DFOO=1" builds libaudio8_b200_x.so beside the default library
+TAG = os.environ.get("A8_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libaudio8_b200" + ("_" + TAG if TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr"]
+         "--expt-relaxed-constexpr"] + os.environ.get("A8_NVCC_EXTRA", "").split()
 
 
 def _stale(target, deps):

@@ -91,6 +91,11 @@ void copy_coef(OpCoef& o, const a8_operand_t& v) {
 using namespace a8;
 using namespace a8::gemm;
 
+static long long* g_trace = nullptr;
+// debug: device buffer of TRACE_CTAS*3*TRACE_TILES*TRACE_EVENTS int64 that the next launches stamp (nullptr = off)
+extern "C" void a8_gemm_set_trace(void* buf) { g_trace = static_cast<long long*>(buf); }
+
+
 extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   A8_REQUIRE(gp != nullptr, "gemm: null descriptor");
   const a8_gemm_t& g = *gp;
@@ -125,6 +130,7 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   kp.c = g.c; kp.c_dtype = g.c_dtype; kp.z_out = g.z_out; kp.aux = g.aux; kp.aux_mode = g.aux_mode;
   kp.bias = g.bias; kp.bias_stride_lo = g.bias_stride_lo; kp.act = g.act; kp.alpha = g.alpha;
   kp.ldc = g.ldc; kp.c_stride_lo = g.c_stride_lo; kp.c_stride_hi = g.c_stride_hi;
+  kp.trace = g_trace;
   const long long tiles = (long long)kp.m_tiles * kp.n_tiles * kp.lo_count * kp.hi_count * split;
   A8_REQUIRE(tiles < (1ll << 30), "gemm: too many tiles");
   kp.total_tiles = (int)tiles;

@@ -50,6 +50,7 @@ struct KParams {
   float alpha;
   long long ldc, c_stride_lo, c_stride_hi;
   int total_tiles;
+  long long* trace;  // debug timeline (a8_gemm_set_trace), normally null
 };
 
 __device__ __forceinline__ void op_coords(const OpCoef& o, int kin, int kbatch, int r, int lo, int hi,
@@ -59,11 +60,29 @@ __device__ __forceinline__ void op_coords(const OpCoef& o, int kin, int kbatch, 
     c[d] = o.base[d] + o.ck[d] * kin + o.cb[d] * kbatch + o.cr[d] * r + o.cl[d] * lo + o.ch[d] * hi;
 }
 
-template <int BN>
+// debug timeline: clock64() stamps of CTAs 0..3, roles {0 producer, 1 MMA issuer, 2 epilogue warp 4}, up to 8 tiles,
+// 4 events each (scripts/gemm_trace.py).  One predicated store per event when the pointer is null-checked.
+constexpr int TRACE_CTAS = 4, TRACE_TILES = 8, TRACE_EVENTS = 4;
+__device__ __forceinline__ void trace_ev(const KParams& p, int role, int iter, int ev) {
+  if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && iter < TRACE_TILES)
+    p.trace[((blockIdx.x * 3 + role) * TRACE_TILES + iter) * TRACE_EVENTS + ev] = clock64();
+}
+
+__device__ __forceinline__ void trace_wall(const KParams& p, int slot) {  // %globaltimer (ns) of CTAs 0..3, thread 0
+  if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[((blockIdx.x * 3 + 0) * TRACE_TILES + (TRACE_TILES - 1)) * TRACE_EVENTS + slot] = (long long)t;
+  }
+}
+
+template <int BN, int CL = 1>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  // CL == 2: a CTA pair works on one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of A and
+  // its own HALF of the B tile (BN/2 rows), so a stage is smaller and the ring deeper.
+  static constexpr int STAGES = (CL == 2) ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8)));
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = (BN / CL) * BLOCK_K * 2;
   static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // powers of two >= 32; 2 accumulator stages
   static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * 32 * 80 + 1024;
 };
@@ -95,6 +114,9 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int
   return t;
 }
 
+#ifndef A8_EPI_DIRECT
+#define A8_EPI_DIRECT 0  // 1: bf16 outputs / aux go straight between registers and global memory (no smem staging)
+#endif
 constexpr int STG_PITCH = 80;                 // bytes per staged row: 64 payload + 16 pad (conflict-free 16B writes)
 constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
 
@@ -145,18 +167,30 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
   uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
   uint4 a[4];
   if (has_aux) {
+#if A8_EPI_DIRECT
+    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row_off0 +
+                                                     (long long)lane * p.ldc + nb);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      a[g] = (lane < rows_valid && nb + 8 * g < cols_valid) ? __ldg(ap + g) : make_uint4(0u, 0u, 0u, 0u);
+#else
     stage_copy<2, STG_LOAD>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
 #pragma unroll
     for (int g = 0; g < 4; ++g) a[g] = my[g];
     __syncwarp();
+#endif
   }
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-  if (sb != nullptr) {
+  if (sb != nullptr) {  // 8 broadcast LDS.128 (a scalar LDS per column costs a full shared-memory wavefront each)
+    const float4* sb4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += sb[i];
+    for (int i = 0; i < 8; ++i) {
+      const float4 b4 = sb4[i];
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+    }
   }
   if (do_z) {
 #pragma unroll
@@ -164,11 +198,17 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
       uint4 z;
       z.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); z.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
       z.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); z.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+#if A8_EPI_DIRECT
+      if (lane < rows_valid && nb + 8 * g < cols_valid)
+        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.z_out) + row_off0 + (long long)lane * p.ldc + nb)[g] = z;
+    }
+#else
       my[g] = z;
     }
     __syncwarp();
     stage_copy<2, STG_STORE>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
+#endif
   }
   if (do_gelu) {
 #pragma unroll
@@ -197,11 +237,17 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
       uint4 o;
       o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
       o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+#if A8_EPI_DIRECT
+      if (lane < rows_valid && nb + 8 * g < cols_valid)
+        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.c) + row_off0 + (long long)lane * p.ldc + nb)[g] = o;
+    }
+#else
       my[g] = o;
     }
     __syncwarp();
     stage_copy<2, STG_STORE>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
+#endif
   } else {  // fp32: plain stores, or vector reductions for split-K partial sums
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -219,11 +265,14 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
   }
 }
 
-// ---- 2-CTA cluster mode: the two CTAs of a cluster own vertically adjacent 128-row tiles of the same n-tile, so they
-// need the SAME B tile: each loads half of it and multicasts that half into both CTAs' shared memory.  L2 -> SM
-// traffic per CTA and k-block drops from (128 + BN) x 128 B to (128 + BN/2) x 128 B, which is what bounds these GEMMs
-// (the measured L2 feed is ~43 B/clk/SM).  A stage may be refilled only when BOTH CTAs have consumed it: the MMA
-// issuer's tcgen05.commit arrives on the stage's empty barrier of both CTAs.
+// ---- 2-CTA mode (CL == 2, cta_group::2): the two CTAs of a cluster (one TPC) compute ONE 256 x BN tile.  CTA r
+// stages A rows [128 r, 128 r + 128) and B rows [r BN/2, (r+1) BN/2) of the tile in its own shared memory; the leader
+// (rank 0) issues tcgen05.mma.cta_group::2 with M = 256, which reads both CTAs' shared memory and writes each CTA's half
+// of the accumulator into that CTA's own TMEM.  Per k-block every SM now reads 16 + 16 KB of operands from shared memory
+// (instead of 16 + 32 KB single-CTA) and receives 32 KB from L2: the shared-memory port stops being the bound.
+// Barriers: both producers' TMA loads complete on the LEADER's full barrier (the leader posts the expected bytes of
+// both); the leader's tcgen05.commit is multicast to the empty / accumulator-full barriers of both CTAs; the peer's
+// epilogue warps arrive remotely on the leader's accumulator-empty barrier.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -233,27 +282,55 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1,
-                                               int c2, int c3, uint16_t mask) {
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are posted on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst, int c0,
+                                                int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
       :
-      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
   asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"(mask)
       : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 template <int MA, int MB, int BN, int CL, int EK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const KParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -273,6 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  trace_wall(p, 0);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -283,16 +361,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (elect_one()) {
       for (int i = 0; i < STAGES; ++i) {
         mbar_init(full_bar(i), 1);
-        mbar_init(empty_bar(i), CL);  // one tcgen05.commit arrival per CTA of the cluster
+        mbar_init(empty_bar(i), 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(tfull_bar(i), 1);
-        mbar_init(tempty_bar(i), 32 * EPI_WARPS);
+        mbar_init(tempty_bar(i), CL * EPI_WARPS);  // lane 0 of every epilogue warp of every CTA of the pair
       }
       mbar_fence_init();
     }
   } else if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (CL == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);  // the same warp of BOTH CTAs issues the paired allocation
   }
   tc_fence_before();
   __syncthreads();
@@ -300,7 +379,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_launch_dependents();  // the next kernel's prologue may start; it waits for this grid before touching memory
+  trace_wall(p, 1);
   pdl_wait();               // everything above overlapped the previous kernel's tail
+  trace_wall(p, 2);
   const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
   const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
 
@@ -309,27 +390,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+      int piter = 0;
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++piter) {
         const TileCoord t = decode_tile<CL>(p, tile, rank);
         const int m0 = t.mt * BLOCK_M, n0 = t.nt * BN;
+        trace_ev(p, 0, piter, 0);
         int kin = t.kb_begin % p.k_inner, kbatch = t.kb_begin / p.k_inner;  // advanced incrementally: no division
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {                     // on the per-k-block issue path
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), C::A_BYTES + C::B_BYTES);
           const uint32_t a_dst = sA + stage * C::A_BYTES;
           const uint32_t b_dst = sB + stage * C::B_BYTES;
           int cc[4];
-          if (MA == MAJOR_K) {
-            op_coords(p.a, kin, kbatch, m0, t.lo, t.hi, cc);
-            tma_load_4d(&map_a, full_bar(stage), a_dst, cc[0], cc[1], cc[2], cc[3]);
-          } else {
-#pragma unroll
-            for (int at = 0; at < BLOCK_M / 64; ++at) {
-              op_coords(p.a, kin, kbatch, m0 / 64 + at, t.lo, t.hi, cc);
-              tma_load_4d(&map_a, full_bar(stage), a_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
-            }
-          }
           if (CL == 1) {
+            mbar_expect_tx(full_bar(stage), C::A_BYTES + C::B_BYTES);
+            if (MA == MAJOR_K) {
+              op_coords(p.a, kin, kbatch, m0, t.lo, t.hi, cc);
+              tma_load_4d(&map_a, full_bar(stage), a_dst, cc[0], cc[1], cc[2], cc[3]);
+            } else {
+#pragma unroll
+              for (int at = 0; at < BLOCK_M / 64; ++at) {
+                op_coords(p.a, kin, kbatch, m0 / 64 + at, t.lo, t.hi, cc);
+                tma_load_4d(&map_a, full_bar(stage), a_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+              }
+            }
             if (MB == MAJOR_K) {
               op_coords(p.b, kin, kbatch, n0, t.lo, t.hi, cc);
               tma_load_4d(&map_b, full_bar(stage), b_dst, cc[0], cc[1], cc[2], cc[3]);
@@ -340,16 +423,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tma_load_4d(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
               }
             }
-          } else {  // this CTA's half of the B tile, multicast into both CTAs (same smem offset, same barrier offset)
-            if (MB == MAJOR_K) {
+          } else {
+            // both CTAs' loads complete on the leader's barrier; the leader posts the byte count of the pair
+            const uint32_t fb = mapa_rank(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (C::A_BYTES + C::B_BYTES));
+            if (MA == MAJOR_K) {
+              op_coords(p.a, kin, kbatch, m0, t.lo, t.hi, cc);
+              tma_load_4d_2sm(&map_a, fb, a_dst, cc[0], cc[1], cc[2], cc[3]);
+            } else {
+#pragma unroll
+              for (int at = 0; at < BLOCK_M / 64; ++at) {
+                op_coords(p.a, kin, kbatch, m0 / 64 + at, t.lo, t.hi, cc);
+                tma_load_4d_2sm(&map_a, fb, a_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
+              }
+            }
+            if (MB == MAJOR_K) {  // this CTA's half of the tile's B rows
               op_coords(p.b, kin, kbatch, n0 + rank * (BN / 2), t.lo, t.hi, cc);
-              tma_load_4d_mc(&map_b, full_bar(stage), b_dst + rank * (C::B_BYTES / 2), cc[0], cc[1], cc[2], cc[3], 3);
+              tma_load_4d_2sm(&map_b, fb, b_dst, cc[0], cc[1], cc[2], cc[3]);
             } else {
 #pragma unroll
               for (int a2 = 0; a2 < BN / 128; ++a2) {
-                const int at = rank * (BN / 128) + a2;
-                op_coords(p.b, kin, kbatch, n0 / 64 + at, t.lo, t.hi, cc);
-                tma_load_4d_mc(&map_b, full_bar(stage), b_dst + at * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3], 3);
+                op_coords(p.b, kin, kbatch, n0 / 64 + rank * (BN / 128) + a2, t.lo, t.hi, cc);
+                tma_load_4d_2sm(&map_b, fb, b_dst + a2 * (BLOCK_K * 128), cc[0], cc[1], cc[2], cc[3]);
               }
             }
           }
@@ -362,14 +457,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             ++kbatch;
           }
         }
+        trace_ev(p, 0, piter, 1);
       }
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (elect_one()) {
+    if (rank == 0 && elect_one()) {  // pair mode: the leader CTA issues for both
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)MA << 15) |
                                  ((uint32_t)MB << 16) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(BLOCK_M >> 4) << 24);
+                                 ((uint32_t)((BLOCK_M * CL) >> 4) << 24);
       // K-major: 8-row groups are 1024 B apart (SBO), one swizzle span along K (LBO unused).
       // MN-major: 64-element MN atoms are BLOCK_K*128 B apart (LBO), 8-row K groups 1024 B (SBO).
       constexpr uint32_t A_LBO = (MA == MAJOR_K) ? 0u : BLOCK_K * 128u;
@@ -383,23 +479,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const TileCoord t = decode_tile<CL>(p, tile, rank);
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1u;
+        trace_ev(p, 1, iter, 0);
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
+        trace_ev(p, 1, iter, 1);
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (kb == t.kb_begin) trace_ev(p, 1, iter, 2);
           const uint32_t a_addr = sA + stage * C::A_BYTES;
           const uint32_t b_addr = sB + stage * C::B_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(a_addr + k * A_KADV, A_LBO, 1024u);
             const uint64_t db = make_smem_desc(b_addr + k * B_KADV, B_LBO, 1024u);
-            umma_bf16(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            if (CL == 1) umma_bf16(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            else umma_bf16_2sm(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(empty_bar(stage));
-          else umma_commit_mc(empty_bar(stage), 3);
-          if (kb == t.kb_end - 1) umma_commit(tfull_bar(as));
+          if (CL == 1) {
+            umma_commit(empty_bar(stage));
+            if (kb == t.kb_end - 1) umma_commit(tfull_bar(as));
+          } else {  // the stage is free / the accumulator is ready in BOTH CTAs
+            umma_commit_2sm(empty_bar(stage), 3);
+            if (kb == t.kb_end - 1) umma_commit_2sm(tfull_bar(as), 3);
+          }
+          if (kb == t.kb_end - 1) trace_ev(p, 1, iter, 3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -428,8 +533,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) sb[i] = (t.nt * BN + i < p.N) ? __ldg(bsrc + i) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
+      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 0);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 1);
       const int row0 = t.mt * BLOCK_M + q * 32;
       const long long row_off0 =
           (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row0 * p.ldc;
@@ -448,16 +555,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         epilogue_chunk<EK>(p, ra, row_off0, row0, nb0 + c * 32, sbw ? sbw + c * 32 : nullptr, stg, lane);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      __syncwarp();
+      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 2);
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(tempty_bar(as));
+        else mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));  // the leader's MMA thread waits for both CTAs
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();  // neither CTA exits while the peer may still write its smem or signal its barriers
+  trace_wall(p, 3);
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CL == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -472,12 +586,12 @@ int launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp,
   auto kern = gemm_tc_kernel<MA, MB, BN, CL, EK>;
   if (!configured) {
     A8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)Cfg<BN>::SMEM_BYTES));
+                                 (int)Cfg<BN, CL>::SMEM_BYTES));
     configured = true;
   }
   const int slots = num_sms() / CL;
   const int grid = CL * (kp.total_tiles < slots ? kp.total_tiles : slots);
-  A8_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN>::SMEM_BYTES, stream, CL, ma, mb, kp));
+  A8_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, CL>::SMEM_BYTES, stream, CL, ma, mb, kp));
   return check_launch("gemm_tc_kernel");
 }
 

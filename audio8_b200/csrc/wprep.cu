@@ -79,17 +79,35 @@ __global__ void __launch_bounds__(256) conv_unpack_kernel(const float* dwk, int 
 }
 
 // ---------------------------------------------------------------------------------------------- pos-conv weight norm
-// norm2[j] = sum_{o,i} v[o,i,j]^2   (v [D,cg,k], k contiguous).  grid (chunks), block 128+: thread = tap
-__global__ void posconv_norm_kernel(const float* v, int rows, int k, int rows_per_block, float* norm2) {
+// norm2[j] = sum_{o,i} v[o,i,j]^2   (v [D,cg,k], k contiguous).  grid (chunks), block 128+: thread = tap.
+// Deterministic (the packed bf16 weights must not change between two calls on the same parameters): every block
+// stores its partial sums, and the block that finishes last adds them in block order.  scratch = [gridDim.x][k]
+// partials followed by one zeroed counter word.
+__global__ void posconv_norm_kernel(const float* v, int rows, int k, int rows_per_block, float* norm2, float* scratch) {
   const int j = threadIdx.x;
-  if (j >= k) return;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float acc = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const float x = v[(long long)r * k + j];
-    acc = fmaf(x, x, acc);
+  __shared__ int s_last;
+  if (j < k) {
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float x = v[(long long)r * k + j];
+      acc = fmaf(x, x, acc);
+    }
+    scratch[(long long)blockIdx.x * k + j] = acc;
   }
-  atomicAdd(norm2 + j, acc);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (long long)gridDim.x * k);
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && j < k) {
+    __threadfence();
+    float tot = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) tot += __ldcg(scratch + (long long)b * k + j);
+    norm2[j] = tot;
+  }
 }
 
 // w = g[j] * v / sqrt(norm2[j]); packed bf16 [D, k*64]: wp row = output channel (g*cg+co), col j*64+ci;
@@ -183,14 +201,21 @@ extern "C" int a8_posconv_pack(const float* g, const float* v, int32_t D, int32_
                                void* wp, void* wpt, void* stream_v) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(k <= 1024 && cg <= 64 && D % cg == 0, "posconv_pack: unsupported shape D=%d cg=%d k=%d", D, cg, k);
-  A8_CUDA(cudaMemsetAsync(norm2, 0, sizeof(float) * k, st));
+  // norm2: k results followed by scratch of a8_posconv_norm_scratch_floats(D, cg, k) floats (partials + counter)
   const int rows = D * cg, rpb = 128;
-  posconv_norm_kernel<<<cdiv(rows, rpb), ((k + 31) / 32) * 32, 0, st>>>(v, rows, k, rpb, norm2);
+  const int nblk = cdiv(rows, rpb);
+  float* scratch = norm2 + k;
+  A8_CUDA(cudaMemsetAsync(scratch + (long long)nblk * k, 0, sizeof(float), st));
+  posconv_norm_kernel<<<nblk, ((k + 31) / 32) * 32, 0, st>>>(v, rows, k, rpb, norm2, scratch);
   int rc = check_launch("posconv_norm_kernel");
   if (rc) return rc;
   posconv_pack_kernel<<<egrid((long long)D * k * 64), 256, 0, st>>>(g, v, norm2, D, cg, k, (__nv_bfloat16*)wp,
                                                                     (__nv_bfloat16*)wpt);
   return check_launch("posconv_pack_kernel");
+}
+
+extern "C" int64_t a8_posconv_norm_scratch_floats(int32_t D, int32_t cg, int32_t k) {
+  return (int64_t)cdiv((long long)D * cg, 128) * k + 1;
 }
 
 extern "C" int a8_posconv_wn_bwd(const float* dwp, const float* g, const float* v, const float* norm2, int32_t D,

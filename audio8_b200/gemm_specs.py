@@ -44,6 +44,16 @@ def _sig(v):
     return v
 
 
+_ALL_CACHES = []
+
+
+def clear_spec_caches():
+    """drop every frozen descriptor (tests and tiling experiments change FORCE between launches of equal shapes)"""
+    for c in _ALL_CACHES:
+        c.clear()
+    _tiling.cache_clear()
+
+
 def cached_spec(builder):
     cache = {}
 
@@ -55,6 +65,8 @@ def cached_spec(builder):
         return BoundSpec(cache, key, builder, args, kwargs)
 
     wrapper.raw = builder
+    wrapper.cache = cache
+    _ALL_CACHES.append(cache)
     return wrapper
 
 

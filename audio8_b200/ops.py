@@ -485,7 +485,8 @@ class CudaBackend:
         """weight-normed pos-conv weight -> (wp, wpt or None, norm2)"""
         D, cg, k = v.shape
         assert g.numel() == k and v.is_contiguous() and g.is_contiguous()
-        norm2 = torch.empty(k, dtype=torch.float32, device=v.device)
+        buf = torch.empty(k + self.lib.a8_posconv_norm_scratch_floats(D, cg, k), dtype=torch.float32, device=v.device)
+        norm2 = buf[:k]  # followed by the ordered-partial-sum scratch of the deterministic reduction
         wp = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device)
         wpt = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device) if want_t else None
         _lib.check(self.lib.a8_posconv_pack(_ptr(g), _ptr(v), D, cg, k, _ptr(norm2), _ptr(wp), _ptr(wpt), _stream()),

@@ -85,6 +85,9 @@ typedef struct {
 } a8_gemm_t;
 
 int a8_gemm(const a8_gemm_t* p, void* stream);
+/* debug aid: later a8_gemm launches stamp clock64() timelines of their first CTAs into `buf` (device memory,
+ * 4*3*8*4 int64); NULL turns it off.  Not used by the product path. */
+void a8_gemm_set_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC loss.  Replaces `torch.nn.functional.ctc_loss` as called at `ctc.py:197-205`
@@ -244,13 +247,16 @@ int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32
  * a8_conv_pack: Conv1d weight [Cout,Cin,k] (`wav2vec2.py:426`) -> wk [Cout,k*Cin] and, per stride phase p < 2,
  *   wt_p [Cin, ntaps_p*Cout] for the data-gradient GEMMs (wt0/wt1 may be NULL).  a8_conv_unpack: the inverse for dwk.
  * a8_posconv_pack: weight_norm(dim=2) (`wav2vec2.py:609`): w = g[j]*v/||v[:,:,j]|| -> packed bf16 [D,k*64] (rows =
- *   output channels) and its per-group transpose (rows = input channels); norm2[k] is kept for backward.
+ *   output channels) and its per-group transpose (rows = input channels); norm2[k] is kept for backward and must be
+ *   followed by a8_posconv_norm_scratch_floats(D, cg, k) floats of scratch (ordered partial sums: the result is
+ *   bit-reproducible, no atomics).
  * a8_posconv_wn_bwd: from the GEMM's dwp fp32 [groups,k*64,64] to dv [D,cg,k], dg [k]; t_scratch: k floats.
  * ---------------------------------------------------------------------------------------------- */
 int a8_cast_multi(const void* table, int32_t n_entries, void* stream);
 int a8_conv_pack(const float* w, int32_t Cout, int32_t Cin, int32_t k, int32_t s, void* wk, void* wt0, void* wt1,
                  void* stream);
 int a8_conv_unpack(const float* dwk, int32_t Cout, int32_t Cin, int32_t k, float* dw, void* stream);
+int64_t a8_posconv_norm_scratch_floats(int32_t D, int32_t cg, int32_t k);
 int a8_posconv_pack(const float* g, const float* v, int32_t D, int32_t cg, int32_t k, float* norm2, void* wp,
                     void* wpt, void* stream);
 int a8_posconv_wn_bwd(const float* dwp, const float* g, const float* v, const float* norm2, int32_t D, int32_t cg,

@@ -11,7 +11,7 @@ HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 def _declared():
     h = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     out = {}
-    for name, args in re.findall(r"\b(?:int|size_t|int64_t|const char\*)\s+(a8_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+    for name, args in re.findall(r"\b(?:int|void|size_t|int64_t|const char\*)\s+(a8_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
         out[name] = 0 if args.strip() == "void" else len(args.split(","))
     return out
 

@@ -16,3 +16,52 @@ def test_spec_semantics_cpu(name, emu_backend):
 def test_tcgen05_gemm(name):
     from audio8_b200 import ops
     gemm_cases.run_case(name, "cuda", ops.backend())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("name", ["linear_fwd", "linear_dgrad", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad"])
+def test_tcgen05_gemm_cta_pair(name, bn):
+    """the same cases with the 2-CTA (cta_group::2, 256 x BN pair tile) variant forced for every launch that allows it"""
+    from audio8_b200 import gemm_specs as G
+    from audio8_b200 import ops
+    G.clear_spec_caches()
+    G.FORCE.update(bn=bn, cluster=2, split=1)
+    try:
+        gemm_cases.run_case(name, "cuda", ops.backend())
+    finally:
+        G.FORCE.clear()
+        G.clear_spec_caches()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(4494, 2304, 768), (4494, 768, 3072), (1153, 640, 512), (257, 256, 64)])
+@pytest.mark.parametrize("cluster", [1, 2])
+def test_tcgen05_linear_large(M, N, K, cluster):
+    """transformer-sized linears (odd number of 128-row tiles: the pair's second CTA runs past M) vs fp32 matmul"""
+    from audio8_b200 import gemm_specs as G
+    from audio8_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=g)).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    dy = (torch.randn(M, N, generator=g)).to(torch.bfloat16).cuda()
+    G.clear_spec_caches()
+    G.FORCE.update(cluster=cluster)
+    try:
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+        ops.backend().gemm(G.linear_fwd.raw(x, w, out, b))
+        dx = torch.zeros(M, K, dtype=torch.bfloat16, device="cuda")
+        ops.backend().gemm(G.linear_dgrad.raw(dy, w, dx))
+        dw = torch.zeros(N, K, dtype=torch.float32, device="cuda")
+        ops.backend().gemm(G.linear_wgrad.raw(dy, x, dw))
+        torch.cuda.synchronize()
+    finally:
+        G.FORCE.clear()
+        G.clear_spec_caches()
+    ref = x.float() @ w.float().t() + b
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    ref = dy.float() @ w.float()
+    assert (dx.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    ref = dy.float().t() @ x.float()
+    assert (dw - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
