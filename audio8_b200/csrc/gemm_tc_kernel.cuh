@@ -80,7 +80,7 @@ template <int BN, int CL = 1>
 struct Cfg {
   // CL == 2: a CTA pair works on one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of A and
   // its own HALF of the B tile (BN/2 rows), so a stage is smaller and the ring deeper.
-  static constexpr int STAGES = (CL == 2) ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8)));
+  static constexpr int STAGES = (CL == 2) ? (BN == 256 ? 6 : (BN == 192 ? 7 : 8)) : ((BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8)));
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = (BN / CL) * BLOCK_K * 2;
   static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // powers of two >= 32; 2 accumulator stages
@@ -602,8 +602,11 @@ int launch_bn(int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, cons
     switch (bn) {
       case 128: return launch_inst<MA, MB, 128, 2, EK>(ma, mb, kp, stream);
       case 256: return launch_inst<MA, MB, 256, 2, EK>(ma, mb, kp, stream);
+      case 192:  // each CTA stages 96 B rows: only expressible for a K-major B (MN-major atoms are 64 wide)
+        if constexpr (MB == MAJOR_K) return launch_inst<MA, MB, 192, 2, EK>(ma, mb, kp, stream);
+        break;
     }
-    set_error("gemm: cluster mode needs block_n 128 or 256 (got %d)", bn);
+    set_error("gemm: pair mode needs block_n 128 or 256 (or 192 with a K-major B), got %d", bn);
     return -1;
   }
   switch (bn) {

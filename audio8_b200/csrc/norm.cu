@@ -101,7 +101,19 @@ struct LnFwdArgs {
   const unsigned long long* seed_src;
 };
 
-template <int NCH>  // chunks of 8 elements per lane: C <= NCH*256
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); v[0] = t.x; v[1] = t.y;
+  t = unpack_bf16(u.y); v[2] = t.x; v[3] = t.y;
+  t = unpack_bf16(u.z); v[4] = t.x; v[5] = t.y;
+  t = unpack_bf16(u.w); v[6] = t.x; v[7] = t.y;
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// NCH chunks of 8 elements per lane (C <= NCH*256); FULL: C == NCH*256, no column guards; HAS_H: residual input.
+// Every global load of a row is issued before the first dependent instruction (the earlier version interleaved one
+// load, its Philox mask and its arithmetic per chunk behind branches: nine serial memory round trips per row).
+template <int NCH, bool FULL, bool HAS_H>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();
@@ -109,36 +121,51 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int C = a.C;
+  const float invC = 1.f / (float)C;
+  float g[NCH][8], bt[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    const bool ok = FULL || c < C;
+    const int cc = ok ? c : 0;
+    load8f(a.gamma + cc, g[i]);
+    load8f(a.beta + cc, bt[i]);
+  }
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.R; row += warps) {
-    float v[NCH][8];
-    float sum = 0.f;
     const long long ro = (long long)row * C;
+    uint4 xr[NCH], hr[NCH];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
-      if (c < C) {
-        load8(a.x + ro + c, v[i]);
-        if (a.h != nullptr) {
-          float hv[8];
-          load8(a.h + ro + c, hv);
-          const DropMask8 d = drop_mask8(a.p_h, a.seed_h + sbase, (unsigned long long)(ro + c) >> 3);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] += hv[j] * d.m[j];
-          // statistics are taken on the bf16-rounded sum, the value backward re-reads
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16(v[i][j]));
-          if (a.s_out != nullptr) store8(a.s_out + ro + c, v[i]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[i][j];
-      }
+      const bool ok = FULL || c < C;
+      xr[i] = ok ? ldg128(a.x + ro + c) : make_uint4(0u, 0u, 0u, 0u);
+      if (HAS_H) hr[i] = ok ? ldg128(a.h + ro + c) : make_uint4(0u, 0u, 0u, 0u);
     }
-    const float mu = warp_sum(sum) / (float)C;
+    float v[NCH][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      const bool ok = FULL || c < C;
+      unpack8(xr[i], v[i]);
+      if (HAS_H) {
+        float hv[8];
+        unpack8(hr[i], hv);
+        const DropMask8 d = drop_mask8(a.p_h, a.seed_h + sbase, (unsigned long long)(ro + c) >> 3);
+        // statistics are taken on the bf16-rounded sum, the value backward re-reads
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16(v[i][j] + hv[j] * d.m[j]));
+        if (ok && a.s_out != nullptr) store8(a.s_out + ro + c, v[i]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];  // guarded-off chunks hold zeros
+    }
+    const float mu = warp_sum(sum) * invC;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
-      if (c < C) {
+      if (FULL || c < C) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = v[i][j] - mu;
@@ -146,7 +173,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
         }
       }
     }
-    const float rs = rsqrtf(warp_sum(sq) / (float)C + a.eps);
+    const float rs = rsqrtf(warp_sum(sq) * invC + a.eps);
     if (lane == 0) {
       a.mean[row] = mu;
       a.rstd[row] = rs;
@@ -154,13 +181,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
-      if (c < C) {
-        float g[8], b[8], o[8];
-        load8f(a.gamma + c, g);
-        load8f(a.beta + c, b);
+      if (FULL || c < C) {
+        float o[8];
         const DropMask8 d = drop_mask8(a.p_y, a.seed_y + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = ((v[i][j] - mu) * rs * g[j] + b[j]) * d.m[j];
+        for (int j = 0; j < 8; ++j) o[j] = ((v[i][j] - mu) * rs * g[i][j] + bt[i][j]) * d.m[j];
         store8(a.y + ro + c, o);
         if (a.y_f32 != nullptr) store8f(a.y_f32 + ro + c, o);
       }
@@ -192,62 +217,84 @@ struct LnBwdArgs {
   const unsigned long long* seed_src;
 };
 
-template <int NCH>
+// One warp per row, two rows in flight per warp (the next row's dy / s tiles are loaded before the current row's
+// arithmetic starts); column partials (dgamma, dbeta, dbias) are reduced across the CTA's warps in shared memory and
+// leave as 16-byte vector reductions (one red.v4 per 4 columns per CTA).
+template <int NCH, bool FULL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   const unsigned long long sbase = seed_base(a.seed_src);
-  __shared__ float red[8][NCH * 256 + 8];
+  __shared__ __align__(16) float red[8][NCH * 256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int C = a.C;
-  float acc_g[NCH][8], acc_b[NCH][8], acc_h[NCH][8];
+  const float invC = 1.f / (float)C;
+  float acc_g[NCH][8], acc_b[NCH][8], acc_h[NCH][8], gm[NCH][8];
 #pragma unroll
-  for (int i = 0; i < NCH; ++i)
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    load8f(a.gamma + ((FULL || c < C) ? c : 0), gm[i]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = acc_h[i][j] = 0.f;
-
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.R; row += warps) {
+  }
+  const bool has_f32 = a.dy_f32 != nullptr;
+  uint4 dyr[NCH], sr[NCH];
+  float mu = 0.f, rs = 0.f;
+  auto load_row = [&](int row) {
     const long long ro = (long long)row * C;
-    const float mu = a.mean[row], rs = a.rstd[row];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      const bool ok = FULL || c < C;
+      dyr[i] = ok ? ldg128(a.dy + ro + c) : make_uint4(0u, 0u, 0u, 0u);
+      sr[i] = ok ? ldg128(a.s + ro + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    mu = __ldg(a.mean + row);
+    rs = __ldg(a.rstd + row);
+  };
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row < a.R) load_row(row);
+  for (; row < a.R; row += warps) {
+    const long long ro = (long long)row * C;
     float g[NCH][8], xh[NCH][8];
     float s1 = 0.f, s2 = 0.f;
+    const float mu_c = mu, rs_c = rs;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
-      if (c < C) {
-        float dy[8], sv[8], gm[8];
-        load8(a.dy + ro + c, dy);
-        if (a.dy_f32 != nullptr) {
-          float e[8];
-          load8f(a.dy_f32 + ro + c, e);
+      const bool ok = FULL || c < C;
+      float dy[8], sv[8];
+      unpack8(dyr[i], dy);
+      unpack8(sr[i], sv);
+      if (has_f32 && ok) {
+        float e[8];
+        load8f(a.dy_f32 + ro + c, e);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dy[j] += e[j];
-        }
-        load8(a.s + ro + c, sv);
-        load8f(a.gamma + c, gm);
-        const DropMask8 d = drop_mask8(a.p_y, a.seed_y + sbase, (unsigned long long)(ro + c) >> 3);
+        for (int j = 0; j < 8; ++j) dy[j] += e[j];
+      }
+      const DropMask8 d = drop_mask8(a.p_y, a.seed_y + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = dy[j] * d.m[j];
-          xh[i][j] = (sv[j] - mu) * rs;
-          acc_g[i][j] += gg * xh[i][j];
-          acc_b[i][j] += gg;
-          g[i][j] = gg * gm[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float gg = ok ? dy[j] * d.m[j] : 0.f;
+        xh[i][j] = ok ? (sv[j] - mu_c) * rs_c : 0.f;
+        acc_g[i][j] += gg * xh[i][j];
+        acc_b[i][j] += gg;
+        g[i][j] = gg * gm[i][j];
+        s1 += g[i][j];
+        s2 += g[i][j] * xh[i][j];
       }
     }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
+    if (row + warps < a.R) load_row(row + warps);  // next row's tiles are in flight during this row's reductions
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
-      if (c < C) {
+      if (FULL || c < C) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) o[j] = rs_c * (g[i][j] - s1 - xh[i][j] * s2);
         store8(a.ds + ro + c, o);
         if (a.dh != nullptr) {
           const DropMask8 d = drop_mask8(a.p_h, a.seed_h + sbase, (unsigned long long)(ro + c) >> 3);
@@ -264,7 +311,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       }
     }
   }
-  // block reduction of the column partials, then one atomic per column per CTA
+  // block reduction of the column partials, then one 16-byte vector reduction per 4 columns per CTA
   for (int pass = 0; pass < 3; ++pass) {
     float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dbias_h);
     if (dst == nullptr) continue;
@@ -272,16 +319,19 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        red[w][c + j] = pass == 0 ? acc_g[i][j] : (pass == 1 ? acc_b[i][j] : acc_h[i][j]);
+      float* rp = &red[w][c];
+      if (pass == 0) { store8f(rp, acc_g[i]); } else if (pass == 1) { store8f(rp, acc_b[i]); } else { store8f(rp, acc_h[i]); }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float t = 0.f;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t += red[k][c];
-      atomicAdd(dst + c, t);
+      for (int k = 0; k < 8; ++k) {
+        const float4 u = *reinterpret_cast<const float4*>(&red[k][c]);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+                   : "memory");
     }
   }
 }
@@ -549,12 +599,23 @@ extern "C" int a8_layernorm_fwd(const void* x, const void* h, float p_h, uint64_
               eps, (__nv_bfloat16*)y, y_f32, p_y, seed_y, mean, rstd, R, C, seed_source()};
   const int nch = cdiv(C, 256);
   const int grid = row_grid(R);
+  const bool full = (C == nch * 256);
+#define A8_LN_FWD(N, F, HH) A8_CUDA(launch_pdl(ln_fwd_kernel<N, F, HH>, dim3(grid), dim3(256), 0, stream, 1, a))
+#define A8_LN_FWD_N(N)                                   \
+  do {                                                   \
+    if (full && h != nullptr) A8_LN_FWD(N, true, true);  \
+    else if (full) A8_LN_FWD(N, true, false);            \
+    else if (h != nullptr) A8_LN_FWD(N, false, true);    \
+    else A8_LN_FWD(N, false, false);                     \
+  } while (0)
   switch (nch) {
-    case 1: A8_CUDA(launch_pdl(ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
-    case 2: A8_CUDA(launch_pdl(ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
-    case 3: A8_CUDA(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
-    default: A8_CUDA(launch_pdl(ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    case 1: A8_LN_FWD_N(1); break;
+    case 2: A8_LN_FWD_N(2); break;
+    case 3: A8_LN_FWD_N(3); break;
+    default: A8_LN_FWD_N(4); break;
   }
+#undef A8_LN_FWD_N
+#undef A8_LN_FWD
   return check_launch("ln_fwd_kernel");
 }
 
@@ -566,15 +627,26 @@ extern "C" int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, 
   A8_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && C <= 1024, "layernorm_bwd: unsupported shape R=%d C=%d", R, C);
   LnBwdArgs a{(const __nv_bfloat16*)dy, dy_f32, p_y, seed_y, (const __nv_bfloat16*)s, mean, rstd, gamma,
               (__nv_bfloat16*)ds, (__nv_bfloat16*)dh, p_h, seed_h, dgamma, dbeta, dbias_h, R, C, seed_source()};
+  A8_REQUIRE(C % 4 == 0 && (reinterpret_cast<uintptr_t>(dgamma) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dbeta) & 15u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(dbias_h) & 15u) == 0,
+             "layernorm_bwd: accumulators must be 16-byte aligned (vector reductions)");
   const int nch = cdiv(C, 256);
-  int grid = cdiv(R, 8 * 4);  // >= 4 rows per warp so the column partials amortise their atomics
-  grid = grid < 1 ? 1 : (grid > 148 * 2 ? 148 * 2 : grid);
+  int grid = cdiv(R, 8 * 2);  // two rows per warp: the column partials amortise their reductions
+  const int cap = 148 * (nch >= 3 ? 1 : 2);  // the 3- and 4-chunk variants hold ~250 registers: one CTA per SM
+  grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+  const bool full = (C == nch * 256);
+#define A8_LN_BWD(N)                                                                                        \
+  do {                                                                                                      \
+    if (full) A8_CUDA(launch_pdl(ln_bwd_kernel<N, true>, dim3(grid), dim3(256), 0, stream, 1, a));          \
+    else A8_CUDA(launch_pdl(ln_bwd_kernel<N, false>, dim3(grid), dim3(256), 0, stream, 1, a));              \
+  } while (0)
   switch (nch) {
-    case 1: A8_CUDA(launch_pdl(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
-    case 2: A8_CUDA(launch_pdl(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
-    case 3: A8_CUDA(launch_pdl(ln_bwd_kernel<3>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
-    default: A8_CUDA(launch_pdl(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, stream, 1, a)); break;
+    case 1: A8_LN_BWD(1); break;
+    case 2: A8_LN_BWD(2); break;
+    case 3: A8_LN_BWD(3); break;
+    default: A8_LN_BWD(4); break;
   }
+#undef A8_LN_BWD
   return check_launch("ln_bwd_kernel");
 }
 

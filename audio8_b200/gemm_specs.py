@@ -91,7 +91,8 @@ FORCE = {}  # experiments (scripts/gemm_bench.py): {"bn": .., "split": .., "clus
 
 
 @functools.lru_cache(maxsize=None)
-def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(128, 192, 256), allow_cluster=True):
+def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(128, 192, 256), allow_cluster=True,
+            b_k_major=False, prefer192=False):
     """(block_n, split_k, cluster) minimising a small cost model of the persistent kernel: CTAs take
     ceil(tiles / SMs) tiles each; a k-block costs max(tensor time, L2 feed time of its operand bytes); a tile costs
     max(main loop, epilogue) because the two overlap through the TMEM accumulator ring.  cluster = 2: CTA pairs on
@@ -101,7 +102,8 @@ def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(
     for bn in candidates:
         if bn > 64 and N <= bn // 2 and bn != candidates[0]:
             continue
-        for cl in ((1, 2) if (allow_cluster and bn in (128, 256) and m_tiles >= 2) else (1,)):
+        pair_ok = bn in (128, 256) or (bn == 192 and b_k_major)  # a pair stages BN/2 B rows per CTA (64-wide MN atoms)
+        for cl in ((1, 2) if (allow_cluster and pair_ok and m_tiles >= 2) else (1,)):
             tiles = cdiv(m_tiles, cl) * cdiv(N, bn) * batch  # tile pairs when cl == 2
             slots = NUM_SMS // cl
             kb_clk = max(_MMA_CLK[bn], (128 + bn // cl) * 128 / _L2_BYTES_PER_CLK)
@@ -117,9 +119,14 @@ def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(
                 if best is None or cost < best[0]:
                     best = (cost, bn, sp, cl)
     bn, sp, cl = best[1], best[2], best[3]
+    if prefer192 and N % 192 == 0 and N >= 384 and 192 in candidates and not allow_split:
+        # measured on the transformer linears (scripts/gemm_bench.py sweep, r01): with only 12-48 k-blocks per tile the
+        # launch is dominated by wave quantisation and the exposed last epilogue, and 192-wide tiles (144 or 216 or
+        # 432 tiles for N = 768 / 2304) beat what the model above picks; pairs only where B is K-major
+        bn, sp, cl = 192, 1, (2 if (b_k_major and allow_cluster and m_tiles >= 2) else 1)
     if FORCE:
         bn = FORCE.get("bn", bn)
-        cl = FORCE.get("cluster", cl) if bn in (128, 256) and m_tiles >= 2 else 1
+        cl = FORCE.get("cluster", cl) if (bn in (128, 256) or (bn == 192 and b_k_major)) and m_tiles >= 2 else 1
         sp = FORCE.get("split", sp) if allow_split else 1
     return bn, sp, cl
 
@@ -139,7 +146,7 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
     a = Op(x, (K, M), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     epi = "gelu" if act == ACT_GELU else ("f32" if c_dtype == OUT_F32 else "bf16")
-    bn, _, cl = _tiling(M, N, cdiv(K, 64), epi=epi) if N > 128 else (0, 1, 1)
+    bn, _, cl = _tiling(M, N, cdiv(K, 64), epi=epi, b_k_major=True, prefer192=act != ACT_GELU) if N > 128 else (0, 1, 1)
     return _with_flops(GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
                                 aux_mode=aux_mode, bias=bias, block_n=bn, cluster=cl), 2 * M * N * K)
 
@@ -152,7 +159,7 @@ def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     epi = "gelu" if aux_mode == AUX_MUL_GELU_GRAD else ("f32" if c_dtype == OUT_F32 else "bf16")
-    bn, _, cl = _tiling(M, K, cdiv(N, 64), epi=epi) if K > 128 else (0, 1, 1)
+    bn, _, cl = _tiling(M, K, cdiv(N, 64), epi=epi, prefer192=True) if K > 128 else (0, 1, 1)
     return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode, block_n=bn,
                                 cluster=cl), 2 * M * N * K)
 
