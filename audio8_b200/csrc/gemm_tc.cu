@@ -1,6 +1,7 @@
 // audio8_b200 — host side of the tcgen05 GEMM (tensor maps, tiling, dispatch).  The kernel lives in
 // gemm_tc_kernel.cuh and is instantiated in gemm_tc_inst_{kk,kmn,mnmn}.cu.
 #include "gemm_tc_kernel.cuh"
+#include <stdlib.h>
 
 namespace a8 {
 namespace gemm {
@@ -73,6 +74,13 @@ int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    // A8_GEMM_SMS=<k>: persistent GEMM grids use k SMs (an even number for CTA pairs).  Data-parallel runs leave a few
+    // SMs to the concurrent NCCL all-reduce: a persistent CTA that cannot be scheduled because a collective holds its
+    // SM would otherwise start late and stretch the whole launch (tiles are assigned statically).
+    if (const char* e = getenv("A8_GEMM_SMS")) {
+      const int k = atoi(e);
+      if (k >= 2 && k <= n) n = k & ~1;
+    }
   }
   return n;
 }

@@ -244,6 +244,9 @@ class ConvFeatureFn(torch.autograd.Function):
             wts.append(wt)
             a = y
         if need_grad:
+            # never keep a RETURNED tensor object in ctx: its grad_fn is this node, and the reference cycle would hold
+            # every saved activation until Python's cyclic GC runs (a detached alias shares the storage, not the cycle)
+            acts[-1] = a.detach()
             ctx.saved = (x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec)
         return a
 
@@ -479,7 +482,8 @@ class QuantizerFn(torch.autograd.Function):
         be.gemm(G.linear_fwd(be.split3(y2, False), be.split3(w32, True), z, b.detach(), c_dtype=OUT_F32))
         v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
         q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_)
-        ctx.saved = (y2, w32, v2, z, noise, kidx, avg, ppl, G_, float(tau), y.shape, vars_.shape)
+        # outputs are kept as detached aliases (no ctx <-> output reference cycle)
+        ctx.saved = (y2, w32, v2, z, noise, kidx.detach(), avg, ppl.detach(), G_, float(tau), y.shape, vars_.shape)
         ctx.mark_non_differentiable(kidx)
         return q.view(Bq, Tm, -1), ppl, kidx
 
@@ -540,7 +544,7 @@ class LogSoftmaxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         y = _be().log_softmax_fwd(x.detach().contiguous().float())
-        ctx.saved = y
+        ctx.saved = y.detach()  # alias, not the returned object (no reference cycle through grad_fn)
         return y
 
     @staticmethod

@@ -67,11 +67,13 @@ class _PinnedRing:
 
     def __init__(self, nbytes=8 << 20):
         self.buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        self.off = 0
+        self.np = self.buf.numpy()  # staging copies go through numpy: a torch CPU copy_ of this size wakes the OpenMP
+        self.off = 0                # pool, whose workers then spin for their block time and preempt the enqueuing threads
         self.inflight = []  # (start, end, event)
 
-    def upload(self, src, device):
-        n = src.numel() * src.element_size()
+    def upload(self, arr, device):
+        """arr: contiguous numpy array -> device tensor of the same dtype/shape (asynchronous copy)"""
+        n = arr.nbytes
         if n > self.buf.numel():
             self.__init__(2 * n)
         start = (self.off + 255) & ~255
@@ -85,8 +87,8 @@ class _PinnedRing:
             elif not ev.query():
                 keep.append((a, b, ev))
         self.inflight = keep
-        stage = self.buf[start:end].view(src.dtype).view(src.shape)
-        stage.copy_(src)
+        np.copyto(self.np[start:end].view(arr.dtype).reshape(arr.shape), arr)
+        stage = self.buf[start:end].view(_NP2TORCH[arr.dtype.type]).view(arr.shape)
         out = stage.to(device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -95,20 +97,22 @@ class _PinnedRing:
         return out
 
 
+_NP2TORCH = {np.int32: torch.int32, np.int64: torch.int64, np.uint8: torch.uint8, np.bool_: torch.bool,
+             np.float32: torch.float32}
 _RING = {}
 
 
 def _to_device(arr, device):
     """numpy -> device, asynchronously (through the pinned ring)"""
-    src = torch.from_numpy(np.ascontiguousarray(arr))
+    arr = np.ascontiguousarray(arr)
     device = torch.device(device)
-    if device.type != "cuda" or src.numel() == 0:
-        return src.to(device)
+    if device.type != "cuda" or arr.size == 0 or arr.dtype.type not in _NP2TORCH:
+        return torch.from_numpy(arr).to(device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ring = _RING.get(key)
     if ring is None:
         ring = _RING[key] = _PinnedRing()
-    return ring.upload(src, device)
+    return ring.upload(arr, device)
 
 
 def _mask_rows(mask_np, device):
@@ -152,6 +156,9 @@ class Sampler:
         return negs.view(B, T, self.n_negatives, C).permute(2, 0, 1, 3), idx
 
 
+_DRAW_THREAD = __import__("os").environ.get("A8_HOST_DRAWS_THREAD", "1") != "0"
+
+
 class _HostDraws:
     """All numpy-RNG draws of one pre-training step, made on a helper thread in the reference's order — span mask
     (wav2vec2.py:189-216), one draw per transformer layer (eight_mile's LayerDrop test), negative indices
@@ -165,8 +172,11 @@ class _HostDraws:
         self.args = (B, T, p_start, mask_length, n_layers, sampler)
         self.mask = self.layer_draws = self.neg = self.error = None
         self.ev_mask, self.ev_neg = threading.Event(), threading.Event()
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        if _DRAW_THREAD:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        else:  # A8_HOST_DRAWS_THREAD=0: same draws, made inline by the calling thread
+            self._run()
 
     def _run(self):
         B, T, p_start, mask_length, n_layers, sampler = self.args

@@ -43,54 +43,21 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML from a helper thread (a
-    `nvidia-smi -lms` child takes driver-wide locks on every poll and stalled kernel launches by tens of ms on these
-    boxes); `nvidia-smi` is only the fallback when pynvml is unusable.  Only samples inside [mark_begin, mark_end]
-    are reported."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, without perturbing it: NVML queries (in-process
+    or through nvidia-smi) take driver-wide locks and were measured to stall concurrent kernel launches by 40-130 ms on
+    these boxes, which drained the GPU in the middle of the timed loop.  The samples are therefore taken by the main
+    thread right after the LAST step of the region has been enqueued, while the GPU is still executing the queued steps
+    (the host runs several steps ahead of the device), i.e. under the region's load but with no launch in flight."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.samples = []  # (t, sm_mhz, max_mhz, set(reasons))
-        self.stop_flag = False
-        self.thread = None
-        self.t0 = self.t1 = 0.0
+        self.samples = []  # (sm_mhz, max_mhz, set(reasons))
         self.how = None
-
-    def _nvml_loop(self, period):
-        import pynvml as N
-        h = N.nvmlDeviceGetHandleByIndex(self.index)
-        mx = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
-        names = [("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap)]
-        while not self.stop_flag:
-            try:
-                sm = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
-                bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
-                self.samples.append((time.perf_counter(), sm, mx, {n for n, b in names if bits & b}))
-            except Exception:
-                pass
-            time.sleep(period)
-
-    def _smi_loop(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                self.samples.append((time.perf_counter(), float(f[0]), float(f[1]),
-                                     {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
-            except ValueError:
-                continue
+        self.h = None
 
     def start(self):
         if os.environ.get("A8_NO_CLOCKS"):
             return
-        period = float(os.environ.get("A8_CLOCK_MS", "25")) / 1e3
         try:
             import pynvml as N
             N.nvmlInit()
@@ -101,43 +68,55 @@ class ClockSampler:
                     idx = int(vis.split(",")[self.index])
                 except ValueError:
                     pass
-            self.index = idx
+            self.N, self.h = N, N.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
             self.how = "nvml"
-            self.thread = threading.Thread(target=self._nvml_loop, args=(period,), daemon=True)
-            self.thread.start()
-            return
         except Exception:
-            pass
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.how = "nvidia-smi"
-            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
 
-    def mark_begin(self):
-        self.t0 = time.perf_counter()
+    def sample(self):
+        if self.how == "nvml":
+            N = self.N
+            names = [("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap)]
+            try:
+                sm = float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((sm, self.mx, {n for n, b in names if bits & b}))
+            except Exception:
+                pass
+        elif self.how == "nvidia-smi":
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                f = [x.strip() for x in out.split(",")]
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                self.samples.append((float(f[0]), float(f[1]), {n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")}))
+            except Exception:
+                pass
 
-    def mark_end(self):
-        self.t1 = time.perf_counter()
+    def sample_while_busy(self, done_event, max_samples=4):
+        """a few samples while the stream is still working through the queued steps"""
+        n = 0
+        while n < max_samples and not done_event.query():
+            self.sample()
+            n += 1
+            time.sleep(0.002)
+        self.in_region = n
 
     def stop(self):
-        self.stop_flag = True
-        if self.proc is not None:
-            self.proc.terminate()
         if self.how is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
-        inside = [x for x in self.samples if self.t0 <= x[0] <= self.t1]
-        use = inside if inside else self.samples[-3:]
         reasons = set()
-        for x in use:
-            reasons |= x[3]
-        sm = [x[1] for x in use]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": use[0][2] if use else None,
-                "samples": len(inside), "reasons": sorted(reasons), "source": self.how}
+        for x in self.samples:
+            reasons |= x[2]
+        sm = [x[0] for x in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.samples[0][1] if self.samples else None,
+                "samples": len(self.samples), "samples_while_gpu_busy": getattr(self, "in_region", 0),
+                "reasons": sorted(reasons), "source": self.how,
+                "when": "after the last timed step was enqueued, while the GPU was still executing the timed region"}
 
 
 class GemmProfiler:
@@ -243,7 +222,12 @@ def run_ours(args):
     loss_fn = W.create_loss(N_VARS, N_NEG)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local)
+        # stock DistributedDataParallel as in pretrain.py:158; gradients as views of few large buckets (no per-parameter
+        # copy kernels, a handful of NCCL launches per step instead of ~16)
+        net = torch.nn.parallel.DistributedDataParallel(
+            model, device_ids=[local], output_device=local,
+            gradient_as_bucket_view=os.environ.get("A8_DDP_BUCKET_VIEW", "1") != "0",
+            bucket_cap_mb=int(os.environ.get("A8_DDP_BUCKET_MB", "128")))
     B = B_PER_GPU
     lib = _lib.load()
     x_dev = torch.randn(B, L, device=dev) * 0.1
@@ -267,7 +251,6 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-        time.sleep(0.1)
     for _ in range(2):
         step(x_dev)
     # Python's cyclic GC: a full (generation-2) collection walks every live object of the process (~100 ms with torch
@@ -275,8 +258,7 @@ def run_ours(args):
     # freeze what exists after warm-up and collect by hand between the timed regions, not inside them.
     import gc
     gc.collect()
-    gc.freeze()
-    gc.disable()
+    gc.freeze()  # the young generations stay enabled: they are cheap and reclaim whatever cycles a step leaves behind
     if args.ncu_step:
         # `ncu --profile-from-start off ... bench.py --ncu-step`: exactly ONE warmed-up step inside the profiler range
         # (numbers printed by a run under ncu are never bench values: nothing is printed)
@@ -293,21 +275,29 @@ def run_ours(args):
         return
     # ---- device-resident timing: exactly K steps between barriers, CUDA events, max over ranks
     barrier()
-    clocks.mark_begin()
     n0 = lib.a8_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    host_t = []
+    host_t, step_ev = [], []
     e0.record()
     for _ in range(args.steps):
         th = time.perf_counter()
         step(x_dev)
         host_t.append((time.perf_counter() - th) * 1e3)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        step_ev.append(ev)
     e1.record()
+    if rank == 0:
+        clocks.sample_while_busy(e1)
     barrier()
-    clocks.mark_end()
     launches = lib.a8_launch_count() - n0
     if rank == 0:
         sys.stderr.write("host enqueue ms per step: " + " ".join(f"{t:.1f}" for t in host_t) + "\n")
+        prev, gpu_t = e0, []
+        for ev in step_ev:
+            gpu_t.append(prev.elapsed_time(ev))
+            prev = ev
+        sys.stderr.write("gpu ms per step (event to event): " + " ".join(f"{t:.1f}" for t in gpu_t) + "\n")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -318,10 +308,19 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host input -> device every step, loss read back every step
     gc.collect()
     barrier()
+    for _ in range(3):  # this loop's own warm-up: the per-step input tensor changes the allocator's request sequence
+        step(x_host.to(dev, non_blocking=True)).item()
+    gc.collect()
+    barrier()
     t0 = time.perf_counter()
+    e2e_t = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         loss = step(x_host.to(dev, non_blocking=True))
         loss_val = loss.item()
+        e2e_t.append((time.perf_counter() - ts) * 1e3)
+    if rank == 0:
+        sys.stderr.write("e2e ms per step (host clock, loss.item() each step): " + " ".join(f"{t:.1f}" for t in e2e_t) + "\n")
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -382,7 +381,7 @@ def run_ours(args):
                        "batch_per_gpu": B, "crop_s": CROP_S, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "launch": "conv/encoder segments replayed as CUDA graphs (fwd and bwd), the rest eager",
-                       "gc": "Python GC frozen after warm-up, collected between (not inside) the timed regions"},
+                       "gc": "gc.freeze() after warm-up (full collections no longer walk the long-lived heap)"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": 4,
                     "last_loss": loss_val},
             "gpu_launches": int(launches),

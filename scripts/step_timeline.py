@@ -76,6 +76,8 @@ def _gc_cb(phase, info):
 
 
 gc.callbacks.append(_gc_cb)
+if os.environ.get("TL_SWITCH"):
+    sys.setswitchinterval(float(os.environ["TL_SWITCH"]))
 if os.environ.get("TL_GC_OFF"):
     gc.disable()
 for _ in range(14):
@@ -98,7 +100,8 @@ def sampler():
         time.sleep(0.0005)
 
 
-threading.Thread(target=sampler, daemon=True).start()
+if not os.environ.get('TL_NO_SAMPLER'):
+    threading.Thread(target=sampler, daemon=True).start()
 
 
 def mstat():

@@ -206,3 +206,51 @@ def run_graph_case():
     finally:
         graphs.set_enabled(was)
     return l0, l1
+
+
+def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=("mask_emb", "final_proj.layer.weight", "project_q.layer.weight",
+                                                                    "encoder.transformer.encoders.0.ffn.0.layer.weight",
+                                                                    "encoder.transformer.encoders.0.self_attn.w_O.layer.weight",
+                                                                    "encoder.ln.weight", "proj_to_input.layer.bias")):
+    """Any configuration / size (no committed fixture): the product and the oracle are driven from the same numpy seed
+    (the oracle's create_mask / sample_negative_indices are pinned to the reference by test_oracle.py), eval-mode
+    quantizer (no Gumbel noise), dropout 0.  Integer artefacts bit-exact, loss rel 1e-2, the listed gradients by
+    cosine / rel-L2 (the whole set at small sizes is covered by run_pretrain_case)."""
+    from audio8_b200 import wav2vec2 as W
+    sd = P.pretrain_state_dict(seed=11, **{k: v for k, v in cfg.items() if k != "num_heads"})
+    model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg)
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    model = model.to(device).eval()  # eval: arg-max quantizer, masking still applied (reference :937)
+    n_vars = cfg.get("num_vq_vars", 320) * cfg.get("num_vq_groups", 2)
+    loss_fn = W.create_loss(n_vars, K)
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(5)) * 0.1
+    np.random.seed(seed)
+    loss = loss_fn(model, x.to(device))
+    loss.backward()
+    # the oracle's draws from the same seed, in the reference's order
+    T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+    np.random.seed(seed)
+    tmask = R.create_mask((B, T), 0.65, 10)
+    for _ in range(cfg.get("num_layers", 12)):
+        np.random.random()
+    Tm = int(tmask[0].sum())
+    neg = R.sample_negative_indices(B, Tm, K)
+    assert (loss_fn.last_neg_idx.astype(np.int64) == neg).all(), "negative indices differ from the oracle's draws"
+    kidx = model.quantizer.last_indices.cpu().numpy()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    st = R.pretrain_loss(sdg, x, tmask, neg, n_vars=n_vars, num_heads=cfg.get("num_heads", 12),
+                         num_layers=cfg.get("num_layers", 12), num_groups=cfg.get("num_vq_groups", 2), tau=0.5,
+                         gumbel_noise=None, force_idx=kidx)
+    st["loss"].backward()
+    with torch.no_grad():
+        st_free = R.pretrain_loss(sd, x, tmask, neg, n_vars=n_vars, num_heads=cfg.get("num_heads", 12),
+                                  num_layers=cfg.get("num_layers", 12), num_groups=cfg.get("num_vq_groups", 2), tau=0.5,
+                                  gumbel_noise=None)
+    vq_match = (kidx == st_free["vq_idx"].numpy()).mean()
+    assert vq_match >= 0.95, f"VQ arg-max agreement {vq_match:.4f}"
+    assert abs(loss.item() - st["loss"].item()) <= 1e-2 * abs(st["loss"].item()), (loss.item(), st["loss"].item())
+    got = dict(model.named_parameters())
+    for k in check_grads:
+        grad_close(got[k].grad, sdg[k].grad, "grad " + k, **grad_tol(k))
+    return loss.item(), st["loss"].item(), vq_match

@@ -29,3 +29,25 @@ def test_acoustic_cuda(mode):
 @pytest.mark.gpu
 def test_cuda_graph_replay_matches_eager():
     model_cases.run_graph_case()
+
+
+def test_pretrain_generic_host_logic_cpu(emu_backend):
+    """the fixture-free parity driver itself, on CPU through the ABI emulation (helper-thread draws included)"""
+    cfg = dict(d_model=128, num_heads=2, num_layers=2, d_ff=256, final_dim=64, num_vq_vars=24, num_vq_groups=2)
+    model_cases.run_pretrain_generic("cpu", cfg, B=2, L=8000, K=10)
+
+
+@pytest.mark.gpu
+def test_pretrain_large_config_cuda():
+    """wav2vec2-large widths (d=1024, 16 heads, d_ff=4096; BASELINE configs[3]) at a short crop, 2 layers"""
+    cfg = dict(d_model=1024, num_heads=16, num_layers=2, d_ff=4096, final_dim=256, num_vq_vars=320, num_vq_groups=2)
+    model_cases.run_pretrain_generic("cuda", cfg, B=2, L=16000, K=20)
+
+
+@pytest.mark.gpu
+def test_pretrain_full_size_cuda():
+    """BASELINE configs[1] at FULL size (base model, B=6 x 15 s, K=100) against the CPU oracle: loss and a sample of
+    gradients (about half a minute of host time for the oracle's fp32 forward+backward)."""
+    cfg = dict(d_model=768, num_heads=12, num_layers=12, final_dim=256, num_vq_vars=320, num_vq_groups=2)
+    ours, ref, vq = model_cases.run_pretrain_generic("cuda", cfg, B=6, L=240000, K=100)
+    assert vq >= 0.95
