@@ -334,21 +334,27 @@ class EncoderFn(torch.autograd.Function):
         if D % (8 * groups) != 0 or D != H * 64:
             raise ValueError(f"d_model={D}, heads={H}: this build needs d_model % {8 * groups} == 0 and d_k == 64 "
                              "(wav2vec2 base and large both use 64)")
-        k = pos_v.shape[-1]
+        k = pos_v.shape[-1] if pos_v is not None else 0
         pad_l = k // 2 - 1 if k % 2 == 0 else k // 2
-        if row_keep is not None:
+        if row_keep is not None and cfg.get("front", True):  # `x[~pad_mask] = 0` (wav2vec2.py:632): encoder input only
             x = x.clone()
             be.mask_apply(x, row_keep, None)
         need_grad = any(ctx.needs_input_grad)
         seed_src = step_seed(x) if p > 0 else None
         be.set_seed_source(seed_src)
-        pg, pv = pos_g.detach().contiguous(), pos_v.detach().contiguous()
-        wp, wpt, norm2 = be.posconv_pack(pg, pv, need_grad)
-        s0 = _empty(x.shape, BF16, x)
-        z0 = _empty(x.shape, BF16, x)
-        be.gemm(G.posconv_fwd(x, wp, s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
-        seed0 = next_seed() if p > 0 else 0
-        h, _, _, mean0, rstd0 = be.layernorm_fwd(s0, ln_g.detach(), ln_b.detach(), 1e-5, p_y=p, seed_y=seed0)
+        front = cfg.get("front", True)  # False: a later slice of the stack (no positional conv / LayerNorm in front)
+        if front:
+            pg, pv = pos_g.detach().contiguous(), pos_v.detach().contiguous()
+            wp, wpt, norm2 = be.posconv_pack(pg, pv, need_grad)
+            s0 = _empty(x.shape, BF16, x)
+            z0 = _empty(x.shape, BF16, x)
+            be.gemm(G.posconv_fwd(x, wp, s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
+            seed0 = next_seed() if p > 0 else 0
+            h, _, _, mean0, rstd0 = be.layernorm_fwd(s0, ln_g.detach(), ln_b.detach(), 1e-5, p_y=p, seed_y=seed0)
+        else:
+            pg = pv = wpt = norm2 = s0 = z0 = mean0 = rstd0 = None
+            seed0 = 0
+            h = x
         Tp = (T + 7) // 8 * 8
         scale = 1.0 / math.sqrt(D // H)
         wviews = _prepare_layer_weights(be, cfg["arena"], lw, PL) if len(lw) else []
@@ -384,7 +390,8 @@ class EncoderFn(torch.autograd.Function):
                                    z1=z1, hid=hid, s2=s2, mean1=mean1, rstd1=rstd1, seeds=(seed_a, seed1, seed2),
                                    w=(wqkv_b, wo_b, w1_b, w2_b), ln=(g2, g1)))
         if need_grad:
-            ctx.saved = dict(x=x, s0=s0, z0=z0, mean0=mean0, rstd0=rstd0, seed0=seed0, ln_g=ln_g.detach(),
+            ctx.saved = dict(x=x, s0=s0, z0=z0, mean0=mean0, rstd0=rstd0, seed0=seed0, front=front,
+                             ln_g=ln_g.detach() if front else None,
                              pg=pg, pv=pv, norm2=norm2, wpt=wpt, layers=layers, row_keep=row_keep, p=p, H=H,
                              groups=groups, k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw), seed_src=seed_src)
         be.set_seed_source(None)
@@ -449,6 +456,9 @@ class EncoderFn(torch.autograd.Function):
             lgrads[li * PL:(li + 1) * PL] = [dwqkv[0:D], dbqkv[0:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:],
                                              dbqkv[2 * D:], dwo, dbo, dg2, db2ln, dw1, db1, dw2, dbias2, dg1, db1ln]
             sv["layers"][li] = None  # free this layer's activations
+        if not sv["front"]:
+            be.set_seed_source(None)
+            return (dcur.view(B, T, D), None, None, None, None, None, None, None, *lgrads)
         # ---- front: LN(+dropout) <- x + gelu(pos_conv(x))
         ds0, _, dlg, dlb, _ = be.layernorm_bwd(dcur.view(B, T, D), sv["s0"], sv["mean0"], sv["rstd0"], sv["ln_g"],
                                                p_y=p, seed_y=sv["seed0"])

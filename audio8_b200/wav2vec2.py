@@ -388,8 +388,11 @@ class AudioTransformerEncoder(nn.Module):
         self.pos_conv = _PosConv(d_model, conv_pos_kernel, conv_groups, std)
         self.transformer = _Stack(d_model, d_ff if d_ff else 4 * d_model, layers)
         self.ln = _Affine(d_model)
-        self._arena = {}  # persistent bf16 operand buffers + device pointer table (values rewritten every call)
-        self._graph = GraphedSegment("transformer encoder")
+        self._arena = {}  # per stack slice: persistent bf16 operand buffers + device pointer table (values rewritten every call)
+        self._graph = GraphedSegment("transformer encoder (front + lower layers)")
+        self._graph2 = GraphedSegment("transformer encoder (upper layers)")
+        # measured at N=2 (round 1): the split neither helps nor hurts the step time, so it stays off by default
+        self.split_min_layers = int(__import__("os").environ.get("A8_ENCODER_SPLIT_MIN", "1000"))
 
     def forward(self, x, pad_mask=None):
         return self.extract_features(x, pad_mask)
@@ -404,21 +407,39 @@ class AudioTransformerEncoder(nn.Module):
         row_keep = None
         if pad_mask is not None:
             row_keep = pad_mask.to(device=x.device, dtype=torch.uint8).contiguous()
-        cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
-                   active=active, arena=self._arena)
-        flat = []
-        for layer in self.transformer.encoders:
-            flat += layer.flat()
         pc = self.pos_conv.conv[1]
-        params = (pc.weight_g, pc.weight_v, pc.bias, self.ln.weight, self.ln.bias, *flat)
-        if not all(active):  # LayerDrop changes the launch sequence per step: eager
-            return Fn.EncoderFn.apply(x, cfg, row_keep, *params)
+        front_params = (pc.weight_g, pc.weight_v, pc.bias, self.ln.weight, self.ln.bias)
+        # The stack runs as one or two autograd nodes / CUDA-graph segments.  Two (split in the middle) when it is deep
+        # enough: under DistributedDataParallel the gradients of the upper half then leave their node — and their
+        # buckets start to all-reduce — while the lower half's backward is still running.
+        cuts = [0, n // 2, n] if (n >= self.split_min_layers and all(active)) else [0, n]
+        h = x
+        for part in range(len(cuts) - 1):
+            lo, hi = cuts[part], cuts[part + 1]
+            cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
+                       active=active[lo:hi], arena=self._arena.setdefault(part, {}), front=(part == 0))
+            flat = []
+            for layer in self.transformer.encoders[lo:hi]:
+                flat += layer.flat()
+            params = (*front_params, *flat) if part == 0 else tuple(flat)
+            h = self._run_part(part, h, cfg, row_keep, params)
+        return h
+
+    def _run_part(self, part, x, cfg, row_keep, params):
+        nf = 5 if cfg["front"] else 0
+
+        def call(x_, rk, ps):
+            fr = ps[:nf] if nf else (None,) * 5
+            return Fn.EncoderFn.apply(x_, cfg, rk, *fr, *ps[nf:])
+
+        if not all(cfg["active"]):  # LayerDrop changes the launch sequence per step: eager
+            return call(x, row_keep, params)
         # static shapes: replay a captured CUDA graph once this (shape, mode) has been seen before (graphs.py)
+        seg = self._graph if part == 0 else self._graph2
         if row_keep is None:
-            return self._graph.run(lambda x_, *ps: Fn.EncoderFn.apply(x_, cfg, None, *ps), (x,), params,
-                                   extra=(self.training, self.pdrop))
-        return self._graph.run(lambda x_, rk, *ps: Fn.EncoderFn.apply(x_, cfg, rk, *ps), (x, row_keep), params,
-                               extra=(self.training, self.pdrop))
+            return seg.run(lambda x_, *ps: call(x_, None, ps), (x,), params, extra=(self.training, self.pdrop, part))
+        return seg.run(lambda x_, rk, *ps: call(x_, rk, ps), (x, row_keep), params,
+                       extra=(self.training, self.pdrop, part))
 
 
 class Wav2Vec2Encoder(nn.Module):

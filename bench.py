@@ -308,7 +308,7 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host input -> device every step, loss read back every step
     gc.collect()
     barrier()
-    for _ in range(3):  # this loop's own warm-up: the per-step input tensor changes the allocator's request sequence
+    for _ in range(8):  # this loop's own warm-up: the per-step input tensor changes the allocator's request sequence
         step(x_host.to(dev, non_blocking=True)).item()
     gc.collect()
     barrier()

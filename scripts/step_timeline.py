@@ -13,10 +13,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from audio8_b200 import wav2vec2 as W  # noqa: E402
 
-dev = torch.device("cuda")
-torch.manual_seed(0)
-np.random.seed(0)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+torch.manual_seed(rank)
+np.random.seed(rank)
 model = W.create_model().to(dev).train()
+net = model
+if world > 1:
+    import datetime
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=128)
+    if rank != 0:
+        sys.stdout = open(os.devnull, "w")
 loss_fn = W.create_loss(640, 100)
 x_host = (torch.randn(6, 240000) * 0.1).pin_memory()
 params = list(model.parameters())
@@ -56,7 +68,7 @@ def step():
     mark("step start")
     x = x_host.to(dev, non_blocking=True)
     mark("h2d issued")
-    loss = loss_fn(model, x)
+    loss = loss_fn(net, x)
     mark("forward enqueued")
     loss.backward()
     mark("backward enqueued")

@@ -211,7 +211,8 @@ def run_graph_case():
 def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=("mask_emb", "final_proj.layer.weight", "project_q.layer.weight",
                                                                     "encoder.transformer.encoders.0.ffn.0.layer.weight",
                                                                     "encoder.transformer.encoders.0.self_attn.w_O.layer.weight",
-                                                                    "encoder.ln.weight", "proj_to_input.layer.bias")):
+                                                                    "encoder.ln.weight", "proj_to_input.layer.bias"),
+                         split_min=None):
     """Any configuration / size (no committed fixture): the product and the oracle are driven from the same numpy seed
     (the oracle's create_mask / sample_negative_indices are pinned to the reference by test_oracle.py), eval-mode
     quantizer (no Gumbel noise), dropout 0.  Integer artefacts bit-exact, loss rel 1e-2, the listed gradients by
@@ -222,6 +223,8 @@ def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=("mask_emb", 
     res = model.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     model = model.to(device).eval()  # eval: arg-max quantizer, masking still applied (reference :937)
+    if split_min is not None:
+        model.encoder.split_min_layers = split_min  # force the two-segment encoder on shallow test models
     n_vars = cfg.get("num_vq_vars", 320) * cfg.get("num_vq_groups", 2)
     loss_fn = W.create_loss(n_vars, K)
     x = torch.randn(B, L, generator=torch.Generator().manual_seed(5)) * 0.1

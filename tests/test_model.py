@@ -37,6 +37,15 @@ def test_pretrain_generic_host_logic_cpu(emu_backend):
     model_cases.run_pretrain_generic("cpu", cfg, B=2, L=8000, K=10)
 
 
+def test_pretrain_split_encoder_host_logic_cpu(emu_backend):
+    """the encoder as two autograd nodes (what deep stacks use so that DDP can overlap the all-reduce)"""
+    cfg = dict(d_model=128, num_heads=2, num_layers=2, d_ff=256, final_dim=64, num_vq_vars=24, num_vq_groups=2)
+    model_cases.run_pretrain_generic("cpu", cfg, B=2, L=8000, K=10, split_min=2,
+                                     check_grads=("mask_emb", "encoder.transformer.encoders.0.ffn.0.layer.weight",
+                                                  "encoder.transformer.encoders.1.self_attn.w_O.layer.weight",
+                                                  "encoder.ln.weight", "encoder.pos_conv.conv.1.weight_v"))
+
+
 @pytest.mark.gpu
 def test_pretrain_large_config_cuda():
     """wav2vec2-large widths (d=1024, 16 heads, d_ff=4096; BASELINE configs[3]) at a short crop, 2 layers"""
