@@ -15,7 +15,7 @@ namespace {
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int RING = 4;
+constexpr int RING = 8;  // log-prob rows in flight per warp (7 time steps of look-ahead cover an L2/HBM round trip)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -29,9 +29,11 @@ __device__ __forceinline__ float lg2(float x) {
 }
 // log2(2^a + 2^b + 2^c) with -inf handling (never forms inf - inf)
 __device__ __forceinline__ float lse3(float a, float b, float c) {
+  // branch-free (the recursion evaluates NS of these per lane and time step; a divergent early return serialises
+  // them): with every input -inf the shift is 0, ex2(-inf) = 0 and lg2(0) = -inf is the result
   const float m = fmaxf(a, fmaxf(b, c));
-  if (m == -INFINITY) return -INFINITY;
-  return m + lg2(ex2(a - m) + ex2(b - m) + ex2(c - m));
+  const float ms = (m == -INFINITY) ? 0.f : m;
+  return ms + lg2(ex2(a - ms) + ex2(b - ms) + ex2(c - ms));
 }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");

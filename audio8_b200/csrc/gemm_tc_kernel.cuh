@@ -17,7 +17,17 @@ namespace gemm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;  // warps 4..11: two per TMEM lane quarter, each owns half of the tile's columns
+#ifndef A8_EPI16
+#define A8_EPI16 0
+#endif
+// epilogue warps 4..: EPI_PARTS per TMEM lane quarter, each owns 1/EPI_PARTS of the tile's columns and drains them in
+// chunks of EPI_CW columns.  16 warps x 16-column chunks (~100 registers) hide the latency of the GELU epilogues twice
+// as well as 8 warps x 32 columns did.
+constexpr int EPI_PARTS = A8_EPI16 ? 4 : 2;
+constexpr int EPI_CW = A8_EPI16 ? 16 : 32;
+constexpr int EPI_WARPS = 4 * EPI_PARTS;
+constexpr int STG_PITCH = 80;                 // bytes per staged row: <= 64 payload + 16 pad (conflict-free 16B writes)
+constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
 constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
 enum { MAJOR_K = A8_MAJOR_K, MAJOR_MN = A8_MAJOR_MN };
 enum { OUT_BF16 = A8_OUT_BF16, OUT_F32 = A8_OUT_F32, OUT_F32_ATOMIC = A8_OUT_F32_ATOMIC };
@@ -80,11 +90,12 @@ template <int BN, int CL = 1>
 struct Cfg {
   // CL == 2: a CTA pair works on one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of A and
   // its own HALF of the B tile (BN/2 rows), so a stage is smaller and the ring deeper.
-  static constexpr int STAGES = (CL == 2) ? (BN == 256 ? 6 : (BN == 192 ? 7 : 8)) : ((BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8)));
+  static constexpr int STAGES0 = (CL == 2) ? (BN == 256 ? 6 : (BN == 192 ? 7 : 8)) : ((BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8)));
+  static constexpr int STAGES = STAGES0 - (EPI_WARPS > 8 ? 1 : 0);  // the 16-warp staging buffers take one stage's room
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = (BN / CL) * BLOCK_K * 2;
   static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // powers of two >= 32; 2 accumulator stages
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * 32 * 80 + 1024;
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * STG_BYTES + 1024;
 };
 
 // UMMA shared-memory matrix descriptor, 128B swizzle (layout type 2), descriptor version 1.
@@ -114,25 +125,20 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int
   return t;
 }
 
-#ifndef A8_EPI_DIRECT
-#define A8_EPI_DIRECT 0  // 1: bf16 outputs / aux go straight between registers and global memory (no smem staging)
-#endif
-constexpr int STG_PITCH = 80;                 // bytes per staged row: 64 payload + 16 pad (conflict-free 16B writes)
-constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
-
-// Coalesced copy between a warp's staging buffer (32 rows x 64 B) and global rows `row_off0 + r*ldc` (element
-// offsets of element size ES): lane l moves 16 B of row (l/4 + 8i), piece (l%4) — every instruction touches 8 rows
-// x 64 contiguous bytes instead of 32 rows x 16 bytes.
+// Coalesced copy between a warp's staging buffer (32 rows x PIECES*16 B) and global rows `row_off0 + r*ldc` (element
+// offsets of element size ES): lane l moves 16 B of row (l/PIECES + (32/PIECES) i), piece (l % PIECES) — every
+// instruction touches 32/PIECES rows x PIECES*16 contiguous bytes instead of 32 rows x 16 bytes.
 enum { STG_LOAD = 0, STG_STORE = 1, STG_RED = 2 };
-template <int ES, int MODE>
+template <int ES, int MODE, int PIECES>
 __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long row_off0, long long ldc, int col0,
                                            int rows_valid, int cols_valid, int lane) {
   constexpr int EPP = 16 / ES;  // elements per 16-byte piece
-  const int piece = lane & 3;
+  constexpr int RPI = 32 / PIECES;  // rows per instruction
+  const int piece = lane % PIECES;
   const int col = col0 + piece * EPP;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = (lane >> 2) + 8 * i;
+  for (int i = 0; i < PIECES; ++i) {
+    const int r = lane / PIECES + RPI * i;
     if (r < rows_valid && col < cols_valid) {
       uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (row_off0 + (long long)r * ldc + col) * ES;
       uint4* sp = reinterpret_cast<uint4*>(stg + r * STG_PITCH + piece * 16);
@@ -140,7 +146,7 @@ __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long 
         *reinterpret_cast<uint4*>(g) = *sp;
       } else if (MODE == STG_LOAD) {
         *sp = *reinterpret_cast<const uint4*>(g);
-      } else {  // split-K: one 16-byte vector reduction per lane, 64 contiguous bytes per row
+      } else {  // split-K: one 16-byte vector reduction per lane
         const float4 v = *reinterpret_cast<const float4*>(sp);
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                      : "memory");
@@ -149,74 +155,60 @@ __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long 
   }
 }
 
-// 32 columns x 32 rows (one row per lane) of accumulators in registers -> epilogue math -> global memory.
-// Non-atomic outputs (and the bf16 aux input) go through the warp's smem staging buffer so that global accesses
-// are row-contiguous; the split-K fp32 path adds atomically straight from registers.
-template <int EK>
+// CW columns x 32 rows (one row per lane) of accumulators in registers -> epilogue math -> global memory.  Outputs (and
+// the bf16 aux input) go through the warp's smem staging buffer so that global accesses are row-contiguous (direct
+// 16-byte-per-row stores from registers were measured: slower, L2 sees partial sectors).
+template <int EK, int CW>
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t* r, long long row_off0, int row0,
                                                int nb, const float* sb, uint8_t* stg, int lane) {
   constexpr bool GEN = (EK < 0);
+  constexpr int NP = CW / 8;  // 16-byte bf16 pieces per row
   const int c_dtype = GEN ? p.c_dtype : (EK & 3);
   const bool do_gelu = GEN ? (p.act == ACT_GELU) : (((EK >> 2) & 1) != 0);
   const bool do_z = GEN ? (p.z_out != nullptr) : (((EK >> 3) & 1) != 0);
   const int aux_mode = GEN ? p.aux_mode : ((EK >> 4) & 3);
   const int rows_valid = min(32, p.M - row0);        // may be <= 0
-  const int n8 = (p.N + 7) & ~7;
-  const int cols_valid = n8;                          // absolute column bound for the 16-byte pieces
+  const int cols_valid = (p.N + 7) & ~7;              // absolute column bound for the 16-byte pieces
   const bool has_aux = aux_mode != AUX_NONE;
   uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
-  uint4 a[4];
+  uint4 a[NP];
   if (has_aux) {
-#if A8_EPI_DIRECT
-    const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + row_off0 +
-                                                     (long long)lane * p.ldc + nb);
-#pragma unroll
-    for (int g = 0; g < 4; ++g)
-      a[g] = (lane < rows_valid && nb + 8 * g < cols_valid) ? __ldg(ap + g) : make_uint4(0u, 0u, 0u, 0u);
-#else
-    stage_copy<2, STG_LOAD>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_LOAD, NP>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) a[g] = my[g];
+    for (int g = 0; g < NP; ++g) a[g] = my[g];
     __syncwarp();
-#endif
   }
-  float v[32];
+  float v[CW];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-  if (sb != nullptr) {  // 8 broadcast LDS.128 (a scalar LDS per column costs a full shared-memory wavefront each)
+  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (sb != nullptr) {  // broadcast LDS.128 (a scalar LDS per column costs a full shared-memory wavefront each)
     const float4* sb4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CW / 4; ++i) {
       const float4 b4 = sb4[i];
       v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
     }
   }
   if (do_z) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NP; ++g) {
       uint4 z;
       z.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); z.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
       z.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); z.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-#if A8_EPI_DIRECT
-      if (lane < rows_valid && nb + 8 * g < cols_valid)
-        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.z_out) + row_off0 + (long long)lane * p.ldc + nb)[g] = z;
-    }
-#else
       my[g] = z;
     }
     __syncwarp();
-    stage_copy<2, STG_STORE>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_STORE, NP>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
-#endif
   }
   if (do_gelu) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+    for (int i = 0; i < CW; ++i) v[i] = gelu_fast(v[i]);
   }
   if (has_aux) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NP; ++g) {
       const uint32_t w[4] = {a[g].x, a[g].y, a[g].z, a[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -233,33 +225,27 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
   }
   if (c_dtype == OUT_BF16) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NP; ++g) {
       uint4 o;
       o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]); o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
       o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-#if A8_EPI_DIRECT
-      if (lane < rows_valid && nb + 8 * g < cols_valid)
-        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.c) + row_off0 + (long long)lane * p.ldc + nb)[g] = o;
-    }
-#else
       my[g] = o;
     }
     __syncwarp();
-    stage_copy<2, STG_STORE>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_STORE, NP>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
-#endif
-  } else {  // fp32: plain stores, or vector reductions for split-K partial sums
+  } else {  // fp32: plain stores, or vector reductions for split-K partial sums; 16 columns (64 B per row) at a time
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < CW / 16; ++h) {
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         my[g] = make_uint4(__float_as_uint(v[16 * h + 4 * g]), __float_as_uint(v[16 * h + 4 * g + 1]),
                            __float_as_uint(v[16 * h + 4 * g + 2]), __float_as_uint(v[16 * h + 4 * g + 3]));
       __syncwarp();
       if (c_dtype == OUT_F32)
-        stage_copy<4, STG_STORE>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+        stage_copy<4, STG_STORE, 4>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
       else
-        stage_copy<4, STG_RED>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+        stage_copy<4, STG_RED, 4>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
       __syncwarp();
     }
   }
@@ -273,6 +259,17 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
 // Barriers: both producers' TMA loads complete on the LEADER's full barrier (the leader posts the expected bytes of
 // both); the leader's tcgen05.commit is multicast to the empty / accumulator-full barriers of both CTAs; the peer's
 // epilogue warps arrive remotely on the leader's accumulator-empty barrier.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x16(taddr, r); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -516,9 +513,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ======================================= epilogue =======================================
     // warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the tile's columns.
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    constexpr int COLS = BN / 2;         // columns per warp
-    constexpr int NCH = COLS / 32;       // 32-column chunks per warp (4 / 2 / 1)
+    const int half = (warp - 4) >> 2;    // which 1/EPI_PARTS of the tile's columns
+    constexpr int COLS = BN / EPI_PARTS;  // columns per warp
+    constexpr int NCH = COLS / EPI_CW;    // chunks per warp
     const int tid_e = threadIdx.x - 128;
     int iter = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
@@ -544,15 +541,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int nb0 = t.nt * BN + half * COLS;
       const float* sbw = sb ? sb + half * COLS : nullptr;
       uint8_t* stg = s_stage + (warp - 4) * STG_BYTES;
-      // one 32-column chunk at a time, NOT unrolled: the chunk body is several hundred instructions and the 8
-      // epilogue warps must stay inside the instruction cache (the other 7 warps hide this warp's tcgen05.ld latency)
-      uint32_t ra[32];
+      // one chunk at a time, NOT unrolled: the chunk body is several hundred instructions and the epilogue warps must
+      // stay inside the instruction cache (the other epilogue warps hide this warp's tcgen05.ld latency)
+      uint32_t ra[EPI_CW];
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        if (nb0 + c * 32 >= p.N) break;
-        tmem_ld_32x32(t_addr + c * 32, ra);
+        if (nb0 + c * EPI_CW >= p.N) break;
+        tmem_ld_chunk(t_addr + c * EPI_CW, ra);
         tmem_ld_wait();
-        epilogue_chunk<EK>(p, ra, row_off0, row0, nb0 + c * 32, sbw ? sbw + c * 32 : nullptr, stg, lane);
+        epilogue_chunk<EK, EPI_CW>(p, ra, row_off0, row0, nb0 + c * EPI_CW, sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
       }
       tc_fence_before();
       __syncwarp();

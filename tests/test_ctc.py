@@ -58,7 +58,7 @@ def test_cuda_ctc_matches_fixture(name, red):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("T,B,S,V", [(50, 8, 10, 32), (250, 32, 50, 32), (750, 64, 150, 32), (300, 5, 40, 100),
-                                     (1500, 16, 300, 32), (64, 3, 0, 8)])
+                                     (1500, 16, 300, 32), (64, 3, 0, 8), (1500, 256, 300, 32)])
 def test_cuda_ctc_matches_oracle_sweep(T, B, S, V):
     """config-5 sweep shapes; log-probs arrive as the transposed [B,T,V] view the trainer passes (train.py:39)"""
     from audio8_b200.ctc import ctc_loss

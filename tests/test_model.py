@@ -60,3 +60,18 @@ def test_pretrain_full_size_cuda():
     cfg = dict(d_model=768, num_heads=12, num_layers=12, final_dim=256, num_vq_vars=320, num_vq_groups=2)
     ours, ref, vq = model_cases.run_pretrain_generic("cuda", cfg, B=6, L=240000, K=100)
     assert vq >= 0.95
+
+
+def test_acoustic_generic_host_logic_cpu(emu_backend):
+    cfg = dict(d_model=128, num_heads=2, num_layers=2, d_ff=256)
+    model_cases.run_acoustic_generic("cpu", cfg, V=32, B=3, L=12000, S=8,
+                                     check_grads=("proj.weight", "encoder.mask_emb",
+                                                  "encoder.encoder.transformer.encoders.0.ffn.3.layer.weight"))
+
+
+@pytest.mark.gpu
+def test_acoustic_full_size_cuda():
+    """BASELINE configs[2] per GPU at FULL size: wav2vec2-base CTC fine-tune (char vocab 32), B=8 x 15 s ragged,
+    150-char targets, frozen feature encoder, time + channel masks, against the CPU oracle"""
+    cfg = dict(d_model=768, num_heads=12, num_layers=12)
+    model_cases.run_acoustic_generic("cuda", cfg, V=32, B=8, L=240000, S=150)
