@@ -21,8 +21,8 @@ constexpr int UMMA_K = 16;
 #define A8_EPI16 0
 #endif
 // epilogue warps 4..: EPI_PARTS per TMEM lane quarter, each owns 1/EPI_PARTS of the tile's columns and drains them in
-// chunks of EPI_CW columns.  16 warps x 16-column chunks (~100 registers) hide the latency of the GELU epilogues twice
-// as well as 8 warps x 32 columns did.
+// chunks of EPI_CW columns.  A8_EPI16=1 (16 warps x 16-column chunks, one pipeline stage less) was measured on the
+// step's shapes (scripts/gemm_bench.py, r01): 0-8 % slower than 8 warps x 32 columns on every GEMM, GELU kinds included.
 constexpr int EPI_PARTS = A8_EPI16 ? 4 : 2;
 constexpr int EPI_CW = A8_EPI16 ? 16 : 32;
 constexpr int EPI_WARPS = 4 * EPI_PARTS;

@@ -32,17 +32,31 @@ struct VqArgs {
   float* dvars;        // [G*V, vd]
 };
 
+// All loads of the row are issued before the first dependent instruction: clamped addresses instead of per-lane
+// branches (a divergent `if (v < V)` around load + arithmetic serialised the 2 x VPL loads of a warp, which is what
+// these L2-resident kernels spend their time on).
 __device__ __forceinline__ void load_row(const VqArgs& a, int n, int lane, float (&zv)[VPL], float (&uv)[VPL]) {
   const int r = n / a.G, g = n - r * a.G;
   const float* zr = a.z + ((long long)r * a.G + g) * a.V;
-  const float* nr = a.noise ? a.noise + (long long)n * a.V : nullptr;
+  const float* nr = a.noise ? a.noise + (long long)n * a.V : zr;
+  const bool has_noise = a.noise != nullptr;
   const float it = 1.f / a.tau;
+  const int nvl = (a.V + 31) >> 5;  // warp-uniform trip count
+  float zraw[VPL], nraw[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (i < nvl) {
+      const int vc = min(lane + 32 * i, a.V - 1);
+      zraw[i] = __ldg(zr + vc);
+      nraw[i] = __ldg(nr + vc);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
-    if (v < a.V) {
-      zv[i] = zr[v];
-      uv[i] = nr ? (zv[i] + nr[v]) * it : zv[i];
+    if (i < nvl && v < a.V) {
+      zv[i] = zraw[i];
+      uv[i] = has_noise ? (zraw[i] + nraw[i]) * it : zraw[i];
     } else {
       zv[i] = -INFINITY;
       uv[i] = -INFINITY;
@@ -189,9 +203,9 @@ __global__ void __launch_bounds__(256) vq_bwd_kernel(const VqArgs a) {
   }
 }
 
-int vq_grid(int N) {
-  int g = cdiv(N, 8 * 4);
-  return g < 1 ? 1 : (g > 148 * 2 ? 148 * 2 : g);
+int vq_grid(int N) {  // one (row, group) per warp when they fit in one wave of 8-warp CTAs
+  int g = cdiv(N, 8);
+  return g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g);
 }
 
 }  // namespace

@@ -7,6 +7,7 @@ read from `Offsets` at call time, like the reference does (`ctc.py:193,202`; `tr
 import torch
 
 from . import ops
+from .functional import _take_saved
 
 
 class Offsets:
@@ -45,7 +46,7 @@ class _CTCFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        lp, flat, off, tl32, il32, alpha, beta, nll = ctx.saved
+        lp, flat, off, tl32, il32, alpha, beta, nll = _take_saved(ctx)
         max_S, blank, mean, zero_infinity, dtype = ctx.cfg
         grad = ops.backend().ctc_backward(lp, flat, off, tl32, il32, max_S, blank, alpha, beta, nll, grad_out, mean,
                                           zero_infinity)

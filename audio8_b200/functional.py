@@ -36,6 +36,18 @@ def _be():
     return ops.backend()
 
 
+def _take_saved(ctx):
+    """Activations a Function kept for backward, released as backward starts (what save_for_backward does for built-in
+    nodes): a loss tensor that outlives its step must not pin the step's activations.  A second backward through the
+    same graph (retain_graph) is therefore not supported, as with freed PyTorch buffers."""
+    saved = ctx.saved
+    if saved is None:
+        raise RuntimeError("audio8_b200: backward through this graph a second time: its activations were released "
+                           "after the first backward (retain_graph is not supported)")
+    ctx.saved = None
+    return saved
+
+
 def _empty(shape, dtype, like, dynamic=False):
     """dynamic=True: the size follows the per-step masked-row count -> bucketed allocation (ops.bucketed_empty)"""
     if dynamic:
@@ -78,7 +90,7 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         be = _be()
-        xb, wb, xdtype, shp, has_bias = ctx.saved
+        xb, wb, xdtype, shp, has_bias = _take_saved(ctx)
         N, K = wb.shape
         dyb = _bf16(dy.reshape(-1, N))
         dx = dw = db = None
@@ -117,7 +129,7 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, dyf=None):
         be = _be()
-        s, mean, rstd, gamma, xdtype = ctx.saved
+        s, mean, rstd, gamma, xdtype = _take_saved(ctx)
         if dy is None:
             dy = _zeros(s.shape, BF16, s)
         ds, _, dg, db, _ = be.layernorm_bwd(_bf16(dy), s, mean, rstd, gamma,
@@ -253,7 +265,7 @@ class ConvFeatureFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         be = _be()
-        x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec = ctx.saved
+        x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec = _take_saved(ctx)
         n = len(spec)
         grads = [None] * n
         if n > 1:
@@ -400,7 +412,7 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dh):
         be = _be()
-        sv = ctx.saved
+        sv = _take_saved(ctx)
         PL = EncoderFn.PER_LAYER
         p, H, Tp, scale = sv["p"], sv["H"], sv["Tp"], sv["scale"]
         x = sv["x"]
@@ -500,7 +512,7 @@ class QuantizerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, dppl, _dk):
         be = _be()
-        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape = ctx.saved
+        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape = _take_saved(ctx)
         R = y2.shape[0]
         vd = v2.shape[1]
         if dq is None:
@@ -538,7 +550,7 @@ class ContrastiveFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, dce_extra):
         be = _be()
-        x2, y2, idx, saved, xs, ys, n_vars, xe_w, div_w, has_ppl = ctx.saved
+        x2, y2, idx, saved, xs, ys, n_vars, xe_w, div_w, has_ppl = _take_saved(ctx)
         dce = dloss * xe_w
         if dce_extra is not None:
             dce = dce + dce_extra
@@ -559,6 +571,6 @@ class LogSoftmaxFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        y = ctx.saved
+        y = _take_saved(ctx)
         dx = _be().log_softmax_bwd(dy.float(), y)  # strided dy (e.g. CTC's [T,B,V] transposed back) is consumed as is
         return dx.float()
