@@ -431,7 +431,10 @@ class EncoderFn(torch.autograd.Function):
             F_ = w1_b.shape[0]
             # every fp32 accumulator of this layer's backward comes from ONE zero-filled buffer (one fill launch)
             sizes = [3 * D * D, D * D, F_ * D, D * F_, 3 * D, 3 * D, F_, 3 * D]
-            zbuf = _zeros((sum(sizes),), F32, x)
+            # data-parallel runs: the block lives in the wrapper's gradient arena (parallel.py) and is reduced in place
+            zbuf = ops.grad_arena_take(("enc", L["w"][0].data_ptr()), sum(sizes))
+            if zbuf is None:
+                zbuf = _zeros((sum(sizes),), F32, x)
             parts, o = [], 0
             for n_ in sizes:
                 parts.append(zbuf[o:o + n_])

@@ -49,6 +49,39 @@ class GemmSpec:
         self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
 
 
+# gradient arena of the data-parallel wrapper (parallel.py): [arena used by forward-time decisions, arena for the
+# backward that belongs to the last forward, callback fired when the encoder's backward has been enqueued]
+_ARENA = [None, None, None]
+
+
+def set_grad_arena(arena, encoder_done_cb, keep_for_backward=False):
+    if keep_for_backward:  # forward is over: later forwards must not see it, this step's backward still does
+        _ARENA[0] = None
+        return
+    _ARENA[0] = _ARENA[1] = arena
+    _ARENA[2] = encoder_done_cb
+
+
+def grad_arena_for_backward():
+    return _ARENA[1]
+
+
+def grad_arena_take(key, numel):
+    """a zeroed persistent block for a layer's gradient accumulators, or None (no arena: allocate normally)"""
+    a = _ARENA[1]
+    return a.take(key, numel) if a is not None else None
+
+
+def encoder_backward_done():
+    cb = _ARENA[2]
+    if cb is not None and _ARENA[1] is not None:
+        cb()
+
+
+def grad_arena_active():
+    return _ARENA[1] is not None
+
+
 _DYN = [0, 0]  # (rows of the current step's masked-row tensors, their upper bound); set_dynamic_rows()
 
 

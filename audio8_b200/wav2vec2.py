@@ -369,6 +369,11 @@ class _Stack(nn.Module):
         self.encoders = nn.ModuleList([_LayerParams(d, d_ff) for _ in range(layers)])
 
 
+def _encoder_backward_done(grad):
+    Fn.ops.encoder_backward_done()
+    return grad
+
+
 class AudioTransformerEncoder(nn.Module):
     """Reference wav2vec2.py:579-646: positional conv (k=128, groups=16, weight-normed) + GELU, residual, LayerNorm,
     dropout, then a post-LN transformer stack (eight_mile TransformerEncoderStack, layer_norms_after=True)."""
@@ -399,6 +404,10 @@ class AudioTransformerEncoder(nn.Module):
 
     def extract_features(self, x, pad_mask=None, _layer_draws=None):
         """x [B,T,D] (bf16 or fp32), pad_mask bool [B,T] (True = valid) or None -> bf16 [B,T,D]"""
+        if x.requires_grad and Fn.ops.grad_arena_active():
+            # data-parallel wrapper (parallel.py): when the gradient w.r.t. the encoder's input exists, every layer has
+            # written its gradients into the arena and their all-reduce can start under the rest of backward
+            x.register_hook(_encoder_backward_done)
         n = len(self.transformer.encoders)
         active = []
         for i in range(n):  # eight_mile draws one numpy random per layer, even with layer_drop == 0
@@ -437,9 +446,9 @@ class AudioTransformerEncoder(nn.Module):
         # static shapes: replay a captured CUDA graph once this (shape, mode) has been seen before (graphs.py)
         seg = self._graph if part == 0 else self._graph2
         if row_keep is None:
-            return seg.run(lambda x_, *ps: call(x_, None, ps), (x,), params, extra=(self.training, self.pdrop, part))
+            return seg.run(lambda x_, *ps: call(x_, None, ps), (x,), params, extra=(self.training, self.pdrop, part, Fn.ops.grad_arena_active()))
         return seg.run(lambda x_, rk, *ps: call(x_, rk, ps), (x, row_keep), params,
-                       extra=(self.training, self.pdrop, part))
+                       extra=(self.training, self.pdrop, part, Fn.ops.grad_arena_active()))
 
 
 class Wav2Vec2Encoder(nn.Module):

@@ -226,13 +226,21 @@ def run_ours(args):
     model.train()
     loss_fn = W.create_loss(N_VARS, N_NEG)
     net = model
+    dp_name = "single process"
     if world > 1:
-        # stock DistributedDataParallel as in pretrain.py:158; gradients as views of few large buckets (no per-parameter
-        # copy kernels, a handful of NCCL launches per step instead of ~16)
-        net = torch.nn.parallel.DistributedDataParallel(
-            model, device_ids=[local], output_device=local,
-            gradient_as_bucket_view=os.environ.get("A8_DDP_BUCKET_VIEW", "1") != "0",
-            bucket_cap_mb=int(os.environ.get("A8_DDP_BUCKET_MB", "128")))
+        if os.environ.get("A8_DP", "arena") == "ddp":
+            # stock DistributedDataParallel as in pretrain.py:158; gradients as views of few large buckets
+            net = torch.nn.parallel.DistributedDataParallel(
+                model, device_ids=[local], output_device=local,
+                gradient_as_bucket_view=os.environ.get("A8_DDP_BUCKET_VIEW", "1") != "0",
+                bucket_cap_mb=int(os.environ.get("A8_DDP_BUCKET_MB", "128")))
+            dp_name = "torch DistributedDataParallel (bucket views, 128 MB buckets)"
+        else:
+            # the package's data-parallel wrapper: transformer-layer gradients are written into one contiguous arena and
+            # all-reduced in place under the conv stack's backward (audio8_b200/parallel.py); same interface as DDP
+            from audio8_b200.parallel import DataParallel
+            net = DataParallel(model)
+            dp_name = "audio8_b200.parallel.DataParallel (gradient arena, in-place NCCL all-reduce)"
     B = B_PER_GPU
     lib = _lib.load()
     x_dev = torch.randn(B, L, device=dev) * 0.1
@@ -384,7 +392,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": model_name + " contrastive pretrain fwd+bwd, G=2 V=320 K=100, dropout 0.1",
-                       "batch_per_gpu": B, "crop_s": CROP_S, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "batch_per_gpu": B, "crop_s": CROP_S, "global_batch": world * B, "parallelism": f"dp{world}", "data_parallel": dp_name,
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "launch": "conv/encoder segments replayed as CUDA graphs (fwd and bwd), the rest eager",
                        "gc": "gc.freeze() after warm-up (full collections no longer walk the long-lived heap)"},

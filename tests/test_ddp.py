@@ -146,3 +146,72 @@ def test_ddp_gloo_world2_ctc_unequal_batches(tmp_path):
     world = 2
     mp.spawn(_ctc_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _arena_worker(rank, world, port, out_dir):
+    """audio8_b200.parallel.DataParallel (gradient arena + one in-place all-reduce) against the mean of the per-rank
+    gradients, incl. a no_sync() micro-step followed by a synchronised one (gradient accumulation)"""
+    for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        from audio8_b200 import ops
+        from audio8_b200 import wav2vec2 as W
+        from audio8_b200.parallel import DataParallel
+        ops.set_backend(emu.EmuOps())
+        torch.manual_seed(rank)  # different initial weights per rank: the wrapper must broadcast rank 0's
+        model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **TINY).train()
+        loss_fn = W.create_loss(TINY["num_vq_vars"] * TINY["num_vq_groups"], 10)
+        net = DataParallel(model)
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        assert torch.equal(gathered[0], gathered[1]), "parameters were not broadcast"
+        xs = [torch.randn(2, 8000, generator=torch.Generator().manual_seed(100 + r)) * 0.1 for r in range(world)]
+        want = None
+        for r in range(world):
+            _, g = _local_grads(model, loss_fn, xs[r], 7 + r)
+            want = g if want is None else {k: want[k] + g[k] for k in g}
+        want = {k: v / world for k, v in want.items()}
+        for rep in range(2):  # twice: the second step reuses the arena blocks
+            _, got = _local_grads(net, loss_fn, xs[rank], 7 + rank)
+            got = {k.replace("module.", "", 1): v for k, v in got.items()}
+            assert set(got) == set(want)
+            for k in want:
+                err = (got[k] - want[k]).abs().max().item()
+                scale = want[k].abs().max().item() + 1e-8
+                assert err <= 1e-4 * scale + 1e-7, f"rank {rank} step {rep} grad {k}: {err:.3g} vs scale {scale:.3g}"
+        assert net._arena is not None and net._arena.used > 0, "the transformer layers did not use the gradient arena"
+        in_arena = sum(1 for p in model.parameters() if p.grad is not None and
+                       net._arena.buf.data_ptr() <= p.grad.data_ptr() < net._arena.buf.data_ptr() + 4 * net._arena.buf.numel())
+        assert in_arena >= 6, f"only {in_arena} gradients alias the arena (expected the six weight matrices of the layer)"
+        # accumulation: micro-step under no_sync() + synchronised micro-step = mean over ranks of the SUM of both
+        model.zero_grad(set_to_none=True)
+        np.random.seed(7 + rank)
+        torch.manual_seed(7 + rank)
+        with net.no_sync():
+            loss_fn(net, xs[rank]).backward()
+        np.random.seed(7 + rank)
+        torch.manual_seed(7 + rank)
+        loss_fn(net, xs[rank]).backward()
+        for k, p_ in model.named_parameters():
+            if p_.grad is None:
+                continue
+            err = (p_.grad - 2 * want[k]).abs().max().item()
+            scale = want[k].abs().max().item() + 1e-8
+            assert err <= 2e-4 * scale + 1e-7, f"accumulated grad {k}: {err:.3g} vs scale {scale:.3g}"
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_arena_data_parallel_gloo_world2(tmp_path):
+    world = 2
+    mp.spawn(_arena_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
