@@ -1,5 +1,7 @@
+"""Regenerates profiles/r01_summary.md from profiles/r01_launches.csv, r01_gemm_traffic.json, r01_bench.json and
+r01_kernel_table.md (run from the repo root)."""
 import json,subprocess
-ls=open('/tmp/ls.md').read()
+ls=subprocess.run(['python','scripts/launch_summary.py','profiles/r01_launches.csv'],capture_output=True,text=True).stdout
 tr=json.load(open('profiles/r01_gemm_traffic.json'))
 b=json.load(open('profiles/r01_bench.json'))
 kt=open('profiles/r01_kernel_table.md').read()
