@@ -37,8 +37,14 @@ class GraphedSegment:
         self.failed = set()
 
     def _key(self, inputs, params, extra):
-        return (tuple((tuple(t.shape), t.dtype, t.requires_grad) for t in inputs),
-                tuple((p.data_ptr(), p.requires_grad) for p in params), torch.is_grad_enabled(), extra)
+        # the parameter part (address + requires_grad of ~200 tensors) is cached per params-tuple object and re-derived
+        # when the probe (first / last address, count) changes: a module moved with .to() moves all of its storage
+        probe = (id(params), len(params), params[0].data_ptr() if params else 0, params[-1].data_ptr() if params else 0,
+                 params[-1].requires_grad if params else False)
+        cached = self.__dict__.get("_pkey")
+        if cached is None or cached[0] != probe:
+            cached = self._pkey = (probe, tuple((p.data_ptr(), p.requires_grad) for p in params), params)
+        return (tuple((tuple(t.shape), t.dtype, t.requires_grad) for t in inputs), cached[1], torch.is_grad_enabled(), extra)
 
     def run(self, fn, inputs, params, extra=()):
         """fn(*inputs, *params) -> tensor or tuple of tensors, FUNCTIONAL in both (it must not reach parameters through

@@ -427,12 +427,22 @@ class AudioTransformerEncoder(nn.Module):
             lo, hi = cuts[part], cuts[part + 1]
             cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
                        active=active[lo:hi], arena=self._arena.setdefault(part, {}), front=(part == 0))
+            params = self._part_params(part, lo, hi, front_params)
+            h = self._run_part(part, h, cfg, row_keep, params)
+        return h
+
+    def _part_params(self, part, lo, hi, front_params):
+        """the flat parameter tuple of a stack slice, built once (192 attribute look-ups through nn.Module per call
+        otherwise); the same tuple OBJECT is handed to the graph segment so that its key cache hits"""
+        cache = self.__dict__.setdefault("_pp_cache", {})
+        probe = (lo, hi, id(self.transformer.encoders[lo].self_attn.w_Q.layer.weight), id(front_params[0]))
+        ent = cache.get(part)
+        if ent is None or ent[0] != probe:
             flat = []
             for layer in self.transformer.encoders[lo:hi]:
                 flat += layer.flat()
-            params = (*front_params, *flat) if part == 0 else tuple(flat)
-            h = self._run_part(part, h, cfg, row_keep, params)
-        return h
+            ent = cache[part] = (probe, (*front_params, *flat) if part == 0 else tuple(flat))
+        return ent[1]
 
     def _run_part(self, part, x, cfg, row_keep, params):
         nf = 5 if cfg["front"] else 0
