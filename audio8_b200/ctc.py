@@ -74,3 +74,21 @@ class CTCLoss(torch.nn.Module):
         O = _offsets()
         return ctc_loss(log_prob, input_lengths, targets, target_lengths, blank=O.GO, pad=O.PAD, eos=O.EOS,
                         reduction=self.reduction_type, zero_infinity=self.zero_infinity)
+
+
+def greedy_decode(log_probs, input_lengths=None, blank=None):
+    """Best-path decode on the device: per utterance `log_probs[b, :len].argmax(-1).unique_consecutive()` with the blank
+    removed — exactly the token sequence `ctc_metrics` feeds to editdistance (reference ctc.py:161-162), without moving the
+    [B,T,V] log-probs to the host (`train.py:46`).  log_probs [B,T,V]; returns a list of B python lists of ints."""
+    if blank is None:
+        blank = _offsets().GO
+    lp = log_probs.detach()
+    if lp.dtype != torch.float32:
+        lp = lp.float()
+    il = None
+    if input_lengths is not None:
+        il = torch.as_tensor(input_lengths).to(device=lp.device, dtype=torch.int32)
+    ids, lens = ops.backend().ctc_greedy(lp, il, int(blank))
+    ids, lens = ids.cpu(), lens.cpu().tolist()
+    return [ids[b, : lens[b]].tolist() for b in range(lp.shape[0])]
+

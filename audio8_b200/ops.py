@@ -275,6 +275,16 @@ class CudaBackend:
                                             _stream()), "a8_ctc_backward")
         return grad
 
+    def ctc_greedy(self, lp, in_len, blank):
+        """lp fp32 [B,T,V] (any strides), in_len int32 [B] or None -> (ids int32 [B,T] padded with -1, lengths int32 [B])"""
+        B, T, V = lp.shape
+        assert lp.is_cuda and lp.dtype == torch.float32 and (in_len is None or in_len.dtype == torch.int32)
+        out = torch.empty(B, T, dtype=torch.int32, device=lp.device)
+        out_len = torch.empty(B, dtype=torch.int32, device=lp.device)
+        _lib.check(self.lib.a8_ctc_greedy(_ptr(lp), lp.stride(0), lp.stride(1), lp.stride(2), B, T, V, _ptr(in_len), blank,
+                                          _ptr(out), _ptr(out_len), _stream()), "a8_ctc_greedy")
+        return out, out_len
+
     # ------------------------------------------------------------------ dropout seeds
     def set_seed_source(self, t):
         """t: int64 CUDA tensor with one element (or None): added to the seed argument of every later dropout-capable

@@ -106,6 +106,11 @@ size_t a8_ctc_scratch_floats(int32_t T, int32_t B, int32_t max_S);
 /* ctc.py:193-194 on the device, sync-free: flat[] = row-major compaction of targets[B,S] (int64, strided)
  * without PAD/EOS; tgt_offsets = exclusive cumsum(target_lengths); lengths converted to int32.
  * flat has room for B*S entries, row_start is B ints of scratch. */
+/* Greedy best-path decode, the reference's only alignment (`ctc.py:161-162`: argmax(-1).unique_consecutive(), blank
+ * dropped): lp fp32 [B,T,V] with element strides, in_len int32 [B] (or NULL) -> out int32 [B,T] (decoded ids, then -1)
+ * and out_len int32 [B].  Integer result, bit-exact against the reference's ops on the same log-probs. */
+int a8_ctc_greedy(const float* lp, int64_t stride_b, int64_t stride_t, int64_t stride_v, int32_t B, int32_t T, int32_t V,
+                  const int32_t* in_len, int32_t blank, int32_t* out, int32_t* out_len, void* stream);
 int a8_ctc_prep(const int64_t* targets, int64_t stride_b, int64_t stride_s, int32_t B, int32_t S, int32_t pad,
                 int32_t eos, const int64_t* target_lengths, const int64_t* input_lengths, int32_t* flat,
                 int32_t* row_start, int32_t* tgt_offsets, int32_t* tgt_lengths, int32_t* in_lengths, void* stream);

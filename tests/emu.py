@@ -385,6 +385,19 @@ class EmuOps(EmuBackend):
         return dx, dy
 
     # ---- ctc (emulated with the installed torch op)
+    def ctc_greedy(self, lp, in_len, blank):
+        """literal restatement of ctc.py:161-162 per utterance"""
+        B, T, V = lp.shape
+        out = torch.full((B, T), -1, dtype=torch.int32)
+        lens = torch.zeros(B, dtype=torch.int32)
+        for b in range(B):
+            n = T if in_len is None else min(int(in_len[b]), T)
+            toks = lp[b, :n].argmax(dim=-1).unique_consecutive() if n > 0 else torch.zeros(0, dtype=torch.long)
+            toks = toks[toks != blank]
+            out[b, : toks.numel()] = toks.to(torch.int32)
+            lens[b] = toks.numel()
+        return out.to(lp.device), lens.to(lp.device)
+
     def ctc_prep(self, targets, pad, eos, target_lengths, input_lengths):
         keep = (targets != pad) & (targets != eos)
         flat = targets[keep].int()

@@ -90,3 +90,45 @@ def test_cuda_ctc_matches_oracle_sweep(T, B, S, V):
     for b in range(B):
         assert gr[b, il[b]:].abs().max().item() == 0 if il[b] < T else True
     assert gr.sum(-1).abs().max().item() < 1e-3
+
+
+def _greedy_reference(lp_btv, lengths, blank):
+    """the reference's own ops (ctc.py:161-162)"""
+    out = []
+    for lp, n in zip(lp_btv, lengths):
+        toks = lp[: int(n)].argmax(dim=-1).unique_consecutive()
+        out.append(toks[toks != blank].tolist())
+    return out
+
+
+def _greedy_inputs(B, T, V, seed):
+    g = torch.Generator().manual_seed(seed)
+    # peaky, run-heavy posteriors (repeats and blanks matter) with exact ties sprinkled in
+    base = torch.randint(0, V, (B, (T + 3) // 4), generator=g).repeat_interleave(4, dim=1)[:, :T]
+    lp = torch.randn(B, T, V, generator=g) * 0.3
+    lp.scatter_add_(2, base[..., None], torch.full((B, T, 1), 2.0))
+    lp[:, ::7, 3] = lp[:, ::7].max(-1).values  # ties: the first maximal index must win
+    lengths = torch.randint(T // 2, T + 1, (B,), generator=g)
+    lengths[0] = T
+    return lp.log_softmax(-1), lengths
+
+
+def test_greedy_decode_host_logic_cpu(emu_backend):
+    from audio8_b200.ctc import greedy_decode
+    lp, lengths = _greedy_inputs(3, 57, 8, 0)
+    assert greedy_decode(lp, lengths, blank=0) == _greedy_reference(lp, lengths, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V", [(4, 99, 32), (8, 749, 32), (3, 1500, 100), (2, 1, 5), (64, 750, 32)])
+def test_cuda_greedy_decode_bit_exact(B, T, V):
+    """integer alignments: identical to the reference's argmax / unique_consecutive / blank removal on the same
+    log-probs, incl. ties, ragged lengths and the non-contiguous [T,B,V] -> [B,T,V] view the trainer produces"""
+    from audio8_b200.ctc import greedy_decode
+    lp, lengths = _greedy_inputs(B, T, V, B + T)
+    want = _greedy_reference(lp, lengths, 0)
+    assert greedy_decode(lp.cuda(), lengths, blank=0) == want
+    tbv = lp.transpose(0, 1).contiguous().cuda()  # [T,B,V] storage seen as [B,T,V]
+    assert greedy_decode(tbv.transpose(0, 1), lengths.cuda(), blank=0) == want
+    assert greedy_decode(lp.cuda(), None, blank=0) == _greedy_reference(lp, [T] * B, 0)
+
