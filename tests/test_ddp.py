@@ -136,6 +136,16 @@ def _ctc_worker(rank, world, port, out_dir):
         gathered = [torch.empty_like(grads) for _ in range(world)]
         dist.all_gather(gathered, grads)
         assert torch.equal(gathered[0], gathered[1])
+        # the package's own wrapper on the same step: same averaged gradients as DistributedDataParallel
+        from audio8_b200.parallel import DataParallel
+        del ddp
+        model.zero_grad(set_to_none=True)
+        net = DataParallel(model)
+        lp, fmask = net(x, pad_mask)
+        crit(lp.transpose(1, 0), fmask.sum(-1), targets, tl).backward()
+        grads2 = torch.cat([p.grad.reshape(-1) * scale for p in model.parameters() if p.grad is not None])
+        assert grads2.shape == grads.shape
+        assert (grads2 - grads).abs().max().item() <= 1e-4 * grads.abs().max().item() + 1e-7
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
