@@ -85,7 +85,7 @@ def _pick_bn(N):
 
 # cycles of one 128 x BN x 64 k-block on the tensor pipe (BN <= 128 tiles are bound by shared-memory operand reads)
 _MMA_CLK = {64: 192, 128: 282, 192: 384, 256: 512}
-_EPI_CLK_PER_COL = {"bf16": 10, "f32": 14, "atomic": 20, "gelu": 22}
+_EPI_CLK_PER_COL = {"bf16": 10, "f32": 14, "atomic": 40, "gelu": 22}  # atomic: measured with the r01 split-K sweep
 _L2_BYTES_PER_CLK = 43.0  # measured L2 -> SM feed per SM with all SMs loading (what bounds these GEMMs)
 FORCE = {}  # experiments (scripts/gemm_bench.py): {"bn": .., "split": .., "cluster": ..}
 
@@ -115,7 +115,8 @@ def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(
                 epi_clk = _EPI_CLK_PER_COL[kind] * bn
                 main = cdiv(k_blocks, sp) * kb_clk
                 per_cta = cdiv(tiles * sp, slots)
-                cost = per_cta * max(main, epi_clk) + epi_clk + 2000 + (1500 if sp > 1 else 0) + (300 if cl > 1 else 0)
+                # ~1000 clk per tile for the accumulator hand-over and the first k-block's latency (r01 timeline traces)
+                cost = per_cta * (max(main, epi_clk) + 1000) + epi_clk + 2000 + (1500 if sp > 1 else 0) + (300 if cl > 1 else 0)
                 if best is None or cost < best[0]:
                     best = (cost, bn, sp, cl)
     bn, sp, cl = best[1], best[2], best[3]
