@@ -44,7 +44,8 @@ DRAM traffic {tr['gemm_dram_bytes_per_step']/1e9:.2f} GB per step = {tr['gemm_dr
 | host draws on a helper thread, static allocation sizes | 9.57 | 9401 | 7846 | 598 |
 | cta_group::2 pair tiles, 192-wide tiles, LayerNorm with batched loads | 8.94 | 10063 | 8546 | 619 |
 | + fast contrastive / quantizer kernels, steady host path (no reference cycles, no OpenMP wake-ups, activations released at backward) | 8.70 | 10350 | 9282 | 606 |
-| + relaxed accumulator-empty arrivals in the GEMM epilogue (final) | {b['ms_per_step']:.2f} | {b['value']:.0f} | {b['e2e']['value']:.0f} | {b['roofline']['achieved']:.0f} |
+| + relaxed accumulator-empty arrivals in the GEMM epilogue | 8.54 | 10543 | 9464 | 636 |
+| + split-K choices from the sweep, quantizer branch built before the encoder (final) | {b['ms_per_step']:.2f} | {b['value']:.0f} | {b['e2e']['value']:.0f} | {b['roofline']['achieved']:.0f} |
 
 Findings that drove the changes (all from ncu source-page stall sampling or the in-kernel clock64 timeline,
 `scripts/gemm_trace.py`):

@@ -54,7 +54,7 @@ def _worker(rank, world, port, out_dir, no_sync):
         torch.manual_seed(0)  # identical initial weights on every rank (DDP would broadcast rank 0's anyway)
         model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **TINY).train()
         loss_fn = W.create_loss(TINY["num_vq_vars"] * TINY["num_vq_groups"], 10)
-        xs = [torch.randn(2, 8000, generator=torch.Generator().manual_seed(100 + r)) * 0.1 for r in range(world)]
+        xs = [torch.randn(2, 5000, generator=torch.Generator().manual_seed(100 + r)) * 0.1 for r in range(world)]
         # expected: average over ranks of the per-rank gradients, computed locally without DDP
         want, losses = None, []
         for r in range(world):
@@ -182,7 +182,7 @@ def _arena_worker(rank, world, port, out_dir):
         gathered = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         assert torch.equal(gathered[0], gathered[1]), "parameters were not broadcast"
-        xs = [torch.randn(2, 8000, generator=torch.Generator().manual_seed(100 + r)) * 0.1 for r in range(world)]
+        xs = [torch.randn(2, 5000, generator=torch.Generator().manual_seed(100 + r)) * 0.1 for r in range(world)]
         want = None
         for r in range(world):
             _, g = _local_grads(model, loss_fn, xs[r], 7 + r)
