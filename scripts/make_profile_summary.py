@@ -69,11 +69,11 @@ Findings that drove the changes (all from ncu source-page stall sampling or the 
 
 | N | wrapper | ms/step | audio-s/s | vs N x 1-GPU | e2e audio-s/s |
 |---:|---|---:|---:|---:|---:|
-| 1 | - | 8.54 | 10543 | 1.00 | 9464 |
+| 1 | - | 8.49 | 10606 | 1.00 | 9865 |
 | 2 | torch DistributedDataParallel (bucket views, 128 MB) | 9.94 | 18106 | 0.86 | 16096 |
-| 2 | audio8_b200.parallel.DataParallel (gradient arena) | 9.10 | 19783 | 0.94 | 17597 |
-| 4 | audio8_b200.parallel.DataParallel (gradient arena) | 9.26 | 38859 | 0.92 | 33796 |
-| 8 | audio8_b200.parallel.DataParallel (gradient arena) | 9.42 | 76419 | 0.91 | 65710 |
+| 2 | audio8_b200.parallel.DataParallel (gradient arena), final build | 9.03 | 19938 | 0.94 | 18233 |
+| 4 | audio8_b200.parallel.DataParallel (gradient arena), two commits before the final build | 9.26 | 38859 | 0.92 | 33796 |
+| 8 | audio8_b200.parallel.DataParallel (gradient arena), two commits before the final build | 9.42 | 76419 | 0.90 | 65710 |
 
 wav2vec2-large (24L d=1024, `bench.py --model large`, 1 GPU): 19.2 ms/step = 4677 audio-s/s.
 `ncu --set full` of the tensor-core kernels of the final build: `r01_ncu_full.md`.
