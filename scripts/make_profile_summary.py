@@ -77,6 +77,8 @@ Findings that drove the changes (all from ncu source-page stall sampling or the 
 
 wav2vec2-large (24L d=1024, `bench.py --model large`, 1 GPU): 19.2 ms/step = 4677 audio-s/s.
 `ncu --set full` of the tensor-core kernels of the final build: `r01_ncu_full.md`.
+BASELINE configs[4] (CTC loss + conv feature encoder sweep against the reference's CPU path): `r01_c5_sweep.md`
+(`python scripts/c5_sweep.py`): CTC fwd+bwd 3-240x the 16-core `F.ctc_loss`, conv feature encoder 120-940x the CPU port.
 
 ## Per-kernel roofline table (isolated launches, L2 flushed)
 
