@@ -75,3 +75,19 @@ def test_acoustic_full_size_cuda():
     150-char targets, frozen feature encoder, time + channel masks, against the CPU oracle"""
     cfg = dict(d_model=768, num_heads=12, num_layers=12)
     model_cases.run_acoustic_generic("cuda", cfg, V=32, B=8, L=240000, S=150)
+
+
+def test_activations_released_at_backward_cpu(emu_backend):
+    """a Function's saved activations are dropped when its backward starts (a loss tensor kept across steps must not pin
+    them), so a second backward through the same graph fails loudly instead of silently reusing freed state"""
+    import torch
+    from audio8_b200 import functional as Fn
+    x = torch.randn(5, 16, requires_grad=True)
+    w = torch.randn(8, 16, requires_grad=True)
+    y = Fn.linear(x, w, None, out_f32=True)
+    ctx = y.grad_fn
+    assert ctx.saved is not None
+    y.sum().backward(retain_graph=True)
+    assert ctx.saved is None
+    with pytest.raises(RuntimeError, match="second time"):
+        y.sum().backward()
