@@ -76,6 +76,8 @@ Findings that drove the changes (all from ncu source-page stall sampling or the 
 | 8 | audio8_b200.parallel.DataParallel (gradient arena), two commits before the final build | 9.42 | 76419 | 0.90 | 65710 |
 
 wav2vec2-large (24L d=1024, `bench.py --model large`, 1 GPU): 19.2 ms/step = 4677 audio-s/s.
+wav2vec2-base CTC fine-tuning step (BASELINE configs[2] per GPU: B=8 x 15 s ragged, V=32, 150-char targets, frozen feature
+encoder, `python scripts/ctc_finetune_bench.py`): 9.38 ms/step = 12.8 k audio-s/s resident, 11.9 k with `loss.item()` every step.
 `ncu --set full` of the tensor-core kernels of the final build: `r01_ncu_full.md`.
 BASELINE configs[4] (CTC loss + conv feature encoder sweep against the reference's CPU path): `r01_c5_sweep.md`
 (`python scripts/c5_sweep.py`): CTC fwd+bwd 3-240x the 16-core `F.ctc_loss`, conv feature encoder 120-940x the CPU port.
