@@ -46,18 +46,34 @@ __global__ void __launch_bounds__(256) rows_set_kernel(__nv_bfloat16* x, const i
   }
 }
 
-// backward of rows_set: dvec += sum_i dx[idx[i], :], then dx[idx[i], :] = 0
+// backward of rows_set: dvec += sum_i dx[idx[i], :], then dx[idx[i], :] = 0.  A CTA owns RSB rows: their indices are
+// staged in shared memory and a thread's RSB loads of one channel pair are independent (the first version chased
+// index -> row -> add serially, 48 dependent round trips per thread).
+constexpr int RSB = 16;
 __global__ void __launch_bounds__(256) rows_set_bwd_kernel(__nv_bfloat16* dx, const int* idx, int n, int C,
                                                            int rows_per_block, float* dvec) {
-  const int i0 = blockIdx.x * rows_per_block, i1 = min(n, i0 + rows_per_block);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int i = i0; i < i1; ++i) {
-      __nv_bfloat16* p = dx + (long long)idx[i] * C + c;
-      acc += __bfloat162float(*p);
-      *p = __float2bfloat16(0.f);
+  __shared__ int s_idx[RSB];
+  const int i0 = blockIdx.x * RSB;
+  if (threadIdx.x < RSB) s_idx[threadIdx.x] = (i0 + threadIdx.x < n) ? idx[i0 + threadIdx.x] : -1;
+  __syncthreads();
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {  // C is even (bf16x2 accesses)
+    uint32_t w[RSB];
+#pragma unroll
+    for (int i = 0; i < RSB; ++i) {
+      const int r = s_idx[i];
+      w[i] = (r >= 0) ? *reinterpret_cast<const uint32_t*>(dx + (long long)r * C + c) : 0u;
     }
-    atomicAdd(dvec + c, acc);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < RSB; ++i) {
+      const float2 t = unpack_bf16(w[i]);
+      a0 += t.x;
+      a1 += t.y;
+      const int r = s_idx[i];
+      if (r >= 0) *reinterpret_cast<uint32_t*>(dx + (long long)r * C + c) = 0u;
+    }
+    atomicAdd(dvec + c, a0);
+    atomicAdd(dvec + c + 1, a1);
   }
 }
 
@@ -136,8 +152,8 @@ extern "C" int a8_rows_set(void* x, const int32_t* idx, int32_t n, int32_t C, co
 }
 
 extern "C" int a8_rows_set_bwd(void* dx, const int32_t* idx, int32_t n, int32_t C, float* dvec, void* stream_v) {
-  A8_REQUIRE(n > 0 && C > 0, "rows_set_bwd: empty");
-  const int rpb = 16;
+  A8_REQUIRE(n > 0 && C > 0 && C % 2 == 0, "rows_set_bwd: empty or odd channel count");
+  const int rpb = RSB;
   rows_set_bwd_kernel<<<cdiv(n, rpb), 256, 0, static_cast<cudaStream_t>(stream_v)>>>((__nv_bfloat16*)dx, idx, n, C,
                                                                                     rpb, dvec);
   return check_launch("rows_set_bwd_kernel");
