@@ -200,6 +200,22 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    # stdout carries exactly ONE line, the JSON: anything libraries print on file descriptor 1 meanwhile (NCCL's version
+    # banner, for one) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(line, flush=True)
+
+
+def _run_ours(args):
     import torch.distributed as dist
     from audio8_b200 import _lib, ops
     from audio8_b200 import wav2vec2 as W
@@ -351,6 +367,7 @@ def run_ours(args):
     barrier()
 
     out = None
+    result_line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every launch of 2 further steps
         from audio8_b200 import graphs
@@ -413,10 +430,11 @@ def run_ours(args):
                          "model_frac_of_tensor_roofline": value / world * gflop_per_audio_s / 1e3 / tf_peak},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        result_line = json.dumps(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return result_line
 
 
 def main():
