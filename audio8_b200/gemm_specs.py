@@ -95,8 +95,8 @@ def _tiling(M, N, k_blocks, batch=1, epi="bf16", allow_split=False, candidates=(
             b_k_major=False, prefer192=False):
     """(block_n, split_k, cluster) minimising a small cost model of the persistent kernel: CTAs take
     ceil(tiles / SMs) tiles each; a k-block costs max(tensor time, L2 feed time of its operand bytes); a tile costs
-    max(main loop, epilogue) because the two overlap through the TMEM accumulator ring.  cluster = 2: CTA pairs on
-    vertically adjacent tiles multicast one B tile (half the B bytes per CTA)."""
+    max(main loop, epilogue) because the two overlap through the TMEM accumulator ring.  cluster = 2: a CTA pair
+    computes one 256 x BN tile with cta_group::2 MMAs (each CTA stages half of the B tile)."""
     best = None
     m_tiles = cdiv(M, 128)
     for bn in candidates:

@@ -45,7 +45,7 @@ class GemmSpec:
         self.c_stride_lo, self.c_stride_hi = c_stride_lo, c_stride_hi
         self.act, self.z_out, self.aux, self.aux_mode = act, z_out, aux, aux_mode
         self.bias, self.bias_stride_lo, self.alpha = bias, bias_stride_lo, alpha
-        self.cluster = cluster  # 2: CTA pairs share (multicast) the B tile; needs block_n 128 or 256
+        self.cluster = cluster  # 2: CTA pair per 256 x BN tile (cta_group::2); block_n 128 / 256 (192 with a K-major B)
         self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
 
 
