@@ -3,7 +3,10 @@
 fwd+bwd of `loss_function(model, inputs)` on synthetic 16 kHz audio, B=6 x 15 s crops per GPU, dropout 0.1
 (the reference's defaults), reported as audio-seconds/sec.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload pretrain|ctc] [--model base|large]
+
+`--workload ctc` times BASELINE configs[2] instead (wav2vec2-base CTC fine-tuning step, char vocab 32, B=8 x 15 s ragged
+per GPU, 150-char targets, frozen feature encoder as train.py defaults); `--model large` configs[3].
 
 * our arm: audio8_b200 modules (hand-written sm_100a kernels through the C ABI); N>1 under torchrun with DDP/NCCL.
 * `--impl reference`: the reference algorithm on the host CPU cores (oracle port of audio8/wav2vec2.py — the
@@ -142,31 +145,103 @@ class GemmProfiler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(threads):
-    """the reference algorithm (oracle port of audio8/wav2vec2.py:377-392, 927-952) fwd+bwd on the host CPU"""
+B_CTC, S_CTC, V_CTC = 8, 150, 32  # BASELINE configs[2] per GPU
+
+
+def workload_name(args):
+    if args.workload == "ctc":
+        return "wav2vec2-base (12L d=768) CTC fine-tune fwd+bwd, char vocab 32, 150-char targets, ragged 15 s crops, frozen feature encoder, dropout 0.1"
+    m = "wav2vec2-large (24L d=1024)" if args.model == "large" else "wav2vec2-base (12L d=768)"
+    return m + " contrastive pretrain fwd+bwd, G=2 V=320 K=100, dropout 0.1"
+
+
+def metric_name(args):
+    if args.workload == "ctc":
+        return "wav2vec2-base CTC fine-tune audio-sec/sec fwd+bwd"
+    return ("wav2vec2-large" if args.model == "large" else "wav2vec2-base") + " pretrain audio-sec/sec fwd+bwd"
+
+
+def bench_config(args, world, extra=None):
+    """the `config` object shared by both arms (same keys, same workload string)"""
+    B = B_CTC if args.workload == "ctc" else B_PER_GPU
+    cfg = {"workload": workload_name(args), "batch_per_gpu": B, "crop_s": CROP_S, "global_batch": world * B,
+           "parallelism": f"dp{world}"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def ctc_batch(B, gen):
+    """synthetic fine-tuning batch: ragged utterances (70-100 % of 15 s, one full-length), 150-char targets"""
+    x = torch.randn(B, L, generator=gen) * 0.1
+    in_len = torch.randint(int(0.7 * L), L + 1, (B,), generator=gen)
+    in_len[0] = L
+    pad_mask = torch.arange(L)[None, :] < in_len[:, None]
+    x = x * pad_mask
+    targets = torch.randint(4, V_CTC, (B, S_CTC), generator=gen)
+    tl = torch.full((B,), S_CTC, dtype=torch.long)
+    return x, pad_mask, targets, tl
+
+
+def reference_step_fn(args, device="cpu", threads=None, dtype_mode="fp32"):
+    """The reference algorithm (oracle port of audio8/wav2vec2.py:377-392,927-952 / :696-770 + ctc.py:186-206), fwd+bwd,
+    dropout 0.1 as in the reference's defaults.  device="cpu": the CPU arm; device=cuda: the eager-PyTorch GPU incumbent
+    (dtype_mode fp32 | tf32 | bf16-autocast)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_ctc
     import ref_params as P
     import ref_wav2vec2 as R
-    torch.set_num_threads(threads)
-    sd = {k: v.requires_grad_(True) for k, v in P.pretrain_state_dict(seed=0).items()}
+    if threads:
+        torch.set_num_threads(threads)
+    large = args.model == "large"
+    kw = dict(d_model=1024, num_layers=24, d_ff=4096) if large else {}
+    heads, layers = (16, 24) if large else (12, 12)
+    if args.workload == "ctc":
+        sd = P.acoustic_state_dict(V_CTC, seed=0, **kw)
+    else:
+        sd = P.pretrain_state_dict(seed=0, **kw)
+    sd = {k: v.to(device).requires_grad_(True) for k, v in sd.items()}
     g = torch.Generator().manual_seed(0)
+    if device != "cpu":
+        torch.backends.cuda.matmul.allow_tf32 = dtype_mode == "tf32"
+        torch.backends.cudnn.allow_tf32 = dtype_mode == "tf32"
+    import contextlib
+    cast = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if dtype_mode == "bf16" else contextlib.nullcontext
 
-    def step(batch):
-        x = torch.randn(batch, L, generator=g) * 0.1
+    def step_pretrain(batch):
+        x = (torch.randn(batch, L, generator=g) * 0.1).to(device)
         T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
         tmask = R.create_mask((batch, T), 0.65, 10)
         Tm = int(tmask[0].sum())
-        for _ in range(12):
+        for _ in range(layers):
             np.random.random()
         idx = R.sample_negative_indices(batch, Tm, N_NEG)
-        noise = -torch.empty(batch * Tm * 2, 320).exponential_().log()
-        st = R.pretrain_loss(sd, x, tmask, idx, n_vars=N_VARS, gumbel_noise=noise)
+        noise = -torch.empty(batch * Tm * 2, 320, device=device).exponential_().log()
+        with cast():
+            st = R.pretrain_loss(sd, x, tmask, idx, n_vars=N_VARS, gumbel_noise=noise, num_heads=heads, num_layers=layers,
+                                 dropout=0.1, dropout_input=0.1, dropout_features=0.1)
         st["loss"].backward()
         for v in sd.values():
             v.grad = None
-        return st["loss"].item()
+        return st["loss"]
 
-    return step
+    def step_ctc(batch):
+        x, pad_mask, targets, tl = ctc_batch(batch, g)
+        x, pad_mask = x.to(device), pad_mask.to(device)
+        T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+        tm = R.create_mask((batch, T), 0.5, 10)
+        cm = R.create_mask((batch, 1024 if large else 768), 0.1, 64)
+        for _ in range(layers):
+            np.random.random()
+        with cast():
+            lp, fmask = R.acoustic_forward(sd, x, pad_mask, heads, layers, tm, cm, dropout=0.1, freeze_fx=True)
+        loss = ref_ctc.ctc_loss_reference(lp.float().transpose(1, 0), fmask.sum(-1).cpu(), targets.to(device), tl, 0, 1, 2)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        return loss
+
+    return step_ctc if args.workload == "ctc" else step_pretrain
 
 
 def run_reference(args):
@@ -174,28 +249,62 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    step = cpu_reference_step_fn(threads)
-    batch = 1  # bounded sample: one 15 s crop per step
+    step = reference_step_fn(args, "cpu", threads)
+    batch = B_CTC if args.workload == "ctc" else B_PER_GPU  # the arm's own per-GPU batch: same config as ours
+    # bounded sample: a probe step of one utterance sizes the batch so that the whole run stays within ~4 minutes
+    step(1)
+    t0 = time.perf_counter()
+    step(1)
+    t1 = time.perf_counter() - t0
+    batch = int(max(1, min(batch, 240.0 / (max(args.steps + args.warmup, 1) * t1))))
     for _ in range(args.warmup):
         step(batch)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step(batch)
+        step(batch).item()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = batch * CROP_S / dt
+    sample = (f"{args.steps} steps of B={batch} x {CROP_S} s (one GPU's batch) on the host CPU, {threads} threads "
+              "(oracle port of the reference algorithm, fp32, dropout 0.1)")
     out = {
-        "impl": "reference", "metric": "wav2vec2-base pretrain audio-sec/sec fwd+bwd", "value": v, "unit": "audio-s/s",
+        "impl": "reference", "metric": metric_name(args), "value": v, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the same workload as our arm's line (same model, crop length, loss), timed on a bounded sample of it
-        "config": {"workload": "wav2vec2-base (12L d=768) contrastive pretrain fwd+bwd, G=2 V=320 K=100, dropout 0.1",
-                   "crop_s": CROP_S, "sample": f"B={batch} utterance per step on the host cores; dropout 0 in the oracle port "
-                   "(dropout does not change the arithmetic cost)"},
-        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of B={batch} x {CROP_S} s on the host CPU (oracle port, fp32)"},
+        "config": bench_config(args, max(args.gpus, 1)),
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
+
+
+def gpu_incumbent(args, dev, B):
+    """SURVEY §8d's 'honest GPU incumbent': the reference algorithm (oracle port, plain eager PyTorch: cuDNN convs, cuBLAS
+    matmuls, ATen softmax/LayerNorm/CTC) on the same B200, same batch, CUDA events; informational."""
+    out = {}
+    for mode in ("fp32", "tf32", "bf16"):
+        try:
+            step = reference_step_fn(args, str(dev), None, mode)
+            for _ in range(2):
+                step(B)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                step(B)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out[mode] = {"ms_per_step": ms, "value": B * CROP_S / (ms * 1e-3), "unit": "audio-s/s"}
+        except Exception as e:  # informational leg: never takes the bench line down
+            out[mode] = {"error": repr(e)[:200]}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = True
+            torch.cuda.empty_cache()
+    out["what"] = ("oracle port of the reference modules under eager PyTorch on this GPU (fp32 with TF32 off / TF32 on / "
+                   f"bf16 autocast), B={B} x {CROP_S} s, dropout 0.1, 5 steps after 2 warm-up, CUDA events; host draws included")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -234,12 +343,20 @@ def _run_ours(args):
     torch.manual_seed(1234 + rank)
     np.random.seed(1234 + rank)
 
-    if args.model == "large":  # BASELINE configs[3]: wav2vec2-large widths (final_dim 256 as through pretrain.py's CLI)
-        model = W.create_model(d_model=1024, num_heads=16, num_layers=24, d_ff=4096).to(dev)
-        model_name, gflop_per_audio_s = "wav2vec2-large (24L d=1024)", 3 * 39.8
-    else:  # the headline: wav2vec2-base defaults, 12L d=768, dropout 0.1, G=2 V=320
-        model = W.create_model().to(dev)
-        model_name, gflop_per_audio_s = "wav2vec2-base (12L d=768)", GFLOP_PER_AUDIO_S
+    os.environ.setdefault("A8_GRAPH_STRICT", "1")  # a failed CUDA-graph capture must fail the bench, not slow it down
+    ctc = args.workload == "ctc"
+    large = args.model == "large"
+    mkw = dict(d_model=1024, num_heads=16, num_layers=24, d_ff=4096) if large else {}
+    # algorithmic fwd+bwd GFLOP per audio-second; CTC fine-tuning: the frozen conv stack counts once
+    gflop_per_audio_s = (3 * 39.8 if large else GFLOP_PER_AUDIO_S) if not ctc else (46.0 - 2 * 0.32 * 15.3)
+    if ctc:  # BASELINE configs[2]: create_acoustic_model(32) as train.py builds it (freeze_fx=True), encoder trainable
+        from audio8_b200.ctc import CTCLoss, Offsets
+        Offsets.GO, Offsets.PAD = 0, 1  # train.py:22-27
+        model = W.create_acoustic_model(V_CTC, **mkw).to(dev)
+        model.freeze = False
+        crit = CTCLoss()
+    else:  # the headline: wav2vec2-base defaults, 12L d=768, dropout 0.1, G=2 V=320 (BASELINE configs[1]; large = configs[3])
+        model = W.create_model(**mkw).to(dev)
     model.train()
     loss_fn = W.create_loss(N_VARS, N_NEG)
     net = model
@@ -253,36 +370,59 @@ def _run_ours(args):
                 bucket_cap_mb=int(os.environ.get("A8_DDP_BUCKET_MB", "128")))
             dp_name = "torch DistributedDataParallel (bucket views, 128 MB buckets)"
         else:
-            # the package's data-parallel wrapper: transformer-layer gradients are written into one contiguous arena and
-            # all-reduced in place under the conv stack's backward (audio8_b200/parallel.py); same interface as DDP
+            # the package's data-parallel wrapper: gradients are written into one contiguous arena and all-reduced in
+            # place under the rest of backward (audio8_b200/parallel.py); same interface as DDP
             from audio8_b200.parallel import DataParallel
             net = DataParallel(model)
             dp_name = "audio8_b200.parallel.DataParallel (gradient arena, in-place NCCL all-reduce)"
-    B = B_PER_GPU
+    B = B_CTC if ctc else B_PER_GPU
     lib = _lib.load()
-    x_dev = torch.randn(B, L, device=dev) * 0.1
-    x_host = (torch.randn(B, L) * 0.1).pin_memory()
+    gen = torch.Generator().manual_seed(1234 + rank)
+    params = [p for p in model.parameters()]
+    if ctc:
+        xh, pmh, tgh, tlh = ctc_batch(B, gen)
+        host_in = tuple(t.pin_memory() for t in (xh, pmh, tgh))
+        dev_in = tuple(t.to(dev) for t in host_in)
+        h2d_bytes = sum(t.numel() * t.element_size() for t in host_in)
 
-    def step(x, module=None):
-        loss = loss_fn(net if module is None else module, x)
-        loss.backward()
-        for p in model.parameters():
-            p.grad = None
-        return loss
+        def step(inp, module=None):
+            x, pm, tg = inp
+            lp, fmask = (net if module is None else module)(x, pm)
+            loss = crit(lp.transpose(1, 0), fmask.sum(-1), tg, tlh)
+            loss.backward()
+            for p in params:
+                p.grad = None
+            return loss
+    else:
+        dev_in = (torch.randn(B, L, device=dev) * 0.1,)
+        host_in = ((torch.randn(B, L, generator=gen) * 0.1).pin_memory(),)
+        h2d_bytes = B * L * 4
+
+        def step(inp, module=None):
+            loss = loss_fn(net if module is None else module, inp[0])
+            loss.backward()
+            for p in params:
+                p.grad = None
+            return loss
+
+    def upload():
+        return tuple(t.to(dev, non_blocking=True) for t in host_in)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_warm = max(args.warmup, 3) + 12  # graph capture happens on the 2nd step; the masked-row count varies per step,
-    for _ in range(n_warm - 2):         # so torch's caching allocator needs ~10 steps before it stops calling cudaMalloc
-        step(x_dev)
+    # set-up steps, NOT the warm-up the caller asked for: CUDA-graph capture happens on the 2nd step and torch's caching
+    # allocator needs ~10 steps of varying masked-row counts before it stops calling cudaMalloc; reported as extra_warmup
+    extra_warm = 12
+    for _ in range(extra_warm):
+        step(dev_in)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    for _ in range(2):
-        step(x_dev)
+    for _ in range(args.warmup):  # the W untimed warm-up steps of the contract
+        step(dev_in)
     # Python's cyclic GC: a full (generation-2) collection walks every live object of the process (~100 ms with torch
     # loaded) and lands inside whichever step happens to trip its allocation counter.  Like Megatron-style trainers do,
     # freeze what exists after warm-up and collect by hand between the timed regions, not inside them.
@@ -296,10 +436,10 @@ def _run_ours(args):
         if eager:
             from audio8_b200 import graphs
             graphs.set_enabled(False)
-            step(x_dev)
+            step(dev_in)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(x_dev)
+        step(dev_in)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -311,7 +451,7 @@ def _run_ours(args):
     e0.record()
     for _ in range(args.steps):
         th = time.perf_counter()
-        step(x_dev)
+        step(dev_in)
         host_t.append((time.perf_counter() - th) * 1e3)
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
@@ -339,7 +479,7 @@ def _run_ours(args):
     gc.collect()
     barrier()
     for _ in range(8):  # this loop's own warm-up: the per-step input tensor changes the allocator's request sequence
-        loss = step(x_host.to(dev, non_blocking=True))  # same statement shape as the timed loop (object lifetimes)
+        loss = step(upload())  # same statement shape as the timed loop (object lifetimes)
         loss_val = loss.item()
     gc.collect()
     barrier()
@@ -347,7 +487,7 @@ def _run_ours(args):
     e2e_t = []
     for _ in range(args.steps):
         ts = time.perf_counter()
-        loss = step(x_host.to(dev, non_blocking=True))
+        loss = step(upload())
         loss_val = loss.item()
         e2e_t.append((time.perf_counter() - ts) * 1e3)
     if rank == 0:
@@ -362,7 +502,7 @@ def _run_ours(args):
     gc.collect()
     barrier()
     t0 = time.perf_counter()
-    step(x_dev)
+    step(dev_in)
     host_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
@@ -374,47 +514,54 @@ def _run_ours(args):
         graphs.set_enabled(False)  # single launches cannot be bracketed inside a graph replay: eager for these 2 steps
         # rank 0 only: these steps run on the bare module (a DDP-wrapped step here would wait for the other ranks'
         # all-reduce forever)
-        step(x_dev, model)
+        step(dev_in, model)
         prof = GemmProfiler()
         ops.backend().profiler = prof
         for _ in range(2):
-            step(x_dev, model)
+            step(dev_in, model)
         gemm_ms, gemm_flops, n_gemm = prof.summary()
         ops.backend().profiler = None
         graphs.set_enabled(True)
         tf_peak, hbm_peak, which = peaks()
         traffic, traffic_src = None, None  # DRAM bytes per GEMM launch from the committed ncu capture (profiles/)
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-                tr = json.load(f)
-            traffic = tr["gemm_dram_bytes_per_launch"]  # bytes per launch, like `achieved` is per launch
-            traffic_src = tr["source"]
-        except Exception:
-            pass
+        for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    tr = json.load(f)
+                traffic = tr["gemm_dram_bytes_per_launch"]  # bytes per launch, like `achieved` is per launch
+                traffic_src = tr["source"]
+                break
+            except Exception:
+                pass
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
-        cpu = None
+        cpu = incumbent = None
+        if world == 1 and not args.no_incumbent:
+            incumbent = gpu_incumbent(args, dev, B)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cstep = cpu_reference_step_fn(threads)
-            cstep(1)
+            cstep = reference_step_fn(args, "cpu", threads)
+            cb = 2
+            cstep(cb)  # 1 warm-up, then 3 timed steps
             t0 = time.perf_counter()
-            reps = 2
+            reps = 3
             for _ in range(reps):
-                cstep(1)
+                cstep(cb).item()
             cdt = (time.perf_counter() - t0) / reps
-            cpu = {"value": CROP_S / cdt, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                   "sample": f"{reps} steps of B=1 x {CROP_S} s (oracle port of the reference algorithm, fp32, dropout 0)"}
+            cpu = {"value": cb * CROP_S / cdt, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                   "sample": f"{reps} steps of B={cb} x {CROP_S} s after 1 warm-up (oracle port of the reference algorithm, "
+                             "fp32, dropout 0.1)"}
         out = {
-            "metric": "wav2vec2-base pretrain audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s",
-            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step,
+            "metric": metric_name(args), "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "extra_warmup": extra_warm,
+            "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": model_name + " contrastive pretrain fwd+bwd, G=2 V=320 K=100, dropout 0.1",
-                       "batch_per_gpu": B, "crop_s": CROP_S, "global_batch": world * B, "parallelism": f"dp{world}", "data_parallel": dp_name,
-                       "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                       "launch": "conv/encoder segments replayed as CUDA graphs (fwd and bwd), the rest eager",
-                       "gc": "gc.freeze() after warm-up (full collections no longer walk the long-lived heap)"},
-            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": 4,
+            "config": bench_config(args, world, {
+                "data_parallel": dp_name,
+                "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                "launch": "conv/encoder segments replayed as CUDA graphs (fwd and bwd), the rest eager",
+                "gc": "gc.freeze() after warm-up (full collections no longer walk the long-lived heap)"}),
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "last_loss": loss_val},
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
@@ -429,6 +576,7 @@ def _run_ours(args):
                          "measured_on": "2 extra eager steps after the timed region, CUDA events around each launch",
                          "model_frac_of_tensor_roofline": value / world * gflop_per_audio_s / 1e3 / tf_peak},
             "cpu_baseline": cpu,
+            "gpu_incumbent": incumbent,
         }
         result_line = json.dumps(out)
     if world > 1:
@@ -444,6 +592,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the eager-PyTorch GPU incumbent leg")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "ctc"],
+                    help="pretrain = BASELINE configs[1] (the driver's line); ctc = configs[2] (CTC fine-tuning step)")
     ap.add_argument("--model", default="base", choices=["base", "large"],
                     help="base = the headline workload (BASELINE configs[1]); large = configs[3] (not the driver's line)")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (cudaProfilerStart/Stop) and exit")

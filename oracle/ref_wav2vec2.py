@@ -8,7 +8,10 @@ indices) as an explicit argument so parity tests can share them with the CUDA pa
 Pinned by `oracle/gen_golden.py` against the UNMODIFIED `/root/reference/audio8/wav2vec2.py` run in the dev
 container (fixtures in `tests/golden/`).  The `eight_mile` pieces (transformer layer order, LN eps 1e-6, pad
 split 63/64) are recalled — parity unpinned at that boundary (see `eight_mile_compat.py`).
-Dropout is not restated: parity runs use p = 0 (SURVEY §8c protocol).
+Dropout (torch's own F.dropout, at the reference's five sites) and LayerDrop (an explicit list of active layers)
+are optional arguments, off by default: exact parity runs use p = 0 (SURVEY §8c protocol); the statistical
+dropout test and the GPU-incumbent timing in bench.py switch them on.  Every function follows the device of its
+tensor arguments (the GPU-incumbent leg of bench.py runs this same code on `cuda`).
 """
 import math
 import numpy as np
@@ -109,7 +112,11 @@ def pos_conv_weight(sd, prefix):
     return g * v / v.norm(2, dim=(0, 1), keepdim=True)
 
 
-def transformer_layer(sd, pre, x, num_heads, key_mask=None):
+def _drop(x, p):
+    return F.dropout(x, p, True) if p > 0 else x
+
+
+def transformer_layer(sd, pre, x, num_heads, key_mask=None, pdrop=0.0):
     """eight_mile TransformerEncoder with layer_norms_after=True [RECALLED; structure per wav2vec2.py:110-126]:
     x = ln2(x + MHA(x)); x = ln1(x + FFN(x)).  key_mask: bool [B,T], False = padded key."""
     B, T, D = x.shape
@@ -120,15 +127,17 @@ def transformer_layer(sd, pre, x, num_heads, key_mask=None):
     s = q @ k.transpose(-1, -2) / math.sqrt(dk)
     if key_mask is not None:
         s = s.masked_fill(~key_mask[:, None, None, :], -1e9)
-    a = torch.softmax(s, -1) @ v
+    a = _drop(torch.softmax(s, -1), pdrop) @ v  # eight_mile SeqScaledDotProductAttention: dropout on the probabilities
     a = a.transpose(1, 2).reshape(B, T, D)
-    x = _ln(sd, pre + "ln2", x + _lin(sd, pre + "self_attn.w_O.layer", a), LN_EPS_8MILE)
+    x = _ln(sd, pre + "ln2", x + _drop(_lin(sd, pre + "self_attn.w_O.layer", a), pdrop), LN_EPS_8MILE)
     f = _lin(sd, pre + "ffn.3.layer", F.gelu(_lin(sd, pre + "ffn.0.layer", x)))
-    return _ln(sd, pre + "ln1", x + f, LN_EPS_8MILE)
+    return _ln(sd, pre + "ln1", x + _drop(f, pdrop), LN_EPS_8MILE)
 
 
-def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", pad_mask=None, groups=16):
-    """wav2vec2.py:629-646 with dropout off: zero padded frames, x += gelu(pos_conv(x)), LN, transformer stack."""
+def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", pad_mask=None, groups=16, pdrop=0.0,
+                              active_layers=None):
+    """wav2vec2.py:629-646: zero padded frames, x += gelu(pos_conv(x)), LN, dropout, transformer stack.
+    active_layers: LayerDrop outcome, one bool per layer (eight_mile skips a layer when its draw < layer_drop)."""
     if pad_mask is not None:
         x = x.masked_fill(~pad_mask[..., None], 0.0)
     w = pos_conv_weight(sd, prefix)
@@ -137,9 +146,11 @@ def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", p
     start_pad = end_pad - 1 if k % 2 == 0 else end_pad
     xc = F.conv1d(F.pad(x.transpose(1, 2), (start_pad, end_pad)), w, sd[prefix + "pos_conv.conv.1.bias"], groups=groups)
     x = x + F.gelu(xc).transpose(1, 2)
-    x = _ln(sd, prefix + "ln", x, LN_EPS_TORCH)
+    x = _drop(_ln(sd, prefix + "ln", x, LN_EPS_TORCH), pdrop)
     for i in range(num_layers):
-        x = transformer_layer(sd, f"{prefix}transformer.encoders.{i}.", x, num_heads, pad_mask)
+        if active_layers is not None and not active_layers[i]:
+            continue
+        x = transformer_layer(sd, f"{prefix}transformer.encoders.{i}.", x, num_heads, pad_mask, pdrop)
     return x
 
 
@@ -155,11 +166,11 @@ def gumbel_quantizer(sd, y, num_groups, tau=0.5, gumbel_noise=None, prefix="quan
     if gumbel_noise is not None:
         u = (z + gumbel_noise) / tau
         soft = torch.softmax(u, -1)
-        k = soft.argmax(-1) if force_idx is None else torch.as_tensor(force_idx).long()
+        k = soft.argmax(-1) if force_idx is None else torch.as_tensor(force_idx).long().to(z.device)
         hard = torch.zeros_like(z).scatter_(-1, k[:, None], 1.0)
         onehot = hard - soft.detach() + soft  # straight-through (torch F.gumbel_softmax hard=True)
     else:
-        k = z.argmax(-1) if force_idx is None else torch.as_tensor(force_idx).long()
+        k = z.argmax(-1) if force_idx is None else torch.as_tensor(force_idx).long().to(z.device)
         onehot = torch.zeros_like(z).scatter_(-1, k[:, None], 1.0)
     ppl = torch.exp(-torch.sum(avg_probs * torch.log(avg_probs + 1e-7)))  # wav2vec2.py:565
     vars_ = sd[prefix + "vars"]  # [1, G*V, var_dim]
@@ -172,29 +183,31 @@ def contrastive_loss(x_masked, y, neg_idx, ppl, n_vars):
     neg_idx [B,K*Tm] (already offset).  loss = 0.1*CE(cos-sim logits, class 0) + 10*(n_vars-ppl)/n_vars."""
     B, Tm, C = y.shape
     K = neg_idx.shape[1] // Tm
-    negs = y.reshape(-1, C)[torch.as_tensor(neg_idx).reshape(-1)].view(B, Tm, K, C).permute(2, 0, 1, 3)
+    negs = y.reshape(-1, C)[torch.as_tensor(neg_idx).reshape(-1).to(y.device)].view(B, Tm, K, C).permute(2, 0, 1, 3)
     targets = torch.cat([y.unsqueeze(0), negs], 0)
     logits = torch.cosine_similarity(x_masked.unsqueeze(0), targets, dim=-1)  # [K+1,B,Tm]
     logits = logits.transpose(2, 0).reshape(-1, K + 1)
-    ce = F.cross_entropy(logits, torch.zeros(logits.shape[0], dtype=torch.long))
+    ce = F.cross_entropy(logits, torch.zeros(logits.shape[0], dtype=torch.long, device=logits.device))
     return XE_WGT * ce + DIVERSITY_WGT * (n_vars - ppl) / n_vars, ce
 
 
 # ------------------------------------------------------------------------------------------------
-# whole-model forwards (dropout off)
+# whole-model forwards
 # ------------------------------------------------------------------------------------------------
 def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2, tau=0.5, gumbel_noise=None,
-                     conv_features=CONV_FEATURES[16], force_idx=None):
+                     conv_features=CONV_FEATURES[16], force_idx=None, dropout=0.0, dropout_input=0.0,
+                     dropout_features=0.0, active_layers=None):
     """Wav2Vec2Model.forward (wav2vec2.py:927-952) with the time mask supplied.  Returns a dict of stages."""
     fx = conv_feature_extractor(sd, x, conv_features=conv_features).transpose(1, 2)
     feats = _ln(sd, "layer_norm", fx, LN_EPS_TORCH)
     unmasked = feats
-    h = _lin(sd, "proj_to_input.layer", feats)
+    h = _drop(_lin(sd, "proj_to_input.layer", feats), dropout_input)
+    unmasked = _drop(unmasked, dropout_features)
     B, T, _ = h.shape
-    tm = torch.as_tensor(time_mask)
+    tm = torch.as_tensor(time_mask).to(h.device)
     h = torch.where(tm[..., None], sd["mask_emb"].expand_as(h), h)
     y_in = unmasked[tm].view(B, -1, unmasked.shape[-1])
-    enc = audio_transformer_encoder(sd, h, num_heads, num_layers)
+    enc = audio_transformer_encoder(sd, h, num_heads, num_layers, pdrop=dropout, active_layers=active_layers)
     q, ppl, k = gumbel_quantizer(sd, y_in, num_groups, tau, gumbel_noise, force_idx=force_idx)
     y = _lin(sd, "project_q.layer", q)
     xo = _lin(sd, "final_proj.layer", enc)
@@ -204,7 +217,7 @@ def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2
 def pretrain_loss(sd, x, time_mask, neg_idx, n_vars=640, **kw):
     """Wav2Vec2Loss.__call__ (wav2vec2.py:377-392) with the random draws supplied."""
     st = pretrain_forward(sd, x, time_mask, **kw)
-    tm = torch.as_tensor(time_mask)
+    tm = torch.as_tensor(time_mask).to(x.device)
     B = x.shape[0]
     xm = st["x"][tm].view(B, -1, st["x"].shape[-1])
     loss, ce = contrastive_loss(xm, st["y"], neg_idx, st["ppl"], n_vars)
@@ -213,19 +226,22 @@ def pretrain_loss(sd, x, time_mask, neg_idx, n_vars=640, **kw):
 
 
 def acoustic_forward(sd, x, pad_mask, num_heads=12, num_layers=12, time_mask=None, channel_mask=None,
-                     conv_features=CONV_FEATURES[16]):
+                     conv_features=CONV_FEATURES[16], dropout=0.0, dropout_input=0.0, active_layers=None,
+                     freeze_fx=False):
     """Wav2Vec2AcousticModel.forward (wav2vec2.py:765-770) over Wav2Vec2Encoder.forward (:696-723).
     time_mask / channel_mask: the training-time masks (None = eval).  Returns (log_probs [B,T,V], frame_mask)."""
     p = "encoder."
-    fx = conv_feature_extractor(sd, x, prefix=p + "feature_extractor.", conv_features=conv_features).transpose(1, 2)
+    with torch.no_grad() if freeze_fx else torch.enable_grad():
+        fx = conv_feature_extractor(sd, x, prefix=p + "feature_extractor.", conv_features=conv_features).transpose(1, 2)
     feats = _ln(sd, p + "layer_norm", fx, LN_EPS_TORCH)
     T = feats.shape[1]
     fmask = frame_mask_from_sample_mask(pad_mask, T) if pad_mask is not None else None
-    h = _lin(sd, p + "proj_to_input.layer", feats)
+    h = _drop(_lin(sd, p + "proj_to_input.layer", feats), dropout_input)
     if time_mask is not None:
-        h = torch.where(torch.as_tensor(time_mask)[..., None], sd[p + "mask_emb"].expand_as(h), h)
+        h = torch.where(torch.as_tensor(time_mask).to(h.device)[..., None], sd[p + "mask_emb"].expand_as(h), h)
     if channel_mask is not None:
-        h = h.masked_fill(torch.as_tensor(channel_mask)[:, None, :], 0.0)
-    enc = audio_transformer_encoder(sd, h, num_heads, num_layers, prefix=p + "encoder.", pad_mask=fmask)
+        h = h.masked_fill(torch.as_tensor(channel_mask).to(h.device)[:, None, :], 0.0)
+    enc = audio_transformer_encoder(sd, h, num_heads, num_layers, prefix=p + "encoder.", pad_mask=fmask, pdrop=dropout,
+                                    active_layers=active_layers)
     logits = _lin(sd, "proj", enc)
     return F.log_softmax(logits, -1), fmask
