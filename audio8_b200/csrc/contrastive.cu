@@ -309,8 +309,11 @@ extern "C" int a8_contrastive_fwd(const float* x, const float* y, const int32_t*
   int rc = check_launch("row_norm_kernel");
   if (rc) return rc;
   ConArgs a{x, y, idx, xn, yn, R, C, K, cosv, prob, row_loss, nullptr, nullptr, nullptr};
-  if (!launch_contrastive_fast<false>(a, st))
+  if (!launch_contrastive_fast<false>(a, st)) {
+    // the generic kernel holds 32 * CPL channels per row: wider rows exist only on the fast path
+    A8_REQUIRE(C <= 32 * CPL, "contrastive: C=%d needs the vectorised path (16-byte aligned x/y, K <= ~760)", C);
     contrastive_fwd_kernel<<<con_grid(R), 256, 8 * (K + 1) * sizeof(float), st>>>(a);
+  }
   rc = check_launch("contrastive_fwd_kernel");
   if (rc) return rc;
   contrastive_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, R, ppl, n_vars, xe_w, div_w, ce, loss);
@@ -324,6 +327,9 @@ extern "C" int a8_contrastive_bwd(const float* x, const float* y, const int32_t*
   A8_REQUIRE(R > 0 && C > 0 && (C <= 32 * CPL || C == 768) && K >= 0, "contrastive_bwd: unsupported shape");
   A8_CUDA(cudaMemsetAsync(dy, 0, sizeof(float) * (size_t)R * C, st));
   ConArgs a{x, y, idx, xn, yn, R, C, K, const_cast<float*>(cosv), const_cast<float*>(prob), nullptr, dce, dx, dy};
-  if (!launch_contrastive_fast<true>(a, st)) contrastive_bwd_kernel<<<con_grid(R), 256, 0, st>>>(a);
+  if (!launch_contrastive_fast<true>(a, st)) {
+    A8_REQUIRE(C <= 32 * CPL, "contrastive_bwd: C=%d needs the vectorised path (16-byte aligned tensors, K <= ~500)", C);
+    contrastive_bwd_kernel<<<con_grid(R), 256, 0, st>>>(a);
+  }
   return check_launch("contrastive_bwd_kernel");
 }

@@ -61,6 +61,29 @@ def _zeros(shape, dtype, like, dynamic=False):
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
+def _grad_zeros(key, shape, like):
+    """zeroed fp32 buffer for a parameter gradient: the parameter's own block of the data-parallel wrapper's gradient
+    arena when one is active for this backward (parallel.py: the gradient is then reduced in place), else a fresh one"""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    buf = ops.grad_arena_take(key, n) if key is not None else None
+    if buf is None:
+        return torch.zeros(shape, dtype=F32, device=like.device)
+    return buf.view(shape)
+
+
+def _grad_empty(key, shape, like):
+    """same, for gradients that are fully overwritten by their kernel (no zero fill)"""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    buf = ops.grad_arena_take(key, n, zero=False) if key is not None else None
+    if buf is None:
+        return torch.empty(shape, dtype=F32, device=like.device)
+    return buf.view(shape)
+
+
 def _bf16(t):
     """bf16 contiguous copy of a tensor through the cast kernel (parameters are fp32 masters)"""
     t = t.detach()
@@ -72,7 +95,17 @@ def _bf16(t):
 # =================================================================================================
 # Linear  (nn.Linear / eight_mile Dense: wav2vec2.py:932,950,951,762)
 # =================================================================================================
+def _pad_rows8(t, n8):
+    """[N, ...] -> [n8, ...] with zero rows appended (the tcgen05 GEMM wants N % 8 == 0: 16-byte TMA strides / stores)"""
+    out = torch.zeros((n8,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
+
+
 class LinearFn(torch.autograd.Function):
+    """An output width that is not a multiple of 8 (e.g. a CTC head over a 29- or 37-symbol vocabulary, train.py's
+    `len(vocab)`) runs zero-padded to the next multiple and is sliced back: the reference works for any width."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, out_f32):
         be = _be()
@@ -81,28 +114,40 @@ class LinearFn(torch.autograd.Function):
         xb = _bf16(x2)
         wb = _bf16(weight)
         N = weight.shape[0]
-        out = _empty((x2.shape[0], N), F32 if out_f32 else BF16, x, dynamic=True)
-        be.gemm(G.linear_fwd(xb, wb, out, bias.detach() if bias is not None else None,
-                             c_dtype=OUT_F32 if out_f32 else OUT_BF16))
-        ctx.saved = (xb, wb, x.dtype, shp, bias is not None)
-        return out.view(*shp[:-1], N)
+        N8 = (N + 7) // 8 * 8
+        bvec = bias.detach() if bias is not None else None
+        if N8 != N:
+            wb = _pad_rows8(wb, N8)
+            bvec = _pad_rows8(bvec.float(), N8) if bvec is not None else None
+        out = _empty((x2.shape[0], N8), F32 if out_f32 else BF16, x, dynamic=True)
+        be.gemm(G.linear_fwd(xb, wb, out, bvec, c_dtype=OUT_F32 if out_f32 else OUT_BF16))
+        ctx.saved = (xb, wb, x.dtype, shp, bias is not None, N, ops.grad_key(weight), ops.grad_key(bias))
+        if N8 != N:
+            out = out[:, :N]
+        return out.reshape(*shp[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
         be = _be()
-        xb, wb, xdtype, shp, has_bias = _take_saved(ctx)
-        N, K = wb.shape
-        dyb = _bf16(dy.reshape(-1, N))
+        xb, wb, xdtype, shp, has_bias, N, wkey, bkey = _take_saved(ctx)
+        N8, K = wb.shape
+        dy2 = dy.reshape(-1, N)
+        if N8 != N:
+            dyp = torch.zeros((dy2.shape[0], N8), dtype=dy2.dtype, device=dy2.device)
+            dyp[:, :N] = dy2
+            dy2 = dyp
+        dyb = _bf16(dy2)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = _empty(xb.shape, xdtype, xb, dynamic=True)
             be.gemm(G.linear_dgrad(dyb, wb, dx, c_dtype=OUT_F32 if xdtype == F32 else OUT_BF16))
             dx = dx.view(shp)
         if ctx.needs_input_grad[1]:
-            dw = _zeros((N, K), F32, xb)
+            dw = _grad_zeros(wkey, (N8, K), xb) if N8 == N else _zeros((N8, K), F32, xb)
             be.gemm(G.linear_wgrad(dyb, xb, dw))
+            dw = dw[:N]
         if has_bias and ctx.needs_input_grad[2]:
-            db = be.colsum(dyb)
+            db = be.colsum(dyb, out=_grad_zeros(bkey, (N8,), xb) if N8 == N else None)[:N]
         return dx, dw, db, None
 
 
@@ -121,7 +166,7 @@ class LayerNormFn(torch.autograd.Function):
         be = _be()
         xb = _bf16(x)
         y, yf, s, mean, rstd = be.layernorm_fwd(xb, gamma.detach(), beta.detach(), eps, want_f32=want_f32)
-        ctx.saved = (s, mean, rstd, gamma.detach(), x.dtype)
+        ctx.saved = (s, mean, rstd, gamma.detach(), x.dtype, ops.grad_key(gamma), ops.grad_key(beta))
         if want_f32:
             return y, yf
         return y
@@ -129,11 +174,13 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, dyf=None):
         be = _be()
-        s, mean, rstd, gamma, xdtype = _take_saved(ctx)
+        s, mean, rstd, gamma, xdtype, gkey, bkey = _take_saved(ctx)
         if dy is None:
             dy = _zeros(s.shape, BF16, s)
+        C = s.shape[-1]
         ds, _, dg, db, _ = be.layernorm_bwd(_bf16(dy), s, mean, rstd, gamma,
-                                            dy_f32=dyf.contiguous() if dyf is not None else None)
+                                            dy_f32=dyf.contiguous() if dyf is not None else None,
+                                            dg_out=_grad_zeros(gkey, (C,), s), db_out=_grad_zeros(bkey, (C,), s))
         return ds.to(xdtype), dg, db, None, None
 
 
@@ -180,12 +227,14 @@ class RowsSetFn(torch.autograd.Function):
         out = x.detach().clone()
         _be().rows_set(out.view(-1, out.shape[-1]), idx, vec.detach().float().contiguous())
         ctx.idx = idx
+        ctx.vkey = ops.grad_key(vec)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         dx = dy.clone().contiguous()
-        dvec = _be().rows_set_bwd(dx.view(-1, dx.shape[-1]), ctx.idx)
+        C = dx.shape[-1]
+        dvec = _be().rows_set_bwd(dx.view(-1, C), ctx.idx, out=_grad_zeros(ctx.vkey, (C,), dx))
         return dx, None, dvec
 
 
@@ -259,13 +308,14 @@ class ConvFeatureFn(torch.autograd.Function):
             # never keep a RETURNED tensor object in ctx: its grad_fn is this node, and the reference cycle would hold
             # every saved activation until Python's cyclic GC runs (a detached alias shares the storage, not the cycle)
             acts[-1] = a.detach()
-            ctx.saved = (x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec)
+            keys = [ops.grad_key(w) for w in weights] + [ops.grad_key(gn_w), ops.grad_key(gn_b)]
+            ctx.saved = (x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec, keys)
         return a
 
     @staticmethod
     def backward(ctx, dy):
         be = _be()
-        x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec = _take_saved(ctx)
+        x, w0, gw, gb, mean, rstd, mom, acts, zs, wts, spec, keys = _take_saved(ctx)
         n = len(spec)
         grads = [None] * n
         if n > 1:
@@ -276,7 +326,7 @@ class ConvFeatureFn(torch.autograd.Function):
                 Cin = a_prev.shape[2]
                 dwk = _zeros((c, k * Cin), F32, a_prev)
                 be.gemm(G.conv_wgrad(dz, a_prev, dwk, k, s))
-                grads[i] = be.conv_unpack(dwk, Cin, k)
+                grads[i] = be.conv_unpack(dwk, Cin, k, out=_grad_empty(keys[i], (c, Cin, k), a_prev))
                 dprev = _empty(a_prev.shape, BF16, a_prev)
                 for p in range(s):
                     be.gemm(G.conv_dgrad(dz, wts[i][p], dprev, k, s, p, aux=zs[i - 1] if i > 1 else None))
@@ -286,7 +336,8 @@ class ConvFeatureFn(torch.autograd.Function):
         else:
             da0 = _bf16(dy)
         (c0, k0, s0) = spec[0]
-        dw0, dg, db = be.conv0_bwd(x, w0, gw, gb, mean, rstd, mom, k0, s0, da0)
+        dest = (_grad_empty(keys[0], (c0, k0), x), _grad_empty(keys[n], (c0,), x), _grad_empty(keys[n + 1], (c0,), x))
+        dw0, dg, db = be.conv0_bwd(x, w0, gw, gb, mean, rstd, mom, k0, s0, da0, out=dest)
         grads[0] = dw0.view(c0, 1, k0)
         return (None, None, dg, db, *grads)
 
@@ -400,14 +451,31 @@ class EncoderFn(torch.autograd.Function):
             if need_grad:
                 layers.append(dict(xin=x2d, qkv=qkv, lse=lse, ctx=ctxv, s1=s1, mean2=mean2, rstd2=rstd2, x1=x1,
                                    z1=z1, hid=hid, s2=s2, mean1=mean1, rstd1=rstd1, seeds=(seed_a, seed1, seed2),
-                                   w=(wqkv_b, wo_b, w1_b, w2_b), ln=(g2, g1)))
+                                   w=(wqkv_b, wo_b, w1_b, w2_b), ln=(g2, g1), key=ops.grad_key(lw[li * PL])))
         if need_grad:
             ctx.saved = dict(x=x, s0=s0, z0=z0, mean0=mean0, rstd0=rstd0, seed0=seed0, front=front,
                              ln_g=ln_g.detach() if front else None,
+                             fkeys=[ops.grad_key(t) for t in (pos_g, pos_v, pos_b, ln_g, ln_b)] if front else None,
+                             lkeys=[ops.grad_key(lw[li * PL]) for li in range(len(lw) // PL)], F_=lw[10].shape[0] if len(lw) else 0,
                              pg=pg, pv=pv, norm2=norm2, wpt=wpt, layers=layers, row_keep=row_keep, p=p, H=H,
                              groups=groups, k=k, pad_l=pad_l, Tp=Tp, scale=scale, nlw=len(lw), seed_src=seed_src)
         be.set_seed_source(None)
         return h
+
+    @staticmethod
+    def _layer_views(zbuf, D, F_):
+        """one layer's gradient block [dWqkv | dWo | dW1 | dW2 | (dg1, db1ln, db2) | (dg2, db2ln, dbo) | db1 | dbqkv] as
+        (the 16 per-parameter gradients in `PER_LAYER` order, the accumulators the kernels write)"""
+        sizes = [3 * D * D, D * D, F_ * D, D * F_, 3 * D, 3 * D, F_, 3 * D]
+        parts, o = [], 0
+        for n_ in sizes:
+            parts.append(zbuf[o:o + n_])
+            o += n_
+        dwqkv, dwo, dw1, dw2 = parts[0].view(3 * D, D), parts[1].view(D, D), parts[2].view(F_, D), parts[3].view(D, F_)
+        acc1, acc2, db1, dbqkv = parts[4].view(3, D), parts[5].view(3, D), parts[6], parts[7]
+        grads = [dwqkv[0:D], dbqkv[0:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, acc2[2],
+                 acc2[0], acc2[1], dw1, db1, dw2, acc1[2], acc1[0], acc1[1]]
+        return grads, (dwqkv, dwo, dw1, dw2, acc1, acc2, db1, dbqkv)
 
     @staticmethod
     def backward(ctx, dh):
@@ -424,6 +492,12 @@ class EncoderFn(torch.autograd.Function):
         for li in range(len(sv["layers"]) - 1, -1, -1):
             L = sv["layers"][li]
             if L is None:
+                # LayerDrop skipped this layer.  Under the data-parallel wrapper its gradient block still takes part in
+                # the all-reduce (other ranks may have run the layer): hand out the zeroed block as this rank's gradients
+                F0 = sv["F_"]
+                zb = ops.grad_arena_take(sv["lkeys"][li], 4 * D * D + 2 * F0 * D + 9 * D + F0)
+                if zb is not None:
+                    lgrads[li * PL:(li + 1) * PL] = EncoderFn._layer_views(zb, D, F0)[0]
                 continue
             wqkv_b, wo_b, w1_b, w2_b = L["w"]
             g2, g1 = L["ln"]
@@ -432,15 +506,10 @@ class EncoderFn(torch.autograd.Function):
             # every fp32 accumulator of this layer's backward comes from ONE zero-filled buffer (one fill launch)
             sizes = [3 * D * D, D * D, F_ * D, D * F_, 3 * D, 3 * D, F_, 3 * D]
             # data-parallel runs: the block lives in the wrapper's gradient arena (parallel.py) and is reduced in place
-            zbuf = ops.grad_arena_take(("enc", L["w"][0].data_ptr()), sum(sizes))
+            zbuf = ops.grad_arena_take(L["key"], sum(sizes))
             if zbuf is None:
                 zbuf = _zeros((sum(sizes),), F32, x)
-            parts, o = [], 0
-            for n_ in sizes:
-                parts.append(zbuf[o:o + n_])
-                o += n_
-            dwqkv, dwo, dw1, dw2 = parts[0].view(3 * D, D), parts[1].view(D, D), parts[2].view(F_, D), parts[3].view(D, F_)
-            acc1, acc2, db1, dbqkv = parts[4].view(3, D), parts[5].view(3, D), parts[6], parts[7]
+            _, (dwqkv, dwo, dw1, dw2, acc1, acc2, db1, dbqkv) = EncoderFn._layer_views(zbuf, D, F_)
             # ---- ln1( x1 + drop(ffn) )
             ds2, df, dg1, db1ln, dbias2 = be.layernorm_bwd(dcur, L["s2"], L["mean1"], L["rstd1"], g1, want_dh=p > 0,
                                                            p_h=p, seed_h=seed2, want_dbias=True, acc=acc1)
@@ -475,14 +544,17 @@ class EncoderFn(torch.autograd.Function):
             be.set_seed_source(None)
             return (dcur.view(B, T, D), None, None, None, None, None, None, None, *lgrads)
         # ---- front: LN(+dropout) <- x + gelu(pos_conv(x))
+        kg, kv, kb_, klg, klb = sv["fkeys"]
         ds0, _, dlg, dlb, _ = be.layernorm_bwd(dcur.view(B, T, D), sv["s0"], sv["mean0"], sv["rstd0"], sv["ln_g"],
-                                               p_y=p, seed_y=sv["seed0"])
+                                               p_y=p, seed_y=sv["seed0"], dg_out=_grad_zeros(klg, (D,), x),
+                                               db_out=_grad_zeros(klb, (D,), x))
         dz0 = be.gelu_bwd(ds0, sv["z0"])
-        dpos_b = be.colsum(dz0)
+        dpos_b = be.colsum(dz0, out=_grad_zeros(kb_, (D,), x))
         groups, k, pad_l = sv["groups"], sv["k"], sv["pad_l"]
         dwp = _empty((groups, k * 64, 64), F32, x)
         be.gemm(G.posconv_wgrad(dz0, x, dwp, groups, k, pad_l))
-        dpos_v, dpos_g = be.posconv_wn_bwd(dwp, sv["pg"], sv["pv"], sv["norm2"])
+        dpos_v, dpos_g = be.posconv_wn_bwd(dwp, sv["pg"], sv["pv"], sv["norm2"],
+                                           out=(_grad_empty(kv, tuple(sv["pv"].shape), x), _grad_empty(kg, tuple(sv["pg"].shape), x)))
         dx = _empty((B, T, D), BF16, x)
         be.gemm(G.posconv_dgrad(dz0, sv["wpt"], dx, groups, k, pad_l, aux=ds0))
         if sv["row_keep"] is not None:
@@ -508,14 +580,15 @@ class QuantizerFn(torch.autograd.Function):
         v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
         q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_)
         # outputs are kept as detached aliases (no ctx <-> output reference cycle)
-        ctx.saved = (y2, w32, v2, z, noise, kidx.detach(), avg, ppl.detach(), G_, float(tau), y.shape, vars_.shape)
+        ctx.saved = (y2, w32, v2, z, noise, kidx.detach(), avg, ppl.detach(), G_, float(tau), y.shape, vars_.shape,
+                     (ops.grad_key(w), ops.grad_key(b), ops.grad_key(vars_)))
         ctx.mark_non_differentiable(kidx)
         return q.view(Bq, Tm, -1), ppl, kidx
 
     @staticmethod
     def backward(ctx, dq, dppl, _dk):
         be = _be()
-        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape = _take_saved(ctx)
+        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape, (wkey, bkey, vkey) = _take_saved(ctx)
         R = y2.shape[0]
         vd = v2.shape[1]
         if dq is None:
@@ -527,9 +600,10 @@ class QuantizerFn(torch.autograd.Function):
         if noise is not None:
             a_dot = _empty((R, v2.shape[0]), F32, y2, dynamic=True)
             be.gemm(G.vq_codebook_dots(_bf16(dq2), _bf16(v2), a_dot, G_))
-        dz, dvars = be.vq_bwd(z, noise, tau, G_, vd, a_dot, dq2, kidx, avg, ppl, dppl.contiguous().float())
-        db = be.colsum(dz)
-        dw = _zeros(w32.shape, F32, y2)
+        dz, dvars = be.vq_bwd(z, noise, tau, G_, vd, a_dot, dq2, kidx, avg, ppl, dppl.contiguous().float(),
+                              dvars_out=_grad_zeros(vkey, tuple(v2.shape), y2))
+        db = be.colsum(dz, out=_grad_zeros(bkey, (dz.shape[-1],), y2))
+        dw = _grad_zeros(wkey, tuple(w32.shape), y2)
         be.gemm(G.linear_wgrad(dz, _bf16(y2), dw))
         dy = _empty(y2.shape, F32, y2, dynamic=True)
         be.gemm(G.linear_dgrad(dz, _bf16(w32), dy, c_dtype=OUT_F32))

@@ -12,6 +12,8 @@ Policy: a signature is captured when it is seen for the `A8_GRAPH_AFTER`-th time
 disables the mechanism.  Captured activations live in the graph's private pool (~4 GB at B=6 x 15 s).
 """
 import os
+import warnings
+import weakref
 
 import torch
 
@@ -35,6 +37,8 @@ class GraphedSegment:
         self.entries = {}  # key -> (graphed callable, kernels per replay)
         self.seen = {}
         self.failed = set()
+        self.live = {}  # key -> (weakref to the last replay's autograd node, [backward started?])
+        self.warned = False
 
     def _key(self, inputs, params, extra):
         # the parameter part (address + requires_grad of ~200 tensors) is cached per params-tuple object and re-derived
@@ -46,10 +50,17 @@ class GraphedSegment:
             cached = self._pkey = (probe, tuple((p.data_ptr(), p.requires_grad) for p in params), params)
         return (tuple((tuple(t.shape), t.dtype, t.requires_grad) for t in inputs), cached[1], torch.is_grad_enabled(), extra)
 
-    def run(self, fn, inputs, params, extra=()):
+    def run(self, fn, inputs, params, extra=(), clone_outputs=False):
         """fn(*inputs, *params) -> tensor or tuple of tensors, FUNCTIONAL in both (it must not reach parameters through
         module attributes).  `inputs` are the tensors whose VALUES change per call (fixed shapes); `params` the
-        nn.Parameters the segment reads (their storage must not move)."""
+        nn.Parameters the segment reads (their storage must not move).
+
+        A replay returns ALIASES of the graph's static output buffers and keeps its activations in static buffers too:
+        * clone_outputs=True (what the public module boundaries pass) hands the caller fresh tensors, so results kept
+          across calls (`outs.append(encoder(x))`) are not overwritten by the next replay;
+        * a second forward while the previous replay's autograd graph is still alive and has not started its backward
+          would overwrite that graph's saved activations: such a call runs eagerly instead (one forward per backward is
+          the replayed pattern; anything else is correct but slower)."""
         if not ENABLED or not inputs[0].is_cuda or torch.cuda.is_current_stream_capturing():
             return fn(*inputs, *params)
         key = self._key(inputs, params, extra)
@@ -63,8 +74,36 @@ class GraphedSegment:
             if ent is None:
                 return fn(*inputs, *params)
         graphed, n_kernels = ent
+        prev = self.live.get(key)
+        if prev is not None and not prev[1][0] and prev[0]() is not None:
+            if not self.warned:
+                self.warned = True
+                warnings.warn(f"audio8_b200: segment '{self.name}' called again before the backward of its previous call: "
+                              "running this call eagerly (a CUDA-graph replay would overwrite the saved activations)")
+            return fn(*inputs, *params)
         _lib.load().a8_launch_count_add(n_kernels)
-        return graphed(*inputs, *params)
+        out = graphed(*inputs, *params)
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        node = next((t.grad_fn for t in outs if isinstance(t, torch.Tensor) and t.grad_fn is not None), None)
+        if node is not None:
+            done = [False]
+
+            def _started(_g, d=done):
+                d[0] = True
+
+            for t in outs:
+                if isinstance(t, torch.Tensor) and t.requires_grad:
+                    t.register_hook(_started)
+            try:
+                self.live[key] = (weakref.ref(node), done)
+            except TypeError:  # a node type without weak references: fall back to the backward-started flag alone
+                self.live[key] = ((lambda n=node: None), done)
+        else:
+            self.live.pop(key, None)
+        if clone_outputs:
+            out = tuple(t.clone() if isinstance(t, torch.Tensor) else t for t in outs) if isinstance(out, (tuple, list)) \
+                else out.clone()
+        return out
 
     def _capture(self, fn, inputs, params, key):
         lib = _lib.load()
@@ -81,7 +120,6 @@ class GraphedSegment:
             if os.environ.get("A8_GRAPH_STRICT"):
                 raise
             self.failed.add(key)
-            import warnings
             warnings.warn(f"audio8_b200: CUDA-graph capture of segment '{self.name}' failed, running eagerly: {e!r}")
             return None
         per_replay = (lib.a8_launch_count() - n0) // (WARMUP_ITERS + 1)

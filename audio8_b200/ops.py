@@ -66,10 +66,16 @@ def grad_arena_for_backward():
     return _ARENA[1]
 
 
-def grad_arena_take(key, numel):
-    """a zeroed persistent block for a layer's gradient accumulators, or None (no arena: allocate normally)"""
+def grad_key(param):
+    """arena key of a parameter (its storage address: the aliases a CUDA-graph capture runs on share it); None stays None"""
+    return None if param is None else ("p", param.data_ptr())
+
+
+def grad_arena_take(key, numel, zero=True):
+    """the parameter's (or transformer layer's) persistent gradient block of the data-parallel wrapper's arena, zeroed
+    unless zero=False; None when no arena is active for this backward or the key has no block (allocate normally)"""
     a = _ARENA[1]
-    return a.take(key, numel) if a is not None else None
+    return a.take(key, numel, zero) if a is not None else None
 
 
 def encoder_backward_done():
@@ -309,20 +315,25 @@ class CudaBackend:
         return y, yf, s, mean, rstd
 
     def layernorm_bwd(self, dy, s, mean, rstd, gamma, dy_f32=None, p_y=0.0, seed_y=0, want_dh=False, p_h=0.0,
-                      seed_h=0, want_dbias=False, acc=None):
-        """returns ds, dh (or None), dgamma, dbeta, dbias (or None); acc: optional ZEROED fp32 [3,C] accumulator"""
+                      seed_h=0, want_dbias=False, acc=None, dg_out=None, db_out=None):
+        """returns ds, dh (or None), dgamma, dbeta, dbias (or None); acc: optional ZEROED fp32 [3,C] accumulator;
+        dg_out / db_out: optional ZEROED fp32 [C] destinations for dgamma / dbeta (gradient-arena blocks)"""
         C = s.shape[-1]
         R = s.numel() // C
         assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and s.is_contiguous()
         ds = torch.empty_like(s)
         dh = torch.empty_like(s) if want_dh else None
-        if acc is None:
-            acc = torch.zeros(3, C, dtype=torch.float32, device=s.device)
+        if dg_out is not None and db_out is not None and not want_dbias:
+            a0, a1, a2 = dg_out, db_out, None
+        else:
+            if acc is None:
+                acc = torch.zeros(3, C, dtype=torch.float32, device=s.device)
+            a0, a1, a2 = acc[0], acc[1], acc[2]
         _lib.check(self.lib.a8_layernorm_bwd(_ptr(dy), _ptr(dy_f32), p_y, seed_y, _ptr(s), _ptr(mean), _ptr(rstd),
-                                             _ptr(gamma), _ptr(ds), _ptr(dh), p_h, seed_h, _ptr(acc[0]), _ptr(acc[1]),
-                                             _ptr(acc[2]) if want_dbias else None, R, C, _stream()),
+                                             _ptr(gamma), _ptr(ds), _ptr(dh), p_h, seed_h, _ptr(a0), _ptr(a1),
+                                             _ptr(a2) if want_dbias else None, R, C, _stream()),
                    "a8_layernorm_bwd")
-        return ds, dh, acc[0], acc[1], (acc[2] if want_dbias else None)
+        return ds, dh, a0, a1, (a2 if want_dbias else None)
 
     def softmax_fwd(self, s, T, key_keep=None, pdrop=0.0, seed=0):
         B, H, _, Tp = s.shape
@@ -426,13 +437,16 @@ class CudaBackend:
                                          stride, _ptr(y), _stream()), "a8_conv0_fwd")
         return y
 
-    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, mom, k, stride, da):
+    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, mom, k, stride, da, out=None):
+        """out: optional (dw [C,k], dgamma [C], dbeta [C]) fp32 destinations (fully overwritten)"""
         B, L = x.shape
         C = w.shape[0]
         assert da.dtype == torch.bfloat16 and da.is_contiguous() and mom.dtype == torch.float64
         acc = torch.empty(B * C * 12, dtype=torch.float32, device=x.device)
-        out = torch.empty(C * k + 2 * C, dtype=torch.float32, device=x.device)
-        dw, dg, db = out[:C * k].view(C, k), out[C * k:C * k + C], out[C * k + C:]
+        if out is None:
+            buf = torch.empty(C * k + 2 * C, dtype=torch.float32, device=x.device)
+            out = (buf[:C * k].view(C, k), buf[C * k:C * k + C], buf[C * k + C:])
+        dw, dg, db = out
         _lib.check(self.lib.a8_conv0_bwd(_ptr(x), B, L, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd),
                                          _ptr(mom), C, k, stride, _ptr(da), _ptr(acc), _ptr(dw), _ptr(dg), _ptr(db),
                                          _stream()), "a8_conv0_bwd")
@@ -466,10 +480,10 @@ class CudaBackend:
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and vec.dtype == torch.float32
         _lib.check(self.lib.a8_rows_set(_ptr(x), _ptr(idx), idx.numel(), C, _ptr(vec), _stream()), "a8_rows_set")
 
-    def rows_set_bwd(self, dx, idx):
-        """in place: zero dx[idx[i], :]; returns the column sum of the rows it zeroed"""
+    def rows_set_bwd(self, dx, idx, out=None):
+        """in place: zero dx[idx[i], :]; returns the column sum of the rows it zeroed (out: optional ZEROED fp32 [C])"""
         C = dx.shape[-1]
-        dvec = torch.zeros(C, dtype=torch.float32, device=dx.device)
+        dvec = out if out is not None else torch.zeros(C, dtype=torch.float32, device=dx.device)
         _lib.check(self.lib.a8_rows_set_bwd(_ptr(dx), _ptr(idx), idx.numel(), C, _ptr(dvec), _stream()),
                    "a8_rows_set_bwd")
         return dvec
@@ -518,9 +532,9 @@ class CudaBackend:
                                          _ptr(wts[1]) if wts else None, _stream()), "a8_conv_pack")
         return wk, wts
 
-    def conv_unpack(self, dwk, Cin, k):
+    def conv_unpack(self, dwk, Cin, k, out=None):
         Cout = dwk.shape[0]
-        dw = torch.empty(Cout, Cin, k, dtype=torch.float32, device=dwk.device)
+        dw = out if out is not None else torch.empty(Cout, Cin, k, dtype=torch.float32, device=dwk.device)
         _lib.check(self.lib.a8_conv_unpack(_ptr(dwk), Cout, Cin, k, _ptr(dw), _stream()), "a8_conv_unpack")
         return dw
 
@@ -536,11 +550,11 @@ class CudaBackend:
                    "a8_posconv_pack")
         return wp, wpt, norm2
 
-    def posconv_wn_bwd(self, dwp, g, v, norm2):
+    def posconv_wn_bwd(self, dwp, g, v, norm2, out=None):
+        """out: optional (dv like v, dg like g) fp32 destinations (fully overwritten)"""
         D, cg, k = v.shape
         t = torch.empty(k, dtype=torch.float32, device=v.device)
-        dv = torch.empty_like(v)
-        dg = torch.empty_like(g)
+        dv, dg = out if out is not None else (torch.empty_like(v), torch.empty_like(g))
         _lib.check(self.lib.a8_posconv_wn_bwd(_ptr(dwp), _ptr(g), _ptr(v), _ptr(norm2), D, cg, k, _ptr(t), _ptr(dv),
                                               _ptr(dg), _stream()), "a8_posconv_wn_bwd")
         return dv, dg
@@ -560,11 +574,12 @@ class CudaBackend:
                                       _ptr(avg), _ptr(ppl), _stream()), "a8_vq_fwd")
         return q, qb, kidx, avg, ppl
 
-    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl):
+    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl, dvars_out=None):
+        """dvars_out: optional ZEROED fp32 [G*V, vd] destination of the codebook gradient"""
         R = z.shape[0]
         V = z.shape[1] // G
         dz = bucketed_empty((R, G * V), torch.bfloat16, z.device)
-        dvars = torch.zeros(G * V, vd, dtype=torch.float32, device=z.device)
+        dvars = dvars_out if dvars_out is not None else torch.zeros(G * V, vd, dtype=torch.float32, device=z.device)
         _lib.check(self.lib.a8_vq_bwd(_ptr(z), _ptr(noise), tau, R, G, V, vd, _ptr(a_dot), _ptr(dq), _ptr(kidx), _ptr(avg),
                                       _ptr(ppl), _ptr(dppl), _ptr(dz), _ptr(dvars), _stream()), "a8_vq_bwd")
         return dz, dvars

@@ -2,13 +2,13 @@
 per optimizer step (the gradient average) — the same contract as `torch.nn.parallel.DistributedDataParallel`, which the
 reference's trainers construct (`pretrain.py:158`, `train.py:266`) and which keeps working with these modules.
 
-What differs from DistributedDataParallel is where the gradients live.  The transformer layers (89 % of the parameters
-of wav2vec2-base) write their weight gradients straight into a persistent, contiguous fp32 **gradient arena**
-(`functional.EncoderFn.backward` takes each layer's accumulator block from it), so `param.grad` of those parameters are
-views of the arena and the all-reduce runs in place over one buffer: no per-parameter hook, no bucket copy kernels (DDP
-launched ~200 of them per step here) and a single NCCL call, started as soon as the encoder's backward has been
-enqueued so that it overlaps the conv feature encoder's backward.  The remaining gradients (conv stack, projections,
-quantizer: ~10 % of the bytes) are flattened, reduced and copied back with three launches at the end of backward.
+What differs from DistributedDataParallel is where the gradients live.  Every backward kernel writes its parameter
+gradients straight into a persistent, contiguous fp32 **gradient arena** whose layout is planned once from the module
+structure (identical on every rank), so `param.grad` are views of the arena and the all-reduce runs in place: no
+per-parameter hook, no bucket copy kernels (DDP launched ~200 of them per step here) and two NCCL calls per step — the
+transformer-layer region (89 % of the bytes of wav2vec2-base), started as soon as the encoder's backward has been
+enqueued so that it overlaps the conv feature encoder's backward, and the rest (conv stack, projections, quantizer) when
+backward ends.
 
 Interface kept: `.module`, `forward`, `no_sync()`, `state_dict()` with the `module.` prefix.  Gradient accumulation
 (`no_sync()` micro-steps, or gradients not reset to None) falls back to freshly allocated gradients and the flattening
@@ -24,27 +24,46 @@ from . import ops
 
 
 class GradArena:
-    """bump allocator over one persistent fp32 buffer; blocks are keyed (a layer's first parameter) and keep their place"""
+    """One persistent fp32 buffer holding every trainable parameter's gradient at a FIXED offset, planned once from the
+    module structure (never from the order in which backward happens to reach the layers: with LayerDrop each rank drops
+    different layers, and a lazily assigned layout would differ between ranks and corrupt the in-place all-reduce).
+    Layout: [transformer layers: one block per layer, last layer first | everything else]; the first region is complete
+    when the encoder's backward has been enqueued and is reduced under the rest of backward, the second at its end."""
 
-    def __init__(self, numel, device):
-        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+    def __init__(self, module, device):
+        from .wav2vec2 import AudioTransformerEncoder
+        plan, covered = [], set()
+        for m in module.modules():
+            if isinstance(m, AudioTransformerEncoder):
+                for layer in reversed(list(m.transformer.encoders)):
+                    flat = layer.flat()
+                    if not all(p.requires_grad for p in flat):
+                        continue
+                    plan.append((ops.grad_key(flat[0]), sum(p.numel() for p in flat)))
+                    covered.update(id(p) for p in flat)
+        self.early = None
+        rest = [(ops.grad_key(p), p.numel()) for p in module.parameters() if p.requires_grad and id(p) not in covered]
         self.slots = {}
-        self.used = 0
+        off = 0
+        for part in (plan, rest):
+            for key, n in part:
+                off = (off + 63) & ~63  # 256-byte alignment
+                self.slots[key] = (off, n)
+                off += n
+            if self.early is None:
+                self.early = off  # end of the transformer-layer region
+        self.used = off
+        self.buf = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
 
-    def take(self, key, numel):
-        """zeroed block of `numel` floats for `key` (same storage on every step), or None when the arena is full"""
+    def take(self, key, numel, zero=True):
+        """the block planned for `key` (same storage on every step and every rank), zeroed unless zero=False; None when
+        the key has no block or the size differs (the caller allocates normally and the gradient is reduced separately)"""
         slot = self.slots.get(key)
-        if slot is None:
-            start = (self.used + 63) & ~63  # 256-byte alignment
-            if start + numel > self.buf.numel():
-                return None
-            slot = self.slots[key] = (start, numel)
-            self.used = start + numel
-        start, n = slot
-        if n != numel:
+        if slot is None or slot[1] != numel:
             return None
-        out = self.buf[start:start + n]
-        out.zero_()
+        out = self.buf[slot[0]:slot[0] + numel]
+        if zero:
+            out.zero_()
         return out
 
 
@@ -58,7 +77,7 @@ class DataParallel(nn.Module):
         self.overlap = overlap
         self._params = [p for p in module.parameters() if p.requires_grad]
         self._arena = None
-        self._early = None  # (work handle, numel) of the arena all-reduce started inside backward
+        self._early = None  # work handle of the all-reduce of the transformer-layer region started inside backward
         self._callback_queued = False
         if self.world > 1:  # every rank starts from rank 0's parameters, like DistributedDataParallel
             with torch.no_grad():
@@ -82,8 +101,7 @@ class DataParallel(nn.Module):
         sync = self.require_sync and self.world > 1 and torch.is_grad_enabled()
         fresh = sync and all(p.grad is None for p in self._params)
         if fresh and self._arena is None and self._params:
-            n = sum(p.numel() for p in self._params) + 64 * 64
-            self._arena = GradArena(n, self._params[0].device)
+            self._arena = GradArena(self.module, self._params[0].device)
         ops.set_grad_arena(self._arena if fresh else None, self._encoder_done if (fresh and self.overlap) else None)
         try:
             out = self.module(*args, **kwargs)
@@ -112,34 +130,35 @@ class DataParallel(nn.Module):
 
     def _encoder_done(self):
         """called (on the autograd thread) when the gradient w.r.t. the encoder's input exists, i.e. every transformer
-        layer has put its gradients into the arena: start reducing them under the rest of backward"""
+        layer has put its gradients into the arena: start reducing that region under the rest of backward"""
         a = self._arena
-        if a is None or a.used == 0 or self._early is not None:
+        if a is None or a.early == 0 or self._early is not None:
             return
-        self._early = (self._all_reduce(a.buf[:a.used], async_op=True), a.used)
+        self._early = self._all_reduce(a.buf[:a.early], async_op=True) or True
 
     def _finish(self):
         a = self._arena
-        arena_ptr0 = a.buf.data_ptr() if a is not None else 0
-        arena_ptr1 = arena_ptr0 + (a.buf.numel() * 4 if a is not None else 0)
         arena_on = ops.grad_arena_for_backward() is a and a is not None
-        if arena_on and a.used and self._early is None:
-            self._early = (self._all_reduce(a.buf[:a.used], async_op=True), a.used)
+        works = []
+        if arena_on:
+            lo = a.early if self._early is not None else 0  # whatever has not been started yet: one call, in place
+            if a.used > lo:
+                works.append(self._all_reduce(a.buf[lo:a.used], async_op=True))
+            ptr0, ptr1 = a.buf.data_ptr(), a.buf.data_ptr() + a.buf.numel() * 4
         rest = []
         for p in self._params:
             g = p.grad
-            if g is None:
-                continue
-            if arena_on and arena_ptr0 <= g.data_ptr() < arena_ptr1:
-                continue  # lives in the arena: reduced in place
+            if g is None or (arena_on and ptr0 <= g.data_ptr() < ptr1):
+                continue  # no gradient, or one that lives in the arena (reduced in place)
             rest.append(g)
-        if rest:
+        if rest:  # gradients produced outside the arena (gradient accumulation, or a parameter the plan does not know)
             flat = torch.cat([g.reshape(-1) for g in rest])
             self._all_reduce(flat, async_op=False)
             torch._foreach_copy_(rest, [f.view_as(g) for f, g in zip(flat.split([g.numel() for g in rest]), rest)])
-        if self._early is not None:
-            w = self._early[0]
+        if self._early is not None and self._early is not True:
+            works.append(self._early)
+        for w in works:
             if w is not None:
                 w.wait()  # the compute stream waits for the collective; the host does not
-            self._early = None
+        self._early = None
         ops.set_grad_arena(None, None)

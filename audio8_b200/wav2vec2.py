@@ -403,8 +403,10 @@ class AudioTransformerEncoder(nn.Module):
     def forward(self, x, pad_mask=None):
         return self.extract_features(x, pad_mask)
 
-    def extract_features(self, x, pad_mask=None, _layer_draws=None):
-        """x [B,T,D] (bf16 or fp32), pad_mask bool [B,T] (True = valid) or None -> bf16 [B,T,D]"""
+    def extract_features(self, x, pad_mask=None, _layer_draws=None, _internal=False):
+        """x [B,T,D] (bf16 or fp32), pad_mask bool [B,T] (True = valid) or None -> bf16 [B,T,D].
+        The result is a fresh tensor (a CUDA-graph replay's static output buffer is cloned at this public boundary);
+        `_internal` callers that consume the result within the same step skip the copy."""
         if x.requires_grad and Fn.ops.grad_arena_active():
             # data-parallel wrapper (parallel.py): when the gradient w.r.t. the encoder's input exists, every layer has
             # written its gradients into the arena and their all-reduce can start under the rest of backward
@@ -429,7 +431,7 @@ class AudioTransformerEncoder(nn.Module):
             cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
                        active=active[lo:hi], arena=self._arena.setdefault(part, {}), front=(part == 0))
             params = self._part_params(part, lo, hi, front_params)
-            h = self._run_part(part, h, cfg, row_keep, params)
+            h = self._run_part(part, h, cfg, row_keep, params, clone=(not _internal) and part == len(cuts) - 2)
         return h
 
     def _part_params(self, part, lo, hi, front_params):
@@ -445,7 +447,7 @@ class AudioTransformerEncoder(nn.Module):
             ent = cache[part] = (probe, (*front_params, *flat) if part == 0 else tuple(flat))
         return ent[1]
 
-    def _run_part(self, part, x, cfg, row_keep, params):
+    def _run_part(self, part, x, cfg, row_keep, params, clone=False):
         nf = 5 if cfg["front"] else 0
 
         def call(x_, rk, ps):
@@ -457,9 +459,10 @@ class AudioTransformerEncoder(nn.Module):
         # static shapes: replay a captured CUDA graph once this (shape, mode) has been seen before (graphs.py)
         seg = self._graph if part == 0 else self._graph2
         if row_keep is None:
-            return seg.run(lambda x_, *ps: call(x_, None, ps), (x,), params, extra=(self.training, self.pdrop, part, Fn.ops.grad_arena_active()))
+            return seg.run(lambda x_, *ps: call(x_, None, ps), (x,), params,
+                           extra=(self.training, self.pdrop, part, Fn.ops.grad_arena_active()), clone_outputs=clone)
         return seg.run(lambda x_, rk, *ps: call(x_, rk, ps), (x, row_keep), params,
-                       extra=(self.training, self.pdrop, part, Fn.ops.grad_arena_active()))
+                       extra=(self.training, self.pdrop, part, Fn.ops.grad_arena_active()), clone_outputs=clone)
 
 
 class Wav2Vec2Encoder(nn.Module):
@@ -499,11 +502,13 @@ class Wav2Vec2Encoder(nn.Module):
         features = Fn.dropout(features, self.dropout_input_p, self.training)
         if self.training and self.timestep_masking > 0.0:
             time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
-            features = Fn.RowsSetFn.apply(features, _mask_rows(time_mask, x.device), self.mask_emb)
+            if time_mask.any():  # num_mask == 0 on very short utterances: `features[time_mask] = ...` is a no-op (:717)
+                features = Fn.RowsSetFn.apply(features, _mask_rows(time_mask, x.device), self.mask_emb)
         if self.training and self.channel_masking > 0.0:
             channel_mask = create_mask((B, C), p_start=self.channel_masking, mask_length=self.channel_mask_len)
-            cz = _to_device(channel_mask.astype(np.uint8), x.device)
-            features = Fn.MaskApplyFn.apply(features, None, cz)
+            if channel_mask.any():
+                cz = _to_device(channel_mask.astype(np.uint8), x.device)
+                features = Fn.MaskApplyFn.apply(features, None, cz)
         out = self.encoder(features, pad_mask)
         return out, pad_mask
 
@@ -588,7 +593,7 @@ class Wav2Vec2Model(nn.Module):
         sampler = self.__dict__.pop("_host_draw_request", None)
         self._host_draws = draws = None
         features, unmasked = self._front_graph.run(self._front, (x,), self._front_params(),
-                                                   extra=(self.training, self.dropout_input_p))
+                                                   extra=(self.training, self.dropout_input_p, Fn.ops.grad_arena_active()))
         if sampler is not None:
             self._host_draws = draws = _HostDraws(x.shape[0], unmasked.shape[1], self.timestep_masking,
                                                   self.timestep_mask_len, len(self.encoder.transformer.encoders), sampler)
@@ -616,9 +621,9 @@ class Wav2Vec2Model(nn.Module):
             y = Fn.dropout(y, self.dropout_features_p, self.training)
             q, vq_probs = self.quantizer(y)
             y = self.project_q(q, out_f32=True)
-            enc = self.encoder.extract_features(features, None, layer_draws)
+            enc = self.encoder.extract_features(features, None, layer_draws, _internal=True)
         else:  # the encoder (the longest stretch of GPU work) first; the quantizer branch follows it on the stream
-            enc = self.encoder.extract_features(features, None, layer_draws)
+            enc = self.encoder.extract_features(features, None, layer_draws, _internal=True)
             y = Fn.RowsGatherFn.apply(unmasked, rows).view(B, -1, C)
             y = Fn.dropout(y, self.dropout_features_p, self.training)
             q, vq_probs = self.quantizer(y)

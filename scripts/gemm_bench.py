@@ -45,9 +45,45 @@ cases["conv1_wgrad"] = lambda: G.conv_wgrad(r(B, 23999, 512), r(B, 47999, 512), 
 cases["conv2_dgrad_p0"] = lambda: G.conv_dgrad(r(B, 11999, 512), r(512, 1024), torch.empty(B, 23999, 512, device=dev, dtype=bf), 3, 2, 0, aux=r(B, 23999, 512))
 cases["posconv_fwd"] = lambda: G.posconv_fwd(r(B, T, D), r(D, 128 * 64), torch.empty(B, T, D, device=dev, dtype=bf), r(D, dtype=torch.float32), 16, 128, 63, z_out=torch.empty(B, T, D, device=dev, dtype=bf))
 
+# the library incumbent on the same contraction (cuBLAS through torch.matmul, cuDNN through F.conv1d; bf16 in, bf16 out,
+# WITHOUT the fused bias / GELU / residual epilogues our kernel carries: a lower bound on what eager PyTorch spends)
+import torch.nn.functional as F  # noqa: E402
+flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
+lib_cases = {
+    "qkv_fwd 4494x2304x768": lambda a=r(M, D), w=r(3 * D, D): a @ w.t(),
+    "ffn1_fwd+gelu+z 4494x3072x768": lambda a=r(M, D), w=r(F_, D): a @ w.t(),
+    "ffn2_fwd 4494x768x3072": lambda a=r(M, F_), w=r(D, F_): a @ w.t(),
+    "wo_fwd 4494x768x768": lambda a=r(M, D), w=r(D, D): a @ w.t(),
+    "ffn2_dgrad*gelu' 4494x3072x768": lambda a=r(M, D), w=r(D, F_): a @ w,
+    "ffn1_dgrad+add 4494x768x3072": lambda a=r(M, F_), w=r(F_, D): a @ w,
+    "ffn_wgrad 3072x768x4494": lambda a=r(M, F_), b=r(M, D): a.t() @ b,
+    "qkv_wgrad 2304x768x4494": lambda a=r(M, 3 * D), b=r(M, D): a.t() @ b,
+    "wo_wgrad 768x768x4494": lambda a=r(M, D), b=r(M, D): a.t() @ b,
+    "qkv_dgrad+add 4494x768x2304": lambda a=r(M, 3 * D), w=r(3 * D, D): a @ w,
+    "conv1_fwd": lambda a=r(B, 512, 47999), w=r(512, 512, 3): F.conv1d(a, w, stride=2),
+    "posconv_fwd": lambda a=r(B, D, T + 127), w=r(D, D // 16, 128): F.conv1d(a, w, groups=16),
+}
+
+
+def time_fn(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
 sel = sys.argv[1] if len(sys.argv) > 1 else ""
 reps = int(os.environ.get("REPS", "20"))
-flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
 for name, mk in cases.items():
     if sel and sel not in name:
         continue
@@ -67,7 +103,11 @@ for name, mk in cases.items():
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     med = ts[len(ts) // 2]
-    print(f"{name:36s} {med * 1e3:8.1f} us   {full.flops / med / 1e9:7.1f} TFLOP/s   (min {ts[0] * 1e3:.1f} us)", flush=True)
+    lib = ""
+    if name in lib_cases:
+        lmed, lmin = time_fn(lib_cases[name], reps)
+        lib = f"   | library {lmed * 1e3:7.1f} us {full.flops / lmed / 1e9:7.1f} TFLOP/s  (ours/library time {med / lmed:.2f})"
+    print(f"{name:36s} {med * 1e3:8.1f} us   {full.flops / med / 1e9:7.1f} TFLOP/s   (min {ts[0] * 1e3:.1f} us){lib}", flush=True)
 
 # ---- fused attention (csrc/attn.cu) at the step's shape
 if not sel or "attn" in sel:

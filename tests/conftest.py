@@ -22,3 +22,25 @@ def emu_backend():
     ops.set_backend(emu.EmuOps())
     yield ops._BACKEND
     ops.set_backend(prev)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """every gradient comparison of a GPU session, with its measured cosine / rel-L2 and the tolerance it was held to,
+    as a markdown table under gpurun_out/ (copied to profiles/r02_parity.md)"""
+    try:
+        import torch
+        import model_cases as mc
+        if not mc.PARITY_LOG or not torch.cuda.is_available():
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.md"), "w") as f:
+            f.write("| case | tensor | cosine | rel-L2 | held to (cos >= / rel <=) |\n|---|---|---:|---:|---|\n")
+            for case, what, cos, rel, cmin, rmax in mc.PARITY_LOG:
+                f.write(f"| {case} | {what} | {cos:.6f} | {rel:.5f} | {cmin} / {rmax} |\n")
+            if mc.VQ_LOG:
+                f.write("\n| case | VQ code-index flips vs the oracle's arg-max | entries |\n|---|---:|---:|\n")
+                for case, flips, n in mc.VQ_LOG:
+                    f.write(f"| {case} | {flips} | {n} |\n")
+    except Exception as e:  # reporting only
+        print("parity report not written:", e)

@@ -118,6 +118,14 @@ def _bf(x):
     return x.to(torch.bfloat16)
 
 
+def _into(out, val):
+    """the ABI's `out=` destinations (zeroed accumulators / overwritten buffers) as a plain copy"""
+    if out is None:
+        return val
+    out.copy_(val.reshape(out.shape))
+    return out
+
+
 class EmuOps(EmuBackend):
     """row / index / loss kernels of the ABI, emulated with fp32 PyTorch math and bf16 storage"""
 
@@ -137,7 +145,7 @@ class EmuOps(EmuBackend):
         return _bf(y), (y.clone() if want_f32 else None), s, mean.reshape(-1), rstd.reshape(-1)
 
     def layernorm_bwd(self, dy, s, mean, rstd, gamma, dy_f32=None, p_y=0.0, seed_y=0, want_dh=False, p_h=0.0,
-                      seed_h=0, want_dbias=False, acc=None):
+                      seed_h=0, want_dbias=False, acc=None, dg_out=None, db_out=None):
         C = s.shape[-1]
         g = dy.float() + (dy_f32 if dy_f32 is not None else 0.0)
         g = (g * _drop_mask(s.shape, p_y, seed_y)).reshape(-1, C)
@@ -152,6 +160,11 @@ class EmuOps(EmuBackend):
         dbias = None
         if want_dbias:
             dbias = (dh if dh is not None else ds).reshape(-1, C).sum(0)
+        if acc is not None:
+            dgamma, dbeta = _into(acc[0], dgamma), _into(acc[1], dbeta)
+            dbias = _into(acc[2], dbias) if dbias is not None else None
+        elif dg_out is not None and not want_dbias:
+            dgamma, dbeta = _into(dg_out, dgamma), _into(db_out, dbeta)
         return _bf(ds), (_bf(dh) if dh is not None else None), dgamma, dbeta, dbias
 
     # ---- softmax
@@ -210,7 +223,7 @@ class EmuOps(EmuBackend):
         return _drop_mask(shape, pdrop, seed)
 
     def colsum(self, x, out=None):
-        return x.float().reshape(-1, x.shape[-1]).sum(0)
+        return _into(out, x.float().reshape(-1, x.shape[-1]).sum(0))
 
     # ---- parameter re-layout
     def cast_multi(self, pairs, cache):
@@ -225,8 +238,8 @@ class EmuOps(EmuBackend):
             wts = [_bf(torch.cat([w[:, :, j].t() for j in range(k) if j % s == p], 1)).contiguous() for p in range(s)]
         return wk, wts
 
-    def conv_unpack(self, dwk, Cin, k):
-        return dwk.view(dwk.shape[0], k, Cin).permute(0, 2, 1).contiguous()
+    def conv_unpack(self, dwk, Cin, k, out=None):
+        return _into(out, dwk.view(dwk.shape[0], k, Cin).permute(0, 2, 1).contiguous())
 
     @staticmethod
     def _pc_pack(w, groups, transpose):
@@ -245,7 +258,7 @@ class EmuOps(EmuBackend):
         groups = D // cg
         return self._pc_pack(w, groups, False), (self._pc_pack(w, groups, True) if want_t else None), norm2
 
-    def posconv_wn_bwd(self, dwp, g, v, norm2):
+    def posconv_wn_bwd(self, dwp, g, v, norm2, out=None):
         D, cg, k = v.shape
         groups = D // cg
         dW = dwp.view(groups, k, 64, 64)[:, :, :cg, :cg].permute(0, 3, 2, 1).reshape(D, cg, k)
@@ -253,6 +266,8 @@ class EmuOps(EmuBackend):
         t = (dW * v).sum((0, 1))
         dg = (t / nrm).reshape(g.shape)
         dv = g.reshape(1, 1, k) / nrm * (dW - v * t / norm2)
+        if out is not None:
+            return _into(out[0], dv), _into(out[1], dg)
         return dv, dg
 
     def dropout(self, x, p, seed):
@@ -282,7 +297,7 @@ class EmuOps(EmuBackend):
         y = (z - mean[:, None, :]) * rstd[:, None, :] * gamma + beta
         return _bf(gelu(y)).contiguous()
 
-    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, mom, k, stride, da):
+    def conv0_bwd(self, x, w, gamma, beta, mean, rstd, mom, k, stride, da, out=None):
         z = self._conv0_z(x, w, stride)
         xh = (z - mean[:, None, :]) * rstd[:, None, :]
         dy = da.float() * gelu_grad(xh * gamma + beta)
@@ -291,6 +306,8 @@ class EmuOps(EmuBackend):
         B, L0, C = dz.shape
         win = x.unfold(1, k, stride)  # [B, L0, k]
         dw = torch.einsum("blc,blk->ck", dz, win)
+        if out is not None:
+            return _into(out[0], dw), _into(out[1], dgamma), _into(out[2], dbeta)
         return dw, dgamma, dbeta
 
     # ---- masks / indices / casts
@@ -305,10 +322,10 @@ class EmuOps(EmuBackend):
     def rows_set(self, x, idx, vec):
         x[idx.long()] = vec.to(x.dtype)
 
-    def rows_set_bwd(self, dx, idx):
+    def rows_set_bwd(self, dx, idx, out=None):
         dvec = dx[idx.long()].float().sum(0)
         dx[idx.long()] = 0
-        return dvec
+        return _into(out, dvec)
 
     def mask_apply(self, x, row_keep=None, chan_zero=None):
         B, T, C = x.shape
@@ -339,7 +356,7 @@ class EmuOps(EmuBackend):
         q = vars2d[g * V + kidx].reshape(R, -1)
         return q, _bf(q), kidx.int(), avg, ppl
 
-    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl):
+    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl, dvars_out=None):
         R = z.shape[0]
         V = z.shape[1] // G
         N = R * G
@@ -355,7 +372,7 @@ class EmuOps(EmuBackend):
         dvars = torch.zeros(G * V, vd)
         g = torch.arange(N) % G
         dvars.index_add_(0, g * V + kidx.long(), dq.reshape(N, vd))
-        return _bf(dz.reshape(R, G * V)), dvars
+        return _bf(dz.reshape(R, G * V)), _into(dvars_out, dvars)
 
     def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w):
         R, C = x.shape

@@ -4,8 +4,9 @@ fixtures.  Run on CPU through the ABI emulation (host logic) and on the GPU thro
 
 Tolerances (bf16 activations / fp32 accumulation vs the fp32 reference; stated once, not tuned per run):
   activations  max|err| <= 3e-2 * max|ref|      loss  rel 1e-2
-  gradients    cosine >= 0.995 and rel-L2 <= 8e-2 per parameter tensor (0.99 / 0.15 for the feature encoder, the
-               post-extractor LayerNorm and the quantizer's logit projection: see grad_tol)
+  gradients    SURVEY §8c's policy: cosine >= 0.999 and rel-L2 <= 3e-2 per parameter tensor; the exceptions are listed
+               one by one in `grad_tol` with the measured value and its cause (profiles/r02_parity.md holds every
+               tensor's measured cosine / rel-L2, written by the GPU test session itself: see conftest.py)
 Integer artefacts (time mask, negative indices, frame lengths, VQ arg-max with shared noise) are bit-exact.
 """
 import os
@@ -34,7 +35,12 @@ def act_close(got, want, what, tol=3e-2):
     assert err <= tol * scale, f"{what}: max abs err {err:.4g} vs scale {scale:.4g}"
 
 
-def grad_close(got, want, what, cos_min=0.995, rel_max=8e-2):
+PARITY_LOG = []  # (case, tensor, cosine, rel-L2, cos_min, rel_max) of every gradient comparison of this session
+CASE = ["?"]
+SOFT = os.environ.get("A8_PARITY_RECORD") == "1"  # measure-only mode: record every value, fail on none
+
+
+def grad_close(got, want, what, cos_min=0.999, rel_max=3e-2):
     got, want = got.detach().double().cpu().reshape(-1), want.detach().double().cpu().reshape(-1)
     nw = want.norm().item()
     if nw < 1e-10:
@@ -42,7 +48,9 @@ def grad_close(got, want, what, cos_min=0.995, rel_max=8e-2):
         return
     cos = (got @ want / (got.norm() * want.norm() + 1e-30)).item()
     rel = ((got - want).norm() / want.norm()).item()
-    assert cos >= cos_min and rel <= rel_max, f"{what}: cosine {cos:.5f}, rel-L2 {rel:.4f}"
+    PARITY_LOG.append((CASE[0], what, cos, rel, cos_min, rel_max))
+    if not SOFT:
+        assert cos >= cos_min and rel <= rel_max, f"{what}: cosine {cos:.5f}, rel-L2 {rel:.4f} (need {cos_min} / {rel_max})"
 
 
 def check_param_grads(named_got, want):
@@ -208,68 +216,145 @@ def run_graph_case():
     return l0, l1
 
 
-def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=("mask_emb", "final_proj.layer.weight", "project_q.layer.weight",
-                                                                    "encoder.transformer.encoders.0.ffn.0.layer.weight",
-                                                                    "encoder.transformer.encoders.0.self_attn.w_O.layer.weight",
-                                                                    "encoder.ln.weight", "proj_to_input.layer.bias"),
-                         split_min=None):
+FULL_SIZE_GRADS = ("mask_emb", "final_proj.layer.weight", "project_q.layer.weight",
+                   "encoder.transformer.encoders.0.ffn.0.layer.weight",
+                   "encoder.transformer.encoders.0.self_attn.w_O.layer.weight",
+                   "encoder.ln.weight", "proj_to_input.layer.bias")
+# what the full-size case adds: the conv feature encoder (32 % of the FLOPs), its GroupNorm, the
+# post-extractor LayerNorm, the quantizer and the weight-normed positional conv
+FULL_SIZE_GRADS_FRONT = ("feature_extractor.conv_layers.0.0.weight", "feature_extractor.conv_layers.1.0.weight",
+                         "feature_extractor.conv_layers.6.0.weight", "feature_extractor.conv_layers.0.2.weight",
+                         "layer_norm.weight", "quantizer.weight_proj.weight", "quantizer.vars",
+                         "encoder.pos_conv.conv.1.weight_g", "encoder.pos_conv.conv.1.weight_v")
+
+
+def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRADS, split_min=None, train=False,
+                         layer_drop=0.0, sample_rate=16, case=None):
     """Any configuration / size (no committed fixture): the product and the oracle are driven from the same numpy seed
-    (the oracle's create_mask / sample_negative_indices are pinned to the reference by test_oracle.py), eval-mode
-    quantizer (no Gumbel noise), dropout 0.  Integer artefacts bit-exact, loss rel 1e-2, the listed gradients by
-    cosine / rel-L2 (the whole set at small sizes is covered by run_pretrain_case)."""
+    (the oracle's create_mask / sample_negative_indices are pinned to the reference by test_oracle.py), dropout 0.
+    train=False: eval-mode quantizer (arg-max, no Gumbel noise); train=True: training mode with shared Gumbel noise and,
+    with layer_drop > 0, LayerDrop decided by the same numpy draws on both sides (eight_mile: one draw per layer, a layer
+    runs iff draw >= layer_drop).  Integer artefacts bit-exact, loss rel 1e-2, the listed gradients ("all" = every
+    parameter) by cosine / rel-L2."""
     from audio8_b200 import wav2vec2 as W
-    sd = P.pretrain_state_dict(seed=11, **{k: v for k, v in cfg.items() if k != "num_heads"})
-    model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg)
+    CASE[0] = case or f"pretrain d={cfg.get('d_model', 768)} L={cfg.get('num_layers', 12)} B={B} x {L} K={K}"
+    sd = P.pretrain_state_dict(seed=11, sample_rate=sample_rate, **{k: v for k, v in cfg.items() if k != "num_heads"})
+    model = W.create_model(sample_rate=sample_rate, dropout=0.0, dropout_input=0.0, dropout_features=0.0,
+                           layer_drop=layer_drop, **cfg)
     res = model.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
-    model = model.to(device).eval()  # eval: arg-max quantizer, masking still applied (reference :937)
+    model = model.to(device).train(train)  # eval: arg-max quantizer, masking still applied (reference :937)
     if split_min is not None:
         model.encoder.split_min_layers = split_min  # force the two-segment encoder on shallow test models
-    n_vars = cfg.get("num_vq_vars", 320) * cfg.get("num_vq_groups", 2)
+    G_, V_ = cfg.get("num_vq_groups", 2), cfg.get("num_vq_vars", 320)
+    n_vars = V_ * G_
+    n_layers = cfg.get("num_layers", 12)
     loss_fn = W.create_loss(n_vars, K)
     x = torch.randn(B, L, generator=torch.Generator().manual_seed(5)) * 0.1
+    # the oracle's draws from the seed, in the reference's order: mask, one draw per layer, negatives
+    cf = R.CONV_FEATURES[sample_rate]
+    T = R.conv_out_lengths(L, cf)[-1]
+    np.random.seed(seed)
+    tmask = R.create_mask((B, T), 0.65, 10)
+    draws = [np.random.random() for _ in range(n_layers)]
+    active = [(not train) or d >= layer_drop for d in draws]
+    Tm = int(tmask[0].sum())
+    neg = R.sample_negative_indices(B, Tm, K)
+    noise = None
+    if train:
+        noise = gumbel_noise_like_torch(seed, (B * Tm * G_, V_))
+        model.quantizer.noise_override = noise.to(device)
+        if layer_drop > 0:
+            assert not all(active) and any(active), "pick a seed that drops some but not all layers"
     np.random.seed(seed)
     loss = loss_fn(model, x.to(device))
     loss.backward()
-    # the oracle's draws from the same seed, in the reference's order
-    T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
-    np.random.seed(seed)
-    tmask = R.create_mask((B, T), 0.65, 10)
-    for _ in range(cfg.get("num_layers", 12)):
-        np.random.random()
-    Tm = int(tmask[0].sum())
-    neg = R.sample_negative_indices(B, Tm, K)
     assert (loss_fn.last_neg_idx.astype(np.int64) == neg).all(), "negative indices differ from the oracle's draws"
     kidx = model.quantizer.last_indices.cpu().numpy()
+    okw = dict(n_vars=n_vars, num_heads=cfg.get("num_heads", 12), num_layers=n_layers, num_groups=G_, tau=0.5,
+               gumbel_noise=noise, conv_features=cf, active_layers=active)
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    st = R.pretrain_loss(sdg, x, tmask, neg, n_vars=n_vars, num_heads=cfg.get("num_heads", 12),
-                         num_layers=cfg.get("num_layers", 12), num_groups=cfg.get("num_vq_groups", 2), tau=0.5,
-                         gumbel_noise=None, force_idx=kidx)
+    st = R.pretrain_loss(sdg, x, tmask, neg, force_idx=kidx, **okw)
     st["loss"].backward()
     with torch.no_grad():
-        st_free = R.pretrain_loss(sd, x, tmask, neg, n_vars=n_vars, num_heads=cfg.get("num_heads", 12),
-                                  num_layers=cfg.get("num_layers", 12), num_groups=cfg.get("num_vq_groups", 2), tau=0.5,
-                                  gumbel_noise=None)
+        st_free = R.pretrain_loss(sd, x, tmask, neg, **okw)
     vq_match = (kidx == st_free["vq_idx"].numpy()).mean()
+    VQ_LOG.append((CASE[0], int((kidx != st_free["vq_idx"].numpy()).sum()), int(kidx.size)))
     assert vq_match >= 0.95, f"VQ arg-max agreement {vq_match:.4f}"
     assert abs(loss.item() - st["loss"].item()) <= 1e-2 * abs(st["loss"].item()), (loss.item(), st["loss"].item())
     got = dict(model.named_parameters())
-    for k in check_grads:
-        grad_close(got[k].grad, sdg[k].grad, "grad " + k, **grad_tol(k))
+    if check_grads == "all":
+        want = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sdg.items()}
+        for k, p_ in got.items():
+            layer = int(k.split("encoders.")[1].split(".")[0]) if "encoders." in k else None
+            if layer is not None and not active[layer]:
+                assert p_.grad is None or p_.grad.abs().max().item() == 0, f"dropped layer got a gradient: {k}"
+        check_param_grads([(k, p_.grad) for k, p_ in got.items()], want)
+    else:
+        for k in check_grads:
+            grad_close(got[k].grad, sdg[k].grad, "grad " + k, **grad_tol(k))
     return loss.item(), st["loss"].item(), vq_match
+
+
+VQ_LOG = []  # (case, code-index flips against the oracle's free arg-max, entries)
+
+
+def run_dropout_statistics(device, n_seeds=8):
+    """The BENCHMARKED configuration's dropout (0.1 at the reference's five sites) has no bit-level oracle: torch's and
+    this package's Philox streams differ.  Statistical parity instead: the loss averaged over `n_seeds` dropout seeds
+    (same weights, input, mask, negatives, Gumbel noise) agrees with the oracle's average under torch's own dropout
+    within 1 %, and both differ from the dropout-free loss in the same direction."""
+    from audio8_b200 import wav2vec2 as W
+    cfg = dict(d_model=256, num_heads=4, num_layers=3, d_ff=1024, final_dim=128, num_vq_vars=64, num_vq_groups=2)
+    B, L, K, seed = 4, 48000, 50, 21
+    sd = P.pretrain_state_dict(seed=13, **{k: v for k, v in cfg.items() if k != "num_heads"})
+    model = W.create_model(dropout=0.1, dropout_input=0.1, dropout_features=0.1, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device).train()
+    n_vars = cfg["num_vq_vars"] * cfg["num_vq_groups"]
+    loss_fn = W.create_loss(n_vars, K)
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(6)) * 0.1
+    T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+    np.random.seed(seed)
+    tmask = R.create_mask((B, T), 0.65, 10)
+    for _ in range(cfg["num_layers"]):
+        np.random.random()
+    Tm = int(tmask[0].sum())
+    neg = R.sample_negative_indices(B, Tm, K)
+    noise = gumbel_noise_like_torch(seed, (B * Tm * 2, cfg["num_vq_vars"]))
+    model.quantizer.noise_override = noise.to(device)
+    okw = dict(n_vars=n_vars, num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], num_groups=2, tau=0.5,
+               gumbel_noise=noise)
+    ours, ref = [], []
+    xd = x.to(device)
+    for i in range(n_seeds):
+        np.random.seed(seed)
+        torch.manual_seed(1000 + i)
+        ours.append(loss_fn(model, xd).item())
+        torch.manual_seed(2000 + i)
+        with torch.no_grad():
+            ref.append(R.pretrain_loss(sd, x, tmask, neg, dropout=0.1, dropout_input=0.1, dropout_features=0.1, **okw)["loss"].item())
+    with torch.no_grad():
+        base = R.pretrain_loss(sd, x, tmask, neg, **okw)["loss"].item()
+    mo, mr = float(np.mean(ours)), float(np.mean(ref))
+    assert len(set(round(v, 6) for v in ours)) > 1, "dropout did not vary with the torch seed"
+    assert abs(mo - mr) <= 1e-2 * abs(mr), f"mean loss under dropout 0.1: ours {mo:.5f} vs oracle {mr:.5f} (no dropout {base:.5f})"
+    return mo, mr, base
 
 
 def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
                          check_grads=("proj.weight", "encoder.mask_emb", "encoder.proj_to_input.layer.weight",
                                       "encoder.encoder.transformer.encoders.0.ffn.3.layer.weight",
-                                      "encoder.encoder.transformer.encoders.0.self_attn.w_Q.layer.weight")):
+                                      "encoder.encoder.transformer.encoders.0.self_attn.w_Q.layer.weight"),
+                         in_lens=None, tgt_lens=None, freeze_fx=True, case=None):
     """CTC fine-tuning step at any size (BASELINE configs[2] per GPU at full size): ragged utterance lengths, time and
     channel masks drawn by the product under a numpy seed and re-drawn for the oracle from the same seed (reference
     order: time mask, channel mask, one draw per layer), dropout 0, feature encoder frozen as in train.py's default."""
     from audio8_b200 import wav2vec2 as W
     from audio8_b200.ctc import ctc_loss
+    CASE[0] = case or f"acoustic d={cfg.get('d_model', 768)} L={cfg.get('num_layers', 12)} B={B} x {L} V={V}"
     sd = P.acoustic_state_dict(V, seed=12, **{k: v for k, v in cfg.items() if k != "num_heads"})
-    model = W.create_acoustic_model(V, dropout=0.0, freeze_fx=True, **cfg)
+    model = W.create_acoustic_model(V, dropout=0.0, freeze_fx=freeze_fx, **cfg)
     res = model.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     model = model.to(device)
@@ -279,10 +364,14 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
     x = torch.randn(B, L, generator=g) * 0.1
     in_len = torch.randint(int(0.6 * L), L + 1, (B,), generator=g)
     in_len[0] = L
+    if in_lens is not None:
+        in_len = torch.tensor(in_lens)
     for b in range(B):
         x[b, in_len[b]:] = 0
     pad_mask = torch.arange(L)[None, :] < in_len[:, None]
     tgt_len = torch.randint(max(S // 2, 1), S + 1, (B,), generator=g)
+    if tgt_lens is not None:
+        tgt_len = torch.tensor(tgt_lens)
     targets = torch.full((B, S), 1, dtype=torch.long)
     for b in range(B):
         targets[b, : tgt_len[b]] = torch.randint(4, V, (int(tgt_len[b]),), generator=g)
@@ -299,7 +388,8 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
         tm = R.create_mask((B, T), 0.5, 10)
         cm = R.create_mask((B, D), 0.1, 64)
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    lp2, fm2 = R.acoustic_forward(sdg, x, pad_mask, cfg.get("num_heads", 12), cfg.get("num_layers", 12), tm, cm)
+    lp2, fm2 = R.acoustic_forward(sdg, x, pad_mask, cfg.get("num_heads", 12), cfg.get("num_layers", 12), tm, cm,
+                                  freeze_fx=freeze_fx)
     assert (fm2.sum(-1).numpy() == out_len.cpu().numpy()).all(), "frame lengths differ"
     # CTC occupancies are exponentially sensitive to the sequence of log-probs (an untrained model spreads its mass
     # over ~10^100 alignments: the bf16-sized log-prob differences, 0.3 % rms, move dL/dlogprob by ~25 % at T=749 even
@@ -330,6 +420,6 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
             bad.append(str(e))
     assert not bad, "; ".join(bad)
     for k, p_ in got.items():
-        if "feature_extractor" in k:
+        if "feature_extractor" in k and freeze_fx:
             assert p_.grad is None, f"frozen feature encoder got a gradient: {k}"
     return loss.item(), loss2.item()

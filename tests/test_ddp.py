@@ -199,7 +199,8 @@ def _arena_worker(rank, world, port, out_dir):
         assert net._arena is not None and net._arena.used > 0, "the transformer layers did not use the gradient arena"
         in_arena = sum(1 for p in model.parameters() if p.grad is not None and
                        net._arena.buf.data_ptr() <= p.grad.data_ptr() < net._arena.buf.data_ptr() + 4 * net._arena.buf.numel())
-        assert in_arena >= 6, f"only {in_arena} gradients alias the arena (expected the six weight matrices of the layer)"
+        n_grads = sum(1 for p in model.parameters() if p.grad is not None)
+        assert in_arena == n_grads, f"only {in_arena} of {n_grads} gradients alias the arena (all of them should)"
         # accumulation: micro-step under no_sync() + synchronised micro-step = mean over ranks of the SUM of both
         model.zero_grad(set_to_none=True)
         np.random.seed(7 + rank)
@@ -215,6 +216,7 @@ def _arena_worker(rank, world, port, out_dir):
             err = (p_.grad - 2 * want[k]).abs().max().item()
             scale = want[k].abs().max().item() + 1e-8
             assert err <= 2e-4 * scale + 1e-7, f"accumulated grad {k}: {err:.3g} vs scale {scale:.3g}"
+        _layerdrop_body(rank, world, torch.device("cpu"), False)  # LayerDrop under the wrapper (defined below)
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
@@ -224,4 +226,140 @@ def _arena_worker(rank, world, port, out_dir):
 def test_arena_data_parallel_gloo_world2(tmp_path):
     world = 2
     mp.spawn(_arena_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def _layerdrop_worker(rank, world, port, out_dir, backend):
+    """with LayerDrop every rank drops DIFFERENT layers (per-rank numpy RNG).  The arena layout is planned from
+    the module structure, so a layer's block sits at the same offset on every rank whatever order backward reaches it
+    in; a rank that skipped a layer contributes zeros.  Expected: mean over ranks of the per-rank gradients (None = 0)."""
+    for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    cuda = backend == "nccl"
+    if cuda:
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        torch.set_num_threads(2)
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _layerdrop_body(rank, world, dev, cuda)
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def _layerdrop_body(rank, world, dev, cuda):
+    if True:
+        from audio8_b200 import ops
+        from audio8_b200 import wav2vec2 as W
+        from audio8_b200.parallel import DataParallel
+        if not cuda:
+            import emu
+            ops.set_backend(emu.EmuOps())
+        cfg = dict(TINY, num_layers=4)
+        torch.manual_seed(0)
+        model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, layer_drop=0.5, **cfg).to(dev).train()
+        loss_fn = W.create_loss(cfg["num_vq_vars"] * cfg["num_vq_groups"], 10)
+        L = 16000 if cuda else 5000
+        xs = [(torch.randn(2, L, generator=torch.Generator().manual_seed(100 + r)) * 0.1).to(dev) for r in range(world)]
+        import ref_wav2vec2 as R
+        T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+        seeds, seen = [], set()
+        for sd_ in range(1, 200):  # two numpy seeds whose LayerDrop outcomes differ (and drop some, not all, layers)
+            np.random.seed(sd_)
+            R.create_mask((2, T), 0.65, 10)
+            act = tuple(np.random.random() >= 0.5 for _ in range(cfg["num_layers"]))
+            if 0 < sum(act) < len(act) and act not in seen:
+                seen.add(act)
+                seeds.append(sd_)
+            if len(seeds) == world:
+                break
+        want, dropped = None, []
+        for r in range(world):
+            _, g = _local_grads(model, loss_fn, xs[r], seeds[r])
+            dropped.append(sorted(k for k, p_ in model.named_parameters() if k not in g))
+            g = {k: g.get(k, torch.zeros_like(p_)) for k, p_ in model.named_parameters()}
+            want = g if want is None else {k: want[k] + g[k] for k in g}
+        assert dropped[0] != dropped[1], "pick seeds that drop different layers on the two ranks"
+        want = {k: v / world for k, v in want.items()}
+        net = DataParallel(model)
+        tol = 2e-3 if cuda else 1e-4  # CUDA: fp32 atomics order + bf16 operand rounding is deterministic; atomics are not
+        for rep in range(3):
+            _, got = _local_grads(net, loss_fn, xs[rank], seeds[rank])
+            got = {k.replace("module.", "", 1): v for k, v in got.items()}
+            assert set(got) == set(want), "a rank that dropped a layer must still hold that layer's averaged gradient"
+            for k in want:
+                err = (got[k] - want[k]).abs().max().item()
+                scale = want[k].abs().max().item() + 1e-8
+                assert err <= tol * scale + 1e-7, f"rank {rank} step {rep} grad {k}: {err:.3g} vs scale {scale:.3g}"
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    """the CUDA kernels + NCCL: audio8_b200.parallel.DataParallel against the mean of the per-rank gradients computed
+    without any wrapper, over 4 steps (eager, CUDA-graph capture, replays)"""
+    for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from audio8_b200 import wav2vec2 as W
+        from audio8_b200.parallel import DataParallel
+        cfg = dict(d_model=256, num_heads=4, num_layers=3, d_ff=1024, final_dim=128, num_vq_vars=64, num_vq_groups=2)
+        torch.manual_seed(0)
+        model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg).to(dev).train()
+        loss_fn = W.create_loss(128, 20)
+        xs = [(torch.randn(3, 32000, generator=torch.Generator().manual_seed(100 + r)) * 0.1).to(dev) for r in range(world)]
+        want = None
+        for r in range(world):
+            _, g = _local_grads(model, loss_fn, xs[r], 7 + r)
+            want = g if want is None else {k: want[k] + g[k] for k in g}
+        want = {k: v / world for k, v in want.items()}
+        net = DataParallel(model)
+        for rep in range(4):
+            _, got = _local_grads(net, loss_fn, xs[rank], 7 + rank)
+            torch.cuda.synchronize()
+            got = {k.replace("module.", "", 1): v for k, v in got.items()}
+            assert set(got) == set(want)
+            for k in want:
+                err = (got[k].float() - want[k].float()).abs().max().item()
+                scale = want[k].abs().max().item() + 1e-8
+                assert err <= 3e-3 * scale + 1e-7, f"rank {rank} step {rep} grad {k}: {err:.3g} vs scale {scale:.3g}"
+        a = net._arena
+        n_in = sum(1 for p in model.parameters() if p.grad is not None and a.buf.data_ptr() <= p.grad.data_ptr() < a.buf.data_ptr() + 4 * a.buf.numel())
+        assert n_in == sum(1 for p in model.parameters() if p.grad is not None), "every gradient should live in the arena"
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_arena_data_parallel_nccl_world2(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+@pytest.mark.gpu
+def test_arena_data_parallel_layerdrop_nccl_world2(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_layerdrop_worker, args=(world, _free_port(), str(tmp_path), "nccl"), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
