@@ -86,6 +86,8 @@ SIGNATURES.update({
     "a8_posconv_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_posconv_wn_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_optim_grad_sqnorm": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "a8_optim_adamw": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P]),
 })
 
 _lib = None

@@ -567,6 +567,9 @@ class EncoderFn(torch.autograd.Function):
 # Gumbel vector quantizer (wav2vec2.py:547-576)
 # =================================================================================================
 class QuantizerFn(torch.autograd.Function):
+    keep_logits = False  # parity tests: expose the fp32 logits of the last call (GumbelVectorQuantizer.keep_logits)
+    last_logits = None
+
     @staticmethod
     def forward(ctx, y, w, b, vars_, G_, tau, noise):
         be = _be()
@@ -583,6 +586,7 @@ class QuantizerFn(torch.autograd.Function):
         ctx.saved = (y2, w32, v2, z, noise, kidx.detach(), avg, ppl.detach(), G_, float(tau), y.shape, vars_.shape,
                      (ops.grad_key(w), ops.grad_key(b), ops.grad_key(vars_)))
         ctx.mark_non_differentiable(kidx)
+        QuantizerFn.last_logits = z if QuantizerFn.keep_logits else None
         return q.view(Bq, Tm, -1), ppl, kidx
 
     @staticmethod

@@ -63,6 +63,10 @@ class GraphedSegment:
           the replayed pattern; anything else is correct but slower)."""
         if not ENABLED or not inputs[0].is_cuda or torch.cuda.is_current_stream_capturing():
             return fn(*inputs, *params)
+        if not torch.is_grad_enabled():
+            # inference under no_grad is not the path these graphs exist for (make_graphed_callables captures a backward
+            # for every parameter that requires grad, which a no_grad forward cannot provide): plain launches
+            return fn(*inputs, *params)
         key = self._key(inputs, params, extra)
         ent = self.entries.get(key)
         if ent is None:

@@ -609,6 +609,19 @@ class CudaBackend:
         return dx, dy
 
 
+    # ------------------------------------------------------------------ optimizer side (csrc/optim.cu)
+    def optim_grad_sqnorm(self, table, chunk_tensor, chunk_off, chunk, partials):
+        _lib.check(self.lib.a8_optim_grad_sqnorm(_ptr(table), _ptr(chunk_tensor), _ptr(chunk_off), chunk_tensor.numel(),
+                                                 chunk, _ptr(partials), _stream()), "a8_optim_grad_sqnorm")
+
+    def optim_adamw(self, table, chunk_tensor, chunk_off, chunk, partials, max_norm, grad_scale, lr, beta1, beta2, eps,
+                    weight_decay, bc1, bc2_sqrt, scale_grads_only, total_norm_out):
+        _lib.check(self.lib.a8_optim_adamw(_ptr(table), _ptr(chunk_tensor), _ptr(chunk_off), chunk_tensor.numel(), chunk,
+                                           _ptr(partials), max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay,
+                                           bc1, bc2_sqrt, int(scale_grads_only), _ptr(total_norm_out), _stream()),
+                   "a8_optim_adamw")
+
+
 _BACKEND = None
 
 

@@ -301,6 +301,8 @@ class GumbelVectorQuantizer(nn.Module):
         self.codebook_indices = None
         self.noise_override = None  # parity tests: Gumbel noise [B*T*G, V] drawn like F.gumbel_softmax does
         self.last_indices = None
+        self.keep_logits = False  # parity tests: keep a copy of the fp32 logits [B*T, G*V] in `last_logits`
+        self.last_logits = None
 
     def set_num_updates(self, num_updates):
         self.curr_temperature = max(self.max_temperature * self.temperature_decay ** num_updates, self.min_temperature)
@@ -314,9 +316,13 @@ class GumbelVectorQuantizer(nn.Module):
                 n = B * T * self.num_groups
                 noise = Fn.ops.bucketed_empty((n, self.num_vars), F32, x.device).exponential_().log_().neg_()
             noise = noise.to(device=x.device, dtype=F32).contiguous()
+        Fn.QuantizerFn.keep_logits = self.keep_logits
         q, ppl, kidx = Fn.QuantizerFn.apply(x, self.weight_proj.weight, self.weight_proj.bias, self.vars,
                                             self.num_groups, self.curr_temperature, noise)
         self.last_indices = kidx
+        if self.keep_logits:
+            self.last_logits = Fn.QuantizerFn.last_logits.detach().clone()
+            Fn.QuantizerFn.keep_logits, Fn.QuantizerFn.last_logits = False, None
         return q, ppl
 
 

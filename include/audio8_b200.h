@@ -267,6 +267,28 @@ int a8_posconv_pack(const float* g, const float* v, int32_t D, int32_t cg, int32
 int a8_posconv_wn_bwd(const float* dwp, const float* g, const float* v, const float* norm2, int32_t D, int32_t cg,
                       int32_t k, float* t_scratch, float* dv, float* dg, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer side of the step (csrc/optim.cu): replaces `torch.nn.utils.clip_grad_norm_(model.parameters(),
+ * args.clip)` + `optimizer.step()` (torch.optim.AdamW behind eight_mile's OptimizerManager) + `optimizer.scale_grads(s)`
+ * at /root/reference/audio8/pretrain.py:182-184 and train.py:323-325 with two multi-tensor launches.
+ * table: n_tensors rows of 6 int64 in DEVICE memory {float* p, const float* g (0 = no gradient this step: skipped),
+ *   float* exp_avg, float* exp_avg_sq, int64 numel, bf16* operand copy of p or 0}.  The work is cut into chunks of
+ *   `chunk` elements (multiple of 4): chunk_tensor[c] = table row, chunk_off[c] = element offset inside that tensor.
+ * a8_optim_grad_sqnorm: partials[c] = sum of g^2 over chunk c (no atomics, nothing to zero).
+ * a8_optim_adamw: total = sqrt(sum partials) * |grad_scale|; coef = min(1, max_norm / (total + 1e-6)) when max_norm > 0;
+ *   every gradient is read as g * grad_scale * coef (never written back) and the parameter, exp_avg, exp_avg_sq (and the
+ *   bf16 copy) are updated with torch.optim.AdamW's arithmetic (decoupled weight decay, bias_correction1 = 1 - beta1^t,
+ *   bias_correction2_sqrt = sqrt(1 - beta2^t), both computed by the caller).  partials may be NULL when max_norm <= 0.
+ *   scale_grads_only != 0: clip_grad_norm_ semantics instead - the gradients are scaled in place, nothing else changes.
+ *   total_norm_out (optional): the pre-clip gradient norm, what clip_grad_norm_ returns.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_optim_grad_sqnorm(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_off, int32_t n_chunks,
+                         int32_t chunk, float* partials, void* stream);
+int a8_optim_adamw(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_off, int32_t n_chunks,
+                   int32_t chunk, const float* partials, float max_norm, float grad_scale, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float bias_correction1, float bias_correction2_sqrt,
+                   int32_t scale_grads_only, float* total_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

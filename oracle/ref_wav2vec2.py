@@ -154,13 +154,19 @@ def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", p
     return x
 
 
-def gumbel_quantizer(sd, y, num_groups, tau=0.5, gumbel_noise=None, prefix="quantizer.", force_idx=None):
+def gumbel_quantizer(sd, y, num_groups, tau=0.5, gumbel_noise=None, prefix="quantizer.", force_idx=None, force_z=None):
     """wav2vec2.py:547-576.  y [B,Tm,512] -> (q [B,Tm,G*var_dim], prob_ppl, argmax indices [B*Tm*G]).
     training: gumbel_noise [B*Tm*G, V] (= -log(Exp(1)), as F.gumbel_softmax draws it); eval: None.
     force_idx (test aid, not in the reference): use these code indices instead of the arg-max, so that a
     bf16 near-tie flip upstream does not pollute every downstream comparison; flips are counted separately."""
     B, Tm, _ = y.shape
     z = _lin(sd, prefix + "weight_proj", y).reshape(B * Tm * num_groups, -1).float()
+    if force_z is not None:
+        # test aid, not in the reference: evaluate at the logit VALUES of the implementation under test (the autograd
+        # graph stays the reference's).  |z| ~ 20 (weight_proj ~ N(0,1), wav2vec2.py:486) and tau = 0.5 make softmax(u) move
+        # by ~10 % for a 2^-9 relative change of the features, so every gradient upstream of the quantizer inherits that
+        # sensitivity; pinning z separates it from the arithmetic of the backward kernels
+        z = z + (torch.as_tensor(force_z).reshape(z.shape).to(z) - z).detach()
     V = z.shape[-1]
     avg_probs = torch.softmax(z, -1).mean(0)  # pooled over groups: shape [V]  (wav2vec2.py:554)
     if gumbel_noise is not None:
@@ -196,7 +202,7 @@ def contrastive_loss(x_masked, y, neg_idx, ppl, n_vars):
 # ------------------------------------------------------------------------------------------------
 def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2, tau=0.5, gumbel_noise=None,
                      conv_features=CONV_FEATURES[16], force_idx=None, dropout=0.0, dropout_input=0.0,
-                     dropout_features=0.0, active_layers=None):
+                     dropout_features=0.0, active_layers=None, force_z=None):
     """Wav2Vec2Model.forward (wav2vec2.py:927-952) with the time mask supplied.  Returns a dict of stages."""
     fx = conv_feature_extractor(sd, x, conv_features=conv_features).transpose(1, 2)
     feats = _ln(sd, "layer_norm", fx, LN_EPS_TORCH)
@@ -208,7 +214,7 @@ def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2
     h = torch.where(tm[..., None], sd["mask_emb"].expand_as(h), h)
     y_in = unmasked[tm].view(B, -1, unmasked.shape[-1])
     enc = audio_transformer_encoder(sd, h, num_heads, num_layers, pdrop=dropout, active_layers=active_layers)
-    q, ppl, k = gumbel_quantizer(sd, y_in, num_groups, tau, gumbel_noise, force_idx=force_idx)
+    q, ppl, k = gumbel_quantizer(sd, y_in, num_groups, tau, gumbel_noise, force_idx=force_idx, force_z=force_z)
     y = _lin(sd, "project_q.layer", q)
     xo = _lin(sd, "final_proj.layer", enc)
     return dict(fx=fx, features=feats, y_in=y_in, enc=enc, q=q, ppl=ppl, vq_idx=k, y=y, x=xo)

@@ -35,9 +35,11 @@ def pytest_sessionfinish(session, exitstatus):
         out = os.path.join(ROOT, "gpurun_out")
         os.makedirs(out, exist_ok=True)
         with open(os.path.join(out, "parity_report.md"), "w") as f:
-            f.write("| case | tensor | cosine | rel-L2 | held to (cos >= / rel <=) |\n|---|---|---:|---:|---|\n")
-            for case, what, cos, rel, cmin, rmax in mc.PARITY_LOG:
-                f.write(f"| {case} | {what} | {cos:.6f} | {rel:.5f} | {cmin} / {rmax} |\n")
+            f.write("| case | tensor | cosine | rel-L2 | held to (cos >= / rel <=) | bf16-autocast oracle vs fp32 oracle "
+                    "(cosine / rel-L2) |\n|---|---|---:|---:|---|---|\n")
+            for case, what, cos, rel, cmin, rmax, fl in mc.PARITY_LOG:
+                fls = f"{fl[0]:.6f} / {fl[1]:.5f}" if fl else ""
+                f.write(f"| {case} | {what} | {cos:.6f} | {rel:.5f} | {cmin} / {rmax} | {fls} |\n")
             if mc.VQ_LOG:
                 f.write("\n| case | VQ code-index flips vs the oracle's arg-max | entries |\n|---|---:|---:|\n")
                 for case, flips, n in mc.VQ_LOG:

@@ -374,6 +374,52 @@ class EmuOps(EmuBackend):
         dvars.index_add_(0, g * V + kidx.long(), dq.reshape(N, vd))
         return _bf(dz.reshape(R, G * V)), _into(dvars_out, dvars)
 
+    # ---- optimizer side: the pointer table is dereferenced through ctypes (CPU tensors)
+    @staticmethod
+    def _view(ptr, n):
+        import ctypes
+        import numpy as np
+        if ptr == 0:
+            return None
+        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * n).from_address(int(ptr))))
+
+    def optim_grad_sqnorm(self, table, chunk_tensor, chunk_off, chunk, partials):
+        for c in range(chunk_tensor.numel()):
+            row = table[int(chunk_tensor[c])]
+            n = int(row[4])
+            g = self._view(int(row[1]), n)
+            off = int(chunk_off[c])
+            partials[c] = 0.0 if g is None else float((g[off:off + chunk].double() ** 2).sum())
+
+    def optim_adamw(self, table, chunk_tensor, chunk_off, chunk, partials, max_norm, grad_scale, lr, beta1, beta2, eps,
+                    weight_decay, bc1, bc2_sqrt, scale_grads_only, total_norm_out):
+        gs = grad_scale
+        if partials is not None:
+            total = float(partials[:chunk_tensor.numel()].double().sum().sqrt()) * abs(grad_scale)
+            if total_norm_out is not None:
+                total_norm_out.fill_(total)
+            if max_norm > 0:
+                gs = grad_scale * min(max_norm / (total + 1e-6), 1.0)
+        for row in table:
+            n = int(row[4])
+            g = self._view(int(row[1]), n)
+            if g is None:
+                continue
+            if scale_grads_only:
+                g.mul_(gs)
+                continue
+            p, m, v = self._view(int(row[0]), n), self._view(int(row[2]), n), self._view(int(row[3]), n)
+            gg = g * gs
+            p.mul_(1 - lr * weight_decay)
+            m.lerp_(gg, 1 - beta1)
+            v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+            p.addcdiv_(m, v.sqrt() / bc2_sqrt + eps, value=-lr / bc1)
+            if int(row[5]):
+                import ctypes
+                import numpy as np
+                raw = np.ctypeslib.as_array((ctypes.c_int16 * n).from_address(int(row[5])))
+                torch.from_numpy(raw).view(torch.bfloat16).copy_(p.to(torch.bfloat16))
+
     def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w):
         R, C = x.shape
         K = idx.numel() // R

@@ -40,20 +40,33 @@ CASE = ["?"]
 SOFT = os.environ.get("A8_PARITY_RECORD") == "1"  # measure-only mode: record every value, fail on none
 
 
-def grad_close(got, want, what, cos_min=0.999, rel_max=3e-2):
+def _cos_rel(got, want):
     got, want = got.detach().double().cpu().reshape(-1), want.detach().double().cpu().reshape(-1)
-    nw = want.norm().item()
-    if nw < 1e-10:
-        assert got.norm().item() < 1e-6, f"{what}: expected ~0 gradient"
-        return
     cos = (got @ want / (got.norm() * want.norm() + 1e-30)).item()
-    rel = ((got - want).norm() / want.norm()).item()
-    PARITY_LOG.append((CASE[0], what, cos, rel, cos_min, rel_max))
-    if not SOFT:
-        assert cos >= cos_min and rel <= rel_max, f"{what}: cosine {cos:.5f}, rel-L2 {rel:.4f} (need {cos_min} / {rel_max})"
+    return cos, ((got - want).norm() / (want.norm() + 1e-30)).item()
 
 
-def check_param_grads(named_got, want):
+def grad_close(got, want, what, cos_min=0.999, rel_max=3e-2, floor=None):
+    """floor: the same gradient from the ORACLE run under torch's bf16 autocast (its distance to the fp32 oracle is the
+    noise floor of bf16 activation storage for this tensor).  A tensor outside (cos_min, rel_max) still passes when it
+    is within 1.5x that floor: the deviation is then the storage format's, not the kernels'.  Both are reported."""
+    nw = want.detach().double().norm().item()
+    if nw < 1e-10:
+        assert got.detach().double().norm().item() < 1e-6, f"{what}: expected ~0 gradient"
+        return
+    cos, rel = _cos_rel(got, want)
+    fl = _cos_rel(floor, want) if floor is not None else None
+    PARITY_LOG.append((CASE[0], what, cos, rel, cos_min, rel_max, fl))
+    if SOFT:
+        return
+    ok = cos >= cos_min and rel <= rel_max
+    if not ok and fl is not None:
+        ok = rel <= 1.5 * fl[1] and (1.0 - cos) <= 2.25 * (1.0 - fl[0])
+    assert ok, (f"{what}: cosine {cos:.5f}, rel-L2 {rel:.4f} (need {cos_min} / {rel_max}"
+                + (f"; bf16-autocast oracle floor: cosine {fl[0]:.5f}, rel-L2 {fl[1]:.4f})" if fl else ")"))
+
+
+def check_param_grads(named_got, want, pinned=True, label="grad "):
     """want: dict name -> reference grad.  The key-projection bias gradient is zero in exact arithmetic (softmax is
     shift invariant along keys); in bf16 it is rounding noise, bounded here against the query-bias gradient."""
     for k, g in named_got:
@@ -62,13 +75,21 @@ def check_param_grads(named_got, want):
             ref = want[k.replace("w_K", "w_Q")].norm().item()
             assert g.norm().item() <= 0.1 * ref + 1e-6, f"grad {k}: |g| {g.norm().item():.3g} vs |dq bias| {ref:.3g}"
             continue
-        grad_close(g, want[k], "grad " + k, **grad_tol(k))
+        grad_close(g, want[k], label + k, **grad_tol(k, pinned))
 
 
-def grad_tol(name):
-    # everything upstream of the Gumbel quantizer's logits: weight_proj is N(0,1)-initialised (wav2vec2.py:486), so
-    # |logit| ~ 20 and a 2^-9 relative (bf16) perturbation of the features moves softmax(u) by ~10 %
-    if "feature_extractor" in name or name.startswith("layer_norm") or "quantizer.weight_proj" in name:
+def upstream_of_quantizer(name):
+    return "feature_extractor" in name or name.startswith("layer_norm") or "quantizer.weight_proj" in name
+
+
+def grad_tol(name, pinned=True):
+    """SURVEY §8c's 0.999 / 3e-2 for every tensor when the oracle is evaluated at OUR quantizer logits (`force_z`).
+    With free-running logits the tensors upstream of the quantizer inherit the sensitivity of softmax((z + noise) / 0.5)
+    at |z| ~ 20 (weight_proj ~ N(0,1), wav2vec2.py:486): a 2^-9 relative (bf16) perturbation of the conv features moves the
+    probabilities by ~10 %.  Measured on the B200: cosine 0.9937-0.9990, rel-L2 0.045-0.112 (profiles/r02_parity.md), the
+    same value on every conv layer of a case, i.e. one perturbation at the logits carried through linear maps — and the
+    same tensors sit at <= 3e-2 once the logits are pinned, which is the check that holds the kernels to account."""
+    if not pinned and upstream_of_quantizer(name):
         return dict(cos_min=0.99, rel_max=0.15)
     return {}
 
@@ -92,9 +113,12 @@ def run_pretrain_case(device, mode="train"):
     if mode == "train":
         noise = gumbel_noise_like_torch(seed, (B * Tm * cfg["num_vq_groups"], cfg["num_vq_vars"]))
         model.quantizer.noise_override = noise.to(device)
+    model.quantizer.keep_logits = True
+    CASE[0] = f"tiny pretrain fixture ({mode}, {device})"
     np.random.seed(seed)
     loss = loss_fn(model, x.to(device))
     loss.backward()
+    z_ours = model.quantizer.last_logits.float().cpu()
     # ---- integer artefacts: bit-exact against the fixture written from the unmodified reference
     np.random.seed(seed)
     xo, yo, ppl, tm = model(x.to(device))
@@ -114,12 +138,18 @@ def run_pretrain_case(device, mode="train"):
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     st = R.pretrain_loss(sdg, x, tmask, gold[mode + "_neg_idx"].astype(np.int64), force_idx=kidx, **okw)
     st["loss"].backward()
+    # second oracle pass evaluated at OUR quantizer logits: every gradient is held to 0.999 / 3e-2 there (see grad_tol)
+    sdz = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    R.pretrain_loss(sdz, x, tmask, gold[mode + "_neg_idx"].astype(np.int64), force_idx=kidx, force_z=z_ours, **okw)["loss"].backward()
+    check_param_grads([(k, p.grad) for k, p in model.named_parameters()], {k: v.grad for k, v in sdz.items()},
+                      pinned=True, label="grad [logits pinned] ")
     act_close(xo, st["x"], "x (context outputs)")
     act_close(xo.cpu()[:, ::7, ::5], torch.from_numpy(gold[mode + "_x"]), "x vs fixture")
     act_close(yo, st["y"], "y (quantized targets)")
     assert abs(ppl.item() - st["ppl"].item()) <= 2e-2 * st["ppl"].item(), (ppl.item(), st["ppl"].item())
     assert abs(loss.item() - st["loss"].item()) <= 1e-2 * abs(st["loss"].item()), (loss.item(), st["loss"].item())
-    check_param_grads([(k, p.grad) for k, p in model.named_parameters()], {k: v.grad for k, v in sdg.items()})
+    check_param_grads([(k, p.grad) for k, p in model.named_parameters()], {k: v.grad for k, v in sdg.items()},
+                      pinned=False, label="grad [free logits] ")
     return loss.item(), st["loss"].item(), vq_match
 
 
@@ -229,7 +259,7 @@ FULL_SIZE_GRADS_FRONT = ("feature_extractor.conv_layers.0.0.weight", "feature_ex
 
 
 def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRADS, split_min=None, train=False,
-                         layer_drop=0.0, sample_rate=16, case=None):
+                         layer_drop=0.0, sample_rate=16, case=None, bf16_floor=False):
     """Any configuration / size (no committed fixture): the product and the oracle are driven from the same numpy seed
     (the oracle's create_mask / sample_negative_indices are pinned to the reference by test_oracle.py), dropout 0.
     train=False: eval-mode quantizer (arg-max, no Gumbel noise); train=True: training mode with shared Gumbel noise and,
@@ -266,11 +296,13 @@ def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRA
         model.quantizer.noise_override = noise.to(device)
         if layer_drop > 0:
             assert not all(active) and any(active), "pick a seed that drops some but not all layers"
+    model.quantizer.keep_logits = True
     np.random.seed(seed)
     loss = loss_fn(model, x.to(device))
     loss.backward()
     assert (loss_fn.last_neg_idx.astype(np.int64) == neg).all(), "negative indices differ from the oracle's draws"
     kidx = model.quantizer.last_indices.cpu().numpy()
+    z_ours = model.quantizer.last_logits.float().cpu()
     okw = dict(n_vars=n_vars, num_heads=cfg.get("num_heads", 12), num_layers=n_layers, num_groups=G_, tau=0.5,
                gumbel_noise=noise, conv_features=cf, active_layers=active)
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -283,16 +315,32 @@ def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRA
     assert vq_match >= 0.95, f"VQ arg-max agreement {vq_match:.4f}"
     assert abs(loss.item() - st["loss"].item()) <= 1e-2 * abs(st["loss"].item()), (loss.item(), st["loss"].item())
     got = dict(model.named_parameters())
-    if check_grads == "all":
-        want = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sdg.items()}
-        for k, p_ in got.items():
-            layer = int(k.split("encoders.")[1].split(".")[0]) if "encoders." in k else None
-            if layer is not None and not active[layer]:
-                assert p_.grad is None or p_.grad.abs().max().item() == 0, f"dropped layer got a gradient: {k}"
-        check_param_grads([(k, p_.grad) for k, p_ in got.items()], want)
-    else:
-        for k in check_grads:
-            grad_close(got[k].grad, sdg[k].grad, "grad " + k, **grad_tol(k))
+    names = list(got) if check_grads == "all" else list(check_grads)
+    # the oracle evaluated at OUR quantizer logits: the pass that holds every gradient to 0.999 / 3e-2 (see grad_tol)
+    sdz = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    R.pretrain_loss(sdz, x, tmask, neg, force_idx=kidx, force_z=z_ours, **okw)["loss"].backward()
+    floor = {}
+    if bf16_floor and torch.cuda.is_available():
+        # noise floor of bf16 activation storage: the SAME oracle under torch's bf16 autocast on the GPU (cuBLAS / cuDNN
+        # bf16 kernels, fp32 LayerNorm / softmax), same draws, same pinned logits, against the fp32 CPU oracle
+        sdb = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
+        okb = dict(okw, gumbel_noise=noise.cuda() if noise is not None else None)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            lb = R.pretrain_loss(sdb, x.cuda(), tmask, neg, force_idx=kidx, force_z=z_ours.cuda(), **okb)["loss"]
+        lb.backward()
+        floor = {k: v.grad.float().cpu() for k, v in sdb.items() if v.grad is not None}
+    for k in names:
+        layer = int(k.split("encoders.")[1].split(".")[0]) if "encoders." in k else None
+        if layer is not None and not active[layer]:
+            assert got[k].grad is None or got[k].grad.abs().max().item() == 0, f"dropped layer got a gradient: {k}"
+            continue
+        if k.endswith("w_K.layer.bias"):  # zero in exact arithmetic (softmax is shift invariant along keys)
+            ref = sdg[k.replace("w_K", "w_Q")].grad.norm().item()
+            assert got[k].grad.norm().item() <= 0.1 * ref + 1e-6
+            continue
+        grad_close(got[k].grad, sdz[k].grad, "grad [logits pinned] " + k, floor=floor.get(k), **grad_tol(k, True))
+        if upstream_of_quantizer(k):  # reported (and loosely bounded) with free-running logits as well
+            grad_close(got[k].grad, sdg[k].grad, "grad [free logits] " + k, **grad_tol(k, False))
     return loss.item(), st["loss"].item(), vq_match
 
 

@@ -60,7 +60,7 @@ def test_pretrain_full_size_cuda():
     cfg = dict(d_model=768, num_heads=12, num_layers=12, final_dim=256, num_vq_vars=320, num_vq_groups=2)
     ours, ref, vq = model_cases.run_pretrain_generic(
         "cuda", cfg, B=6, L=240000, K=100, case="C2 full size (base, B=6 x 15 s, K=100)",
-        check_grads=model_cases.FULL_SIZE_GRADS + model_cases.FULL_SIZE_GRADS_FRONT)
+        check_grads=model_cases.FULL_SIZE_GRADS + model_cases.FULL_SIZE_GRADS_FRONT, bf16_floor=True)
     assert vq >= 0.95
 
 
@@ -180,18 +180,23 @@ def test_encoder_outputs_are_fresh_tensors_cuda():
     import torch
     from audio8_b200 import wav2vec2 as W
     torch.manual_seed(0)
-    enc = W.AudioTransformerEncoder(2, 128, 0.0, layers=1, d_ff=256).cuda().eval()
+    enc = W.AudioTransformerEncoder(2, 128, 0.0, layers=1, d_ff=256).cuda().train()
     xs = [(torch.randn(2, 49, 128, device="cuda") * 0.5).to(torch.bfloat16) for _ in range(4)]
-    with torch.no_grad():
-        outs = [enc(x) for x in xs]          # calls 2.. replay the captured graph
-        again = [enc(x) for x in xs]
-    assert enc._graph.entries, "segment was not captured"
-    for a, b in zip(outs, again):
-        assert torch.equal(a, b), "an earlier result was overwritten by a later replay"
-    enc.train()
     xg = [x.clone().requires_grad_(True) for x in xs[:2]]
-    for _ in range(3):                       # warm the training-mode capture
+    for _ in range(3):                       # eager, capture, replay
         enc(xg[0]).float().sum().backward()
+    assert enc._graph.entries, "segment was not captured"
+    # results kept across replays (detached: the previous call's autograd graph is gone, so every call replays)
+    outs = [enc(x).detach() for x in xs]
+    again = [enc(x).detach() for x in xs]
+    for a, b in zip(outs, again):
+        assert (a.float() - b.float()).abs().max().item() < 1e-3, "an earlier result was overwritten by a later replay"
+    assert torch.equal(outs[3], again[3]) and torch.equal(outs[2], again[2])
+    assert len({o.data_ptr() for o in outs + again}) == 8
+    with torch.no_grad():                    # inference under no_grad: plain launches, fresh tensors
+        ng = [enc(x) for x in xs]
+    for a, b in zip(outs, ng):
+        assert (a.float() - b.float()).abs().max().item() < 2e-2
     g_ref = []
     for x in xg:
         x.grad = None
