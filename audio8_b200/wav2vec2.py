@@ -696,3 +696,61 @@ def create_acoustic_model(num_labels, sample_rate=16, d_model=768, num_heads=12,
     return Wav2Vec2AcousticModel(num_labels, CONV_FEATURES[sample_rate], d_model, num_heads, num_layers, dropout, d_ff,
                                  dropout_input, 0.0, timestep_masking, channel_masking, timestep_mask_len,
                                  channel_mask_len, layer_drop, freeze_fx)
+
+
+# --------------------------------------------------------------------------------------------------
+# fairseq checkpoint import (reference wav2vec2.py:36-186): same function names, same key mapping
+# --------------------------------------------------------------------------------------------------
+_FAIRSEQ_LAYER = (("self_attn.k_proj", "self_attn.w_K.layer"), ("self_attn.v_proj", "self_attn.w_V.layer"),
+                  ("self_attn.q_proj", "self_attn.w_Q.layer"), ("self_attn.out_proj", "self_attn.w_O.layer"),
+                  ("self_attn_layer_norm", "ln2"), ("fc1", "ffn.0.layer"), ("fc2", "ffn.3.layer"), ("final_layer_norm", "ln1"))
+
+
+def fairseq_key_map(num_layers, ctc=False, sr=16):
+    """{fairseq key: audio8 key} for a checkpoint with `num_layers` transformer layers: what the reference's
+    `convert_keys` renames (W2V_MAP for a pre-training checkpoint, W2V_CTC_MAP[sr] for a fine-tuned one,
+    wav2vec2.py:36-151); every other key keeps its name."""
+    src, dst = ("w2v_encoder.w2v_model.", "encoder.") if ctc else ("", "")
+    m = {}
+    for i in range(num_layers):
+        for fs, a8 in _FAIRSEQ_LAYER:
+            for leaf in ("weight", "bias"):
+                m[f"{src}encoder.layers.{i}.{fs}.{leaf}"] = f"{dst}encoder.transformer.encoders.{i}.{a8}.{leaf}"
+    for leaf in ("weight", "bias"):
+        m[f"{src}post_extract_proj.{leaf}"] = f"{dst}proj_to_input.layer.{leaf}"
+        m[f"{src}encoder.layer_norm.{leaf}"] = f"{dst}encoder.ln.{leaf}"
+    for leaf in ("bias", "weight_g", "weight_v"):
+        m[f"{src}encoder.pos_conv.0.{leaf}"] = f"{dst}encoder.pos_conv.conv.1.{leaf}"
+    if not ctc:
+        for name in ("project_q", "final_proj"):
+            for leaf in ("weight", "bias"):
+                m[f"{name}.{leaf}"] = f"{name}.layer.{leaf}"
+        return m
+    for i in range(len(CONV_FEATURES[sr])):
+        m[f"{src}feature_extractor.conv_layers.{i}.0.weight"] = f"{dst}feature_extractor.conv_layers.{i}.0.weight"
+    for leaf in ("weight", "bias"):
+        m[f"{src}feature_extractor.conv_layers.0.2.{leaf}"] = f"{dst}feature_extractor.conv_layers.0.2.{leaf}"
+        m[f"{src}layer_norm.{leaf}"] = f"{dst}layer_norm.{leaf}"
+        m[f"w2v_encoder.proj.{leaf}"] = f"proj.{leaf}"
+    m[f"{src}mask_emb"] = f"{dst}mask_emb"
+    return m
+
+
+def convert_keys(num_layers, d, ctc=False, sr=16):
+    """rename a fairseq state dict (consumed, like the reference pops from it); a mapped key missing from `d` raises
+    KeyError as in the reference (wav2vec2.py:154-168)"""
+    out = {}
+    for k, v in fairseq_key_map(num_layers, ctc, sr).items():
+        out[v] = d.pop(k)
+    out.update(d)
+    return out
+
+
+def load_fairseq_bin(w2v, bin_file, ctc=False, sr=16):
+    """Reference wav2vec2.py:171-186: load a fairseq `.pt`/`.bin` checkpoint (`{"model": state_dict}`) into a drop-in
+    model; returns {'missing': [...], 'unexpected': [...]} from a non-strict load."""
+    transformer = w2v.encoder.encoder.transformer if ctc else w2v.encoder.transformer
+    d = torch.load(bin_file, map_location="cpu")["model"]
+    mapped = convert_keys(len(transformer.encoders), d, ctc, sr)
+    res = w2v.load_state_dict(mapped, strict=False)
+    return {"missing": list(res.missing_keys), "unexpected": list(res.unexpected_keys)}
