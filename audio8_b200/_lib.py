@@ -45,6 +45,7 @@ SIGNATURES = {
     "a8_launch_count_add": (_I, [_L]),
     "a8_set_seed_source": (_I, [_P]),
     "a8_gemm": (_I, [C.POINTER(Gemm), _P]),
+    "a8_gemm_group": (_I, [C.POINTER(Gemm), _I, _P]),
     "a8_ctc_scratch_floats": (_Z, [_I, _I, _I]),
     "a8_ctc_greedy": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P]),
     "a8_ctc_prep": (_I, [_P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -157,3 +157,59 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   if (g.a.major == MAJOR_K && g.b.major == MAJOR_MN) return launch_kmn(ek, bn, cl, ma, mb, kp, stream);
   return launch_mnmn(ek, bn, cl, ma, mb, kp, stream);
 }
+
+
+// One persistent launch over n problems that share operand majors, coordinate maps, tile shape, split-K factor and
+// epilogue kind (see GroupParams in gemm_tc_kernel.cuh).  Used for the weight-gradient GEMMs of the transformer stack:
+// every layer's dW = dY^T X (4 per layer) is deferred to the end of the stack's backward and run as one kernel.
+extern "C" int a8_gemm_group(const a8_gemm_t* gs, int32_t n, void* stream_v) {
+  A8_REQUIRE(gs != nullptr && n >= 1 && n <= GROUP_MAX, "gemm_group: %d problems (1..%d supported per launch)", n, GROUP_MAX);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const a8_gemm_t& g0 = gs[0];
+  int bn = g0.block_n;
+  if (bn == 0) bn = 256;
+  const int cl = (g0.reserved == 2) ? 2 : 1;
+  const int split = g0.split_k > 1 ? g0.split_k : 1;
+  A8_REQUIRE(g0.a.major == MAJOR_MN && g0.b.major == MAJOR_MN, "gemm_group: only (MN,MN) operand majors are instantiated");
+  A8_REQUIRE(split == 1 || g0.c_dtype == OUT_F32_ATOMIC, "gemm_group: split_k needs atomic fp32 output");
+  static thread_local GroupParams gp;  // 14 KB: filled per call, passed by value as a kernel parameter
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  copy_coef(kp.a, g0.a);
+  copy_coef(kp.b, g0.b);
+  kp.lo_count = kp.hi_count = 1;
+  kp.k_inner = g0.k_inner; kp.split_k = split;
+  kp.c_dtype = g0.c_dtype; kp.alpha = g0.alpha; kp.aux_mode = AUX_NONE; kp.act = ACT_NONE;
+  kp.trace = nullptr;
+  long long tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const a8_gemm_t& g = gs[i];
+    A8_REQUIRE(g.M > 0 && g.N > 0 && g.k_blocks > 0 && g.c != nullptr, "gemm_group[%d]: empty problem", i);
+    A8_REQUIRE(g.a.major == g0.a.major && g.b.major == g0.b.major && g.block_n == g0.block_n && g.reserved == g0.reserved &&
+                   g.c_dtype == g0.c_dtype && g.split_k == g0.split_k && g.k_inner == g0.k_inner && g.alpha == g0.alpha,
+               "gemm_group[%d]: majors / tile shape / output type / split / k_inner / alpha differ from problem 0", i);
+    A8_REQUIRE(g.act == ACT_NONE && g.z_out == nullptr && g.aux == nullptr && g.bias == nullptr &&
+                   (g.lo_count <= 1) && (g.hi_count <= 1),
+               "gemm_group[%d]: epilogue extras and batched problems are not supported in groups", i);
+    A8_REQUIRE(memcmp(g.a.base, g0.a.base, sizeof(int32_t) * 24) == 0 && memcmp(g.b.base, g0.b.base, sizeof(int32_t) * 24) == 0,
+               "gemm_group[%d]: operand coordinate maps differ from problem 0", i);
+    A8_REQUIRE(g.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(g.c) & 15u) == 0, "gemm_group[%d]: C alignment", i);
+    A8_REQUIRE(split <= g.k_blocks, "gemm_group[%d]: split_k %d > k_blocks %d", i, split, g.k_blocks);
+    GroupProb& q = gp.prob[i];
+    q.c = g.c; q.ldc = g.ldc; q.M = g.M; q.N = g.N;
+    q.m_tiles = cdiv(cdiv(g.M, BLOCK_M), cl);
+    q.n_tiles = cdiv(g.N, bn);
+    q.k_blocks = g.k_blocks;
+    tiles += (long long)q.m_tiles * q.n_tiles * split;
+    A8_REQUIRE(tiles < (1ll << 30), "gemm_group: too many tiles");
+    q.tile_end = (int)tiles;
+    int rc = make_tmap(&gp.map_a[i], g.a, 64, BLOCK_K, "group A");
+    if (rc) return rc;
+    rc = make_tmap(&gp.map_b[i], g.b, 64, BLOCK_K, "group B");
+    if (rc) return rc;
+  }
+  gp.n_prob = n;
+  kp.total_tiles = (int)tiles;
+  const int ek = ek_make(g0.c_dtype, 0, 0, AUX_NONE);
+  return launch_group_mnmn(ek, bn, cl, gp, kp, stream);
+}

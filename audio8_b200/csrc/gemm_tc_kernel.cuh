@@ -63,6 +63,23 @@ struct KParams {
   long long* trace;  // debug timeline (a8_gemm_set_trace), normally null
 };
 
+// Grouped launch (a8_gemm_group): ONE persistent kernel walks the tiles of up to GROUP_MAX problems that share operand
+// majors, tile shape, epilogue kind, coordinate maps and split-K factor but have their own operands (tensor maps),
+// output, extents and contraction length.  Set-up, first-load latency and the exposed last epilogue are then paid once
+// per group instead of once per problem (e.g. the 4 weight-gradient GEMMs of each of the 12 transformer layers).
+constexpr int GROUP_MAX = 48;
+struct GroupProb {
+  void* c;
+  long long ldc;
+  int M, N, m_tiles, n_tiles, k_blocks, tile_end;  // tile_end: exclusive prefix over the group's tile counts
+};
+struct alignas(64) GroupParams {
+  CUtensorMap map_a[GROUP_MAX];
+  CUtensorMap map_b[GROUP_MAX];
+  GroupProb prob[GROUP_MAX];
+  int n_prob;
+};
+
 __device__ __forceinline__ void op_coords(const OpCoef& o, int kin, int kbatch, int r, int lo, int hi,
                                           int (&c)[4]) {
 #pragma unroll
@@ -108,6 +125,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 
 struct TileCoord {
   int nt, mt, lo, hi, kb_begin, kb_end;
+  // the problem this tile belongs to (the launch's only one, or an entry of the group)
+  int M, N;
+  void* c;
+  long long ldc;
+  int g;
 };
 template <int CL>
 __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int rank) {
@@ -122,6 +144,25 @@ __device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile, int
   const int split = r / p.hi_count;
   t.kb_begin = (int)(((long long)split * p.k_blocks) / p.split_k);
   t.kb_end = (int)(((long long)(split + 1) * p.k_blocks) / p.split_k);
+  t.M = p.M; t.N = p.N; t.c = p.c; t.ldc = p.ldc; t.g = 0;
+  return t;
+}
+// grouped launch: `g` is the caller's cursor into the problem table (tiles are visited in increasing order)
+template <int CL>
+__device__ __forceinline__ TileCoord decode_tile_group(const KParams& p, const GroupProb* __restrict__ probs, int tile,
+                                                       int rank, int& g) {
+  while (tile >= probs[g].tile_end) ++g;
+  const GroupProb& q = probs[g];
+  int r = tile - (g > 0 ? probs[g - 1].tile_end : 0);
+  TileCoord t;
+  t.nt = r % q.n_tiles;
+  r /= q.n_tiles;
+  t.mt = (r % q.m_tiles) * CL + rank;
+  const int split = r / q.m_tiles;
+  t.lo = 0; t.hi = 0;
+  t.kb_begin = (int)(((long long)split * q.k_blocks) / p.split_k);
+  t.kb_end = (int)(((long long)(split + 1) * q.k_blocks) / p.split_k);
+  t.M = q.M; t.N = q.N; t.c = q.c; t.ldc = q.ldc; t.g = g;
   return t;
 }
 
@@ -159,21 +200,24 @@ __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long 
 // the bf16 aux input) go through the warp's smem staging buffer so that global accesses are row-contiguous (direct
 // 16-byte-per-row stores from registers were measured: slower, L2 sees partial sectors).
 template <int EK, int CW>
-__device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t* r, long long row_off0, int row0,
-                                               int nb, const float* sb, uint8_t* stg, int lane) {
+__device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord& tc, const uint32_t* r,
+                                               long long row_off0, int row0, int nb, const float* sb, uint8_t* stg,
+                                               int lane) {
   constexpr bool GEN = (EK < 0);
   constexpr int NP = CW / 8;  // 16-byte bf16 pieces per row
   const int c_dtype = GEN ? p.c_dtype : (EK & 3);
   const bool do_gelu = GEN ? (p.act == ACT_GELU) : (((EK >> 2) & 1) != 0);
   const bool do_z = GEN ? (p.z_out != nullptr) : (((EK >> 3) & 1) != 0);
   const int aux_mode = GEN ? p.aux_mode : ((EK >> 4) & 3);
-  const int rows_valid = min(32, p.M - row0);        // may be <= 0
-  const int cols_valid = (p.N + 7) & ~7;              // absolute column bound for the 16-byte pieces
+  const int rows_valid = min(32, tc.M - row0);       // may be <= 0
+  const int cols_valid = (tc.N + 7) & ~7;             // absolute column bound for the 16-byte pieces
+  const long long ldc = tc.ldc;
+  void* const cptr = tc.c;
   const bool has_aux = aux_mode != AUX_NONE;
   uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
   uint4 a[NP];
   if (has_aux) {
-    stage_copy<2, STG_LOAD, NP>(stg, const_cast<void*>(p.aux), row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_LOAD, NP>(stg, const_cast<void*>(p.aux), row_off0, ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
 #pragma unroll
     for (int g = 0; g < NP; ++g) a[g] = my[g];
@@ -199,7 +243,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
       my[g] = z;
     }
     __syncwarp();
-    stage_copy<2, STG_STORE, NP>(stg, p.z_out, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_STORE, NP>(stg, p.z_out, row_off0, ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
   }
   if (do_gelu) {
@@ -232,7 +276,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
       my[g] = o;
     }
     __syncwarp();
-    stage_copy<2, STG_STORE, NP>(stg, p.c, row_off0, p.ldc, nb, rows_valid, cols_valid, lane);
+    stage_copy<2, STG_STORE, NP>(stg, cptr, row_off0, ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
   } else {  // fp32: plain stores, or vector reductions for split-K partial sums; 16 columns (64 B per row) at a time
 #pragma unroll
@@ -243,9 +287,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const uint32_t*
                            __float_as_uint(v[16 * h + 4 * g + 2]), __float_as_uint(v[16 * h + 4 * g + 3]));
       __syncwarp();
       if (c_dtype == OUT_F32)
-        stage_copy<4, STG_STORE, 4>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+        stage_copy<4, STG_STORE, 4>(stg, cptr, row_off0, ldc, nb + 16 * h, rows_valid, cols_valid, lane);
       else
-        stage_copy<4, STG_RED, 4>(stg, p.c, row_off0, p.ldc, nb + 16 * h, rows_valid, cols_valid, lane);
+        stage_copy<4, STG_RED, 4>(stg, cptr, row_off0, ldc, nb + 16 * h, rows_valid, cols_valid, lane);
       __syncwarp();
     }
   }
@@ -329,10 +373,10 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MA, int MB, int BN, int CL, int EK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const KParams p) {
+template <int MA, int MB, int BN, int CL, int EK, bool GROUP>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ maps_a,
+                                             const CUtensorMap* __restrict__ maps_b, const KParams& p,
+                                             const GroupProb* __restrict__ probs, int n_prob) {
   using C = Cfg<BN, CL>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -357,8 +401,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     if (elect_one()) {
-      tma_prefetch_desc(&map_a);
-      tma_prefetch_desc(&map_b);
+      tma_prefetch_desc(maps_a);
+      tma_prefetch_desc(maps_b);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -394,8 +438,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int piter = 0;
+      int gcur = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++piter) {
-        const TileCoord t = decode_tile<CL>(p, tile, rank);
+        const TileCoord t = GROUP ? decode_tile_group<CL>(p, probs, tile, rank, gcur) : decode_tile<CL>(p, tile, rank);
+        const CUtensorMap& map_a = maps_a[t.g];
+        const CUtensorMap& map_b = maps_b[t.g];
         const int m0 = t.mt * BLOCK_M, n0 = t.nt * BN;
         trace_ev(p, 0, piter, 0);
         int kin = t.kb_begin % p.k_inner, kbatch = t.kb_begin / p.k_inner;  // advanced incrementally: no division
@@ -478,8 +525,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      int gcur = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
-        const TileCoord t = decode_tile<CL>(p, tile, rank);
+        const TileCoord t = GROUP ? decode_tile_group<CL>(p, probs, tile, rank, gcur) : decode_tile<CL>(p, tile, rank);
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1u;
         trace_ev(p, 1, iter, 0);
@@ -524,8 +572,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int NCH = COLS / EPI_CW;    // chunks per warp
     const int tid_e = threadIdx.x - 128;
     int iter = 0;
+    int gcur = 0;
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
-      const TileCoord t = decode_tile<CL>(p, tile, rank);
+      const TileCoord t = GROUP ? decode_tile_group<CL>(p, probs, tile, rank, gcur) : decode_tile<CL>(p, tile, rank);
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1u;
       float* sb = nullptr;
@@ -533,7 +582,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // stage this tile's bias slice in shared memory while the main loop of the tile is still running
         sb = s_bias + as * BN;
         const float* bsrc = p.bias + (long long)t.lo * p.bias_stride_lo + t.nt * BN;
-        for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) sb[i] = (t.nt * BN + i < p.N) ? __ldg(bsrc + i) : 0.f;
+        for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) sb[i] = (t.nt * BN + i < t.N) ? __ldg(bsrc + i) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
       if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 0);
@@ -542,7 +591,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 1);
       const int row0 = t.mt * BLOCK_M + q * 32;
       const long long row_off0 =
-          (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row0 * p.ldc;
+          (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row0 * t.ldc;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * COLS;
       const int nb0 = t.nt * BN + half * COLS;
       const float* sbw = sb ? sb + half * COLS : nullptr;
@@ -552,10 +601,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t ra[EPI_CW];
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        if (nb0 + c * EPI_CW >= p.N) break;
+        if (nb0 + c * EPI_CW >= t.N) break;
         tmem_ld_chunk(t_addr + c * EPI_CW, ra);
         tmem_ld_wait();
-        epilogue_chunk<EK, EPI_CW>(p, ra, row_off0, row0, nb0 + c * EPI_CW, sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
+        epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, nb0 + c * EPI_CW, sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -576,6 +625,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (CL == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
     else tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
   }
+}
+
+template <int MA, int MB, int BN, int CL, int EK>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const KParams p) {
+  gemm_tc_body<MA, MB, BN, CL, EK, false>(&map_a, &map_b, p, nullptr, 1);
+}
+
+template <int MA, int MB, int BN, int CL, int EK>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_group_kernel(const __grid_constant__ GroupParams gp, const KParams p) {
+  gemm_tc_body<MA, MB, BN, CL, EK, true>(gp.map_a, gp.map_b, p, gp.prob, gp.n_prob);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -621,6 +683,21 @@ int launch_bn(int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, cons
   set_error("gemm: unsupported block_n %d", bn);
   return -1;
 }
+
+template <int MA, int MB, int BN, int CL, int EK>
+int launch_group_inst(const GroupParams& gp, const KParams& kp, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_tc_group_kernel<MA, MB, BN, CL, EK>;
+  if (!configured) {
+    A8_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN, CL>::SMEM_BYTES));
+    configured = true;
+  }
+  const int slots = num_sms() / CL;
+  const int grid = CL * (kp.total_tiles < slots ? kp.total_tiles : slots);
+  A8_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg<BN, CL>::SMEM_BYTES, stream, CL, gp, kp));
+  return check_launch("gemm_tc_group_kernel");
+}
+int launch_group_mnmn(int ek, int bn, int cl, const GroupParams& gp, const KParams& kp, cudaStream_t s);  // gemm_tc_inst_mnmn.cu
 
 // one entry per (MA, MB): picks the specialised epilogue when (c_dtype, act, z_out, aux_mode) is on its list
 int launch_kk(int ek, int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t s);

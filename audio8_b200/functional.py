@@ -489,6 +489,12 @@ class EncoderFn(torch.autograd.Function):
         dcur = _bf16(dh).view(M, D)
         be.set_seed_source(sv["seed_src"])
         lgrads = [None] * sv["nlw"]
+        # The 4 weight-gradient GEMMs of every layer (dW = dY^T X) are deferred and issued as ONE grouped persistent launch
+        # when the stack's data-gradient chain is done (ops.gemm_group): per-launch set-up, first-load latency and the
+        # exposed last epilogue are paid once instead of 48 times, the group needs no split-K (plain stores: no zero fill
+        # of dW), and the contraction (B*T tokens) is long enough to run at the conv-wgrad rate.  Costs ~62 MB per layer of
+        # gradients kept alive until then.
+        deferred = []
         for li in range(len(sv["layers"]) - 1, -1, -1):
             L = sv["layers"][li]
             if L is None:
@@ -506,20 +512,21 @@ class EncoderFn(torch.autograd.Function):
             # every fp32 accumulator of this layer's backward comes from ONE zero-filled buffer (one fill launch)
             sizes = [3 * D * D, D * D, F_ * D, D * F_, 3 * D, 3 * D, F_, 3 * D]
             # data-parallel runs: the block lives in the wrapper's gradient arena (parallel.py) and is reduced in place
-            zbuf = ops.grad_arena_take(L["key"], sum(sizes))
+            zbuf = ops.grad_arena_take(L["key"], sum(sizes), zero=False)
             if zbuf is None:
-                zbuf = _zeros((sum(sizes),), F32, x)
+                zbuf = _empty((sum(sizes),), F32, x)
+            zbuf[sum(sizes[:4]):].zero_()  # only the small bias / LayerNorm accumulators are accumulated into
             _, (dwqkv, dwo, dw1, dw2, acc1, acc2, db1, dbqkv) = EncoderFn._layer_views(zbuf, D, F_)
             # ---- ln1( x1 + drop(ffn) )
             ds2, df, dg1, db1ln, dbias2 = be.layernorm_bwd(dcur, L["s2"], L["mean1"], L["rstd1"], g1, want_dh=p > 0,
                                                            p_h=p, seed_h=seed2, want_dbias=True, acc=acc1)
             if df is None:
                 df = ds2
-            be.gemm(G.linear_wgrad(df, L["hid"], dw2))
+            deferred.append(G.linear_wgrad_grouped(df, L["hid"], dw2))
             dz1 = _empty((M, F_), BF16, x)
             be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL_GELU_GRAD))
             db1 = be.colsum(dz1, out=db1)
-            be.gemm(G.linear_wgrad(dz1, L["x1"], dw1))
+            deferred.append(G.linear_wgrad_grouped(dz1, L["x1"], dw1))
             dx1 = _empty((M, D), BF16, x)
             be.gemm(G.linear_dgrad(dz1, w1_b, dx1, aux=ds2, aux_mode=AUX_ADD))
             # ---- ln2( x + drop(attn) )
@@ -527,19 +534,23 @@ class EncoderFn(torch.autograd.Function):
                                                         p_h=p, seed_h=seed1, want_dbias=True, acc=acc2)
             if da is None:
                 da = ds1
-            be.gemm(G.linear_wgrad(da, L["ctx"].view(M, D), dwo))
+            deferred.append(G.linear_wgrad_grouped(da, L["ctx"].view(M, D), dwo))
             dctx = _empty((B, T, D), BF16, x)
             be.gemm(G.linear_dgrad(da, wo_b, dctx.view(M, D)))
             dqkv = be.attn_bwd(L["qkv"], L["ctx"], dctx, L["lse"], H, scale, sv["row_keep"], p, seed_a)
             dqkv2 = dqkv.view(M, 3 * D)
             dbqkv = be.colsum(dqkv2, out=dbqkv)
-            be.gemm(G.linear_wgrad(dqkv2, L["xin"], dwqkv))
+            deferred.append(G.linear_wgrad_grouped(dqkv2, L["xin"], dwqkv))
             dxin = _empty((M, D), BF16, x)
             be.gemm(G.linear_dgrad(dqkv2, wqkv_b, dxin, aux=ds1, aux_mode=AUX_ADD))
             dcur = dxin
             lgrads[li * PL:(li + 1) * PL] = [dwqkv[0:D], dbqkv[0:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:],
                                              dbqkv[2 * D:], dwo, dbo, dg2, db2ln, dw1, db1, dw2, dbias2, dg1, db1ln]
-            sv["layers"][li] = None  # free this layer's activations
+            # (the layer's activations that the deferred weight gradients read stay referenced by `deferred`)
+            sv["layers"][li] = None
+        if deferred:
+            be.gemm_group(deferred)
+            deferred = None
         if not sv["front"]:
             be.set_seed_source(None)
             return (dcur.view(B, T, D), None, None, None, None, None, None, None, *lgrads)

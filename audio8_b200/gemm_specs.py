@@ -180,6 +180,18 @@ def linear_wgrad(dy, x, dw):
                                 cluster=cl), 2 * M * N * K)
 
 
+@cached_spec
+def linear_wgrad_grouped(dy, x, dw):
+    """the same contraction as `linear_wgrad`, shaped for a grouped launch (ops.gemm_group): 256 x 256 pair tiles, no
+    split-K (the group supplies the parallelism: 108 tile pairs per wav2vec2-base layer), plain fp32 stores — dw needs
+    no zero fill"""
+    M, N = dy.shape
+    K = x.shape[1]
+    a = Op(dy, (N, M), (N,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
+    b = Op(x, (K, M), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
+    return _with_flops(GemmSpec(a, b, N, K, cdiv(M, 64), dw, K, OUT_F32, split_k=1, block_n=256, cluster=2), 2 * M * N * K)
+
+
 # ------------------------------------------------------------------------------------------------ conv 1..6
 @cached_spec
 def conv_fwd(x, wk, y, k, s, z_out=None, act=ACT_GELU):

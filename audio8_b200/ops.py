@@ -222,6 +222,19 @@ class CudaBackend:
         if self.profiler is not None:
             self.profiler.end()
 
+    def gemm_group(self, specs):
+        """one persistent launch per <= 48 problems (a8_gemm_group): same majors / tiling / epilogue kind, own operands"""
+        for lo in range(0, len(specs), 48):
+            part = [b.spec() if hasattr(b, "spec") else b for b in specs[lo:lo + 48]]
+            arr = (_lib.Gemm * len(part))()
+            for i, g in enumerate(part):
+                arr[i] = self._fill(g)
+            if self.profiler is not None:
+                self.profiler.begin("gemm", sum(g.flops for g in part))
+            _lib.check(self.lib.a8_gemm_group(arr, len(part), _stream()), "a8_gemm_group")
+            if self.profiler is not None:
+                self.profiler.end()
+
     def _fill(self, g):
         s = _lib.Gemm()
         s.a, s.b = self._operand(g.a), self._operand(g.b)

@@ -85,6 +85,13 @@ typedef struct {
 } a8_gemm_t;
 
 int a8_gemm(const a8_gemm_t* p, void* stream);
+
+/* One persistent launch over n (<= 48) GEMM problems that share operand majors, coordinate maps, block_n, cluster
+ * request, split_k, k_inner, alpha and output type, each with its own operands, output, M, N and k_blocks (no bias / aux /
+ * z_out / activation, lo_count = hi_count = 1).  Instantiated for (MN-major, MN-major) operands, i.e. weight gradients
+ * dW = dY^T X: the transformer stack defers the 4 weight-gradient GEMMs of every layer (what autograd runs as 48 separate
+ * addmm calls behind `/root/reference/audio8/wav2vec2.py:644`) to the end of its backward and issues them as one kernel. */
+int a8_gemm_group(const a8_gemm_t* problems, int32_t n, void* stream);
 /* debug aid: later a8_gemm launches stamp clock64() timelines of their first CTAs into `buf` (device memory,
  * 4*3*8*4 int64); NULL turns it off.  Not used by the product path. */
 void a8_gemm_set_trace(void* buf);

@@ -100,6 +100,10 @@ class EmuBackend:
     def gemm(self, g):
         emu_gemm(g.spec() if hasattr(g, "spec") else g)
 
+    def gemm_group(self, specs):
+        for g in specs:
+            self.gemm(g)
+
 
 _SEED_SRC = [None]
 

@@ -65,3 +65,36 @@ def test_tcgen05_linear_large(M, N, K, cluster):
     assert (dx.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     ref = dy.float().t() @ x.float()
     assert (dw - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def _group_case(dev, be, shapes):
+    from audio8_b200 import gemm_specs as G
+    g = torch.Generator().manual_seed(17)
+    probs, specs = [], []
+    for (M, N, K) in shapes:
+        dy = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev)
+        x = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+        dw = torch.full((N, K), float("nan"), dtype=torch.float32, device=dev)  # plain stores: no zero fill needed
+        probs.append((dy, x, dw))
+        specs.append(G.linear_wgrad_grouped(dy, x, dw))
+    be.gemm_group(specs)
+    for i, (dy, x, dw) in enumerate(probs):
+        ref = dy.float().t() @ x.float()
+        err = (dw - ref).abs().max().item()
+        assert err <= 2e-3 * ref.abs().max().item() + 1e-6, f"group problem {i} {tuple(dw.shape)}: {err:.4g}"
+
+
+def test_grouped_wgrad_cpu(emu_backend):
+    _group_case("cpu", emu_backend, [(200, 136, 72), (200, 64, 264)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shapes", [
+    [(4494, 2304, 768), (4494, 768, 768), (4494, 3072, 768), (4494, 768, 3072)] * 3,  # 12 problems, 324 tile pairs
+    [(301, 384, 128), (301, 128, 128), (301, 256, 128), (301, 128, 256), (77, 136, 72)],  # ragged tiny shapes
+    [(1000, 264, 520)] * 50,  # more than one launch (48 per group)
+])
+def test_grouped_wgrad_tcgen05(shapes):
+    """a8_gemm_group: several weight-gradient problems with their own operands / extents in one persistent launch"""
+    from audio8_b200 import ops
+    _group_case("cuda", ops.backend(), shapes)
