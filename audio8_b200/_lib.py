@@ -11,8 +11,8 @@ LIB_PATH = os.path.join(HERE, "libaudio8_b200" + ("_" + _TAG if _TAG else "") + 
 
 MAJOR_K, MAJOR_MN = 0, 1
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
-ACT_NONE, ACT_GELU = 0, 1
-AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_GELU_DZ = 0, 1, 2
+AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_MUL = 0, 1, 2, 3
 
 _i32x4 = C.c_int32 * 4
 
@@ -65,6 +65,7 @@ SIGNATURES.update({
     "a8_colsum": (_I, [_P, _L, _I, _I, _P, _P]),
     "a8_dropout": (_I, [_P, _P, _I, _L, _F, _U, _P]),
     "a8_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "a8_mul_bf16": (_I, [_P, _P, _P, _L, _P]),
     "a8_log_softmax_fwd": (_I, [_P, _P, _I, _I, _P]),
     "a8_log_softmax_bwd": (_I, [_P, _L, _L, _L, _I, _P, _P, _I, _I, _P]),
     "a8_conv0_stats": (_I, [_P, _I, _L, _P, _I, _I, _I, _F, _P, _P, _P, _P]),

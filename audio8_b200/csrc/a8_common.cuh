@@ -131,6 +131,20 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float cdf = 0.5f + copysignf(half_erf, x);
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
+// gelu(x) and gelu'(x) together: Phi(x) is shared and the exponential of erf (7.1.26) IS the one of phi(x)
+__device__ __forceinline__ float gelu_both_fast(float x, float& dgelu) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = ex2_approx(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  const float half_erf = 0.5f - 0.5f * p * t * e;
+  const float cdf = 0.5f + copysignf(half_erf, x);
+  dgelu = fmaf(x * 0.3989422804014327f, e, cdf);
+  return x * cdf;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // per-step dropout seed word in device memory (a8_set_seed_source), nullable

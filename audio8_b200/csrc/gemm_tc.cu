@@ -152,7 +152,8 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   else rc = make_tmap(&mb, g.b, 64, BLOCK_K, "B");
   if (rc) return rc;
 
-  const int ek = ek_make(g.c_dtype, g.act == ACT_GELU, g.z_out != nullptr, g.aux_mode);
+  A8_REQUIRE(g.act >= ACT_NONE && g.act <= ACT_GELU_DZ && g.aux_mode >= AUX_NONE && g.aux_mode <= AUX_MUL, "gemm: bad act / aux_mode");
+  const int ek = ek_make(g.c_dtype, g.act, g.z_out != nullptr, g.aux_mode);
   if (g.a.major == MAJOR_K && g.b.major == MAJOR_K) return launch_kk(ek, bn, cl, ma, mb, kp, stream);
   if (g.a.major == MAJOR_K && g.b.major == MAJOR_MN) return launch_kmn(ek, bn, cl, ma, mb, kp, stream);
   return launch_mnmn(ek, bn, cl, ma, mb, kp, stream);

@@ -7,9 +7,12 @@ namespace gemm {
 int launch_kk(int ek, int bn, int cl, const CUtensorMap& ma, const CUtensorMap& mb, const KParams& kp, cudaStream_t s) {
   switch (ek) {
     case ek_make(OUT_BF16, 0, 0, AUX_NONE): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, 0, 0, AUX_NONE)>(bn, cl, ma, mb, kp, s);
-    case ek_make(OUT_BF16, 1, 1, AUX_NONE): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, 1, 1, AUX_NONE)>(bn, cl, ma, mb, kp, s);
-    case ek_make(OUT_BF16, 0, 0, AUX_MUL_GELU_GRAD): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, 0, 0, AUX_MUL_GELU_GRAD)>(bn, cl, ma, mb, kp, s);
-    case ek_make(OUT_BF16, 1, 1, AUX_ADD): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, 1, 1, AUX_ADD)>(bn, cl, ma, mb, kp, s);
+    // out = gelu(z), z_out = gelu'(z): conv layers 1.., FFN first linear (forward)
+    case ek_make(OUT_BF16, ACT_GELU_DZ, 1, AUX_NONE): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, ACT_GELU_DZ, 1, AUX_NONE)>(bn, cl, ma, mb, kp, s);
+    // out = acc * aux (aux = the stored gelu'): conv data gradients
+    case ek_make(OUT_BF16, 0, 0, AUX_MUL): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, 0, 0, AUX_MUL)>(bn, cl, ma, mb, kp, s);
+    // positional conv forward: x + gelu(conv + bias), gelu' kept
+    case ek_make(OUT_BF16, ACT_GELU_DZ, 1, AUX_ADD): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, ACT_GELU_DZ, 1, AUX_ADD)>(bn, cl, ma, mb, kp, s);
     case ek_make(OUT_BF16, 0, 0, AUX_ADD): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_BF16, 0, 0, AUX_ADD)>(bn, cl, ma, mb, kp, s);
     case ek_make(OUT_F32, 0, 0, AUX_NONE): return launch_bn<MAJOR_K, MAJOR_K, ek_make(OUT_F32, 0, 0, AUX_NONE)>(bn, cl, ma, mb, kp, s);
   }

@@ -8,7 +8,7 @@ int launch_kmn(int ek, int bn, int cl, const CUtensorMap& ma, const CUtensorMap&
   switch (ek) {
     case ek_make(OUT_BF16, 0, 0, AUX_NONE): return launch_bn<MAJOR_K, MAJOR_MN, ek_make(OUT_BF16, 0, 0, AUX_NONE)>(bn, cl, ma, mb, kp, s);
     case ek_make(OUT_BF16, 0, 0, AUX_ADD): return launch_bn<MAJOR_K, MAJOR_MN, ek_make(OUT_BF16, 0, 0, AUX_ADD)>(bn, cl, ma, mb, kp, s);
-    case ek_make(OUT_BF16, 0, 0, AUX_MUL_GELU_GRAD): return launch_bn<MAJOR_K, MAJOR_MN, ek_make(OUT_BF16, 0, 0, AUX_MUL_GELU_GRAD)>(bn, cl, ma, mb, kp, s);
+    case ek_make(OUT_BF16, 0, 0, AUX_MUL): return launch_bn<MAJOR_K, MAJOR_MN, ek_make(OUT_BF16, 0, 0, AUX_MUL)>(bn, cl, ma, mb, kp, s);
     case ek_make(OUT_F32, 0, 0, AUX_NONE): return launch_bn<MAJOR_K, MAJOR_MN, ek_make(OUT_F32, 0, 0, AUX_NONE)>(bn, cl, ma, mb, kp, s);
   }
   return launch_bn<MAJOR_K, MAJOR_MN, EK_GENERIC>(bn, cl, ma, mb, kp, s);

@@ -31,8 +31,8 @@ constexpr int STG_BYTES = 32 * STG_PITCH;     // per epilogue warp
 constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
 enum { MAJOR_K = A8_MAJOR_K, MAJOR_MN = A8_MAJOR_MN };
 enum { OUT_BF16 = A8_OUT_BF16, OUT_F32 = A8_OUT_F32, OUT_F32_ATOMIC = A8_OUT_F32_ATOMIC };
-enum { ACT_NONE = A8_ACT_NONE, ACT_GELU = A8_ACT_GELU };
-enum { AUX_NONE = A8_AUX_NONE, AUX_ADD = A8_AUX_ADD, AUX_MUL_GELU_GRAD = A8_AUX_MUL_GELU_GRAD };
+enum { ACT_NONE = A8_ACT_NONE, ACT_GELU = A8_ACT_GELU, ACT_GELU_DZ = A8_ACT_GELU_DZ };
+enum { AUX_NONE = A8_AUX_NONE, AUX_ADD = A8_AUX_ADD, AUX_MUL_GELU_GRAD = A8_AUX_MUL_GELU_GRAD, AUX_MUL = A8_AUX_MUL };
 
 struct OpCoef {
   int base[4], ck[4], cb[4], cr[4], cl[4], ch[4];
@@ -40,10 +40,10 @@ struct OpCoef {
 
 // Epilogue kind, a template parameter of the kernel: EK_GENERIC reads every switch from KParams at run time (one
 // large body: ~9000 SASS instructions, which thrashes the instruction cache of the 8 epilogue warps); any other
-// value fixes (c_dtype | gelu << 2 | z_out << 3 | aux_mode << 4) at compile time so that the hot shapes run a
+// value fixes (c_dtype | act << 2 | z_out << 4 | aux_mode << 5) at compile time so that the hot shapes run a
 // straight-line epilogue a few hundred instructions long.
 constexpr int EK_GENERIC = -1;
-constexpr int ek_make(int c_dtype, int gelu, int z, int aux) { return c_dtype | (gelu << 2) | (z << 3) | (aux << 4); }
+constexpr int ek_make(int c_dtype, int act, int z, int aux) { return c_dtype | (act << 2) | (z << 4) | (aux << 5); }
 
 struct KParams {
   int M, N, m_tiles, n_tiles, lo_count, hi_count;  // m_tiles counts tile PAIRS when the kernel runs as 2-CTA clusters
@@ -206,9 +206,11 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
   constexpr bool GEN = (EK < 0);
   constexpr int NP = CW / 8;  // 16-byte bf16 pieces per row
   const int c_dtype = GEN ? p.c_dtype : (EK & 3);
-  const bool do_gelu = GEN ? (p.act == ACT_GELU) : (((EK >> 2) & 1) != 0);
-  const bool do_z = GEN ? (p.z_out != nullptr) : (((EK >> 3) & 1) != 0);
-  const int aux_mode = GEN ? p.aux_mode : ((EK >> 4) & 3);
+  const int act = GEN ? p.act : ((EK >> 2) & 3);
+  const bool do_gelu = act == ACT_GELU;
+  const bool do_gelu_dz = act == ACT_GELU_DZ;  // out = gelu(v), z_out = gelu'(v)
+  const bool do_z = GEN ? (p.z_out != nullptr) : (((EK >> 4) & 1) != 0);
+  const int aux_mode = GEN ? p.aux_mode : ((EK >> 5) & 3);
   const int rows_valid = min(32, tc.M - row0);       // may be <= 0
   const int cols_valid = (tc.N + 7) & ~7;             // absolute column bound for the 16-byte pieces
   const long long ldc = tc.ldc;
@@ -234,7 +236,15 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
     }
   }
-  if (do_z) {
+  if (do_gelu_dz) {  // the activation and its derivative from one erf / exp evaluation; the derivative goes to z_out
+#pragma unroll
+    for (int g = 0; g < NP; ++g) {
+      float d[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * g + j] = gelu_both_fast(v[8 * g + j], d[j]);
+      if (do_z) my[g] = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+    }
+  } else if (do_z) {
 #pragma unroll
     for (int g = 0; g < NP; ++g) {
       uint4 z;
@@ -242,6 +252,8 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       z.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]); z.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
       my[g] = z;
     }
+  }
+  if (do_z) {
     __syncwarp();
     stage_copy<2, STG_STORE, NP>(stg, p.z_out, row_off0, ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
@@ -260,6 +272,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
         if (aux_mode == AUX_ADD) {
           v[8 * g + 2 * j] += t.x;
           v[8 * g + 2 * j + 1] += t.y;
+        } else if (aux_mode == AUX_MUL) {
+          v[8 * g + 2 * j] *= t.x;
+          v[8 * g + 2 * j + 1] *= t.y;
         } else {
           v[8 * g + 2 * j] *= gelu_grad_fast(t.x);
           v[8 * g + 2 * j + 1] *= gelu_grad_fast(t.y);

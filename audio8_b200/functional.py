@@ -13,7 +13,7 @@ import torch
 
 from . import gemm_specs as G
 from . import ops
-from .ops import ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, OUT_BF16, OUT_F32
+from .ops import ACT_GELU, ACT_GELU_DZ, ACT_NONE, AUX_ADD, AUX_MUL, AUX_NONE, OUT_BF16, OUT_F32
 
 BF16, F32 = torch.bfloat16, torch.float32
 _site = [0]
@@ -319,7 +319,7 @@ class ConvFeatureFn(torch.autograd.Function):
         n = len(spec)
         grads = [None] * n
         if n > 1:
-            dz = be.gelu_bwd(_bf16(dy), zs[n - 1])
+            dz = be.mul(_bf16(dy), zs[n - 1])  # zs hold gelu'(pre-activation) (ACT_GELU_DZ)
             for i in range(n - 1, 0, -1):
                 (c, k, s) = spec[i]
                 a_prev = acts[i - 1]
@@ -442,7 +442,7 @@ class EncoderFn(torch.autograd.Function):
             x1, _, s1, mean2, rstd2 = be.layernorm_fwd(x2d, g2, b2, 1e-6, h=a, p_h=p, seed_h=seed1)
             z1 = _empty((M, F_), BF16, x)
             hid = _empty((M, F_), BF16, x)
-            be.gemm(G.linear_fwd(x1, w1_b, hid, b1, act=ACT_GELU, z_out=z1))
+            be.gemm(G.linear_fwd(x1, w1_b, hid, b1, act=ACT_GELU_DZ if need_grad else ACT_GELU, z_out=z1 if need_grad else None))
             f = _empty((M, D), BF16, x)
             be.gemm(G.linear_fwd(hid, w2_b, f, bb2))
             seed2 = next_seed() if p > 0 else 0
@@ -524,7 +524,7 @@ class EncoderFn(torch.autograd.Function):
                 df = ds2
             deferred.append(G.linear_wgrad_grouped(df, L["hid"], dw2))
             dz1 = _empty((M, F_), BF16, x)
-            be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL_GELU_GRAD))
+            be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL))
             db1 = be.colsum(dz1, out=db1)
             deferred.append(G.linear_wgrad_grouped(dz1, L["x1"], dw1))
             dx1 = _empty((M, D), BF16, x)
@@ -559,7 +559,7 @@ class EncoderFn(torch.autograd.Function):
         ds0, _, dlg, dlb, _ = be.layernorm_bwd(dcur.view(B, T, D), sv["s0"], sv["mean0"], sv["rstd0"], sv["ln_g"],
                                                p_y=p, seed_y=sv["seed0"], dg_out=_grad_zeros(klg, (D,), x),
                                                db_out=_grad_zeros(klb, (D,), x))
-        dz0 = be.gelu_bwd(ds0, sv["z0"])
+        dz0 = be.mul(ds0, sv["z0"])
         dpos_b = be.colsum(dz0, out=_grad_zeros(kb_, (D,), x))
         groups, k, pad_l = sv["groups"], sv["k"], sv["pad_l"]
         dwp = _empty((groups, k * 64, 64), F32, x)

@@ -11,7 +11,7 @@ Reference call sites replaced (under /root/reference/audio8):
   posconv_*   grouped positional conv (k=128, g=16)   wav2vec2.py:600-609,634
   attn_*      scaled-dot-product attention matmuls    eight_mile SeqScaledDotProductAttention via wav2vec2.py:644
 """
-from .ops import (ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, MAJOR_K, MAJOR_MN, OUT_BF16, OUT_F32,
+from .ops import (ACT_GELU, ACT_GELU_DZ, ACT_NONE, AUX_ADD, AUX_MUL, AUX_MUL_GELU_GRAD, AUX_NONE, MAJOR_K, MAJOR_MN, OUT_BF16, OUT_F32,
                   OUT_F32_ATOMIC, GemmSpec, Op)
 
 import functools
@@ -146,15 +146,15 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
     N = w.shape[0]
     a = Op(x, (K, M), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
     b = Op(w, (K, N), (K,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
-    epi = "gelu" if act == ACT_GELU else ("f32" if c_dtype == OUT_F32 else "bf16")
-    bn, _, cl = _tiling(M, N, cdiv(K, 64), epi=epi, b_k_major=True, prefer192=act != ACT_GELU) if N > 128 else (0, 1, 1)
+    epi = "gelu" if act != ACT_NONE else ("f32" if c_dtype == OUT_F32 else "bf16")
+    bn, _, cl = _tiling(M, N, cdiv(K, 64), epi=epi, b_k_major=True, prefer192=act == ACT_NONE) if N > 128 else (0, 1, 1)
     return _with_flops(GemmSpec(a, b, M, N, cdiv(K, 64), out, out.shape[-1], c_dtype, act=act, z_out=z_out, aux=aux,
                                 aux_mode=aux_mode, bias=bias, block_n=bn, cluster=cl), 2 * M * N * K)
 
 
 @cached_spec
 def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
-    """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | + aux)."""
+    """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | * aux | + aux)."""
     M, N = dy.shape
     K = w.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
@@ -196,12 +196,15 @@ def linear_wgrad_grouped(dy, x, dw):
 @cached_spec
 def conv_fwd(x, wk, y, k, s, z_out=None, act=ACT_GELU):
     """y[b,t,:] = act( sum_{j,c} x[b, s*t+j, c] wk[:, j*C+c] ).  x [B,Lin,C], wk [Cout, k*C], y [B,Lout,Cout].
-    The A operand is a tensor map with OVERLAPPING rows (row pitch s*C, row length k*C): zero-copy im2col."""
+    The A operand is a tensor map with OVERLAPPING rows (row pitch s*C, row length k*C): zero-copy im2col.
+    z_out (training): receives gelu'(pre-activation), the factor the backward pass multiplies by."""
+    if z_out is not None and act == ACT_GELU:
+        act = ACT_GELU_DZ
     B, Lin, Cin = x.shape
     _, Lout, Cout = y.shape
     a = Op(x, (k * Cin, Lout, B), (s * Cin, Lin * Cin), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, 0, 1, 0))
     b = Op(wk, (k * Cin, Cout), (k * Cin,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
-    bn, _, cl = _tiling(Lout, Cout, k * Cin // 64, batch=B, epi="gelu" if act == ACT_GELU else "bf16", candidates=(256,))
+    bn, _, cl = _tiling(Lout, Cout, k * Cin // 64, batch=B, epi="gelu" if act != ACT_NONE else "bf16", candidates=(256,))
     return _with_flops(GemmSpec(a, b, Lout, Cout, k * Cin // 64, y, Cout, OUT_BF16, lo_count=B, block_n=bn, cluster=cl,
                                 c_stride_lo=Lout * Cout, act=act, z_out=z_out), 2 * B * Lout * Cout * k * Cin)
 
@@ -213,7 +216,7 @@ def conv_dgrad_taps(k, s, p):
 
 @cached_spec
 def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
-    """dx[b, s*u+p, :] = sum_{i, co} dz[b, u-i, co] wt_p[:, i*Cout+co]  (* gelu'(aux[b, s*u+p, :])).
+    """dx[b, s*u+p, :] = sum_{i, co} dz[b, u-i, co] wt_p[:, i*Cout+co]  (* aux[b, s*u+p, :], aux = the stored gelu').
     dz [B,Lout,Cout], wt_p [Cin, ntaps*Cout], dx [B,Lin,Cin]; one launch per phase p of the stride."""
     B, Lout, Cout = dz.shape
     _, Lin, Cin = dx.shape
@@ -222,10 +225,10 @@ def conv_dgrad(dz, wt_p, dx, k, s, p, aux=None):
     a = Op(dz, (Cout, Lout, B), (Cout, Lout * Cout), MAJOR_K, ck=(64, 0, 0, 0), cb=(0, -1, 0, 0), cr=(0, 1, 0, 0),
            cl=(0, 0, 1, 0))
     b = Op(wt_p, (ntaps * Cout, Cin), (ntaps * Cout,), MAJOR_K, ck=(64, 0, 0, 0), cb=(Cout, 0, 0, 0), cr=(0, 1, 0, 0))
-    bn, _, cl = _tiling(U, Cin, ntaps * Cout // 64, batch=B, epi="gelu" if aux is not None else "bf16", candidates=(256,))
+    bn, _, cl = _tiling(U, Cin, ntaps * Cout // 64, batch=B, epi="bf16", candidates=(256,))
     return _with_flops(GemmSpec(a, b, U, Cin, ntaps * Cout // 64, dx, s * Cin, OUT_BF16, lo_count=B, block_n=bn, cluster=cl,
                                 k_inner=Cout // 64, c_offset=p * Cin, c_stride_lo=Lin * Cin, aux=aux,
-                                aux_mode=AUX_MUL_GELU_GRAD if aux is not None else AUX_NONE),
+                                aux_mode=AUX_MUL if aux is not None else AUX_NONE),
                        2 * B * U * Cin * ntaps * Cout)
 
 
@@ -245,7 +248,7 @@ def conv_wgrad(dz, x, dwk, k, s):
 # ------------------------------------------------------------------------------------------------ pos conv
 @cached_spec
 def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
-    """out = x + gelu(conv_same(x) + bias) for the grouped positional conv.  x/out [B,T,D]; wp [D, k*64] packed
+    """out = x + gelu(conv_same(x) + bias) for the grouped positional conv (z_out: gelu' of the pre-activation).  x/out [B,T,D]; wp [D, k*64] packed
     (row = output channel, column j*64+ci, ci >= D/groups zero).  One k-block per tap: the A tile is 64
     channels starting at the group's first channel, shifted in time by the tap ('same' padding = TMA zero fill)."""
     B, T, D = x.shape
@@ -254,7 +257,8 @@ def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
            cl=(cg, 0, 0, 0), ch=(0, 0, 1, 0))
     b = Op(wp, (k * 64, D), (k * 64,), MAJOR_K, cb=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, cg, 0, 0))
     return _with_flops(GemmSpec(a, b, T, cg, k, out, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
-                    c_stride_lo=cg, c_stride_hi=T * D, act=ACT_GELU, z_out=z_out, aux=x, aux_mode=AUX_ADD,
+                    c_stride_lo=cg, c_stride_hi=T * D, act=ACT_GELU_DZ if z_out is not None else ACT_GELU, z_out=z_out,
+                    aux=x, aux_mode=AUX_ADD,
                     bias=bias, bias_stride_lo=cg), 2 * B * T * D * cg * k)
 
 

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, MAJOR_K, MAJOR_MN, OUT_BF16, OUT_F32,
+from ._lib import (ACT_GELU, ACT_GELU_DZ, ACT_NONE, AUX_ADD, AUX_MUL, AUX_MUL_GELU_GRAD, AUX_NONE, MAJOR_K, MAJOR_MN, OUT_BF16, OUT_F32,
                    OUT_F32_ATOMIC)
 
 __all__ = ["Op", "GemmSpec", "gemm", "backend", "set_backend"]
@@ -412,6 +412,13 @@ class CudaBackend:
         dz = torch.empty_like(z)
         _lib.check(self.lib.a8_gelu_bwd(_ptr(dy), _ptr(z), _ptr(dz), z.numel(), _stream()), "a8_gelu_bwd")
         return dz
+
+    def mul(self, a, b):
+        """a * b elementwise, bf16 (GELU backward: b = the gelu'(z) a forward GEMM stored with ACT_GELU_DZ)"""
+        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+        out = torch.empty_like(a)
+        _lib.check(self.lib.a8_mul_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "a8_mul_bf16")
+        return out
 
     def log_softmax_fwd(self, x):
         V = x.shape[-1]

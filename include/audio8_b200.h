@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define A8_ABI_VERSION 1
+#define A8_ABI_VERSION 2
 
 int a8_version(void);
 const char* a8_last_error(void);
@@ -53,8 +53,8 @@ int a8_launch_count_add(int64_t n);
  * ---------------------------------------------------------------------------------------------- */
 enum { A8_MAJOR_K = 0, A8_MAJOR_MN = 1 };
 enum { A8_OUT_BF16 = 0, A8_OUT_F32 = 1, A8_OUT_F32_ATOMIC = 2 };
-enum { A8_ACT_NONE = 0, A8_ACT_GELU = 1 };
-enum { A8_AUX_NONE = 0, A8_AUX_ADD = 1, A8_AUX_MUL_GELU_GRAD = 2 };
+enum { A8_ACT_NONE = 0, A8_ACT_GELU = 1, A8_ACT_GELU_DZ = 2 };
+enum { A8_AUX_NONE = 0, A8_AUX_ADD = 1, A8_AUX_MUL_GELU_GRAD = 2, A8_AUX_MUL = 3 };
 
 typedef struct {
   const void* ptr;    /* bf16 */
@@ -75,9 +75,12 @@ typedef struct {
   int32_t c_dtype;            /* A8_OUT_* */
   int32_t act;                /* A8_ACT_* applied after bias */
   int64_t ldc, c_stride_lo, c_stride_hi; /* multiples of 8 elements; rows are padded to 8 columns */
-  void* z_out;                /* optional bf16 copy of (alpha*acc + bias) before the activation, addressed like C */
+  void* z_out;                /* optional bf16 side output addressed like C: the pre-activation (alpha*acc + bias), or, with
+                                 act = A8_ACT_GELU_DZ, gelu'(pre-activation) - what the backward pass multiplies by
+                                 (A8_AUX_MUL), so that its epilogue is one multiply instead of an erf + exp evaluation */
   const void* aux;            /* optional bf16 tensor addressed like C */
-  int32_t aux_mode;           /* A8_AUX_ADD: out = act(..) + aux;  A8_AUX_MUL_GELU_GRAD: out = (..) * gelu'(aux) */
+  int32_t aux_mode;           /* A8_AUX_ADD: out = act(..) + aux;  A8_AUX_MUL_GELU_GRAD: out = (..) * gelu'(aux);
+                                 A8_AUX_MUL: out = (..) * aux */
   int32_t bias_stride_lo;
   const float* bias;          /* optional fp32, index lo*bias_stride_lo + n */
   float alpha;
@@ -186,6 +189,8 @@ int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void*
 int a8_dropout(const void* x, void* out, int32_t dtype, int64_t n, float p, uint64_t seed, void* stream);
 /* dz = dy * gelu'(z) (bf16): backward of the GELU that a GEMM epilogue applied (`wav2vec2.py:422,428,607`) */
 int a8_gelu_bwd(const void* dy, const void* z, void* dz, int64_t n, void* stream);
+/* out = a * b elementwise, bf16 (the GELU backward when b holds gelu'(z) as written by A8_ACT_GELU_DZ); n % 8 == 0 */
+int a8_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* F.log_softmax(-1) of `wav2vec2.py:770`: x fp32 [R,V] -> y fp32; bwd consumes a strided fp32 gradient
  * (element (row, c) at dy[(row / rows_inner)*stride_outer + (row % rows_inner)*stride_row + c*stride_v], so the
  * [T,B,V] CTC gradient needs no transpose) and writes dx bf16 [R,V] */

@@ -81,13 +81,15 @@ def emu_gemm(g):
                     cols = torch.arange(n0, n0 + nv)
                     off = g.c_offset + hi * g.c_stride_hi + lo * g.c_stride_lo + rows[:, None] * g.ldc + cols[None, :]
                     if z is not None:
-                        z[off] = v.to(z.dtype)
-                    if g.act == _lib.ACT_GELU:
+                        z[off] = (gelu_grad(v) if g.act == _lib.ACT_GELU_DZ else v).to(z.dtype)
+                    if g.act in (_lib.ACT_GELU, _lib.ACT_GELU_DZ):
                         v = gelu(v)
                     if g.aux_mode == _lib.AUX_ADD:
                         v = v + aux[off].float()
                     elif g.aux_mode == _lib.AUX_MUL_GELU_GRAD:
                         v = v * gelu_grad(aux[off].float())
+                    elif g.aux_mode == _lib.AUX_MUL:
+                        v = v * aux[off].float()
                     if g.c_dtype == _lib.OUT_F32_ATOMIC:
                         c[off] += v
                     else:
@@ -276,6 +278,9 @@ class EmuOps(EmuBackend):
 
     def dropout(self, x, p, seed):
         return (x.float() * _drop_mask(x.shape, p, seed)).to(x.dtype)
+
+    def mul(self, a, b):
+        return _bf(a.float() * b.float())
 
     def gelu_bwd(self, dy, z):
         return _bf(dy.float() * gelu_grad(z.float()))

@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from audio8_b200 import gemm_specs as G
-from audio8_b200.ops import ACT_GELU, ACT_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, OUT_BF16, OUT_F32
+from audio8_b200.ops import ACT_GELU, ACT_GELU_DZ, ACT_NONE, AUX_ADD, AUX_MUL, AUX_MUL_GELU_GRAD, OUT_BF16, OUT_F32
 
 from emu import gelu, gelu_grad
 
@@ -34,18 +34,19 @@ def case_linear_fwd(dev, M=300, K=192, N=136, act=ACT_GELU, f32=False):
 
     def check():
         zz = x.float() @ w.float().t() + bias
-        _cmp(z, zz, 1e-2, "linear z_out")
-        _cmp(out, (gelu(zz) if act == ACT_GELU else zz) + aux.float(), 1e-2, "linear out")
+        _cmp(z, gelu_grad(zz) if act == ACT_GELU_DZ else zz, 1e-2, "linear z_out")
+        _cmp(out, (gelu(zz) if act != ACT_NONE else zz) + aux.float(), 1e-2, "linear out")
     return spec, check
 
 
-def case_linear_dgrad(dev, M=260, N=200, K=320):
+def case_linear_dgrad(dev, M=260, N=200, K=320, mode=AUX_MUL_GELU_GRAD):
     dy, w, z = _r((M, N), dev, 5), _r((N, K), dev, 6, 0.1), _r((M, K), dev, 7)
     dx = torch.zeros(M, K, dtype=torch.bfloat16, device=dev)
-    spec = G.linear_dgrad(dy, w, dx, z, AUX_MUL_GELU_GRAD)
+    spec = G.linear_dgrad(dy, w, dx, z, mode)
 
     def check():
-        _cmp(dx, (dy.float() @ w.float()) * gelu_grad(z.float()), 1e-2, "linear dgrad")
+        f = gelu_grad(z.float()) if mode == AUX_MUL_GELU_GRAD else z.float()
+        _cmp(dx, (dy.float() @ w.float()) * f, 1e-2, "linear dgrad")
     return spec, check
 
 
@@ -72,7 +73,7 @@ def case_conv_fwd(dev, B=2, Lin=301, C=128, Cout=192, k=3, s=2):
 
     def check():
         zz = F.conv1d(x.float().cpu().transpose(1, 2), w.float().cpu(), stride=s).transpose(1, 2)
-        _cmp(z, zz, 1e-2, "conv z")
+        _cmp(z, gelu_grad(zz), 1e-2, "conv z_out = gelu'(pre-activation)")
         _cmp(y, gelu(zz), 1e-2, "conv y")
     return spec, check
 
@@ -91,7 +92,7 @@ def case_conv_dgrad(dev, B=2, Lin=301, C=128, Cout=192, k=3, s=2):
     def check():
         g = F.conv_transpose1d(dz.float().cpu().transpose(1, 2), w.float().cpu(), stride=s)
         g = F.pad(g, (0, Lin - g.shape[-1])).transpose(1, 2)
-        _cmp(dx, g * gelu_grad(zprev.float().cpu()), 1e-2, "conv dgrad")
+        _cmp(dx, g * zprev.float().cpu(), 1e-2, "conv dgrad (* stored gelu')")
     return specs, check
 
 
@@ -138,7 +139,7 @@ def case_posconv(dev, B=2, T=70, D=128, groups=16, k=16):
         xc = x.float().cpu().transpose(1, 2).requires_grad_(True)
         wc = w.float().cpu().requires_grad_(True)
         zz = F.conv1d(F.pad(xc, (pad_l, k // 2)), wc, bias.cpu(), groups=groups)
-        _cmp(z, zz.transpose(1, 2), 1e-2, "posconv z")
+        _cmp(z, gelu_grad(zz.detach()).transpose(1, 2), 1e-2, "posconv z_out = gelu'(pre-activation)")
         _cmp(out, (gelu(zz) + xc).transpose(1, 2), 1e-2, "posconv out")
         zz.backward(dz.float().cpu().transpose(1, 2))
         _cmp(dx, xc.grad.transpose(1, 2) + res.float().cpu(), 1e-2, "posconv dgrad")
@@ -185,7 +186,9 @@ def case_attention(dev, B=2, T=150, H=2):
 ALL_CASES = dict(
     linear_fwd=case_linear_fwd,
     linear_fwd_f32=lambda dev: case_linear_fwd(dev, M=130, K=64, N=32, act=ACT_NONE, f32=True),
+    linear_fwd_gelu_dz=lambda dev: case_linear_fwd(dev, act=ACT_GELU_DZ),
     linear_dgrad=case_linear_dgrad,
+    linear_dgrad_mul=lambda dev: case_linear_dgrad(dev, mode=AUX_MUL),
     linear_wgrad=case_linear_wgrad,
     conv_fwd=case_conv_fwd,
     conv_fwd_k2=lambda dev: case_conv_fwd(dev, Lin=200, k=2, s=2),
