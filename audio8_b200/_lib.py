@@ -35,7 +35,7 @@ class A8Error(RuntimeError):
     pass
 
 
-_P, _I, _L, _F, _Z = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+_P, _I, _L, _F, _Z, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); every symbol declared in include/audio8_b200.h must be listed here
 SIGNATURES = {
@@ -65,7 +65,7 @@ SIGNATURES.update({
     "a8_colsum": (_I, [_P, _L, _I, _I, _P, _P]),
     "a8_dropout": (_I, [_P, _P, _I, _L, _F, _U, _P]),
     "a8_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
-    "a8_mul_bf16": (_I, [_P, _P, _P, _L, _P]),
+    "a8_mul_dgelu": (_I, [_P, _P, _P, _L, _P]),
     "a8_log_softmax_fwd": (_I, [_P, _P, _I, _I, _P]),
     "a8_log_softmax_bwd": (_I, [_P, _L, _L, _L, _I, _P, _P, _I, _I, _P]),
     "a8_conv0_stats": (_I, [_P, _I, _L, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
@@ -89,7 +89,7 @@ SIGNATURES.update({
     "a8_posconv_wn_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "a8_optim_grad_sqnorm": (_I, [_P, _P, _P, _I, _I, _P, _P]),
-    "a8_optim_adamw": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P]),
+    "a8_optim_adamw": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _D, _D, _D, _D, _D, _D, _D, _I, _P, _P]),
 })
 
 _lib = None

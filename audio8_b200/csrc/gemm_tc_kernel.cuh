@@ -236,13 +236,13 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
     }
   }
-  if (do_gelu_dz) {  // the activation and its derivative from one erf / exp evaluation; the derivative goes to z_out
+  if (do_gelu_dz) {  // the activation and its derivative from one erf / exp evaluation; the derivative goes to z_out as fp16
 #pragma unroll
     for (int g = 0; g < NP; ++g) {
       float d[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[8 * g + j] = gelu_both_fast(v[8 * g + j], d[j]);
-      if (do_z) my[g] = make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+      if (do_z) my[g] = make_uint4(pack_f16(d[0], d[1]), pack_f16(d[2], d[3]), pack_f16(d[4], d[5]), pack_f16(d[6], d[7]));
     }
   } else if (do_z) {
 #pragma unroll
@@ -268,7 +268,7 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       const uint32_t w[4] = {a[g].x, a[g].y, a[g].z, a[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16(w[j]);
+        const float2 t = (aux_mode == AUX_MUL) ? unpack_f16(w[j]) : unpack_bf16(w[j]);
         if (aux_mode == AUX_ADD) {
           v[8 * g + 2 * j] += t.x;
           v[8 * g + 2 * j + 1] += t.y;

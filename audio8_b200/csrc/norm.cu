@@ -545,16 +545,21 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* dy, 
   }
 }
 
-__global__ void __launch_bounds__(256) mul_bf16_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out,
-                                                       long long n8) {
+__global__ void __launch_bounds__(256) mul_dgelu_kernel(const __nv_bfloat16* a, const __half* b, __nv_bfloat16* out,
+                                                        long long n8) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    float x[8], y[8];
+    float x[8];
     load8(a + i * 8, x);
-    load8(b + i * 8, y);
+    const uint4 raw = *reinterpret_cast<const uint4*>(b + i * 8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] *= y[j];
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_f16(w[j]);
+      x[2 * j] *= t.x;
+      x[2 * j + 1] *= t.y;
+    }
     store8(out + i * 8, x);
   }
 }
@@ -729,15 +734,15 @@ extern "C" int a8_gelu_bwd(const void* dy, const void* z, void* dz, int64_t n, v
   return check_launch("gelu_bwd_kernel");
 }
 
-extern "C" int a8_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream_v) {
+extern "C" int a8_mul_dgelu(const void* a, const void* b, void* out, int64_t n, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  A8_REQUIRE(n > 0 && n % 8 == 0, "mul_bf16: n must be a positive multiple of 8");
+  A8_REQUIRE(n > 0 && n % 8 == 0, "mul_dgelu: n must be a positive multiple of 8");
   const long long n8 = n / 8;
   long long gl = (n8 + 255) / 256;
   const int grid = (int)(gl > 148 * 8 ? 148 * 8 : gl);
-  A8_CUDA(launch_pdl(mul_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+  A8_CUDA(launch_pdl(mul_dgelu_kernel, dim3(grid), dim3(256), 0, stream, 1, (const __nv_bfloat16*)a, (const __half*)b,
                      (__nv_bfloat16*)out, n8));
-  return check_launch("mul_bf16_kernel");
+  return check_launch("mul_dgelu_kernel");
 }
 
 extern "C" int a8_log_softmax_fwd(const float* x, float* y, int32_t R, int32_t V, void* stream_v) {

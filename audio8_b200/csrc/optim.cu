@@ -72,18 +72,24 @@ optim_sqnorm_kernel(const OptTensor* __restrict__ tab, const int* __restrict__ c
   }
 }
 
+// every constant below is derived on the host in double precision and rounded once, exactly like the Python scalars
+// torch.optim.AdamW hands to its kernels (1.f - 0.999f is 4.7e-5 away from float(1 - 0.999))
 struct AdamArgs {
-  float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, grad_scale;
-  int scale_grads_only;  // 1: clip_grad_norm_ semantics (scale the gradients in place, touch nothing else)
+  float decay;      // 1 - lr * weight_decay
+  float omb1;       // 1 - beta1
+  float beta2, omb2;
+  float eps, bc2_sqrt, step_size;  // step_size = lr / bias_correction1
+  float max_norm, grad_scale;
+  int scale_grads_only;  // 1: clip_grad_norm_ / scale_grads semantics (scale the gradients in place, touch nothing else)
 };
 
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamArgs& a, float gs) {
   g *= gs;
-  p *= 1.f - a.lr * a.weight_decay;                 // torch: param.mul_(1 - lr * weight_decay)
-  m = m + (g - m) * (1.f - a.beta1);                // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * a.beta2 + (1.f - a.beta2) * g * g;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+  p *= a.decay;                                     // torch: param.mul_(1 - lr * weight_decay)
+  m = m + (g - m) * a.omb1;                         // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * a.beta2 + a.omb2 * g * g;                 // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-  p -= (a.lr / a.bc1) * (m / denom);                // param.addcdiv_(exp_avg, denom, value=-step_size)
+  p -= a.step_size * (m / denom);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
 __global__ void __launch_bounds__(OPT_THREADS)
@@ -183,14 +189,15 @@ extern "C" int a8_optim_grad_sqnorm(const void* table, const int32_t* chunk_tens
 }
 
 extern "C" int a8_optim_adamw(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_off, int32_t n_chunks,
-                              int32_t chunk, const float* partials, float max_norm, float grad_scale, float lr,
-                              float beta1, float beta2, float eps, float weight_decay, float bias_correction1,
-                              float bias_correction2_sqrt, int32_t scale_grads_only, float* total_norm_out,
+                              int32_t chunk, const float* partials, float max_norm, float grad_scale, double lr,
+                              double beta1, double beta2, double eps, double weight_decay, double bias_correction1,
+                              double bias_correction2_sqrt, int32_t scale_grads_only, float* total_norm_out,
                               void* stream_v) {
   A8_REQUIRE(n_chunks > 0 && chunk > 0 && chunk % 4 == 0, "optim_adamw: bad chunking");
   A8_REQUIRE(max_norm <= 0.f || partials != nullptr, "optim_adamw: clipping needs the partial squared norms");
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt, max_norm, grad_scale,
-             scale_grads_only};
+  AdamArgs a{(float)(1.0 - lr * weight_decay), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
+             (float)bias_correction2_sqrt, (float)(bias_correction1 != 0.0 ? lr / bias_correction1 : 0.0), max_norm,
+             grad_scale, scale_grads_only};
   optim_adamw_kernel<<<opt_grid(n_chunks), OPT_THREADS, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const OptTensor*>(table), chunk_tensor, reinterpret_cast<const long long*>(chunk_off), n_chunks, chunk,
       partials, n_chunks, a, total_norm_out);

@@ -15,7 +15,7 @@ from . import gemm_specs as G
 from . import ops
 from .ops import ACT_GELU, ACT_GELU_DZ, ACT_NONE, AUX_ADD, AUX_MUL, AUX_NONE, OUT_BF16, OUT_F32
 
-BF16, F32 = torch.bfloat16, torch.float32
+BF16, F32, F16 = torch.bfloat16, torch.float32, torch.float16
 _site = [0]
 
 
@@ -298,7 +298,7 @@ class ConvFeatureFn(torch.autograd.Function):
             Lout = (Lin - k) // s + 1
             wk, wt = be.conv_pack(weights[i].detach().contiguous(), s, need_grad)
             y = _empty((B, Lout, c), BF16, a)
-            z = _empty((B, Lout, c), BF16, a) if need_grad else None
+            z = _empty((B, Lout, c), F16, a) if need_grad else None
             be.gemm(G.conv_fwd(a, wk, y, k, s, z_out=z))
             acts.append(y)
             zs.append(z)
@@ -319,7 +319,7 @@ class ConvFeatureFn(torch.autograd.Function):
         n = len(spec)
         grads = [None] * n
         if n > 1:
-            dz = be.mul(_bf16(dy), zs[n - 1])  # zs hold gelu'(pre-activation) (ACT_GELU_DZ)
+            dz = be.mul_dgelu(_bf16(dy), zs[n - 1])  # zs hold gelu'(pre-activation) in fp16 (ACT_GELU_DZ)
             for i in range(n - 1, 0, -1):
                 (c, k, s) = spec[i]
                 a_prev = acts[i - 1]
@@ -410,7 +410,7 @@ class EncoderFn(torch.autograd.Function):
             pg, pv = pos_g.detach().contiguous(), pos_v.detach().contiguous()
             wp, wpt, norm2 = be.posconv_pack(pg, pv, need_grad)
             s0 = _empty(x.shape, BF16, x)
-            z0 = _empty(x.shape, BF16, x)
+            z0 = _empty(x.shape, F16, x)
             be.gemm(G.posconv_fwd(x, wp, s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
             seed0 = next_seed() if p > 0 else 0
             h, _, _, mean0, rstd0 = be.layernorm_fwd(s0, ln_g.detach(), ln_b.detach(), 1e-5, p_y=p, seed_y=seed0)
@@ -440,7 +440,7 @@ class EncoderFn(torch.autograd.Function):
             be.gemm(G.linear_fwd(ctxv.view(M, D), wo_b, a, bo))
             seed1 = next_seed() if p > 0 else 0
             x1, _, s1, mean2, rstd2 = be.layernorm_fwd(x2d, g2, b2, 1e-6, h=a, p_h=p, seed_h=seed1)
-            z1 = _empty((M, F_), BF16, x)
+            z1 = _empty((M, F_), F16, x) if need_grad else None
             hid = _empty((M, F_), BF16, x)
             be.gemm(G.linear_fwd(x1, w1_b, hid, b1, act=ACT_GELU_DZ if need_grad else ACT_GELU, z_out=z1 if need_grad else None))
             f = _empty((M, D), BF16, x)
@@ -559,7 +559,7 @@ class EncoderFn(torch.autograd.Function):
         ds0, _, dlg, dlb, _ = be.layernorm_bwd(dcur.view(B, T, D), sv["s0"], sv["mean0"], sv["rstd0"], sv["ln_g"],
                                                p_y=p, seed_y=sv["seed0"], dg_out=_grad_zeros(klg, (D,), x),
                                                db_out=_grad_zeros(klb, (D,), x))
-        dz0 = be.mul(ds0, sv["z0"])
+        dz0 = be.mul_dgelu(ds0, sv["z0"])
         dpos_b = be.colsum(dz0, out=_grad_zeros(kb_, (D,), x))
         groups, k, pad_l = sv["groups"], sv["k"], sv["pad_l"]
         dwp = _empty((groups, k * 64, 64), F32, x)

@@ -189,7 +189,10 @@ def linear_wgrad_grouped(dy, x, dw):
     K = x.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
     b = Op(x, (K, M), (K,), MAJOR_MN, ck=(0, 64, 0, 0), cr=(64, 0, 0, 0))
-    return _with_flops(GemmSpec(a, b, N, K, cdiv(M, 64), dw, K, OUT_F32, split_k=1, block_n=256, cluster=2), 2 * M * N * K)
+    # k_inner: the operands' coordinate maps do not use the (kin, kbatch) split; a constant keeps problems with different
+    # token counts groupable
+    return _with_flops(GemmSpec(a, b, N, K, cdiv(M, 64), dw, K, OUT_F32, split_k=1, block_n=256, cluster=2,
+                                k_inner=1 << 20), 2 * M * N * K)
 
 
 # ------------------------------------------------------------------------------------------------ conv 1..6

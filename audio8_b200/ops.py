@@ -413,11 +413,11 @@ class CudaBackend:
         _lib.check(self.lib.a8_gelu_bwd(_ptr(dy), _ptr(z), _ptr(dz), z.numel(), _stream()), "a8_gelu_bwd")
         return dz
 
-    def mul(self, a, b):
-        """a * b elementwise, bf16 (GELU backward: b = the gelu'(z) a forward GEMM stored with ACT_GELU_DZ)"""
-        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
-        out = torch.empty_like(a)
-        _lib.check(self.lib.a8_mul_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "a8_mul_bf16")
+    def mul_dgelu(self, dy, g):
+        """GELU backward with the stored derivative: dy (bf16) * g (fp16: the gelu'(z) a forward GEMM wrote with ACT_GELU_DZ)"""
+        assert dy.dtype == torch.bfloat16 and g.dtype == torch.float16 and dy.is_contiguous() and g.is_contiguous()
+        out = torch.empty_like(dy)
+        _lib.check(self.lib.a8_mul_dgelu(_ptr(dy), _ptr(g), _ptr(out), dy.numel(), _stream()), "a8_mul_dgelu")
         return out
 
     def log_softmax_fwd(self, x):

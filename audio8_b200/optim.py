@@ -105,20 +105,28 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
 
 class FusedAdamW(torch.optim.Optimizer):
     """`torch.optim.AdamW` (amsgrad=False, maximize=False) with the update of ALL parameters in one launch, optionally
-    fused with gradient-norm clipping (`step(clip=...)`) and gradient unscaling (`step(grad_scale=...)` or
-    `scale_grads(s)` before `step()`, eight_mile OptimizerManager's name for it).  State keys match torch's
+    fused with gradient-norm clipping (`step(clip=...)`) and gradient unscaling (`step(grad_scale=...)`; `scale_grads(s)`,
+    eight_mile OptimizerManager's name for it, scales in place with one launch).  State keys match torch's
     (`step`, `exp_avg`, `exp_avg_sq`), so `state_dict()` round-trips with `torch.optim.AdamW`."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._plans = {}
-        self._pending_scale = 1.0
         self.operand_copies = {}  # parameter -> persistent bf16 buffer refreshed by the update kernel (optional)
         self.last_grad_norm = None
 
     def scale_grads(self, s):
-        """eight_mile OptimizerManager.scale_grads (train.py:323): folded into the next step's gradient reads"""
-        self._pending_scale *= float(s)
+        """eight_mile OptimizerManager.scale_grads (train.py:323): every gradient *= s, in place, one launch (so that a
+        later `clip_grad_norm_` sees the scaled gradients exactly as in the reference's call order).  `step(grad_scale=s)`
+        is the fused alternative that never writes the gradients back."""
+        params = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+        if not params:
+            return
+        _check(params)
+        plan = self._plan(("all",), params)
+        table = plan.refresh(None, None)
+        ops.backend().optim_adamw(table, plan.chunk_tensor, plan.chunk_off, CHUNK, None, 0.0, float(s), 0.0, 0.0, 0.0, 0.0,
+                                  0.0, 1.0, 1.0, True, None)
 
     def register_operand_copy(self, param, bf16_buffer):
         """the update kernel also writes bf16(param) into `bf16_buffer` (same numel): the GEMM operand copy a forward pass
@@ -135,8 +143,7 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         be = ops.backend()
-        gscale = float(grad_scale) * self._pending_scale
-        self._pending_scale = 1.0
+        gscale = float(grad_scale)
         groups = [([p for p in g["params"] if p.requires_grad], g) for g in self.param_groups]
         partial_sets = []
         if clip is not None and clip > 0:  # the norm runs over ALL groups' gradients, like clip_grad_norm_(model.parameters())

@@ -75,12 +75,13 @@ typedef struct {
   int32_t c_dtype;            /* A8_OUT_* */
   int32_t act;                /* A8_ACT_* applied after bias */
   int64_t ldc, c_stride_lo, c_stride_hi; /* multiples of 8 elements; rows are padded to 8 columns */
-  void* z_out;                /* optional bf16 side output addressed like C: the pre-activation (alpha*acc + bias), or, with
-                                 act = A8_ACT_GELU_DZ, gelu'(pre-activation) - what the backward pass multiplies by
-                                 (A8_AUX_MUL), so that its epilogue is one multiply instead of an erf + exp evaluation */
+  void* z_out;                /* optional 2-byte side output addressed like C: the pre-activation (alpha*acc + bias) in bf16,
+                                 or, with act = A8_ACT_GELU_DZ, gelu'(pre-activation) in IEEE fp16 (values in [-0.13, 1.13]:
+                                 11 mantissa bits) - what the backward pass multiplies by (A8_AUX_MUL), so that its epilogue
+                                 is one multiply instead of an erf + exp evaluation */
   const void* aux;            /* optional bf16 tensor addressed like C */
   int32_t aux_mode;           /* A8_AUX_ADD: out = act(..) + aux;  A8_AUX_MUL_GELU_GRAD: out = (..) * gelu'(aux);
-                                 A8_AUX_MUL: out = (..) * aux */
+                                 A8_AUX_MUL: out = (..) * aux with aux in IEEE fp16 (the factors A8_ACT_GELU_DZ wrote) */
   int32_t bias_stride_lo;
   const float* bias;          /* optional fp32, index lo*bias_stride_lo + n */
   float alpha;
@@ -189,8 +190,9 @@ int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void*
 int a8_dropout(const void* x, void* out, int32_t dtype, int64_t n, float p, uint64_t seed, void* stream);
 /* dz = dy * gelu'(z) (bf16): backward of the GELU that a GEMM epilogue applied (`wav2vec2.py:422,428,607`) */
 int a8_gelu_bwd(const void* dy, const void* z, void* dz, int64_t n, void* stream);
-/* out = a * b elementwise, bf16 (the GELU backward when b holds gelu'(z) as written by A8_ACT_GELU_DZ); n % 8 == 0 */
-int a8_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* GELU backward with the stored derivative: out = dy * g elementwise, dy / out bf16, g = gelu'(z) in IEEE fp16 as written
+ * by A8_ACT_GELU_DZ; n % 8 == 0 */
+int a8_mul_dgelu(const void* dy, const void* g, void* out, int64_t n, void* stream);
 /* F.log_softmax(-1) of `wav2vec2.py:770`: x fp32 [R,V] -> y fp32; bwd consumes a strided fp32 gradient
  * (element (row, c) at dy[(row / rows_inner)*stride_outer + (row % rows_inner)*stride_row + c*stride_v], so the
  * [T,B,V] CTC gradient needs no transpose) and writes dx bf16 [R,V] */
@@ -290,15 +292,16 @@ int a8_posconv_wn_bwd(const float* dwp, const float* g, const float* v, const fl
  * a8_optim_adamw: total = sqrt(sum partials) * |grad_scale|; coef = min(1, max_norm / (total + 1e-6)) when max_norm > 0;
  *   every gradient is read as g * grad_scale * coef (never written back) and the parameter, exp_avg, exp_avg_sq (and the
  *   bf16 copy) are updated with torch.optim.AdamW's arithmetic (decoupled weight decay, bias_correction1 = 1 - beta1^t,
- *   bias_correction2_sqrt = sqrt(1 - beta2^t), both computed by the caller).  partials may be NULL when max_norm <= 0.
+ *   bias_correction2_sqrt = sqrt(1 - beta2^t), both computed by the caller; the hyper-parameters arrive as doubles and
+ *   1 - lr*wd, 1 - beta1, 1 - beta2, lr / bias_correction1 are formed in double and rounded once, as torch does).  partials may be NULL when max_norm <= 0.
  *   scale_grads_only != 0: clip_grad_norm_ semantics instead - the gradients are scaled in place, nothing else changes.
  *   total_norm_out (optional): the pre-clip gradient norm, what clip_grad_norm_ returns.
  * ---------------------------------------------------------------------------------------------- */
 int a8_optim_grad_sqnorm(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_off, int32_t n_chunks,
                          int32_t chunk, float* partials, void* stream);
 int a8_optim_adamw(const void* table, const int32_t* chunk_tensor, const int64_t* chunk_off, int32_t n_chunks,
-                   int32_t chunk, const float* partials, float max_norm, float grad_scale, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, float bias_correction1, float bias_correction2_sqrt,
+                   int32_t chunk, const float* partials, float max_norm, float grad_scale, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, double bias_correction1, double bias_correction2_sqrt,
                    int32_t scale_grads_only, float* total_norm_out, void* stream);
 
 #ifdef __cplusplus

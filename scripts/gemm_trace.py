@@ -31,6 +31,10 @@ elif which == "ffn1":
                         z_out=torch.empty(M, F_, device=dev, dtype=bf))
 elif which == "ffn2":
     spec = G.linear_fwd(r(M, F_), r(D, F_), torch.empty(M, D, device=dev, dtype=bf), r(D, dtype=torch.float32))
+elif which == "wgrad":  # one weight-gradient problem with the grouped launch's tiling (256 x 256 pairs, no split-K)
+    spec = G.linear_wgrad_grouped(r(M, F_), r(M, D), torch.empty(F_, D, device=dev))
+elif which == "convw":
+    spec = G.conv_wgrad(r(6, 23999, 512), r(6, 47999, 512), torch.zeros(512, 1536, device=dev), 3, 2)
 else:
     spec = G.conv_fwd(r(6, 47999, 512), r(512, 1536), torch.empty(6, 23999, 512, device=dev, dtype=bf), 3, 2,
                       z_out=torch.empty(6, 23999, 512, device=dev, dtype=bf))

@@ -2,7 +2,7 @@
 # round 2, run A: full parity suite (no -x: every failure listed), parity report, GEMM bench with library column, bench lines
 tag=${1:-r2a}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/${tag}_tests.log 2>&1
+timeout 2400 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/${tag}_tests.log 2>&1
 echo "tests exit $?" >> gpurun_out/${tag}_tests.log
 cp gpurun_out/parity_report.md gpurun_out/${tag}_parity.md 2>/dev/null
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from audio8_b200 import gemm_specs as G  # noqa: E402
 from audio8_b200 import ops  # noqa: E402
-from audio8_b200.ops import ACT_GELU, AUX_ADD, AUX_MUL_GELU_GRAD  # noqa: E402
+from audio8_b200.ops import ACT_GELU, ACT_GELU_DZ, AUX_ADD, AUX_MUL  # noqa: E402
 
 dev = "cuda"
 bf = torch.bfloat16
@@ -142,13 +142,13 @@ bench("fused attention fwd (dropout 0.1)", lambda: be.attn_fwd(qkv, H, 0.125, No
 bench("fused attention bwd (dq + dkv kernels)", lambda: be.attn_bwd(qkv, ctx, dctx, lse, H, 0.125, None, 0.1, 7), flops=8 * B * H * T * T * 64)
 gemms = {
     "gemm qkv_fwd 4494x2304x768": lambda: G.linear_fwd(r(M, D), r(3 * D, D), torch.empty(M, 3 * D, device=dev, dtype=bf), r(3 * D, dtype=torch.float32)),
-    "gemm ffn1_fwd+gelu 4494x3072x768": lambda: G.linear_fwd(r(M, D), r(F_, D), torch.empty(M, F_, device=dev, dtype=bf), r(F_, dtype=torch.float32), act=ACT_GELU, z_out=torch.empty(M, F_, device=dev, dtype=bf)),
+    "gemm ffn1_fwd+gelu 4494x3072x768": lambda: G.linear_fwd(r(M, D), r(F_, D), torch.empty(M, F_, device=dev, dtype=bf), r(F_, dtype=torch.float32), act=ACT_GELU_DZ, z_out=torch.empty(M, F_, device=dev, dtype=bf)),
     "gemm ffn2_fwd 4494x768x3072": lambda: G.linear_fwd(r(M, F_), r(D, F_), torch.empty(M, D, device=dev, dtype=bf), r(D, dtype=torch.float32)),
-    "gemm ffn2_dgrad*gelu' 4494x3072x768": lambda: G.linear_dgrad(r(M, D), r(D, F_), torch.empty(M, F_, device=dev, dtype=bf), aux=r(M, F_), aux_mode=AUX_MUL_GELU_GRAD),
+    "gemm ffn2_dgrad*gelu' 4494x3072x768": lambda: G.linear_dgrad(r(M, D), r(D, F_), torch.empty(M, F_, device=dev, dtype=bf), aux=r(M, F_).to(torch.float16), aux_mode=AUX_MUL),
     "gemm ffn_wgrad 3072x768x4494": lambda: G.linear_wgrad(r(M, F_), r(M, D), torch.zeros(F_, D, device=dev)),
     "gemm conv1_fwd (implicit, k=3 s=2)": lambda: G.conv_fwd(r(B, 47999, 512), r(512, 1536), torch.empty(B, 23999, 512, device=dev, dtype=bf), 3, 2, z_out=torch.empty(B, 23999, 512, device=dev, dtype=bf)),
     "gemm conv1_wgrad": lambda: G.conv_wgrad(r(B, 23999, 512), r(B, 47999, 512), torch.zeros(512, 1536, device=dev), 3, 2),
-    "gemm conv2_dgrad phase 0 (*gelu')": lambda: G.conv_dgrad(r(B, 11999, 512), r(512, 1024), torch.empty(B, 23999, 512, device=dev, dtype=bf), 3, 2, 0, aux=r(B, 23999, 512)),
+    "gemm conv2_dgrad phase 0 (*gelu')": lambda: G.conv_dgrad(r(B, 11999, 512), r(512, 1024), torch.empty(B, 23999, 512, device=dev, dtype=bf), 3, 2, 0, aux=r(B, 23999, 512).to(torch.float16)),
     "gemm posconv_fwd (k=128, g=16)": lambda: G.posconv_fwd(r(B, T, D), r(D, 128 * 64), torch.empty(B, T, D, device=dev, dtype=bf), r(D, dtype=torch.float32), 16, 128, 63, z_out=torch.empty(B, T, D, device=dev, dtype=bf)),
 }
 for name, mk in gemms.items():

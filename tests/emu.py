@@ -279,8 +279,8 @@ class EmuOps(EmuBackend):
     def dropout(self, x, p, seed):
         return (x.float() * _drop_mask(x.shape, p, seed)).to(x.dtype)
 
-    def mul(self, a, b):
-        return _bf(a.float() * b.float())
+    def mul_dgelu(self, dy, g):
+        return _bf(dy.float() * g.float())
 
     def gelu_bwd(self, dy, z):
         return _bf(dy.float() * gelu_grad(z.float()))

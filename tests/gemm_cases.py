@@ -29,7 +29,7 @@ def case_linear_fwd(dev, M=300, K=192, N=136, act=ACT_GELU, f32=False):
     bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).to(dev)
     aux = _r((M, N), dev, 4)
     out = torch.zeros(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=dev)
-    z = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    z = torch.zeros(M, N, dtype=torch.float16 if act == ACT_GELU_DZ else torch.bfloat16, device=dev)
     spec = G.linear_fwd(x, w, out, bias, act, z, aux, AUX_ADD, OUT_F32 if f32 else OUT_BF16)
 
     def check():
@@ -41,6 +41,8 @@ def case_linear_fwd(dev, M=300, K=192, N=136, act=ACT_GELU, f32=False):
 
 def case_linear_dgrad(dev, M=260, N=200, K=320, mode=AUX_MUL_GELU_GRAD):
     dy, w, z = _r((M, N), dev, 5), _r((N, K), dev, 6, 0.1), _r((M, K), dev, 7)
+    if mode == AUX_MUL:  # the stored gelu' factors are fp16
+        z = z.to(torch.float16)
     dx = torch.zeros(M, K, dtype=torch.bfloat16, device=dev)
     spec = G.linear_dgrad(dy, w, dx, z, mode)
 
@@ -68,7 +70,7 @@ def case_conv_fwd(dev, B=2, Lin=301, C=128, Cout=192, k=3, s=2):
     Lout = (Lin - k) // s + 1
     x, w = _r((B, Lin, C), dev, 10), _r((Cout, C, k), dev, 11, 0.05)
     y = torch.zeros(B, Lout, Cout, dtype=torch.bfloat16, device=dev)
-    z = torch.zeros_like(y)
+    z = torch.zeros(B, Lout, Cout, dtype=torch.float16, device=dev)
     spec = G.conv_fwd(x, _conv_pack(w), y, k, s, z)
 
     def check():
@@ -85,7 +87,7 @@ def conv_wt(w, s, p):  # [Cout, Cin, k] -> [Cin, ntaps*Cout] for phase p
 
 def case_conv_dgrad(dev, B=2, Lin=301, C=128, Cout=192, k=3, s=2):
     Lout = (Lin - k) // s + 1
-    dz, w, zprev = _r((B, Lout, Cout), dev, 12), _r((Cout, C, k), dev, 13, 0.05), _r((B, Lin, C), dev, 14)
+    dz, w, zprev = _r((B, Lout, Cout), dev, 12), _r((Cout, C, k), dev, 13, 0.05), _r((B, Lin, C), dev, 14).to(torch.float16)
     dx = torch.zeros(B, Lin, C, dtype=torch.bfloat16, device=dev)
     specs = [G.conv_dgrad(dz, conv_wt(w, s, p), dx, k, s, p, zprev) for p in range(s)]
 
@@ -127,7 +129,7 @@ def case_posconv(dev, B=2, T=70, D=128, groups=16, k=16):
     x, w = _r((B, T, D), dev, 17), _r((D, cg, k), dev, 18, 0.2)
     bias = torch.randn(D, generator=torch.Generator().manual_seed(19)).to(dev)
     out = torch.zeros(B, T, D, dtype=torch.bfloat16, device=dev)
-    z = torch.zeros_like(out)
+    z = torch.zeros(B, T, D, dtype=torch.float16, device=dev)
     f = G.posconv_fwd(x, posconv_pack(w, groups), out, bias, groups, k, pad_l, z)
     dz, res = _r((B, T, D), dev, 20), _r((B, T, D), dev, 21)
     dx = torch.zeros_like(out)

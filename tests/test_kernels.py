@@ -100,7 +100,8 @@ def test_colsum_gelu_dropout_cast(be):
     _close(be.colsum(x.cuda()), E.colsum(x), 2e-3, "colsum")
     dy, z = _bf((300, 512), 2), _bf((300, 512), 3, 2.0)
     _close(be.gelu_bwd(dy.cuda(), z.cuda()), E.gelu_bwd(dy, z), 2e-2, "gelu_bwd")
-    _close(be.mul(dy.cuda(), z.cuda()), E.mul(dy, z), 1e-2, "mul")
+    gz = torch.rand(300, 512, generator=_g(5)).to(torch.float16)
+    _close(be.mul_dgelu(dy.cuda(), gz.cuda()), E.mul_dgelu(dy, gz), 1e-2, "mul_dgelu")
     for t in (x, torch.randn(64, 512, generator=_g(4))):
         d = be.dropout(t.cuda(), 0.1, 99)
         kept = (d.float() != 0).float().mean().item()

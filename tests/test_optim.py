@@ -28,22 +28,21 @@ def _run(device, clip, grad_scale, steps=4, skip_grad=False):
         if skip_grad:
             ours[4].grad = ref[4].grad = None  # a parameter without a gradient is left untouched
         if grad_scale != 1.0:
-            o1.scale_grads(grad_scale)  # eight_mile OptimizerManager.scale_grads (train.py:323)
             for b in ref:
                 if b.grad is not None:
                     b.grad.mul_(grad_scale)
         if clip is not None:
             n_ref = torch.nn.utils.clip_grad_norm_(ref, clip)
         if it % 2 == 0 or clip is None:
-            o1.step(clip=clip)  # fused clip + update
+            o1.step(clip=clip, grad_scale=grad_scale)  # fused unscale + clip + update (gradients never rewritten)
             n_ours = o1.last_grad_norm
-        else:  # the trainers' unmodified call pattern: clip in place, then a plain step
+        else:  # the trainers' unmodified call pattern (train.py:323-325): scale in place, clip in place, plain step
+            if grad_scale != 1.0:
+                o1.scale_grads(grad_scale)  # eight_mile OptimizerManager.scale_grads
             n_ours = clip_grad_norm_(ours, clip)
-            if grad_scale != 1.0:  # the pending scale is applied inside step(); compare the norms on scaled gradients
-                n_ours = n_ours * abs(grad_scale)
             o1.step()
         o2.step()
-        if clip is not None and not (it % 2 == 1 and grad_scale != 1.0):
+        if clip is not None:
             assert abs(float(n_ours) - float(n_ref)) <= 1e-5 * float(n_ref), (it, float(n_ours), float(n_ref))
     for i, (a, b) in enumerate(zip(ours, ref)):
         err = (a.detach() - b.detach()).abs().max().item()
@@ -52,7 +51,7 @@ def _run(device, clip, grad_scale, steps=4, skip_grad=False):
             continue
         for key in ("exp_avg", "exp_avg_sq"):
             sa, sb = o1.state[a][key], o2.state[b][key]
-            tol = 1e-6 if clip is None else 1e-5  # with clipping the coefficient inherits torch's fp32 norm error
+            tol = 2e-6 if clip is None else 1e-5  # with clipping the coefficient inherits torch's fp32 norm error
             assert (sa - sb).abs().max().item() <= tol * sb.abs().max().item() + 1e-12, (i, key)
     assert torch.equal(bf.view(ours[0].shape), ours[0].detach().to(torch.bfloat16)), "bf16 operand copy not refreshed"
     # state_dict round trip with torch's optimizer
@@ -65,8 +64,6 @@ CASES = [(None, 1.0, False), (0.5, 1.0, False), (25.0, 1.0, True), (1.0, 0.125, 
 
 @pytest.mark.parametrize("clip,grad_scale,skip", CASES)
 def test_fused_adamw_host_logic_cpu(clip, grad_scale, skip, emu_backend):
-    if grad_scale != 1.0:
-        pytest.skip("the in-place clip_grad_norm_ + pending scale pattern is exercised on the GPU")
     _run("cpu", clip, grad_scale, skip_grad=skip)
 
 
