@@ -46,6 +46,9 @@ SIGNATURES = {
     "a8_set_seed_source": (_I, [_P]),
     "a8_gemm": (_I, [C.POINTER(Gemm), _P]),
     "a8_gemm_group": (_I, [C.POINTER(Gemm), _I, _P]),
+    "a8_gemm_group_blob_bytes": (_Z, []),
+    "a8_gemm_group_prepare": (_I, [C.POINTER(Gemm), _I, _P]),
+    "a8_gemm_group_launch": (_I, [_P, _P]),
     "a8_ctc_scratch_floats": (_Z, [_I, _I, _I]),
     "a8_ctc_greedy": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P]),
     "a8_ctc_prep": (_I, [_P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -163,9 +163,31 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
 // One persistent launch over n problems that share operand majors, coordinate maps, tile shape, split-K factor and
 // epilogue kind (see GroupParams in gemm_tc_kernel.cuh).  Used for the weight-gradient GEMMs of the transformer stack:
 // every layer's dW = dY^T X (4 per layer) is deferred to the end of the stack's backward and run as one kernel.
-extern "C" int a8_gemm_group(const a8_gemm_t* gs, int32_t n, void* stream_v) {
+namespace {
+struct GroupBlob {  // everything one grouped launch needs, built on the host once per set of operand addresses
+  GroupParams gp;
+  KParams kp;
+  int ek, bn, cl, magic;
+};
+constexpr int GROUP_MAGIC = 0x61386772;
+}  // namespace
+
+extern "C" size_t a8_gemm_group_blob_bytes(void) { return sizeof(GroupBlob) + 64; }
+
+extern "C" int a8_gemm_group_launch(const void* blob_v, void* stream_v) {
+  A8_REQUIRE(blob_v != nullptr, "gemm_group_launch: null blob");
+  const GroupBlob* blob = reinterpret_cast<const GroupBlob*>((reinterpret_cast<uintptr_t>(blob_v) + 63u) & ~uintptr_t(63));
+  A8_REQUIRE(blob->magic == GROUP_MAGIC, "gemm_group_launch: blob was not written by a8_gemm_group_prepare");
+  return launch_group_mnmn(blob->ek, blob->bn, blob->cl, blob->gp, blob->kp, static_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int a8_gemm_group_prepare(const a8_gemm_t* gs, int32_t n, void* blob_v) {
   A8_REQUIRE(gs != nullptr && n >= 1 && n <= GROUP_MAX, "gemm_group: %d problems (1..%d supported per launch)", n, GROUP_MAX);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  A8_REQUIRE(blob_v != nullptr, "gemm_group_prepare: null blob");
+  GroupBlob* blob = reinterpret_cast<GroupBlob*>((reinterpret_cast<uintptr_t>(blob_v) + 63u) & ~uintptr_t(63));
+  blob->magic = 0;
+  GroupParams& gp = blob->gp;
+  KParams& kp = blob->kp;
   const a8_gemm_t& g0 = gs[0];
   int bn = g0.block_n;
   if (bn == 0) bn = 256;
@@ -173,8 +195,6 @@ extern "C" int a8_gemm_group(const a8_gemm_t* gs, int32_t n, void* stream_v) {
   const int split = g0.split_k > 1 ? g0.split_k : 1;
   A8_REQUIRE(g0.a.major == MAJOR_MN && g0.b.major == MAJOR_MN, "gemm_group: only (MN,MN) operand majors are instantiated");
   A8_REQUIRE(split == 1 || g0.c_dtype == OUT_F32_ATOMIC, "gemm_group: split_k needs atomic fp32 output");
-  static thread_local GroupParams gp;  // 14 KB: filled per call, passed by value as a kernel parameter
-  KParams kp;
   memset(&kp, 0, sizeof(kp));
   copy_coef(kp.a, g0.a);
   copy_coef(kp.b, g0.b);
@@ -211,6 +231,17 @@ extern "C" int a8_gemm_group(const a8_gemm_t* gs, int32_t n, void* stream_v) {
   }
   gp.n_prob = n;
   kp.total_tiles = (int)tiles;
-  const int ek = ek_make(g0.c_dtype, 0, 0, AUX_NONE);
-  return launch_group_mnmn(ek, bn, cl, gp, kp, stream);
+  blob->ek = ek_make(g0.c_dtype, 0, 0, AUX_NONE);
+  blob->bn = bn;
+  blob->cl = cl;
+  blob->magic = GROUP_MAGIC;
+  return 0;
+}
+
+extern "C" int a8_gemm_group(const a8_gemm_t* gs, int32_t n, void* stream_v) {
+  static thread_local GroupBlob* blob = nullptr;
+  if (blob == nullptr) blob = static_cast<GroupBlob*>(aligned_alloc(64, (sizeof(GroupBlob) + 63) & ~size_t(63)));
+  A8_REQUIRE(blob != nullptr, "gemm_group: out of host memory");
+  const int rc = a8_gemm_group_prepare(gs, n, blob);
+  return rc ? rc : a8_gemm_group_launch(blob, stream_v);
 }

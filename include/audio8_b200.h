@@ -96,6 +96,12 @@ int a8_gemm(const a8_gemm_t* p, void* stream);
  * dW = dY^T X: the transformer stack defers the 4 weight-gradient GEMMs of every layer (what autograd runs as 48 separate
  * addmm calls behind `/root/reference/audio8/wav2vec2.py:644`) to the end of its backward and issues them as one kernel. */
 int a8_gemm_group(const a8_gemm_t* problems, int32_t n, void* stream);
+/* The same in two steps, for callers that launch the same group repeatedly (fixed operand addresses): prepare encodes
+ * the 2n tensor maps and the tile table into a caller-owned HOST buffer of a8_gemm_group_blob_bytes() bytes (~100 us of
+ * host time for 48 problems), launch only enqueues the kernel. */
+size_t a8_gemm_group_blob_bytes(void);
+int a8_gemm_group_prepare(const a8_gemm_t* problems, int32_t n, void* blob);
+int a8_gemm_group_launch(const void* blob, void* stream);
 /* debug aid: later a8_gemm launches stamp clock64() timelines of their first CTAs into `buf` (device memory,
  * 4*3*8*4 int64); NULL turns it off.  Not used by the product path. */
 void a8_gemm_set_trace(void* buf);

@@ -84,6 +84,34 @@ def conv_out_lengths(L, conv_features):
 # ------------------------------------------------------------------------------------------------
 # layers
 # ------------------------------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    """value and gradient rounded to bf16 (computed in fp32 on both sides): one STORED activation of the implementation
+    under test"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+STORAGE_EMULATION = [False]
+
+
+def set_storage_emulation(flag):
+    """Test aid (not in the reference): round every activation the CUDA path STORES in bf16 — conv / linear / LayerNorm
+    outputs, residual sums, attention probabilities and context — and the gradients at the same points, while all
+    arithmetic stays fp32.  The distance between this run and the plain fp32 oracle is the noise floor of the storage
+    format itself, which a correct kernel cannot beat and a wrong one exceeds."""
+    STORAGE_EMULATION[0] = bool(flag)
+
+
+def _q(x):
+    return _RoundBF16.apply(x) if STORAGE_EMULATION[0] else x
+
+
 def _lin(sd, key, x):
     return F.linear(x, sd[key + ".weight"], sd.get(key + ".bias"))
 
@@ -101,7 +129,7 @@ def conv_feature_extractor(sd, x, prefix="feature_extractor.", conv_features=CON
         if i == 0:
             C = h.shape[1]
             h = F.group_norm(h, C, sd[f"{prefix}conv_layers.0.2.weight"], sd[f"{prefix}conv_layers.0.2.bias"], 1e-5)
-        h = F.gelu(h)
+        h = _q(F.gelu(h))
     return h
 
 
@@ -121,17 +149,17 @@ def transformer_layer(sd, pre, x, num_heads, key_mask=None, pdrop=0.0):
     x = ln2(x + MHA(x)); x = ln1(x + FFN(x)).  key_mask: bool [B,T], False = padded key."""
     B, T, D = x.shape
     dk = D // num_heads
-    q = _lin(sd, pre + "self_attn.w_Q.layer", x).view(B, T, num_heads, dk).transpose(1, 2)
-    k = _lin(sd, pre + "self_attn.w_K.layer", x).view(B, T, num_heads, dk).transpose(1, 2)
-    v = _lin(sd, pre + "self_attn.w_V.layer", x).view(B, T, num_heads, dk).transpose(1, 2)
+    q = _q(_lin(sd, pre + "self_attn.w_Q.layer", x)).view(B, T, num_heads, dk).transpose(1, 2)
+    k = _q(_lin(sd, pre + "self_attn.w_K.layer", x)).view(B, T, num_heads, dk).transpose(1, 2)
+    v = _q(_lin(sd, pre + "self_attn.w_V.layer", x)).view(B, T, num_heads, dk).transpose(1, 2)
     s = q @ k.transpose(-1, -2) / math.sqrt(dk)
     if key_mask is not None:
         s = s.masked_fill(~key_mask[:, None, None, :], -1e9)
-    a = _drop(torch.softmax(s, -1), pdrop) @ v  # eight_mile SeqScaledDotProductAttention: dropout on the probabilities
+    a = _q(_q(_drop(torch.softmax(s, -1), pdrop)) @ v)  # eight_mile SeqScaledDotProductAttention: dropout on the probabilities
     a = a.transpose(1, 2).reshape(B, T, D)
-    x = _ln(sd, pre + "ln2", x + _drop(_lin(sd, pre + "self_attn.w_O.layer", a), pdrop), LN_EPS_8MILE)
-    f = _lin(sd, pre + "ffn.3.layer", F.gelu(_lin(sd, pre + "ffn.0.layer", x)))
-    return _ln(sd, pre + "ln1", x + _drop(f, pdrop), LN_EPS_8MILE)
+    x = _q(_ln(sd, pre + "ln2", _q(x + _drop(_q(_lin(sd, pre + "self_attn.w_O.layer", a)), pdrop)), LN_EPS_8MILE))
+    f = _q(_lin(sd, pre + "ffn.3.layer", _q(F.gelu(_lin(sd, pre + "ffn.0.layer", x)))))
+    return _q(_ln(sd, pre + "ln1", _q(x + _drop(f, pdrop)), LN_EPS_8MILE))
 
 
 def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", pad_mask=None, groups=16, pdrop=0.0,
@@ -145,8 +173,8 @@ def audio_transformer_encoder(sd, x, num_heads, num_layers, prefix="encoder.", p
     end_pad = k // 2
     start_pad = end_pad - 1 if k % 2 == 0 else end_pad
     xc = F.conv1d(F.pad(x.transpose(1, 2), (start_pad, end_pad)), w, sd[prefix + "pos_conv.conv.1.bias"], groups=groups)
-    x = x + F.gelu(xc).transpose(1, 2)
-    x = _drop(_ln(sd, prefix + "ln", x, LN_EPS_TORCH), pdrop)
+    x = _q(x + F.gelu(xc).transpose(1, 2))
+    x = _q(_drop(_ln(sd, prefix + "ln", x, LN_EPS_TORCH), pdrop))
     for i in range(num_layers):
         if active_layers is not None and not active_layers[i]:
             continue
@@ -206,8 +234,8 @@ def pretrain_forward(sd, x, time_mask, num_heads=12, num_layers=12, num_groups=2
     """Wav2Vec2Model.forward (wav2vec2.py:927-952) with the time mask supplied.  Returns a dict of stages."""
     fx = conv_feature_extractor(sd, x, conv_features=conv_features).transpose(1, 2)
     feats = _ln(sd, "layer_norm", fx, LN_EPS_TORCH)
-    unmasked = feats
-    h = _drop(_lin(sd, "proj_to_input.layer", feats), dropout_input)
+    unmasked = feats  # the quantizer branch reads the fp32 copy of the LayerNorm output in the CUDA path as well
+    h = _q(_drop(_lin(sd, "proj_to_input.layer", _q(feats)), dropout_input))
     unmasked = _drop(unmasked, dropout_features)
     B, T, _ = h.shape
     tm = torch.as_tensor(time_mask).to(h.device)

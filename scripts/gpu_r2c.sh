@@ -10,3 +10,5 @@ timeout 120 python scripts/gemm_trace.py convw > gpurun_out/${tag}_trace_convw.l
 timeout 300 python scripts/gemm_bench.py group > gpurun_out/${tag}_group.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:gemm_tc_group -c 1 --csv --page raw --log-file gpurun_out/${tag}_ncu_group.csv python scripts/gemm_bench.py group > gpurun_out/${tag}_ncu.log 2>&1
 tail -12 gpurun_out/${tag}_tests.log | cut -c1-300; cat gpurun_out/${tag}_trace_wgrad.log; cat gpurun_out/${tag}_trace_convw.log | head -40; cat gpurun_out/${tag}_group.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'attn_' -c 3 -o gpurun_out/${tag}_attn python scripts/kernel_table.py --once > gpurun_out/${tag}_ncu_attn.log 2>&1
+ls -la gpurun_out/ | tail -5

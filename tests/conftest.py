@@ -35,7 +35,7 @@ def pytest_sessionfinish(session, exitstatus):
         out = os.path.join(ROOT, "gpurun_out")
         os.makedirs(out, exist_ok=True)
         with open(os.path.join(out, "parity_report.md"), "w") as f:
-            f.write("| case | tensor | cosine | rel-L2 | held to (cos >= / rel <=) | bf16-autocast oracle vs fp32 oracle "
+            f.write("| case | tensor | cosine | rel-L2 | held to (cos >= / rel <=) | bf16-storage oracle vs fp32 oracle "
                     "(cosine / rel-L2) |\n|---|---|---:|---:|---|---|\n")
             for case, what, cos, rel, cmin, rmax, fl in mc.PARITY_LOG:
                 fls = f"{fl[0]:.6f} / {fl[1]:.5f}" if fl else ""

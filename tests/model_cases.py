@@ -47,9 +47,10 @@ def _cos_rel(got, want):
 
 
 def grad_close(got, want, what, cos_min=0.999, rel_max=3e-2, floor=None):
-    """floor: the same gradient from the ORACLE run under torch's bf16 autocast (its distance to the fp32 oracle is the
-    noise floor of bf16 activation storage for this tensor).  A tensor outside (cos_min, rel_max) still passes when it
-    is within 1.5x that floor: the deviation is then the storage format's, not the kernels'.  Both are reported."""
+    """floor: the same gradient from the ORACLE run with every activation the CUDA path stores in bf16 rounded to bf16
+    (values and gradients; all arithmetic fp32: `ref_wav2vec2.set_storage_emulation`).  Its distance to the plain fp32
+    oracle is the noise floor of the storage format for this tensor.  A tensor outside (cos_min, rel_max) still passes
+    when it is within 1.5x that floor: the deviation is then the storage format's, not the kernels'.  Both are reported."""
     nw = want.detach().double().norm().item()
     if nw < 1e-10:
         assert got.detach().double().norm().item() < 1e-6, f"{what}: expected ~0 gradient"
@@ -63,7 +64,7 @@ def grad_close(got, want, what, cos_min=0.999, rel_max=3e-2, floor=None):
     if not ok and fl is not None:
         ok = rel <= 1.5 * fl[1] and (1.0 - cos) <= 2.25 * (1.0 - fl[0])
     assert ok, (f"{what}: cosine {cos:.5f}, rel-L2 {rel:.4f} (need {cos_min} / {rel_max}"
-                + (f"; bf16-autocast oracle floor: cosine {fl[0]:.5f}, rel-L2 {fl[1]:.4f})" if fl else ")"))
+                + (f"; bf16-storage oracle floor: cosine {fl[0]:.5f}, rel-L2 {fl[1]:.4f})" if fl else ")"))
 
 
 def check_param_grads(named_got, want, pinned=True, label="grad "):
@@ -321,13 +322,20 @@ def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRA
     R.pretrain_loss(sdz, x, tmask, neg, force_idx=kidx, force_z=z_ours, **okw)["loss"].backward()
     floor = {}
     if bf16_floor and torch.cuda.is_available():
-        # noise floor of bf16 activation storage: the SAME oracle under torch's bf16 autocast on the GPU (cuBLAS / cuDNN
-        # bf16 kernels, fp32 LayerNorm / softmax), same draws, same pinned logits, against the fp32 CPU oracle
+        # noise floor of bf16 activation STORAGE: the same oracle, fp32 arithmetic (run on the GPU with TF32 off, for
+        # speed), every activation the CUDA path stores in bf16 rounded to bf16 in value and gradient; same draws, same
+        # pinned logits; compared against the fp32 CPU oracle
         sdb = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
         okb = dict(okw, gumbel_noise=noise.cuda() if noise is not None else None)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        R.set_storage_emulation(True)
+        try:
             lb = R.pretrain_loss(sdb, x.cuda(), tmask, neg, force_idx=kidx, force_z=z_ours.cuda(), **okb)["loss"]
-        lb.backward()
+            lb.backward()
+        finally:
+            R.set_storage_emulation(False)
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
         floor = {k: v.grad.float().cpu() for k, v in sdb.items() if v.grad is not None}
     for k in names:
         layer = int(k.split("encoders.")[1].split(".")[0]) if "encoders." in k else None
