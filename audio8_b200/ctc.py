@@ -1,7 +1,7 @@
 """Drop-in for the CTC loss of `audio8/ctc.py` (reference: /root/reference/audio8/ctc.py:186-206).
 
 `CTCLoss` keeps the reference's constructor and call signature; the arithmetic runs in hand-written
-sm_100a kernels (audio8_b200/csrc/ctc.cu) instead of ATen's ctc_loss kernels.  Blank / PAD / EOS ids are
+sm_100a kernels (audio8_b200/csrc/ctc_loss.cu, ctc.cu) instead of ATen's ctc_loss kernels.  Blank / PAD / EOS ids are
 read from `Offsets` at call time, like the reference does (`ctc.py:193,202`; `train.py:22-27` re-points them).
 """
 import torch
@@ -26,8 +26,13 @@ def _offsets():
 
 
 class _CTCFunction(torch.autograd.Function):
+    """x: log-probs [T,B,V] (any strides) or, with from_logits, the [T,B,V] view of the classifier's logits [B,T,V]:
+    the kernels then normalise the rows themselves and backward returns d loss / d logits directly (the log_softmax
+    at wav2vec2.py:770 and its backward never run as separate passes)."""
+
     @staticmethod
-    def forward(ctx, log_prob, input_lengths, targets, target_lengths, blank, pad, eos, mean, zero_infinity):
+    def forward(ctx, log_prob, input_lengths, targets, target_lengths, blank, pad, eos, mean, zero_infinity,
+                from_logits=False):
         be = ops.backend()
         dev = log_prob.device
         lp = log_prob if log_prob.dtype == torch.float32 else log_prob.float()
@@ -39,18 +44,20 @@ class _CTCFunction(torch.autograd.Function):
         il = torch.as_tensor(input_lengths).to(device=dev, dtype=torch.int64, non_blocking=True)
         tg = targets.to(device=dev, dtype=torch.int64, non_blocking=True)
         flat, off, tl32, il32 = be.ctc_prep(tg, pad, eos, tl, il)
-        loss, nll, alpha, beta = be.ctc_forward(lp, flat, off, tl32, il32, max_S, blank, mean, zero_infinity)
-        ctx.saved = (lp, flat, off, tl32, il32, alpha, beta, nll)
-        ctx.cfg = (max_S, blank, mean, zero_infinity, log_prob.dtype)
+        loss, nll, alpha = be.ctc_forward(lp, flat, off, tl32, il32, max_S, blank, mean, zero_infinity, from_logits)
+        ctx.saved = (lp, flat, off, tl32, il32, alpha, nll)
+        # the gradient is written in the memory order of the input: [B,T,V]-major for the transposed views train.py passes
+        batch_major = lp.dim() == 3 and lp.stride(1) > lp.stride(0)
+        ctx.cfg = (max_S, blank, mean, zero_infinity, log_prob.dtype, from_logits, batch_major)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        lp, flat, off, tl32, il32, alpha, beta, nll = _take_saved(ctx)
-        max_S, blank, mean, zero_infinity, dtype = ctx.cfg
-        grad = ops.backend().ctc_backward(lp, flat, off, tl32, il32, max_S, blank, alpha, beta, nll, grad_out, mean,
-                                          zero_infinity)
-        return grad.to(dtype), None, None, None, None, None, None, None, None
+        lp, flat, off, tl32, il32, alpha, nll = _take_saved(ctx)
+        max_S, blank, mean, zero_infinity, dtype, from_logits, batch_major = ctx.cfg
+        grad = ops.backend().ctc_backward(lp, flat, off, tl32, il32, max_S, blank, alpha, nll, grad_out, mean,
+                                          zero_infinity, from_logits, batch_major)
+        return grad.to(dtype), None, None, None, None, None, None, None, None, None
 
 
 def ctc_loss(log_prob, input_lengths, targets, target_lengths, blank=0, pad=1, eos=2, reduction="sum",
@@ -58,8 +65,30 @@ def ctc_loss(log_prob, input_lengths, targets, target_lengths, blank=0, pad=1, e
     """log_prob [T,B,V] (any strides, e.g. the transposed view train.py:39 passes), targets [B,S] padded."""
     if reduction not in ("sum", "mean"):
         raise ValueError(f"reduction {reduction!r} not supported (the reference uses 'sum', ctc.py:187)")
+    logits = _fused_logits(log_prob)
+    if logits is not None:
+        return _CTCFunction.apply(logits.transpose(0, 1), input_lengths, targets, target_lengths, int(blank), int(pad),
+                                  int(eos), reduction == "mean", bool(zero_infinity), True)
     return _CTCFunction.apply(log_prob, input_lengths, targets, target_lengths, int(blank), int(pad), int(eos),
                               reduction == "mean", bool(zero_infinity))
+
+
+def _fused_logits(log_prob):
+    """`Wav2Vec2AcousticModel.forward` tags the log-probs it returns with the logits they were computed from
+    (`a8_logits`).  When the tensor handed to the loss is that tensor, or the `[T,B,V]` transposed view of it that
+    `train.py:39` builds, the loss is computed from the logits and its gradient flows into them directly; anything
+    else (sliced, copied, cast, produced elsewhere) takes the plain log-prob path."""
+    base = log_prob._base if log_prob._base is not None else log_prob
+    logits = getattr(base, "a8_logits", None)
+    if logits is None or logits.dtype != torch.float32 or logits.dim() != 3:
+        return None
+    B, T, V = logits.shape
+    same_storage = log_prob.untyped_storage().data_ptr() == base.untyped_storage().data_ptr()
+    if not (same_storage and log_prob.storage_offset() == base.storage_offset() and base.is_contiguous()):
+        return None
+    if tuple(log_prob.shape) == (T, B, V) and log_prob.stride() == (V, T * V, 1):
+        return logits
+    return None
 
 
 class CTCLoss(torch.nn.Module):

@@ -273,37 +273,43 @@ class CudaBackend:
         B, S = targets.shape
         dev = targets.device
         assert targets.dtype == torch.int64 and target_lengths.dtype == torch.int64 and input_lengths.dtype == torch.int64
-        ints = torch.empty(B * S + 4 * B, dtype=torch.int32, device=dev)
+        ints = torch.empty(B * S + 4 * B + 1, dtype=torch.int32, device=dev)
         flat, row_start, off, tl, il = (ints[:B * S], ints[B * S:B * S + B], ints[B * S + B:B * S + 2 * B],
-                                        ints[B * S + 2 * B:B * S + 3 * B], ints[B * S + 3 * B:])
+                                        ints[B * S + 2 * B:B * S + 3 * B], ints[B * S + 3 * B:])  # il: B lengths + ticket
         _lib.check(self.lib.a8_ctc_prep(_ptr(targets), targets.stride(0), targets.stride(1), B, S, pad, eos,
                                         _ptr(target_lengths), _ptr(input_lengths), _ptr(flat), _ptr(row_start),
                                         _ptr(off), _ptr(tl), _ptr(il), _stream()), "a8_ctc_prep")
         return flat, off, tl, il
 
-    def ctc_forward(self, lp, flat, off, tl, il, max_S, blank, mean, zero_inf):
-        T, B, V = lp.shape
-        assert lp.is_cuda and lp.dtype == torch.float32
+    def ctc_forward(self, x, flat, off, tl, il, max_S, blank, mean, zero_inf, from_logits=False):
+        """x: fp32 [T,B,V] view (any strides) of log-probs, or of the classifier's logits when from_logits"""
+        T, B, V = x.shape
+        assert x.is_cuda and x.dtype == torch.float32 and il.numel() == B + 1
         n = self.lib.a8_ctc_scratch_floats(T, B, max_S)
-        alpha = torch.empty(n, dtype=torch.float32, device=lp.device)
-        beta = torch.empty(n, dtype=torch.float32, device=lp.device)
-        nll = torch.empty(B, dtype=torch.float32, device=lp.device)
-        loss = torch.empty((), dtype=torch.float32, device=lp.device)
-        _lib.check(self.lib.a8_ctc_forward(_ptr(lp), lp.stride(0), lp.stride(1), lp.stride(2), T, B, V, _ptr(flat),
-                                           _ptr(off), _ptr(tl), _ptr(il), max_S, blank, int(mean), int(zero_inf),
-                                           _ptr(alpha), _ptr(beta), _ptr(nll), _ptr(loss), _stream()),
+        alpha = torch.empty(n, dtype=torch.float32, device=x.device)
+        out = torch.empty(B + 1, dtype=torch.float32, device=x.device)
+        nll, loss = out[:B], out[B]
+        _lib.check(self.lib.a8_ctc_forward(_ptr(x), x.stride(0), x.stride(1), x.stride(2), T, B, V, int(from_logits),
+                                           _ptr(flat), _ptr(off), _ptr(tl), _ptr(il), max_S, blank, int(mean),
+                                           int(zero_inf), _ptr(alpha), _ptr(nll), _ptr(loss), _stream()),
                    "a8_ctc_forward")
-        return loss, nll, alpha, beta
+        return loss, nll, alpha
 
-    def ctc_backward(self, lp, flat, off, tl, il, max_S, blank, alpha, beta, nll, grad_out, mean, zero_inf):
-        T, B, V = lp.shape
-        grad = torch.empty(T, B, V, dtype=torch.float32, device=lp.device)
+    def ctc_backward(self, x, flat, off, tl, il, max_S, blank, alpha, nll, grad_out, mean, zero_inf, from_logits=False,
+                     batch_major=False):
+        """-> fp32 gradient w.r.t. x, laid out [T,B,V] contiguous, or [B,T,V] contiguous (returned as its [T,B,V] view)
+        when batch_major: the layout of the logits tensor it flows back into"""
+        T, B, V = x.shape
+        if batch_major:
+            grad = torch.empty(B, T, V, dtype=torch.float32, device=x.device).transpose(0, 1)
+        else:
+            grad = torch.empty(T, B, V, dtype=torch.float32, device=x.device)
         go = grad_out.contiguous().float()
         go_stride = 0 if go.numel() == 1 else 1
-        _lib.check(self.lib.a8_ctc_backward(_ptr(lp), lp.stride(0), lp.stride(1), lp.stride(2), T, B, V, _ptr(flat),
-                                            _ptr(off), _ptr(tl), _ptr(il), max_S, blank, _ptr(alpha), _ptr(beta),
+        _lib.check(self.lib.a8_ctc_backward(_ptr(x), x.stride(0), x.stride(1), x.stride(2), T, B, V, int(from_logits),
+                                            _ptr(flat), _ptr(off), _ptr(tl), _ptr(il), max_S, blank, _ptr(alpha),
                                             _ptr(nll), _ptr(go), go_stride, int(mean), int(zero_inf), _ptr(grad),
-                                            _stream()), "a8_ctc_backward")
+                                            grad.stride(0), grad.stride(1), _stream()), "a8_ctc_backward")
         return grad
 
     def ctc_greedy(self, lp, in_len, blank):

@@ -536,7 +536,10 @@ class Wav2Vec2AcousticModel(nn.Module):
         with torch.no_grad() if self.freeze else contextlib.ExitStack():
             encoded, pad_mask = self.encoder(x, pad_mask)
         logits = self.proj(encoded, out_f32=True)
-        return Fn.LogSoftmaxFn.apply(logits), pad_mask
+        lp = Fn.LogSoftmaxFn.apply(logits)
+        # the CTC loss (audio8_b200.ctc) recognises this tensor and works from the logits: fused log_softmax + CTC
+        lp.a8_logits = logits if logits.is_contiguous() else None
+        return lp, pad_mask
 
 
 class Wav2Vec2Model(nn.Module):

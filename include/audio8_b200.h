@@ -107,22 +107,26 @@ int a8_gemm_group_launch(const void* blob, void* stream);
 void a8_gemm_set_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
- * CTC loss.  Replaces `torch.nn.functional.ctc_loss` as called at `ctc.py:197-205`
- * (ATen ctc_loss_log_alpha / log_beta / collect kernels; cuDNN disabled by the reference).
- * log_probs: fp32 [T,B,V] with arbitrary element strides (the reference passes a transposed view,
- * `train.py:39`).  targets: int32 concatenated labels (ctc.py:193-194 stripping is done by the caller),
- * tgt_offsets[b] = start of utterance b.  alpha/beta: fp32 scratch [B, T, 2*max_S+1].
- * a8_ctc_forward fills alpha, beta (log2 domain, row pitch 32*ceil4((2*max_S+1)/32)), nll[b] (+inf if
- * infeasible) and, if loss != NULL, the reduced loss: sum_b nll_b, or mean_b(nll_b / max(S_b,1)) when
- * reduction_mean; infinite rows count as 0 when zero_infinity.
- * a8_ctc_backward writes grad[T,B,V] (contiguous) = (exp(lp) - occupancy) * scale_b for t < len, else 0
- * (PyTorch's convention), scale_b = grad_out[b*grad_out_stride] (/ (max(S_b,1)*B) when
- * reduction_mean); infeasible rows get 0.
+ * CTC loss (csrc/ctc_loss.cu).  Replaces `torch.nn.functional.ctc_loss` as called at `ctc.py:197-205`
+ * (ATen ctc_loss_log_alpha / log_beta / collect kernels; cuDNN disabled by the reference) and, with from_logits != 0,
+ * the `log_softmax` in front of it as well (`wav2vec2.py:770`): x then holds the classifier's logits, rows are
+ * normalised on the fly and the backward pass returns d loss / d logits = (softmax - occupancy) * scale directly.
+ * x: fp32 [T,B,V] with arbitrary element strides (the reference passes a transposed view, `train.py:39`).
+ * targets: int32 concatenated labels (ctc.py:193-194 stripping is done by a8_ctc_prep), tgt_offsets[b] = start of
+ * utterance b.  in_lengths: B ints followed by ONE int that is zero on entry (a8_ctc_prep writes it).
+ * alpha: fp32 scratch of a8_ctc_scratch_floats(T, B, max_S) floats (log2 domain; the only scratch: the beta sweep emits
+ * the gradient directly).
+ * a8_ctc_forward fills alpha, nll[b] (+inf if infeasible) and, if loss != NULL, the reduced loss: sum_b nll_b, or
+ * mean_b(nll_b / max(S_b,1)) when reduction_mean; infinite rows count as 0 when zero_infinity.  One launch.
+ * a8_ctc_backward writes grad[t*grad_stride_t + b*grad_stride_b + v] = (exp(logp) - occupancy) * scale_b for t < len,
+ * else 0 (PyTorch's convention; with from_logits this IS the gradient w.r.t. the logits), scale_b =
+ * grad_out[b*grad_out_stride] (/ (max(S_b,1)*B) when reduction_mean); infeasible rows get 0.  One launch.
  * ---------------------------------------------------------------------------------------------- */
 size_t a8_ctc_scratch_floats(int32_t T, int32_t B, int32_t max_S);
 /* ctc.py:193-194 on the device, sync-free: flat[] = row-major compaction of targets[B,S] (int64, strided)
  * without PAD/EOS; tgt_offsets = exclusive cumsum(target_lengths); lengths converted to int32.
- * flat has room for B*S entries, row_start is B ints of scratch. */
+ * flat has room for B*S entries, row_start is B ints of scratch, in_lengths has room for B + 1 ints (the last one is
+ * set to 0: the completion ticket a8_ctc_forward's loss reduction counts on). */
 /* Greedy best-path decode, the reference's only alignment (`ctc.py:161-162`: argmax(-1).unique_consecutive(), blank
  * dropped): lp fp32 [B,T,V] with element strides, in_len int32 [B] (or NULL) -> out int32 [B,T] (decoded ids, then -1)
  * and out_len int32 [B].  Integer result, bit-exact against the reference's ops on the same log-probs. */
@@ -131,17 +135,15 @@ int a8_ctc_greedy(const float* lp, int64_t stride_b, int64_t stride_t, int64_t s
 int a8_ctc_prep(const int64_t* targets, int64_t stride_b, int64_t stride_s, int32_t B, int32_t S, int32_t pad,
                 int32_t eos, const int64_t* target_lengths, const int64_t* input_lengths, int32_t* flat,
                 int32_t* row_start, int32_t* tgt_offsets, int32_t* tgt_lengths, int32_t* in_lengths, void* stream);
-int a8_ctc_forward(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T,
-                   int32_t B, int32_t V, const int32_t* targets, const int32_t* tgt_offsets,
-                   const int32_t* tgt_lengths, const int32_t* in_lengths, int32_t max_S, int32_t blank,
-                   int32_t reduction_mean, int32_t zero_infinity, float* alpha, float* beta, float* nll,
-                   float* loss, void* stream);
-int a8_ctc_backward(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T,
-                    int32_t B, int32_t V, const int32_t* targets, const int32_t* tgt_offsets,
-                    const int32_t* tgt_lengths, const int32_t* in_lengths, int32_t max_S, int32_t blank,
-                    const float* alpha, const float* beta, const float* nll, const float* grad_out,
-                    int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity, float* grad,
-                    void* stream);
+int a8_ctc_forward(const float* x, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T, int32_t B, int32_t V,
+                   int32_t from_logits, const int32_t* targets, const int32_t* tgt_offsets, const int32_t* tgt_lengths,
+                   const int32_t* in_lengths, int32_t max_S, int32_t blank, int32_t reduction_mean,
+                   int32_t zero_infinity, float* alpha, float* nll, float* loss, void* stream);
+int a8_ctc_backward(const float* x, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T, int32_t B, int32_t V,
+                    int32_t from_logits, const int32_t* targets, const int32_t* tgt_offsets, const int32_t* tgt_lengths,
+                    const int32_t* in_lengths, int32_t max_S, int32_t blank, const float* alpha, const float* nll,
+                    const float* grad_out, int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity,
+                    float* grad, int64_t grad_stride_t, int64_t grad_stride_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (+ residual add, + dropout), bf16 rows of C <= 1024 channels (C % 8 == 0), fp32 statistics.

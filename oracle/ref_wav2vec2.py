@@ -261,7 +261,7 @@ def pretrain_loss(sd, x, time_mask, neg_idx, n_vars=640, **kw):
 
 def acoustic_forward(sd, x, pad_mask, num_heads=12, num_layers=12, time_mask=None, channel_mask=None,
                      conv_features=CONV_FEATURES[16], dropout=0.0, dropout_input=0.0, active_layers=None,
-                     freeze_fx=False):
+                     freeze_fx=False, return_logits=False):
     """Wav2Vec2AcousticModel.forward (wav2vec2.py:765-770) over Wav2Vec2Encoder.forward (:696-723).
     time_mask / channel_mask: the training-time masks (None = eval).  Returns (log_probs [B,T,V], frame_mask)."""
     p = "encoder."
@@ -278,4 +278,6 @@ def acoustic_forward(sd, x, pad_mask, num_heads=12, num_layers=12, time_mask=Non
     enc = audio_transformer_encoder(sd, h, num_heads, num_layers, prefix=p + "encoder.", pad_mask=fmask, pdrop=dropout,
                                     active_layers=active_layers)
     logits = _lin(sd, "proj", enc)
+    if return_logits:
+        return F.log_softmax(logits, -1), fmask, logits
     return F.log_softmax(logits, -1), fmask

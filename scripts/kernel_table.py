@@ -110,13 +110,13 @@ tg = torch.randint(4, Vc, (Bc, S), device=dev)
 tl = torch.full((Bc,), S, dtype=torch.int64, device=dev)
 il = torch.full((Bc,), Tc, dtype=torch.int64, device=dev)
 flat, off, tl32, il32 = be.ctc_prep(tg, 1, 2, tl, il)
-lossc, nll, alpha, beta = be.ctc_forward(lp, flat, off, tl32, il32, S, 0, False, True)
+lossc, nll, alpha = be.ctc_forward(lp, flat, off, tl32, il32, S, 0, False, True)
 go = torch.ones((), device=dev)
 
 
 def ctc_both():
-    l_, n_, a_, b_ = be.ctc_forward(lp, flat, off, tl32, il32, S, 0, False, True)
-    be.ctc_backward(lp, flat, off, tl32, il32, S, 0, a_, b_, n_, go, False, True)
+    l_, n_, a_ = be.ctc_forward(lp, flat, off, tl32, il32, S, 0, False, True)
+    be.ctc_backward(lp, flat, off, tl32, il32, S, 0, a_, n_, go, False, True)
 
 
 bench("ctc fwd+bwd (T=1500,B=256,V=32,S=300)", ctc_both, bytes_=2 * Tc * Bc * Vc * 4, note="latency-bound recursion (T serial steps)")
@@ -129,8 +129,8 @@ f2, o2, t2, i2 = be.ctc_prep(tg2, 1, 2, tl2, il2)
 
 
 def ctc_small():
-    l_, n_, a_, b_ = be.ctc_forward(lp2, f2, o2, t2, i2, 150, 0, False, True)
-    be.ctc_backward(lp2, f2, o2, t2, i2, 150, 0, a_, b_, n_, go, False, True)
+    l_, n_, a_ = be.ctc_forward(lp2, f2, o2, t2, i2, 150, 0, False, True)
+    be.ctc_backward(lp2, f2, o2, t2, i2, 150, 0, a_, n_, go, False, True)
 
 
 bench("ctc fwd+bwd (T=749,B=8,V=32,S=150)", ctc_small, bytes_=2 * Tc2 * Bc2 * Vc * 4, note="latency-bound")

@@ -474,18 +474,22 @@ class EmuOps(EmuBackend):
         keep = (targets != pad) & (targets != eos)
         flat = targets[keep].int()
         off = (torch.cumsum(target_lengths, 0) - target_lengths).int()
-        return flat, off, target_lengths.int(), input_lengths.int()
+        il = torch.cat([input_lengths.int(), torch.zeros(1, dtype=torch.int32)])  # + the loss reduction's ticket
+        return flat, off, target_lengths.int(), il
 
-    def ctc_forward(self, lp, flat, off, tl, il, max_S, blank, mean, zero_inf):
+    def ctc_forward(self, lp, flat, off, tl, il, max_S, blank, mean, zero_inf, from_logits=False):
+        il = il[:-1]
         with torch.enable_grad():
             lpg = lp.detach().clone().requires_grad_(True)
-            nll = torch.nn.functional.ctc_loss(lpg, flat.long(), il.long(), tl.long(), blank=blank, reduction="none",
+            lpn = torch.log_softmax(lpg, -1) if from_logits else lpg
+            nll = torch.nn.functional.ctc_loss(lpn, flat.long(), il.long(), tl.long(), blank=blank, reduction="none",
                                                zero_infinity=False)
         v = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll) if zero_inf else nll
         loss = (v / tl.clamp_min(1)).mean() if mean else v.sum()
-        return loss.detach(), nll.detach(), (lpg, nll), None
+        return loss.detach(), nll.detach(), (lpg, nll)
 
-    def ctc_backward(self, lp, flat, off, tl, il, max_S, blank, alpha, beta, nll, grad_out, mean, zero_inf):
+    def ctc_backward(self, lp, flat, off, tl, il, max_S, blank, alpha, nll, grad_out, mean, zero_inf, from_logits=False,
+                     batch_major=False):
         lpg, nll_g = alpha
         B = lp.shape[1]
         scale = grad_out.reshape(-1).expand(B).clone()

@@ -321,7 +321,7 @@ def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRA
     sdz = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     R.pretrain_loss(sdz, x, tmask, neg, force_idx=kidx, force_z=z_ours, **okw)["loss"].backward()
     floor = {}
-    if bf16_floor and torch.cuda.is_available():
+    if (bf16_floor or device == "cuda") and torch.cuda.is_available():
         # noise floor of bf16 activation STORAGE: the same oracle, fp32 arithmetic (run on the GPU with TF32 off, for
         # speed), every activation the CUDA path stores in bf16 rounded to bf16 in value and gradient; same draws, same
         # pinned logits; compared against the fp32 CPU oracle
@@ -434,7 +434,8 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
     np.random.seed(seed)
     lp, fmask = model(x.to(device), pad_mask.to(device))
     out_len = fmask.sum(-1)
-    lp.retain_grad()
+    logits_ours = lp.a8_logits  # the loss works from the logits (fused log_softmax + CTC): its gradient lands there
+    logits_ours.retain_grad()
     loss = ctc_loss(lp.transpose(1, 0), out_len, targets.to(device), tgt_len, blank=0, pad=1, eos=2)
     loss.backward()
     T, D = lp.shape[1], cfg.get("d_model", 768)
@@ -444,15 +445,15 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
         tm = R.create_mask((B, T), 0.5, 10)
         cm = R.create_mask((B, D), 0.1, 64)
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    lp2, fm2 = R.acoustic_forward(sdg, x, pad_mask, cfg.get("num_heads", 12), cfg.get("num_layers", 12), tm, cm,
-                                  freeze_fx=freeze_fx)
+    lp2, fm2, logits2 = R.acoustic_forward(sdg, x, pad_mask, cfg.get("num_heads", 12), cfg.get("num_layers", 12), tm, cm,
+                                           freeze_fx=freeze_fx, return_logits=True)
     assert (fm2.sum(-1).numpy() == out_len.cpu().numpy()).all(), "frame lengths differ"
     # CTC occupancies are exponentially sensitive to the sequence of log-probs (an untrained model spreads its mass
     # over ~10^100 alignments: the bf16-sized log-prob differences, 0.3 % rms, move dL/dlogprob by ~25 % at T=749 even
     # though the loss agrees to 0.07 %), so at this size parity is checked piecewise, every piece on identical inputs:
     #   (1) log-probs and loss against the oracle;
     #   (2) the CTC kernel against float64 CTC on the ORACLE's log-probs (ATen's fp32 CTC is the less accurate one);
-    #   (3) the network's backward against the oracle's backward driven by the SAME dL/dlogprob (ours).
+    #   (3) the network's backward against the oracle's backward driven by the SAME dL/dlogits (ours).
     valid = fm2[..., None].expand_as(lp2)
     act_close(torch.where(valid, lp.detach().float().cpu(), torch.zeros(())), torch.where(valid, lp2.detach(), torch.zeros(())),
               "log-probs (valid frames)", tol=5e-2)
@@ -465,8 +466,7 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
     loss_same.backward()
     assert abs(loss_same.item() - loss2.item()) <= 2e-5 * abs(loss2.item()), (loss_same.item(), loss2.item())
     grad_close(lp_same.grad.cpu(), lp64.grad, "CTC gradient on identical log-probs", cos_min=0.99999, rel_max=2e-3)
-    dlp = lp.grad
-    lp2.backward(dlp.detach().float().cpu())
+    logits2.backward(logits_ours.grad.detach().float().cpu())
     got = dict(model.named_parameters())
     bad = []
     for k in check_grads:

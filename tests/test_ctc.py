@@ -92,6 +92,71 @@ def test_cuda_ctc_matches_oracle_sweep(T, B, S, V):
     assert gr.sum(-1).abs().max().item() < 1e-3
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,B,S,V", [(50, 8, 10, 32), (749, 8, 150, 32), (300, 5, 40, 100), (1500, 16, 300, 32), (40, 3, 0, 8),
+                                     (600, 4, 400, 29)])
+def test_cuda_ctc_from_logits_matches_log_softmax_then_ctc(T, B, S, V):
+    """fused log_softmax + CTC (wav2vec2.py:770 + ctc.py:197): loss and d loss / d logits against float64
+    log_softmax -> ctc_loss autograd, through the tagging the acoustic model uses (`a8_logits` on the log-probs)"""
+    from audio8_b200.ctc import ctc_loss
+    from audio8_b200.functional import LogSoftmaxFn
+    g = torch.Generator().manual_seed(3 * T + B)
+    logits = torch.randn(B, T, V, generator=g) * 2.0
+    tl = torch.randint(max(S // 2, 0), S + 1, (B,), generator=g)
+    il = torch.randint(max(T // 2, min(2 * S + 1, T)), T + 1, (B,), generator=g)
+    tg = torch.full((B, S + 1), 1, dtype=torch.long)
+    for b in range(B):
+        tg[b, : tl[b]] = torch.randint(3, V, (int(tl[b]),), generator=g)
+    x64 = logits.double().clone().requires_grad_(True)
+    ref = ref_ctc.ctc_loss_reference(torch.log_softmax(x64, -1).transpose(0, 1), il, tg, tl, 0, 1, 2, "sum")
+    ref.backward()
+    x32 = logits.clone().requires_grad_(True)
+    ref32 = ref_ctc.ctc_loss_reference(torch.log_softmax(x32, -1).transpose(0, 1), il, tg, tl, 0, 1, 2, "sum")
+    ref32.backward()
+    aten_err = (x32.grad.double() - x64.grad).abs().max().item()
+    d = logits.cuda().requires_grad_(True)
+    lp = LogSoftmaxFn.apply(d)
+    lp.a8_logits = d  # what Wav2Vec2AcousticModel.forward does
+    loss = ctc_loss(lp.transpose(1, 0), il.cuda(), tg.cuda(), tl, reduction="sum")
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-5 * abs(ref.item()) + 1e-4, (loss.item(), ref.item())
+    my_err = (d.grad.cpu().double() - x64.grad).abs().max().item()
+    assert my_err <= 3 * aten_err + 5e-5, (my_err, aten_err)
+    gr = d.grad.cpu()
+    for b in range(B):
+        assert gr[b, il[b]:].abs().max().item() == 0 if il[b] < T else True
+    assert gr.sum(-1).abs().max().item() < 1e-3  # softmax - occupancy sums to zero over classes
+    # an untagged / re-laid-out tensor takes the plain log-prob path and agrees
+    d2 = logits.cuda().requires_grad_(True)
+    loss2 = ctc_loss(torch.log_softmax(d2, -1).transpose(1, 0), il.cuda(), tg.cuda(), tl, reduction="sum")
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) <= 2e-5 * abs(loss.item()) + 1e-4
+    assert (d2.grad - d.grad).abs().max().item() <= 3 * aten_err + 1e-4
+
+
+def test_ctc_from_logits_host_logic_cpu(emu_backend):
+    """the tagging / view recognition of the fused path, through the ABI emulation"""
+    from audio8_b200.ctc import _fused_logits, ctc_loss
+    from audio8_b200.functional import LogSoftmaxFn
+    g = torch.Generator().manual_seed(0)
+    logits = (torch.randn(3, 30, 16, generator=g)).requires_grad_(True)
+    lp = LogSoftmaxFn.apply(logits)
+    lp.a8_logits = logits
+    assert _fused_logits(lp.transpose(1, 0)) is logits
+    assert _fused_logits(lp.transpose(1, 0)[1:]) is None and _fused_logits(lp.transpose(1, 0).contiguous()) is None
+    assert _fused_logits(lp) is None  # [B,T,V] order is not what the loss takes
+    tg = torch.randint(3, 16, (3, 5), generator=g)
+    tl = torch.full((3,), 5, dtype=torch.long)
+    il = torch.tensor([30, 25, 28])
+    loss = ctc_loss(lp.transpose(1, 0), il, tg, tl)
+    loss.backward()
+    x = logits.detach().clone().requires_grad_(True)
+    ref = ref_ctc.ctc_loss_reference(torch.log_softmax(x, -1).transpose(0, 1), il, tg, tl, 0, 1, 2, "sum")
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert (logits.grad - x.grad).abs().max().item() < 1e-4
+
+
 def _greedy_reference(lp_btv, lengths, blank):
     """the reference's own ops (ctc.py:161-162)"""
     out = []
