@@ -52,8 +52,8 @@ SIGNATURES = {
     "a8_ctc_scratch_floats": (_Z, [_I, _I, _I]),
     "a8_ctc_greedy": (_I, [_P, _L, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P]),
     "a8_ctc_prep": (_I, [_P, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "a8_ctc_forward": (_I, [_P, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "a8_ctc_backward": (_I, [_P, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _L, _I, _I, _P, _L, _L, _P]),
+    "a8_ctc_forward": (_I, [_P, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "a8_ctc_backward": (_I, [_P, _L, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _L, _I, _I, _P, _L, _L, _P]),
 }
 
 _U = C.c_uint64

@@ -1,23 +1,22 @@
-// audio8_b200 — CTC loss for sm_100a, second generation: warp-specialised log2-space alpha sweep and a beta sweep that
-// emits the gradient directly (no beta scratch, no separate gradient pass).
+// audio8_b200 — CTC loss for sm_100a, second generation: warp-specialised log2-space alpha and beta sweeps running
+// CONCURRENTLY in one CTA per utterance, then a gradient kernel that is parallel over (utterance, time).
 //
 // Replaces torch.nn.functional.ctc_loss as called by the reference (audio8/ctc.py:197-205; ATen's
 // ctc_loss_log_alpha / log_beta / collect kernels) and, when the input is the classifier's LOGITS, the log_softmax in
-// front of it as well (audio8/wav2vec2.py:770): the row normalisation is done by the producer warps on the fly and the
-// backward pass returns d loss / d logits = softmax - occupancy, the composition of both backward formulas.
+// front of it as well (audio8/wav2vec2.py:770): rows are normalised on the fly and the backward pass returns
+// d loss / d logits = softmax - occupancy, the composition of both backward formulas.
 //
-// One CTA per utterance:
-//   warps 0..W-1   recursion: lane g (= 32*warp + lane) keeps NS consecutive extended-label states in registers;
-//                  neighbours through two shuffles, across warps through a double-buffered smem slot and ONE named barrier
-//                  per time step (only when W > 1).  log2 domain; the largest of the three terms of every log-sum-exp is
-//                  factored out, so a blank state costs 1 ex2 + 1 lg2 and a label state 2 ex2 + 1 lg2.
-//   warps W, W+1   producers: stream the log-prob / logit rows through a cp.async ring, convert them to log2 units
-//                  (logits: minus the row's log-sum-exp) and publish each row on an mbarrier; they run ahead of the
-//                  recursion by up to RING rows, so global-memory latency never sits on the serial chain.
-//   warp  W+2      (beta sweep only) emitter: per time step turns the per-class occupancy bins the recursion warps
-//                  accumulate in shared memory into one gradient row, (softmax - occupancy / sum) * scale.
-// Scratch: alpha only, fp32 [B, T, Epad]; the beta sweep prefetches its own states of alpha with per-thread cp.async.
-// nll reduction: the last CTA of the alpha sweep to finish (atomic ticket) sums nll[0..B) in a fixed order.
+// Sweep kernel, one CTA per utterance, two symmetric halves (alpha: t ascending, beta: t descending), each with
+//   W recursion warps: lane g (= 32*warp + lane) keeps NS consecutive extended-label states in registers; neighbours
+//                  through two shuffles, across warps through a double-buffered smem slot and ONE named barrier per time
+//                  step (only when W > 1).  log2 domain; the largest term of every log-sum-exp is factored out, so a
+//                  blank state costs 1 ex2 + 1 lg2 and a label state 2 ex2 + 1 lg2.
+//   2 producer warps: stream the log-prob / logit rows through a cp.async ring, convert them to log2 units (logits:
+//                  minus the row's log-sum-exp) and publish each row on an mbarrier; they run ahead of the recursion by up
+//                  to RING rows, so global-memory latency never sits on the serial chain.
+// alpha (emission included) and beta~ (the sum over successors, emission excluded) go to fp32 scratch [B, T, Epad].
+// nll reduction: the last CTA to finish (atomic ticket) sums nll[0..B) in a fixed order.
+// Gradient kernel: a warp per time step; occupancy(s) = 2^(alpha + beta~ - ll), binned per class in shared memory.
 #include "a8_common.cuh"
 #include "../../include/audio8_b200.h"
 
@@ -82,7 +81,8 @@ struct CtcArgs {
   int blank;
   int W;                 // recursion warps per CTA
   int epad;              // 32 * W * NS: row pitch of alpha
-  float* alpha;          // [B, T, epad] log2 domain
+  float* alpha;          // [B, T, epad] log2 domain, emission included
+  float* beta;           // [B, T, epad] log2 domain, emission excluded
   float* nll;            // [B]
   // alpha sweep: reduced loss
   float* loss;
@@ -94,42 +94,38 @@ struct CtcArgs {
   long long gt, gb;
 };
 
-// shared-memory carve-up (floats): ring[RING][Vp] | xch[2][W][2] | bins[2][Vp] | alpha ring (beta sweep) | mbarriers
+// shared-memory carve-up of one sweep direction (floats): ring[RING][Vp] | xch[2][W][2] | mbarriers
 struct Smem {
   float* ring;
   float* xch;
-  float* bins;
-  float* aring;
   uint32_t bars;  // shared-space address of the mbarrier block
 };
 constexpr int BAR_FULL = 0;               // [RING] row converted
-constexpr int BAR_FREE = RING;            // [RING] row consumed by every reader
-constexpr int BAR_BINFULL = 2 * RING;     // [2]
-constexpr int BAR_BINFREE = 2 * RING + 2; // [2]
-constexpr int NBARS = 2 * RING + 4;
+constexpr int BAR_FREE = RING;            // [RING] row consumed by every recursion warp
+constexpr int NBARS = 2 * RING;
 
 __device__ __forceinline__ uint32_t bar_addr(const Smem& s, int i) { return s.bars + 8u * i; }
 
 __host__ __device__ inline int vpad(int V) { return (V + 31) & ~31; }
-__host__ __device__ inline size_t ctc_smem_bytes(int V, int W, int NS, bool beta) {
-  size_t f = (size_t)RING * vpad(V) + 2 * W * 2 + (beta ? 2 * vpad(V) : 0) + (beta ? (size_t)(AHEAD + 1) * 32 * W * NS : 0);
+__host__ __device__ inline size_t ctc_smem_bytes(int V, int W, int NS) {  // one direction
+  size_t f = (size_t)RING * vpad(V) + 2 * W * 2;
+  (void)NS;
   return f * sizeof(float) + NBARS * 8 + 16;
 }
 
-__device__ __forceinline__ Smem carve(float* base, int V, int W, int NS, bool beta) {
+__device__ __forceinline__ Smem carve(float* base, int V, int W, int NS) {
   Smem s;
+  (void)NS;
   s.ring = base;
   s.xch = s.ring + (size_t)RING * vpad(V);
-  s.bins = s.xch + 2 * W * 2;
-  s.aring = s.bins + (beta ? 2 * vpad(V) : 0);
-  float* end = s.aring + (beta ? (size_t)(AHEAD + 1) * 32 * W * NS : 0);
+  float* end = s.xch + 2 * W * 2;
   s.bars = (smem_u32(end) + 7u) & ~7u;
   return s;
 }
 
 // ---- producers: row r of the sweep (time t_of(r)) -> ring[r % RING] in log2 units
 template <bool BACKWARD>
-__device__ __forceinline__ void producer_loop(const CtcArgs& a, const Smem& s, int b, int Tb, int pid, int lane, int readers) {
+__device__ __forceinline__ void producer_loop(const CtcArgs& a, const Smem& s, int b, int Tb, int pid, int lane) {
   const int V = a.V, Vp = vpad(V);
   const float* xb = a.x + (long long)b * a.sb;
   auto t_of = [&](int r) { return BACKWARD ? Tb - 1 - r : r; };
@@ -169,7 +165,6 @@ __device__ __forceinline__ void producer_loop(const CtcArgs& a, const Smem& s, i
     issue(k + DEPTH);
   }
   cp_async_wait<0>();
-  (void)readers;
 }
 
 // per-state class and skip flag of the lane's NS states
@@ -229,80 +224,94 @@ __device__ __forceinline__ void neighbours(const float (&cur)[NS], const Smem& s
     }
   }
 }
+// ================================================================================================ alpha || beta sweeps
+// one direction's recursion warp: BACKWARD = false writes alpha (emission included), true writes beta~ (emission
+// excluded: exactly the factor the occupancy needs next to alpha)
 template <int NS, bool BACKWARD>
-__device__ __forceinline__ void publish(const float (&cur)[NS], const Smem& s, int w, int W, int lane, int par) {
-  if (W == 1) return;
-  if (!BACKWARD) {
-    if (lane == 31) { s.xch[(par * W + w) * 2] = cur[NS - 1]; s.xch[(par * W + w) * 2 + 1] = cur[NS - 2]; }
-  } else {
-    if (lane == 0) { s.xch[(par * W + w) * 2] = cur[0]; s.xch[(par * W + w) * 2 + 1] = cur[1]; }
+__device__ __forceinline__ void recursion_loop(const CtcArgs& a, const Smem& s, int b, int Tb, int E, int w, int lane, int bar_id,
+                                               float* __restrict__ scratch, float (&cur)[NS]) {
+  const int W = a.W;
+  const int g = w * 32 + lane;
+  int cls[NS];
+  bool skp[NS];
+  state_setup<NS, BACKWARD>(a, b, g, E, cls, skp);
+  const int Vp = vpad(a.V);
+  float* out = scratch + (long long)b * a.T * a.epad + (long long)g * NS;
+#pragma unroll 1
+  for (int r = 0; r < Tb; ++r) {
+    float acc[NS];
+    if (r == 0) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const int st = g * NS + i;
+        acc[i] = (BACKWARD ? (st < E && st >= E - 2) : (st <= 1)) ? 0.f : -INFINITY;
+      }
+    } else {
+      float n1, n2;
+      neighbours<NS, BACKWARD>(cur, s, w, W, lane, (r - 1) & 1, n1, n2);
+      recur<NS, BACKWARD>(cur, n1, n2, skp, acc);
+    }
+    mbar_wait(bar_addr(s, BAR_FULL + r % RING), (r / RING) & 1);
+    const float* row = s.ring + (size_t)(r % RING) * Vp;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) cur[i] = (g * NS + i < E) ? row[cls[i]] + acc[i] : -INFINITY;
+    // hand the boundary states to the neighbouring warps first: everything below is off the serial chain
+    if (W > 1) {
+      if (!BACKWARD) {
+        if (lane == 31) { s.xch[((r & 1) * W + w) * 2] = cur[NS - 1]; s.xch[((r & 1) * W + w) * 2 + 1] = cur[NS - 2]; }
+      } else {
+        if (lane == 0) { s.xch[((r & 1) * W + w) * 2] = cur[0]; s.xch[((r & 1) * W + w) * 2 + 1] = cur[1]; }
+      }
+      named_bar(bar_id, 32 * W);
+    } else {
+      __syncwarp();
+    }
+    if (lane == 0) mbar_arrive(bar_addr(s, BAR_FREE + r % RING));  // every lane's row reads precede the barrier / this point
+    const int t = BACKWARD ? Tb - 1 - r : r;
+    float4* dst = reinterpret_cast<float4*>(out + (long long)t * a.epad);
+#pragma unroll
+    for (int i = 0; i < NS / 4; ++i) {
+      if (BACKWARD) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      else dst[i] = make_float4(cur[4 * i], cur[4 * i + 1], cur[4 * i + 2], cur[4 * i + 3]);
+    }
   }
-  named_bar(1, 32 * W);
 }
 
-__device__ __forceinline__ void init_barriers(const CtcArgs& a, const Smem& s, bool beta) {
-  if (threadIdx.x == 0) {
-    const int readers = a.W + (beta ? 1 : 0);
-    for (int i = 0; i < RING; ++i) {
-      mbar_init(bar_addr(s, BAR_FULL + i), 1);
-      mbar_init(bar_addr(s, BAR_FREE + i), readers);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_addr(s, BAR_BINFULL + i), a.W);
-      mbar_init(bar_addr(s, BAR_BINFREE + i), 1);
-    }
-    mbar_fence_init();
-  }
-}
-
-// ================================================================================================ alpha sweep
 template <int NS>
-__global__ void __launch_bounds__(32 * 8) ctc_alpha_kernel(const CtcArgs a) {
+__global__ void __launch_bounds__(32 * 16) ctc_sweep_kernel(const CtcArgs a) {
   extern __shared__ float smem_f[];
   const int b = blockIdx.x;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W = a.W;
-  const Smem s = carve(smem_f, a.V, W, NS, false);
+  const int half_warps = W + NPROD;
+  const int wg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dir = wg / half_warps;       // 0: alpha, 1: beta
+  const int w = wg - dir * half_warps;   // warp within the half
+  const size_t half_floats = (ctc_smem_bytes(a.V, W, NS) + 15) / 16 * 4;
+  const Smem s = carve(smem_f + dir * half_floats, a.V, W, NS);
   const int Tb = min(a.in_len[b], a.T);
   const int S = a.tgt_len[b];
   const int E = 2 * S + 1;
   const bool degenerate = (Tb <= 0) || (E > 32 * W * NS);
-  init_barriers(a, s, false);
+  if (w == 0 && lane == 0) {
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(bar_addr(s, BAR_FULL + i), 1);
+      mbar_init(bar_addr(s, BAR_FREE + i), W);
+    }
+    mbar_fence_init();
+  }
   __syncthreads();
   if (!degenerate) {
     if (w >= W) {
-      producer_loop<false>(a, s, b, Tb, w - W, lane, W);
-    } else {
-      const int g = w * 32 + lane;
-      int cls[NS];
-      bool skp[NS];
-      state_setup<NS, false>(a, b, g, E, cls, skp);
-      const int Vp = vpad(a.V);
+      if (dir == 0) producer_loop<false>(a, s, b, Tb, w - W, lane);
+      else producer_loop<true>(a, s, b, Tb, w - W, lane);
+    } else if (dir == 1) {
       float cur[NS];
-      float* out = a.alpha + (long long)b * a.T * a.epad + (long long)g * NS;
-#pragma unroll 1
-      for (int r = 0; r < Tb; ++r) {
-        float acc[NS];
-        if (r == 0) {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) acc[i] = (g * NS + i <= 1) ? 0.f : -INFINITY;
-        } else {
-          float n1, n2;
-          neighbours<NS, false>(cur, s, w, W, lane, (r - 1) & 1, n1, n2);
-          recur<NS, false>(cur, n1, n2, skp, acc);
-        }
-        mbar_wait(bar_addr(s, BAR_FULL + r % RING), (r / RING) & 1);
-        const float* row = s.ring + (size_t)(r % RING) * Vp;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) cur[i] = (g * NS + i < E) ? row[cls[i]] + acc[i] : -INFINITY;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_addr(s, BAR_FREE + r % RING));
-        float4* dst = reinterpret_cast<float4*>(out + (long long)r * a.epad);
-#pragma unroll
-        for (int i = 0; i < NS / 4; ++i) dst[i] = make_float4(cur[4 * i], cur[4 * i + 1], cur[4 * i + 2], cur[4 * i + 3]);
-        publish<NS, false>(cur, s, w, W, lane, r & 1);
-      }
+      recursion_loop<NS, true>(a, s, b, Tb, E, w, lane, 2, a.beta, cur);
+    } else {
+      float cur[NS];
+      recursion_loop<NS, false>(a, s, b, Tb, E, w, lane, 1, a.alpha, cur);
       // ll = log2-sum of alpha[Tb-1, E-1] and alpha[Tb-1, E-2]: the owners drop them into the exchange slots
+      const int g = w * 32 + lane;
       if (W > 1) named_bar(1, 32 * W);
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(32 * 8) ctc_alpha_kernel(const CtcArgs a) {
       if (s_last) *ticket = 0;
     }
     __syncthreads();
-    if (s_last && w == 0) {
+    if (s_last && wg == 0) {
       __threadfence();
       float acc = 0.f;
       for (int i = lane; i < a.B; i += 32) {
@@ -347,130 +356,79 @@ __global__ void __launch_bounds__(32 * 8) ctc_alpha_kernel(const CtcArgs a) {
   }
 }
 
-// ================================================================================================ beta sweep + gradient
-template <int NS>
-__global__ void __launch_bounds__(32 * 9) ctc_beta_grad_kernel(const CtcArgs a) {
-  extern __shared__ float smem_f[];
-  const int b = blockIdx.x;
+// ================================================================================================ gradient
+constexpr int GRAD_WARPS = 8;
+// grid (ceil(T / (GRAD_WARPS*tpw)), B): each warp handles tpw consecutive time steps of utterance b.
+// The state posteriors are normalised per time step by their own sum (in exact arithmetic that sum equals the utterance
+// likelihood for every t): this cancels the common-mode rounding drift that fp32 log-space alpha / beta of magnitude
+// ~|nll| accumulate over T steps, so each gradient row sums to zero to fp32 precision.
+__global__ void __launch_bounds__(GRAD_WARPS * 32) ctc_grad_kernel(const CtcArgs a, int tpw) {
+  extern __shared__ float smem_f[];  // [GRAD_WARPS][2][Vp] : log2-prob row, bins ; then int ext[epad]
+  const int b = blockIdx.y;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int W = a.W;
   const int V = a.V, Vp = vpad(V);
-  const Smem s = carve(smem_f, V, W, NS, true);
   const int Tb = min(a.in_len[b], a.T);
   const int S = a.tgt_len[b];
   const int E = 2 * S + 1;
-  const float nll = a.nll[b];
-  const bool dead = (Tb <= 0) || (E > 32 * W * NS) || isinf(nll) || isnan(nll);
-  float* gb = a.grad + (long long)b * a.gb;
-  // rows past the utterance (and whole infeasible utterances: zero_infinity semantics; without zero_infinity the
-  // reference's gradient is NaN garbage, zero is returned there as well) are zero
-  {
-    const int t0 = dead ? 0 : Tb;
-    const long long n = (long long)(a.T - t0) * V;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) gb[(t0 + i / V) * a.gt + (i % V)] = 0.f;
-  }
-  if (dead) return;
-  init_barriers(a, s, true);
-  for (int i = threadIdx.x; i < 2 * Vp; i += blockDim.x) s.bins[i] = 0.f;
+  int* ext = reinterpret_cast<int*>(smem_f + (size_t)GRAD_WARPS * 2 * Vp);
+  const int* lab = a.targets + a.tgt_off[b];
+  for (int st = threadIdx.x; st < E && st < a.epad; st += blockDim.x) ext[st] = (st & 1) ? lab[st >> 1] : a.blank;
   __syncthreads();
+  float* row = smem_f + (size_t)w * 2 * Vp;
+  float* bins = row + Vp;
+  const float nll = a.nll[b];
+  const bool dead = isinf(nll) || isnan(nll) || E > a.epad;
   float scale = a.grad_out[(long long)b * a.go_stride];
   if (a.mean) scale /= (float)(max(S, 1) * a.B);
-  const float ll2 = -nll * LOG2E;  // log2 likelihood
-
-  if (w >= W + NPROD) {
-    // ------------------------------------------------------------------------------------ emitter
-#pragma unroll 1
-    for (int r = 0; r < Tb; ++r) {
-      const int par = r & 1;
-      mbar_wait(bar_addr(s, BAR_BINFULL + par), (r >> 1) & 1);
-      const float* row = s.ring + (size_t)(r % RING) * Vp;  // still held: the emitter is one of the row's readers
-      float* bins = s.bins + par * Vp;
-      float tot = 0.f;
-      for (int v = lane; v < Vp; v += 32) tot += bins[v];
-      tot = warp_sum(tot);
-      const float inv = (tot > 0.f) ? 1.f / tot : 0.f;
-      float* gout = gb + (long long)(Tb - 1 - r) * a.gt;
-      for (int v = lane; v < V; v += 32) {
-        gout[v] = (ex2f(row[v]) - bins[v] * inv) * scale;
-        bins[v] = 0.f;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_addr(s, BAR_BINFREE + par));
-        mbar_arrive(bar_addr(s, BAR_FREE + r % RING));
-      }
+  const float ll2 = -nll * LOG2E;
+  const int t0 = (blockIdx.x * GRAD_WARPS + w) * tpw;
+  for (int t = t0; t < min(t0 + tpw, a.T); ++t) {
+    float* gout = a.grad + (long long)t * a.gt + (long long)b * a.gb;
+    if (t >= Tb || dead) {
+      // PyTorch: zero for t >= input_length; an infeasible row (loss +inf) is zeroed by zero_infinity — without
+      // zero_infinity the reference's gradient is NaN garbage, zero is returned there as well
+      for (int c = lane; c < V; c += 32) gout[c] = 0.f;
+      continue;
     }
-  } else if (w >= W) {
-    producer_loop<true>(a, s, b, Tb, w - W, lane, W + 1);
-  } else {
-    // ------------------------------------------------------------------------------------ recursion
-    const int g = w * 32 + lane;
-    int cls[NS];
-    bool skp[NS];
-    state_setup<NS, true>(a, b, g, E, cls, skp);
-    // this lane's NS states of alpha, AHEAD time steps in flight (per-thread cp.async: no cross-thread hand-over)
-    const float* asrc = a.alpha + (long long)b * a.T * a.epad + (long long)g * NS;
-    const uint32_t adst = smem_u32(s.aring + (size_t)g * NS);
-    const uint32_t apitch = (uint32_t)(32 * W * NS) * 4u;
-    auto issue_alpha = [&](int r) {
-      if (r < Tb) {
-        const float* src = asrc + (long long)(Tb - 1 - r) * a.epad;
-        const uint32_t dst = adst + (uint32_t)(r % (AHEAD + 1)) * apitch;
-#pragma unroll
-        for (int i = 0; i < NS / 4; ++i) cp_async16(dst + 16u * i, src + 4 * i);
-      }
-      cp_async_commit();
-    };
-#pragma unroll 1
-    for (int r = 0; r < AHEAD; ++r) issue_alpha(r);
-    float cur[NS];
-#pragma unroll 1
-    for (int r = 0; r < Tb; ++r) {
-      const int par = r & 1;
-      float inner[NS];
-      if (r == 0) {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          const int st = g * NS + i;
-          inner[i] = (st < E && st >= E - 2) ? 0.f : -INFINITY;
-        }
+    const float* xr = a.x + (long long)b * a.sb + (long long)t * a.st;
+    float mx = -INFINITY;
+    for (int c = lane; c < V; c += 32) {
+      const float v = xr[(long long)c * a.sv];
+      row[c] = v;
+      bins[c] = 0.f;
+      mx = fmaxf(mx, v);
+    }
+    float shift = 0.f;
+    if (a.from_logits) {  // log2-softmax of the row
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int c = lane; c < V; c += 32) sum += ex2f((row[c] - mx) * LOG2E);
+      sum = warp_sum(sum);
+      shift = mx * LOG2E + lg2f(sum);
+    }
+    __syncwarp();
+    const float* al = a.alpha + ((long long)b * a.T + t) * a.epad;
+    const float* be = a.beta + ((long long)b * a.T + t) * a.epad;
+    // occupancy of state s: alpha (emission included) * beta~ (emission excluded) / likelihood, renormalised per step
+    float tot = 0.f, blank_sum = 0.f;
+    for (int st = lane; st < E; st += 32) {
+      const float o = al[st] + be[st] - ll2;
+      const float occ = (o > -INFINITY) ? ex2f(o) : 0.f;
+      tot += occ;
+      if (st & 1) {
+        if (occ > 0.f) atomicAdd(&bins[ext[st]], occ);
       } else {
-        float n1, n2;
-        neighbours<NS, true>(cur, s, w, W, lane, (r - 1) & 1, n1, n2);
-        recur<NS, true>(cur, n1, n2, skp, inner);
+        blank_sum += occ;
       }
-      issue_alpha(r + AHEAD);
-      cp_async_wait<AHEAD>();
-      const float* al = s.aring + (size_t)(r % (AHEAD + 1)) * (32 * W * NS) + (size_t)g * NS;
-      mbar_wait(bar_addr(s, BAR_FULL + r % RING), (r / RING) & 1);
-      const float* row = s.ring + (size_t)(r % RING) * Vp;
-      if (r >= 2) mbar_wait(bar_addr(s, BAR_BINFREE + par), ((r >> 1) - 1) & 1);
-      float* bins = s.bins + par * Vp;
-      float blank_sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        const int st = g * NS + i;
-        const bool live = st < E;
-        cur[i] = live ? row[cls[i]] + inner[i] : -INFINITY;
-        // occupancy of state st at this time step: alpha (emission included) * beta without the emission / likelihood
-        const float o = al[i] + inner[i] - ll2;
-        const float occ = (live && o > -INFINITY) ? ex2f(o) : 0.f;
-        if (i & 1) {
-          if (occ > 0.f) atomicAdd(&bins[cls[i]], occ);
-        } else {
-          blank_sum += occ;
-        }
-      }
-      blank_sum = warp_sum(blank_sum);
-      if (lane == 0 && blank_sum > 0.f) atomicAdd(&bins[a.blank], blank_sum);
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_addr(s, BAR_BINFULL + par));
-        mbar_arrive(bar_addr(s, BAR_FREE + r % RING));
-      }
-      publish<NS, true>(cur, s, w, W, lane, par);
     }
-    cp_async_wait<0>();
+    tot = warp_sum(tot);
+    blank_sum = warp_sum(blank_sum);
+    __syncwarp();
+    if (lane == 0) bins[a.blank] += blank_sum;
+    __syncwarp();
+    const float inv = (tot > 0.f) ? 1.f / tot : 0.f;
+    for (int c = lane; c < V; c += 32) gout[c] = (ex2f(fmaf(row[c], LOG2E, -shift)) - bins[c] * inv) * scale;
+    __syncwarp();
   }
 }
 
@@ -500,57 +458,57 @@ extern "C" size_t a8_ctc_scratch_floats(int32_t T, int32_t B, int32_t max_S) {
 extern "C" int a8_ctc_forward(const float* x, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T, int32_t B,
                               int32_t V, int32_t from_logits, const int32_t* targets, const int32_t* tgt_offsets,
                               const int32_t* tgt_lengths, const int32_t* in_lengths, int32_t max_S, int32_t blank,
-                              int32_t reduction_mean, int32_t zero_infinity, float* alpha, float* nll, float* loss,
-                              void* stream_v) {
+                              int32_t reduction_mean, int32_t zero_infinity, float* alpha, float* beta, float* nll,
+                              float* loss, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(T > 0 && B > 0 && V > 0, "ctc: empty problem T=%d B=%d V=%d", T, B, V);
   A8_REQUIRE(blank >= 0 && blank < V, "ctc: blank %d outside [0,%d)", blank, V);
   A8_REQUIRE(max_S >= 0 && max_S <= 511, "ctc: target length %d unsupported (max 511)", max_S);
   int ns;
   const int W = pick_layout(max_S, &ns);
-  const size_t smem = ctc_smem_bytes(V, W, ns, false);
-  A8_REQUIRE(smem <= 200 * 1024, "ctc: vocabulary %d too large for the row ring", V);
+  const size_t half = (ctc_smem_bytes(V, W, ns) + 15) / 16 * 16;
+  const size_t smem = 2 * half;
+  A8_REQUIRE(smem <= 200 * 1024, "ctc: vocabulary %d too large for the row rings", V);
   CtcArgs a{};
   a.x = x; a.st = stride_t; a.sb = stride_b; a.sv = stride_v; a.T = T; a.B = B; a.V = V; a.from_logits = from_logits;
   a.targets = targets; a.tgt_off = tgt_offsets; a.tgt_len = tgt_lengths; a.in_len = in_lengths; a.blank = blank;
-  a.W = W; a.epad = 32 * W * ns; a.alpha = alpha; a.nll = nll; a.loss = loss; a.mean = reduction_mean;
+  a.W = W; a.epad = 32 * W * ns; a.alpha = alpha; a.beta = beta; a.nll = nll; a.loss = loss; a.mean = reduction_mean;
   a.zero_inf = zero_infinity;
-  const int threads = 32 * (W + NPROD);
+  const int threads = 2 * 32 * (W + NPROD);
   if (ns == 4) {
-    if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_alpha_kernel<4><<<B, threads, smem, stream>>>(a);
+    if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_sweep_kernel<4><<<B, threads, smem, stream>>>(a);
   } else {
-    if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_alpha_kernel<8><<<B, threads, smem, stream>>>(a);
+    if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_sweep_kernel<8><<<B, threads, smem, stream>>>(a);
   }
-  return check_launch("ctc_alpha_kernel");
+  return check_launch("ctc_sweep_kernel");
 }
 
 extern "C" int a8_ctc_backward(const float* x, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T, int32_t B,
                                int32_t V, int32_t from_logits, const int32_t* targets, const int32_t* tgt_offsets,
                                const int32_t* tgt_lengths, const int32_t* in_lengths, int32_t max_S, int32_t blank,
-                               const float* alpha, const float* nll, const float* grad_out, int64_t grad_out_stride,
-                               int32_t reduction_mean, int32_t zero_infinity, float* grad, int64_t grad_stride_t,
-                               int64_t grad_stride_b, void* stream_v) {
+                               const float* alpha, const float* beta, const float* nll, const float* grad_out,
+                               int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity, float* grad,
+                               int64_t grad_stride_t, int64_t grad_stride_b, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(T > 0 && B > 0 && V > 0, "ctc: empty problem");
   int ns;
   const int W = pick_layout(max_S, &ns);
-  const size_t smem = ctc_smem_bytes(V, W, ns, true);
-  A8_REQUIRE(smem <= 200 * 1024, "ctc: vocabulary %d too large", V);
   CtcArgs a{};
   a.x = x; a.st = stride_t; a.sb = stride_b; a.sv = stride_v; a.T = T; a.B = B; a.V = V; a.from_logits = from_logits;
   a.targets = targets; a.tgt_off = tgt_offsets; a.tgt_len = tgt_lengths; a.in_len = in_lengths; a.blank = blank;
-  a.W = W; a.epad = 32 * W * ns; a.alpha = const_cast<float*>(alpha); a.nll = const_cast<float*>(nll);
+  a.W = W; a.epad = 32 * W * ns; a.alpha = const_cast<float*>(alpha); a.beta = const_cast<float*>(beta);
+  a.nll = const_cast<float*>(nll);
   a.mean = reduction_mean; a.zero_inf = zero_infinity; a.grad_out = grad_out; a.go_stride = grad_out_stride;
   a.grad = grad; a.gt = grad_stride_t; a.gb = grad_stride_b;
-  const int threads = 32 * (W + NPROD + 1);
-  if (ns == 4) {
-    if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_beta_grad_kernel<4><<<B, threads, smem, stream>>>(a);
-  } else {
-    if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_beta_grad_kernel<8><<<B, threads, smem, stream>>>(a);
-  }
-  return check_launch("ctc_beta_grad_kernel");
+  const size_t smem = (size_t)GRAD_WARPS * 2 * vpad(V) * sizeof(float) + (size_t)a.epad * sizeof(int);
+  A8_REQUIRE(smem <= 200 * 1024, "ctc: vocabulary %d too large", V);
+  // enough CTAs to fill 148 SMs a few times over, at least 1 step per warp
+  int tpw = 1;
+  while ((long long)cdiv(T, GRAD_WARPS * tpw) * B > 148 * 16 && tpw < 16) tpw *= 2;
+  dim3 grid(cdiv(T, GRAD_WARPS * tpw), B);
+  if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_grad_kernel<<<grid, GRAD_WARPS * 32, smem, stream>>>(a, tpw);
+  return check_launch("ctc_grad_kernel");
 }

@@ -286,14 +286,14 @@ class CudaBackend:
         T, B, V = x.shape
         assert x.is_cuda and x.dtype == torch.float32 and il.numel() == B + 1
         n = self.lib.a8_ctc_scratch_floats(T, B, max_S)
-        alpha = torch.empty(n, dtype=torch.float32, device=x.device)
+        ab = torch.empty(2, n, dtype=torch.float32, device=x.device)  # alpha | beta~ scratch
         out = torch.empty(B + 1, dtype=torch.float32, device=x.device)
         nll, loss = out[:B], out[B]
         _lib.check(self.lib.a8_ctc_forward(_ptr(x), x.stride(0), x.stride(1), x.stride(2), T, B, V, int(from_logits),
                                            _ptr(flat), _ptr(off), _ptr(tl), _ptr(il), max_S, blank, int(mean),
-                                           int(zero_inf), _ptr(alpha), _ptr(nll), _ptr(loss), _stream()),
+                                           int(zero_inf), _ptr(ab[0]), _ptr(ab[1]), _ptr(nll), _ptr(loss), _stream()),
                    "a8_ctc_forward")
-        return loss, nll, alpha
+        return loss, nll, ab
 
     def ctc_backward(self, x, flat, off, tl, il, max_S, blank, alpha, nll, grad_out, mean, zero_inf, from_logits=False,
                      batch_major=False):
@@ -307,8 +307,8 @@ class CudaBackend:
         go = grad_out.contiguous().float()
         go_stride = 0 if go.numel() == 1 else 1
         _lib.check(self.lib.a8_ctc_backward(_ptr(x), x.stride(0), x.stride(1), x.stride(2), T, B, V, int(from_logits),
-                                            _ptr(flat), _ptr(off), _ptr(tl), _ptr(il), max_S, blank, _ptr(alpha),
-                                            _ptr(nll), _ptr(go), go_stride, int(mean), int(zero_inf), _ptr(grad),
+                                            _ptr(flat), _ptr(off), _ptr(tl), _ptr(il), max_S, blank, _ptr(alpha[0]),
+                                            _ptr(alpha[1]), _ptr(nll), _ptr(go), go_stride, int(mean), int(zero_inf), _ptr(grad),
                                             grad.stride(0), grad.stride(1), _stream()), "a8_ctc_backward")
         return grad
 

@@ -114,10 +114,11 @@ void a8_gemm_set_trace(void* buf);
  * x: fp32 [T,B,V] with arbitrary element strides (the reference passes a transposed view, `train.py:39`).
  * targets: int32 concatenated labels (ctc.py:193-194 stripping is done by a8_ctc_prep), tgt_offsets[b] = start of
  * utterance b.  in_lengths: B ints followed by ONE int that is zero on entry (a8_ctc_prep writes it).
- * alpha: fp32 scratch of a8_ctc_scratch_floats(T, B, max_S) floats (log2 domain; the only scratch: the beta sweep emits
- * the gradient directly).
- * a8_ctc_forward fills alpha, nll[b] (+inf if infeasible) and, if loss != NULL, the reduced loss: sum_b nll_b, or
- * mean_b(nll_b / max(S_b,1)) when reduction_mean; infinite rows count as 0 when zero_infinity.  One launch.
+ * alpha, beta: fp32 scratch of a8_ctc_scratch_floats(T, B, max_S) floats each (log2 domain; alpha includes the emission
+ * at t, beta holds the sum over successors without it).
+ * a8_ctc_forward runs both sweeps concurrently (one CTA per utterance), fills alpha, beta, nll[b] (+inf if infeasible)
+ * and, if loss != NULL, the reduced loss: sum_b nll_b, or mean_b(nll_b / max(S_b,1)) when reduction_mean; infinite rows
+ * count as 0 when zero_infinity.  One launch.
  * a8_ctc_backward writes grad[t*grad_stride_t + b*grad_stride_b + v] = (exp(logp) - occupancy) * scale_b for t < len,
  * else 0 (PyTorch's convention; with from_logits this IS the gradient w.r.t. the logits), scale_b =
  * grad_out[b*grad_out_stride] (/ (max(S_b,1)*B) when reduction_mean); infeasible rows get 0.  One launch.
@@ -138,11 +139,11 @@ int a8_ctc_prep(const int64_t* targets, int64_t stride_b, int64_t stride_s, int3
 int a8_ctc_forward(const float* x, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T, int32_t B, int32_t V,
                    int32_t from_logits, const int32_t* targets, const int32_t* tgt_offsets, const int32_t* tgt_lengths,
                    const int32_t* in_lengths, int32_t max_S, int32_t blank, int32_t reduction_mean,
-                   int32_t zero_infinity, float* alpha, float* nll, float* loss, void* stream);
+                   int32_t zero_infinity, float* alpha, float* beta, float* nll, float* loss, void* stream);
 int a8_ctc_backward(const float* x, int64_t stride_t, int64_t stride_b, int64_t stride_v, int32_t T, int32_t B, int32_t V,
                     int32_t from_logits, const int32_t* targets, const int32_t* tgt_offsets, const int32_t* tgt_lengths,
-                    const int32_t* in_lengths, int32_t max_S, int32_t blank, const float* alpha, const float* nll,
-                    const float* grad_out, int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity,
+                    const int32_t* in_lengths, int32_t max_S, int32_t blank, const float* alpha, const float* beta,
+                    const float* nll, const float* grad_out, int64_t grad_out_stride, int32_t reduction_mean, int32_t zero_infinity,
                     float* grad, int64_t grad_stride_t, int64_t grad_stride_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

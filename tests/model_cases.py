@@ -434,8 +434,9 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
     np.random.seed(seed)
     lp, fmask = model(x.to(device), pad_mask.to(device))
     out_len = fmask.sum(-1)
-    logits_ours = lp.a8_logits  # the loss works from the logits (fused log_softmax + CTC): its gradient lands there
-    logits_ours.retain_grad()
+    # the loss works from the logits when it can (fused log_softmax + CTC): its gradient then lands there, not on lp
+    logits_ours = getattr(lp, "a8_logits", None)
+    (logits_ours if logits_ours is not None else lp).retain_grad()
     loss = ctc_loss(lp.transpose(1, 0), out_len, targets.to(device), tgt_len, blank=0, pad=1, eos=2)
     loss.backward()
     T, D = lp.shape[1], cfg.get("d_model", 768)
@@ -466,7 +467,10 @@ def run_acoustic_generic(device, cfg, V, B, L, S, seed=4, train=True,
     loss_same.backward()
     assert abs(loss_same.item() - loss2.item()) <= 2e-5 * abs(loss2.item()), (loss_same.item(), loss2.item())
     grad_close(lp_same.grad.cpu(), lp64.grad, "CTC gradient on identical log-probs", cos_min=0.99999, rel_max=2e-3)
-    logits2.backward(logits_ours.grad.detach().float().cpu())
+    if logits_ours is not None:
+        logits2.backward(logits_ours.grad.detach().float().cpu())
+    else:  # e.g. a head width that is not a multiple of 8: the sliced logits are not the contiguous tensor the loss wants
+        lp2.backward(lp.grad.detach().float().cpu())
     got = dict(model.named_parameters())
     bad = []
     for k in check_grads:
