@@ -1,12 +1,12 @@
 // audio8_b200 — CTC loss for sm_100a, second generation: warp-specialised log2-space alpha and beta sweeps running
-// CONCURRENTLY in one CTA per utterance, then a gradient kernel that is parallel over (utterance, time).
+// CONCURRENTLY (one CTA per utterance and direction), then a gradient kernel that is parallel over (utterance, time).
 //
 // Replaces torch.nn.functional.ctc_loss as called by the reference (audio8/ctc.py:197-205; ATen's
 // ctc_loss_log_alpha / log_beta / collect kernels) and, when the input is the classifier's LOGITS, the log_softmax in
 // front of it as well (audio8/wav2vec2.py:770): rows are normalised on the fly and the backward pass returns
 // d loss / d logits = softmax - occupancy, the composition of both backward formulas.
 //
-// Sweep kernel, one CTA per utterance, two symmetric halves (alpha: t ascending, beta: t descending), each with
+// Sweep kernel, one CTA per (utterance, direction) (alpha: t ascending, beta: t descending), each with
 //   W recursion warps: lane g (= 32*warp + lane) keeps NS consecutive extended-label states in registers; neighbours
 //                  through two shuffles, across warps through a double-buffered smem slot and ONE named barrier per time
 //                  step (only when W > 1).  log2 domain; the largest term of every log-sum-exp is factored out, so a
@@ -278,16 +278,16 @@ __device__ __forceinline__ void recursion_loop(const CtcArgs& a, const Smem& s, 
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32 * 16) ctc_sweep_kernel(const CtcArgs a) {
+__global__ void __launch_bounds__(32 * 8) ctc_sweep_kernel(const CtcArgs a) {
   extern __shared__ float smem_f[];
-  const int b = blockIdx.x;
+  // the two directions of an utterance are independent until the gradient: separate CTAs (neighbouring block ids), so a
+  // small batch spreads over twice as many SMs and neither sweep shares its SM's MUFU / issue slots with the other
+  const int b = blockIdx.x >> 1;
+  const int dir = blockIdx.x & 1;        // 0: alpha, 1: beta
   const int W = a.W;
-  const int half_warps = W + NPROD;
-  const int wg = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int dir = wg / half_warps;       // 0: alpha, 1: beta
-  const int w = wg - dir * half_warps;   // warp within the half
-  const size_t half_floats = (ctc_smem_bytes(a.V, W, NS) + 15) / 16 * 4;
-  const Smem s = carve(smem_f + dir * half_floats, a.V, W, NS);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = w;
+  const Smem s = carve(smem_f, a.V, W, NS);
   const int Tb = min(a.in_len[b], a.T);
   const int S = a.tgt_len[b];
   const int E = 2 * S + 1;
@@ -327,11 +327,11 @@ __global__ void __launch_bounds__(32 * 16) ctc_sweep_kernel(const CtcArgs a) {
         a.nll[b] = (ll2 == -INFINITY) ? INFINITY : -ll2 * LN2;
       }
     }
-  } else if (threadIdx.x == 0) {
+  } else if (threadIdx.x == 0 && dir == 0) {
     a.nll[b] = (S == 0 && Tb <= 0) ? 0.f : INFINITY;
   }
-  // ---- reduced loss: the last CTA to finish sums nll in a fixed order (deterministic), and re-arms the ticket
-  if (a.loss != nullptr) {
+  // ---- reduced loss: the last alpha CTA to finish sums nll in a fixed order (deterministic), and re-arms the ticket
+  if (a.loss != nullptr && dir == 0) {
     __syncthreads();
     __shared__ int s_last;
     if (threadIdx.x == 0) {
@@ -466,21 +466,20 @@ extern "C" int a8_ctc_forward(const float* x, int64_t stride_t, int64_t stride_b
   A8_REQUIRE(max_S >= 0 && max_S <= 511, "ctc: target length %d unsupported (max 511)", max_S);
   int ns;
   const int W = pick_layout(max_S, &ns);
-  const size_t half = (ctc_smem_bytes(V, W, ns) + 15) / 16 * 16;
-  const size_t smem = 2 * half;
+  const size_t smem = (ctc_smem_bytes(V, W, ns) + 15) / 16 * 16;
   A8_REQUIRE(smem <= 200 * 1024, "ctc: vocabulary %d too large for the row rings", V);
   CtcArgs a{};
   a.x = x; a.st = stride_t; a.sb = stride_b; a.sv = stride_v; a.T = T; a.B = B; a.V = V; a.from_logits = from_logits;
   a.targets = targets; a.tgt_off = tgt_offsets; a.tgt_len = tgt_lengths; a.in_len = in_lengths; a.blank = blank;
   a.W = W; a.epad = 32 * W * ns; a.alpha = alpha; a.beta = beta; a.nll = nll; a.loss = loss; a.mean = reduction_mean;
   a.zero_inf = zero_infinity;
-  const int threads = 2 * 32 * (W + NPROD);
+  const int threads = 32 * (W + NPROD);
   if (ns == 4) {
     if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_sweep_kernel<4><<<B, threads, smem, stream>>>(a);
+    ctc_sweep_kernel<4><<<2 * B, threads, smem, stream>>>(a);
   } else {
     if (smem > 48 * 1024) A8_CUDA(cudaFuncSetAttribute(ctc_sweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_sweep_kernel<8><<<B, threads, smem, stream>>>(a);
+    ctc_sweep_kernel<8><<<2 * B, threads, smem, stream>>>(a);
   }
   return check_launch("ctc_sweep_kernel");
 }
