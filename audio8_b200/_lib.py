@@ -80,9 +80,9 @@ SIGNATURES.update({
     "a8_mask_apply": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "a8_cast": (_I, [_P, _I, _P, _I, _L, _P]),
     "a8_split3": (_I, [_P, _P, _I, _I, _I, _P]),
-    "a8_vq_fwd": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "a8_vq_bwd": (_I, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "a8_contrastive_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_vq_fwd": (_I, [_P, _P, _F, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_vq_bwd": (_I, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_contrastive_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "a8_cast_multi": (_I, [_P, _I, _P]),
     "a8_conv_pack": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "a8_conv_unpack": (_I, [_P, _I, _I, _I, _P, _P]),
@@ -90,7 +90,7 @@ SIGNATURES.update({
     "a8_posconv_norm_scratch_floats": (_L, [_I, _I, _I]),
     "a8_posconv_pack": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "a8_posconv_wn_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
-    "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "a8_optim_grad_sqnorm": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "a8_optim_adamw": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _D, _D, _D, _D, _D, _D, _D, _I, _P, _P]),
 })

@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float* x, const flo
   }
 }
 
+struct ConArgs;
+__device__ __forceinline__ int rows_valid(const ConArgs& a);
+
 struct ConArgs {
   const float* x;   // [R,C]
   const float* y;   // [R,C]
@@ -38,6 +41,7 @@ struct ConArgs {
   const float* xn;  // [R] clamped norms
   const float* yn;
   int R, C, K;
+  const int* n_valid;  // device scalar: only rows [0, *n_valid) exist (the rest of the R rows is padding); null = all R
   float* cosv;      // [R,K+1]
   float* prob;      // [R,K+1] softmax over candidates
   float* row_loss;  // [R]
@@ -47,12 +51,22 @@ struct ConArgs {
   float* dy;         // [R,C] zeroed, atomics
 };
 
+__device__ __forceinline__ int rows_valid(const ConArgs& a) { return a.n_valid ? min(__ldg(a.n_valid), a.R) : a.R; }
+// backward: the padding rows of dx (dy is zero-filled by the host side) get zeros
+__device__ __forceinline__ void zero_padding_rows(const ConArgs& a, int Rv) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = Rv + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < a.R; i += warps)
+    for (int c = lane; c < a.C; c += 32) a.dx[(long long)i * a.C + c] = 0.f;
+}
+
 __global__ void __launch_bounds__(256) contrastive_fwd_kernel(const ConArgs a) {
+  const int Rv = rows_valid(a);
   extern __shared__ float s_cos[];  // [8 warps][K+1]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   float* cs = s_cos + w * (a.K + 1);
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.R; i += warps) {
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < Rv; i += warps) {
     float xv[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
@@ -90,10 +104,11 @@ __global__ void __launch_bounds__(256) contrastive_fwd_kernel(const ConArgs a) {
 }
 
 // ce = mean_i row_loss;  loss = xe_w * ce + div_w * (n_vars - ppl) / n_vars   (single CTA, deterministic)
-__global__ void __launch_bounds__(1024) contrastive_finalize_kernel(const float* row_loss, int R, const float* ppl,
-                                                                    float n_vars, float xe_w, float div_w,
-                                                                    float* ce, float* loss) {
+__global__ void __launch_bounds__(1024) contrastive_finalize_kernel(const float* row_loss, int R, const int* n_valid,
+                                                                    const float* ppl, float n_vars, float xe_w,
+                                                                    float div_w, float* ce, float* loss) {
   __shared__ float red[32];
+  if (n_valid != nullptr) R = min(R, *n_valid);
   float acc = 0.f;
   for (int i = threadIdx.x; i < R; i += blockDim.x) acc += row_loss[i];
   acc = block_sum(acc, red);
@@ -107,8 +122,10 @@ __global__ void __launch_bounds__(1024) contrastive_finalize_kernel(const float*
 __global__ void __launch_bounds__(256) contrastive_bwd_kernel(const ConArgs a) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  const float scale = (*a.dce) / (float)a.R;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.R; i += warps) {
+  const int Rv = rows_valid(a);
+  zero_padding_rows(a, Rv);
+  const float scale = (*a.dce) / (float)Rv;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < Rv; i += warps) {
     float xh[CPL], dxv[CPL];
     const float inx = 1.f / a.xn[i];
 #pragma unroll
@@ -154,6 +171,7 @@ int con_grid(int R) {
 // chased index -> row -> reduce serially, ~800 clk per candidate).
 template <int NQ>
 __global__ void __launch_bounds__(256) contrastive_fwd_fast_kernel(const ConArgs a) {
+  const int Rv = rows_valid(a);
   extern __shared__ float s_dyn[];  // per warp: [K+1] cos values, [K+1] candidate ids
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -161,7 +179,7 @@ __global__ void __launch_bounds__(256) contrastive_fwd_fast_kernel(const ConArgs
   float* cs = s_dyn + w * 2 * K1p;
   int* cid = reinterpret_cast<int*>(cs + K1p);
   const int sub = lane & 7, grp = lane >> 3;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.R; i += warps) {
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < Rv; i += warps) {
     for (int j = lane; j < K1p; j += 32) cid[j] = (j == 0) ? i : (j < K1 ? __ldg(a.idx + (long long)i * a.K + j - 1) : i);
     float4 xv[NQ];
     const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)i * a.C);
@@ -213,8 +231,10 @@ __global__ void __launch_bounds__(256) contrastive_bwd_fast_kernel(const ConArgs
   float* dc = cs + K1p;
   int* cid = reinterpret_cast<int*>(dc + K1p);
   const int sub = lane & 7, grp = lane >> 3;
-  const float scale = (*a.dce) / (float)a.R;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.R; i += warps) {
+  const int Rv = rows_valid(a);
+  zero_padding_rows(a, Rv);
+  const float scale = (*a.dce) / (float)Rv;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < Rv; i += warps) {
     for (int j = lane; j < K1p; j += 32) {
       const bool ok = j < K1;
       cid[j] = (j == 0 || !ok) ? i : __ldg(a.idx + (long long)i * a.K + j - 1);
@@ -300,7 +320,7 @@ int launch_contrastive_fast(const ConArgs& a, cudaStream_t st) {
 using namespace a8;
 
 extern "C" int a8_contrastive_fwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
-                                  const float* ppl, float n_vars, float xe_w, float div_w, float* xn, float* yn,
+                                  const int32_t* n_valid, const float* ppl, float n_vars, float xe_w, float div_w, float* xn, float* yn,
                                   float* cosv, float* prob, float* row_loss, float* ce, float* loss, void* stream_v) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && (C <= 32 * CPL || C == 768) && K >= 0 && K <= 4095,
@@ -308,7 +328,7 @@ extern "C" int a8_contrastive_fwd(const float* x, const float* y, const int32_t*
   row_norm_kernel<<<con_grid(2 * R), 256, 0, st>>>(x, y, R, C, xn, yn);
   int rc = check_launch("row_norm_kernel");
   if (rc) return rc;
-  ConArgs a{x, y, idx, xn, yn, R, C, K, cosv, prob, row_loss, nullptr, nullptr, nullptr};
+  ConArgs a{x, y, idx, xn, yn, R, C, K, n_valid, cosv, prob, row_loss, nullptr, nullptr, nullptr};
   if (!launch_contrastive_fast<false>(a, st)) {
     // the generic kernel holds 32 * CPL channels per row: wider rows exist only on the fast path
     A8_REQUIRE(C <= 32 * CPL, "contrastive: C=%d needs the vectorised path (16-byte aligned x/y, K <= ~760)", C);
@@ -316,17 +336,17 @@ extern "C" int a8_contrastive_fwd(const float* x, const float* y, const int32_t*
   }
   rc = check_launch("contrastive_fwd_kernel");
   if (rc) return rc;
-  contrastive_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, R, ppl, n_vars, xe_w, div_w, ce, loss);
+  contrastive_finalize_kernel<<<1, 1024, 0, st>>>(row_loss, R, n_valid, ppl, n_vars, xe_w, div_w, ce, loss);
   return check_launch("contrastive_finalize_kernel");
 }
 
 extern "C" int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
-                                  const float* xn, const float* yn, const float* cosv, const float* prob,
+                                  const int32_t* n_valid, const float* xn, const float* yn, const float* cosv, const float* prob,
                                   const float* dce, float* dx, float* dy, void* stream_v) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && C > 0 && (C <= 32 * CPL || C == 768) && K >= 0, "contrastive_bwd: unsupported shape");
   A8_CUDA(cudaMemsetAsync(dy, 0, sizeof(float) * (size_t)R * C, st));
-  ConArgs a{x, y, idx, xn, yn, R, C, K, const_cast<float*>(cosv), const_cast<float*>(prob), nullptr, dce, dx, dy};
+  ConArgs a{x, y, idx, xn, yn, R, C, K, n_valid, const_cast<float*>(cosv), const_cast<float*>(prob), nullptr, dce, dx, dy};
   if (!launch_contrastive_fast<true>(a, st)) {
     A8_REQUIRE(C <= 32 * CPL, "contrastive_bwd: C=%d needs the vectorised path (16-byte aligned tensors, K <= ~500)", C);
     contrastive_bwd_kernel<<<con_grid(R), 256, 0, st>>>(a);

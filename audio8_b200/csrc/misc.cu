@@ -23,13 +23,20 @@ __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
-// gather: dst[i,:] = src[idx[i],:]   scatter: dst[idx[i],:] = src[i,:]   (one warp per row)
+// gather: dst[i,:] = src[idx[i],:]   scatter: dst[idx[i],:] = src[i,:]   (one warp per row).  A negative index marks a
+// padding entry (index lists are padded to their worst-case length so that shapes are static): gather writes a zero
+// row, scatter skips it.
 template <typename TS, typename TD, bool SCATTER>
 __global__ void __launch_bounds__(256) rows_copy_kernel(const TS* src, TD* dst, const int* idx, int n, int C) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
     const long long r = idx[i];
+    if (r < 0) {
+      if (!SCATTER)
+        for (int c = lane; c < C; c += 32) dst[(long long)i * C + c] = from_f<TD>(0.f);
+      continue;
+    }
     const TS* s = src + (SCATTER ? (long long)i : r) * C;
     TD* d = dst + (SCATTER ? r : (long long)i) * C;
     for (int c = lane; c < C; c += 32) d[c] = from_f<TD>(to_f<TS>(s[c]));
@@ -41,6 +48,7 @@ __global__ void __launch_bounds__(256) rows_set_kernel(__nv_bfloat16* x, const i
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    if (idx[i] < 0) continue;  // padding entry
     __nv_bfloat16* d = x + (long long)idx[i] * C;
     for (int c = lane; c < C; c += 32) d[c] = __float2bfloat16(vec[c]);
   }

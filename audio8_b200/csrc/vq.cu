@@ -19,6 +19,7 @@ struct VqArgs {
   float tau;
   const float* vars;   // [G*V, vd]
   int R, G, V, vd;
+  const int* n_valid;  // device scalar: rows [0, *n_valid) of the R rows exist, the rest is padding; null = all
   float* q;            // [R, G*vd]
   __nv_bfloat16* q_bf16;  // nullable
   int* kidx;           // [R*G]
@@ -81,6 +82,8 @@ __device__ __forceinline__ void softmax_row(float (&x)[VPL]) {
   for (int i = 0; i < VPL; ++i) x[i] *= inv;
 }
 
+__device__ __forceinline__ int vq_rows(const VqArgs& a) { return a.n_valid ? min(__ldg(a.n_valid), a.R) : a.R; }
+
 __global__ void __launch_bounds__(256) vq_fwd_kernel(const VqArgs a) {
   extern __shared__ float s_avg[];  // [V]
   for (int v = threadIdx.x; v < a.V; v += blockDim.x) s_avg[v] = 0.f;
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(256) vq_fwd_kernel(const VqArgs a) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int N = a.R * a.G;
+  const int Nv = vq_rows(a) * a.G;  // padding rows still get a (meaningless) code, but stay out of the statistics
   for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
     float zv[VPL], uv[VPL];
     load_row(a, n, lane, zv, uv);
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(256) vq_fwd_kernel(const VqArgs a) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < a.V) atomicAdd(&s_avg[v], zv[i]);
+      if (v < a.V && n < Nv) atomicAdd(&s_avg[v], zv[i]);
     }
     const int r = n / a.G, g = n - r * a.G;
     if (lane == 0) a.kidx[n] = bi;
@@ -132,7 +136,8 @@ __global__ void __launch_bounds__(256) vq_fwd_kernel(const VqArgs a) {
 }
 
 // ppl = exp(-sum_v q_v log(q_v + 1e-7)),  q = avg_sums / N   (wav2vec2.py:565)
-__global__ void vq_ppl_kernel(const float* avg_sums, int V, int N, float* ppl) {
+__global__ void vq_ppl_kernel(const float* avg_sums, int V, int N, const int* n_valid, int G, float* ppl) {
+  if (n_valid != nullptr) N = min(N, *n_valid * G);
   float acc = 0.f;
   for (int v = threadIdx.x; v < V; v += 32) {
     const float q = avg_sums[v] / (float)N;
@@ -144,7 +149,8 @@ __global__ void vq_ppl_kernel(const float* avg_sums, int V, int N, float* ppl) {
 
 __global__ void __launch_bounds__(256) vq_bwd_kernel(const VqArgs a) {
   extern __shared__ float s_dqb[];  // [V] : d loss / d q_bar
-  const int N = a.R * a.G;
+  const int Nall = a.R * a.G;
+  const int N = vq_rows(a) * a.G;
   {
     const float c = (*a.dppl) * (*a.ppl) / (float)N;
     for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
@@ -156,8 +162,13 @@ __global__ void __launch_bounds__(256) vq_bwd_kernel(const VqArgs a) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const float it = 1.f / a.tau;
-  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < Nall; n += warps) {
     const int r = n / a.G, g = n - r * a.G;
+    if (n >= N) {  // padding row: no gradient
+      __nv_bfloat16* dzp = a.dz + ((long long)r * a.G + g) * a.V;
+      for (int v = lane; v < a.V; v += 32) dzp[v] = __float2bfloat16(0.f);
+      continue;
+    }
     float zv[VPL], uv[VPL];
     load_row(a, n, lane, zv, uv);
     softmax_row(zv);  // s
@@ -214,27 +225,27 @@ int vq_grid(int N) {  // one (row, group) per warp when they fit in one wave of 
 using namespace a8;
 
 extern "C" int a8_vq_fwd(const float* z, const float* noise, float tau, const float* vars, int32_t R, int32_t G,
-                         int32_t V, int32_t vd, float* q, void* q_bf16, int32_t* kidx, float* avg_sums, float* ppl,
+                         int32_t V, int32_t vd, const int32_t* n_valid, float* q, void* q_bf16, int32_t* kidx, float* avg_sums, float* ppl,
                          void* stream_v) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && G > 0 && V > 0 && V <= 32 * VPL && vd > 0, "vq: unsupported shape R=%d G=%d V=%d vd=%d", R, G, V, vd);
   A8_REQUIRE(tau > 0.f, "vq: temperature must be positive");
-  VqArgs a{z, noise, tau, vars, R, G, V, vd, q, (__nv_bfloat16*)q_bf16, kidx, avg_sums,
+  VqArgs a{z, noise, tau, vars, R, G, V, vd, n_valid, q, (__nv_bfloat16*)q_bf16, kidx, avg_sums,
            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   A8_CUDA(cudaMemsetAsync(avg_sums, 0, sizeof(float) * V, st));
   vq_fwd_kernel<<<vq_grid(R * G), 256, V * sizeof(float), st>>>(a);
   int rc = check_launch("vq_fwd_kernel");
   if (rc) return rc;
-  vq_ppl_kernel<<<1, 32, 0, st>>>(avg_sums, V, R * G, ppl);
+  vq_ppl_kernel<<<1, 32, 0, st>>>(avg_sums, V, R * G, n_valid, G, ppl);
   return check_launch("vq_ppl_kernel");
 }
 
 extern "C" int a8_vq_bwd(const float* z, const float* noise, float tau, int32_t R, int32_t G, int32_t V, int32_t vd,
-                         const float* a_dot, const float* dq, const int32_t* kidx, const float* avg_sums,
+                         const int32_t* n_valid, const float* a_dot, const float* dq, const int32_t* kidx, const float* avg_sums,
                          const float* ppl, const float* dppl, void* dz, float* dvars, void* stream_v) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   A8_REQUIRE(R > 0 && G > 0 && V > 0 && V <= 32 * VPL && vd > 0, "vq_bwd: unsupported shape");
-  VqArgs a{z, noise, tau, nullptr, R, G, V, vd, nullptr, nullptr, const_cast<int*>(kidx),
+  VqArgs a{z, noise, tau, nullptr, R, G, V, vd, n_valid, nullptr, nullptr, const_cast<int*>(kidx),
            const_cast<float*>(avg_sums), a_dot, dq, ppl, dppl, (__nv_bfloat16*)dz, dvars};
   vq_bwd_kernel<<<vq_grid(R * G), 256, V * sizeof(float), st>>>(a);
   return check_launch("vq_bwd_kernel");

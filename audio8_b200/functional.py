@@ -578,11 +578,14 @@ class EncoderFn(torch.autograd.Function):
 # Gumbel vector quantizer (wav2vec2.py:547-576)
 # =================================================================================================
 class QuantizerFn(torch.autograd.Function):
+    """n_valid: optional int32 device scalar — only the first n_valid of the B*Tm rows exist, the rest is the padding of
+    a worst-case-length (static-shape, CUDA-graph-replayable) row list."""
+
     keep_logits = False  # parity tests: expose the fp32 logits of the last call (GumbelVectorQuantizer.keep_logits)
     last_logits = None
 
     @staticmethod
-    def forward(ctx, y, w, b, vars_, G_, tau, noise):
+    def forward(ctx, y, w, b, vars_, G_, tau, noise, n_valid=None):
         be = _be()
         Bq, Tm, Cin = y.shape
         R = Bq * Tm
@@ -592,10 +595,10 @@ class QuantizerFn(torch.autograd.Function):
         z = _empty((R, w.shape[0]), F32, y, dynamic=True)
         be.gemm(G.linear_fwd(be.split3(y2, False), be.split3(w32, True), z, b.detach(), c_dtype=OUT_F32))
         v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
-        q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_)
+        q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_, n_valid=n_valid)
         # outputs are kept as detached aliases (no ctx <-> output reference cycle)
         ctx.saved = (y2, w32, v2, z, noise, kidx.detach(), avg, ppl.detach(), G_, float(tau), y.shape, vars_.shape,
-                     (ops.grad_key(w), ops.grad_key(b), ops.grad_key(vars_)))
+                     (ops.grad_key(w), ops.grad_key(b), ops.grad_key(vars_)), n_valid)
         ctx.mark_non_differentiable(kidx)
         QuantizerFn.last_logits = z if QuantizerFn.keep_logits else None
         return q.view(Bq, Tm, -1), ppl, kidx
@@ -603,7 +606,7 @@ class QuantizerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, dppl, _dk):
         be = _be()
-        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape, (wkey, bkey, vkey) = _take_saved(ctx)
+        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape, (wkey, bkey, vkey), n_valid = _take_saved(ctx)
         R = y2.shape[0]
         vd = v2.shape[1]
         if dq is None:
@@ -616,13 +619,13 @@ class QuantizerFn(torch.autograd.Function):
             a_dot = _empty((R, v2.shape[0]), F32, y2, dynamic=True)
             be.gemm(G.vq_codebook_dots(_bf16(dq2), _bf16(v2), a_dot, G_))
         dz, dvars = be.vq_bwd(z, noise, tau, G_, vd, a_dot, dq2, kidx, avg, ppl, dppl.contiguous().float(),
-                              dvars_out=_grad_zeros(vkey, tuple(v2.shape), y2))
+                              dvars_out=_grad_zeros(vkey, tuple(v2.shape), y2), n_valid=n_valid)
         db = be.colsum(dz, out=_grad_zeros(bkey, (dz.shape[-1],), y2))
         dw = _grad_zeros(wkey, tuple(w32.shape), y2)
         be.gemm(G.linear_wgrad(dz, _bf16(y2), dw))
         dy = _empty(y2.shape, F32, y2, dynamic=True)
         be.gemm(G.linear_dgrad(dz, _bf16(w32), dy, c_dtype=OUT_F32))
-        return dy.view(yshape), dw, db, dvars.view(vshape), None, None, None
+        return dy.view(yshape), dw, db, dvars.view(vshape), None, None, None, None
 
 
 # =================================================================================================
@@ -630,25 +633,26 @@ class QuantizerFn(torch.autograd.Function):
 # =================================================================================================
 class ContrastiveFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, idx, ppl, n_vars, xe_w, div_w):
+    def forward(ctx, x, y, idx, ppl, n_vars, xe_w, div_w, n_valid=None):
         be = _be()
         x2 = x.detach().reshape(-1, x.shape[-1]).contiguous().float()
         y2 = y.detach().reshape(-1, y.shape[-1]).contiguous().float()
         loss, ce, saved = be.contrastive_fwd(x2, y2, idx, ppl.detach().float() if ppl is not None else None,
-                                             float(n_vars), float(xe_w), float(div_w))
-        ctx.saved = (x2, y2, idx, saved, x.shape, y.shape, float(n_vars), float(xe_w), float(div_w), ppl is not None)
+                                             float(n_vars), float(xe_w), float(div_w), n_valid=n_valid)
+        ctx.saved = (x2, y2, idx, saved, x.shape, y.shape, float(n_vars), float(xe_w), float(div_w), ppl is not None,
+                     n_valid)
         return loss, ce
 
     @staticmethod
     def backward(ctx, dloss, dce_extra):
         be = _be()
-        x2, y2, idx, saved, xs, ys, n_vars, xe_w, div_w, has_ppl = _take_saved(ctx)
+        x2, y2, idx, saved, xs, ys, n_vars, xe_w, div_w, has_ppl, n_valid = _take_saved(ctx)
         dce = dloss * xe_w
         if dce_extra is not None:
             dce = dce + dce_extra
-        dx, dy = be.contrastive_bwd(x2, y2, idx, saved, dce.contiguous().float())
+        dx, dy = be.contrastive_bwd(x2, y2, idx, saved, dce.contiguous().float(), n_valid=n_valid)
         dppl = (-div_w / n_vars) * dloss if has_ppl else None
-        return dx.view(xs), dy.view(ys), None, dppl, None, None, None
+        return dx.view(xs), dy.view(ys), None, dppl, None, None, None, None
 
 
 # =================================================================================================

@@ -598,7 +598,7 @@ class CudaBackend:
         return dv, dg
 
     # ------------------------------------------------------------------ quantizer / contrastive
-    def vq_fwd(self, z, noise, tau, vars2d, G):
+    def vq_fwd(self, z, noise, tau, vars2d, G, n_valid=None):
         R = z.shape[0]
         V = z.shape[1] // G
         vd = vars2d.shape[1]
@@ -608,21 +608,21 @@ class CudaBackend:
         kidx = torch.empty(R * G, dtype=torch.int32, device=dev)
         avg = torch.empty(V, dtype=torch.float32, device=dev)
         ppl = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(self.lib.a8_vq_fwd(_ptr(z), _ptr(noise), tau, _ptr(vars2d), R, G, V, vd, _ptr(q), _ptr(qb), _ptr(kidx),
+        _lib.check(self.lib.a8_vq_fwd(_ptr(z), _ptr(noise), tau, _ptr(vars2d), R, G, V, vd, _ptr(n_valid), _ptr(q), _ptr(qb), _ptr(kidx),
                                       _ptr(avg), _ptr(ppl), _stream()), "a8_vq_fwd")
         return q, qb, kidx, avg, ppl
 
-    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl, dvars_out=None):
+    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl, dvars_out=None, n_valid=None):
         """dvars_out: optional ZEROED fp32 [G*V, vd] destination of the codebook gradient"""
         R = z.shape[0]
         V = z.shape[1] // G
         dz = bucketed_empty((R, G * V), torch.bfloat16, z.device)
         dvars = dvars_out if dvars_out is not None else torch.zeros(G * V, vd, dtype=torch.float32, device=z.device)
-        _lib.check(self.lib.a8_vq_bwd(_ptr(z), _ptr(noise), tau, R, G, V, vd, _ptr(a_dot), _ptr(dq), _ptr(kidx), _ptr(avg),
+        _lib.check(self.lib.a8_vq_bwd(_ptr(z), _ptr(noise), tau, R, G, V, vd, _ptr(n_valid), _ptr(a_dot), _ptr(dq), _ptr(kidx), _ptr(avg),
                                       _ptr(ppl), _ptr(dppl), _ptr(dz), _ptr(dvars), _stream()), "a8_vq_bwd")
         return dz, dvars
 
-    def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w):
+    def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w, n_valid=None):
         R, Cc = x.shape
         K = idx.numel() // R
         dev = x.device
@@ -630,18 +630,18 @@ class CudaBackend:
         xn = torch.empty(2 * R, dtype=torch.float32, device=dev)
         cp = bucketed_empty((2, R, K + 1), torch.float32, dev)
         rl = torch.empty(R + 2, dtype=torch.float32, device=dev)
-        _lib.check(self.lib.a8_contrastive_fwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(ppl), n_vars, xe_w, div_w,
+        _lib.check(self.lib.a8_contrastive_fwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(n_valid), _ptr(ppl), n_vars, xe_w, div_w,
                                                _ptr(xn), _ptr(xn, R), _ptr(cp[0]), _ptr(cp[1]), _ptr(rl), _ptr(rl, R),
                                                _ptr(rl, R + 1), _stream()), "a8_contrastive_fwd")
         return rl[R + 1], rl[R], (xn, cp)
 
-    def contrastive_bwd(self, x, y, idx, saved, dce):
+    def contrastive_bwd(self, x, y, idx, saved, dce, n_valid=None):
         R, Cc = x.shape
         K = idx.numel() // R
         xn, cp = saved
         dx = bucketed_empty(x.shape, x.dtype, x.device)
         dy = bucketed_empty(y.shape, y.dtype, y.device)
-        _lib.check(self.lib.a8_contrastive_bwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(xn), _ptr(xn, R), _ptr(cp[0]),
+        _lib.check(self.lib.a8_contrastive_bwd(_ptr(x), _ptr(y), _ptr(idx), R, Cc, K, _ptr(n_valid), _ptr(xn), _ptr(xn, R), _ptr(cp[0]),
                                                _ptr(cp[1]), _ptr(dce), _ptr(dx), _ptr(dy), _stream()),
                    "a8_contrastive_bwd")
         return dx, dy

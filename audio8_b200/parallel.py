@@ -27,8 +27,13 @@ class GradArena:
     """One persistent fp32 buffer holding every trainable parameter's gradient at a FIXED offset, planned once from the
     module structure (never from the order in which backward happens to reach the layers: with LayerDrop each rank drops
     different layers, and a lazily assigned layout would differ between ranks and corrupt the in-place all-reduce).
-    Layout: [transformer layers: one block per layer, last layer first | everything else]; the first region is complete
-    when the encoder's backward has been enqueued and is reduced under the rest of backward, the second at its end."""
+    Layout: [transformer layers: one block per layer, last layer first | heads, quantizer, positional conv: everything
+    whose backward runs before or inside the encoder's | conv feature encoder, its LayerNorm, input projection, mask
+    embedding].  The first two regions are complete when the gradient w.r.t. the encoder's input exists (the modules build
+    the encoder BEFORE the quantizer branch when an arena is active, so autograd runs that branch first) and are reduced
+    under the conv stack's backward; the last region (5 % of the bytes) is reduced when backward ends."""
+
+    LATE = ("feature_extractor", "layer_norm", "proj_to_input", "mask_emb")  # gradients that complete after the encoder's
 
     def __init__(self, module, device):
         from .wav2vec2 import AudioTransformerEncoder
@@ -41,23 +46,29 @@ class GradArena:
                         continue
                     plan.append((ops.grad_key(flat[0]), sum(p.numel() for p in flat)))
                     covered.update(id(p) for p in flat)
-        self.early = None
-        rest = [(ops.grad_key(p), p.numel()) for p in module.parameters() if p.requires_grad and id(p) not in covered]
+        named = [(k, p) for k, p in module.named_parameters() if p.requires_grad and id(p) not in covered]
+        late = lambda k: any(part in self.LATE for part in k.split("."))
+        mid = [(ops.grad_key(p), p.numel()) for k, p in named if not late(k)]
+        rest = [(ops.grad_key(p), p.numel()) for k, p in named if late(k)]
         self.slots = {}
         off = 0
-        for part in (plan, rest):
+        for part in (plan, mid, rest):
             for key, n in part:
                 off = (off + 63) & ~63  # 256-byte alignment
                 self.slots[key] = (off, n)
                 off += n
-            if self.early is None:
-                self.early = off  # end of the transformer-layer region
+            if part is mid:
+                self.early = off  # end of the region that is complete when the encoder's backward has been enqueued
         self.used = off
         self.buf = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
 
     def take(self, key, numel, zero=True):
         """the block planned for `key` (same storage on every step and every rank), zeroed unless zero=False; None when
         the key has no block or the size differs (the caller allocates normally and the gradient is reduced separately)"""
+        cb = self.__dict__.get("on_first_take")
+        if cb is not None:
+            self.on_first_take = None
+            cb()
         slot = self.slots.get(key)
         if slot is None or slot[1] != numel:
             return None
@@ -102,6 +113,8 @@ class DataParallel(nn.Module):
         fresh = sync and all(p.grad is None for p in self._params)
         if fresh and self._arena is None and self._params:
             self._arena = GradArena(self.module, self._params[0].device)
+        if self._arena is not None:
+            self._arena.on_first_take = None  # armed after forward: a CUDA-graph capture inside forward must not trigger it
         ops.set_grad_arena(self._arena if fresh else None, self._encoder_done if (fresh and self.overlap) else None)
         try:
             out = self.module(*args, **kwargs)
@@ -109,17 +122,26 @@ class DataParallel(nn.Module):
             ops.set_grad_arena(None, None, keep_for_backward=True)
         if sync:
             self._callback_queued = False
+            if fresh and self._arena is not None:
+                self._arena.on_first_take = self._queue_finish  # the first gradient block handed out in backward
             for t in (out if isinstance(out, (tuple, list)) else (out,)):
-                if isinstance(t, torch.Tensor) and t.requires_grad:
-                    t.register_hook(self._queue_callback)
+                # the loss may bypass an output and differentiate a tensor it carries instead (the CTC loss works from the
+                # logits tagged onto the log-probs: wav2vec2.Wav2Vec2AcousticModel.forward): hook both
+                for u in (t, getattr(t, "a8_logits", None)):
+                    if isinstance(u, torch.Tensor) and u.requires_grad:
+                        u.register_hook(self._queue_callback)
         return out
 
     # ------------------------------------------------------------------------------------------------ backward side
     def _queue_callback(self, grad):
+        self._queue_finish()
+        return grad
+
+    def _queue_finish(self):
+        """(inside backward) make sure `_finish` runs when this backward pass ends"""
         if not self._callback_queued:
             self._callback_queued = True
             torch.autograd.Variable._execution_engine.queue_callback(self._finish)
-        return grad
 
     def _all_reduce(self, t, async_op):
         if dist.get_backend(self.pg) == "nccl":

@@ -160,6 +160,10 @@ _DRAW_THREAD = __import__("os").environ.get("A8_HOST_DRAWS_THREAD", "1") != "0"
 _ENCODER_LAST = __import__("os").environ.get("A8_ENCODER_LAST", "1") != "0"
 
 
+def _rng_state_equal(a, b):
+    return b is not None and a[0] == b[0] and a[2] == b[2] and a[3] == b[3] and a[4] == b[4] and np.array_equal(a[1], b[1])
+
+
 class _HostDraws:
     """All numpy-RNG draws of one pre-training step, made on a helper thread in the reference's order — span mask
     (wav2vec2.py:189-216), one draw per transformer layer (eight_mile's LayerDrop test), negative indices
@@ -168,10 +172,38 @@ class _HostDraws:
     The draws are the same calls on the same global generator in the same order: results stay bit-identical to the
     reference's as long as nothing else draws from np.random during the step (nothing in this package does)."""
 
+    prefetch = False   # set by the trainer / bench: draw the NEXT step's numbers while the GPU runs the current step
+    _pending = None    # the prefetched draws, if any
+
+    @classmethod
+    def get(cls, B, T, p_start, mask_length, n_layers, sampler):
+        """the draws of the step that starts now.  With `prefetch` they were usually made during the previous step; they
+        are used only if they are what the reference would draw now: same shapes AND numpy's global generator is in
+        exactly the state the prefetch left it in (nobody reseeded it or drew from it since).  Otherwise the generator
+        is put back where the prefetch found it (shape change) or left alone (somebody else touched it) and the
+        numbers are drawn afresh — bit-identical to the reference either way."""
+        pend, cls._pending = cls._pending, None
+        if pend is not None:
+            pend.ev_neg.wait()
+            untouched = _rng_state_equal(np.random.get_state(), pend.state_after)
+            if untouched and pend.error is None and pend.args[:5] == (B, T, p_start, mask_length, n_layers) and \
+                    pend.args[5].n_negatives == sampler.n_negatives:
+                return pend
+            if untouched:
+                np.random.set_state(pend.state_before)
+        return cls(B, T, p_start, mask_length, n_layers, sampler)
+
+    def consumed(self):
+        """the step has taken its negatives: with `prefetch`, start drawing for the next step (same shapes assumed)"""
+        if _HostDraws.prefetch and _DRAW_THREAD and _HostDraws._pending is None:
+            _HostDraws._pending = _HostDraws(*self.args)
+
     def __init__(self, B, T, p_start, mask_length, n_layers, sampler=None):
         import threading
         self.args = (B, T, p_start, mask_length, n_layers, sampler)
         self.mask = self.layer_draws = self.neg = self.error = None
+        self.state_before = np.random.get_state()
+        self.state_after = None
         self.ev_mask, self.ev_neg = threading.Event(), threading.Event()
         if _DRAW_THREAD:
             self.thread = threading.Thread(target=self._run, daemon=True)
@@ -192,6 +224,7 @@ class _HostDraws:
                 self.neg = sampler.indices32(B, int(self.mask[0].sum()))
         except BaseException as e:
             self.error = e
+        self.state_after = np.random.get_state()
         self.ev_neg.set()
 
     def time_mask(self):
@@ -205,6 +238,16 @@ class _HostDraws:
         if self.error is not None:
             raise self.error
         return self.neg
+
+def set_prefetch_draws(flag):
+    """Trainer-level switch: make the numpy draws of step i+1 (span mask, LayerDrop, negatives) on the helper thread while
+    the GPU runs step i, instead of at the start of step i+1.  The numbers are the ones the reference would draw (same
+    calls, same order, same global generator) provided nothing else draws from `np.random` between two steps; a reseed
+    or a shape change between steps is detected and handled exactly (see _HostDraws.get)."""
+    _HostDraws.prefetch = bool(flag)
+    if not flag:
+        _HostDraws._pending = None
+
 
 # --------------------------------------------------------------------------------------------------
 # small modules with reference-identical parameter names
@@ -307,18 +350,25 @@ class GumbelVectorQuantizer(nn.Module):
     def set_num_updates(self, num_updates):
         self.curr_temperature = max(self.max_temperature * self.temperature_decay ** num_updates, self.min_temperature)
 
-    def forward(self, x):
+    def forward(self, x, n_valid=None, _params=None):
+        """x [B, Tm, C].  n_valid (int32 device scalar, optional): only the first n_valid of the B*Tm rows exist (the
+        rest pads a worst-case-length row list).  _params: (weight, bias, vars) aliases when run inside a CUDA-graph
+        capture (graphs.py hands the segment functional copies of the parameters)."""
         B, T, _ = x.shape
+        w, b, v = _params if _params is not None else (self.weight_proj.weight, self.weight_proj.bias, self.vars)
         noise = None
         if self.training:
             noise = self.noise_override
             if noise is None:  # what F.gumbel_softmax draws (wav2vec2.py:557)
                 n = B * T * self.num_groups
                 noise = Fn.ops.bucketed_empty((n, self.num_vars), F32, x.device).exponential_().log_().neg_()
-            noise = noise.to(device=x.device, dtype=F32).contiguous()
+            else:
+                noise = noise.to(device=x.device, dtype=F32).contiguous()
+                n = B * T * self.num_groups
+                if noise.shape[0] < n:  # parity tests supply noise for the valid rows only: pad rows are never read
+                    noise = torch.cat([noise, noise.new_zeros(n - noise.shape[0], noise.shape[1])])
         Fn.QuantizerFn.keep_logits = self.keep_logits
-        q, ppl, kidx = Fn.QuantizerFn.apply(x, self.weight_proj.weight, self.weight_proj.bias, self.vars,
-                                            self.num_groups, self.curr_temperature, noise)
+        q, ppl, kidx = Fn.QuantizerFn.apply(x, w, b, v, self.num_groups, self.curr_temperature, noise, n_valid)
         self.last_indices = kidx
         if self.keep_logits:
             self.last_logits = Fn.QuantizerFn.last_logits.detach().clone()
@@ -569,25 +619,40 @@ class Wav2Vec2Model(nn.Module):
         self.timestep_mask_len = timestep_mask_len
         self.channel_mask_len = channel_mask_len
         self.mask_emb = nn.Parameter(torch.FloatTensor(d_model).uniform_())
-        self._front_graph = GraphedSegment("conv feature encoder + LayerNorm + input projection")
+        self._front_graph = GraphedSegment("conv feature encoder + LayerNorm + input projection + time mask")
+        self._branch_graph = GraphedSegment("quantizer branch (gather, Gumbel VQ, project_q)")
 
     def _front_params(self):
         fe = self.feature_extractor
         gn = fe.conv_layers[0][2]
         return (gn.weight, gn.bias, *[layer[0].weight for layer in fe.conv_layers], self.layer_norm.weight,
-                self.layer_norm.bias, self.proj_to_input.layer.weight, self.proj_to_input.layer.bias)
+                self.layer_norm.bias, self.proj_to_input.layer.weight, self.proj_to_input.layer.bias, self.mask_emb)
 
-    def _front(self, x, gn_w, gn_b, *rest):
-        """audio -> (projected, dropped-out features bf16 [B,T,D], un-projected LayerNorm output fp32 [B,T,512]);
-        reference :929-935.  Functional in the parameters (order of `_front_params`) so that a CUDA-graph capture can
-        run it on aliases of them (graphs.py)."""
+    def _branch_params(self):
+        q = self.quantizer
+        return (q.weight_proj.weight, q.weight_proj.bias, q.vars, self.project_q.layer.weight, self.project_q.layer.bias)
+
+    def _front(self, x, rows, gn_w, gn_b, *rest):
+        """audio -> (projected, dropped-out features with the mask embedding at the masked frames, bf16 [B,T,D];
+        un-projected LayerNorm output fp32 [B,T,512]); reference :929-939.  Functional in the parameters (order of
+        `_front_params`) so that a CUDA-graph capture can run it on aliases of them (graphs.py)."""
         n = len(self.feature_extractor.spec)
-        conv_w, (ln_w, ln_b, pw, pb) = rest[:n], rest[n:]
+        conv_w, (ln_w, ln_b, pw, pb, mask_emb) = rest[:n], rest[n:]
         fx = Fn.ConvFeatureFn.apply(x, self.feature_extractor.spec, gn_w, gn_b, *conv_w)
         features, unmasked = Fn.layer_norm(fx, ln_w, ln_b, 1e-5, want_f32=True)
         features = Fn.linear(features, pw, pb)
         features = Fn.dropout(features, self.dropout_input_p, self.training)
+        features = Fn.RowsSetFn.apply(features, rows[:-1], mask_emb)
         return features, unmasked
+
+    def _branch(self, unmasked, rows, wq, bq, vars_, pw, pb):
+        """quantizer branch (reference :946-950): masked frames of the un-projected features -> dropout -> Gumbel VQ ->
+        project_q.  Works on the padded row list (rows[:-1], -1 = padding; rows[-1] = number of real rows)."""
+        B, _, C = unmasked.shape
+        y = Fn.RowsGatherFn.apply(unmasked, rows[:-1]).view(B, -1, C)
+        y = Fn.dropout(y, self.dropout_features_p, self.training)
+        q, vq_probs = self.quantizer(y, n_valid=rows[-1:], _params=(wq, bq, vars_))
+        return Fn.linear(q, pw, pb, out_f32=True), vq_probs
 
     def set_num_updates(self, s):
         self.quantizer.set_num_updates(s)
@@ -598,48 +663,64 @@ class Wav2Vec2Model(nn.Module):
         the first GPU work of the step has been enqueued, and leaves the handle in `self._host_draws`"""
         self._host_draw_request = sampler
 
+    def max_masked_rows(self, B, T):
+        """worst-case number of masked frames of a batch: every span of every row lands without overlap"""
+        n_spans = int(self.timestep_masking * T / float(self.timestep_mask_len)) + 1
+        return B * min(T, n_spans * self.timestep_mask_len)
+
     def forward(self, x):
         sampler = self.__dict__.pop("_host_draw_request", None)
         self._host_draws = draws = None
-        features, unmasked = self._front_graph.run(self._front, (x,), self._front_params(),
-                                                   extra=(self.training, self.dropout_input_p, Fn.ops.grad_arena_active()))
-        if sampler is not None:
-            self._host_draws = draws = _HostDraws(x.shape[0], unmasked.shape[1], self.timestep_masking,
-                                                  self.timestep_mask_len, len(self.encoder.transformer.encoders), sampler)
-        B, T, C = unmasked.shape
-        # masking runs in eval mode too (reference :937 has no training guard)
-        layer_draws = None
-        if draws is not None:
-            time_mask, layer_draws = draws.time_mask()
-            assert time_mask.shape == (B, T)
-        else:
-            time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
-        rows = _mask_rows(time_mask, x.device)
-        # masked-row tensors are allocated at their worst-case size for this (B, T): see ops.set_dynamic_rows
-        n_spans = int(self.timestep_masking * T / float(self.timestep_mask_len)) + 1
-        Fn.ops.set_dynamic_rows(rows.numel(), B * min(T, n_spans * self.timestep_mask_len))
-        features = Fn.RowsSetFn.apply(features, rows, self.mask_emb)
+        B = x.shape[0]
+        T = conv_out_length(x.shape[1], self.feature_extractor.spec)
         if self.channel_masking > 0.0:
             raise NotImplementedError("channel masking in pre-training is broken in the reference (wav2vec2.py:943)")
-        if _ENCODER_LAST:
+        # ---- the step's numpy draws (mask, LayerDrop, negatives) in the reference's order; they depend on shapes only, so
+        # they are made BEFORE any GPU work (prefetched during the previous step when the caller allows it: _HostDraws)
+        layer_draws = None
+        if sampler is not None:
+            self._host_draws = draws = _HostDraws.get(B, T, self.timestep_masking, self.timestep_mask_len,
+                                                      len(self.encoder.transformer.encoders), sampler)
+            time_mask, layer_draws = draws.time_mask()
+        else:
+            time_mask = create_mask((B, T), p_start=self.timestep_masking, mask_length=self.timestep_mask_len)
+        # masked rows as a worst-case-length list (static shapes: every segment below replays as a CUDA graph):
+        # [flat row indices, -1 padding ..., number of real rows]
+        idx = np.flatnonzero(time_mask.reshape(-1)).astype(np.int32)
+        R_max = max(self.max_masked_rows(B, T), idx.size)
+        buf = np.full(R_max + 1, -1, dtype=np.int32)
+        buf[:idx.size] = idx
+        buf[R_max] = idx.size
+        rows = _to_device(buf, x.device)
+        Fn.ops.set_dynamic_rows(R_max, R_max)
+        eager = self.quantizer.noise_override is not None or self.quantizer.keep_logits  # parity-test hooks: no replay
+        arena = Fn.ops.grad_arena_active()
+        features, unmasked = self._front_graph.run(self._front, (x, rows), self._front_params(),
+                                                   extra=(self.training, self.dropout_input_p, arena))
+        branch = lambda: (self._branch(unmasked, rows, *self._branch_params()) if eager else
+                          self._branch_graph.run(self._branch, (unmasked, rows), self._branch_params(),
+                                                 extra=(self.training, self.dropout_features_p, arena,
+                                                        self.quantizer.curr_temperature)))
+        if _ENCODER_LAST and not arena:
             # The quantizer branch is built BEFORE the encoder: autograd runs ready nodes in reverse creation order, so in
-            # backward the encoder's (long, graph-replayed) backward is enqueued right after final_proj's and the host
-            # works through the quantizer branch's backward while the GPU is busy.  Costs ~0.3 ms of forward latency
-            # (the encoder launch moves behind ~0.5 ms of host work) for ~0.65 ms of backward latency.
-            y = Fn.RowsGatherFn.apply(unmasked, rows).view(B, -1, C)
-            y = Fn.dropout(y, self.dropout_features_p, self.training)
-            q, vq_probs = self.quantizer(y)
-            y = self.project_q(q, out_f32=True)
+            # backward the encoder's (long, graph-replayed) backward is enqueued right after final_proj's.
+            y_pad, vq_probs = branch()
             enc = self.encoder.extract_features(features, None, layer_draws, _internal=True)
-        else:  # the encoder (the longest stretch of GPU work) first; the quantizer branch follows it on the stream
+        else:  # the encoder first.  Under the data-parallel wrapper this is the order that lets autograd finish the
+            # quantizer branch's backward BEFORE the encoder's, so its gradients join the early all-reduce (parallel.py)
             enc = self.encoder.extract_features(features, None, layer_draws, _internal=True)
-            y = Fn.RowsGatherFn.apply(unmasked, rows).view(B, -1, C)
-            y = Fn.dropout(y, self.dropout_features_p, self.training)
-            q, vq_probs = self.quantizer(y)
-            y = self.project_q(q, out_f32=True)
+            y_pad, vq_probs = branch()
         xo = self.final_proj(enc, out_f32=True)
+        qz = self.quantizer  # inspection hooks: the real rows only
+        if qz.last_indices is not None and qz.last_indices.numel() == R_max * qz.num_groups:
+            qz.last_indices = qz.last_indices[:idx.size * qz.num_groups]
+        if qz.last_logits is not None and qz.last_logits.shape[0] == R_max:
+            qz.last_logits = qz.last_logits[:idx.size]
         mask_t = _to_device(time_mask, x.device)
-        mask_t.a8_rows = rows
+        mask_t.a8_rows = rows       # padded row list + count: the loss needs no nonzero / host sync
+        mask_t.a8_ypad = y_pad      # the padded latents the loss kernels work on (gradients flow into this tensor)
+        Tm = idx.size // B
+        y = y_pad.view(-1, y_pad.shape[-1])[:idx.size].view(B, Tm, -1)
         return xo, y, vq_probs, mask_t
 
 
@@ -665,16 +746,35 @@ class Wav2Vec2Loss(nn.Module):
                 draws = inner.__dict__.pop("_host_draws", None)
         B, Tm, C = latents.shape
         rows = getattr(time_mask, "a8_rows", None)
-        if rows is None:
-            rows = torch.nonzero(time_mask.reshape(-1)).reshape(-1).int()
-        xm = Fn.RowsGatherFn.apply(outputs, rows)  # outputs[time_mask] -> [B*Tm, C]
+        y_pad = getattr(time_mask, "a8_ypad", None)
+        if rows is None or y_pad is None:  # a model that is not ours: plain (dynamic-shape) path
+            rows = torch.cat([torch.nonzero(time_mask.reshape(-1)).reshape(-1).int(),
+                              torch.tensor([B * Tm], dtype=torch.int32, device=outputs.device)])
+            y_pad = latents.reshape(B * Tm, C)
+        R_max = rows.numel() - 1
         # numpy draws, bit-exact with the reference's Sampler (already made on the helper thread when `draws`)
         neg = draws.negatives() if draws is not None else self.sample.indices32(B, Tm)
         assert neg.shape == (B, self.sample.n_negatives * Tm)
         self.last_neg_idx = neg
-        idx = _to_device(neg, outputs.device)
-        loss, _ = Fn.ContrastiveFn.apply(xm, latents.reshape(B * Tm, C), idx, gs_probs, self.n_vars, XE_WGT,
-                                         DIVERSITY_WGT)
+        K = self.sample.n_negatives
+        if R_max > B * Tm:  # pad to the static length (the kernels never read the padding rows' candidates)
+            pad = np.zeros(R_max * K, dtype=np.int32)
+            pad[:neg.size] = neg.reshape(-1)
+            neg = pad
+        idx = _to_device(neg.reshape(-1), outputs.device)
+        if draws is not None:
+            draws.consumed()
+        y2 = y_pad.reshape(R_max, C)
+        graph = self.__dict__.setdefault("_graph", GraphedSegment("contrastive loss (gather, cosine logits, CE)"))
+        if gs_probs.requires_grad and outputs.requires_grad:
+            loss = graph.run(self._loss, (outputs, y2, gs_probs, rows, idx), (), extra=(self.n_vars, K))
+        else:
+            loss = self._loss(outputs, y2, gs_probs, rows, idx)
+        return loss
+
+    def _loss(self, outputs, y2, gs_probs, rows, idx):
+        xm = Fn.RowsGatherFn.apply(outputs, rows[:-1])  # outputs[time_mask] -> [R_max, C], zero rows for the padding
+        loss, _ = Fn.ContrastiveFn.apply(xm, y2, idx, gs_probs, self.n_vars, XE_WGT, DIVERSITY_WGT, rows[-1:])
         return loss
 
 

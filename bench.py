@@ -357,6 +357,7 @@ def _run_ours(args):
         crit = CTCLoss()
     else:  # the headline: wav2vec2-base defaults, 12L d=768, dropout 0.1, G=2 V=320 (BASELINE configs[1]; large = configs[3])
         model = W.create_model(**mkw).to(dev)
+        W.set_prefetch_draws(True)  # next step's numpy draws (same numbers, same order) while the GPU runs this step
     model.train()
     loss_fn = W.create_loss(N_VARS, N_NEG)
     net = model
@@ -601,7 +602,8 @@ def _run_ours(args):
             "config": bench_config(args, world, {
                 "data_parallel": dp_name,
                 "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                "launch": "conv/encoder segments replayed as CUDA graphs (fwd and bwd), the rest eager",
+                "launch": "the step is 4 CUDA-graph segments (front+mask, quantizer branch, encoder, loss), fwd and bwd; "
+                          "masked-row lists padded to their worst-case length; host draws prefetched one step ahead",
                 "gc": "gc.freeze() after warm-up (full collections no longer walk the long-lived heap)"}),
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "last_loss": loss_val},

@@ -231,7 +231,9 @@ int a8_conv0_bwd(const float* x, int32_t B, int64_t L, const float* w, const flo
  * dtype codes: 0 = fp32, 1 = bf16.
  * ---------------------------------------------------------------------------------------------- */
 int a8_rows_copy(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, const int32_t* idx, int32_t n,
-                 int32_t C, int32_t scatter, void* stream); /* gather dst[i]=src[idx[i]] / scatter dst[idx[i]]=src[i] */
+                 int32_t C, int32_t scatter, void* stream); /* gather dst[i]=src[idx[i]] / scatter dst[idx[i]]=src[i];
+                                                               idx[i] < 0 = padding entry: zero row / skipped (also in
+                                                               a8_rows_set / a8_rows_set_bwd) */
 int a8_rows_set(void* x, const int32_t* idx, int32_t n, int32_t C, const float* vec, void* stream);
 int a8_rows_set_bwd(void* dx, const int32_t* idx, int32_t n, int32_t C, float* dvec, void* stream);
 int a8_mask_apply(void* x, const uint8_t* row_keep, const uint8_t* chan_zero, int32_t B, int32_t T, int32_t C,
@@ -247,10 +249,14 @@ int a8_split3(const float* src, void* dst, int32_t R, int32_t C, int32_t b_side,
  * copy), avg_sums[V] = sum of softmax(z) rows pooled over groups, ppl = exp(-sum q log(q+1e-7)).
  * bwd: a_dot fp32 [R,G*V] = dq . vars^T per group (from a8_gemm); writes dz bf16 [R,G*V]; dvars ACCUMULATED.
  * ---------------------------------------------------------------------------------------------- */
+/* n_valid (device int32 scalar, may be NULL = all rows): the row lists of a step are padded to their worst-case length R
+ * so that every shape is static (CUDA-graph replay); only rows [0, *n_valid) exist.  Padding rows get a code / zero
+ * gradient but stay out of the pooled statistics (fwd) and contribute nothing (bwd). */
 int a8_vq_fwd(const float* z, const float* noise, float tau, const float* vars, int32_t R, int32_t G, int32_t V,
-              int32_t vd, float* q, void* q_bf16, int32_t* kidx, float* avg_sums, float* ppl, void* stream);
+              int32_t vd, const int32_t* n_valid, float* q, void* q_bf16, int32_t* kidx, float* avg_sums, float* ppl,
+              void* stream);
 int a8_vq_bwd(const float* z, const float* noise, float tau, int32_t R, int32_t G, int32_t V, int32_t vd,
-              const float* a_dot, const float* dq, const int32_t* kidx, const float* avg_sums, const float* ppl,
+              const int32_t* n_valid, const float* a_dot, const float* dq, const int32_t* kidx, const float* avg_sums, const float* ppl,
               const float* dppl, void* dz, float* dvars, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -260,12 +266,13 @@ int a8_vq_bwd(const float* z, const float* noise, float tau, int32_t R, int32_t 
  * ce = mean_i CE(logits_i, 0), loss = xe_w*ce + div_w*(n_vars - *ppl)/n_vars (ppl may be NULL).
  * Scratch kept for backward: xn, yn [R]; cosv, prob [R,K+1]; row_loss [R].
  * bwd: dce = d loss / d ce (device scalar) -> dx [R,C], dy [R,C].
+ * n_valid (device int32 scalar or NULL): rows [*n_valid, R) are padding - excluded from the mean, zero gradient.
  * ---------------------------------------------------------------------------------------------- */
 int a8_contrastive_fwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
-                       const float* ppl, float n_vars, float xe_w, float div_w, float* xn, float* yn, float* cosv,
+                       const int32_t* n_valid, const float* ppl, float n_vars, float xe_w, float div_w, float* xn, float* yn, float* cosv,
                        float* prob, float* row_loss, float* ce, float* loss, void* stream);
 int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32_t R, int32_t C, int32_t K,
-                       const float* xn, const float* yn, const float* cosv, const float* prob, const float* dce,
+                       const int32_t* n_valid, const float* xn, const float* yn, const float* cosv, const float* prob, const float* dce,
                        float* dx, float* dy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -320,20 +320,26 @@ class EmuOps(EmuBackend):
         return dw, dgamma, dbeta
 
     # ---- masks / indices / casts
+    # a negative index is a padding entry of a worst-case-length index list: gather -> zero row, others skip it
     def rows_gather(self, src, idx, out_dtype):
-        return src[idx.long()].to(out_dtype)
+        ok = idx >= 0
+        out = src[idx.clamp_min(0).long()].to(out_dtype)
+        out[~ok] = 0
+        return out
 
     def rows_scatter(self, src, idx, n_rows, out_dtype):
         out = torch.zeros(n_rows, src.shape[-1], dtype=out_dtype)
-        out[idx.long()] = src.to(out_dtype)
+        ok = idx >= 0
+        out[idx[ok].long()] = src[ok].to(out_dtype)
         return out
 
     def rows_set(self, x, idx, vec):
-        x[idx.long()] = vec.to(x.dtype)
+        x[idx[idx >= 0].long()] = vec.to(x.dtype)
 
     def rows_set_bwd(self, dx, idx, out=None):
-        dvec = dx[idx.long()].float().sum(0)
-        dx[idx.long()] = 0
+        ii = idx[idx >= 0].long()
+        dvec = dx[ii].float().sum(0)
+        dx[ii] = 0
         return _into(out, dvec)
 
     def mask_apply(self, x, row_keep=None, chan_zero=None):
@@ -352,21 +358,29 @@ class EmuOps(EmuBackend):
         return torch.cat([hi, lo, hi] if b_side else [hi, hi, lo], 1).contiguous()
 
     # ---- quantizer / contrastive
-    def vq_fwd(self, z, noise, tau, vars2d, G):
+    def vq_fwd(self, z, noise, tau, vars2d, G, n_valid=None):
         R = z.shape[0]
         V = z.shape[1] // G
         zz = z.reshape(R * G, V)
         u = (zz + noise) / tau if noise is not None else zz
         kidx = u.argmax(-1)
-        avg = torch.softmax(zz, -1).sum(0)
-        qbar = avg / (R * G)
+        Rv = R if n_valid is None else min(int(n_valid), R)  # rows beyond are padding: out of the statistics
+        avg = torch.softmax(zz[:Rv * G], -1).sum(0)
+        qbar = avg / (Rv * G)
         ppl = torch.exp(-(qbar * torch.log(qbar + 1e-7)).sum())
         g = torch.arange(R * G) % G
         q = vars2d[g * V + kidx].reshape(R, -1)
         return q, _bf(q), kidx.int(), avg, ppl
 
-    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl, dvars_out=None):
-        R = z.shape[0]
+    def vq_bwd(self, z, noise, tau, G, vd, a_dot, dq, kidx, avg, ppl, dppl, dvars_out=None, n_valid=None):
+        Rall = z.shape[0]
+        R = Rall if n_valid is None else min(int(n_valid), Rall)
+        if R < Rall:  # padding rows: zero gradient, no codebook contribution
+            dzv, dvars = self.vq_bwd(z[:R], noise[:R * G] if noise is not None else None, tau, G, vd,
+                                     a_dot[:R] if a_dot is not None else None, dq[:R], kidx[:R * G], avg, ppl, dppl, dvars_out)
+            dz = torch.zeros(Rall, z.shape[1], dtype=dzv.dtype)
+            dz[:R] = dzv
+            return dz, dvars
         V = z.shape[1] // G
         N = R * G
         zz = z.reshape(N, V)
@@ -429,9 +443,14 @@ class EmuOps(EmuBackend):
                 raw = np.ctypeslib.as_array((ctypes.c_int16 * n).from_address(int(row[5])))
                 torch.from_numpy(raw).view(torch.bfloat16).copy_(p.to(torch.bfloat16))
 
-    def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w):
+    def contrastive_fwd(self, x, y, idx, ppl, n_vars, xe_w, div_w, n_valid=None):
+        Rall = x.shape[0]
+        K = idx.numel() // Rall
+        if n_valid is not None and int(n_valid) < Rall:
+            R = int(n_valid)
+            loss, ce, saved = self.contrastive_fwd(x[:R], y, idx.reshape(Rall, K)[:R], ppl, n_vars, xe_w, div_w)
+            return loss, ce, saved + (Rall,)
         R, C = x.shape
-        K = idx.numel() // R
         xn = x.norm(dim=-1).clamp_min(1e-8)
         yn = y.norm(dim=-1).clamp_min(1e-8)
         cand = torch.cat([torch.arange(R)[:, None], idx.reshape(R, K).long()], 1)
@@ -442,7 +461,14 @@ class EmuOps(EmuBackend):
         loss = xe_w * ce + (div_w * (n_vars - ppl) / n_vars if ppl is not None else 0.0)
         return loss, ce, (xn, yn, cos, prob, cand)
 
-    def contrastive_bwd(self, x, y, idx, saved, dce):
+    def contrastive_bwd(self, x, y, idx, saved, dce, n_valid=None):
+        if len(saved) == 6:  # padded call: gradients of the valid rows, zeros for the padding
+            Rall = saved[5]
+            R = saved[2].shape[0]
+            dxv, dy = self.contrastive_bwd(x[:R], y, None, saved[:5], dce)
+            dx = torch.zeros_like(x)
+            dx[:R] = dxv
+            return dx, dy
         xn, yn, cos, prob, cand = saved
         R, C = x.shape
         dcos = prob.clone()
