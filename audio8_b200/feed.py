@@ -89,7 +89,8 @@ class PinnedRing:
 
 
 class DeviceFeed:
-    """Iterator adaptor: numpy batches (a single array or a tuple of arrays) -> device tensors, `depth` batches ahead."""
+    """Iterator adaptor: host batches (a single numpy array / pinned tensor or a tuple of them) -> device tensors,
+    `depth` batches ahead."""
 
     def __init__(self, batches, device, depth=2):
         self.it = iter(batches)
@@ -107,7 +108,10 @@ class DeviceFeed:
             return False
         single = not isinstance(b, (tuple, list))
         arrays = [b] if single else list(b)
-        slot, views = self.ring.stage(arrays)
+        if all(isinstance(a, torch.Tensor) and (a.is_pinned() or self.stream is None) for a in arrays):
+            slot, views = None, arrays  # already in pinned host memory (the caller keeps it alive): no staging copy
+        else:
+            slot, views = self.ring.stage([a.numpy() if isinstance(a, torch.Tensor) else a for a in arrays])
         self.h2d_bytes += sum(v.numel() * v.element_size() for v in views)
         if self.stream is None:
             out, ev = [v.clone() for v in views], None
@@ -116,7 +120,8 @@ class DeviceFeed:
                 out = [v.to(self.device, non_blocking=True) for v in views]
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
-            self.ring.events[slot] = ev
+            if slot is not None:
+                self.ring.events[slot] = ev
         self.queue.append((out[0] if single else tuple(out), ev))
         return True
 

@@ -20,7 +20,7 @@ import ref_wav2vec2 as R  # noqa: E402
 
 dev = "cuda"
 torch.set_num_threads(os.cpu_count() or 1)
-out = ["# Round 1 — configs[4]: CTC loss and conv feature encoder sweep, B200 kernels vs the reference's CPU path",
+out = ["# Round 2 — configs[4]: CTC loss and conv feature encoder sweep, B200 kernels vs the reference's CPU path",
        f"\nCPU: {os.cpu_count()} host cores of the GPU box, torch {torch.__version__}.  GB/s = 2*T*B*V*4 bytes (log-probs read once,",
        "gradient written once) / time.\n", "## CTC loss fwd+bwd (V=32, S=T/5)\n",
        "| T | B | GPU us | GPU GB/s | CPU F.ctc_loss ms | speed-up |", "|---:|---:|---:|---:|---:|---:|"]

@@ -155,6 +155,21 @@ for name, mk in gemms.items():
     spec = mk()
     fl = spec.spec().flops
     bench(name, lambda: be.gemm(spec), flops=fl)
+# the 48 weight-gradient GEMMs of the 12-layer stack as ONE grouped persistent launch (a8_gemm_group)
+probs = []
+for _ in range(12):
+    for (n_, k_) in ((3 * D, D), (D, D), (F_, D), (D, F_)):
+        probs.append(G.linear_wgrad_grouped(r(M, n_), r(M, k_), torch.empty(n_, k_, device=dev)))
+bench("gemm grouped wgrad, 12 layers x 4 problems, one launch", lambda: be.gemm_group(probs), flops=sum(b.spec().flops for b in probs))
+del probs
+# optimizer side: fused clip-grad-norm + AdamW over the base model's 95 M parameters (norm pass 4 B/elem, update 28 B/elem)
+from audio8_b200.optim import FusedAdamW  # noqa: E402
+ps = [torch.nn.Parameter(torch.randn(n, device=dev) * 0.02) for n in (590 * 1000,) * 160 + (768,) * 40]
+for p_ in ps:
+    p_.grad = torch.randn_like(p_) * 1e-3
+opt = FusedAdamW(ps, lr=2e-4, weight_decay=0.01)
+nel = sum(p_.numel() for p_ in ps)
+bench(f"fused clip + AdamW step ({nel / 1e6:.0f} M parameters, 2 launches)", lambda: opt.step(clip=1.0), bytes_=nel * 32)
 
 if md_path:
     with open(md_path, "w") as f:
