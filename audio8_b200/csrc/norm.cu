@@ -1,5 +1,5 @@
-// audio8_b200 — HBM-bound row kernels: LayerNorm (+residual, +dropout) fwd/bwd, attention softmax fwd/bwd,
-// column sums (bias gradients), element-wise dropout, log-softmax fwd/bwd.
+// audio8_b200 — HBM-bound row kernels: LayerNorm (+residual, +dropout) fwd/bwd, column sums (bias gradients),
+// element-wise dropout, GELU backward, log-softmax fwd/bwd.  (Attention's softmax lives inside the fused kernels, attn.cu.)
 //
 // Replaces the ATen kernels the reference dispatches for nn.LayerNorm (wav2vec2.py:623,639,904,930 and the
 // ln1/ln2 of every eight_mile TransformerEncoder layer), the residual adds and nn.Dropout around them,
@@ -337,128 +337,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention softmax: P = softmax(S + key_mask) (bf16), optionally P_drop = dropout(P)
-// S fp32 [rows, Tp] (rows = B*H*T), valid columns T; key_keep uint8 [B, T] (0 = padded key -> -1e9)
-// ------------------------------------------------------------------------------------------------
-struct SmFwdArgs {
-  const float* s;
-  const unsigned char* key_keep;  // nullable
-  __nv_bfloat16* p;
-  __nv_bfloat16* p_drop;  // nullable
-  float pdrop;
-  unsigned long long seed;
-  int rows, T, Tp, rows_per_batch;
-  const unsigned long long* seed_src;
-};
-
-template <int NV>  // 8-element chunks per lane: Tp <= NV*256
-__global__ void __launch_bounds__(256) softmax_fwd_kernel(const SmFwdArgs a) {
-  const unsigned long long sbase = seed_base(a.seed_src);
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps) {
-    const long long ro = (long long)row * a.Tp;
-    const unsigned char* keep = a.key_keep ? a.key_keep + (long long)(row / a.rows_per_batch) * a.T : nullptr;
-    float v[NV][8];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      if (c < a.Tp) {
-        load8f(a.s + ro + c, v[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c + j >= a.T) v[i][j] = -INFINITY;
-          else if (keep != nullptr && keep[c + j] == 0) v[i][j] = -1e9f;
-          mx = fmaxf(mx, v[i][j]);
-        }
-      }
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      if (c < a.Tp) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[i][j] = __expf(v[i][j] - mx);
-          sum += v[i][j];
-        }
-      }
-    }
-    const float inv = 1.f / warp_sum(sum);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      if (c < a.Tp) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] *= inv;
-        store8(a.p + ro + c, v[i]);
-        if (a.p_drop != nullptr) {
-          const DropMask8 d = drop_mask8(a.pdrop, a.seed + sbase, (unsigned long long)(ro + c) >> 3);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] *= d.m[j];
-          store8(a.p_drop + ro + c, v[i]);
-        }
-      }
-    }
-  }
-}
-
-// dS = P * (g - sum(P*g)),  g = dropout-mask * dP   (bf16 out; pad columns written as 0)
-struct SmBwdArgs {
-  const __nv_bfloat16* p;
-  const float* dp;
-  __nv_bfloat16* ds;
-  float pdrop;
-  unsigned long long seed;
-  int rows, T, Tp;
-  const unsigned long long* seed_src;
-};
-
-template <int NV>
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const SmBwdArgs a) {
-  const unsigned long long sbase = seed_base(a.seed_src);
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps) {
-    const long long ro = (long long)row * a.Tp;
-    float pv[NV][8], g[NV][8];
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      if (c < a.Tp) {
-        load8(a.p + ro + c, pv[i]);
-        load8f(a.dp + ro + c, g[i]);
-        const DropMask8 d = drop_mask8(a.pdrop, a.seed + sbase, (unsigned long long)(ro + c) >> 3);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c + j >= a.T) {
-            pv[i][j] = 0.f;
-            g[i][j] = 0.f;
-          }
-          g[i][j] *= d.m[j];
-          dot += pv[i][j] * g[i][j];
-        }
-      }
-    }
-    dot = warp_sum(dot);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      if (c < a.Tp) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = pv[i][j] * (g[i][j] - dot);
-        store8(a.ds + ro + c, o);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // column sum: out[c] += sum_r x[r][c]   (bf16 [R, ld] -> fp32 atomics; out zeroed by the caller)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* x, long long ld, int R, int C,
@@ -667,38 +545,6 @@ extern "C" int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, 
   }
 #undef A8_LN_BWD
   return check_launch("ln_bwd_kernel");
-}
-
-extern "C" int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, void* p_drop, float pdrop,
-                              uint64_t seed, int32_t B, int32_t H, int32_t T, int32_t Tp, void* stream_v) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax: bad T=%d Tp=%d", T, Tp);
-  SmFwdArgs a{s, key_keep, (__nv_bfloat16*)p, (__nv_bfloat16*)p_drop, pdrop, seed, B * H * T, T, Tp, H * T, seed_source()};
-  const int nv = cdiv(Tp, 256);
-  const int grid = row_grid(a.rows);
-  if (nv <= 1) softmax_fwd_kernel<1><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 2) softmax_fwd_kernel<2><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 3) softmax_fwd_kernel<3><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 4) softmax_fwd_kernel<4><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 8) softmax_fwd_kernel<8><<<grid, 256, 0, stream>>>(a);
-  else softmax_fwd_kernel<16><<<grid, 256, 0, stream>>>(a);
-  return check_launch("softmax_fwd_kernel");
-}
-
-extern "C" int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pdrop, uint64_t seed, int32_t B,
-                              int32_t H, int32_t T, int32_t Tp, void* stream_v) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  A8_REQUIRE(Tp % 8 == 0 && Tp >= T && Tp <= 4096, "softmax_bwd: bad T=%d Tp=%d", T, Tp);
-  SmBwdArgs a{(const __nv_bfloat16*)p, dp, (__nv_bfloat16*)ds, pdrop, seed, B * H * T, T, Tp, seed_source()};
-  const int nv = cdiv(Tp, 256);
-  const int grid = row_grid(a.rows);
-  if (nv <= 1) softmax_bwd_kernel<1><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 2) softmax_bwd_kernel<2><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 3) softmax_bwd_kernel<3><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 4) softmax_bwd_kernel<4><<<grid, 256, 0, stream>>>(a);
-  else if (nv <= 8) softmax_bwd_kernel<8><<<grid, 256, 0, stream>>>(a);
-  else softmax_bwd_kernel<16><<<grid, 256, 0, stream>>>(a);
-  return check_launch("softmax_bwd_kernel");
 }
 
 extern "C" int a8_colsum(const void* x, int64_t ld, int32_t R, int32_t C, float* out, void* stream_v) {

@@ -84,6 +84,74 @@ def _grad_empty(key, shape, like):
     return buf.view(shape)
 
 
+def operands(cache, key, params, build):
+    """GEMM operands derived from fp32 parameters (bf16 copies, packed conv / pos-conv layouts, bf16x3 splits): rebuilt
+    only when a parameter changed (storage address or autograd version counter, which every in-place update bumps),
+    and then written into the SAME buffers, so CUDA-graph replays that read them stay valid.  `cache` is a dict owned by
+    the module (None: no caching); `build(prev)` launches the re-layout kernels into `prev` when it is not None.
+    Modules refresh their operands eagerly at the start of forward(), before any graph segment replays; the calls
+    inside the autograd Functions then hit."""
+    if cache is None:
+        return build(None)
+    ver = tuple((p.data_ptr(), p._version) for p in params)
+    ent = cache.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    bufs = build(ent[1] if ent is not None else None)
+    cache[key] = (ver, bufs)
+    return bufs
+
+
+def linear_operands(cache, weight, bias):
+    """(bf16 weight [N8, K], fp32 bias [N8] or None): N padded to a multiple of 8 with zero rows when needed"""
+    def build(prev):
+        N = weight.shape[0]
+        N8 = (N + 7) // 8 * 8
+        w32 = weight.detach().contiguous().float()
+        if N8 != N:
+            w32 = _pad_rows8(w32, N8)
+        wb = _be().cast(w32, BF16, out=prev[0] if prev is not None else None)
+        bv = None
+        if bias is not None:
+            bv = bias.detach().float()
+            if N8 != N:
+                bv = _pad_rows8(bv, N8)
+                if prev is not None:
+                    prev[1].copy_(bv)
+                    bv = prev[1]
+        return wb, bv
+    if weight.dtype == BF16:
+        return weight.detach().contiguous(), (bias.detach() if bias is not None else None)
+    return operands(cache, "linear", [weight] + ([bias] if bias is not None else []), build)
+
+
+def conv_operands(cache, spec, weights):
+    """per conv layer i >= 1: (wk bf16 [Cout, k*Cin], [wt_0, wt_1] for the data-gradient GEMMs)"""
+    def build(prev):
+        out = [None]
+        for i in range(1, len(spec)):
+            out.append(_be().conv_pack(weights[i].detach().contiguous(), spec[i][2], True, out=prev[i] if prev is not None else None))
+        return out
+    return operands(cache, "conv", list(weights[1:]), build)
+
+
+def posconv_operands(cache, pos_g, pos_v):
+    def build(prev):
+        return _be().posconv_pack(pos_g.detach().contiguous(), pos_v.detach().contiguous(), True, out=prev)
+    return operands(cache, "posconv", [pos_g, pos_v], build)
+
+
+def quantizer_operands(cache, w, vars_):
+    """(fp32 weight, bf16x3 split of it (B side), bf16 weight, fp32 codebook [G*V, vd], bf16 codebook)"""
+    def build(prev):
+        be = _be()
+        w32 = w.detach().contiguous().float()
+        v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
+        p = prev if prev is not None else (None,) * 5
+        return (w32, be.split3(w32, True, out=p[1]), be.cast(w32, BF16, out=p[2]), v2, be.cast(v2, BF16, out=p[4]))
+    return operands(cache, "vq", [w, vars_], build)
+
+
 def _bf16(t):
     """bf16 contiguous copy of a tensor through the cast kernel (parameters are fp32 masters)"""
     t = t.detach()
@@ -107,18 +175,14 @@ class LinearFn(torch.autograd.Function):
     `len(vocab)`) runs zero-padded to the next multiple and is sliced back: the reference works for any width."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, out_f32):
+    def forward(ctx, x, weight, bias, out_f32, cache=None):
         be = _be()
         shp = x.shape
         x2 = x.detach().reshape(-1, shp[-1])
         xb = _bf16(x2)
-        wb = _bf16(weight)
         N = weight.shape[0]
-        N8 = (N + 7) // 8 * 8
-        bvec = bias.detach() if bias is not None else None
-        if N8 != N:
-            wb = _pad_rows8(wb, N8)
-            bvec = _pad_rows8(bvec.float(), N8) if bvec is not None else None
+        wb, bvec = linear_operands(cache, weight, bias)
+        N8 = wb.shape[0]
         out = _empty((x2.shape[0], N8), F32 if out_f32 else BF16, x, dynamic=True)
         be.gemm(G.linear_fwd(xb, wb, out, bvec, c_dtype=OUT_F32 if out_f32 else OUT_BF16))
         ctx.saved = (xb, wb, x.dtype, shp, bias is not None, N, ops.grad_key(weight), ops.grad_key(bias))
@@ -148,11 +212,11 @@ class LinearFn(torch.autograd.Function):
             dw = dw[:N]
         if has_bias and ctx.needs_input_grad[2]:
             db = be.colsum(dyb, out=_grad_zeros(bkey, (N8,), xb) if N8 == N else None)[:N]
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def linear(x, weight, bias=None, out_f32=False):
-    return LinearFn.apply(x, weight, bias, out_f32)
+def linear(x, weight, bias=None, out_f32=False, cache=None):
+    return LinearFn.apply(x, weight, bias, out_f32, cache)
 
 
 # =================================================================================================
@@ -282,7 +346,7 @@ class ConvFeatureFn(torch.autograd.Function):
     layers 1.. = implicit-GEMM tcgen05 convs with GELU epilogues (zero-copy im2col through overlapping TMA rows)."""
 
     @staticmethod
-    def forward(ctx, x, spec, gn_w, gn_b, *weights):
+    def forward(ctx, x, spec, cache, gn_w, gn_b, *weights):
         be = _be()
         x = x.detach().contiguous().float()
         (c0, k0, s0) = spec[0]
@@ -292,11 +356,12 @@ class ConvFeatureFn(torch.autograd.Function):
         mean, rstd, mom = be.conv0_stats(x, w0, k0, s0, 1e-5)
         a = be.conv0_fwd(x, w0, gw, gb, mean, rstd, k0, s0)
         acts, zs, wts = [a], [None], [None]
+        packed = conv_operands(cache, spec, weights)
         for i in range(1, len(spec)):
             (c, k, s) = spec[i]
             B, Lin, Cin = a.shape
             Lout = (Lin - k) // s + 1
-            wk, wt = be.conv_pack(weights[i].detach().contiguous(), s, need_grad)
+            wk, wt = packed[i]
             y = _empty((B, Lout, c), BF16, a)
             z = _empty((B, Lout, c), F16, a) if need_grad else None
             be.gemm(G.conv_fwd(a, wk, y, k, s, z_out=z))
@@ -339,7 +404,7 @@ class ConvFeatureFn(torch.autograd.Function):
         dest = (_grad_empty(keys[0], (c0, k0), x), _grad_empty(keys[n], (c0,), x), _grad_empty(keys[n + 1], (c0,), x))
         dw0, dg, db = be.conv0_bwd(x, w0, gw, gb, mean, rstd, mom, k0, s0, da0, out=dest)
         grads[0] = dw0.view(c0, 1, k0)
-        return (None, None, dg, db, *grads)
+        return (None, None, None, dg, db, *grads)
 
 
 # =================================================================================================
@@ -347,8 +412,8 @@ class ConvFeatureFn(torch.autograd.Function):
 # =================================================================================================
 def _prepare_layer_weights(be, arena, lw, per_layer):
     """one launch: every transformer GEMM weight fp32 -> bf16 into a persistent arena (w_Q|w_K|w_V land in one fused
-    [3D,D] operand, their biases in one fp32 [3D] vector).  Values are rewritten on every call; only the buffers and
-    the device-side pointer table persist."""
+    [3D,D] operand, their biases in one fp32 [3D] vector).  The buffers and the device-side pointer table persist; the
+    values are rewritten only when a parameter changed (see `operands`)."""
     nl = len(lw) // per_layer
     D = lw[0].shape[1]
     F_ = lw[10].shape[0]
@@ -374,8 +439,20 @@ def _prepare_layer_weights(be, arena, lw, per_layer):
         (wq, bq, wk, bk, wv, bv, wo, _bo, _g2, _b2, w1, _b1, w2, _bb2, _g1, _b1l) = lw[li * per_layer:(li + 1) * per_layer]
         srcs = [wq, wk, wv, wo, w1, w2, bq, bk, bv]
         pairs += [(sv.detach(), d) for sv, d in zip(srcs, arena["dsts"][li])]
-    be.cast_multi(pairs, arena["cache"])
+    ver = tuple((sv.data_ptr(), sv._version) for sv, _ in pairs)
+    if arena.get("ver") != ver:
+        be.cast_multi(pairs, arena["cache"])
+        arena["ver"] = ver
     return arena["views"]
+
+
+def encoder_operands(arena, pos_g, pos_v, lw, per_layer, front=True):
+    """refresh (if stale) the transformer stack's bf16 weight arena and the packed positional conv: what
+    AudioTransformerEncoder calls before it replays its CUDA-graph segments"""
+    if front and pos_v is not None:
+        posconv_operands(arena, pos_g, pos_v)
+    if len(lw):
+        _prepare_layer_weights(_be(), arena, lw, per_layer)
 
 
 class EncoderFn(torch.autograd.Function):
@@ -408,7 +485,7 @@ class EncoderFn(torch.autograd.Function):
         front = cfg.get("front", True)  # False: a later slice of the stack (no positional conv / LayerNorm in front)
         if front:
             pg, pv = pos_g.detach().contiguous(), pos_v.detach().contiguous()
-            wp, wpt, norm2 = be.posconv_pack(pg, pv, need_grad)
+            wp, wpt, norm2 = posconv_operands(cfg["arena"], pos_g, pos_v)
             s0 = _empty(x.shape, BF16, x)
             z0 = _empty(x.shape, F16, x)
             be.gemm(G.posconv_fwd(x, wp, s0, pos_b.detach(), groups, k, pad_l, z_out=z0))
@@ -585,20 +662,19 @@ class QuantizerFn(torch.autograd.Function):
     last_logits = None
 
     @staticmethod
-    def forward(ctx, y, w, b, vars_, G_, tau, noise, n_valid=None):
+    def forward(ctx, y, w, b, vars_, G_, tau, noise, n_valid=None, cache=None):
         be = _be()
         Bq, Tm, Cin = y.shape
         R = Bq * Tm
         y2 = y.detach().reshape(R, Cin).contiguous().float()
-        w32 = w.detach().contiguous().float()
+        w32, w_split, w_bf, v2, v_bf = quantizer_operands(cache, w, vars_)
         # logits with fp32-accurate products on the tensor cores: bf16x3 split along K (csrc/misc.cu)
         z = _empty((R, w.shape[0]), F32, y, dynamic=True)
-        be.gemm(G.linear_fwd(be.split3(y2, False), be.split3(w32, True), z, b.detach(), c_dtype=OUT_F32))
-        v2 = vars_.detach().reshape(-1, vars_.shape[-1]).contiguous().float()
+        be.gemm(G.linear_fwd(be.split3(y2, False), w_split, z, b.detach(), c_dtype=OUT_F32))
         q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, float(tau), v2, G_, n_valid=n_valid)
         # outputs are kept as detached aliases (no ctx <-> output reference cycle)
         ctx.saved = (y2, w32, v2, z, noise, kidx.detach(), avg, ppl.detach(), G_, float(tau), y.shape, vars_.shape,
-                     (ops.grad_key(w), ops.grad_key(b), ops.grad_key(vars_)), n_valid)
+                     (ops.grad_key(w), ops.grad_key(b), ops.grad_key(vars_)), n_valid, w_bf, v_bf)
         ctx.mark_non_differentiable(kidx)
         QuantizerFn.last_logits = z if QuantizerFn.keep_logits else None
         return q.view(Bq, Tm, -1), ppl, kidx
@@ -606,7 +682,7 @@ class QuantizerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dq, dppl, _dk):
         be = _be()
-        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape, (wkey, bkey, vkey), n_valid = _take_saved(ctx)
+        y2, w32, v2, z, noise, kidx, avg, ppl, G_, tau, yshape, vshape, (wkey, bkey, vkey), n_valid, w_bf, v_bf = _take_saved(ctx)
         R = y2.shape[0]
         vd = v2.shape[1]
         if dq is None:
@@ -617,15 +693,15 @@ class QuantizerFn(torch.autograd.Function):
         a_dot = None
         if noise is not None:
             a_dot = _empty((R, v2.shape[0]), F32, y2, dynamic=True)
-            be.gemm(G.vq_codebook_dots(_bf16(dq2), _bf16(v2), a_dot, G_))
+            be.gemm(G.vq_codebook_dots(_bf16(dq2), v_bf, a_dot, G_))
         dz, dvars = be.vq_bwd(z, noise, tau, G_, vd, a_dot, dq2, kidx, avg, ppl, dppl.contiguous().float(),
                               dvars_out=_grad_zeros(vkey, tuple(v2.shape), y2), n_valid=n_valid)
         db = be.colsum(dz, out=_grad_zeros(bkey, (dz.shape[-1],), y2))
         dw = _grad_zeros(wkey, tuple(w32.shape), y2)
         be.gemm(G.linear_wgrad(dz, _bf16(y2), dw))
         dy = _empty(y2.shape, F32, y2, dynamic=True)
-        be.gemm(G.linear_dgrad(dz, _bf16(w32), dy, c_dtype=OUT_F32))
-        return dy.view(yshape), dw, db, dvars.view(vshape), None, None, None, None
+        be.gemm(G.linear_dgrad(dz, w_bf, dy, c_dtype=OUT_F32))
+        return dy.view(yshape), dw, db, dvars.view(vshape), None, None, None, None, None
 
 
 # =================================================================================================

@@ -366,21 +366,6 @@ class CudaBackend:
                    "a8_layernorm_bwd")
         return ds, dh, a0, a1, (a2 if want_dbias else None)
 
-    def softmax_fwd(self, s, T, key_keep=None, pdrop=0.0, seed=0):
-        B, H, _, Tp = s.shape
-        p = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
-        pd = torch.empty_like(p) if pdrop > 0 else None
-        _lib.check(self.lib.a8_softmax_fwd(_ptr(s), _ptr(key_keep), _ptr(p), _ptr(pd), pdrop, seed, B, H, T, Tp,
-                                           _stream()), "a8_softmax_fwd")
-        return p, pd
-
-    def softmax_bwd(self, p, dp, T, pdrop=0.0, seed=0):
-        B, H, _, Tp = p.shape
-        ds = torch.empty_like(p)
-        _lib.check(self.lib.a8_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), pdrop, seed, B, H, T, Tp, _stream()),
-                   "a8_softmax_bwd")
-        return ds
-
     # ------------------------------------------------------------------ fused attention
     def attn_fwd(self, qkv, H, scale, key_keep=None, pdrop=0.0, seed=0):
         """qkv bf16 [B,T,3D] -> (ctx bf16 [B,T,D], lse fp32 [B,H,T]); scores / probabilities stay on chip"""
@@ -531,17 +516,19 @@ class CudaBackend:
         B, T, C = x.shape
         _lib.check(self.lib.a8_mask_apply(_ptr(x), _ptr(row_keep), _ptr(chan_zero), B, T, C, _stream()), "a8_mask_apply")
 
-    def cast(self, x, dtype):
+    def cast(self, x, dtype, out=None):
         assert x.is_contiguous()
-        out = bucketed_empty(x.shape, dtype, x.device)
+        if out is None:
+            out = bucketed_empty(x.shape, dtype, x.device)
         _lib.check(self.lib.a8_cast(_ptr(x), self._dt(x.dtype), _ptr(out), self._dt(dtype), x.numel(), _stream()),
                    "a8_cast")
         return out
 
-    def split3(self, x, b_side):
+    def split3(self, x, b_side, out=None):
         R, C = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous()
-        out = bucketed_empty((R, 3 * C), torch.bfloat16, x.device)
+        if out is None:
+            out = bucketed_empty((R, 3 * C), torch.bfloat16, x.device)
         _lib.check(self.lib.a8_split3(_ptr(x), _ptr(out), R, C, int(b_side), _stream()), "a8_split3")
         return out
 
@@ -558,14 +545,18 @@ class CudaBackend:
             cache["sig"] = sig
         _lib.check(self.lib.a8_cast_multi(_ptr(cache["table"]), len(pairs), _stream()), "a8_cast_multi")
 
-    def conv_pack(self, w, s, want_t):
-        """[Cout,Cin,k] fp32 -> (wk bf16 [Cout,k*Cin], [wt_0, wt_1] bf16 [Cin, ntaps_p*Cout] or None)"""
+    def conv_pack(self, w, s, want_t, out=None):
+        """[Cout,Cin,k] fp32 -> (wk bf16 [Cout,k*Cin], [wt_0, wt_1] bf16 [Cin, ntaps_p*Cout] or None); out: a previous
+        result to overwrite (persistent operand buffers)"""
         Cout, Cin, k = w.shape
         assert w.dtype == torch.float32 and w.is_contiguous() and s == 2
-        wk = torch.empty(Cout, k * Cin, dtype=torch.bfloat16, device=w.device)
-        wts = None
-        if want_t:
-            wts = [torch.empty(Cin, ((k - p + s - 1) // s) * Cout, dtype=torch.bfloat16, device=w.device) for p in range(s)]
+        if out is not None:
+            wk, wts = out
+        else:
+            wk = torch.empty(Cout, k * Cin, dtype=torch.bfloat16, device=w.device)
+            wts = None
+            if want_t:
+                wts = [torch.empty(Cin, ((k - p + s - 1) // s) * Cout, dtype=torch.bfloat16, device=w.device) for p in range(s)]
         _lib.check(self.lib.a8_conv_pack(_ptr(w), Cout, Cin, k, s, _ptr(wk), _ptr(wts[0]) if wts else None,
                                          _ptr(wts[1]) if wts else None, _stream()), "a8_conv_pack")
         return wk, wts
@@ -576,14 +567,17 @@ class CudaBackend:
         _lib.check(self.lib.a8_conv_unpack(_ptr(dwk), Cout, Cin, k, _ptr(dw), _stream()), "a8_conv_unpack")
         return dw
 
-    def posconv_pack(self, g, v, want_t):
-        """weight-normed pos-conv weight -> (wp, wpt or None, norm2)"""
+    def posconv_pack(self, g, v, want_t, out=None):
+        """weight-normed pos-conv weight -> (wp, wpt or None, norm2); out: a previous result to overwrite"""
         D, cg, k = v.shape
         assert g.numel() == k and v.is_contiguous() and g.is_contiguous()
-        buf = torch.empty(k + self.lib.a8_posconv_norm_scratch_floats(D, cg, k), dtype=torch.float32, device=v.device)
-        norm2 = buf[:k]  # followed by the ordered-partial-sum scratch of the deterministic reduction
-        wp = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device)
-        wpt = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device) if want_t else None
+        if out is not None:
+            wp, wpt, norm2 = out  # norm2 is a view of the buffer that also holds the reduction scratch
+        else:
+            buf = torch.empty(k + self.lib.a8_posconv_norm_scratch_floats(D, cg, k), dtype=torch.float32, device=v.device)
+            norm2 = buf[:k]  # followed by the ordered-partial-sum scratch of the deterministic reduction
+            wp = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device)
+            wpt = torch.empty(D, k * 64, dtype=torch.bfloat16, device=v.device) if want_t else None
         _lib.check(self.lib.a8_posconv_pack(_ptr(g), _ptr(v), D, cg, k, _ptr(norm2), _ptr(wp), _ptr(wpt), _stream()),
                    "a8_posconv_pack")
         return wp, wpt, norm2

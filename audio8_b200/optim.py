@@ -184,6 +184,10 @@ class FusedAdamW(torch.optim.Optimizer):
             be.optim_adamw(table, plan.chunk_tensor, plan.chunk_off, CHUNK, partial_sets if has_clip else None,
                            float(clip) if has_clip else 0.0, gscale, float(g["lr"]), float(b1), float(b2), float(g["eps"]),
                            float(g["weight_decay"]), bc1, bc2s, False, self.last_grad_norm if has_clip else None)
+            for p in stepped:
+                # the kernel wrote through raw pointers: tell autograd (and the operand caches keyed on the version
+                # counter, functional.operands) that the parameter changed
+                torch.autograd.graph.increment_version(p)
         return loss
 
     def _plan(self, key, params):

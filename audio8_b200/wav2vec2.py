@@ -260,9 +260,13 @@ class _Linear(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_sz, in_sz))
         self.bias = nn.Parameter(torch.zeros(out_sz))
         nn.init.xavier_uniform_(self.weight)
+        self._ops = {}  # bf16 operand copy of the weight, refreshed when the parameter changes (functional.operands)
+
+    def refresh_operands(self):
+        Fn.linear_operands(self._ops, self.weight, self.bias)
 
     def forward(self, x, out_f32=False):
-        return Fn.linear(x, self.weight, self.bias, out_f32)
+        return Fn.linear(x, self.weight, self.bias, out_f32, self._ops)
 
 
 class Dense(nn.Module):
@@ -272,6 +276,9 @@ class Dense(nn.Module):
         super().__init__()
         self.layer = _Linear(insz, outsz)
         self.output_dim = outsz
+
+    def refresh_operands(self):
+        self.layer.refresh_operands()
 
     def forward(self, x, out_f32=False):
         return self.layer(x, out_f32)
@@ -310,12 +317,17 @@ class ConvFeatureExtractionModel(nn.Module):
             mods.append(nn.Identity())
             self.conv_layers.append(nn.ModuleList(mods))
             cin = dim
+        self._ops = {}  # packed bf16 conv weights (forward and data-gradient layouts), refreshed when a weight changes
+
+    def refresh_operands(self):
+        Fn.conv_operands(self._ops, self.spec, [layer[0].weight for layer in self.conv_layers])
 
     def forward_channels_last(self, x):
         """[B,L] fp32 -> bf16 [B,T,C]"""
         gn = self.conv_layers[0][2]
         weights = [layer[0].weight for layer in self.conv_layers]
-        return Fn.ConvFeatureFn.apply(x, self.spec, gn.weight, gn.bias, *weights)
+        self.refresh_operands()
+        return Fn.ConvFeatureFn.apply(x, self.spec, self._ops, gn.weight, gn.bias, *weights)
 
     def forward(self, x):
         """reference layout: [B,C,T] fp32"""
@@ -346,6 +358,10 @@ class GumbelVectorQuantizer(nn.Module):
         self.last_indices = None
         self.keep_logits = False  # parity tests: keep a copy of the fp32 logits [B*T, G*V] in `last_logits`
         self.last_logits = None
+        self._ops = {}  # fp32 / bf16x3-split / bf16 copies of weight_proj and the codebook (functional.operands)
+
+    def refresh_operands(self):
+        Fn.quantizer_operands(self._ops, self.weight_proj.weight, self.vars)
 
     def set_num_updates(self, num_updates):
         self.curr_temperature = max(self.max_temperature * self.temperature_decay ** num_updates, self.min_temperature)
@@ -368,7 +384,7 @@ class GumbelVectorQuantizer(nn.Module):
                 if noise.shape[0] < n:  # parity tests supply noise for the valid rows only: pad rows are never read
                     noise = torch.cat([noise, noise.new_zeros(n - noise.shape[0], noise.shape[1])])
         Fn.QuantizerFn.keep_logits = self.keep_logits
-        q, ppl, kidx = Fn.QuantizerFn.apply(x, w, b, v, self.num_groups, self.curr_temperature, noise, n_valid)
+        q, ppl, kidx = Fn.QuantizerFn.apply(x, w, b, v, self.num_groups, self.curr_temperature, noise, n_valid, self._ops)
         self.last_indices = kidx
         if self.keep_logits:
             self.last_logits = Fn.QuantizerFn.last_logits.detach().clone()
@@ -487,6 +503,9 @@ class AudioTransformerEncoder(nn.Module):
             cfg = dict(num_heads=self.num_heads, groups=self.conv_groups, pdrop=self.pdrop, training=self.training,
                        active=active[lo:hi], arena=self._arena.setdefault(part, {}), front=(part == 0))
             params = self._part_params(part, lo, hi, front_params)
+            # bf16 / packed operand copies: refreshed here, eagerly, only if a parameter changed since the last call
+            Fn.encoder_operands(cfg["arena"], pc.weight_g, pc.weight_v, params[5:] if part == 0 else params,
+                                Fn.EncoderFn.PER_LAYER, front=(part == 0))
             h = self._run_part(part, h, cfg, row_keep, params, clone=(not _internal) and part == len(cuts) - 2)
         return h
 
@@ -638,9 +657,9 @@ class Wav2Vec2Model(nn.Module):
         `_front_params`) so that a CUDA-graph capture can run it on aliases of them (graphs.py)."""
         n = len(self.feature_extractor.spec)
         conv_w, (ln_w, ln_b, pw, pb, mask_emb) = rest[:n], rest[n:]
-        fx = Fn.ConvFeatureFn.apply(x, self.feature_extractor.spec, gn_w, gn_b, *conv_w)
+        fx = Fn.ConvFeatureFn.apply(x, self.feature_extractor.spec, self.feature_extractor._ops, gn_w, gn_b, *conv_w)
         features, unmasked = Fn.layer_norm(fx, ln_w, ln_b, 1e-5, want_f32=True)
-        features = Fn.linear(features, pw, pb)
+        features = Fn.linear(features, pw, pb, cache=self.proj_to_input.layer._ops)
         features = Fn.dropout(features, self.dropout_input_p, self.training)
         features = Fn.RowsSetFn.apply(features, rows[:-1], mask_emb)
         return features, unmasked
@@ -652,7 +671,7 @@ class Wav2Vec2Model(nn.Module):
         y = Fn.RowsGatherFn.apply(unmasked, rows[:-1]).view(B, -1, C)
         y = Fn.dropout(y, self.dropout_features_p, self.training)
         q, vq_probs = self.quantizer(y, n_valid=rows[-1:], _params=(wq, bq, vars_))
-        return Fn.linear(q, pw, pb, out_f32=True), vq_probs
+        return Fn.linear(q, pw, pb, out_f32=True, cache=self.project_q.layer._ops), vq_probs
 
     def set_num_updates(self, s):
         self.quantizer.set_num_updates(s)
@@ -693,6 +712,10 @@ class Wav2Vec2Model(nn.Module):
         buf[R_max] = idx.size
         rows = _to_device(buf, x.device)
         Fn.ops.set_dynamic_rows(R_max, R_max)
+        # operand copies of the parameters (packed conv weights, bf16 projections, quantizer splits): refreshed eagerly and
+        # only when a parameter changed since the last call, so the graph segments below contain no re-layout kernels
+        for m in (self.feature_extractor, self.proj_to_input, self.quantizer, self.project_q, self.final_proj):
+            m.refresh_operands()
         eager = self.quantizer.noise_override is not None or self.quantizer.keep_logits  # parity-test hooks: no replay
         arena = Fn.ops.grad_arena_active()
         features, unmasked = self._front_graph.run(self._front, (x, rows), self._front_params(),

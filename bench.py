@@ -611,6 +611,9 @@ def _run_ours(args):
                 "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                 "launch": "the step is 4 CUDA-graph segments (front+mask, quantizer branch, encoder, loss), fwd and bwd; "
                           "masked-row lists padded to their worst-case length; host draws prefetched one step ahead",
+                "operands": "bf16 / packed operand copies of the parameters are rebuilt when a parameter changes (version "
+                            "counter), i.e. once per optimizer step; the fwd+bwd loop of `value` never changes them, "
+                            "step_with_optimizer rebuilds them every step",
                 "gc": "gc.freeze() after warm-up (full collections no longer walk the long-lived heap)"}),
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "last_loss": loss_val},

@@ -167,16 +167,6 @@ int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, uint64_t se
                      uint64_t seed_h, float* dgamma, float* dbeta, float* dbias_h, int32_t R, int32_t C,
                      void* stream);
 
-/* Attention softmax over keys.  Replaces softmax / masked_fill(-1e9) / dropout in eight_mile's
- * SeqScaledDotProductAttention (called via `wav2vec2.py:644`).  s fp32 [B,H,T,Tp] (Tp = T rounded up to 8),
- * key_keep uint8 [B,T] or NULL (0 = padded key), p / p_drop / ds bf16 [B,H,T,Tp] (pad columns written 0).
- *   fwd: p = softmax(s);  p_drop = dropout(p) if p_drop != NULL
- *   bwd: ds = p * (g - sum(p*g)),  g = dropout-mask * dp */
-int a8_softmax_fwd(const float* s, const uint8_t* key_keep, void* p, void* p_drop, float pdrop, uint64_t seed,
-                   int32_t B, int32_t H, int32_t T, int32_t Tp, void* stream);
-int a8_softmax_bwd(const void* p, const float* dp, void* ds, float pdrop, uint64_t seed, int32_t B, int32_t H,
-                   int32_t T, int32_t Tp, void* stream);
-
 /* Fused scaled-dot-product attention, d_k = 64 (tcgen05 / TMEM; scores and probabilities never reach HBM).
  * Replaces eight_mile's SeqScaledDotProductAttention as called through `wav2vec2.py:644` and its autograd:
  *   P = dropout(softmax(scale * Q K^T + key mask));  ctx = P V

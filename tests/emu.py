@@ -236,12 +236,17 @@ class EmuOps(EmuBackend):
         for s, d in pairs:
             d.copy_(s.reshape(d.shape))
 
-    def conv_pack(self, w, s, want_t):
+    def conv_pack(self, w, s, want_t, out=None):
         Cout, Cin, k = w.shape
         wk = _bf(w.permute(0, 2, 1).reshape(Cout, -1)).contiguous()
         wts = None
         if want_t:
             wts = [_bf(torch.cat([w[:, :, j].t() for j in range(k) if j % s == p], 1)).contiguous() for p in range(s)]
+        if out is not None:  # refresh persistent operand buffers in place
+            out[0].copy_(wk)
+            for d, t in zip(out[1] or [], wts or []):
+                d.copy_(t)
+            return out
         return wk, wts
 
     def conv_unpack(self, dwk, Cin, k, out=None):
@@ -257,12 +262,18 @@ class EmuOps(EmuBackend):
         out[..., :cg] = wg.permute(0, 1, 3, 2)
         return _bf(out.reshape(D, k * 64)).contiguous()
 
-    def posconv_pack(self, g, v, want_t):
+    def posconv_pack(self, g, v, want_t, out=None):
         D, cg, k = v.shape
         norm2 = (v * v).sum((0, 1))
         w = g.reshape(1, 1, k) * v / norm2.sqrt()
         groups = D // cg
-        return self._pc_pack(w, groups, False), (self._pc_pack(w, groups, True) if want_t else None), norm2
+        res = self._pc_pack(w, groups, False), (self._pc_pack(w, groups, True) if want_t else None), norm2
+        if out is not None:
+            for d, t in zip(out, res):
+                if d is not None and t is not None:
+                    d.copy_(t)
+            return out
+        return res
 
     def posconv_wn_bwd(self, dwp, g, v, norm2, out=None):
         D, cg, k = v.shape
@@ -349,13 +360,13 @@ class EmuOps(EmuBackend):
         if chan_zero is not None:
             x.masked_fill_(chan_zero[:, None, :] != 0, 0)
 
-    def cast(self, x, dtype):
-        return x.to(dtype)
+    def cast(self, x, dtype, out=None):
+        return _into(out, x.to(dtype))
 
-    def split3(self, x, b_side):
+    def split3(self, x, b_side, out=None):
         hi = _bf(x)
         lo = _bf(x - hi.float())
-        return torch.cat([hi, lo, hi] if b_side else [hi, hi, lo], 1).contiguous()
+        return _into(out, torch.cat([hi, lo, hi] if b_side else [hi, hi, lo], 1).contiguous())
 
     # ---- quantizer / contrastive
     def vq_fwd(self, z, noise, tau, vars2d, G, n_valid=None):

@@ -75,26 +75,6 @@ def test_layernorm_dropout_consistency(be):
     _close(dh.float()[nz], (ds.float() / (1 - p))[nz], 1e-2, "dh scale")
 
 
-@pytest.mark.parametrize("B,H,T", [(2, 2, 49), (1, 3, 300), (2, 1, 749)])
-def test_softmax(be, B, H, T):
-    Tp = (T + 7) // 8 * 8
-    s = torch.randn(B, H, T, Tp, generator=_g(1)) * 3
-    keep = (torch.rand(B, T, generator=_g(2)) > 0.2).to(torch.uint8)
-    keep[:, 0] = 1
-    dp = torch.randn(B, H, T, Tp, generator=_g(3))
-    for kk in (None, keep):
-        p_ref, _ = E.softmax_fwd(s, T, kk)
-        p_got, pd = be.softmax_fwd(s.cuda(), T, kk.cuda() if kk is not None else None)
-        assert pd is None
-        _close(p_got, p_ref, 1e-2, "softmax fwd")
-        assert p_got[..., T:].abs().max().item() == 0 if Tp > T else True
-        _close(be.softmax_bwd(p_ref.cuda(), dp.cuda(), T), E.softmax_bwd(p_ref, dp, T), 2e-2, "softmax bwd")
-    # dropout: P_drop is P where kept (scaled), 0 where dropped, and backward uses the same mask
-    p_got, pd = be.softmax_fwd(s.cuda(), T, None, 0.25, 77)
-    kept = pd[..., :T].float() != 0
-    assert abs(kept.float().mean().item() - 0.75) < 0.02
-
-
 def test_colsum_gelu_dropout_cast(be):
     x = _bf((1000, 3072), 1)
     _close(be.colsum(x.cuda()), E.colsum(x), 2e-3, "colsum")

@@ -213,3 +213,43 @@ def test_encoder_outputs_are_fresh_tensors_cuda():
     for x, g in zip(xg, g_ref):
         rel = ((x.grad.float() - g.float()).norm() / g.float().norm()).item()
         assert rel < 1e-2, f"gradient after interleaved forwards differs: rel {rel:.3g}"
+
+
+def _operand_refresh_case(device, steps_before):
+    """the bf16 / packed operand copies of the parameters are cached across calls (and read by replayed CUDA graphs): after
+    an in-place parameter update the next forward must see the new weights — same loss as a freshly built model"""
+    import numpy as np
+    import torch
+    from audio8_b200 import wav2vec2 as W
+    cfg = dict(d_model=128, num_heads=2, num_layers=2, d_ff=256, final_dim=64, num_vq_vars=24, num_vq_groups=2)
+    torch.manual_seed(0)
+    model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg).to(device).eval()
+    loss_fn = W.create_loss(48, 10)
+    x = (torch.randn(2, 16000, generator=torch.Generator().manual_seed(1)) * 0.1).to(device)
+
+    def loss_of(m):
+        np.random.seed(3)
+        return loss_fn(m, x)
+
+    for _ in range(steps_before):  # eager, capture, replay
+        loss_of(model).backward()
+        model.zero_grad(set_to_none=True)
+    l0 = loss_of(model).item()
+    with torch.no_grad():  # what an optimizer does: in-place updates
+        for p in model.parameters():
+            p.mul_(0.9).add_(0.01 * torch.randn(p.shape, generator=torch.Generator().manual_seed(p.numel())).to(device))
+    l1 = loss_of(model).item()
+    fresh = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg).to(device).eval()
+    fresh.load_state_dict(model.state_dict())
+    l2 = loss_of(fresh).item()
+    assert abs(l1 - l0) > 1e-4 * abs(l0), "the update did not change the loss: test is vacuous"
+    assert abs(l1 - l2) <= 1e-5 * abs(l2), f"stale operand copies: {l1} after the update vs {l2} from a fresh model"
+
+
+def test_operand_copies_follow_parameter_updates_cpu(emu_backend):
+    _operand_refresh_case("cpu", 1)
+
+
+@pytest.mark.gpu
+def test_operand_copies_follow_parameter_updates_cuda():
+    _operand_refresh_case("cuda", 4)
