@@ -17,7 +17,7 @@ import weakref
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 ENABLED = os.environ.get("A8_CUDA_GRAPHS", "1") != "0"
 MAX_SHAPES = int(os.environ.get("A8_GRAPH_SHAPES", "2"))
@@ -48,7 +48,8 @@ class GraphedSegment:
         cached = self.__dict__.get("_pkey")
         if cached is None or cached[0] != probe:
             cached = self._pkey = (probe, tuple((p.data_ptr(), p.requires_grad) for p in params), params)
-        return (tuple((tuple(t.shape), t.dtype, t.requires_grad) for t in inputs), cached[1], torch.is_grad_enabled(), extra)
+        return (tuple((tuple(t.shape), t.dtype, t.requires_grad) for t in inputs), cached[1], torch.is_grad_enabled(), extra,
+                ops.grad_arena_serial())
 
     def run(self, fn, inputs, params, extra=(), clone_outputs=False):
         """fn(*inputs, *params) -> tensor or tuple of tensors, FUNCTIONAL in both (it must not reach parameters through
@@ -117,6 +118,9 @@ class GraphedSegment:
         # the autograd engine would try to make that stream wait on the capturing one, which CUDA forbids.
         alias = tuple(p.detach().requires_grad_(p.requires_grad) for p in params)
         n0 = lib.a8_launch_count()
+        # the warm-up iterations draw from the CUDA generator; put it back afterwards so that the step that captures sees
+        # the same random stream (Gumbel noise, dropout seeds) as the eager step or the replay it stands in for
+        rng = torch.cuda.get_rng_state(static_in[0].device)
         try:
             graphed = torch.cuda.make_graphed_callables(fn, static_in + alias, num_warmup_iters=WARMUP_ITERS,
                                                         allow_unused_input=True)
@@ -126,6 +130,8 @@ class GraphedSegment:
             self.failed.add(key)
             warnings.warn(f"audio8_b200: CUDA-graph capture of segment '{self.name}' failed, running eagerly: {e!r}")
             return None
+        finally:
+            torch.cuda.set_rng_state(rng, static_in[0].device)
         per_replay = (lib.a8_launch_count() - n0) // (WARMUP_ITERS + 1)
         ent = (graphed, int(per_replay))
         self.entries[key] = ent

@@ -66,6 +66,14 @@ def grad_arena_for_backward():
     return _ARENA[1]
 
 
+def grad_arena_serial():
+    """0 without an arena, else the serial number of the one this forward runs under.  The captured backward of a CUDA
+    graph writes to the addresses it saw at capture time (arena blocks, or the graph's own pool), so graphs.py keeps
+    one capture per arena and never replays one whose arena is gone"""
+    a = _ARENA[0]
+    return 0 if a is None else a.serial
+
+
 def grad_key(param):
     """arena key of a parameter (its storage address: the aliases a CUDA-graph capture runs on share it); None stays None"""
     return None if param is None else ("p", param.data_ptr())

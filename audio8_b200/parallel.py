@@ -34,6 +34,7 @@ class GradArena:
     under the conv stack's backward; the last region (5 % of the bytes) is reduced when backward ends."""
 
     LATE = ("feature_extractor", "layer_norm", "proj_to_input", "mask_emb")  # gradients that complete after the encoder's
+    _serial = 0
 
     def __init__(self, module, device):
         from .wav2vec2 import AudioTransformerEncoder
@@ -61,6 +62,8 @@ class GradArena:
                 self.early = off  # end of the region that is complete when the encoder's backward has been enqueued
         self.used = off
         self.buf = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        GradArena._serial += 1
+        self.serial = GradArena._serial  # part of the CUDA-graph keys: a graph captured under this arena writes into it
 
     def take(self, key, numel, zero=True):
         """the block planned for `key` (same storage on every step and every rank), zeroed unless zero=False; None when
