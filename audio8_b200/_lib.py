@@ -91,6 +91,7 @@ SIGNATURES.update({
     "a8_contrastive_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "a8_optim_grad_sqnorm": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "a8_optim_adamw": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _D, _D, _D, _D, _D, _D, _D, _I, _P, _P]),
+    "a8_allreduce_mc": (_I, [_P, _L, _L, _I, _I, _F, _I, _P]),
 })
 
 _lib = None

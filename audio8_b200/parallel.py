@@ -15,12 +15,50 @@ Interface kept: `.module`, `forward`, `no_sync()`, `state_dict()` with the `modu
 path for everything, because arena-backed gradients alias the next backward's output.
 """
 import contextlib
+import os
+import warnings
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
+
+
+class SwitchAllReduce:
+    """In-place averaging all-reduce of ranges of ONE fp32 buffer through the NVSwitch's multicast + in-fabric reduction
+    (csrc/allreduce_mc.cu).  The buffer is a symmetric-memory allocation that every rank of the group maps into one
+    multicast window (torch.distributed._symmetric_memory does the handle exchange: plumbing); the reduction itself is
+    this repo's kernel, bracketed by the symmetric-memory barrier, on a side stream so that it runs under backward.
+    Construction is a collective; it raises when the fabric offers no multicast (no NVSwitch, or NVLS disabled)."""
+
+    def __init__(self, numel, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.buf = symm.empty(numel, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.mc = int(self.hdl.multicast_ptr)
+        if not self.mc:
+            raise RuntimeError("symmetric memory without a multicast mapping")
+        self.buf.zero_()
+        self.stream = torch.cuda.Stream(device)
+        self.ctas = int(os.environ.get("A8_ALLREDUCE_CTAS", "0"))
+        self._lib = _lib.load()
+
+    def start(self, lo, hi):
+        """queue the all-reduce of elements [lo, hi) (multiples of 4) behind everything already on the current stream;
+        returns an object whose wait() makes the current stream wait for the result (the host never blocks)"""
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier(channel=0)  # every rank's gradients of this range are written
+            _lib.check(self._lib.a8_allreduce_mc(self.mc, lo, hi, self.rank, self.world, 1.0 / self.world, self.ctas,
+                                                 self.stream.cuda_stream), "a8_allreduce_mc")
+            self.hdl.barrier(channel=1)  # every rank's slice has landed everywhere
+        return self
+
+    def wait(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
 
 
 class GradArena:
@@ -36,7 +74,7 @@ class GradArena:
     LATE = ("feature_extractor", "layer_norm", "proj_to_input", "mask_emb")  # gradients that complete after the encoder's
     _serial = 0
 
-    def __init__(self, module, device):
+    def __init__(self, module, device, group=None):
         from .wav2vec2 import AudioTransformerEncoder
         plan, covered = [], set()
         for m in module.modules():
@@ -61,9 +99,31 @@ class GradArena:
             if part is mid:
                 self.early = off  # end of the region that is complete when the encoder's backward has been enqueued
         self.used = off
-        self.buf = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        size = (max(off, 1) + 63) & ~63
+        self.switch = self._switch(size, device, group)
+        self.buf = self.switch.buf if self.switch is not None else torch.zeros(size, dtype=torch.float32, device=device)
         GradArena._serial += 1
         self.serial = GradArena._serial  # part of the CUDA-graph keys: a graph captured under this arena writes into it
+
+    @staticmethod
+    def _switch(size, device, group):
+        """the NVSwitch all-reduce for this arena when every rank can have it (NCCL group on CUDA devices with a
+        multicast-capable fabric; A8_ALLREDUCE=nccl opts out), else None: NCCL's all-reduce on a plain buffer"""
+        if not (dist.is_initialized() and torch.device(device).type == "cuda" and dist.get_backend(group) == "nccl"
+                and dist.get_world_size(group) > 1 and os.environ.get("A8_ALLREDUCE", "switch") != "nccl"):
+            return None
+        sw, err = None, None
+        try:
+            sw = SwitchAllReduce(size, device, group)
+        except Exception as e:  # noqa: BLE001 - any failure means "not available here"; the ranks agree below
+            err = e
+        ok = torch.tensor([1 if sw is not None else 0], device=device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            return sw
+        if dist.get_rank(group) == 0:
+            warnings.warn(f"audio8_b200: NVSwitch multicast all-reduce unavailable ({err!r}); using NCCL")
+        return None
 
     def take(self, key, numel, zero=True):
         """the block planned for `key` (same storage on every step and every rank), zeroed unless zero=False; None when
@@ -115,7 +175,7 @@ class DataParallel(nn.Module):
         sync = self.require_sync and self.world > 1 and torch.is_grad_enabled()
         fresh = sync and all(p.grad is None for p in self._params)
         if fresh and self._arena is None and self._params:
-            self._arena = GradArena(self.module, self._params[0].device)
+            self._arena = GradArena(self.module, self._params[0].device, self.pg)
         if self._arena is not None:
             self._arena.on_first_take = None  # armed after forward: a CUDA-graph capture inside forward must not trigger it
         ops.set_grad_arena(self._arena if fresh else None, self._encoder_done if (fresh and self.overlap) else None)
@@ -153,13 +213,19 @@ class DataParallel(nn.Module):
         t.div_(self.world)
         return w if async_op else None
 
+    def _reduce_range(self, a, lo, hi):
+        """start the in-place average of arena elements [lo, hi); returns something with wait() (or None)"""
+        if a.switch is not None:
+            return a.switch.start(lo, (hi + 3) & ~3)
+        return self._all_reduce(a.buf[lo:hi], async_op=True)
+
     def _encoder_done(self):
         """called (on the autograd thread) when the gradient w.r.t. the encoder's input exists, i.e. every transformer
         layer has put its gradients into the arena: start reducing that region under the rest of backward"""
         a = self._arena
         if a is None or a.early == 0 or self._early is not None:
             return
-        self._early = self._all_reduce(a.buf[:a.early], async_op=True) or True
+        self._early = self._reduce_range(a, 0, a.early) or True
 
     def _finish(self):
         a = self._arena
@@ -168,7 +234,7 @@ class DataParallel(nn.Module):
         if arena_on:
             lo = a.early if self._early is not None else 0  # whatever has not been started yet: one call, in place
             if a.used > lo:
-                works.append(self._all_reduce(a.buf[lo:a.used], async_op=True))
+                works.append(self._reduce_range(a, lo, a.used))
             ptr0, ptr1 = a.buf.data_ptr(), a.buf.data_ptr() + a.buf.numel() * 4
         rest = []
         for p in self._params:

@@ -310,6 +310,18 @@ int a8_optim_adamw(const void* table, const int32_t* chunk_tensor, const int64_t
                    double beta2, double eps, double weight_decay, double bias_correction1, double bias_correction2_sqrt,
                    int32_t scale_grads_only, float* total_norm_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange through the NVSwitch (replaces DistributedDataParallel's bucketed NCCL all-reduce,
+ * /root/reference/audio8/pretrain.py:153, train.py:285): in-place all-reduce of fp32 elements [begin, end) of a buffer
+ * that every rank has mapped into one MULTICAST window (multicast_base = this rank's multicast address of element 0;
+ * audio8_b200/parallel.py gets it from torch's symmetric memory).  Rank r reduces its 1/world slice with
+ * multimem.ld_reduce, multiplies by `scale` (1/world: DDP's average) and multimem.st's it to every rank.
+ * begin / end are multiples of 4 elements.  ctas <= 0 picks the default.  The caller orders the launch between two
+ * cross-rank barriers on the same stream.  Fails (-1) without a multicast mapping.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_allreduce_mc(void* multicast_base, int64_t begin, int64_t end, int32_t rank, int32_t world, float scale,
+                    int32_t ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
