@@ -43,7 +43,9 @@ class SwitchAllReduce:
             raise RuntimeError("symmetric memory without a multicast mapping")
         self.buf.zero_()
         self.stream = torch.cuda.Stream(device)
-        self.ctas = int(os.environ.get("A8_ALLREDUCE_CTAS", "0"))
+        # CTAs that saturate the links (scripts/switch_probe.py: 24 at world 2, 8 at world 8 - every ld_reduce fans out to
+        # world GPUs inside the switch); fewer CTAs leave more SMs to the backward kernels running next to it
+        self.ctas = int(os.environ.get("A8_ALLREDUCE_CTAS", "0")) or (24 if self.world <= 2 else 16 if self.world <= 4 else 8)
         self._lib = _lib.load()
 
     def start(self, lo, hi):
@@ -142,8 +144,9 @@ class GradArena:
 
 
 class DataParallel(nn.Module):
-    def __init__(self, module, process_group=None, overlap=True):
+    def __init__(self, module, process_group=None, overlap=True, force_sync=False):
         super().__init__()
+        self.force_sync = force_sync  # diagnostics: run the arena + exchange machinery even with one rank
         self.module = module
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -172,7 +175,7 @@ class DataParallel(nn.Module):
             self.require_sync = old
 
     def forward(self, *args, **kwargs):
-        sync = self.require_sync and self.world > 1 and torch.is_grad_enabled()
+        sync = self.require_sync and (self.world > 1 or self.force_sync) and torch.is_grad_enabled()
         fresh = sync and all(p.grad is None for p in self._params)
         if fresh and self._arena is None and self._params:
             self._arena = GradArena(self.module, self._params[0].device, self.pg)

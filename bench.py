@@ -336,6 +336,11 @@ def _run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    force_dp = os.environ.get("A8_DP_FORCE") == "1"  # diagnostics: the data-parallel wrapper (arena, hooks) on one GPU
+    if force_dp and world == 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
     if world > 1:
         import datetime
         # a short collective timeout: a rank that falls out of step must fail in minutes, not hold the box for ten
@@ -362,7 +367,7 @@ def _run_ours(args):
     loss_fn = W.create_loss(N_VARS, N_NEG)
     net = model
     dp_name = "single process"
-    if world > 1:
+    if world > 1 or force_dp:
         if os.environ.get("A8_DP", "arena") == "ddp":
             # stock DistributedDataParallel as in pretrain.py:158; gradients as views of few large buckets
             net = torch.nn.parallel.DistributedDataParallel(
@@ -374,8 +379,8 @@ def _run_ours(args):
             # the package's data-parallel wrapper: gradients are written into one contiguous arena and all-reduced in
             # place under the rest of backward (audio8_b200/parallel.py); same interface as DDP
             from audio8_b200.parallel import DataParallel
-            net = DataParallel(model)
-            dp_name = "audio8_b200.parallel.DataParallel (gradient arena, in-place NCCL all-reduce)"
+            net = DataParallel(model, force_sync=force_dp)
+            dp_name = "audio8_b200.parallel.DataParallel (gradient arena, in-place all-reduce: NVSwitch multicast kernel, else NCCL)"
     B = B_CTC if ctc else B_PER_GPU
     lib = _lib.load()
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -607,7 +612,9 @@ def _run_ours(args):
             "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": bench_config(args, world, {
-                "data_parallel": dp_name,
+                "data_parallel": dp_name if getattr(net, "_arena", None) is None else (
+                    "audio8_b200.parallel.DataParallel (gradient arena, in-place all-reduce: "
+                    + ("NVSwitch multicast kernel a8_allreduce_mc)" if net._arena.switch is not None else "NCCL)")),
                 "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                 "launch": "the step is 4 CUDA-graph segments (front+mask, quantizer branch, encoder, loss), fwd and bwd; "
                           "masked-row lists padded to their worst-case length; host draws prefetched one step ahead",
