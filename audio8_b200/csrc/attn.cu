@@ -30,7 +30,9 @@ namespace {
 constexpr uint32_t TILE = 128 * 64 * 2;  // one [128 x 64] bf16 tile, 128B rows
 constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);  // f32 acc, bf16 A/B, M=128
 constexpr uint32_t IDESC_S = IDESC_BASE | ((uint32_t)(128 >> 3) << 17);                 // N=128, A and B K-major
+constexpr uint32_t IDESC_S64 = IDESC_BASE | ((uint32_t)(64 >> 3) << 17);                 // N=64, A and B K-major
 constexpr uint32_t IDESC_ACC = IDESC_BASE | ((uint32_t)(64 >> 3) << 17) | (1u << 16);   // N=64, B MN-major
+constexpr uint32_t HALF_TILE = 64 * 64 * 2;  // 64 rows of a [128 x 64] tile (a multiple of the 1024-byte swizzle atom)
 
 struct AttnArgs {
   int B, H, T, nblk;
@@ -87,7 +89,9 @@ __device__ __forceinline__ uint32_t valid_word(const unsigned char* keep, int T,
 __device__ __forceinline__ uint32_t bar_at(uint32_t bars, int i) { return bars + 8u * i; }
 
 // ================================================================================================ forward
-// TMEM columns: S [0,128)  P (packed bf16) [128,192)  O [192,256)
+// The key axis is walked in UNITS of 64 keys (half of a staged 128-key tile) with S and P double-buffered in TMEM: the
+// score MMA of unit u+1 runs while the softmax warps work on unit u and the PV MMA of unit u-1 is in flight.
+// TMEM columns: S stage s [64s, 64s+64)  P (packed bf16) stage s [128+32s, +32)  O [192,256)
 template <bool DROP>
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
@@ -96,8 +100,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + TILE, sV = base + 3 * TILE;
   const uint32_t bars = base + 5 * TILE;
-  enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, P_READY = 6, PV_DONE = 7 };
-  const uint32_t tmem_slot = bars + 64;
+  enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, P_READY = 7, PV_DONE = 9 };
+  const uint32_t tmem_slot = bars + 96;
   uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -105,6 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
+  const int U = 2 * nblk;
   const int qb = blockIdx.x % nblk;
   const int bh = blockIdx.x / nblk;
   const int h = bh % a.H, b = bh / a.H;
@@ -118,9 +123,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_at(bars, KV_FULL + i), 1);
         mbar_init(bar_at(bars, KV_EMPTY + i), 1);
+        mbar_init(bar_at(bars, S_FULL + i), 1);
+        mbar_init(bar_at(bars, P_READY + i), 128);
       }
-      mbar_init(bar_at(bars, S_FULL), 1);
-      mbar_init(bar_at(bars, P_READY), 128);
       mbar_init(bar_at(bars, PV_DONE), 1);
       mbar_fence_init();
     }
@@ -149,68 +154,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
-      auto issue_pv = [&](int j) {
-        const uint32_t v = sV + (j & 1) * TILE;
+      const uint32_t tO = tmem_base + 192;
+      auto issue_pv = [&](int u) {  // O += P(u) [128 x 64 keys, TMEM] * V(u) [64 keys x 64, read MN-major]
+        const uint32_t v = sV + ((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE;
+        const uint32_t tP = tmem_base + 128 + (u & 1) * 32;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_smem_desc(v + k * 2048, 8192, 1024), IDESC_ACC, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar_at(bars, KV_EMPTY + (j & 1)));
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(tO, tP + k * 8, umma_smem_desc(v + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+        if (u & 1) umma_commit(bar_at(bars, KV_EMPTY + ((u >> 1) & 1)));
         umma_commit(bar_at(bars, PV_DONE));
       };
       mbar_wait(bar_at(bars, Q_FULL), 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        mbar_wait(bar_at(bars, KV_FULL + st), (j >> 1) & 1);
-        if (j > 0) mbar_wait(bar_at(bars, P_READY), (j - 1) & 1);
+      for (int u = 0; u < U; ++u) {
+        const int j = u >> 1, s = u & 1;
+        if (s == 0) mbar_wait(bar_at(bars, KV_FULL + (j & 1)), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t kk = sK + st * TILE;
+        const uint32_t kk = sK + (j & 1) * TILE + s * HALF_TILE;
+        const uint32_t tS = tmem_base + s * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
-        umma_commit(bar_at(bars, S_FULL));
-        if (j > 0) issue_pv(j - 1);
+          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+        umma_commit(bar_at(bars, S_FULL + s));
+        if (u > 0) {
+          mbar_wait(bar_at(bars, P_READY + (s ^ 1)), ((u - 1) >> 1) & 1);
+          tc_fence_after();
+          issue_pv(u - 1);
+        }
       }
-      mbar_wait(bar_at(bars, P_READY), (nblk - 1) & 1);
+      mbar_wait(bar_at(bars, P_READY + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
       tc_fence_after();
-      issue_pv(nblk - 1);
+      issue_pv(U - 1);
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3;
     const int row = qb * 128 + quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr, tP = tS + 128, tO = tS + 192;
+    const uint32_t tmem_row = tmem_base + lane_addr, tO = tmem_row + 192;
     const float c = a.scale_log2;
     uint32_t dkey = 0;
     if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
     const uint32_t mul_e = drop_mul(row & 1, 0), mul_o = drop_mul(row & 1, 1);
     const uint32_t wrow = drop_w(dkey, row >> 1, 0);
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(bar_at(bars, S_FULL), j & 1);
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      const int s = u & 1;
+      const uint32_t tS = tmem_row + s * 64, tP = tmem_row + 128 + s * 32;
+      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // also: PV(u-2) has consumed this stage's P buffer
       tc_fence_after();
-      if (j > 0) {
-        mbar_wait(bar_at(bars, PV_DONE), (j - 1) & 1);  // P buffer free, O up to date
-        tc_fence_after();
-      }
       uint32_t r[32];
-      // The running max is only raised when a block would overflow the row sum (any exp2 above 2^64): the common case
-      // is ONE pass per block with no per-element max.  Block 0 and the rare overflow take the exact-max pass first.
-      bool need_max = (j == 0);
+      // The running max is only raised when a unit would overflow the row sum (any exp2 above 2^64): the common case
+      // is ONE pass per unit with no per-element max.  Unit 0 and the rare overflow take the exact-max pass first.
+      bool need_max = (u == 0);
       while (true) {
         if (need_max) {
           float mx = -INFINITY;
 #pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < 2; ++ch) {
             tmem_ld_32x32(tS + ch * 32, r);
             tmem_ld_wait();
-            const uint32_t word = sValid[j * 4 + ch];
+            const uint32_t word = sValid[u * 2 + ch];
 #pragma unroll
             for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((word >> i) & 1u) ? __uint_as_float(r[i]) : -INFINITY);
           }
           float m_new = fmaxf(m, mx * c);
           if (m_new == -INFINITY) m_new = 0.f;
-          if (j > 0) {  // rescale the row sum and the O accumulator (PV of the previous block has completed)
+          if (u > 0) {  // rescale the row sum and the O accumulator once every PV issued so far has completed
+            mbar_wait(bar_at(bars, PV_DONE), (u - 1) & 1);
+            tc_fence_after();
             const float f = ex2_approx(m - m_new);
             l *= f;
 #pragma unroll 1
@@ -227,11 +238,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
         }
         float lsum = 0.f;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           tmem_ld_32x32(tS + ch * 32, r);
           tmem_ld_wait();
-          const uint32_t word = sValid[j * 4 + ch];
-          const uint32_t wch = wrow + (uint32_t)((j * 128 + ch * 32) >> 1) * HM1;
+          const uint32_t word = sValid[u * 2 + ch];
+          const uint32_t wch = wrow + (uint32_t)((u * 64 + ch * 32) >> 1) * HM1;
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -261,9 +272,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_at(bars, P_READY));
+      mbar_arrive(bar_at(bars, P_READY + s));
     }
-    mbar_wait(bar_at(bars, PV_DONE), (nblk - 1) & 1);
+    mbar_wait(bar_at(bars, PV_DONE), (U - 1) & 1);
     tc_fence_after();
     const float inv = l > 0.f ? a.keep_scale / l : 0.f;
     uint32_t r[32];
@@ -296,8 +307,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
 }
 
 // ================================================================================================ backward: dQ
-// thread = query row; 8 math warps (two per lane quarter, each owns 64 of a block's 128 key columns)
-// TMEM columns: S [0,128)  dP [128,256)  dS packed [256,320)  dQ [320,384)
+// thread = query row; 8 math warps (two per lane quarter).  The key axis is walked in UNITS of 64 keys (half of a
+// staged 128-key tile); S / dP / dS are double-buffered in TMEM, so the score MMAs of unit u+1 run while the math warps
+// work on unit u and the dQ accumulation of unit u-1 is in flight.
+// TMEM columns: stage s: S [128s, 128s+64)  dP [128s+64, 128s+128);  dS packed [256+32s, +32);  dQ [320,384)
 template <bool DROP>
 __global__ void __launch_bounds__(384, 1)
 attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
@@ -307,8 +320,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sQ = base, sdO = base + TILE, sK = base + 2 * TILE, sV = base + 4 * TILE;
   const uint32_t bars = base + 6 * TILE;
-  enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, DS_READY = 6, DQ_DONE = 7 };
-  const uint32_t tmem_slot = bars + 64;
+  enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, DS_READY = 7, DQ_DONE = 9 };
+  const uint32_t tmem_slot = bars + 96;
   uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -316,6 +329,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
+  const int U = 2 * nblk;
   const int qb = blockIdx.x % nblk;
   const int bh = blockIdx.x / nblk;
   const int h = bh % a.H, b = bh / a.H;
@@ -332,9 +346,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_at(bars, KV_FULL + i), 1);
         mbar_init(bar_at(bars, KV_EMPTY + i), 1);
+        mbar_init(bar_at(bars, S_FULL + i), 1);
+        mbar_init(bar_at(bars, DS_READY + i), 256);
       }
-      mbar_init(bar_at(bars, S_FULL), 1);
-      mbar_init(bar_at(bars, DS_READY), 256);
       mbar_init(bar_at(bars, DQ_DONE), 1);
       mbar_fence_init();
     }
@@ -364,40 +378,46 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdS = tmem_base + 256, tdQ = tmem_base + 320;
-      auto issue_dq = [&](int j) {
-        const uint32_t kk = sK + (j & 1) * TILE;
+      const uint32_t tdQ = tmem_base + 320;
+      auto issue_dq = [&](int u) {  // dQ += dS(u) [128 x 64 keys, TMEM] * K(u) [64 keys x 64, read MN-major]
+        const uint32_t kk = sK + ((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE;
+        const uint32_t tdS = tmem_base + 256 + (u & 1) * 32;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16_ts(tdQ, tdS + k * 8, umma_smem_desc(kk + k * 2048, 8192, 1024), IDESC_ACC, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar_at(bars, KV_EMPTY + (j & 1)));
-        umma_commit(bar_at(bars, DQ_DONE));
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(tdQ, tdS + k * 8, umma_smem_desc(kk + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+        if (u & 1) umma_commit(bar_at(bars, KV_EMPTY + ((u >> 1) & 1)));
       };
       mbar_wait(bar_at(bars, QDO_FULL), 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        mbar_wait(bar_at(bars, KV_FULL + st), (j >> 1) & 1);
-        if (j > 0) mbar_wait(bar_at(bars, DS_READY), (j - 1) & 1);
+      for (int u = 0; u < U; ++u) {
+        const int j = u >> 1, s = u & 1;
+        if (s == 0) mbar_wait(bar_at(bars, KV_FULL + (j & 1)), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t kk = sK + st * TILE, vv = sV + st * TILE;
+        // stage s is free: the math warps' DS_READY of unit u-2 was awaited before dQ(u-2) was issued
+        const uint32_t kk = sK + (j & 1) * TILE + s * HALF_TILE, vv = sV + (j & 1) * TILE + s * HALF_TILE;
+        const uint32_t tS = tmem_base + s * 128, tdP = tS + 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tdP, umma_smem_desc(sdO + k * 32, 0, 1024), umma_smem_desc(vv + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
-        umma_commit(bar_at(bars, S_FULL));
-        if (j > 0) issue_dq(j - 1);
+          umma_bf16(tdP, umma_smem_desc(sdO + k * 32, 0, 1024), umma_smem_desc(vv + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+        umma_commit(bar_at(bars, S_FULL + s));
+        if (u > 0) {
+          mbar_wait(bar_at(bars, DS_READY + (s ^ 1)), ((u - 1) >> 1) & 1);
+          tc_fence_after();
+          issue_dq(u - 1);
+        }
       }
-      mbar_wait(bar_at(bars, DS_READY), (nblk - 1) & 1);
+      mbar_wait(bar_at(bars, DS_READY + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
       tc_fence_after();
-      issue_dq(nblk - 1);
+      issue_dq(U - 1);
+      umma_commit(bar_at(bars, DQ_DONE));
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3, half = (warp - 4) >> 2;
     const int row = qb * 128 + quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr, tdP = tS + 128, tdS = tS + 256, tdQ = tS + 320;
+    const uint32_t tmem_row = tmem_base + lane_addr, tdQ = tmem_row + 320;
     const float c = a.scale_log2;
     uint32_t dkey = 0;
     if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
@@ -423,46 +443,43 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
       nlse = -a.lse[(long long)bh * a.T + row];
       if (half == 0) a.delta[(long long)bh * a.T + row] = delta;
     }
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(bar_at(bars, S_FULL), j & 1);
-      tc_fence_after();
-      if (j > 0) {
-        mbar_wait(bar_at(bars, DQ_DONE), (j - 1) & 1);  // dS buffer consumed
-        tc_fence_after();
-      }
+    const float dscale = a.keep_scale * a.scale, ndelta = -delta * a.scale;
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = half * 64 + cc * 32;
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tS + col0, rs);
-        tmem_ld_32x32(tdP + col0, rp);
-        tmem_ld_wait();
-        const uint32_t word = sValid[j * 4 + (col0 >> 5)];
-        const uint32_t wch = wrow + (uint32_t)((j * 128 + col0) >> 1) * HM1;
-        uint32_t pk[16];
+    for (int u = 0; u < U; ++u) {
+      const int s = u & 1;
+      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // also: dQ(u-2) has consumed this stage's dS buffer
+      tc_fence_after();
+      const int col0 = u * 64 + half * 32;  // first key of this thread's 32 columns
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_row + s * 128 + half * 32, rs);
+      tmem_ld_32x32(tmem_row + s * 128 + 64 + half * 32, rp);
+      tmem_ld_wait();
+      const uint32_t word = sValid[col0 >> 5];
+      const uint32_t wch = wrow + (uint32_t)(col0 >> 1) * HM1;
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float t0 = fmaf(__uint_as_float(rs[i]), c, nlse), t1 = fmaf(__uint_as_float(rs[i + 1]), c, nlse);
-          if (word != 0xFFFFFFFFu) {
-            if (!((word >> i) & 1u)) t0 = -INFINITY;
-            if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
-          }
-          const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-          float d0 = __uint_as_float(rp[i]), d1 = __uint_as_float(rp[i + 1]);
-          if (DROP) {
-            const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
-            d0 = (drop_r(w, mul_e) >= a.thr) ? d0 * a.keep_scale : 0.f;
-            d1 = (drop_r(w, mul_o) >= a.thr) ? d1 * a.keep_scale : 0.f;
-          }
-          pk[i >> 1] = pack_bf16(p0 * (d0 - delta) * a.scale, p1 * (d1 - delta) * a.scale);
+      for (int i = 0; i < 32; i += 2) {
+        float t0 = fmaf(__uint_as_float(rs[i]), c, nlse), t1 = fmaf(__uint_as_float(rs[i + 1]), c, nlse);
+        if (word != 0xFFFFFFFFu) {
+          if (!((word >> i) & 1u)) t0 = -INFINITY;
+          if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
         }
-        tmem_st_32x16(tdS + (col0 >> 1), pk);
+        const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+        // dS = p * (keep * dP / (1-p_drop) - delta) * scale, with the scale folded into the two constants
+        float d0 = fmaf(__uint_as_float(rp[i]), dscale, ndelta), d1 = fmaf(__uint_as_float(rp[i + 1]), dscale, ndelta);
+        if (DROP) {
+          const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
+          d0 = (drop_r(w, mul_e) >= a.thr) ? d0 : ndelta;
+          d1 = (drop_r(w, mul_o) >= a.thr) ? d1 : ndelta;
+        }
+        pk[i >> 1] = pack_bf16(p0 * d0, p1 * d1);
       }
+      tmem_st_32x16(tmem_row + 256 + s * 32 + half * 16, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_at(bars, DS_READY));
+      mbar_arrive(bar_at(bars, DS_READY + s));
     }
-    mbar_wait(bar_at(bars, DQ_DONE), (nblk - 1) & 1);
+    mbar_wait(bar_at(bars, DQ_DONE), 0);
     tc_fence_after();
     uint32_t r[32];
     tmem_ld_32x32(tdQ + half * 32, r);
@@ -490,8 +507,9 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
 }
 
 // ================================================================================================ backward: dK, dV
-// thread = key row, walks over query blocks.  TMEM columns:
-//   S^T [0,128)  dP^T [128,256)  P^T packed [256,320)  dS^T packed [320,384)  dV [384,448)  dK [448,512)
+// thread = key row, walks over the queries in UNITS of 64 (half of a staged 128-query tile), S^T / dP^T / P^T / dS^T
+// double-buffered in TMEM like the dQ kernel.  TMEM columns:
+//   stage s: S^T [128s, +64)  dP^T [128s+64, +64);  P^T packed [256+32s, +32)  dS^T packed [320+32s, +32);  dV [384,448)  dK [448,512)
 template <bool DROP>
 __global__ void __launch_bounds__(384, 1)
 attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
@@ -501,8 +519,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sK = base, sV = base + TILE, sQ = base + 2 * TILE, sdO = base + 4 * TILE;
   const uint32_t bars = base + 6 * TILE;
-  enum { KV_FULL = 0, Q_FULL = 1, Q_EMPTY = 3, S_FULL = 5, PS_READY = 6, ACC_DONE = 7 };
-  const uint32_t tmem_slot = bars + 64;
+  enum { KV_FULL = 0, Q_FULL = 1, Q_EMPTY = 3, S_FULL = 5, PS_READY = 7, ACC_DONE = 9 };
+  const uint32_t tmem_slot = bars + 96;
   float* sStat = reinterpret_cast<float*>(smem_raw + (bars + 128 - raw));  // [2 stages][nlse 128 | delta 128]
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -510,6 +528,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
+  const int U = 2 * nblk;
   const int kb = blockIdx.x % nblk;
   const int bh = blockIdx.x / nblk;
   const int h = bh % a.H, b = bh / a.H;
@@ -526,9 +545,9 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_at(bars, Q_FULL + i), 1);
         mbar_init(bar_at(bars, Q_EMPTY + i), 1);
+        mbar_init(bar_at(bars, S_FULL + i), 1);
+        mbar_init(bar_at(bars, PS_READY + i), 256);
       }
-      mbar_init(bar_at(bars, S_FULL), 1);
-      mbar_init(bar_at(bars, PS_READY), 256);
       mbar_init(bar_at(bars, ACC_DONE), 1);
       mbar_fence_init();
     }
@@ -556,7 +575,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         const int q = i * 128 + t * 32 + lane;
         const bool ok = q < a.T;
         dst[t * 32 + lane] = ok ? -a.lse[(long long)bh * a.T + q] : -INFINITY;  // -inf: p == 0 for q >= T
-        dst[128 + t * 32 + lane] = ok ? a.delta[(long long)bh * a.T + q] : 0.f;
+        dst[128 + t * 32 + lane] = ok ? -a.delta[(long long)bh * a.T + q] * a.scale : 0.f;  // -delta * scale
       }
       __syncwarp();
       if (lane == 0) {
@@ -568,97 +587,103 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t tST = tmem_base, tdPT = tmem_base + 128, tPT = tmem_base + 256, tdST = tmem_base + 320,
-                     tdV = tmem_base + 384, tdK = tmem_base + 448;
-      auto issue_acc = [&](int i) {
-        const uint32_t qq = sQ + (i & 1) * TILE, dd = sdO + (i & 1) * TILE;
+      const uint32_t tdV = tmem_base + 384, tdK = tmem_base + 448;
+      auto issue_acc = [&](int u) {  // dV += P^T(u) dO(u),  dK += dS^T(u) Q(u): 64 queries of K extent each
+        const uint32_t off = ((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE;
+        const uint32_t qq = sQ + off, dd = sdO + off;
+        const uint32_t tPT = tmem_base + 256 + (u & 1) * 32, tdST = tmem_base + 320 + (u & 1) * 32;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16_ts(tdV, tPT + k * 8, umma_smem_desc(dd + k * 2048, 8192, 1024), IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(tdV, tPT + k * 8, umma_smem_desc(dd + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16_ts(tdK, tdST + k * 8, umma_smem_desc(qq + k * 2048, 8192, 1024), IDESC_ACC, (i > 0 || k > 0) ? 1u : 0u);
-        umma_commit(bar_at(bars, Q_EMPTY + (i & 1)));
-        umma_commit(bar_at(bars, ACC_DONE));
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ts(tdK, tdST + k * 8, umma_smem_desc(qq + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+        if (u & 1) umma_commit(bar_at(bars, Q_EMPTY + ((u >> 1) & 1)));
       };
       mbar_wait(bar_at(bars, KV_FULL), 0);
-      for (int i = 0; i < nblk; ++i) {
-        const int st = i & 1;
-        mbar_wait(bar_at(bars, Q_FULL + st), (i >> 1) & 1);
-        if (i > 0) mbar_wait(bar_at(bars, PS_READY), (i - 1) & 1);
+      for (int u = 0; u < U; ++u) {
+        const int i = u >> 1, s = u & 1;
+        if (s == 0) mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t qq = sQ + st * TILE, dd = sdO + st * TILE;
+        const uint32_t off = (i & 1) * TILE + s * HALF_TILE;
+        const uint32_t qq = sQ + off, dd = sdO + off;
+        const uint32_t tST = tmem_base + s * 128, tdPT = tST + 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tST, umma_smem_desc(sK + k * 32, 0, 1024), umma_smem_desc(qq + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
+          umma_bf16(tST, umma_smem_desc(sK + k * 32, 0, 1024), umma_smem_desc(qq + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tdPT, umma_smem_desc(sV + k * 32, 0, 1024), umma_smem_desc(dd + k * 32, 0, 1024), IDESC_S, k > 0 ? 1u : 0u);
-        umma_commit(bar_at(bars, S_FULL));
-        if (i > 0) issue_acc(i - 1);
+          umma_bf16(tdPT, umma_smem_desc(sV + k * 32, 0, 1024), umma_smem_desc(dd + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+        umma_commit(bar_at(bars, S_FULL + s));
+        if (u > 0) {
+          mbar_wait(bar_at(bars, PS_READY + (s ^ 1)), ((u - 1) >> 1) & 1);
+          tc_fence_after();
+          issue_acc(u - 1);
+        }
       }
-      mbar_wait(bar_at(bars, PS_READY), (nblk - 1) & 1);
+      mbar_wait(bar_at(bars, PS_READY + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
       tc_fence_after();
-      issue_acc(nblk - 1);
+      issue_acc(U - 1);
+      umma_commit(bar_at(bars, ACC_DONE));
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3, half = (warp - 4) >> 2;
     const int key = kb * 128 + quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tST = tmem_base + lane_addr, tdPT = tST + 128, tPT = tST + 256, tdST = tST + 320, tdV = tST + 384,
-                   tdK = tST + 448;
+    const uint32_t tmem_row = tmem_base + lane_addr, tdV = tmem_row + 384, tdK = tmem_row + 448;
     const bool valid_row = key < a.T && (a.key_keep == nullptr || a.key_keep[(long long)b * a.T + key] != 0);
-    const float c = valid_row ? a.scale_log2 : 0.f;
-    const float rowoff = valid_row ? 0.f : -INFINITY;
+    const float c = a.scale_log2;
+    const float dscale = a.keep_scale * a.scale;
     uint32_t dkey = 0;
     if (DROP) dkey = drop_key(a.seed + seed_base_ld(a.seed_src), bh);
     const uint32_t mul_qe = drop_mul(0, key & 1), mul_qo = drop_mul(1, key & 1);
     const uint32_t wkey = drop_w(dkey, 0, key >> 1);
-    for (int i = 0; i < nblk; ++i) {
-      mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);  // the block's statistics are staged (acquire)
-      mbar_wait(bar_at(bars, S_FULL), i & 1);
-      tc_fence_after();
-      if (i > 0) {
-        mbar_wait(bar_at(bars, ACC_DONE), (i - 1) & 1);  // P^T / dS^T buffers consumed
-        tc_fence_after();
-      }
-      const float* stat = sStat + (i & 1) * 256;
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = half * 64 + cc * 32;
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(tST + col0, rs);
-        tmem_ld_32x32(tdPT + col0, rp);
-        tmem_ld_wait();
-        const uint32_t wq0 = wkey + (uint32_t)((i * 128 + col0) >> 1) * (HM1 << 16);
-        uint32_t pp[16], pd[16];
+    for (int u = 0; u < U; ++u) {
+      const int i = u >> 1, s = u & 1;
+      if (s == 0) mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);  // the block's statistics are staged (acquire)
+      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // also: the accumulation of unit u-2 has consumed P^T / dS^T
+      tc_fence_after();
+      const int col0 = s * 64 + half * 32;  // first query (inside the 128-query tile) of this thread's 32 columns
+      const float* stat = sStat + (i & 1) * 256 + col0;
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem_row + s * 128 + half * 32, rs);
+      tmem_ld_32x32(tmem_row + s * 128 + 64 + half * 32, rp);
+      tmem_ld_wait();
+      const uint32_t wq0 = wkey + (uint32_t)((i * 128 + col0) >> 1) * (HM1 << 16);
+      uint32_t pp[16], pd[16];
+      if (valid_row) {
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float2 nl = *reinterpret_cast<const float2*>(stat + col0 + e);
-          const float2 dl = *reinterpret_cast<const float2*>(stat + 128 + col0 + e);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), c, nl.x + rowoff));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), c, nl.y + rowoff));
-          float d0 = __uint_as_float(rp[e]), d1 = __uint_as_float(rp[e + 1]);
+          const float2 nl = *reinterpret_cast<const float2*>(stat + e);
+          const float2 dl = *reinterpret_cast<const float2*>(stat + 128 + e);  // -delta * scale
+          const float p0 = ex2_approx(fmaf(__uint_as_float(rs[e]), c, nl.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), c, nl.y));
+          // dS = p * (keep * dP / (1-p_drop) - delta) * scale, with the scale folded into dscale and the staged -delta
+          float d0 = fmaf(__uint_as_float(rp[e]), dscale, dl.x), d1 = fmaf(__uint_as_float(rp[e + 1]), dscale, dl.y);
           float k0 = p0, k1 = p1;
           if (DROP) {
             const uint32_t w = drop_x(wq0 + (uint32_t)(e >> 1) * (HM1 << 16));  // patch ((q0 + e) / 2, key / 2)
             const bool keep0 = drop_r(w, mul_qe) >= a.thr, keep1 = drop_r(w, mul_qo) >= a.thr;
             k0 = keep0 ? p0 : 0.f;
             k1 = keep1 ? p1 : 0.f;
-            d0 = keep0 ? d0 * a.keep_scale : 0.f;
-            d1 = keep1 ? d1 * a.keep_scale : 0.f;
+            d0 = keep0 ? d0 : dl.x;
+            d1 = keep1 ? d1 : dl.y;
           }
           pp[e >> 1] = pack_bf16(k0, k1);
-          pd[e >> 1] = pack_bf16(p0 * (d0 - dl.x) * a.scale, p1 * (d1 - dl.y) * a.scale);
+          pd[e >> 1] = pack_bf16(p0 * d0, p1 * d1);
         }
-        tmem_st_32x16(tPT + (col0 >> 1), pp);
-        tmem_st_32x16(tdST + (col0 >> 1), pd);
+      } else {  // a key beyond T or masked out: its column of P and dS is zero
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pp[e] = pd[e] = 0u;
       }
+      tmem_st_32x16(tmem_row + 256 + s * 32 + half * 16, pp);
+      tmem_st_32x16(tmem_row + 320 + s * 32 + half * 16, pd);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_at(bars, PS_READY));
+      mbar_arrive(bar_at(bars, PS_READY + s));
     }
-    mbar_wait(bar_at(bars, ACC_DONE), (nblk - 1) & 1);
+    mbar_wait(bar_at(bars, ACC_DONE), 0);
     tc_fence_after();
     // half 0 writes dV (scaled by 1/(1-p)), half 1 writes dK
     const uint32_t src = half == 0 ? tdV : tdK;

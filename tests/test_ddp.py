@@ -344,7 +344,67 @@ def _nccl_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _switch_worker(rank, world, port, out_dir):
+    """csrc/allreduce_mc.cu (multimem.ld_reduce / multimem.st through the NVSwitch) against NCCL's averaging all-reduce on
+    the same data, over ragged ranges of one symmetric buffer"""
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from audio8_b200.parallel import SwitchAllReduce
+        n = 3_000_000 + 64
+        try:
+            sw = SwitchAllReduce(n, dev, None)
+        except Exception as e:  # no multicast on this box: nothing to test (the wrapper then uses NCCL)
+            with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+                f.write(f"skip {e!r}")
+            return
+        g = torch.Generator(device=dev).manual_seed(10 + rank)
+        src = torch.randn(n, device=dev, generator=g)
+        want = src.clone()
+        ranges = [(0, 4), (4, 1028), (1028, 2_000_000), (2_000_000, n)]
+        for lo, hi in ranges:
+            dist.all_reduce(want[lo:hi], op=dist.ReduceOp.AVG)
+        sw.buf.copy_(src)
+        torch.cuda.synchronize()
+        dist.barrier()
+        for lo, hi in ranges:
+            sw.start(lo, hi).wait()
+        torch.cuda.synchronize()
+        err = (sw.buf - want).abs().max().item()
+        assert err <= 1e-6 * want.abs().max().item() + 1e-7, f"rank {rank}: switch all-reduce differs from NCCL by {err:.3g}"
+        every = [torch.empty(n, device=dev) for _ in range(world)]
+        dist.all_gather(every, sw.buf)
+        assert all(torch.equal(e, every[0]) for e in every), "ranks hold different results"
+        # an empty range and a range that leaves the rest untouched
+        before = sw.buf.clone()
+        sw.start(128, 128).wait()
+        torch.cuda.synchronize()
+        assert torch.equal(before, sw.buf)
+        with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
 import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_switch_allreduce_matches_nccl_world2(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_switch_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    notes = [open(tmp_path / f"ok{r}").read() for r in range(world)]
+    if any(n.startswith("skip") for n in notes):
+        pytest.skip(f"no NVSwitch multicast here: {notes[0]}")
+    assert all(n == "ok" for n in notes)
 
 
 @pytest.mark.gpu
