@@ -100,7 +100,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + TILE, sV = base + 3 * TILE;
   const uint32_t bars = base + 5 * TILE;
-  enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, P_READY = 7, PV_DONE = 9 };
+  enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, P_READY = 7, PV_DONE = 9 };  // two of each but Q_FULL
   const uint32_t tmem_slot = bars + 96;
   uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -125,8 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
         mbar_init(bar_at(bars, KV_EMPTY + i), 1);
         mbar_init(bar_at(bars, S_FULL + i), 1);
         mbar_init(bar_at(bars, P_READY + i), 128);
+        mbar_init(bar_at(bars, PV_DONE + i), 1);
       }
-      mbar_init(bar_at(bars, PV_DONE), 1);
       mbar_fence_init();
     }
   } else if (warp == 2) {
@@ -162,12 +162,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
         for (int k = 0; k < 4; ++k)
           umma_bf16_ts(tO, tP + k * 8, umma_smem_desc(v + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
         if (u & 1) umma_commit(bar_at(bars, KV_EMPTY + ((u >> 1) & 1)));
-        umma_commit(bar_at(bars, PV_DONE));
+        umma_commit(bar_at(bars, PV_DONE + (u & 1)));
       };
       mbar_wait(bar_at(bars, Q_FULL), 0);
       for (int u = 0; u < U; ++u) {
         const int j = u >> 1, s = u & 1;
         if (s == 0) mbar_wait(bar_at(bars, KV_FULL + (j & 1)), (j >> 1) & 1);
+        // PV(u-2), the last reader of P stage s, must have COMPLETED before the scores of unit u are issued: the softmax
+        // warps take S_FULL(u) as the licence to overwrite that P buffer.  Relying on the S_FULL commit merely being
+        // issued after PV(u-2) gave timing-dependent errors on peaked score distributions (scripts/attn_accuracy.py).
+        // Waiting here costs this one thread ~100 cycles it has to spare; in the softmax warps it would cost every unit.
+        if (u >= 2) mbar_wait(bar_at(bars, PV_DONE + s), ((u - 2) >> 1) & 1);
         tc_fence_after();
         const uint32_t kk = sK + (j & 1) * TILE + s * HALF_TILE;
         const uint32_t tS = tmem_base + s * 64;
@@ -200,7 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
     for (int u = 0; u < U; ++u) {
       const int s = u & 1;
       const uint32_t tS = tmem_row + s * 64, tP = tmem_row + 128 + s * 32;
-      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // also: PV(u-2) has consumed this stage's P buffer
+      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // S(u) is only issued once PV(u-2) has released this P stage
       tc_fence_after();
       uint32_t r[32];
       // The running max is only raised when a unit would overflow the row sum (any exp2 above 2^64): the common case
@@ -220,7 +225,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
           float m_new = fmaxf(m, mx * c);
           if (m_new == -INFINITY) m_new = 0.f;
           if (u > 0) {  // rescale the row sum and the O accumulator once every PV issued so far has completed
-            mbar_wait(bar_at(bars, PV_DONE), (u - 1) & 1);
+            mbar_wait(bar_at(bars, PV_DONE + (s ^ 1)), ((u - 1) >> 1) & 1);
             tc_fence_after();
             const float f = ex2_approx(m - m_new);
             l *= f;
@@ -274,7 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
       tc_fence_before();
       mbar_arrive(bar_at(bars, P_READY + s));
     }
-    mbar_wait(bar_at(bars, PV_DONE), (U - 1) & 1);
+    mbar_wait(bar_at(bars, PV_DONE + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
     tc_fence_after();
     const float inv = l > 0.f ? a.keep_scale / l : 0.f;
     uint32_t r[32];
@@ -348,8 +353,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         mbar_init(bar_at(bars, KV_EMPTY + i), 1);
         mbar_init(bar_at(bars, S_FULL + i), 1);
         mbar_init(bar_at(bars, DS_READY + i), 256);
+        mbar_init(bar_at(bars, DQ_DONE + i), 1);
       }
-      mbar_init(bar_at(bars, DQ_DONE), 1);
       mbar_fence_init();
     }
   } else if (warp == 2) {
@@ -386,13 +391,19 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         for (int k = 0; k < 4; ++k)
           umma_bf16_ts(tdQ, tdS + k * 8, umma_smem_desc(kk + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
         if (u & 1) umma_commit(bar_at(bars, KV_EMPTY + ((u >> 1) & 1)));
+        umma_commit(bar_at(bars, DQ_DONE + (u & 1)));
       };
       mbar_wait(bar_at(bars, QDO_FULL), 0);
       for (int u = 0; u < U; ++u) {
         const int j = u >> 1, s = u & 1;
         if (s == 0) mbar_wait(bar_at(bars, KV_FULL + (j & 1)), (j >> 1) & 1);
+        // Stage s: the math warps' DS_READY of unit u-2 was awaited before dQ(u-2) was issued, and dQ(u-2) itself must
+        // have COMPLETED before the scores of unit u are issued: the math warps take S_FULL(u) as the licence to overwrite
+        // this stage's dS buffer.  (Relying on the S_FULL commit being issued after dQ(u-2) was not enough in the forward
+        // variant of this pipeline: timing-dependent errors, scripts/attn_accuracy.py.)  The wait costs this one thread
+        // ~100 cycles it has to spare; in the math warps it would cost every unit.
+        if (u >= 2) mbar_wait(bar_at(bars, DQ_DONE + s), ((u - 2) >> 1) & 1);
         tc_fence_after();
-        // stage s is free: the math warps' DS_READY of unit u-2 was awaited before dQ(u-2) was issued
         const uint32_t kk = sK + (j & 1) * TILE + s * HALF_TILE, vv = sV + (j & 1) * TILE + s * HALF_TILE;
         const uint32_t tS = tmem_base + s * 128, tdP = tS + 64;
 #pragma unroll
@@ -411,7 +422,6 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
       mbar_wait(bar_at(bars, DS_READY + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
       tc_fence_after();
       issue_dq(U - 1);
-      umma_commit(bar_at(bars, DQ_DONE));
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3, half = (warp - 4) >> 2;
@@ -447,7 +457,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
       const int s = u & 1;
-      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // also: dQ(u-2) has consumed this stage's dS buffer
+      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // S(u) is only issued once dQ(u-2) has released this dS stage
       tc_fence_after();
       const int col0 = u * 64 + half * 32;  // first key of this thread's 32 columns
       uint32_t rs[32], rp[32];
@@ -479,7 +489,7 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
       tc_fence_before();
       mbar_arrive(bar_at(bars, DS_READY + s));
     }
-    mbar_wait(bar_at(bars, DQ_DONE), 0);
+    mbar_wait(bar_at(bars, DQ_DONE + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
     tc_fence_after();
     uint32_t r[32];
     tmem_ld_32x32(tdQ + half * 32, r);
@@ -547,8 +557,8 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         mbar_init(bar_at(bars, Q_EMPTY + i), 1);
         mbar_init(bar_at(bars, S_FULL + i), 1);
         mbar_init(bar_at(bars, PS_READY + i), 256);
+        mbar_init(bar_at(bars, ACC_DONE + i), 1);
       }
-      mbar_init(bar_at(bars, ACC_DONE), 1);
       mbar_fence_init();
     }
   } else if (warp == 2) {
@@ -599,11 +609,13 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         for (int k = 0; k < 4; ++k)
           umma_bf16_ts(tdK, tdST + k * 8, umma_smem_desc(qq + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
         if (u & 1) umma_commit(bar_at(bars, Q_EMPTY + ((u >> 1) & 1)));
+        umma_commit(bar_at(bars, ACC_DONE + (u & 1)));
       };
       mbar_wait(bar_at(bars, KV_FULL), 0);
       for (int u = 0; u < U; ++u) {
         const int i = u >> 1, s = u & 1;
         if (s == 0) mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);
+        if (u >= 2) mbar_wait(bar_at(bars, ACC_DONE + s), ((u - 2) >> 1) & 1);  // as in the dQ kernel: acc(u-2) has completed
         tc_fence_after();
         const uint32_t off = (i & 1) * TILE + s * HALF_TILE;
         const uint32_t qq = sQ + off, dd = sdO + off;
@@ -624,7 +636,6 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_wait(bar_at(bars, PS_READY + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
       tc_fence_after();
       issue_acc(U - 1);
-      umma_commit(bar_at(bars, ACC_DONE));
     }
   } else if (warp >= 4) {
     const int quarter = warp & 3, half = (warp - 4) >> 2;
@@ -642,7 +653,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     for (int u = 0; u < U; ++u) {
       const int i = u >> 1, s = u & 1;
       if (s == 0) mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);  // the block's statistics are staged (acquire)
-      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // also: the accumulation of unit u-2 has consumed P^T / dS^T
+      mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // S(u) is only issued once acc(u-2) has released P^T / dS^T
       tc_fence_after();
       const int col0 = s * 64 + half * 32;  // first query (inside the 128-query tile) of this thread's 32 columns
       const float* stat = sStat + (i & 1) * 256 + col0;
@@ -683,7 +694,7 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       tc_fence_before();
       mbar_arrive(bar_at(bars, PS_READY + s));
     }
-    mbar_wait(bar_at(bars, ACC_DONE), 0);
+    mbar_wait(bar_at(bars, ACC_DONE + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
     tc_fence_after();
     // half 0 writes dV (scaled by 1/(1-p)), half 1 writes dK
     const uint32_t src = half == 0 ? tdV : tdK;
