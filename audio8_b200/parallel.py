@@ -110,9 +110,15 @@ class GradArena:
     @staticmethod
     def _switch(size, device, group):
         """the NVSwitch all-reduce for this arena when every rank can have it (NCCL group on CUDA devices with a
-        multicast-capable fabric; A8_ALLREDUCE=nccl opts out), else None: NCCL's all-reduce on a plain buffer"""
+        multicast-capable fabric, world size >= 4; A8_ALLREDUCE=nccl / switch force one or the other), else None: NCCL's
+        all-reduce on a plain buffer"""
         if not (dist.is_initialized() and torch.device(device).type == "cuda" and dist.get_backend(group) == "nccl"
-                and dist.get_world_size(group) > 1 and os.environ.get("A8_ALLREDUCE", "switch") != "nccl"):
+                and dist.get_world_size(group) > 1):
+            return None
+        # measured (profiles/r02_dp.md): at world 2 a ring moves as many bytes as the switch path and NCCL's kernel is
+        # the faster one (698 vs 902 us for 362 MB); from world 4 on the in-switch reduction wins (776 vs 1022 us at 8)
+        mode = os.environ.get("A8_ALLREDUCE", "auto")
+        if mode == "nccl" or (mode == "auto" and dist.get_world_size(group) < 4):
             return None
         sw, err = None, None
         try:

@@ -301,7 +301,7 @@ def _layerdrop_body(rank, world, dev, cuda):
                 assert err <= tol * scale + 1e-7, f"rank {rank} step {rep} grad {k}: {err:.3g} vs scale {scale:.3g}"
 
 
-def _nccl_worker(rank, world, port, out_dir):
+def _nccl_worker(rank, world, port, out_dir, exchange="nccl"):
     """the CUDA kernels + NCCL: audio8_b200.parallel.DataParallel against the mean of the per-rank gradients computed
     without any wrapper, over 4 steps (eager, CUDA-graph capture, replays)"""
     for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
@@ -309,6 +309,7 @@ def _nccl_worker(rank, world, port, out_dir):
             sys.path.insert(0, p)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["A8_ALLREDUCE"] = exchange  # "switch": the multicast kernel even at world size 2 (NCCL when unavailable)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -408,11 +409,12 @@ def test_switch_allreduce_matches_nccl_world2(tmp_path):
 
 
 @pytest.mark.gpu
-def test_arena_data_parallel_nccl_world2(tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "switch"])
+def test_arena_data_parallel_nccl_world2(tmp_path, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     world = 2
-    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path), exchange), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
 
