@@ -88,6 +88,59 @@ __device__ __forceinline__ uint32_t valid_word(const unsigned char* keep, int T,
 // shared prologue: barrier ids are kernel specific; TMEM allocation by warp 2
 __device__ __forceinline__ uint32_t bar_at(uint32_t bars, int i) { return bars + 8u * i; }
 
+// ---------------------------------------------------------------------------------------------- per-chunk math
+// 32 score columns of one row -> 16 packed bf16 probability pairs; returns the row-sum contribution.  MASKED is the
+// rare case (a chunk that contains padded or masked-out keys: the last key block, ragged batches): the common chunk
+// carries no per-element validity test at all (as `if (word != ~0u)` inside the loop the compiler predicated the three
+// mask instructions per element instead of branching around them: 20 % of the kernel's issue slots).
+template <bool DROP, bool MASKED>
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&r)[32], uint32_t (&pk)[16], float c, float m,
+                                               uint32_t word, uint32_t wch, uint32_t mul_e, uint32_t mul_o,
+                                               uint32_t thr) {
+  float lsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float t0 = fmaf(__uint_as_float(r[i]), c, -m), t1 = fmaf(__uint_as_float(r[i + 1]), c, -m);
+    if (MASKED) {
+      if (!((word >> i) & 1u)) t0 = -INFINITY;
+      if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
+    }
+    float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+    lsum += p0 + p1;
+    if (DROP) {
+      const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
+      p0 = (drop_r(w, mul_e) >= thr) ? p0 : 0.f;
+      p1 = (drop_r(w, mul_o) >= thr) ? p1 : 0.f;
+    }
+    pk[i >> 1] = pack_bf16(p0, p1);
+  }
+  return lsum;
+}
+
+// 32 columns of S and dP of one query row -> 16 packed bf16 dS pairs (dQ kernel)
+template <bool DROP, bool MASKED>
+__device__ __forceinline__ void ds_chunk(const uint32_t (&rs)[32], const uint32_t (&rp)[32], uint32_t (&pk)[16],
+                                         float c, float nlse, float dscale, float ndelta, uint32_t word, uint32_t wch,
+                                         uint32_t mul_e, uint32_t mul_o, uint32_t thr) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float t0 = fmaf(__uint_as_float(rs[i]), c, nlse), t1 = fmaf(__uint_as_float(rs[i + 1]), c, nlse);
+    if (MASKED) {
+      if (!((word >> i) & 1u)) t0 = -INFINITY;
+      if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
+    }
+    const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+    // dS = p * (keep * dP / (1-p_drop) - delta) * scale, with the scale folded into the two constants
+    float d0 = fmaf(__uint_as_float(rp[i]), dscale, ndelta), d1 = fmaf(__uint_as_float(rp[i + 1]), dscale, ndelta);
+    if (DROP) {
+      const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
+      d0 = (drop_r(w, mul_e) >= thr) ? d0 : ndelta;
+      d1 = (drop_r(w, mul_o) >= thr) ? d1 : ndelta;
+    }
+    pk[i >> 1] = pack_bf16(p0 * d0, p1 * d1);
+  }
+}
+
 // ================================================================================================ forward
 // The key axis is walked in UNITS of 64 keys (half of a staged 128-key tile) with S and P double-buffered in TMEM: the
 // score MMA of unit u+1 runs while the softmax warps work on unit u and the PV MMA of unit u-1 is in flight.
@@ -249,22 +302,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
           const uint32_t word = sValid[u * 2 + ch];
           const uint32_t wch = wrow + (uint32_t)((u * 64 + ch * 32) >> 1) * HM1;
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0 = fmaf(__uint_as_float(r[i]), c, -m), t1 = fmaf(__uint_as_float(r[i + 1]), c, -m);
-            if (word != 0xFFFFFFFFu) {
-              if (!((word >> i) & 1u)) t0 = -INFINITY;
-              if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
-            }
-            float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-            lsum += p0 + p1;
-            if (DROP) {
-              const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
-              p0 = (drop_r(w, mul_e) >= a.thr) ? p0 : 0.f;
-              p1 = (drop_r(w, mul_o) >= a.thr) ? p1 : 0.f;
-            }
-            pk[i >> 1] = pack_bf16(p0, p1);
-          }
+          if (word == 0xFFFFFFFFu) lsum += softmax_chunk<DROP, false>(r, pk, c, m, word, wch, mul_e, mul_o, a.thr);
+          else lsum += softmax_chunk<DROP, true>(r, pk, c, m, word, wch, mul_e, mul_o, a.thr);
           tmem_st_32x16(tP + ch * 16, pk);
         }
         if (!need_max && __any_sync(0xffffffffu, !(lsum < 1.8e19f))) {
@@ -467,23 +506,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
       const uint32_t word = sValid[col0 >> 5];
       const uint32_t wch = wrow + (uint32_t)(col0 >> 1) * HM1;
       uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float t0 = fmaf(__uint_as_float(rs[i]), c, nlse), t1 = fmaf(__uint_as_float(rs[i + 1]), c, nlse);
-        if (word != 0xFFFFFFFFu) {
-          if (!((word >> i) & 1u)) t0 = -INFINITY;
-          if (!((word >> (i + 1)) & 1u)) t1 = -INFINITY;
-        }
-        const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-        // dS = p * (keep * dP / (1-p_drop) - delta) * scale, with the scale folded into the two constants
-        float d0 = fmaf(__uint_as_float(rp[i]), dscale, ndelta), d1 = fmaf(__uint_as_float(rp[i + 1]), dscale, ndelta);
-        if (DROP) {
-          const uint32_t w = drop_x(wch + (uint32_t)(i >> 1) * HM1);
-          d0 = (drop_r(w, mul_e) >= a.thr) ? d0 : ndelta;
-          d1 = (drop_r(w, mul_o) >= a.thr) ? d1 : ndelta;
-        }
-        pk[i >> 1] = pack_bf16(p0 * d0, p1 * d1);
-      }
+      if (word == 0xFFFFFFFFu) ds_chunk<DROP, false>(rs, rp, pk, c, nlse, dscale, ndelta, word, wch, mul_e, mul_o, a.thr);
+      else ds_chunk<DROP, true>(rs, rp, pk, c, nlse, dscale, ndelta, word, wch, mul_e, mul_o, a.thr);
       tmem_st_32x16(tmem_row + 256 + s * 32 + half * 16, pk);
       tmem_st_wait();
       tc_fence_before();

@@ -182,6 +182,105 @@ __global__ void __launch_bounds__(256) conv0_kernel(const Conv0Args a) {
   }
 }
 
+// The model's layer 0 (k = 10, stride 5), four rows per step: the 25 window samples of rows r..r+3 are contiguous and
+// 16-byte aligned in the staged waveform (row r starts at float 5 r, r a multiple of 4), so they arrive as 7 LDS.128
+// instead of 40 scalar shared loads (the scalar version kept the LSU as busy as the FMA pipe: 5 broadcast loads per
+// output), and the normalisation is folded into the taps (forward: w * rstd * gamma, start value = the shift;
+// backward: w * rstd, start value -mean * rstd, which yields xhat directly).
+template <bool BWD>
+__global__ void __launch_bounds__(256) conv0_k10s5_kernel(const Conv0Args a) {
+  constexpr int K = 10, S = 5;
+  __shared__ __align__(16) float xs[TILE_T * S + 16];
+  const int b = blockIdx.y;
+  const int c0 = threadIdx.x * 2;
+  const bool active = c0 < a.C;
+  float w[2][K], init[2], gm[2], bt[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = min(c0 + i, a.C - 1);
+    const float mu = a.mean[b * a.C + c], rs = a.rstd[b * a.C + c];
+    gm[i] = a.gamma[c];
+    bt[i] = a.beta[c];
+    const float sc = BWD ? rs : rs * gm[i];
+    init[i] = BWD ? -mu * rs : bt[i] - mu * sc;
+#pragma unroll
+    for (int j = 0; j < K; ++j) w[i][j] = a.w[c * K + j] * sc;
+  }
+  float acc1[2] = {0.f, 0.f}, acc2[2] = {0.f, 0.f}, accx[2][K];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < K; ++j) accx[i][j] = 0.f;
+
+  const float* xb = a.x + (long long)b * a.L;
+  const int t_begin = blockIdx.x * a.rows_per_cta;
+  const int t_end = min(a.L0, t_begin + a.rows_per_cta);
+  for (int tt = t_begin; tt < t_end; tt += TILE_T) {
+    const int nrows = min(TILE_T, t_end - tt);
+    const int nx = (nrows - 1) * S + K;
+    __syncthreads();
+    for (int i = threadIdx.x; i < TILE_T * S + 16; i += blockDim.x) xs[i] = i < nx ? xb[(long long)tt * S + i] : 0.f;
+    __syncthreads();
+    if (!active) continue;
+    const long long off0 = ((long long)b * a.L0 + tt) * a.C + c0;
+#pragma unroll 1
+    for (int r = 0; r < nrows; r += 4) {
+      float xv[28];
+      const float4* src = reinterpret_cast<const float4*>(xs + r * S);
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const float4 v = src[q];
+        xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+      }
+      uint32_t dr[4];
+      if (BWD) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+          dr[rr] = (r + rr < nrows) ? __ldg(reinterpret_cast<const uint32_t*>(a.da + off0 + (long long)(r + rr) * a.C)) : 0u;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        float z[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float t = init[i];
+#pragma unroll
+          for (int j = 0; j < K; ++j) t = fmaf(w[i][j], xv[rr * S + j], t);
+          z[i] = t;
+        }
+        if (!BWD) {
+          if (r + rr < nrows)
+            *reinterpret_cast<uint32_t*>(a.y + off0 + (long long)(r + rr) * a.C) = pack_bf16(gelu_fast(z[0]), gelu_fast(z[1]));
+        } else {
+          const float2 d = unpack_bf16(dr[rr]);  // zero beyond the tile's last row: contributes nothing
+          const float dd[2] = {d.x, d.y};
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float xh = z[i];
+            const float dy = dd[i] * gelu_grad_fast(fmaf(xh, gm[i], bt[i]));
+            acc1[i] += dy;
+            acc2[i] = fmaf(dy, xh, acc2[i]);
+#pragma unroll
+            for (int j = 0; j < K; ++j) accx[i][j] = fmaf(dy, xv[rr * S + j], accx[i][j]);
+          }
+        }
+      }
+    }
+  }
+  if (BWD && active) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (c0 + i < a.C) {
+        float* dst = a.acc + ((long long)b * a.C + c0 + i) * 12;
+#pragma unroll
+        for (int j = 0; j < K; ++j) atomicAdd(dst + j, accx[i][j]);
+        atomicAdd(dst + 10, acc1[i]);
+        atomicAdd(dst + 11, acc2[i]);
+      }
+    }
+  }
+}
+
 // dW, dgamma, dbeta from the single backward pass and the forward's window moments.  With dz = sc (dy - mean(dy) -
 // xhat mean(dy xhat)) and xhat linear in the window,  sum_t dz x_j  needs only  sum_t dy x_j  and the moments:
 //   sum_t xhat x_j = rstd ( w . R[:,j] - mean m_j )
@@ -218,8 +317,19 @@ __global__ void conv0_bwd_finalize_kernel(const float* acc, const double* mom, c
   dbeta[c] = (float)db;
 }
 
-int rows_per_cta(int L0, int B) {
-  int per_batch = (148 * 3) / (B > 0 ? B : 1);
+// one wave: the grid is sized to the number of CTAs that are resident at once (registers decide: 3 per SM for the
+// forward kernels, 2 for the k10/s5 backward; a grid sized for 3 with only 2 resident ran two rounds, +33 %)
+template <typename K>
+int resident_ctas(K kern, int threads) {
+  int per_sm = 0, dev = 0, sms = 148;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * (sms > 0 ? sms : 148);
+}
+
+int rows_per_cta(int L0, int B, int ctas = 148 * 3) {
+  int per_batch = ctas / (B > 0 ? B : 1);
   if (per_batch < 1) per_batch = 1;
   int rows = cdiv(L0, per_batch);
   rows = cdiv(rows, TILE_T) * TILE_T;
@@ -259,9 +369,16 @@ extern "C" int a8_conv0_fwd(const float* x, int32_t B, int64_t L, const float* w
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (conv0_check(C, k, s)) return -1;
   const int L0 = (int)((L - k) / s + 1);
-  Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B), w, gamma, beta, mean, rstd, (__nv_bfloat16*)y, nullptr, nullptr};
+  const bool fast = (k == 10 && s == 5);
+  static int ctas[2] = {0, 0}, ctas_c[2] = {0, 0};
+  if (ctas_c[fast] != C) {
+    ctas[fast] = fast ? resident_ctas(conv0_k10s5_kernel<false>, C / 2) : resident_ctas(conv0_kernel<false>, C / 2);
+    ctas_c[fast] = C;
+  }
+  Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B, ctas[fast]), w, gamma, beta, mean, rstd, (__nv_bfloat16*)y, nullptr, nullptr};
   dim3 grid(cdiv(L0, a.rows_per_cta), B);
-  conv0_kernel<false><<<grid, C / 2, 0, stream>>>(a);
+  if (k == 10 && s == 5) conv0_k10s5_kernel<false><<<grid, C / 2, 0, stream>>>(a);
+  else conv0_kernel<false><<<grid, C / 2, 0, stream>>>(a);
   return check_launch("conv0_kernel<fwd>");
 }
 
@@ -272,11 +389,18 @@ extern "C" int a8_conv0_bwd(const float* x, int32_t B, int64_t L, const float* w
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (conv0_check(C, k, s)) return -1;
   const int L0 = (int)((L - k) / s + 1);
-  Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B), w, gamma, beta, mean, rstd, nullptr,
+  const bool fast = (k == 10 && s == 5);
+  static int ctas[2] = {0, 0}, ctas_c[2] = {0, 0};
+  if (ctas_c[fast] != C) {
+    ctas[fast] = fast ? resident_ctas(conv0_k10s5_kernel<true>, C / 2) : resident_ctas(conv0_kernel<true>, C / 2);
+    ctas_c[fast] = C;
+  }
+  Conv0Args a{x, L, L0, k, s, C, rows_per_cta(L0, B, ctas[fast]), w, gamma, beta, mean, rstd, nullptr,
               (const __nv_bfloat16*)da, acc};
   dim3 grid(cdiv(L0, a.rows_per_cta), B);
   A8_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * 12 * B * C, stream));
-  conv0_kernel<true><<<grid, C / 2, 0, stream>>>(a);
+  if (k == 10 && s == 5) conv0_k10s5_kernel<true><<<grid, C / 2, 0, stream>>>(a);
+  else conv0_kernel<true><<<grid, C / 2, 0, stream>>>(a);
   int rc = check_launch("conv0_kernel<bwd>");
   if (rc) return rc;
   conv0_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(acc, moments, w, gamma, mean, rstd, B, C, k, L0, dw,

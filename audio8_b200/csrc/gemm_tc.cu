@@ -86,6 +86,8 @@ int num_sms() {
 }
 
 
+int launch_window(const a8_gemm_t& g, KParams& kp, int k16, cudaStream_t stream);  // gemm_tc_window.cu
+
 void copy_coef(OpCoef& o, const a8_operand_t& v) {
   for (int d = 0; d < 4; ++d) {
     o.base[d] = v.base[d]; o.ck[d] = v.ck[d]; o.cb[d] = v.cb[d];
@@ -127,7 +129,10 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   KParams kp;
   memset(&kp, 0, sizeof(kp));
   kp.M = g.M; kp.N = g.N;
-  const int cl = (g.reserved == 2) ? 2 : 1;  // a8_gemm_t.reserved doubles as the cluster-size request (0/1 = off)
+  // a8_gemm_t.reserved doubles as the launch-shape request: low byte 0/1 = plain, 2 = CTA pairs (cta_group::2),
+  // 3 = tap-window kernel (gemm_tc_window.cu; bits 8..15 = 16-wide k-steps multiplied per tap, 0 = all four)
+  const int mode = g.reserved & 0xFF;
+  const int cl = (mode == 2) ? 2 : 1;
   kp.m_tiles = cdiv(cdiv(g.M, BLOCK_M), cl);
   kp.n_tiles = cdiv(g.N, bn);
   kp.lo_count = g.lo_count > 0 ? g.lo_count : 1;
@@ -142,6 +147,8 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   const long long tiles = (long long)kp.m_tiles * kp.n_tiles * kp.lo_count * kp.hi_count * split;
   A8_REQUIRE(tiles < (1ll << 30), "gemm: too many tiles");
   kp.total_tiles = (int)tiles;
+
+  if (mode == A8_GEMM_TAP_WINDOW) return launch_window(g, kp, (g.reserved >> 8) & 0xFF, stream);
 
   CUtensorMap ma, mb;
   int rc;

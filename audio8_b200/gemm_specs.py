@@ -249,6 +249,14 @@ def conv_wgrad(dz, x, dwk, k, s):
 
 
 # ------------------------------------------------------------------------------------------------ pos conv
+def _tap_window(k, cg):
+    """16-wide k-steps per tap for the tap-window kernel (csrc/gemm_tc_window.cu), or None when the shape is outside
+    what it takes (then the plain kernel runs the same descriptor).  FORCE["window"] = False: A/B measurements."""
+    if not FORCE.get("window", True) or k % 8 != 0 or not 16 <= k <= 128 or cg > 64:
+        return None
+    return cdiv(cg, 16)
+
+
 @cached_spec
 def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
     """out = x + gelu(conv_same(x) + bias) for the grouped positional conv (z_out: gelu' of the pre-activation).  x/out [B,T,D]; wp [D, k*64] packed
@@ -262,7 +270,7 @@ def posconv_fwd(x, wp, out, bias, groups, k, pad_left, z_out=None):
     return _with_flops(GemmSpec(a, b, T, cg, k, out, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
                     c_stride_lo=cg, c_stride_hi=T * D, act=ACT_GELU_DZ if z_out is not None else ACT_GELU, z_out=z_out,
                     aux=x, aux_mode=AUX_ADD,
-                    bias=bias, bias_stride_lo=cg), 2 * B * T * D * cg * k)
+                    bias=bias, bias_stride_lo=cg, window_k16=_tap_window(k, cg)), 2 * B * T * D * cg * k)
 
 
 @cached_spec
@@ -274,7 +282,8 @@ def posconv_dgrad(dz, wpt, dx, groups, k, pad_left, aux=None):
            cl=(cg, 0, 0, 0), ch=(0, 0, 1, 0))
     b = Op(wpt, (k * 64, D), (k * 64,), MAJOR_K, cb=(64, 0, 0, 0), cr=(0, 1, 0, 0), cl=(0, cg, 0, 0))
     return _with_flops(GemmSpec(a, b, T, cg, k, dx, D, OUT_BF16, lo_count=groups, hi_count=B, k_inner=1, block_n=64,
-                    c_stride_lo=cg, c_stride_hi=T * D, aux=aux, aux_mode=AUX_ADD if aux is not None else AUX_NONE), 2 * B * T * D * cg * k)
+                    c_stride_lo=cg, c_stride_hi=T * D, aux=aux, aux_mode=AUX_ADD if aux is not None else AUX_NONE,
+                    window_k16=_tap_window(k, cg)), 2 * B * T * D * cg * k)
 
 
 @cached_spec
@@ -286,8 +295,9 @@ def posconv_wgrad(dz, x, dwp, groups, k, pad_left):
            cr=(0, 1, 0, 0), cl=(cg, 0, 0, 0))
     b = Op(dz, (D, T, B), (D, T * D), MAJOR_MN, ck=(0, 64, 0, 0), cb=(0, 0, 1, 0), cl=(cg, 0, 0, 0))
     ki = cdiv(T, 64)
+    win = 4 if (FORCE.get("window", True) and k % 16 == 0 and 16 <= k <= 128) else None  # gemm_tc_window.cu, wgrad form
     return _with_flops(GemmSpec(a, b, k * 64, 64, B * ki, dwp, 64, OUT_F32, lo_count=groups, k_inner=ki, block_n=64,
-                    c_stride_lo=k * 64 * 64), 2 * B * T * D * cg * k)
+                    c_stride_lo=k * 64 * 64, window_k16=win), 2 * B * T * D * cg * k)
 
 
 # ------------------------------------------------------------------------------------------------ attention

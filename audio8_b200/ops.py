@@ -37,7 +37,7 @@ class GemmSpec:
 
     def __init__(self, a, b, M, N, k_blocks, c, ldc, c_dtype=OUT_BF16, lo_count=1, hi_count=1, k_inner=None,
                  split_k=1, block_n=0, c_offset=0, c_stride_lo=0, c_stride_hi=0, act=ACT_NONE, z_out=None,
-                 aux=None, aux_mode=AUX_NONE, bias=None, bias_stride_lo=0, alpha=1.0, cluster=1):
+                 aux=None, aux_mode=AUX_NONE, bias=None, bias_stride_lo=0, alpha=1.0, cluster=1, window_k16=None):
         self.a, self.b, self.M, self.N, self.k_blocks = a, b, M, N, k_blocks
         self.k_inner = k_inner if k_inner is not None else k_blocks
         self.c, self.ldc, self.c_dtype, self.c_offset = c, ldc, c_dtype, c_offset
@@ -46,6 +46,8 @@ class GemmSpec:
         self.act, self.z_out, self.aux, self.aux_mode = act, z_out, aux, aux_mode
         self.bias, self.bias_stride_lo, self.alpha = bias, bias_stride_lo, alpha
         self.cluster = cluster  # 2: CTA pair per 256 x BN tile (cta_group::2); block_n 128 / 256 (192 with a K-major B)
+        # not None: tap-window kernel (A8_GEMM_TAP_WINDOW), the value = 16-wide k-steps per tap that hold non-zero weights
+        self.window_k16 = window_k16
         self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
 
 
@@ -273,6 +275,8 @@ class CudaBackend:
             s.bias = g.bias.data_ptr()
         s.alpha = float(g.alpha)
         s.reserved = 2 if g.cluster == 2 else 0
+        if g.window_k16 is not None:
+            s.reserved = 3 | (int(g.window_k16) << 8)
         return s
 
 

@@ -55,6 +55,7 @@ enum { A8_MAJOR_K = 0, A8_MAJOR_MN = 1 };
 enum { A8_OUT_BF16 = 0, A8_OUT_F32 = 1, A8_OUT_F32_ATOMIC = 2 };
 enum { A8_ACT_NONE = 0, A8_ACT_GELU = 1, A8_ACT_GELU_DZ = 2 };
 enum { A8_AUX_NONE = 0, A8_AUX_ADD = 1, A8_AUX_MUL_GELU_GRAD = 2, A8_AUX_MUL = 3 };
+enum { A8_GEMM_PAIR = 2, A8_GEMM_TAP_WINDOW = 3 };
 
 typedef struct {
   const void* ptr;    /* bf16 */
@@ -85,7 +86,13 @@ typedef struct {
   int32_t bias_stride_lo;
   const float* bias;          /* optional fp32, index lo*bias_stride_lo + n */
   float alpha;
-  int32_t reserved;
+  int32_t reserved;           /* launch-shape request, low byte: 0 = plain, A8_GEMM_PAIR = CTA pairs compute 256 x block_n
+                                 tiles (cta_group::2), A8_GEMM_TAP_WINDOW = tap-window kernel for K-major operands whose A
+                                 tile moves by exactly one row of dims[1] per k-block (cb = {0, +-1, 0, 0}, k_inner = 1,
+                                 k_blocks a multiple of 8 in [16, 128], N <= 64, bf16 output: the grouped positional conv and
+                                 its data gradient).  Same result as the plain kernel; the rows the taps share are staged
+                                 once per 8 k-blocks instead of once per k-block.  Bits 8..15 (window only): how many of the
+                                 four 16-element k-steps of a k-block hold non-zero B columns (0 = all), the rest is skipped. */
 } a8_gemm_t;
 
 int a8_gemm(const a8_gemm_t* p, void* stream);

@@ -150,6 +150,8 @@ gemms = {
     "gemm conv1_wgrad": lambda: G.conv_wgrad(r(B, 23999, 512), r(B, 47999, 512), torch.zeros(512, 1536, device=dev), 3, 2),
     "gemm conv2_dgrad phase 0 (*gelu')": lambda: G.conv_dgrad(r(B, 11999, 512), r(512, 1024), torch.empty(B, 23999, 512, device=dev, dtype=bf), 3, 2, 0, aux=r(B, 23999, 512).to(torch.float16)),
     "gemm posconv_fwd (k=128, g=16)": lambda: G.posconv_fwd(r(B, T, D), r(D, 128 * 64), torch.empty(B, T, D, device=dev, dtype=bf), r(D, dtype=torch.float32), 16, 128, 63, z_out=torch.empty(B, T, D, device=dev, dtype=bf)),
+    "gemm posconv_dgrad (+add)": lambda: G.posconv_dgrad(r(B, T, D), r(D, 128 * 64), torch.empty(B, T, D, device=dev, dtype=bf), 16, 128, 63, aux=r(B, T, D)),
+    "gemm posconv_wgrad": lambda: G.posconv_wgrad(r(B, T, D), r(B, T, D), torch.empty(16, 128 * 64, 64, device=dev), 16, 128, 63),
 }
 for name, mk in gemms.items():
     spec = mk()

@@ -98,3 +98,25 @@ def test_grouped_wgrad_tcgen05(shapes):
     """a8_gemm_group: several weight-gradient problems with their own operands / extents in one persistent launch"""
     from audio8_b200 import ops
     _group_case("cuda", ops.backend(), shapes)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,D,k", [(2, 749, 768, 128), (1, 300, 1024, 128), (3, 130, 256, 128), (2, 257, 768, 64)])
+@pytest.mark.parametrize("window", [True, False])
+def test_tcgen05_posconv_shapes(B, T, D, k, window):
+    """positional conv fwd / dgrad / wgrad at the model's shapes (base: 16 x 48 channels, large: 16 x 64, C1: 16 x 16),
+    through the tap-window kernel (gemm_tc_window.cu) and through the plain kernel on the same descriptors"""
+    from audio8_b200 import gemm_specs as G
+    from audio8_b200 import ops
+    G.clear_spec_caches()
+    G.FORCE.update(window=window)
+    try:
+        specs, check = gemm_cases.case_posconv("cuda", B=B, T=T, D=D, groups=16, k=k)
+        assert (specs[0].spec().window_k16 is not None) == window
+        for sp in specs:
+            ops.backend().gemm(sp)
+        torch.cuda.synchronize()
+        check()
+    finally:
+        G.FORCE.clear()
+        G.clear_spec_caches()
