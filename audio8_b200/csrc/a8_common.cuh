@@ -248,6 +248,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// a kernel parameter copied into a register the compiler cannot rematerialise from the constant bank inside hot loops
+__device__ __forceinline__ int opaque(int v) {
+  int r;
+  asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
 // TMA tiled load, 4-D tensor map, completes on an mbarrier of this CTA
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst,
                                             int c0, int c1, int c2, int c3) {

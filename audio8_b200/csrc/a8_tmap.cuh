@@ -103,6 +103,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr, uint32_t lbo_b
   const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
+// The same descriptor split into its variable low word (address field, 16-byte units | leading-dimension field) and its
+// constant high word (SBO 1024 B, version 1, 128B swizzle): MMA-issuing threads advance the low word by constants instead
+// of rebuilding the descriptor from a byte address for every tcgen05.mma (shift, mask, or: three dependent uniform-
+// datapath instructions per operand, which is what bounded the issue rate of small MMAs).
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+  return ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_sbo1024(uint32_t lo) {
+  constexpr uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 #endif
 
 }  // namespace a8

@@ -27,6 +27,14 @@ const unsigned long long* seed_source();  // a8_api.cu
 
 namespace {
 
+// A8_ATTN_DIAG (experiments, scripts/attn_diag.py; results are WRONG with any bit set): 1 = forward softmax math replaced
+// by a register move, 2 = no tcgen05.ld of the scores, 4 = no tcgen05.mma issued (commits only)
+#ifndef A8_ATTN_DIAG
+#define A8_ATTN_DIAG 0
+#endif
+#ifndef A8_ATTN_TRACE
+#define A8_ATTN_TRACE 0
+#endif
 constexpr uint32_t TILE = 128 * 64 * 2;  // one [128 x 64] bf16 tile, 128B rows
 constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);  // f32 acc, bf16 A/B, M=128
 constexpr uint32_t IDESC_S = IDESC_BASE | ((uint32_t)(128 >> 3) << 17);                 // N=128, A and B K-major
@@ -47,7 +55,22 @@ struct AttnArgs {
   float* lse;                     // [B,H,T]  log2-sum-exp2 of the scaled scores
   float* delta;                   // [B,H,T]  rowsum(dO * O)
   __nv_bfloat16* dqkv;            // bwd out [B,T,3D]
+  long long* trace;               // A8_ATTN_TRACE builds: [5 CTAs][3 roles][64] clock64 stamps (scripts/attn_trace.py)
 };
+
+#if A8_ATTN_TRACE
+__device__ __forceinline__ int trace_cta() {
+  const int b = blockIdx.x;
+  return b == 0 ? 0 : (b == 1 ? 1 : (b == 150 ? 2 : (b == 300 ? 3 : (b == 431 ? 4 : -1))));
+}
+__device__ __forceinline__ void atrace(const AttnArgs& a, int role, int slot) {
+  const int c = trace_cta();
+  if (a.trace != nullptr && c >= 0 && slot < 64) a.trace[(c * 3 + role) * 64 + slot] = clock64();
+}
+#define ATRACE(role, slot) atrace(a, role, slot)
+#else
+#define ATRACE(role, slot)
+#endif
 
 // ---------------------------------------------------------------------------------------------- dropout hash
 // keep(q,k) <=> r(q,k) >= thr32, with  x = xorshift(((q/2 << 16) + k/2 + key) * M1)  shared by a 2x2 patch of the score
@@ -158,8 +181,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   uint32_t* sValid = reinterpret_cast<uint32_t*>(smem_raw + (bars + 128 - raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
+  if (threadIdx.x == 128) ATRACE(2, 0);
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 128) ATRACE(2, 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.nblk;
   const int U = 2 * nblk;
@@ -192,6 +217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 128) ATRACE(2, 2);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -200,6 +226,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
       for (int j = 0; j < nblk; ++j) {
         const int st = j & 1;
         mbar_wait(bar_at(bars, KV_EMPTY + st), ((j >> 1) & 1) ^ 1u);
+        ATRACE(0, j);
         mbar_expect_tx(bar_at(bars, KV_FULL + st), 2 * TILE);
         tma_load_3d(&map_qkv, bar_at(bars, KV_FULL + st), sK + st * TILE, D + h * 64, j * 128, b);
         tma_load_3d(&map_qkv, bar_at(bars, KV_FULL + st), sV + st * TILE, 2 * D + h * 64, j * 128, b);
@@ -208,34 +235,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t tO = tmem_base + 192;
+      // descriptor low words (16-byte units); a unit's operand = tile base + stage * TILE + half * HALF_TILE
+      const uint32_t q_lo = umma_desc_lo(sQ, 0), k_lo0 = umma_desc_lo(sK, 0), v_lo0 = umma_desc_lo(sV, 8192);
       auto issue_pv = [&](int u) {  // O += P(u) [128 x 64 keys, TMEM] * V(u) [64 keys x 64, read MN-major]
-        const uint32_t v = sV + ((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE;
+        const uint32_t v_lo = v_lo0 + (((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE) / 16;
         const uint32_t tP = tmem_base + 128 + (u & 1) * 32;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ts(tO, tP + k * 8, umma_smem_desc(v + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+          if (!(A8_ATTN_DIAG & 4))
+            umma_bf16_ts(tO, tP + k * 8, umma_desc_sbo1024(v_lo + k * (2048 / 16)), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
         if (u & 1) umma_commit(bar_at(bars, KV_EMPTY + ((u >> 1) & 1)));
         umma_commit(bar_at(bars, PV_DONE + (u & 1)));
       };
       mbar_wait(bar_at(bars, Q_FULL), 0);
+      ATRACE(1, 0);
       for (int u = 0; u < U; ++u) {
         const int j = u >> 1, s = u & 1;
         if (s == 0) mbar_wait(bar_at(bars, KV_FULL + (j & 1)), (j >> 1) & 1);
+        ATRACE(1, 1 + 3 * u);
         // PV(u-2), the last reader of P stage s, must have COMPLETED before the scores of unit u are issued: the softmax
         // warps take S_FULL(u) as the licence to overwrite that P buffer.  Relying on the S_FULL commit merely being
         // issued after PV(u-2) gave timing-dependent errors on peaked score distributions (scripts/attn_accuracy.py).
         // Waiting here costs this one thread ~100 cycles it has to spare; in the softmax warps it would cost every unit.
         if (u >= 2) mbar_wait(bar_at(bars, PV_DONE + s), ((u - 2) >> 1) & 1);
         tc_fence_after();
-        const uint32_t kk = sK + (j & 1) * TILE + s * HALF_TILE;
+        const uint32_t kk_lo = k_lo0 + ((j & 1) * TILE + s * HALF_TILE) / 16;
         const uint32_t tS = tmem_base + s * 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+          if (!(A8_ATTN_DIAG & 4))
+            umma_bf16(tS, umma_desc_sbo1024(q_lo + k * 2), umma_desc_sbo1024(kk_lo + k * 2), IDESC_S64, k > 0 ? 1u : 0u);
         umma_commit(bar_at(bars, S_FULL + s));
+        ATRACE(1, 2 + 3 * u);
         if (u > 0) {
           mbar_wait(bar_at(bars, P_READY + (s ^ 1)), ((u - 1) >> 1) & 1);
           tc_fence_after();
+          ATRACE(1, 3 + 3 * u);
           issue_pv(u - 1);
         }
       }
@@ -258,9 +293,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
     for (int u = 0; u < U; ++u) {
       const int s = u & 1;
       const uint32_t tS = tmem_row + s * 64, tP = tmem_row + 128 + s * 32;
+      if (threadIdx.x == 128) ATRACE(2, 3 + 2 * u);
       mbar_wait(bar_at(bars, S_FULL + s), (u >> 1) & 1);  // S(u) is only issued once PV(u-2) has released this P stage
       tc_fence_after();
+      if (threadIdx.x == 128) ATRACE(2, 4 + 2 * u);
       uint32_t r[32];
+      if (A8_ATTN_DIAG & 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint((float)(lane + i + u) * 0.01f);
+      }
       // The running max is only raised when a unit would overflow the row sum (any exp2 above 2^64): the common case
       // is ONE pass per unit with no per-element max.  Unit 0 and the rare overflow take the exact-max pass first.
       bool need_max = (u == 0);
@@ -297,12 +338,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
         float lsum = 0.f;
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
-          tmem_ld_32x32(tS + ch * 32, r);
-          tmem_ld_wait();
+          if (!(A8_ATTN_DIAG & 2)) {
+            tmem_ld_32x32(tS + ch * 32, r);
+            tmem_ld_wait();
+          }
           const uint32_t word = sValid[u * 2 + ch];
           const uint32_t wch = wrow + (uint32_t)((u * 64 + ch * 32) >> 1) * HM1;
           uint32_t pk[16];
-          if (word == 0xFFFFFFFFu) lsum += softmax_chunk<DROP, false>(r, pk, c, m, word, wch, mul_e, mul_o, a.thr);
+          if (A8_ATTN_DIAG & 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = r[2 * i] + wch;
+            lsum = 1.f;
+          } else if (word == 0xFFFFFFFFu) lsum += softmax_chunk<DROP, false>(r, pk, c, m, word, wch, mul_e, mul_o, a.thr);
           else lsum += softmax_chunk<DROP, true>(r, pk, c, m, word, wch, mul_e, mul_o, a.thr);
           tmem_st_32x16(tP + ch * 16, pk);
         }
@@ -318,8 +365,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
       tc_fence_before();
       mbar_arrive(bar_at(bars, P_READY + s));
     }
+    if (threadIdx.x == 128) ATRACE(2, 3 + 2 * U);
     mbar_wait(bar_at(bars, PV_DONE + ((U - 1) & 1)), ((U - 1) >> 1) & 1);
     tc_fence_after();
+    if (threadIdx.x == 128) ATRACE(2, 4 + 2 * U);
     const float inv = l > 0.f ? a.keep_scale / l : 0.f;
     uint32_t r[32];
     __nv_bfloat16* dst = a.ctx + ((long long)b * a.T + row) * D + h * 64;
@@ -340,10 +389,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnArgs a) {
       }
     }
     if (row < a.T) a.lse[(long long)bh * a.T + row] = l > 0.f ? m + log2f(l) : INFINITY;
+    if (threadIdx.x == 128) ATRACE(2, 5 + 2 * U);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 128) ATRACE(2, 6 + 2 * U);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -423,12 +474,14 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t tdQ = tmem_base + 320;
+      const uint32_t q_lo = umma_desc_lo(sQ, 0), do_lo = umma_desc_lo(sdO, 0), k_lo0 = umma_desc_lo(sK, 0), v_lo0 = umma_desc_lo(sV, 0);
+      const uint32_t kmn_lo0 = umma_desc_lo(sK, 8192);  // K read MN-major (the dQ accumulation)
       auto issue_dq = [&](int u) {  // dQ += dS(u) [128 x 64 keys, TMEM] * K(u) [64 keys x 64, read MN-major]
-        const uint32_t kk = sK + ((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE;
+        const uint32_t kk_lo = kmn_lo0 + (((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE) / 16;
         const uint32_t tdS = tmem_base + 256 + (u & 1) * 32;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ts(tdQ, tdS + k * 8, umma_smem_desc(kk + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ts(tdQ, tdS + k * 8, umma_desc_sbo1024(kk_lo + k * (2048 / 16)), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
         if (u & 1) umma_commit(bar_at(bars, KV_EMPTY + ((u >> 1) & 1)));
         umma_commit(bar_at(bars, DQ_DONE + (u & 1)));
       };
@@ -443,14 +496,15 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         // ~100 cycles it has to spare; in the math warps it would cost every unit.
         if (u >= 2) mbar_wait(bar_at(bars, DQ_DONE + s), ((u - 2) >> 1) & 1);
         tc_fence_after();
-        const uint32_t kk = sK + (j & 1) * TILE + s * HALF_TILE, vv = sV + (j & 1) * TILE + s * HALF_TILE;
+        const uint32_t off = ((j & 1) * TILE + s * HALF_TILE) / 16;
+        const uint32_t kk_lo = k_lo0 + off, vv_lo = v_lo0 + off;
         const uint32_t tS = tmem_base + s * 128, tdP = tS + 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tS, umma_smem_desc(sQ + k * 32, 0, 1024), umma_smem_desc(kk + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+          umma_bf16(tS, umma_desc_sbo1024(q_lo + k * 2), umma_desc_sbo1024(kk_lo + k * 2), IDESC_S64, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tdP, umma_smem_desc(sdO + k * 32, 0, 1024), umma_smem_desc(vv + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+          umma_bf16(tdP, umma_desc_sbo1024(do_lo + k * 2), umma_desc_sbo1024(vv_lo + k * 2), IDESC_S64, k > 0 ? 1u : 0u);
         umma_commit(bar_at(bars, S_FULL + s));
         if (u > 0) {
           mbar_wait(bar_at(bars, DS_READY + (s ^ 1)), ((u - 1) >> 1) & 1);
@@ -622,16 +676,18 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t tdV = tmem_base + 384, tdK = tmem_base + 448;
+      const uint32_t k_lo = umma_desc_lo(sK, 0), v_lo = umma_desc_lo(sV, 0), q_lo0 = umma_desc_lo(sQ, 0), do_lo0 = umma_desc_lo(sdO, 0);
+      const uint32_t qmn_lo0 = umma_desc_lo(sQ, 8192), domn_lo0 = umma_desc_lo(sdO, 8192);  // read MN-major (accumulations)
       auto issue_acc = [&](int u) {  // dV += P^T(u) dO(u),  dK += dS^T(u) Q(u): 64 queries of K extent each
-        const uint32_t off = ((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE;
-        const uint32_t qq = sQ + off, dd = sdO + off;
+        const uint32_t off = (((u >> 1) & 1) * TILE + (u & 1) * HALF_TILE) / 16;
+        const uint32_t qq_lo = qmn_lo0 + off, dd_lo = domn_lo0 + off;
         const uint32_t tPT = tmem_base + 256 + (u & 1) * 32, tdST = tmem_base + 320 + (u & 1) * 32;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ts(tdV, tPT + k * 8, umma_smem_desc(dd + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ts(tdV, tPT + k * 8, umma_desc_sbo1024(dd_lo + k * (2048 / 16)), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ts(tdK, tdST + k * 8, umma_smem_desc(qq + k * 2048, 8192, 1024), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_ts(tdK, tdST + k * 8, umma_desc_sbo1024(qq_lo + k * (2048 / 16)), IDESC_ACC, (u > 0 || k > 0) ? 1u : 0u);
         if (u & 1) umma_commit(bar_at(bars, Q_EMPTY + ((u >> 1) & 1)));
         umma_commit(bar_at(bars, ACC_DONE + (u & 1)));
       };
@@ -641,15 +697,15 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         if (s == 0) mbar_wait(bar_at(bars, Q_FULL + (i & 1)), (i >> 1) & 1);
         if (u >= 2) mbar_wait(bar_at(bars, ACC_DONE + s), ((u - 2) >> 1) & 1);  // as in the dQ kernel: acc(u-2) has completed
         tc_fence_after();
-        const uint32_t off = (i & 1) * TILE + s * HALF_TILE;
-        const uint32_t qq = sQ + off, dd = sdO + off;
+        const uint32_t off = ((i & 1) * TILE + s * HALF_TILE) / 16;
+        const uint32_t qq_lo = q_lo0 + off, dd_lo = do_lo0 + off;
         const uint32_t tST = tmem_base + s * 128, tdPT = tST + 64;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tST, umma_smem_desc(sK + k * 32, 0, 1024), umma_smem_desc(qq + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+          umma_bf16(tST, umma_desc_sbo1024(k_lo + k * 2), umma_desc_sbo1024(qq_lo + k * 2), IDESC_S64, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tdPT, umma_smem_desc(sV + k * 32, 0, 1024), umma_smem_desc(dd + k * 32, 0, 1024), IDESC_S64, k > 0 ? 1u : 0u);
+          umma_bf16(tdPT, umma_desc_sbo1024(v_lo + k * 2), umma_desc_sbo1024(dd_lo + k * 2), IDESC_S64, k > 0 ? 1u : 0u);
         umma_commit(bar_at(bars, S_FULL + s));
         if (u > 0) {
           mbar_wait(bar_at(bars, PS_READY + (s ^ 1)), ((u - 1) >> 1) & 1);
@@ -765,6 +821,8 @@ __global__ void attn_dropmask_kernel(unsigned char* out, int B, int H, int T, ui
   }
 }
 
+long long* g_attn_trace = nullptr;
+
 int fill_args(AttnArgs& a, const uint8_t* key_keep, int B, int H, int T, float scale, float pdrop, uint64_t seed) {
   A8_REQUIRE(B > 0 && H > 0 && T > 0 && T <= 4096, "attention: unsupported shape B=%d H=%d T=%d (T <= 4096)", B, H, T);
   A8_REQUIRE(pdrop >= 0.f && pdrop < 1.f, "attention: dropout probability %f", pdrop);
@@ -777,6 +835,7 @@ int fill_args(AttnArgs& a, const uint8_t* key_keep, int B, int H, int T, float s
   a.keep_scale = pdrop > 0.f ? (float)(4294967296.0 / (4294967296.0 - (double)a.thr)) : 1.f;  // 1 / realised keep rate
   a.seed = seed;
   a.seed_src = seed_source();
+  a.trace = g_attn_trace;
   return 0;
 }
 
@@ -793,6 +852,10 @@ int set_smem(K kern, int bytes) {
 }  // namespace a8
 
 using namespace a8;
+
+#if A8_ATTN_TRACE
+extern "C" void a8_attn_set_trace(void* buf) { g_attn_trace = static_cast<long long*>(buf); }  // debug builds only
+#endif
 
 extern "C" int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, float* lse, int32_t B, int32_t H,
                            int32_t T, float scale, float pdrop, uint64_t seed, void* stream_v) {

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(const Conv0Args a) {
 // output), and the normalisation is folded into the taps (forward: w * rstd * gamma, start value = the shift;
 // backward: w * rstd, start value -mean * rstd, which yields xhat directly).
 template <bool BWD>
-__global__ void __launch_bounds__(256) conv0_k10s5_kernel(const Conv0Args a) {
+__global__ void __launch_bounds__(256, BWD ? 3 : 4) conv0_k10s5_kernel(const Conv0Args a) {
   constexpr int K = 10, S = 5;
   __shared__ __align__(16) float xs[TILE_T * S + 16];
   const int b = blockIdx.y;

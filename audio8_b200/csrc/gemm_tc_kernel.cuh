@@ -537,10 +537,20 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
       constexpr uint32_t B_LBO = (MB == MAJOR_K) ? 0u : BLOCK_K * 128u;
       constexpr uint32_t A_KADV = (MA == MAJOR_K) ? UMMA_K * 2u : UMMA_K * 128u;
       constexpr uint32_t B_KADV = (MB == MAJOR_K) ? UMMA_K * 2u : UMMA_K * 128u;
+      // The per-k-block cost of this loop besides the MMAs bounds the short-K GEMMs (4 MMAs of 96-128 tensor-pipe clocks
+      // per k-block): descriptors are not rebuilt from byte addresses for every MMA (shift, mask, or on the uniform
+      // datapath) but carried as low words (address field in 16-byte units | LBO field) that advance by constants; the
+      // high word (SBO 1024 B, version, 128B swizzle) is a constant.
+      constexpr uint32_t DESC_HI = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      constexpr uint32_t A_LO0 = ((A_LBO >> 4) & 0x3FFFu) << 16, B_LO0 = ((B_LBO >> 4) & 0x3FFFu) << 16;
+      auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
       int gcur = 0;
+      uint32_t a_lo = (sA >> 4) | A_LO0, b_lo = (sB >> 4) | B_LO0, sbar = 0;  // of the current stage
+      // (Probing the next stage's barrier with mbarrier.test_wait ahead of the MMAs was measured and is SLOWER: the thread
+      // issues in order and stalls on the probe's result, ~145 clk, before the MMAs instead of after them.)
       for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
         const TileCoord t = GROUP ? decode_tile_group<CL>(p, probs, tile, rank, gcur) : decode_tile<CL>(p, tile, rank);
         const int as = iter & 1;
@@ -550,30 +560,33 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
         tc_fence_after();
         trace_ev(p, 1, iter, 1);
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          if (kb == t.kb_begin) trace_ev(p, 1, iter, 2);
-          const uint32_t a_addr = sA + stage * C::A_BYTES;
-          const uint32_t b_addr = sB + stage * C::B_BYTES;
+        const int nkb = t.kb_end - t.kb_begin;
+        for (int i = 0; i < nkb; ++i) {
+          // TMA -> mbarrier -> tcgen05.mma needs no tcgen05 fence (both are the async proxy, the barrier orders them)
+          mbar_wait(bars + sbar, phase);  // full_bar(stage)
+          if (i == 0) trace_ev(p, 1, iter, 2);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * A_KADV, A_LBO, 1024u);
-            const uint64_t db = make_smem_desc(b_addr + k * B_KADV, B_LBO, 1024u);
-            if (CL == 1) umma_bf16(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
-            else umma_bf16_2sm(d_tmem, da, db, idesc, (kb > t.kb_begin || k > 0) ? 1u : 0u);
+            if (CL == 1) umma_bf16(d_tmem, desc(a_lo + k * (A_KADV >> 4)), desc(b_lo + k * (B_KADV >> 4)), idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16_2sm(d_tmem, desc(a_lo + k * (A_KADV >> 4)), desc(b_lo + k * (B_KADV >> 4)), idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           if (CL == 1) {
-            umma_commit(empty_bar(stage));
-            if (kb == t.kb_end - 1) umma_commit(tfull_bar(as));
+            umma_commit(bars + 8u * STAGES + sbar);  // empty_bar(stage)
+            if (i == nkb - 1) umma_commit(tfull_bar(as));
           } else {  // the stage is free / the accumulator is ready in BOTH CTAs
-            umma_commit_2sm(empty_bar(stage), 3);
-            if (kb == t.kb_end - 1) umma_commit_2sm(tfull_bar(as), 3);
+            umma_commit_2sm(bars + 8u * STAGES + sbar, 3);
+            if (i == nkb - 1) umma_commit_2sm(tfull_bar(as), 3);
           }
-          if (kb == t.kb_end - 1) trace_ev(p, 1, iter, 3);
+          if (i == nkb - 1) trace_ev(p, 1, iter, 3);
+          a_lo += C::A_BYTES >> 4;
+          b_lo += C::B_BYTES >> 4;
+          sbar += 8u;
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
+            a_lo = (sA >> 4) | A_LO0;
+            b_lo = (sB >> 4) | B_LO0;
+            sbar = 0;
           }
         }
       }

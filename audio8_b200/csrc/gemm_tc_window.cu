@@ -15,6 +15,7 @@
 // Measured at base / 15 s (B=6, T=749; scripts/kernel_table.py): 143 us (plain kernel) -> 88 us with an 8-deep weight ring.
 // Roles, barriers and the epilogue are those of gemm_tc_kernel.cuh (same epilogue_chunk code).
 #include "gemm_tc_kernel.cuh"
+#include <stdlib.h>
 
 namespace a8 {
 namespace gemm {
@@ -42,8 +43,88 @@ struct WinParams {
   int k16;       // 16-wide k-steps per tap that are multiplied (1..4)
   int n_mma;     // UMMA N = B rows fetched per tap (N rounded up to 16, <= 64)
   int m_tiles2;  // 256-row tiles per (hi, lo) block
-  int b_stages;  // depth of the weight ring (<= WIN_B_STAGES_MAX), stage = n_mma * 128 bytes
+  int group;     // taps per weight barrier: one wait / one commit of the MMA thread per `group` taps (a barrier test
+                 // costs the issuing thread ~150 clk, as much as the 6 MMAs of a tap)
+  int b_groups;  // depth of the weight ring in groups (<= WIN_B_STAGES_MAX); a tile = n_mma * 128 bytes
 };
+
+// debug timeline (a8_gemm_set_trace, scripts/win_trace.py): CTA 0, its first tile, per tap: [0..127] the MMA thread saw
+// the weight tile, [128..255] it had issued the tap's MMAs and commit, [256..383] the producer saw the stage free
+__device__ __forceinline__ void wtrace(const KParams& p, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0 && slot < 384) p.trace[slot] = clock64();
+}
+
+// The MMA thread's loop.  What it costs per tap besides the MMAs themselves bounds this kernel (6 MMAs of 24 tensor-pipe
+// clocks per tap): the first version rebuilt both 64-bit descriptors from byte addresses for every MMA (shift, mask, or:
+// ~60 dependent uniform-datapath instructions and three constant-bank loads per tap, 630 clk per tap measured with
+// scripts/win_trace.py against 144 clk of tensor work).  Here the descriptors' low words (address field, 16-byte units)
+// are carried incrementally: a tap's operand is the previous one plus a constant, the k-steps add 2, the lower half-tile
+// adds 1024; the high word is a constant.
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) {
+  constexpr uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, 128B swizzle
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+template <int K16>
+__device__ __forceinline__ void window_mma_loop(const KParams& p, const WinParams& w, uint32_t bars, uint32_t sA,
+                                                uint32_t sB, uint32_t tmem_base) {
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(w.n_mma >> 3) << 17) |
+                         ((uint32_t)(BLOCK_M >> 4) << 24);
+  const int Q = opaque(w.Q), ngrp = opaque(w.b_groups), G = opaque(w.group), dir = opaque(w.dir), total = opaque(p.total_tiles);
+  const uint32_t b_step = (uint32_t)opaque(w.n_mma) * 8u;           // one weight tile, 16-byte units
+  const uint32_t a_first = dir > 0 ? 0u : (uint32_t)(Q - 1) * 64u;  // tap q = 0 of a residue: window offset, 16-byte units
+  const int a_step = dir * 64;                                      // next tap: 8 rows = 1024 B further (or back)
+  const uint32_t a_full0 = bars, a_empty0 = bars + 8u * WIN_A_SLOTS;
+  const uint32_t b_full0 = bars + 8u * (2 * WIN_A_SLOTS), b_empty0 = bars + 8u * (2 * WIN_A_SLOTS + WIN_B_STAGES_MAX);
+  const uint32_t tfull0 = bars + 8u * (2 * WIN_A_SLOTS + 2 * WIN_B_STAGES_MAX), tempty0 = tfull0 + 16u;
+  const uint32_t b_lo0 = sB >> 4;
+  int aslot = 0, grp = 0, iter = 0;
+  uint32_t aphase = 0, bphase = 0;
+  uint32_t b_lo = b_lo0, b_bar = 0;  // current weight group: descriptor word of its first tile, byte offset of its barriers
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++iter) {
+    const int as = iter & 1;
+    mbar_wait(tempty0 + 8u * as, ((iter >> 1) & 1u) ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + as * 128;
+    for (int r = 0; r < 8; ++r) {
+      mbar_wait(a_full0 + 8u * aslot, aphase);
+      tc_fence_after();
+      uint32_t a_lo = ((sA + aslot * WIN_A_BYTES) >> 4) + a_first;
+      for (int q0 = 0; q0 < Q; q0 += G) {
+        // TMA -> mbarrier -> tcgen05.mma needs no tcgen05 fence (both sides are the async proxy, the barrier orders them)
+        mbar_wait(b_full0 + b_bar, bphase);
+        for (int g = 0; g < G; ++g) {
+          if (tracing && iter == 0) wtrace(p, 8 * (q0 + g) + r);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int k = 0; k < K16; ++k)
+              umma_bf16(d_tmem + h * 64, desc_from_lo(a_lo + h * (BLOCK_M * 128 / 16) + k * 2), desc_from_lo(b_lo + k * 2), idesc,
+                        (r > 0 || q0 > 0 || g > 0 || k > 0) ? 1u : 0u);
+          }
+          if (tracing && iter == 0) wtrace(p, 128 + 8 * (q0 + g) + r);
+          a_lo += a_step;
+          b_lo += b_step;
+        }
+        umma_commit(b_empty0 + b_bar);
+        b_bar += 8u;
+        if (++grp == ngrp) {
+          grp = 0;
+          bphase ^= 1u;
+          b_lo = b_lo0;
+          b_bar = 0;
+        }
+      }
+      umma_commit(a_empty0 + 8u * aslot);
+      if (++aslot == WIN_A_SLOTS) {
+        aslot = 0;
+        aphase ^= 1u;
+      }
+    }
+    umma_commit(tfull0 + 8u * as);
+  }
+}
 
 template <int EK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -55,7 +136,7 @@ gemm_tc_window_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   const uint32_t sA = base;
   const uint32_t sB = base + WIN_A_SLOTS * WIN_A_BYTES;
   const uint32_t bars = sB + WIN_B_RING_BYTES;
-  const int WIN_B_STAGES = w.b_stages;
+  const int WIN_B_STAGES = w.b_groups;  // barrier pairs in use
   const uint32_t WIN_B_BYTES = (uint32_t)w.n_mma * 128u;  // a multiple of the 1024-byte swizzle atom (n_mma % 16 == 0)
   auto a_full = [&](int i) { return bars + 8u * i; };
   auto a_empty = [&](int i) { return bars + 8u * (WIN_A_SLOTS + i); };
@@ -117,10 +198,22 @@ gemm_tc_window_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     if (elect_one()) {
       int aslot = 0, stage = 0;
       uint32_t aphase = 0, bphase = 0;
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+      // weight-tile coordinates advance by a constant per tap: kept in registers instead of re-evaluating the affine
+      // map (20 multiply-adds on constant-bank operands) for each of the 128 taps
+      int cb8[4], cb1[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        cb1[d] = p.b.cb[d];
+        cb8[d] = 8 * p.b.cb[d];
+      }
+      const uint32_t b_stage_bytes = WIN_B_BYTES;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int mt2, lo, hi;
         decode(tile, mt2, lo, hi);
         const int m0 = mt2 * WIN_M;
+        int bt[4];
+        op_coords(p.b, 0, 0, 0, lo, hi, bt);  // tap 0 of this (lo, hi)
         for (int r = 0; r < 8; ++r) {
           mbar_wait(a_empty(aslot), aphase ^ 1u);
           mbar_expect_tx(a_full(aslot), a_bytes);
@@ -130,11 +223,18 @@ gemm_tc_window_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
           const uint32_t a_dst = sA + aslot * WIN_A_BYTES;
           tma_load_4d(&map_a_hi, a_full(aslot), a_dst, cc[0], cc[1], cc[2], cc[3]);
           tma_load_4d(&map_a_lo, a_full(aslot), a_dst + WIN_M * 128, cc[0], cc[1] + WIN_M, cc[2], cc[3]);
-          for (int q = 0; q < Q; ++q) {
+          int bq[4];
+#pragma unroll
+          for (int d = 0; d < 4; ++d) bq[d] = bt[d] + cb1[d] * r;
+          for (int q0 = 0; q0 < Q; q0 += w.group) {
             mbar_wait(b_empty(stage), bphase ^ 1u);
-            mbar_expect_tx(b_full(stage), b_bytes);
-            op_coords(p.b, 0, 8 * q + r, 0, lo, hi, cc);
-            tma_load_4d(&map_b, b_full(stage), sB + stage * WIN_B_BYTES, cc[0], cc[1], cc[2], cc[3]);
+            if (tracing && tile == 0) wtrace(p, 256 + 8 * q0 + r);
+            mbar_expect_tx(b_full(stage), b_bytes * w.group);
+            for (int g = 0; g < w.group; ++g) {
+              tma_load_4d(&map_b, b_full(stage), sB + (stage * w.group + g) * b_stage_bytes, bq[0], bq[1], bq[2], bq[3]);
+#pragma unroll
+              for (int d = 0; d < 4; ++d) bq[d] += cb8[d];
+            }
             if (++stage == WIN_B_STAGES) {
               stage = 0;
               bphase ^= 1u;
@@ -150,45 +250,11 @@ gemm_tc_window_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     if (elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(w.n_mma >> 3) << 17) |
-                             ((uint32_t)(BLOCK_M >> 4) << 24);
-      int aslot = 0, stage = 0, iter = 0;
-      uint32_t aphase = 0, bphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
-        const int as = iter & 1;
-        mbar_wait(tempty_bar(as), ((iter >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 128;
-        for (int r = 0; r < 8; ++r) {
-          mbar_wait(a_full(aslot), aphase);
-          tc_fence_after();
-          const uint32_t a_addr = sA + aslot * WIN_A_BYTES;
-          for (int q = 0; q < Q; ++q) {
-            mbar_wait(b_full(stage), bphase);
-            tc_fence_after();
-            const uint32_t b_addr = sB + stage * WIN_B_BYTES;
-            const uint32_t a_tap = a_addr + (uint32_t)(w.dir > 0 ? q : Q - 1 - q) * 1024u;  // 8 rows x 128 B per tap
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              for (int k = 0; k < w.k16; ++k) {
-                const uint64_t da = make_smem_desc(a_tap + h * (BLOCK_M * 128) + k * (UMMA_K * 2), 0u, 1024u);
-                const uint64_t db = make_smem_desc(b_addr + k * (UMMA_K * 2), 0u, 1024u);
-                umma_bf16(d_tmem + h * 64, da, db, idesc, (r > 0 || q > 0 || k > 0) ? 1u : 0u);
-              }
-            }
-            umma_commit(b_empty(stage));
-            if (++stage == WIN_B_STAGES) {
-              stage = 0;
-              bphase ^= 1u;
-            }
-          }
-          umma_commit(a_empty(aslot));
-          if (++aslot == WIN_A_SLOTS) {
-            aslot = 0;
-            aphase ^= 1u;
-          }
-        }
-        umma_commit(tfull_bar(as));
+      switch (w.k16) {
+        case 1: window_mma_loop<1>(p, w, bars, sA, sB, tmem_base); break;
+        case 2: window_mma_loop<2>(p, w, bars, sA, sB, tmem_base); break;
+        case 3: window_mma_loop<3>(p, w, bars, sA, sB, tmem_base); break;
+        default: window_mma_loop<4>(p, w, bars, sA, sB, tmem_base); break;
       }
     }
   } else if (warp >= 4) {
@@ -352,26 +418,34 @@ gemm_tc_wgrad_window_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
                                  ((uint32_t)(BLOCK_M >> 4) << 24);
+      // descriptor low words carried incrementally (see window_mma_loop): address field in 16-byte units, the leading-
+      // dimension offset (1024 B between the two taps' atoms for A, one 8 KB atom for B) in bits 16..29
+      constexpr uint32_t A_LBO = (1024u >> 4) << 16, B_LBO = ((BLOCK_K * 128u) >> 4) << 16;
+      const int halfQ = Q / 2;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t a_lo = (sA >> 4) | A_LBO, b_lo = (sB >> 4) | B_LBO, bar = 0;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait(bars + bar, phase);
         tc_fence_after();
-        const uint32_t a_addr = sA + stage * WG_A_BYTES;
-        const uint32_t b_addr = sB + stage * WG_B_BYTES;
-        for (int i = 0; i < Q / 2; ++i) {
+        uint32_t a_i = a_lo;
+        for (int i = 0; i < halfQ; ++i) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // taps 2i and 2i+1: two 64-channel atoms 8 rows (1024 B) apart; 16 contraction rows per MMA (2048 B)
-            const uint64_t da = make_smem_desc(a_addr + (uint32_t)i * 2048u + k * (UMMA_K * 128), 1024u, 1024u);
-            const uint64_t db = make_smem_desc(b_addr + k * (UMMA_K * 128), BLOCK_K * 128u, 1024u);
-            umma_bf16(tmem_base + i * 64, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)  // 16 contraction rows per MMA = 2048 B
+            umma_bf16(tmem_base + i * 64, desc_from_lo(a_i + k * (UMMA_K * 128 / 16)), desc_from_lo(b_lo + k * (UMMA_K * 128 / 16)),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          a_i += 2048u >> 4;  // taps 2i+2, 2i+3: 16 rows further
         }
-        umma_commit(empty_bar(stage));
+        umma_commit(bars + 8u * WG_STAGES + bar);
+        a_lo += WG_A_BYTES >> 4;
+        b_lo += WG_B_BYTES >> 4;
+        bar += 8u;
         if (++stage == WG_STAGES) {
           stage = 0;
           phase ^= 1u;
+          a_lo = (sA >> 4) | A_LBO;
+          b_lo = (sB >> 4) | B_LBO;
+          bar = 0;
         }
       }
       umma_commit(done_bar);
@@ -463,8 +537,10 @@ int launch_window(const a8_gemm_t& g, KParams& kp, int k16, cudaStream_t stream)
   wp.k16 = k16 == 0 ? 4 : k16;
   wp.n_mma = ((g.N + 15) / 16) * 16;
   wp.m_tiles2 = cdiv(g.M, WIN_M);
-  wp.b_stages = (int)(WIN_B_RING_BYTES / (wp.n_mma * 128u));
-  if (wp.b_stages > WIN_B_STAGES_MAX) wp.b_stages = WIN_B_STAGES_MAX;
+  wp.group = (wp.Q % 4 == 0) ? 4 : ((wp.Q % 2 == 0) ? 2 : 1);
+  wp.b_groups = (int)(WIN_B_RING_BYTES / (wp.n_mma * 128u)) / wp.group;
+  if (wp.b_groups > WIN_B_STAGES_MAX) wp.b_groups = WIN_B_STAGES_MAX;
+
   kp.m_tiles = wp.m_tiles2;
   kp.n_tiles = 1;
   const long long tiles = (long long)wp.m_tiles2 * kp.lo_count * kp.hi_count;
