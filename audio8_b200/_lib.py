@@ -92,6 +92,8 @@ SIGNATURES.update({
     "a8_optim_grad_sqnorm": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "a8_optim_adamw": (_I, [_P, _P, _P, _I, _I, _P, _F, _F, _D, _D, _D, _D, _D, _D, _D, _I, _P, _P]),
     "a8_allreduce_mc": (_I, [_P, _L, _L, _I, _I, _F, _I, _P]),
+    "a8_span_mask_draw": (_I, [_U, _P, _I, _I, _D, _I, _I, _P, _P, _P]),
+    "a8_negatives_draw": (_I, [_U, _P, _P, _I, _I, _I, _P, _P]),
 })
 
 _lib = None

@@ -133,15 +133,16 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 // gelu(x) and gelu'(x) together: Phi(x) is shared and the exponential of erf (7.1.26) IS the one of phi(x)
+// (the 1/sqrt(2) of u = |x|/sqrt(2) is folded into the rational's slope and the 1/2 of erf/2 into the polynomial: this
+// runs 32 times per lane per epilogue chunk of the GELU GEMMs, where the FP32 pipe is what the epilogue waits for)
 __device__ __forceinline__ float gelu_both_fast(float x, float& dgelu) {
-  const float u = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, u, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
+  const float t = rcp_approx(fmaf(0.23164188826636045f, fabsf(x), 1.f));  // 0.3275911 / sqrt(2)
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
   const float e = ex2_approx(-0.72134752044448170f * x * x);  // exp(-x^2/2)
-  const float half_erf = 0.5f - 0.5f * p * t * e;
+  const float half_erf = fmaf(-(p * t), e, 0.5f);
   const float cdf = 0.5f + copysignf(half_erf, x);
   dgelu = fmaf(x * 0.3989422804014327f, e, cdf);
   return x * cdf;

@@ -169,7 +169,7 @@ __device__ __forceinline__ TileCoord decode_tile_group(const KParams& p, const G
 // Coalesced copy between a warp's staging buffer (32 rows x PIECES*16 B) and global rows `row_off0 + r*ldc` (element
 // offsets of element size ES): lane l moves 16 B of row (l/PIECES + (32/PIECES) i), piece (l % PIECES) — every
 // instruction touches 32/PIECES rows x PIECES*16 contiguous bytes instead of 32 rows x 16 bytes.
-enum { STG_LOAD = 0, STG_STORE = 1, STG_RED = 2 };
+enum { STG_STORE = 1, STG_RED = 2 };
 template <int ES, int MODE, int PIECES>
 __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long row_off0, long long ldc, int col0,
                                            int rows_valid, int cols_valid, int lane) {
@@ -177,32 +177,63 @@ __device__ __forceinline__ void stage_copy(uint8_t* stg, void* gbase, long long 
   constexpr int RPI = 32 / PIECES;  // rows per instruction
   const int piece = lane % PIECES;
   const int col = col0 + piece * EPP;
+  // all shared-memory reads first, then the global accesses: with a load -> store pair per piece the compiler reuses one
+  // register quad and every store waits for its own LDS (ncu: 23 % of the epilogue's samples sat on those STGs)
+  uint4 v[PIECES];
+#pragma unroll
+  for (int i = 0; i < PIECES; ++i)
+    v[i] = *reinterpret_cast<const uint4*>(stg + (lane / PIECES + RPI * i) * STG_PITCH + piece * 16);
 #pragma unroll
   for (int i = 0; i < PIECES; ++i) {
     const int r = lane / PIECES + RPI * i;
     if (r < rows_valid && col < cols_valid) {
       uint8_t* g = reinterpret_cast<uint8_t*>(gbase) + (row_off0 + (long long)r * ldc + col) * ES;
-      uint4* sp = reinterpret_cast<uint4*>(stg + r * STG_PITCH + piece * 16);
       if (MODE == STG_STORE) {
-        *reinterpret_cast<uint4*>(g) = *sp;
-      } else if (MODE == STG_LOAD) {
-        *sp = *reinterpret_cast<const uint4*>(g);
+        *reinterpret_cast<uint4*>(g) = v[i];
       } else {  // split-K: one 16-byte vector reduction per lane
-        const float4 v = *reinterpret_cast<const float4*>(sp);
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(__uint_as_float(v[i].x)),
+                     "f"(__uint_as_float(v[i].y)), "f"(__uint_as_float(v[i].z)), "f"(__uint_as_float(v[i].w))
                      : "memory");
       }
     }
   }
 }
+// The bf16 / fp16 aux tile of a chunk (residual to add, GELU' to multiply by) in the same coalesced lane pattern, in two
+// steps: `aux_issue` puts the global loads in flight (for the NEXT chunk, one chunk of math ahead), `aux_commit` parks
+// them in the warp's staging buffer from which every lane then reads its own row.  (Loading the tile where it is
+// consumed left the full global-load latency exposed once per chunk: 60 % of the samples of the dgrad epilogues.)
+template <int PIECES>
+__device__ __forceinline__ void aux_issue(uint4 (&pre)[PIECES], const void* gbase, long long row_off0, long long ldc,
+                                          int col0, int rows_valid, int cols_valid, int lane) {
+  constexpr int RPI = 32 / PIECES;
+  const int piece = lane % PIECES;
+  const int col = col0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < PIECES; ++i) {
+    const int r = lane / PIECES + RPI * i;
+    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid && col < cols_valid)
+      pre[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(gbase) +
+                                                    (row_off0 + (long long)r * ldc + col) * 2));
+  }
+}
+template <int PIECES>
+__device__ __forceinline__ void aux_commit(uint8_t* stg, const uint4 (&pre)[PIECES], int lane) {
+  constexpr int RPI = 32 / PIECES;
+#pragma unroll
+  for (int i = 0; i < PIECES; ++i)
+    *reinterpret_cast<uint4*>(stg + (lane / PIECES + RPI * i) * STG_PITCH + (lane % PIECES) * 16) = pre[i];
+}
 
 // CW columns x 32 rows (one row per lane) of accumulators in registers -> epilogue math -> global memory.  Outputs (and
 // the bf16 aux input) go through the warp's smem staging buffer so that global accesses are row-contiguous (direct
 // 16-byte-per-row stores from registers were measured: slower, L2 sees partial sectors).
+// `pre` holds this chunk's aux tile (aux_issue); it is refilled for the chunk at column nb_next (< 0: none) as soon as it
+// has been parked.
 template <int EK, int CW>
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord& tc, const uint32_t* r,
-                                               long long row_off0, int row0, int nb, const float* sb, uint8_t* stg,
-                                               int lane) {
+                                               long long row_off0, int row0, int nb, int nb_next, uint4 (&pre)[CW / 8],
+                                               const float* sb, uint8_t* stg, int lane) {
   constexpr bool GEN = (EK < 0);
   constexpr int NP = CW / 8;  // 16-byte bf16 pieces per row
   const int c_dtype = GEN ? p.c_dtype : (EK & 3);
@@ -219,22 +250,28 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
   uint4* my = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
   uint4 a[NP];
   if (has_aux) {
-    stage_copy<2, STG_LOAD, NP>(stg, const_cast<void*>(p.aux), row_off0, ldc, nb, rows_valid, cols_valid, lane);
+    aux_commit<NP>(stg, pre, lane);
     __syncwarp();
 #pragma unroll
     for (int g = 0; g < NP; ++g) a[g] = my[g];
     __syncwarp();
+    if (nb_next >= 0) aux_issue<NP>(pre, p.aux, row_off0, ldc, nb_next, rows_valid, cols_valid, lane);
   }
   float v[CW];
-#pragma unroll
-  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  const float alpha = p.alpha;
   if (sb != nullptr) {  // broadcast LDS.128 (a scalar LDS per column costs a full shared-memory wavefront each)
     const float4* sb4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
     for (int i = 0; i < CW / 4; ++i) {
       const float4 b4 = sb4[i];
-      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+      v[4 * i] = fmaf(__uint_as_float(r[4 * i]), alpha, b4.x);
+      v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), alpha, b4.y);
+      v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), alpha, b4.z);
+      v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), alpha, b4.w);
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * alpha;
   }
   if (do_gelu_dz) {  // the activation and its derivative from one erf / exp evaluation; the derivative goes to z_out as fp16
 #pragma unroll
@@ -613,15 +650,19 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
         for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) sb[i] = (t.nt * BN + i < t.N) ? __ldg(bsrc + i) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
       }
-      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 0);
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 1);
       const int row0 = t.mt * BLOCK_M + q * 32;
       const long long row_off0 =
           (long long)t.hi * p.c_stride_hi + (long long)t.lo * p.c_stride_lo + (long long)row0 * t.ldc;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * COLS;
       const int nb0 = t.nt * BN + half * COLS;
+      // the first chunk's aux tile is requested before the wait for the accumulator
+      uint4 aux_pre[EPI_CW / 8];
+      if (((EK < 0) ? p.aux_mode : ((EK >> 5) & 3)) != AUX_NONE && nb0 < t.N)
+        aux_issue<EPI_CW / 8>(aux_pre, p.aux, row_off0, t.ldc, nb0, min(32, t.M - row0), (t.N + 7) & ~7, lane);
+      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 0);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      if (warp == 4 && lane == 0) trace_ev(p, 2, iter, 1);
       const float* sbw = sb ? sb + half * COLS : nullptr;
       uint8_t* stg = s_stage + (warp - 4) * STG_BYTES;
       // one chunk at a time, NOT unrolled: the chunk body is several hundred instructions and the epilogue warps must
@@ -632,7 +673,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
         if (nb0 + c * EPI_CW >= t.N) break;
         tmem_ld_chunk(t_addr + c * EPI_CW, ra);
         tmem_ld_wait();
-        epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, nb0 + c * EPI_CW, sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
+        const int nb_next = (c + 1 < NCH && nb0 + (c + 1) * EPI_CW < t.N) ? nb0 + (c + 1) * EPI_CW : -1;
+        epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, nb0 + c * EPI_CW, nb_next, aux_pre,
+                                   sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
       }
       tc_fence_before();
       __syncwarp();

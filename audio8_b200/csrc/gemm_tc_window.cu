@@ -291,12 +291,16 @@ gemm_tc_window_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         const int nb0 = part * COLS;
         const float* sbw = sb ? sb + part * COLS : nullptr;
         uint32_t ra[EPI_CW];
+        uint4 aux_pre[EPI_CW / 8];
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
           if (nb0 + c * EPI_CW >= p.N) break;
           tmem_ld_chunk(t_addr + c * EPI_CW, ra);
+          if (((EK >> 5) & 3) != AUX_NONE)  // the aux tile's global loads fly under the TMEM load
+            aux_issue<EPI_CW / 8>(aux_pre, p.aux, row_off0, p.ldc, nb0 + c * EPI_CW, min(32, p.M - row0), (p.N + 7) & ~7, lane);
           tmem_ld_wait();
-          epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, nb0 + c * EPI_CW, sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
+          epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, nb0 + c * EPI_CW, -1, aux_pre,
+                                     sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
         }
       }
       tc_fence_before();
@@ -474,7 +478,8 @@ gemm_tc_wgrad_window_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         if (part * COLS + c * EPI_CW >= p.N) break;
         tmem_ld_chunk(t_addr + c * EPI_CW, ra);
         tmem_ld_wait();
-        epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, part * COLS + c * EPI_CW, nullptr, stg, lane);
+        uint4 no_aux[EPI_CW / 8];
+        epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, part * COLS + c * EPI_CW, -1, no_aux, nullptr, stg, lane);
       }
     }
   }

@@ -283,6 +283,21 @@ def dropout(x, p, training):
 # =================================================================================================
 # time-mask plumbing (wav2vec2.py:939, 946, 381, 717, 721)
 # =================================================================================================
+def span_mask_draw(like, B, T, p_start, mask_length, R_max):
+    """device-side `create_mask` (reference wav2vec2.py:189-216; csrc/draws.cu): -> (padded masked-row list int32
+    [R_max + 1] with the count in its last element, mask uint8 [B,T]).  The per-step seed is a device word from torch's
+    CUDA generator (`step_seed`), so the draw follows torch.manual_seed() and changes on every CUDA-graph replay."""
+    with torch.no_grad():
+        return _be().span_mask_draw(next_seed(), step_seed(like), B, T, p_start, mask_length, R_max, like.device)
+
+
+def negatives_draw(rows, B, K):
+    """device-side `Sampler.negatives` indices (reference wav2vec2.py:955-976) for the padded row list of
+    `span_mask_draw` -> int32 [R_max * K]"""
+    with torch.no_grad():
+        return _be().negatives_draw(next_seed(), step_seed(rows), rows, B, K)
+
+
 class RowsSetFn(torch.autograd.Function):
     """features[time_mask] = mask_emb   (rows of a [B,T,C] bf16 tensor given flat row indices)"""
 

@@ -652,6 +652,25 @@ class CudaBackend:
                    "a8_contrastive_bwd")
         return dx, dy
 
+    # ------------------------------------------------------------------ device-side draws (csrc/draws.cu)
+    def span_mask_draw(self, seed, seed_dev, B, T, p_start, mask_length, R_max, device):
+        """-> (rows int32 [R_max + 1]: masked flat rows, -1 padding, count last; mask uint8 [B, T])"""
+        assert seed_dev is None or (seed_dev.is_cuda and seed_dev.dtype == torch.int64)
+        rows = torch.empty(R_max + 1, dtype=torch.int32, device=device)
+        mask = torch.empty(B, T, dtype=torch.uint8, device=device)
+        _lib.check(self.lib.a8_span_mask_draw(seed, _ptr(seed_dev), B, T, float(p_start), mask_length, R_max, _ptr(rows),
+                                              _ptr(mask), _stream()), "a8_span_mask_draw")
+        return rows, mask
+
+    def negatives_draw(self, seed, seed_dev, rows, B, K):
+        """rows: the padded list of span_mask_draw (its last element is the valid count) -> int32 [R_max * K]"""
+        assert rows.is_cuda and rows.dtype == torch.int32 and rows.is_contiguous()
+        assert seed_dev is None or (seed_dev.is_cuda and seed_dev.dtype == torch.int64)
+        R_max = rows.numel() - 1
+        out = torch.empty(R_max * K, dtype=torch.int32, device=rows.device)
+        _lib.check(self.lib.a8_negatives_draw(seed, _ptr(seed_dev), _ptr(rows, R_max), B, K, R_max, _ptr(out), _stream()),
+                   "a8_negatives_draw")
+        return out
 
     # ------------------------------------------------------------------ optimizer side (csrc/optim.cu)
     def optim_grad_sqnorm(self, table, chunk_tensor, chunk_off, chunk, partials):

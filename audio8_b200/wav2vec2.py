@@ -239,6 +239,20 @@ class _HostDraws:
             raise self.error
         return self.neg
 
+_DEVICE_DRAWS = [__import__("os").environ.get("A8_DEVICE_DRAWS", "0") == "1"]
+
+
+def set_device_draws(flag):
+    """Opt-in: draw the span mask and the negative indices of a pre-training step ON THE DEVICE (csrc/draws.cu, Philox)
+    instead of with numpy's global generator on the host.  Same distributions as the reference, not the
+    same numbers: the default (host) mode is the one that is bit-identical to the reference's draws.  In this mode the
+    step uploads no index list, the draws live inside the CUDA-graph segments and change with torch's CUDA generator
+    (`torch.manual_seed`).  Because the number of masked frames is then known only on the device, `forward` returns
+    the latents PADDED: `y` is [B, R_max / B, C] (real rows first, flat over the batch, then zero rows) and
+    `time_mask.a8_rows[-1]` holds the real count; `Wav2Vec2Loss` consumes exactly that."""
+    _DEVICE_DRAWS[0] = bool(flag)
+
+
 def set_prefetch_draws(flag):
     """Trainer-level switch: make the numpy draws of step i+1 (span mask, LayerDrop, negatives) on the helper thread while
     the GPU runs step i, instead of at the start of step i+1.  The numbers are the ones the reference would draw (same
@@ -664,6 +678,13 @@ class Wav2Vec2Model(nn.Module):
         features = Fn.RowsSetFn.apply(features, rows[:-1], mask_emb)
         return features, unmasked
 
+    def _front_dev(self, x, gn_w, gn_b, *rest):
+        """`_front` with the span mask drawn on the device inside the same segment (set_device_draws)"""
+        B, T = x.shape[0], conv_out_length(x.shape[1], self.feature_extractor.spec)
+        rows, mask = Fn.span_mask_draw(x, B, T, self.timestep_masking, self.timestep_mask_len, self.max_masked_rows(B, T))
+        features, unmasked = self._front(x, rows, gn_w, gn_b, *rest)
+        return features, unmasked, rows, mask
+
     def _branch(self, unmasked, rows, wq, bq, vars_, pw, pb):
         """quantizer branch (reference :946-950): masked frames of the un-projected features -> dropout -> Gumbel VQ ->
         project_q.  Works on the padded row list (rows[:-1], -1 = padding; rows[-1] = number of real rows)."""
@@ -697,6 +718,8 @@ class Wav2Vec2Model(nn.Module):
         # ---- the step's numpy draws (mask, LayerDrop, negatives) in the reference's order; they depend on shapes only, so
         # they are made BEFORE any GPU work (prefetched during the previous step when the caller allows it: _HostDraws)
         layer_draws = None
+        if _DEVICE_DRAWS[0]:
+            return self._forward_device_draws(x, B, T)
         if sampler is not None:
             self._host_draws = draws = _HostDraws.get(B, T, self.timestep_masking, self.timestep_mask_len,
                                                       len(self.encoder.transformer.encoders), sampler)
@@ -747,6 +770,38 @@ class Wav2Vec2Model(nn.Module):
         return xo, y, vq_probs, mask_t
 
 
+def _forward_device_draws(self, x, B, T):
+    """Wav2Vec2Model.forward with device-side draws: no numpy draw, no index upload, nothing data dependent on the host"""
+    R_max = self.max_masked_rows(B, T)
+    Fn.ops.set_dynamic_rows(R_max, R_max)
+    for m in (self.feature_extractor, self.proj_to_input, self.quantizer, self.project_q, self.final_proj):
+        m.refresh_operands()
+    eager = self.quantizer.noise_override is not None or self.quantizer.keep_logits
+    arena = Fn.ops.grad_arena_active()
+    features, unmasked, rows, mask = self._front_graph.run(
+        self._front_dev, (x,), self._front_params(),
+        extra=(self.training, self.dropout_input_p, arena, "device draws", self.timestep_masking, self.timestep_mask_len))
+    branch = lambda: (self._branch(unmasked, rows, *self._branch_params()) if eager else
+                      self._branch_graph.run(self._branch, (unmasked, rows), self._branch_params(),
+                                             extra=(self.training, self.dropout_features_p, arena,
+                                                    self.quantizer.curr_temperature)))
+    if _ENCODER_LAST and not arena:
+        y_pad, vq_probs = branch()
+        enc = self.encoder.extract_features(features, None, None, _internal=True)
+    else:
+        enc = self.encoder.extract_features(features, None, None, _internal=True)
+        y_pad, vq_probs = branch()
+    xo = self.final_proj(enc, out_f32=True)
+    mask_t = mask.view(torch.bool)
+    mask_t.a8_rows = rows
+    mask_t.a8_ypad = y_pad
+    mask_t.a8_device_draws = True
+    return xo, y_pad.view(B, R_max // B, -1), vq_probs, mask_t
+
+
+Wav2Vec2Model._forward_device_draws = _forward_device_draws
+
+
 class Wav2Vec2Loss(nn.Module):
     """Reference wav2vec2.py:371-392: 0.1 * CE(cos-sim logits over [positive | K negatives]) + 10 * (n_vars - ppl) / n_vars."""
 
@@ -775,6 +830,20 @@ class Wav2Vec2Loss(nn.Module):
                               torch.tensor([B * Tm], dtype=torch.int32, device=outputs.device)])
             y_pad = latents.reshape(B * Tm, C)
         R_max = rows.numel() - 1
+        if getattr(time_mask, "a8_device_draws", False):  # negatives drawn on the device inside the loss segment
+            K = self.sample.n_negatives
+            y2 = y_pad.reshape(R_max, C)
+            self.last_rows = rows
+
+            def fn(o, y_, g, r):
+                # (device tensors; under a CUDA-graph replay they are the graph's static buffers, refreshed by the replay)
+                self.last_neg_idx = idx = Fn.negatives_draw(r, B, K)
+                return self._loss(o, y_, g, r, idx)
+
+            if gs_probs.requires_grad and outputs.requires_grad:
+                graph = self.__dict__.setdefault("_graph", GraphedSegment("contrastive loss (gather, cosine logits, CE)"))
+                return graph.run(fn, (outputs, y2, gs_probs, rows), (), extra=(self.n_vars, K, B, "device draws"))
+            return fn(outputs, y2, gs_probs, rows)
         # numpy draws, bit-exact with the reference's Sampler (already made on the helper thread when `draws`)
         neg = draws.negatives() if draws is not None else self.sample.indices32(B, Tm)
         assert neg.shape == (B, self.sample.n_negatives * Tm)

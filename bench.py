@@ -617,7 +617,10 @@ def _run_ours(args):
                     + ("NVSwitch multicast kernel a8_allreduce_mc)" if net._arena.switch is not None else "NCCL)")),
                 "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                 "launch": "the step is 4 CUDA-graph segments (front+mask, quantizer branch, encoder, loss), fwd and bwd; "
-                          "masked-row lists padded to their worst-case length; host draws prefetched one step ahead",
+                          "masked-row lists padded to their worst-case length; "
+                          + ("span mask and negatives drawn on the device inside the segments (csrc/draws.cu, A8_DEVICE_DRAWS=1: "
+                             "the reference's distributions, not its numpy numbers)" if (not ctc and W._DEVICE_DRAWS[0]) else
+                             "host draws (numpy, the reference's numbers) prefetched one step ahead"),
                 "operands": "bf16 / packed operand copies of the parameters are rebuilt when a parameter changes (version "
                             "counter), i.e. once per optimizer step; the fwd+bwd loop of `value` never changes them, "
                             "step_with_optimizer rebuilds them every step",

@@ -273,6 +273,25 @@ int a8_contrastive_bwd(const float* x, const float* y, const int32_t* idx, int32
                        float* dx, float* dy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side draws of the pre-training step (opt-in, `wav2vec2.set_device_draws`): the span mask of
+ * `create_mask` (`wav2vec2.py:189-216`) and the negative indices of `Sampler.negatives` (`wav2vec2.py:955-976`) from
+ * Philox4x32-10 on the GPU instead of numpy's global generator on the host.  Same distributions as the reference
+ * (uniform subset of span starts per row, every row cut down to the batch-minimum count by a uniform subset, negatives
+ * uniform over the OTHER masked steps of the same utterance), not the same numbers: the bit-exact path stays the host
+ * one.  Effective seed = seed + *seed_dev (seed_dev: device uint64 or NULL), so a CUDA-graph replay draws afresh.
+ * a8_span_mask_draw: rows int32 [R_max + 1] = flat indices b*T + t of the masked frames in row-major order, -1
+ *   padding, rows[R_max] = their number; mask uint8 [B,T].  R_max >= B * min(T, int(p_start*T/mask_length + 1) *
+ *   mask_length).  Fails (like np.random.choice in the reference) when the spans cannot start at distinct frames.
+ * a8_negatives_draw: out int32 [R_max, K] candidate rows of the flattened latents for every masked step r <
+ *   *n_valid (n_valid = rows + R_max), never r itself, always inside r's utterance (steps per utterance = *n_valid / B);
+ *   0 for the padding rows.
+ * ---------------------------------------------------------------------------------------------- */
+int a8_span_mask_draw(uint64_t seed, const void* seed_dev, int32_t B, int32_t T, double p_start, int32_t mask_length,
+                      int32_t R_max, int32_t* rows, uint8_t* mask, void* stream);
+int a8_negatives_draw(uint64_t seed, const void* seed_dev, const int32_t* n_valid, int32_t B, int32_t K, int32_t R_max,
+                      int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Parameter re-layout, once per step: fp32 masters in PyTorch layouts -> bf16 GEMM operands (csrc/wprep.cu).
  * a8_cast_multi: table of n entries {const float* src; void* dst; int64 numel; int64 dst_is_f32} in DEVICE memory;
  *   one launch casts / copies them all (e.g. w_Q|w_K|w_V into one fused [3D,D] bf16 operand without a concat).

@@ -493,6 +493,17 @@ class EmuOps(EmuBackend):
         dy.index_add_(0, cand.reshape(-1), dyc.reshape(-1, C))
         return dx, dy
 
+    # ---- device-side draws (csrc/draws.cu): the same Philox4x32-10 counters, Floyd subsets and multiply-high range
+    # reduction, literally, so that the kernels can be checked bit for bit
+    def span_mask_draw(self, seed, seed_dev, B, T, p_start, mask_length, R_max, device):
+        rows, mask = emu_span_mask(_eff_seed(seed, seed_dev), B, T, p_start, mask_length, R_max)
+        return torch.from_numpy(rows).to(device), torch.from_numpy(mask).to(device)
+
+    def negatives_draw(self, seed, seed_dev, rows, B, K):
+        R_max = rows.numel() - 1
+        out = emu_negatives(_eff_seed(seed, seed_dev), int(rows[R_max]), B, K, R_max)
+        return torch.from_numpy(out).to(rows.device)
+
     # ---- ctc (emulated with the installed torch op)
     def ctc_greedy(self, lp, in_len, blank):
         """literal restatement of ctc.py:161-162 per utterance"""
@@ -537,3 +548,104 @@ class EmuOps(EmuBackend):
             fin = torch.where(torch.isinf(nll_g), torch.zeros_like(nll_g), nll_g)
             (g,) = torch.autograd.grad((fin * scale).sum(), lpg)
         return torch.nan_to_num(g, nan=0.0, posinf=0.0, neginf=0.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Philox4x32-10 and the draw algorithms of csrc/draws.cu (numpy, uint64 arithmetic)
+# ---------------------------------------------------------------------------------------------------------------
+def _eff_seed(seed, seed_dev):
+    s = int(seed)
+    if seed_dev is not None:
+        s += int(seed_dev.reshape(-1)[0].item())
+    return s & 0xFFFFFFFFFFFFFFFF
+
+
+def philox4x32_10(c0, c1, c2, c3, seed):
+    """vectorised over the counter words (numpy uint64 arrays holding 32-bit values) -> four uint32-valued arrays"""
+    import numpy as np
+    M = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & M for c in (c0, c1, c2, c3))
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        h0, l0, h1, l1 = p0 >> np.uint64(32), p0 & M, p1 >> np.uint64(32), p1 & M
+        c0, c1, c2, c3 = h1 ^ c1 ^ k0, l1, h0 ^ c3 ^ k1, l0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    return c0, c1, c2, c3
+
+
+_TAG_NUM, _TAG_START, _TAG_DROP, _TAG_NEG = 1, 2, 3, 4
+
+
+def _draw32(seed, tag, row, i):
+    return int(philox4x32_10(i, row, tag, 0, seed)[0])
+
+
+def _floyd(marks, n, k, seed, tag, row):
+    import numpy as np
+    if k <= 0:
+        return
+    js = np.arange(n - k, n, dtype=np.uint64)
+    w = philox4x32_10(js, row, tag, 0, seed)[0]
+    ts = (w * (js + np.uint64(1))) >> np.uint64(32)
+    for j, t in zip(js.tolist(), ts.tolist()):
+        if marks[t]:
+            marks[j] = 1
+        else:
+            marks[t] = 1
+
+
+def emu_span_mask(seed, B, T, p_start, mask_length, R_max):
+    import numpy as np
+    L = mask_length
+    u0 = float(_draw32(seed, _TAG_NUM, 0, 0) >> 8) * (1.0 / 16777216.0)
+    num_mask = int(p_start * float(T) / float(L) + u0)
+    span = L
+    if T - span <= num_mask:
+        span = T - num_mask - 1
+    n_start = T - span
+    num_mask = min(num_mask, n_start)
+    m = np.zeros((B, T), dtype=np.uint8)
+    for b in range(B):
+        s = np.zeros(T, dtype=np.uint8)
+        _floyd(s, n_start, num_mask, seed, _TAG_START, b)
+        for t in np.flatnonzero(s[:n_start]):
+            m[b, t:min(T, t + L)] = 1
+    lens = m.sum(1).astype(np.int64)
+    keep = int(lens.min())
+    rows = np.full(R_max + 1, -1, dtype=np.int32)
+    for b in range(B):
+        drop = int(lens[b]) - keep
+        pos = np.flatnonzero(m[b])
+        if drop > 0:
+            s = np.zeros(T, dtype=np.uint8)
+            _floyd(s, int(lens[b]), drop, seed, _TAG_DROP, b)
+            m[b, pos[s[:len(pos)] != 0]] = 0
+            pos = np.flatnonzero(m[b])
+        rows[b * keep:(b + 1) * keep] = b * T + pos
+    rows[R_max] = B * keep
+    return rows, m
+
+
+def emu_negatives(seed, n_valid, B, K, R_max):
+    import numpy as np
+    total = R_max * K
+    groups = (total + 3) // 4
+    g = np.arange(groups, dtype=np.uint64)
+    w = np.stack(philox4x32_10(g & np.uint64(0xFFFFFFFF), g >> np.uint64(32), _TAG_NEG, 0, seed), 1).reshape(-1)[:total]
+    Tm = n_valid // B
+    e = np.arange(total, dtype=np.int64)
+    r = e // K
+    out = np.zeros(total, dtype=np.int64)
+    valid = r < n_valid
+    if Tm > 1:
+        b, t = r // Tm, r % Tm
+        n = ((w * np.uint64(Tm - 1)) >> np.uint64(32)).astype(np.int64)
+        n = n + (n >= t)
+        out = np.where(valid, n + b * Tm, 0)
+    else:
+        out = np.where(valid, r, 0)
+    return out.astype(np.int32)

@@ -352,6 +352,142 @@ def run_pretrain_generic(device, cfg, B, L, K, seed=3, check_grads=FULL_SIZE_GRA
     return loss.item(), st["loss"].item(), vq_match
 
 
+def check_span_mask(rows, mask, B, T, p_start, mask_length, R_max):
+    """structural invariants of a device-drawn span mask (reference wav2vec2.py:189-216)"""
+    rows = np.asarray(rows)
+    mask = np.asarray(mask).astype(bool).reshape(B, T)
+    n = int(rows[R_max])
+    assert rows.shape == (R_max + 1,) and n % B == 0 and 0 <= n <= R_max
+    assert (rows[n:R_max] == -1).all(), "padding entries must be -1"
+    assert (np.flatnonzero(mask.reshape(-1)) == rows[:n]).all(), "row list != nonzero(mask) in row-major order"
+    per_row = mask.sum(1)
+    assert (per_row == n // B).all(), f"rows hold {per_row} masked frames, expected {n // B} each"
+    nm_hi = int(p_start * T / float(mask_length) + 1.0)
+    assert n // B <= min(T, nm_hi * mask_length)
+    assert n // B >= min(T, (nm_hi - 1)) , "fewer masked frames than non-overlapping single-frame spans would give"
+    return n // B
+
+
+def check_negatives(neg, n_valid, B, K, R_max):
+    """never the positive, always inside the utterance (reference wav2vec2.py:955-976); zeros on the padding rows"""
+    neg = np.asarray(neg).reshape(R_max, K).astype(np.int64)
+    Tm = n_valid // B
+    r = np.arange(n_valid)[:, None]
+    v = neg[:n_valid]
+    assert (v != r).all(), "a negative equals its positive"
+    assert (v // Tm == r // Tm).all(), "a negative leaves its utterance"
+    assert (neg[n_valid:] == 0).all()
+
+
+def run_pretrain_device_draws(device, cfg, B, L, K, seed=3, check_grads=("mask_emb", "project_q.layer.weight",
+                                                                       "final_proj.layer.weight",
+                                                                       "feature_extractor.conv_layers.0.0.weight")):
+    """SURVEY 8f-1 device mode: span mask and negatives drawn by csrc/draws.cu inside the step.  The draws are read back
+    and handed to the oracle, so loss and gradients are held to the same bars as in the host-draw mode; the draws
+    themselves are checked structurally here and bit for bit against the emulation in test_kernels.py."""
+    from audio8_b200 import wav2vec2 as W
+    CASE[0] = f"pretrain, device draws d={cfg.get('d_model', 768)} B={B} x {L} K={K}"
+    sd = P.pretrain_state_dict(seed=11, **{k: v for k, v in cfg.items() if k != "num_heads"})
+    model = W.create_model(dropout=0.0, dropout_input=0.0, dropout_features=0.0, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device).eval()
+    G_, V_ = cfg.get("num_vq_groups", 2), cfg.get("num_vq_vars", 320)
+    loss_fn = W.create_loss(V_ * G_, K)
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(5)) * 0.1
+    T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+    model.quantizer.keep_logits = True
+    W.set_device_draws(True)
+    try:
+        torch.manual_seed(seed)
+        state = np.random.get_state()
+        with torch.no_grad():
+            out = model(x.to(device))
+        assert out[1].shape[:2] == (B, model.max_masked_rows(B, T) // B) and out[3].dtype == torch.bool
+        loss = loss_fn(model, x.to(device))
+        loss.backward()
+        assert _same_rng(state, np.random.get_state(), n_layer_draws=2 * cfg.get("num_layers", 12)), \
+            "device mode must not draw masks / negatives from numpy"
+    finally:
+        W.set_device_draws(False)
+    R_max = model.max_masked_rows(B, T)
+    rows = loss_fn.last_rows.cpu().numpy()
+    n = int(rows[R_max])
+    tmask = np.zeros(B * T, dtype=bool)
+    tmask[rows[:n]] = True
+    tmask = tmask.reshape(B, T)
+    Tm = check_span_mask(rows, tmask, B, T, 0.65, 10, R_max)
+    negp = loss_fn.last_neg_idx.cpu().numpy()
+    check_negatives(negp, n, B, K, R_max)
+    neg = negp.reshape(R_max, K)[:n].reshape(B, Tm * K).astype(np.int64)
+    kidx = model.quantizer.last_indices.cpu().numpy()[:n * G_]
+    z_ours = model.quantizer.last_logits.float().cpu()[:n]
+    okw = dict(n_vars=V_ * G_, num_heads=cfg.get("num_heads", 12), num_layers=cfg.get("num_layers", 12), num_groups=G_,
+               tau=0.5, gumbel_noise=None, conv_features=R.CONV_FEATURES[16])
+    sdz = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    st = R.pretrain_loss(sdz, x, tmask, neg, force_idx=kidx, force_z=z_ours, **okw)
+    st["loss"].backward()
+    assert abs(loss.item() - st["loss"].item()) <= 1e-2 * abs(st["loss"].item()), (loss.item(), st["loss"].item())
+    got = dict(model.named_parameters())
+    for k in check_grads:
+        grad_close(got[k].grad, sdz[k].grad, "grad [device draws] " + k, **grad_tol(k, True))
+    return loss.item(), st["loss"].item()
+
+
+def run_device_draws_replay_case():
+    """device draws inside CUDA-graph replays: a fresh mask / fresh negatives on every replay, reproducible under
+    torch.manual_seed, structurally valid every time, and the host uploads nothing"""
+    from audio8_b200 import graphs
+    from audio8_b200 import wav2vec2 as W
+    cfg = dict(TINY_PRE)
+    B, L, K = 3, 24000, 10
+    torch.manual_seed(0)
+    model = W.create_model(**cfg).cuda().train()
+    loss_fn = W.create_loss(cfg["num_vq_vars"] * cfg["num_vq_groups"], K)
+    x = torch.randn(B, L, device="cuda") * 0.1
+    T = R.conv_out_lengths(L, R.CONV_FEATURES[16])[-1]
+    R_max = model.max_masked_rows(B, T)
+    was = graphs.ENABLED
+    W.set_device_draws(True)
+    try:
+        graphs.set_enabled(True)
+        seen = []
+        for i, seed in enumerate([1, 2, 3, 4, 4, 5]):
+            torch.manual_seed(seed)
+            model.zero_grad(set_to_none=True)
+            loss = loss_fn(model, x)
+            loss.backward()
+            assert np.isfinite(loss.item())
+            rows = loss_fn.last_rows.cpu().numpy().copy()
+            neg = loss_fn.last_neg_idx.cpu().numpy().copy()
+            n = int(rows[R_max])
+            tmask = np.zeros(B * T, dtype=bool)
+            tmask[rows[:n]] = True
+            check_span_mask(rows, tmask, B, T, 0.65, 10, R_max)
+            check_negatives(neg, n, B, K, R_max)
+            assert model.mask_emb.grad is not None and model.mask_emb.grad.abs().sum().item() > 0
+            seen.append((rows, neg, loss.item()))
+        assert model._front_graph.entries and loss_fn._graph.entries, "segments were not captured"
+        assert not np.array_equal(seen[2][0], seen[3][0]), "the span mask did not change between graph replays"
+        assert not np.array_equal(seen[2][1], seen[3][1]), "the negatives did not change between graph replays"
+        assert np.array_equal(seen[3][0], seen[4][0]) and np.array_equal(seen[3][1], seen[4][1]), \
+            "the same torch seed must give the same draws"
+    finally:
+        W.set_device_draws(False)
+        graphs.set_enabled(was)
+
+
+def _same_rng(before, after, n_layer_draws):
+    """numpy's global generator advanced by at most the per-layer LayerDrop draws (one double = two 32-bit words each)"""
+    probe = np.random.RandomState()
+    probe.set_state(before)
+    for _ in range(n_layer_draws + 1):
+        st = probe.get_state()
+        if st[2] == after[2] and np.array_equal(st[1], after[1]):
+            return True
+        probe.random_sample()
+    return False
+
+
 VQ_LOG = []  # (case, code-index flips against the oracle's free arg-max, entries)
 
 

@@ -301,3 +301,78 @@ def test_fused_attention_rel_l2_and_determinism(be, qscale):
                 assert e <= 6e-3, f"{name} rel-L2 {e:.5f}"
         else:
             assert torch.equal(ctx, first[0]) and torch.equal(dqkv, first[1]), f"launch {rep} differs from launch 0"
+
+
+# ---- device-side draws (csrc/draws.cu): bit for bit against the emulation, then the distributions
+# against the reference's numpy draws
+def _rmax(B, T, p, L):
+    return B * min(T, (int(p * T / float(L)) + 1) * L)
+
+
+@pytest.mark.parametrize("B,T,p,L", [(6, 749, 0.65, 10), (1, 49, 0.65, 10), (3, 30, 0.65, 10), (40, 99, 0.65, 10),
+                                     (8, 1499, 0.5, 4), (2, 12, 0.65, 10), (4, 20, 0.05, 10)])
+def test_span_mask_draw_matches_emulation(be, B, T, p, L):
+    import model_cases
+    R_max = _rmax(B, T, p, L) + 3  # slack above the worst case is legal
+    for seed in (1, 0x9E3779B97F4A7C15, 77):
+        sd = torch.tensor([(seed * 31 + 5) & 0x3FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+        rows, mask = be.span_mask_draw(seed, sd, B, T, p, L, R_max, "cuda")
+        rows_e, mask_e = E.span_mask_draw(seed, sd.cpu(), B, T, p, L, R_max, "cpu")
+        assert torch.equal(rows.cpu(), rows_e), f"rows differ (seed {seed})"
+        assert torch.equal(mask.cpu(), mask_e), f"mask differs (seed {seed})"
+        if int(rows_e[R_max]) > 0:
+            model_cases.check_span_mask(rows_e.numpy(), mask_e.numpy(), B, T, p, L, R_max)
+        K = 7
+        neg = be.negatives_draw(seed + 1, sd, rows, B, K)
+        neg_e = E.negatives_draw(seed + 1, sd.cpu(), rows_e, B, K)
+        assert torch.equal(neg.cpu(), neg_e), f"negatives differ (seed {seed})"
+        if int(rows_e[R_max]) // B > 1:
+            model_cases.check_negatives(neg_e.numpy(), int(rows_e[R_max]), B, K, R_max)
+
+
+def test_span_mask_draw_rejects_impossible_shapes(be):
+    from audio8_b200._lib import A8Error
+    with pytest.raises(A8Error):  # R_max below the worst case
+        be.span_mask_draw(1, None, 4, 200, 0.65, 10, 10, "cuda")
+    with pytest.raises(A8Error):  # the spans cannot start at distinct frames
+        be.span_mask_draw(1, None, 1, 3, 5.0, 1, 64, "cuda")
+
+
+def test_device_draw_distributions_match_numpy_reference(be):
+    """the device mode draws from the reference's distributions: per-frame masking frequency and masked-frame count of
+    `create_mask` (numpy, reference order) vs the kernel over many seeds; negatives uniform over the other steps"""
+    from audio8_b200.wav2vec2 import create_mask
+    B, T, p, L, N = 4, 149, 0.65, 10, 400
+    R_max = _rmax(B, T, p, L)
+    np.random.seed(0)
+    f_np = np.zeros(T)
+    c_np = []
+    for _ in range(N):
+        m = create_mask((B, T), p, L)
+        f_np += m.mean(0)
+        c_np.append(m[0].sum())
+    f_dev = np.zeros(T)
+    c_dev = []
+    for s in range(N):
+        rows, mask = be.span_mask_draw(1000 + s, None, B, T, p, L, R_max, "cuda")
+        m = mask.cpu().numpy()
+        f_dev += m.mean(0)
+        c_dev.append(m[0].sum())
+    f_np /= N
+    f_dev /= N
+    # N*B = 1600 Bernoulli samples per frame: sigma <= 0.0125; spans make neighbouring frames correlated, not a frame's mean
+    assert np.abs(f_np - f_dev).max() < 0.08, np.abs(f_np - f_dev).max()  # ~4.5 sigma of a difference
+    assert abs(f_np.mean() - f_dev.mean()) < 0.01, (f_np.mean(), f_dev.mean())
+    assert abs(np.mean(c_np) - np.mean(c_dev)) < 0.03 * np.mean(c_np), (np.mean(c_np), np.mean(c_dev))
+    # the first frames are masked less often (no span can start before frame 0): the edge profile must agree too
+    assert abs(f_np[:L].mean() - f_dev[:L].mean()) < 0.03
+    # negatives: every other step of the utterance equally likely
+    rows, _ = be.span_mask_draw(5, None, 2, 60, p, L, _rmax(2, 60, p, L), "cuda")
+    n = int(rows[-1])
+    Tm, K = n // 2, 20000
+    neg = be.negatives_draw(9, None, rows, 2, K).cpu().numpy().reshape(-1, K)
+    hist = np.bincount(neg[3], minlength=n)[:Tm]  # step 3 of utterance 0
+    assert hist[3] == 0 and hist.sum() == K
+    others = np.delete(hist, 3)
+    expect = K / (Tm - 1)
+    assert np.abs(others - expect).max() < 6 * np.sqrt(expect), (others.min(), others.max(), expect)

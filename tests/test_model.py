@@ -253,3 +253,20 @@ def test_operand_copies_follow_parameter_updates_cpu(emu_backend):
 @pytest.mark.gpu
 def test_operand_copies_follow_parameter_updates_cuda():
     _operand_refresh_case("cuda", 4)
+
+
+def test_pretrain_device_draws_host_logic_cpu(emu_backend):
+    """SURVEY 8f-1 device mode through the ABI emulation: mask / negatives from the (emulated) Philox kernels, padded latents"""
+    cfg = dict(d_model=128, num_heads=2, num_layers=2, d_ff=256, final_dim=64, num_vq_vars=24, num_vq_groups=2)
+    model_cases.run_pretrain_device_draws("cpu", cfg, B=2, L=8000, K=10)
+
+
+@pytest.mark.gpu
+def test_pretrain_device_draws_cuda():
+    cfg = dict(d_model=256, num_heads=4, num_layers=2, d_ff=512, final_dim=64, num_vq_vars=32, num_vq_groups=2)
+    model_cases.run_pretrain_device_draws("cuda", cfg, B=3, L=32000, K=20)
+
+
+@pytest.mark.gpu
+def test_device_draws_graph_replays_draw_afresh_cuda():
+    model_cases.run_device_draws_replay_case()
