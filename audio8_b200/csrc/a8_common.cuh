@@ -147,6 +147,86 @@ __device__ __forceinline__ float gelu_both_fast(float x, float& dgelu) {
   dgelu = fmaf(x * 0.3989422804014327f, e, cdf);
   return x * cdf;
 }
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 do two lanes' worth of FP32 work per issue slot).  A pair lives in
+// a 64-bit register; ptxas keeps it in two adjacent 32-bit registers, so packing values that are produced next to each
+// other costs nothing, and broadcast constants become immediates.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 bc2(float c) { return pk2(c, c); }
+// gelu_both_fast on two values at once: same formulas and constants (the polynomial carries the minus sign of
+// 0.5 - p t e so that the packed FMA needs no negated operand); |x| and the two special-function ops stay scalar.
+__device__ __forceinline__ void gelu_both_fast2(float& x0, float& x1, float& d0, float& d1) {
+  const float t0 = rcp_approx(fmaf(0.23164188826636045f, fabsf(x0), 1.f));
+  const float t1 = rcp_approx(fmaf(0.23164188826636045f, fabsf(x1), 1.f));
+  const f32x2 T = pk2(t0, t1), X = pk2(x0, x1);
+  f32x2 p = fma2(bc2(-0.5307027145f), T, bc2(0.7265760135f));
+  p = fma2(p, T, bc2(-0.7107068705f));
+  p = fma2(p, T, bc2(0.142248368f));
+  p = fma2(p, T, bc2(-0.127414796f));
+  float a0, a1;
+  unpk2(mul2(mul2(X, X), bc2(-0.72134752044448170f)), a0, a1);
+  const f32x2 E = pk2(ex2_approx(a0), ex2_approx(a1));  // exp(-x^2/2)
+  float h0, h1;
+  unpk2(fma2(mul2(p, T), E, bc2(0.5f)), h0, h1);        // (1 - erf(|x|/sqrt2)) / 2 ... as 0.5 - p t e
+  const f32x2 CDF = add2(bc2(0.5f), pk2(copysignf(h0, x0), copysignf(h1, x1)));
+  unpk2(fma2(mul2(X, bc2(0.3989422804014327f)), E, CDF), d0, d1);
+  unpk2(mul2(X, CDF), x0, x1);
+}
+// gelu_fast / gelu_grad_fast on a pair (same formulas, same constants)
+__device__ __forceinline__ f32x2 gelu_fast2(f32x2 X) {
+  float x0, x1;
+  unpk2(X, x0, x1);
+  const f32x2 U = pk2(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  f32x2 p = fma2(bc2(0.0000430638f), U, bc2(0.0002765672f));
+  p = fma2(p, U, bc2(0.0001520143f));
+  p = fma2(p, U, bc2(0.0092705272f));
+  p = fma2(p, U, bc2(0.0422820123f));
+  p = fma2(p, U, bc2(0.0705230784f));
+  p = fma2(p, U, bc2(1.f));
+  p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);
+  float p0, p1;
+  unpk2(p, p0, p1);
+  float h0, h1;  // erf(|x|/sqrt2) / 2 = 0.5 - 0.5 / p
+  unpk2(fma2(pk2(rcp_approx(p0), rcp_approx(p1)), bc2(-0.5f), bc2(0.5f)), h0, h1);
+  return mul2(X, add2(bc2(0.5f), pk2(copysignf(h0, x0), copysignf(h1, x1))));
+}
+__device__ __forceinline__ f32x2 gelu_grad_fast2(f32x2 X) {
+  float x0, x1;
+  unpk2(X, x0, x1);
+  const f32x2 T = pk2(rcp_approx(fmaf(0.23164188826636045f, fabsf(x0), 1.f)),
+                      rcp_approx(fmaf(0.23164188826636045f, fabsf(x1), 1.f)));
+  f32x2 p = fma2(bc2(-0.5307027145f), T, bc2(0.7265760135f));
+  p = fma2(p, T, bc2(-0.7107068705f));
+  p = fma2(p, T, bc2(0.142248368f));
+  p = fma2(p, T, bc2(-0.127414796f));
+  float a0, a1;
+  unpk2(mul2(mul2(X, X), bc2(-0.72134752044448170f)), a0, a1);
+  const f32x2 E = pk2(ex2_approx(a0), ex2_approx(a1));
+  float h0, h1;
+  unpk2(fma2(mul2(p, T), E, bc2(0.5f)), h0, h1);
+  const f32x2 CDF = add2(bc2(0.5f), pk2(copysignf(h0, x0), copysignf(h1, x1)));
+  return fma2(mul2(X, bc2(0.3989422804014327f)), E, CDF);
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // per-step dropout seed word in device memory (a8_set_seed_source), nullable

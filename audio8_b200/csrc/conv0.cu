@@ -194,23 +194,30 @@ __global__ void __launch_bounds__(256, BWD ? 3 : 4) conv0_k10s5_kernel(const Con
   const int b = blockIdx.y;
   const int c0 = threadIdx.x * 2;
   const bool active = c0 < a.C;
-  float w[2][K], init[2], gm[2], bt[2];
+  // the thread's two channels ride in the two halves of packed fp32 pairs (FFMA2: one issue slot per tap for both)
+  f32x2 W[K], INIT, GM, BT;
+  {
+    float w[2][K], init[2], gm[2], bt[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = min(c0 + i, a.C - 1);
-    const float mu = a.mean[b * a.C + c], rs = a.rstd[b * a.C + c];
-    gm[i] = a.gamma[c];
-    bt[i] = a.beta[c];
-    const float sc = BWD ? rs : rs * gm[i];
-    init[i] = BWD ? -mu * rs : bt[i] - mu * sc;
+    for (int i = 0; i < 2; ++i) {
+      const int c = min(c0 + i, a.C - 1);
+      const float mu = a.mean[b * a.C + c], rs = a.rstd[b * a.C + c];
+      gm[i] = a.gamma[c];
+      bt[i] = a.beta[c];
+      const float sc = BWD ? rs : rs * gm[i];
+      init[i] = BWD ? -mu * rs : bt[i] - mu * sc;
 #pragma unroll
-    for (int j = 0; j < K; ++j) w[i][j] = a.w[c * K + j] * sc;
+      for (int j = 0; j < K; ++j) w[i][j] = a.w[c * K + j] * sc;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) W[j] = pk2(w[0][j], w[1][j]);
+    INIT = pk2(init[0], init[1]);
+    GM = pk2(gm[0], gm[1]);
+    BT = pk2(bt[0], bt[1]);
   }
-  float acc1[2] = {0.f, 0.f}, acc2[2] = {0.f, 0.f}, accx[2][K];
+  f32x2 ACC1 = bc2(0.f), ACC2 = bc2(0.f), ACCX[K];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < K; ++j) accx[i][j] = 0.f;
+  for (int j = 0; j < K; ++j) ACCX[j] = bc2(0.f);
 
   const float* xb = a.x + (long long)b * a.L;
   const int t_begin = blockIdx.x * a.rows_per_cta;
@@ -240,34 +247,32 @@ __global__ void __launch_bounds__(256, BWD ? 3 : 4) conv0_k10s5_kernel(const Con
       }
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        float z[2];
+        f32x2 Z = INIT;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float t = init[i];
-#pragma unroll
-          for (int j = 0; j < K; ++j) t = fmaf(w[i][j], xv[rr * S + j], t);
-          z[i] = t;
-        }
+        for (int j = 0; j < K; ++j) Z = fma2(W[j], bc2(xv[rr * S + j]), Z);
         if (!BWD) {
-          if (r + rr < nrows)
-            *reinterpret_cast<uint32_t*>(a.y + off0 + (long long)(r + rr) * a.C) = pack_bf16(gelu_fast(z[0]), gelu_fast(z[1]));
+          if (r + rr < nrows) {
+            float y0, y1;
+            unpk2(gelu_fast2(Z), y0, y1);
+            *reinterpret_cast<uint32_t*>(a.y + off0 + (long long)(r + rr) * a.C) = pack_bf16(y0, y1);
+          }
         } else {
           const float2 d = unpack_bf16(dr[rr]);  // zero beyond the tile's last row: contributes nothing
-          const float dd[2] = {d.x, d.y};
+          const f32x2 DY = mul2(pk2(d.x, d.y), gelu_grad_fast2(fma2(Z, GM, BT)));  // Z = xhat here
+          ACC1 = add2(ACC1, DY);
+          ACC2 = fma2(DY, Z, ACC2);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float xh = z[i];
-            const float dy = dd[i] * gelu_grad_fast(fmaf(xh, gm[i], bt[i]));
-            acc1[i] += dy;
-            acc2[i] = fmaf(dy, xh, acc2[i]);
-#pragma unroll
-            for (int j = 0; j < K; ++j) accx[i][j] = fmaf(dy, xv[rr * S + j], accx[i][j]);
-          }
+          for (int j = 0; j < K; ++j) ACCX[j] = fma2(DY, bc2(xv[rr * S + j]), ACCX[j]);
         }
       }
     }
   }
   if (BWD && active) {
+    float acc1[2], acc2[2], accx[2][K];
+    unpk2(ACC1, acc1[0], acc1[1]);
+    unpk2(ACC2, acc2[0], acc2[1]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) unpk2(ACCX[j], accx[0][j], accx[1][j]);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       if (c0 + i < a.C) {

@@ -264,21 +264,22 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
 #pragma unroll
     for (int i = 0; i < CW / 4; ++i) {
       const float4 b4 = sb4[i];
-      v[4 * i] = fmaf(__uint_as_float(r[4 * i]), alpha, b4.x);
-      v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), alpha, b4.y);
-      v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), alpha, b4.z);
-      v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), alpha, b4.w);
+      unpk2(fma2(pk2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), bc2(alpha), pk2(b4.x, b4.y)),
+            v[4 * i], v[4 * i + 1]);
+      unpk2(fma2(pk2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), bc2(alpha), pk2(b4.z, b4.w)),
+            v[4 * i + 2], v[4 * i + 3]);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+    for (int i = 0; i < CW; i += 2)
+      unpk2(mul2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), bc2(alpha)), v[i], v[i + 1]);
   }
   if (do_gelu_dz) {  // the activation and its derivative from one erf / exp evaluation; the derivative goes to z_out as fp16
 #pragma unroll
     for (int g = 0; g < NP; ++g) {
       float d[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[8 * g + j] = gelu_both_fast(v[8 * g + j], d[j]);
+      for (int j = 0; j < 8; j += 2) gelu_both_fast2(v[8 * g + j], v[8 * g + j + 1], d[j], d[j + 1]);
       if (do_z) my[g] = make_uint4(pack_f16(d[0], d[1]), pack_f16(d[2], d[3]), pack_f16(d[4], d[5]), pack_f16(d[6], d[7]));
     }
   } else if (do_z) {
@@ -307,11 +308,9 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       for (int j = 0; j < 4; ++j) {
         const float2 t = (aux_mode == AUX_MUL) ? unpack_f16(w[j]) : unpack_bf16(w[j]);
         if (aux_mode == AUX_ADD) {
-          v[8 * g + 2 * j] += t.x;
-          v[8 * g + 2 * j + 1] += t.y;
+          unpk2(add2(pk2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]), pk2(t.x, t.y)), v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
         } else if (aux_mode == AUX_MUL) {
-          v[8 * g + 2 * j] *= t.x;
-          v[8 * g + 2 * j + 1] *= t.y;
+          unpk2(mul2(pk2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1]), pk2(t.x, t.y)), v[8 * g + 2 * j], v[8 * g + 2 * j + 1]);
         } else {
           v[8 * g + 2 * j] *= gelu_grad_fast(t.x);
           v[8 * g + 2 * j + 1] *= gelu_grad_fast(t.y);

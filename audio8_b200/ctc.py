@@ -101,8 +101,12 @@ class CTCLoss(torch.nn.Module):
 
     def forward(self, log_prob, input_lengths, targets, target_lengths):
         O = _offsets()
-        return ctc_loss(log_prob, input_lengths, targets, target_lengths, blank=O.GO, pad=O.PAD, eos=O.EOS,
+        loss = ctc_loss(log_prob, input_lengths, targets, target_lengths, blank=O.GO, pad=O.PAD, eos=O.EOS,
                         reduction=self.reduction_type, zero_infinity=self.zero_infinity)
+        from . import feed
+        if feed._DEFERRED:  # the step's forward is enqueued: the input feed may post its next H2D copy now
+            feed.flush_deferred()
+        return loss
 
 
 def greedy_decode(log_probs, input_lengths=None, blank=None):

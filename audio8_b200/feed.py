@@ -88,6 +88,17 @@ class PinnedRing:
         return k, views
 
 
+_DEFERRED = []  # feeds that still owe the copy stream one batch (see DeviceFeed.__next__)
+
+
+def flush_deferred():
+    """post the H2D copies that `DeviceFeed.__next__` put off.  The loss objects call this once the step's forward has
+    been enqueued, so the ~60 us of host work a copy launch costs (stream switch, allocation, event) is spent while the
+    GPU is already busy instead of between handing out a batch and the step's first kernel."""
+    while _DEFERRED:
+        _DEFERRED.pop()._launch()
+
+
 class DeviceFeed:
     """Iterator adaptor: host batches (a single numpy array / pinned tensor or a tuple of them) -> device tensors,
     `depth` batches ahead."""
@@ -129,6 +140,8 @@ class DeviceFeed:
         return self
 
     def __next__(self):
+        if self in _DEFERRED:  # nobody flushed since the last batch was handed out
+            _DEFERRED.remove(self)
         while len(self.queue) < self.depth and self._launch():
             pass
         if not self.queue:
@@ -138,7 +151,10 @@ class DeviceFeed:
             torch.cuda.current_stream(self.device).wait_event(ev)  # GPU-side ordering; the host does not block
             for t in (out if isinstance(out, tuple) else (out,)):
                 t.record_stream(torch.cuda.current_stream(self.device))
-        self._launch()
+        if self.queue and self.stream is not None:
+            _DEFERRED.append(self)  # a batch is still in flight: the refill waits for flush_deferred() / the next call
+        else:
+            self._launch()
         return out
 
 

@@ -802,6 +802,13 @@ def _forward_device_draws(self, x, B, T):
 Wav2Vec2Model._forward_device_draws = _forward_device_draws
 
 
+def _flush_feed():
+    """the forward of the step is enqueued: let the input feed post its next H2D copy now (feed.flush_deferred)"""
+    from . import feed
+    if feed._DEFERRED:
+        feed.flush_deferred()
+
+
 class Wav2Vec2Loss(nn.Module):
     """Reference wav2vec2.py:371-392: 0.1 * CE(cos-sim logits over [positive | K negatives]) + 10 * (n_vars - ppl) / n_vars."""
 
@@ -842,8 +849,11 @@ class Wav2Vec2Loss(nn.Module):
 
             if gs_probs.requires_grad and outputs.requires_grad:
                 graph = self.__dict__.setdefault("_graph", GraphedSegment("contrastive loss (gather, cosine logits, CE)"))
-                return graph.run(fn, (outputs, y2, gs_probs, rows), (), extra=(self.n_vars, K, B, "device draws"))
-            return fn(outputs, y2, gs_probs, rows)
+                loss = graph.run(fn, (outputs, y2, gs_probs, rows), (), extra=(self.n_vars, K, B, "device draws"))
+            else:
+                loss = fn(outputs, y2, gs_probs, rows)
+            _flush_feed()
+            return loss
         # numpy draws, bit-exact with the reference's Sampler (already made on the helper thread when `draws`)
         neg = draws.negatives() if draws is not None else self.sample.indices32(B, Tm)
         assert neg.shape == (B, self.sample.n_negatives * Tm)
@@ -862,6 +872,7 @@ class Wav2Vec2Loss(nn.Module):
             loss = graph.run(self._loss, (outputs, y2, gs_probs, rows, idx), (), extra=(self.n_vars, K))
         else:
             loss = self._loss(outputs, y2, gs_probs, rows, idx)
+        _flush_feed()
         return loss
 
     def _loss(self, outputs, y2, gs_probs, rows, idx):

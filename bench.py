@@ -362,7 +362,11 @@ def _run_ours(args):
         crit = CTCLoss()
     else:  # the headline: wav2vec2-base defaults, 12L d=768, dropout 0.1, G=2 V=320 (BASELINE configs[1]; large = configs[3])
         model = W.create_model(**mkw).to(dev)
-        W.set_prefetch_draws(True)  # next step's numpy draws (same numbers, same order) while the GPU runs this step
+        # span mask + negatives: drawn on the device inside the step's CUDA graphs (csrc/draws.cu; the reference's
+        # distributions, seeded by torch's CUDA generator), or --draws host: numpy's global generator in the reference's call
+        # order (its exact numbers), drawn one step ahead on a helper thread
+        W.set_device_draws(args.draws == "device")
+        W.set_prefetch_draws(True)
     model.train()
     loss_fn = W.create_loss(N_VARS, N_NEG)
     net = model
@@ -511,6 +515,31 @@ def _run_ours(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = world * B * CROP_S / (dt.item() / args.steps)
 
+    # ---- the same end-to-end loop with the OTHER draw mode's host path (informational, one GPU only): numpy draws in the
+    # reference's order (prefetched) + the padded index uploads, i.e. the mode whose masks / negatives are bit-identical to
+    # the reference's
+    e2e_host = None
+    if not ctc and world == 1 and args.draws == "device" and not force_dp:
+        W.set_device_draws(False)
+        try:
+            for _ in range(10):  # eager step, capture of the host-draw segments, replays
+                loss = step(upload())
+                loss.item()
+            gc.collect()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                loss = step(upload())
+                loss.item()
+            e2e_host = {"value": B * CROP_S / ((time.perf_counter() - t0) / args.steps), "unit": "audio-s/s",
+                        "what": "the e2e loop with --draws host: numpy global-RNG draws in the reference's call order "
+                                "(bit-identical masks / negatives), prefetched one step ahead, index lists uploaded"}
+        finally:
+            W.set_device_draws(True)
+            W._HostDraws._pending = None
+        for _ in range(2):
+            step(dev_in)
+
     # ---- host-side enqueue time of one step (queue empty at start, no sync inside): the launch-overhead floor
     gc.collect()
     barrier()
@@ -618,8 +647,9 @@ def _run_ours(args):
                 "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                 "launch": "the step is 4 CUDA-graph segments (front+mask, quantizer branch, encoder, loss), fwd and bwd; "
                           "masked-row lists padded to their worst-case length; "
-                          + ("span mask and negatives drawn on the device inside the segments (csrc/draws.cu, A8_DEVICE_DRAWS=1: "
-                             "the reference's distributions, not its numpy numbers)" if (not ctc and W._DEVICE_DRAWS[0]) else
+                          + ("span mask and negatives drawn on the device inside the segments (csrc/draws.cu, --draws device: "
+                             "the reference's distributions, not its numpy numbers; e2e_host_draws = the numpy mode)"
+                             if (not ctc and W._DEVICE_DRAWS[0]) else
                              "host draws (numpy, the reference's numbers) prefetched one step ahead"),
                 "operands": "bf16 / packed operand copies of the parameters are rebuilt when a parameter changes (version "
                             "counter), i.e. once per optimizer step; the fwd+bwd loop of `value` never changes them, "
@@ -630,6 +660,7 @@ def _run_ours(args):
             "gpu_launches": int(launches),
             "gpu_launches_per_step": launches / args.steps,
             "host_enqueue_ms_per_step": host_ms,
+            "e2e_host_draws": e2e_host,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic, "traffic_unit": "bytes per launch",
@@ -658,6 +689,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--draws", default="device", choices=["device", "host"],
+                    help="pretrain workload: where the span mask and the negatives are drawn (see audio8_b200.wav2vec2.set_device_draws)")
     ap.add_argument("--no-incumbent", action="store_true", help="skip the eager-PyTorch GPU incumbent leg")
     ap.add_argument("--workload", default="pretrain", choices=["pretrain", "ctc"],
                     help="pretrain = BASELINE configs[1] (the driver's line); ctc = configs[2] (CTC fine-tuning step)")
