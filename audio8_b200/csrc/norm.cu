@@ -113,8 +113,11 @@ __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpre
 // NCH chunks of 8 elements per lane (C <= NCH*256); FULL: C == NCH*256, no column guards; HAS_H: residual input.
 // Every global load of a row is issued before the first dependent instruction (the earlier version interleaved one
 // load, its Philox mask and its arithmetic per chunk behind branches: nine serial memory round trips per row).
+// gamma / beta are read where they are used (a warp normally owns ONE row, so holding them in 2 x 8 x NCH registers bought
+// nothing and capped the kernel at 2 CTAs per SM: the 4494-row launches ran as two waves): with <= 64 registers the
+// whole launch is resident at once.
 template <int NCH, bool FULL, bool HAS_H>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
+__global__ void __launch_bounds__(256, NCH <= 3 ? 4 : 2) ln_fwd_kernel(const LnFwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   const unsigned long long sbase = seed_base(a.seed_src);
@@ -122,15 +125,6 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int C = a.C;
   const float invC = 1.f / (float)C;
-  float g[NCH][8], bt[NCH][8];
-#pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int c = (lane + 32 * i) * 8;
-    const bool ok = FULL || c < C;
-    const int cc = ok ? c : 0;
-    load8f(a.gamma + cc, g[i]);
-    load8f(a.beta + cc, bt[i]);
-  }
   for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.R; row += warps) {
     const long long ro = (long long)row * C;
     uint4 xr[NCH], hr[NCH];
@@ -182,10 +176,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
     for (int i = 0; i < NCH; ++i) {
       const int c = (lane + 32 * i) * 8;
       if (FULL || c < C) {
-        float o[8];
+        float o[8], g[8], bt[8];
+        load8f(a.gamma + c, g);
+        load8f(a.beta + c, bt);
         const DropMask8 d = drop_mask8(a.p_y, a.seed_y + sbase, (unsigned long long)(ro + c) >> 3);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = ((v[i][j] - mu) * rs * g[i][j] + bt[i][j]) * d.m[j];
+        for (int j = 0; j < 8; ++j) o[j] = ((v[i][j] - mu) * rs * g[j] + bt[j]) * d.m[j];
         store8(a.y + ro + c, o);
         if (a.y_f32 != nullptr) store8f(a.y_f32 + ro + c, o);
       }
