@@ -28,7 +28,7 @@ class Gemm(C.Structure):
                 ("block_n", C.c_int32), ("c", C.c_void_p), ("c_dtype", C.c_int32), ("act", C.c_int32),
                 ("ldc", C.c_int64), ("c_stride_lo", C.c_int64), ("c_stride_hi", C.c_int64), ("z_out", C.c_void_p),
                 ("aux", C.c_void_p), ("aux_mode", C.c_int32), ("bias_stride_lo", C.c_int32), ("bias", C.c_void_p),
-                ("alpha", C.c_float), ("reserved", C.c_int32)]
+                ("alpha", C.c_float), ("reserved", C.c_int32), ("colsum", C.c_void_p)]
 
 
 class A8Error(RuntimeError):

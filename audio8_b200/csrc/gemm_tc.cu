@@ -142,12 +142,16 @@ extern "C" int a8_gemm(const a8_gemm_t* gp, void* stream_v) {
   copy_coef(kp.b, g.b);
   kp.c = g.c; kp.c_dtype = g.c_dtype; kp.z_out = g.z_out; kp.aux = g.aux; kp.aux_mode = g.aux_mode;
   kp.bias = g.bias; kp.bias_stride_lo = g.bias_stride_lo; kp.act = g.act; kp.alpha = g.alpha;
+  kp.colsum = g.colsum;
   kp.ldc = g.ldc; kp.c_stride_lo = g.c_stride_lo; kp.c_stride_hi = g.c_stride_hi;
   kp.trace = g_trace;
   const long long tiles = (long long)kp.m_tiles * kp.n_tiles * kp.lo_count * kp.hi_count * split;
   A8_REQUIRE(tiles < (1ll << 30), "gemm: too many tiles");
   kp.total_tiles = (int)tiles;
 
+  A8_REQUIRE(g.colsum == nullptr || (g.aux_mode == AUX_MUL && g.c_dtype == OUT_BF16 && split == 1 && kp.lo_count == 1 &&
+                                     kp.hi_count == 1 && mode != A8_GEMM_TAP_WINDOW),
+             "gemm: colsum needs A8_AUX_MUL, bf16 output, no split-K, one (hi, lo) block and the plain / pair kernel");
   if (mode == A8_GEMM_TAP_WINDOW) return launch_window(g, kp, (g.reserved >> 8) & 0xFF, stream);
 
   CUtensorMap ma, mb;
@@ -216,7 +220,7 @@ extern "C" int a8_gemm_group_prepare(const a8_gemm_t* gs, int32_t n, void* blob_
     A8_REQUIRE(g.a.major == g0.a.major && g.b.major == g0.b.major && g.block_n == g0.block_n && g.reserved == g0.reserved &&
                    g.c_dtype == g0.c_dtype && g.split_k == g0.split_k && g.k_inner == g0.k_inner && g.alpha == g0.alpha,
                "gemm_group[%d]: majors / tile shape / output type / split / k_inner / alpha differ from problem 0", i);
-    A8_REQUIRE(g.act == ACT_NONE && g.z_out == nullptr && g.aux == nullptr && g.bias == nullptr &&
+    A8_REQUIRE(g.act == ACT_NONE && g.z_out == nullptr && g.aux == nullptr && g.bias == nullptr && g.colsum == nullptr &&
                    (g.lo_count <= 1) && (g.hi_count <= 1),
                "gemm_group[%d]: epilogue extras and batched problems are not supported in groups", i);
     A8_REQUIRE(memcmp(g.a.base, g0.a.base, sizeof(int32_t) * 24) == 0 && memcmp(g.b.base, g0.b.base, sizeof(int32_t) * 24) == 0,

@@ -61,6 +61,7 @@ struct KParams {
   long long ldc, c_stride_lo, c_stride_hi;
   int total_tiles;
   long long* trace;  // debug timeline (a8_gemm_set_trace), normally null
+  float* colsum;     // nullable: += column sums of the stored bf16 output (a8_gemm_t::colsum)
 };
 
 // Grouped launch (a8_gemm_group): ONE persistent kernel walks the tiles of up to GROUP_MAX problems that share operand
@@ -327,6 +328,18 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       my[g] = o;
     }
     __syncwarp();
+    if ((GEN || aux_mode == AUX_MUL) && p.colsum != nullptr) {
+      // bias gradient of the producing layer, from the staged tile: lane l sums column l over the warp's 32 rows (rows of
+      // the staging buffer are 80 B apart: a column's 32 reads touch 16 banks twice through the same words, no conflict)
+      float cs = 0.f;
+      if (lane < CW) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr)
+          if (rr < rows_valid)
+            cs += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(stg + rr * STG_PITCH + lane * 2)) << 16);
+        if (nb + lane < tc.N) atomicAdd(p.colsum + nb + lane, cs);
+      }
+    }
     stage_copy<2, STG_STORE, NP>(stg, cptr, row_off0, ldc, nb, rows_valid, cols_valid, lane);
     __syncwarp();
   } else {  // fp32: plain stores, or vector reductions for split-K partial sums; 16 columns (64 B per row) at a time

@@ -616,8 +616,8 @@ class EncoderFn(torch.autograd.Function):
                 df = ds2
             deferred.append(G.linear_wgrad_grouped(df, L["hid"], dw2))
             dz1 = _empty((M, F_), BF16, x)
-            be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL))
-            db1 = be.colsum(dz1, out=db1)
+            # (the bias gradient db1 = column sums of dz1 comes out of the same epilogue: no separate pass over dz1)
+            be.gemm(G.linear_dgrad(df, w2_b, dz1, aux=L["z1"], aux_mode=AUX_MUL, colsum=db1))
             deferred.append(G.linear_wgrad_grouped(dz1, L["x1"], dw1))
             dx1 = _empty((M, D), BF16, x)
             be.gemm(G.linear_dgrad(dz1, w1_b, dx1, aux=ds2, aux_mode=AUX_ADD))

@@ -153,8 +153,9 @@ def linear_fwd(x, w, out, bias=None, act=ACT_NONE, z_out=None, aux=None, aux_mod
 
 
 @cached_spec
-def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
-    """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | * aux | + aux)."""
+def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16, colsum=None):
+    """dx[M,K] = dy[M,N] w[N,K]  (w read MN-major: no transposed weight copy) (* gelu'(aux) | * aux | + aux).
+    colsum (fp32 [K], zeroed; AUX_MUL only): += column sums of dx as stored — the bias gradient of the layer below."""
     M, N = dy.shape
     K = w.shape[1]
     a = Op(dy, (N, M), (N,), MAJOR_K, ck=(64, 0, 0, 0), cr=(0, 1, 0, 0))
@@ -162,7 +163,7 @@ def linear_dgrad(dy, w, dx, aux=None, aux_mode=AUX_NONE, c_dtype=OUT_BF16):
     epi = "gelu" if aux_mode == AUX_MUL_GELU_GRAD else ("f32" if c_dtype == OUT_F32 else "bf16")
     bn, _, cl = _tiling(M, K, cdiv(N, 64), epi=epi, prefer192=True) if K > 128 else (0, 1, 1)
     return _with_flops(GemmSpec(a, b, M, K, cdiv(N, 64), dx, K, c_dtype, aux=aux, aux_mode=aux_mode, block_n=bn,
-                                cluster=cl), 2 * M * N * K)
+                                cluster=cl, colsum=colsum), 2 * M * N * K)
 
 
 @cached_spec

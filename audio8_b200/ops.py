@@ -37,7 +37,8 @@ class GemmSpec:
 
     def __init__(self, a, b, M, N, k_blocks, c, ldc, c_dtype=OUT_BF16, lo_count=1, hi_count=1, k_inner=None,
                  split_k=1, block_n=0, c_offset=0, c_stride_lo=0, c_stride_hi=0, act=ACT_NONE, z_out=None,
-                 aux=None, aux_mode=AUX_NONE, bias=None, bias_stride_lo=0, alpha=1.0, cluster=1, window_k16=None):
+                 aux=None, aux_mode=AUX_NONE, bias=None, bias_stride_lo=0, alpha=1.0, cluster=1, window_k16=None,
+                 colsum=None):
         self.a, self.b, self.M, self.N, self.k_blocks = a, b, M, N, k_blocks
         self.k_inner = k_inner if k_inner is not None else k_blocks
         self.c, self.ldc, self.c_dtype, self.c_offset = c, ldc, c_dtype, c_offset
@@ -48,6 +49,9 @@ class GemmSpec:
         self.cluster = cluster  # 2: CTA pair per 256 x BN tile (cta_group::2); block_n 128 / 256 (192 with a K-major B)
         # not None: tap-window kernel (A8_GEMM_TAP_WINDOW), the value = 16-wide k-steps per tap that hold non-zero weights
         self.window_k16 = window_k16
+        # fp32 [N] accumulator (zeroed by the caller) that receives the column sums of the stored bf16 output: the bias
+        # gradient of the layer whose output gradient this GEMM produces (a8_gemm_t::colsum; AUX_MUL epilogues only)
+        self.colsum = colsum
         self.flops = 0  # algorithmic 2*MACs of this launch (set by gemm_specs builders; bench accounting only)
 
 
@@ -190,7 +194,7 @@ class CudaBackend:
             fz.ref = C.byref(st)
             # pointer field -> (index of the argument tensor that owns it, byte offset from that tensor's data_ptr)
             fields = [("a", spec.a.t, st.a.ptr), ("b", spec.b.t, st.b.ptr), ("c", spec.c, st.c), ("z", spec.z_out, st.z_out),
-                      ("x", spec.aux, st.aux), ("s", spec.bias, st.bias)]
+                      ("x", spec.aux, st.aux), ("s", spec.bias, st.bias), ("q", spec.colsum, st.colsum)]
             fz.slots = []
             for name, t, val in fields:
                 if t is None:
@@ -216,6 +220,8 @@ class CudaBackend:
                 st.z_out = p
             elif name == "x":
                 st.aux = p
+            elif name == "q":
+                st.colsum = p
             else:
                 st.bias = p
         if self.profiler is not None:
@@ -274,6 +280,9 @@ class CudaBackend:
             assert g.bias.dtype == torch.float32 and g.bias.is_cuda
             s.bias = g.bias.data_ptr()
         s.alpha = float(g.alpha)
+        if g.colsum is not None:
+            assert g.colsum.dtype == torch.float32 and g.colsum.is_cuda and g.colsum.numel() >= g.N and g.aux_mode == AUX_MUL
+            s.colsum = g.colsum.data_ptr()
         s.reserved = 2 if g.cluster == 2 else 0
         if g.window_k16 is not None:
             s.reserved = 3 | (int(g.window_k16) << 8)

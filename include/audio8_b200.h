@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define A8_ABI_VERSION 2
+#define A8_ABI_VERSION 3
 
 int a8_version(void);
 const char* a8_last_error(void);
@@ -93,6 +93,10 @@ typedef struct {
                                  its data gradient).  Same result as the plain kernel; the rows the taps share are staged
                                  once per 8 k-blocks instead of once per k-block.  Bits 8..15 (window only): how many of the
                                  four 16-element k-steps of a k-block hold non-zero B columns (0 = all), the rest is skipped. */
+  float* colsum;              /* optional fp32 [N], accumulated into (zeroed by the caller): column sums over the M rows of
+                                 the bf16 output as stored, i.e. the bias gradient of the layer whose output gradient this
+                                 GEMM produces (`db1 = sum_rows(dY W2 * gelu')`).  Only with A8_AUX_MUL, bf16 output, no
+                                 split-K, lo_count = hi_count = 1, plain / pair kernels. */
 } a8_gemm_t;
 
 int a8_gemm(const a8_gemm_t* p, void* stream);

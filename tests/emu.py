@@ -94,6 +94,8 @@ def emu_gemm(g):
                         c[off] += v
                     else:
                         c[off] = v.to(c.dtype)
+                        if getattr(g, "colsum", None) is not None:  # column sums of the output as stored
+                            g.colsum[n0:n0 + nv] += c[off].float().sum(0)
 
 
 class EmuBackend:

@@ -39,16 +39,19 @@ def case_linear_fwd(dev, M=300, K=192, N=136, act=ACT_GELU, f32=False):
     return spec, check
 
 
-def case_linear_dgrad(dev, M=260, N=200, K=320, mode=AUX_MUL_GELU_GRAD):
+def case_linear_dgrad(dev, M=260, N=200, K=320, mode=AUX_MUL_GELU_GRAD, colsum=False):
     dy, w, z = _r((M, N), dev, 5), _r((N, K), dev, 6, 0.1), _r((M, K), dev, 7)
     if mode == AUX_MUL:  # the stored gelu' factors are fp16
         z = z.to(torch.float16)
     dx = torch.zeros(M, K, dtype=torch.bfloat16, device=dev)
-    spec = G.linear_dgrad(dy, w, dx, z, mode)
+    cs = torch.full((K,), 0.5, dtype=torch.float32, device=dev) if colsum else None  # accumulated INTO: starts non-zero
+    spec = G.linear_dgrad(dy, w, dx, z, mode, colsum=cs)
 
     def check():
         f = gelu_grad(z.float()) if mode == AUX_MUL_GELU_GRAD else z.float()
         _cmp(dx, (dy.float() @ w.float()) * f, 1e-2, "linear dgrad")
+        if colsum:  # the fused bias gradient: column sums of the output AS STORED (bf16), fp32 accumulation
+            _cmp(cs, 0.5 + dx.float().sum(0), 1e-4, "linear dgrad column sums")
     return spec, check
 
 
@@ -191,6 +194,8 @@ ALL_CASES = dict(
     linear_fwd_gelu_dz=lambda dev: case_linear_fwd(dev, act=ACT_GELU_DZ),
     linear_dgrad=case_linear_dgrad,
     linear_dgrad_mul=lambda dev: case_linear_dgrad(dev, mode=AUX_MUL),
+    linear_dgrad_mul_colsum=lambda dev: case_linear_dgrad(dev, mode=AUX_MUL, colsum=True),
+    linear_dgrad_mul_colsum_ffn=lambda dev: case_linear_dgrad(dev, M=1000, N=256, K=1024, mode=AUX_MUL, colsum=True),
     linear_wgrad=case_linear_wgrad,
     conv_fwd=case_conv_fwd,
     conv_fwd_k2=lambda dev: case_conv_fwd(dev, Lin=200, k=2, s=2),

@@ -25,7 +25,7 @@ def test_header_symbols_exported_and_bound():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
         assert len(_lib.SIGNATURES[name][1]) == nargs, f"{name}: header has {nargs} args, ctypes table {len(_lib.SIGNATURES[name][1])}"
     assert set(_lib.SIGNATURES) == set(decl)
-    assert lib.a8_version() == 2
+    assert lib.a8_version() == 3
 
 
 def test_struct_layout_matches_header():
