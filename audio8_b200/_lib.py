@@ -61,7 +61,7 @@ SIGNATURES.update({
     "a8_layernorm_fwd": (_I, [_P, _P, _F, _U, _P, _P, _P, _F, _P, _P, _F, _U, _P, _P, _I, _I, _P]),
     "a8_layernorm_bwd": (_I, [_P, _P, _F, _U, _P, _P, _P, _P, _P, _P, _F, _U, _P, _P, _P, _I, _I, _P]),
     "a8_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _U, _P]),
-    "a8_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _U, _P]),
+    "a8_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _U, _P]),
     "a8_attn_dropmask": (_I, [_P, _I, _I, _I, _F, _U, _P]),
     "a8_colsum": (_I, [_P, _L, _I, _I, _P, _P]),
     "a8_dropout": (_I, [_P, _P, _I, _L, _F, _U, _P]),

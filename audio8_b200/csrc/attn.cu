@@ -55,6 +55,7 @@ struct AttnArgs {
   float* lse;                     // [B,H,T]  log2-sum-exp2 of the scaled scores
   float* delta;                   // [B,H,T]  rowsum(dO * O)
   __nv_bfloat16* dqkv;            // bwd out [B,T,3D]
+  float* dbias;                   // bwd, nullable [3D]: += column sums of dqkv as stored (the QKV bias gradient)
   long long* trace;               // A8_ATTN_TRACE builds: [5 CTAs][3 roles][64] clock64 stamps (scripts/attn_trace.py)
 };
 
@@ -106,6 +107,27 @@ __device__ __forceinline__ uint32_t valid_word(const unsigned char* keep, int T,
     if (k < T && (keep == nullptr || keep[k] != 0)) w |= (1u << i);
   }
   return w;
+}
+
+// Column sums of a 32 (lanes = rows) x 32 (registers = columns) tile: 5 exchange steps, each halves the number of live
+// columns per lane (31 shuffles in all); on return lane l holds the sum of column l in v[0].
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+// the two bf16 values of a packed pair, as the fp32 numbers the consumer of the stored tensor will read
+__device__ __forceinline__ void bf16_pair_values(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xFFFF0000u);
 }
 
 // shared prologue: barrier ids are kernel specific; TMEM allocation by warp 2
@@ -572,7 +594,8 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     uint32_t r[32];
     tmem_ld_32x32(tdQ + half * 32, r);
     tmem_ld_wait();
-    if (row < a.T) {
+    float cs[32];
+    {
       __nv_bfloat16* dst = a.dqkv + ((long long)b * a.T + row) * (3 * D) + h * 64 + half * 32;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -581,8 +604,17 @@ attn_dq_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         o.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
         o.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
         o.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+        if (row < a.T) *reinterpret_cast<uint4*>(dst + g * 8) = o;
+        if (row >= a.T) o = make_uint4(0u, 0u, 0u, 0u);
+        bf16_pair_values(o.x, cs[8 * g + 0], cs[8 * g + 1]);
+        bf16_pair_values(o.y, cs[8 * g + 2], cs[8 * g + 3]);
+        bf16_pair_values(o.z, cs[8 * g + 4], cs[8 * g + 5]);
+        bf16_pair_values(o.w, cs[8 * g + 6], cs[8 * g + 7]);
       }
+    }
+    if (a.dbias != nullptr) {  // QKV bias gradient: column sums of this CTA's rows of dQ (no separate pass over dqkv)
+      const float t = warp_colsum32(cs, lane);
+      atomicAdd(a.dbias + h * 64 + half * 32 + lane, t);
     }
   }
 
@@ -785,16 +817,24 @@ attn_dkv_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     for (int ch = 0; ch < 2; ++ch) {
       tmem_ld_32x32(src + ch * 32, r);
       tmem_ld_wait();
-      if (key < a.T) {
+      float cs[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(r[8 * g + 0]) * sc, __uint_as_float(r[8 * g + 1]) * sc);
-          o.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * sc, __uint_as_float(r[8 * g + 3]) * sc);
-          o.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * sc, __uint_as_float(r[8 * g + 5]) * sc);
-          o.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * sc, __uint_as_float(r[8 * g + 7]) * sc);
-          *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) = o;
-        }
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(r[8 * g + 0]) * sc, __uint_as_float(r[8 * g + 1]) * sc);
+        o.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * sc, __uint_as_float(r[8 * g + 3]) * sc);
+        o.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * sc, __uint_as_float(r[8 * g + 5]) * sc);
+        o.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * sc, __uint_as_float(r[8 * g + 7]) * sc);
+        if (key < a.T) *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) = o;
+        if (key >= a.T) o = make_uint4(0u, 0u, 0u, 0u);
+        bf16_pair_values(o.x, cs[8 * g + 0], cs[8 * g + 1]);
+        bf16_pair_values(o.y, cs[8 * g + 2], cs[8 * g + 3]);
+        bf16_pair_values(o.z, cs[8 * g + 4], cs[8 * g + 5]);
+        bf16_pair_values(o.w, cs[8 * g + 6], cs[8 * g + 7]);
+      }
+      if (a.dbias != nullptr) {  // QKV bias gradient, K (zero in exact arithmetic) and V thirds
+        const float t = warp_colsum32(cs, lane);
+        atomicAdd(a.dbias + (half == 0 ? 2 * D : D) + h * 64 + ch * 32 + lane, t);
       }
     }
   }
@@ -880,8 +920,8 @@ extern "C" int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, 
 }
 
 extern "C" int a8_attn_bwd(const void* qkv, const uint8_t* key_keep, const void* ctx, const void* dctx,
-                           const float* lse, float* delta, void* dqkv, int32_t B, int32_t H, int32_t T, float scale,
-                           float pdrop, uint64_t seed, void* stream_v) {
+                           const float* lse, float* delta, void* dqkv, float* dbias, int32_t B, int32_t H, int32_t T,
+                           float scale, float pdrop, uint64_t seed, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AttnArgs a;
   if (int rc = fill_args(a, key_keep, B, H, T, scale, pdrop, seed)) return rc;
@@ -890,6 +930,7 @@ extern "C" int a8_attn_bwd(const void* qkv, const uint8_t* key_keep, const void*
   a.lse = const_cast<float*>(lse);
   a.delta = delta;
   a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  a.dbias = dbias;
   const long long D = 1ll * H * 64, D3 = 3 * D;
   CUtensorMap mq, md;
   if (int rc = make_tmap_3d(&mq, qkv, D3, T, B, D3, (long long)T * D3, 64, 128, "attention qkv")) return rc;

@@ -629,9 +629,9 @@ class EncoderFn(torch.autograd.Function):
             deferred.append(G.linear_wgrad_grouped(da, L["ctx"].view(M, D), dwo))
             dctx = _empty((B, T, D), BF16, x)
             be.gemm(G.linear_dgrad(da, wo_b, dctx.view(M, D)))
-            dqkv = be.attn_bwd(L["qkv"], L["ctx"], dctx, L["lse"], H, scale, sv["row_keep"], p, seed_a)
+            # (the fused QKV bias gradient dbqkv = column sums of dqkv leaves the attention backward kernels with it)
+            dqkv = be.attn_bwd(L["qkv"], L["ctx"], dctx, L["lse"], H, scale, sv["row_keep"], p, seed_a, dbias=dbqkv)
             dqkv2 = dqkv.view(M, 3 * D)
-            dbqkv = be.colsum(dqkv2, out=dbqkv)
             deferred.append(G.linear_wgrad_grouped(dqkv2, L["xin"], dwqkv))
             dxin = _empty((M, D), BF16, x)
             be.gemm(G.linear_dgrad(dqkv2, wqkv_b, dxin, aux=ds1, aux_mode=AUX_ADD))

@@ -399,14 +399,15 @@ class CudaBackend:
                                         _stream()), "a8_attn_fwd")
         return ctx, lse
 
-    def attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0):
-        """-> dqkv bf16 [B,T,3D] (dQ | dK | dV)"""
+    def attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0, dbias=None):
+        """-> dqkv bf16 [B,T,3D] (dQ | dK | dV); dbias (fp32 [3D], zeroed by the caller) += its column sums"""
         B, T, D3 = qkv.shape
         assert dctx.dtype == torch.bfloat16 and dctx.is_contiguous() and ctx.is_contiguous() and dctx.shape == ctx.shape
+        assert dbias is None or (dbias.dtype == torch.float32 and dbias.is_cuda and dbias.numel() == D3 and dbias.is_contiguous())
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
         _lib.check(self.lib.a8_attn_bwd(_ptr(qkv), _ptr(key_keep), _ptr(ctx), _ptr(dctx), _ptr(lse), _ptr(delta),
-                                        _ptr(dqkv), B, H, T, scale, pdrop, seed, _stream()), "a8_attn_bwd")
+                                        _ptr(dqkv), _ptr(dbias), B, H, T, scale, pdrop, seed, _stream()), "a8_attn_bwd")
         return dqkv
 
     def attn_dropmask(self, B, H, T, pdrop, seed, device):

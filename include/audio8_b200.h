@@ -190,8 +190,9 @@ int a8_layernorm_bwd(const void* dy, const float* dy_f32, float p_y, uint64_t se
 int a8_attn_fwd(const void* qkv, const uint8_t* key_keep, void* ctx, float* lse, int32_t B, int32_t H, int32_t T,
                 float scale, float pdrop, uint64_t seed, void* stream);
 int a8_attn_bwd(const void* qkv, const uint8_t* key_keep, const void* ctx, const void* dctx, const float* lse,
-                float* delta, void* dqkv, int32_t B, int32_t H, int32_t T, float scale, float pdrop, uint64_t seed,
-                void* stream);
+                float* delta, void* dqkv, float* dbias, int32_t B, int32_t H, int32_t T, float scale, float pdrop,
+                uint64_t seed, void* stream); /* dbias: optional fp32 [3D], accumulated into (zeroed by the caller):
+                                                 column sums of dqkv as stored = the gradient of the fused QKV bias */
 int a8_attn_dropmask(uint8_t* keep_out, int32_t B, int32_t H, int32_t T, float pdrop, uint64_t seed, void* stream);
 
 /* out[c] += sum_r x[r][c]  (bias gradients; x bf16 [R, ld], out fp32 zeroed by the caller) */

@@ -212,7 +212,13 @@ class EmuOps(EmuBackend):
         ctx = ((p * m) @ v).transpose(1, 2).reshape(B, T, D3 // 3)
         return _bf(ctx), torch.zeros(B, H, T)
 
-    def attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0, keep=None):
+    def attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0, keep=None, dbias=None):
+        out = self._attn_bwd(qkv, ctx, dctx, lse, H, scale, key_keep, pdrop, seed, keep)
+        if dbias is not None:  # column sums of dqkv as stored
+            dbias += out.float().sum((0, 1))
+        return out
+
+    def _attn_bwd(self, qkv, ctx, dctx, lse, H, scale, key_keep=None, pdrop=0.0, seed=0, keep=None):
         B, T, D3 = qkv.shape
         q, k, v, p = self._attn_probs(qkv, H, scale, key_keep)
         m = self._attn_mask(p.shape, pdrop, seed, keep)

@@ -262,10 +262,15 @@ def test_fused_attention(be, B, H, T, mask, pdrop):
     if mask:
         s = s.masked_fill(keep_keys[:, None, None, :] == 0, float("-inf"))
     _close(lse, torch.logsumexp(s, -1) / math.log(2.0), 1e-3, "attention lse")
-    dqkv = be.attn_bwd(qkv.cuda(), ctx, dctx.cuda(), lse, H, scale, kk, pdrop, seed)
+    dbias = torch.full((3 * D,), 0.25, device="cuda")  # accumulated into: starts non-zero
+    dqkv = be.attn_bwd(qkv.cuda(), ctx, dctx.cuda(), lse, H, scale, kk, pdrop, seed, dbias=dbias)
     ref_d = E.attn_bwd(qkv, ref_ctx, dctx, None, H, scale, keep_keys, pdrop, seed, keep=keep)
     for i, name in enumerate(["dQ", "dK", "dV"]):
         _close(dqkv[..., i * D:(i + 1) * D], ref_d[..., i * D:(i + 1) * D], 3e-2, "attention " + name)
+    # the fused QKV bias gradient: column sums of dqkv exactly as stored (fp32 accumulation order aside)
+    want_b = 0.25 + dqkv.float().sum((0, 1))
+    err = (dbias - want_b).abs().max().item()
+    assert err <= 1e-3 * (want_b.abs().max().item() + 1.0), f"attention dbias: max abs err {err:.4g}"
 
 
 @pytest.mark.parametrize("qscale", [0.3, 1.5, 3.0])
