@@ -113,7 +113,8 @@ struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = (BN / CL) * BLOCK_K * 2;
   static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // powers of two >= 32; 2 accumulator stages
-  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 2 * BN * 4 + EPI_WARPS * STG_BYTES + 1024;
+  // ring | barriers | bias [2][BN] | column-sum partials [2][BN] | epilogue staging | alignment slack
+  static constexpr uint32_t SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 4 * BN * 4 + EPI_WARPS * STG_BYTES + 1024;
 };
 
 // UMMA shared-memory matrix descriptor, 128B swizzle (layout type 2), descriptor version 1.
@@ -234,7 +235,7 @@ __device__ __forceinline__ void aux_commit(uint8_t* stg, const uint4 (&pre)[PIEC
 template <int EK, int CW>
 __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord& tc, const uint32_t* r,
                                                long long row_off0, int row0, int nb, int nb_next, uint4 (&pre)[CW / 8],
-                                               const float* sb, uint8_t* stg, int lane) {
+                                               const float* sb, uint8_t* stg, int lane, float* cs_smem = nullptr) {
   constexpr bool GEN = (EK < 0);
   constexpr int NP = CW / 8;  // 16-byte bf16 pieces per row
   const int c_dtype = GEN ? p.c_dtype : (EK & 3);
@@ -328,16 +329,18 @@ __device__ __forceinline__ void epilogue_chunk(const KParams& p, const TileCoord
       my[g] = o;
     }
     __syncwarp();
-    if ((GEN || aux_mode == AUX_MUL) && p.colsum != nullptr) {
+    if ((GEN || aux_mode == AUX_MUL) && cs_smem != nullptr) {
       // bias gradient of the producing layer, from the staged tile: lane l sums column l over the warp's 32 rows (rows of
       // the staging buffer are 80 B apart: a column's 32 reads touch 16 banks twice through the same words, no conflict)
+      // and adds it to the CTA's per-tile partials in shared memory (cs_smem = this chunk's slice; the tile's total
+      // goes to global memory once: per-warp global reductions on the same 12 KB serialised in the L2 atomic units)
       float cs = 0.f;
       if (lane < CW) {
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr)
           if (rr < rows_valid)
             cs += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(stg + rr * STG_PITCH + lane * 2)) << 16);
-        if (nb + lane < tc.N) atomicAdd(p.colsum + nb + lane, cs);
+        atomicAdd(cs_smem + lane, cs);
       }
     }
     stage_copy<2, STG_STORE, NP>(stg, cptr, row_off0, ldc, nb, rows_valid, cols_valid, lane);
@@ -455,7 +458,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
   auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256u - raw_u32));  // [2 accumulator stages][BN]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + 2 * BN);                // [EPI_WARPS][32 rows][80 B]
+  float* s_cs = s_bias + 2 * BN;                                                 // [2 tile parities][BN] column-sum partials
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_cs + 2 * BN);                  // [EPI_WARPS][32 rows][80 B]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
@@ -650,6 +654,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
     const int tid_e = threadIdx.x - 128;
     int iter = 0;
     int gcur = 0;
+    // fused column sums (a8_gemm_t::colsum): compiled into the epilogues that can carry them only
+    constexpr bool CS_KIND = !GROUP && ((EK < 0) || (((EK >> 5) & 3) == AUX_MUL));
+    const bool do_cs = CS_KIND && p.colsum != nullptr;
+    if (do_cs) {
+      for (int i = tid_e; i < 2 * BN; i += 32 * EPI_WARPS) s_cs[i] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    }
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++iter) {
       const TileCoord t = GROUP ? decode_tile_group<CL>(p, probs, tile, rank, gcur) : decode_tile<CL>(p, tile, rank);
       const int as = iter & 1;
@@ -687,7 +698,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
         tmem_ld_wait();
         const int nb_next = (c + 1 < NCH && nb0 + (c + 1) * EPI_CW < t.N) ? nb0 + (c + 1) * EPI_CW : -1;
         epilogue_chunk<EK, EPI_CW>(p, t, ra, row_off0, row0, nb0 + c * EPI_CW, nb_next, aux_pre,
-                                   sbw ? sbw + c * EPI_CW : nullptr, stg, lane);
+                                   sbw ? sbw + c * EPI_CW : nullptr, stg, lane,
+                                   do_cs ? s_cs + as * BN + half * COLS + c * EPI_CW : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -695,6 +707,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* __restrict__ map
       if (lane == 0) {
         if (CL == 1) mbar_arrive_relaxed(tempty_bar(as));
         else mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));  // the leader's MMA thread waits for both CTAs
+      }
+      if (do_cs) {
+        // the tile's column totals leave the CTA once all epilogue warps have added theirs; the buffer of this parity is
+        // reused two tiles later, after the next tile's barrier
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        for (int i = tid_e; i < BN; i += 32 * EPI_WARPS) {
+          const float v = s_cs[as * BN + i];
+          s_cs[as * BN + i] = 0.f;
+          if (t.nt * BN + i < t.N) atomicAdd(p.colsum + t.nt * BN + i, v);
+        }
       }
     }
   }

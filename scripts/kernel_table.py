@@ -96,6 +96,12 @@ vars2d = torch.rand(Gq * V, vd, device=dev)
 q, qb, kidx, avg, ppl = be.vq_fwd(z, noise, 0.5, vars2d, Gq)
 bench("vq_fwd (gumbel argmax, ppl, codeword gather)", lambda: be.vq_fwd(z, noise, 0.5, vars2d, Gq),
       bytes_=R * Gq * V * 4 * 2 + R * Gq * vd * 6 + Gq * V * vd * 4)
+# device-side draws of the step (csrc/draws.cu): span mask of (6, 749) and its 100 negatives per masked step
+R_max_d = B * 490
+rows_d, _ = be.span_mask_draw(1, None, B, T, 0.65, 10, R_max_d, dev)
+bench("span_mask_draw (B=6, T=749: one CTA, Floyd subsets)", lambda: be.span_mask_draw(1, None, B, T, 0.65, 10, R_max_d, dev),
+      bytes_=B * T + 4 * R_max_d, note="latency-bound (serial subset draws of one CTA)")
+bench("negatives_draw (2940 x 100 indices)", lambda: be.negatives_draw(2, None, rows_d, B, 100), bytes_=R_max_d * 100 * 4)
 xc, yc = torch.randn(R, 256, device=dev), torch.randn(R, 256, device=dev)
 idx = torch.randint(0, R, (R * K,), device=dev, dtype=torch.int32)
 loss, ce, saved = be.contrastive_fwd(xc, yc, idx, ppl, 640.0, 0.1, 10.0)
@@ -139,12 +145,14 @@ qkv = r(B, T, 3 * D)
 dctx = r(B, T, D)
 ctx, lse = be.attn_fwd(qkv, H, 0.125, None, 0.1, 7)
 bench("fused attention fwd (dropout 0.1)", lambda: be.attn_fwd(qkv, H, 0.125, None, 0.1, 7), flops=4 * B * H * T * T * 64)
-bench("fused attention bwd (dq + dkv kernels)", lambda: be.attn_bwd(qkv, ctx, dctx, lse, H, 0.125, None, 0.1, 7), flops=8 * B * H * T * T * 64)
+dbq = torch.zeros(3 * D, device=dev)
+bench("fused attention bwd (dq + dkv kernels, + QKV bias gradient)", lambda: be.attn_bwd(qkv, ctx, dctx, lse, H, 0.125, None, 0.1, 7, dbias=dbq), flops=8 * B * H * T * T * 64)
 gemms = {
     "gemm qkv_fwd 4494x2304x768": lambda: G.linear_fwd(r(M, D), r(3 * D, D), torch.empty(M, 3 * D, device=dev, dtype=bf), r(3 * D, dtype=torch.float32)),
     "gemm ffn1_fwd+gelu 4494x3072x768": lambda: G.linear_fwd(r(M, D), r(F_, D), torch.empty(M, F_, device=dev, dtype=bf), r(F_, dtype=torch.float32), act=ACT_GELU_DZ, z_out=torch.empty(M, F_, device=dev, dtype=bf)),
     "gemm ffn2_fwd 4494x768x3072": lambda: G.linear_fwd(r(M, F_), r(D, F_), torch.empty(M, D, device=dev, dtype=bf), r(D, dtype=torch.float32)),
     "gemm ffn2_dgrad*gelu' 4494x3072x768": lambda: G.linear_dgrad(r(M, D), r(D, F_), torch.empty(M, F_, device=dev, dtype=bf), aux=r(M, F_).to(torch.float16), aux_mode=AUX_MUL),
+    "gemm ffn2_dgrad*gelu' + ffn1 bias gradient (colsum epilogue)": lambda: G.linear_dgrad(r(M, D), r(D, F_), torch.empty(M, F_, device=dev, dtype=bf), aux=r(M, F_).to(torch.float16), aux_mode=AUX_MUL, colsum=torch.zeros(F_, device=dev)),
     "gemm ffn_wgrad 3072x768x4494": lambda: G.linear_wgrad(r(M, F_), r(M, D), torch.zeros(F_, D, device=dev)),
     "gemm conv1_fwd (implicit, k=3 s=2)": lambda: G.conv_fwd(r(B, 47999, 512), r(512, 1536), torch.empty(B, 23999, 512, device=dev, dtype=bf), 3, 2, z_out=torch.empty(B, 23999, 512, device=dev, dtype=bf)),
     "gemm conv1_wgrad": lambda: G.conv_wgrad(r(B, 23999, 512), r(B, 47999, 512), torch.zeros(512, 1536, device=dev), 3, 2),
