@@ -216,6 +216,27 @@ def _arena_worker(rank, world, port, out_dir):
             err = (p_.grad - 2 * want[k]).abs().max().item()
             scale = want[k].abs().max().item() + 1e-8
             assert err <= 2e-4 * scale + 1e-7, f"accumulated grad {k}: {err:.3g} vs scale {scale:.3g}"
+        # device-side draws under the wrapper: the span mask / negatives a rank draws follow its torch seed and
+        # the call-site counter, so the local runs reproduce them; expected = mean over ranks as above
+        from audio8_b200 import functional as Fn
+        W.set_device_draws(True)
+        try:
+            want = None
+            for r in range(world):
+                Fn._site[0] = 99
+                _, g = _local_grads(model, loss_fn, xs[r], 7 + r)
+                want = g if want is None else {k: want[k] + g[k] for k in g}
+            want = {k: v / world for k, v in want.items()}
+            Fn._site[0] = 99
+            _, got = _local_grads(net, loss_fn, xs[rank], 7 + rank)
+            got = {k.replace("module.", "", 1): v for k, v in got.items()}
+            assert set(got) == set(want)
+            for k in want:
+                err = (got[k] - want[k]).abs().max().item()
+                scale = want[k].abs().max().item() + 1e-8
+                assert err <= 1e-4 * scale + 1e-7, f"device draws, rank {rank} grad {k}: {err:.3g} vs scale {scale:.3g}"
+        finally:
+            W.set_device_draws(False)
         _layerdrop_body(rank, world, torch.device("cpu"), False)  # LayerDrop under the wrapper (defined below)
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
