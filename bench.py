@@ -54,6 +54,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []  # (sm_mhz, max_mhz, set(reasons))
+        self.power = []    # (watts drawn, enforced limit) per sample
         self.how = None
         self.h = None
 
@@ -81,10 +82,22 @@ class ClockSampler:
             N = self.N
             names = [("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
                      ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap)]
+            # every other bit NVML may raise is reported under its own name too: a clock below the maximum should come
+            # with its reason (power draw against the enforced limit is sampled for the same purpose)
+            for attr, nm in (("nvmlClocksEventReasonHwPowerBrakeSlowdown", "hw_power_brake_slowdown"),
+                             ("nvmlClocksEventReasonApplicationsClocksSetting", "applications_clocks_setting"),
+                             ("nvmlClocksEventReasonSyncBoost", "sync_boost"),
+                             ("nvmlClocksEventReasonDisplayClockSetting", "display_clock_setting")):
+                if hasattr(N, attr):
+                    names.append((nm, getattr(N, attr)))
             try:
                 sm = float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
                 bits = int(N.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 self.samples.append((sm, self.mx, {n for n, b in names if bits & b}))
+                try:
+                    self.power.append((N.nvmlDeviceGetPowerUsage(self.h) / 1e3, N.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1e3))
+                except Exception:
+                    pass
             except Exception:
                 pass
         elif self.how == "nvidia-smi":
@@ -118,6 +131,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.samples[0][1] if self.samples else None,
                 "samples": len(self.samples), "samples_while_gpu_busy": getattr(self, "in_region", 0),
                 "reasons": sorted(reasons), "source": self.how,
+                "power_w": float(np.median([p[0] for p in self.power])) if self.power else None,
+                "power_limit_w": self.power[0][1] if self.power else None,
                 "when": "after the last timed step was enqueued, while the GPU was still executing the timed region"}
 
 
