@@ -132,24 +132,9 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float cdf = 0.5f + copysignf(half_erf, x);
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
-// gelu(x) and gelu'(x) together: Phi(x) is shared and the exponential of erf (7.1.26) IS the one of phi(x)
-// (the 1/sqrt(2) of u = |x|/sqrt(2) is folded into the rational's slope and the 1/2 of erf/2 into the polynomial: this
-// runs 32 times per lane per epilogue chunk of the GELU GEMMs, where the FP32 pipe is what the epilogue waits for)
-__device__ __forceinline__ float gelu_both_fast(float x, float& dgelu) {
-  const float t = rcp_approx(fmaf(0.23164188826636045f, fabsf(x), 1.f));  // 0.3275911 / sqrt(2)
-  float p = fmaf(0.5307027145f, t, -0.7265760135f);
-  p = fmaf(p, t, 0.7107068705f);
-  p = fmaf(p, t, -0.142248368f);
-  p = fmaf(p, t, 0.127414796f);
-  const float e = ex2_approx(-0.72134752044448170f * x * x);  // exp(-x^2/2)
-  const float half_erf = fmaf(-(p * t), e, 0.5f);
-  const float cdf = 0.5f + copysignf(half_erf, x);
-  dgelu = fmaf(x * 0.3989422804014327f, e, cdf);
-  return x * cdf;
-}
-// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 do two lanes' worth of FP32 work per issue slot).  A pair lives in
-// a 64-bit register; ptxas keeps it in two adjacent 32-bit registers, so packing values that are produced next to each
-// other costs nothing, and broadcast constants become immediates.
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 carry two values per instruction: half the issue slots, the same
+// FP32 throughput).  A pair lives in a 64-bit register; ptxas keeps it in two adjacent 32-bit registers, so packing
+// values that are produced next to each other costs nothing, and broadcast constants become immediates.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
   f32x2 r;

@@ -1,10 +1,11 @@
 // audio8_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
 //
-// Roles inside one 256-thread CTA (one CTA per SM, persistent over output tiles):
+// Roles inside one 384-thread CTA (one CTA per SM, persistent over output tiles):
 //   warp 0 (one elected lane)  TMA producer: cp.async.bulk.tensor.4d -> 128B-swizzled smem ring
 //   warp 1 (one elected lane)  MMA issuer:   tcgen05.mma (M=128, N=BN, K=16) -> TMEM accumulators
 //   warp 2                     TMEM allocator / deallocator
-//   warps 4..7                 epilogue: tcgen05.ld -> registers -> bias/GELU/residual -> HBM
+//   warps 4..11                epilogue: tcgen05.ld -> registers -> bias / GELU (+ derivative) / residual or multiply
+//                              (packed fp32 pairs) -> staged coalesced stores (+ fused column sums) -> HBM
 // Pipelines: smem full/empty mbarrier ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (MMA <-> epilogue), so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
